@@ -1,0 +1,192 @@
+/* b200boot.h — C ABI of libb200boot.so: the sm_100a implementation of the
+ * scikits.bootstrap resampling hot path.
+ *
+ * The reference (cgevans/scikits-bootstrap) is pure Python and has no FFI; the
+ * boundary a maintainer would bind is therefore the set of numpy call sites
+ * inside `src/scikits/bootstrap/bootstrap.py` that this library replaces.  Each
+ * entry point below cites the reference lines it stands in for (bootstrap.py:L).
+ *
+ * Conventions
+ *  - Plain C: pointers and sizes only.  All data pointers are DEVICE pointers
+ *    unless the parameter is documented as host memory; `stream` is a
+ *    cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - Every call returns 0 on success or a negative b200boot_status; the message
+ *    of the last failure on the calling thread is b200boot_last_error().
+ *    Nothing throws across the ABI.
+ *  - The library never allocates caller-visible memory: scratch comes from the
+ *    caller-provided workspace (`ws`, `ws_bytes`; 256-byte aligned), sized by
+ *    b200boot_workspace_bytes().  No pointer is retained after the stream work
+ *    completes.  Calls only enqueue work on `stream` (no host synchronisation)
+ *    unless stated otherwise.
+ *  - Statistic vectors are column-major: `stat[d * n_local + r]` is the value of
+ *    output column d for local resample r.
+ */
+#ifndef B200BOOT_H
+#define B200BOOT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200BOOT_ABI_VERSION 1
+
+typedef enum b200boot_status {
+  B200BOOT_OK = 0,
+  B200BOOT_EINVAL = -1,       /* bad argument */
+  B200BOOT_ECUDA = -2,        /* CUDA runtime error (see last_error) */
+  B200BOOT_EWORKSPACE = -3,   /* workspace too small or misaligned */
+  B200BOOT_EUNSUPPORTED = -4  /* statistic / shape not in the device registry */
+} b200boot_status;
+
+/* Device statistic registry (replaces the user callable at bootstrap.py:431).
+ * Moment statistics are finished from per-resample sums; N is the resample size. */
+typedef enum b200boot_stat {
+  B200BOOT_STAT_MEAN = 0,             /* np.mean / np.average, 1 array            */
+  B200BOOT_STAT_VAR = 1,              /* np.var (ddof=0), 1 array                 */
+  B200BOOT_STAT_STD = 2,              /* np.std (ddof=0), 1 array                 */
+  B200BOOT_STAT_RATIO_OF_MEANS = 3,   /* mean(a)/mean(b), 2 paired arrays         */
+  B200BOOT_STAT_WEIGHTED_AVERAGE = 4, /* sum(x*w)/sum(w), 2 paired arrays (x, w)  */
+  B200BOOT_STAT_PEARSON_R = 5,        /* corrcoef(a,b)[0,1], 2 paired arrays      */
+  B200BOOT_STAT_MEDIAN = 6,           /* np.median, per column                    */
+  B200BOOT_STAT_SUM = 7               /* np.sum, 1 array                          */
+} b200boot_stat;
+
+/* Comparison operators for b200boot_count (bootstrap.py:583 uses LT; pval's
+ * default compfunction, bootstrap.py:793, is GT against 0). */
+typedef enum b200boot_cmp {
+  B200BOOT_CMP_LT = 0,
+  B200BOOT_CMP_LE = 1,
+  B200BOOT_CMP_GT = 2,
+  B200BOOT_CMP_GE = 3,
+  B200BOOT_CMP_BETWEEN = 4 /* t0 <= s <= t1 */
+} b200boot_cmp;
+
+/* How a data set of N rows is cut into shared-memory cells (tiles). */
+typedef struct b200boot_plan {
+  int32_t log2_tile; /* full tiles hold 2^log2_tile rows                        */
+  int32_t n_arrays;
+  int64_t n_full;    /* number of full power-of-two tiles (0 => single cell)   */
+  int64_t rem;       /* rows in the trailing remainder cell (may be 0)         */
+  int64_t n_tiles;   /* n_full + (rem > 0)                                     */
+} b200boot_plan;
+
+int b200boot_version(void);
+const char* b200boot_last_error(void);
+
+/* Tile plan for N rows of `n_arrays` paired float64 arrays. */
+int b200boot_make_plan(int64_t n_rows, int n_arrays, b200boot_plan* out);
+
+/* Upper bound on workspace bytes for any call below with these shapes. */
+size_t b200boot_workspace_bytes(int stat_id, int64_t n_rows, int n_arrays, int64_t n_cols,
+                                int64_t n_local, int n_alphas);
+
+/* K1 — fused draw + gather + FP64 reduce.  Replaces the resample loop
+ * bootstrap.py:429-432 together with the index generator bootstrap.py:677-680.
+ * `data` is a HOST array of n_arrays device pointers to contiguous float64[N].
+ * Resample ids [resample_lo, resample_hi) are this caller's shard; the value of
+ * resample r depends only on (seed, r), never on the shard boundaries.
+ * stat_out: float64[resample_hi - resample_lo]. */
+int b200boot_resample_stat(const double* const* data, int n_arrays, int64_t n_rows, int stat_id,
+                           uint64_t seed, int64_t resample_lo, int64_t resample_hi,
+                           double* stat_out, void* ws, size_t ws_bytes, void* stream);
+
+/* K1i — parity mode: the caller supplies the index arrays (e.g. the reference's
+ * own PCG64 draws).  Replaces bootstrap.py:431 only.  indices: int64[n_sets][N]
+ * row-major, values in [0, N).  stat_out: float64[n_sets]. */
+int b200boot_resample_stat_indexed(const double* const* data, int n_arrays, int64_t n_rows,
+                                   int stat_id, const int64_t* indices, int64_t n_sets,
+                                   double* stat_out, void* ws, size_t ws_bytes, void* stream);
+
+/* K1m — column-batched order statistic: data float64[N][n_cols] row-major
+ * (ld = row stride in elements); every column shares one index set per
+ * resample, as x[indices] does for 2-D data at bootstrap.py:431.
+ * stat_out: float64[n_cols][n_local] (column-major as everywhere). */
+int b200boot_resample_median_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld,
+                                     uint64_t seed, int64_t resample_lo, int64_t resample_hi,
+                                     double* stat_out, void* ws, size_t ws_bytes, void* stream);
+
+/* K2 — materialises exactly the indices K1 draws; backs the Python
+ * `bootstrap_indices` iterator (bootstrap.py:667-680).
+ * out: int64[resample_hi - resample_lo][N] row-major.  `n_arrays` selects the
+ * same tile plan K1 uses for that many paired arrays. */
+int b200boot_fill_indices(uint64_t seed, int64_t n_rows, int n_arrays, int64_t resample_lo,
+                          int64_t resample_hi, int64_t* out, void* ws, size_t ws_bytes,
+                          void* stream);
+
+/* Tile occupancies of the multinomial chain (K0), for inspection and tests:
+ * counts int32[n_tiles][n_local].  Only meaningful when the plan has > 1 tile. */
+int b200boot_tile_counts(uint64_t seed, int64_t n_rows, int n_arrays, int64_t resample_lo,
+                         int64_t resample_hi, int32_t* counts, void* stream);
+
+/* Plain gather out[i] = data[idx[i]] (bit-exactness probe for bootstrap.py:431). */
+int b200boot_gather(const double* data, int64_t n_rows, const int64_t* idx, int64_t n_idx,
+                    double* out, void* stream);
+
+/* K3 — closed-form leave-one-out pass.  Replaces the O(N^2) loop
+ * bootstrap.py:595-599 and the moments at bootstrap.py:609-615.
+ * out (device) float64[8]: [0] statistic on the full data (bootstrap.py:580),
+ * [1] mean of the jackknife statistics, [2] sum d^2, [3] sum d^3,
+ * [4] acceleration a = [3] / (6 * [2]^1.5); d = jmean - jstat_i. */
+int b200boot_jackknife(const double* const* data, int n_arrays, int64_t n_rows, int stat_id,
+                       double* out, void* ws, size_t ws_bytes, void* stream);
+
+/* Column-batched K3 for the median: out float64[n_cols][8]. */
+int b200boot_jackknife_median_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld,
+                                      double* out, void* ws, size_t ws_bytes, void* stream);
+
+/* K4 — count reduction per column: counts[d] = #{ r : stat[d][r] cmp t0[d] (,t1[d]) }.
+ * Replaces np.sum(stat < ostat, axis=0) at bootstrap.py:583 and the pval mean
+ * at bootstrap.py:861-866.  counts: int64[n_cols], overwritten. */
+int b200boot_count(const double* stat, int64_t n_local, int64_t n_cols, int cmp_op,
+                   const double* t0, const double* t1, int64_t* counts, void* stream);
+
+/* K5 — exact k-th order statistics without sorting; replaces stat.sort(axis=0)
+ * (bootstrap.py:445) + the picks at bootstrap.py:485-490.  NaNs order last.
+ * ranks: int64[n_alphas][n_cols] GLOBAL 0-based ranks; out: float64[n_alphas][n_cols].
+ * The select is an 8-pass MSB radix descent.  Single-GPU callers use
+ * b200boot_select; sharded callers run begin / (hist, all-reduce hist, pick) x 8 / end,
+ * all-reducing the int64 histogram buffer returned by b200boot_select_hist_buffer
+ * between hist and pick. */
+int b200boot_select(const double* stat, int64_t n_local, int64_t n_cols, const int64_t* ranks,
+                    int n_alphas, double* out, void* ws, size_t ws_bytes, void* stream);
+int b200boot_select_begin(const int64_t* ranks, int n_alphas, int64_t n_cols, void* ws,
+                          size_t ws_bytes, void* stream);
+int b200boot_select_hist(const double* stat, int64_t n_local, int64_t n_cols, int n_alphas,
+                         int pass, void* ws, size_t ws_bytes, void* stream);
+int b200boot_select_pick(int n_alphas, int64_t n_cols, int pass, void* ws, size_t ws_bytes,
+                         void* stream);
+int b200boot_select_end(int n_alphas, int64_t n_cols, double* out, void* ws, size_t ws_bytes,
+                        void* stream);
+/* Device pointer + element count of the histogram buffer inside `ws`. */
+int b200boot_select_hist_buffer(int n_alphas, int64_t n_cols, void* ws, size_t ws_bytes,
+                                int64_t** hist, int64_t* n_elems);
+
+/* Ascending in-place sort of every column (NaNs last); only for return_dist=True
+ * (bootstrap.py:445, 501-504).  stat: float64[n_cols][n]. */
+int b200boot_sort_columns(double* stat, int64_t n, int64_t n_cols, void* ws, size_t ws_bytes,
+                          void* stream);
+
+/* Instrumentation for bench.py: cumulative number of kernels this library has
+ * launched (host counter), and optional CUDA-event timing of the K1 launch on the
+ * caller's stream.  b200boot_profile_last_k1_ms synchronises on the stop event. */
+int64_t b200boot_launch_count(void);
+int b200boot_profile_enable(int on);
+int b200boot_profile_last_k1_ms(float* ms);
+
+/* Host-side probes built from the same __host__ __device__ sources as the
+ * kernels (no GPU needed); used by the CPU test-suite only. */
+void b200boot_host_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+int64_t b200boot_host_binomial(uint64_t seed, int64_t resample, int64_t cell, int64_t n,
+                               double p);
+int b200boot_host_tile_counts(uint64_t seed, int64_t n_rows, int n_arrays, int64_t resample,
+                              int32_t* counts /* [n_tiles] */);
+int b200boot_host_indices(uint64_t seed, int64_t n_rows, int n_arrays, int64_t resample,
+                          int64_t* out /* [n_rows] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200BOOT_H */

@@ -487,22 +487,27 @@ def cell_draws_lemire(seed: int, resample: int, cell: int, n_draws: int, size: i
     return idx
 
 
-def tile_plan(n_obs: int, log2_tile: int):
-    """(tile_size list) : full power-of-two tiles followed by one remainder tile."""
+SMEM_DATA_BYTES = 224 * 1024     # csrc/draw.cuh: kSmemDataBytes
+
+
+def tile_plan(n_obs: int, log2_tile: int, n_arrays: int = 1):
+    """Cell sizes (csrc/draw.cuh: make_plan): one cell when all rows fit in shared
+    memory, else full power-of-two tiles followed by one remainder cell."""
+    if n_obs <= SMEM_DATA_BYTES // (8 * n_arrays):
+        return [n_obs]
     m = 1 << log2_tile
     full = n_obs // m
     rem = n_obs - full * m
-    if full == 0:
-        return [n_obs]
     return [m] * full + ([rem] if rem else [])
 
 
 def device_indices(seed: int, resample: int, n_obs: int, log2_tile: int,
-                   counts: Sequence[int] | None = None, cell_base: int = 0) -> np.ndarray:
+                   counts: Sequence[int] | None = None, cell_base: int = 0,
+                   n_arrays: int = 1) -> np.ndarray:
     """The canonical index array of resample `resample`: tiles in order, within a
     tile the draws in position order.  `counts` are the tile occupancies (from
     the device multinomial chain); with a single tile the count is n_obs."""
-    sizes = tile_plan(n_obs, log2_tile)
+    sizes = tile_plan(n_obs, log2_tile, n_arrays)
     if len(sizes) == 1:
         return cell_draws_lemire(seed, resample, cell_base, n_obs, n_obs)
     assert counts is not None and len(counts) == len(sizes) and sum(counts) == n_obs

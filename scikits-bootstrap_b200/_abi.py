@@ -1,0 +1,99 @@
+"""ctypes binding of libb200boot.so (C ABI declared in include/b200boot.h).
+
+There is no CPU fallback: if the library is missing or fails to load, every
+entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libb200boot.so")
+
+ABI_VERSION = 1
+
+STAT_MEAN, STAT_VAR, STAT_STD, STAT_RATIO_OF_MEANS, STAT_WEIGHTED_AVERAGE, STAT_PEARSON_R, \
+    STAT_MEDIAN, STAT_SUM = range(8)
+CMP_LT, CMP_LE, CMP_GT, CMP_GE, CMP_BETWEEN = range(5)
+
+
+class Plan(C.Structure):
+    _fields_ = [("log2_tile", C.c_int32), ("n_arrays", C.c_int32), ("n_full", C.c_int64),
+                ("rem", C.c_int64), ("n_tiles", C.c_int64)]
+
+
+class B200BootError(RuntimeError):
+    """A libb200boot call returned a non-zero status."""
+
+
+_vp, _i64, _u64, _int, _sz = C.c_void_p, C.c_int64, C.c_uint64, C.c_int, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/b200boot.h one to one
+SIGNATURES = {
+    "b200boot_version": (_int, []),
+    "b200boot_last_error": (C.c_char_p, []),
+    "b200boot_make_plan": (_int, [_i64, _int, C.POINTER(Plan)]),
+    "b200boot_workspace_bytes": (_sz, [_int, _i64, _int, _i64, _i64, _int]),
+    "b200boot_resample_stat": (_int, [_vp, _int, _i64, _int, _u64, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "b200boot_resample_stat_indexed": (_int, [_vp, _int, _i64, _int, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "b200boot_resample_median_columns": (_int, [_vp, _i64, _i64, _i64, _u64, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "b200boot_fill_indices": (_int, [_u64, _i64, _int, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "b200boot_tile_counts": (_int, [_u64, _i64, _int, _i64, _i64, _vp, _vp]),
+    "b200boot_gather": (_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    "b200boot_jackknife": (_int, [_vp, _int, _i64, _int, _vp, _vp, _sz, _vp]),
+    "b200boot_jackknife_median_columns": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "b200boot_count": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _vp]),
+    "b200boot_select": (_int, [_vp, _i64, _i64, _vp, _int, _vp, _vp, _sz, _vp]),
+    "b200boot_select_begin": (_int, [_vp, _int, _i64, _vp, _sz, _vp]),
+    "b200boot_select_hist": (_int, [_vp, _i64, _i64, _int, _int, _vp, _sz, _vp]),
+    "b200boot_select_pick": (_int, [_int, _i64, _int, _vp, _sz, _vp]),
+    "b200boot_select_end": (_int, [_int, _i64, _vp, _vp, _sz, _vp]),
+    "b200boot_select_hist_buffer": (_int, [_int, _i64, _vp, _sz, C.POINTER(_vp), C.POINTER(_i64)]),
+    "b200boot_sort_columns": (_int, [_vp, _i64, _i64, _vp, _sz, _vp]),
+    "b200boot_launch_count": (_i64, []),
+    "b200boot_profile_enable": (_int, [_int]),
+    "b200boot_profile_last_k1_ms": (_int, [C.POINTER(C.c_float)]),
+    "b200boot_host_philox4x32": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "b200boot_host_binomial": (_i64, [_u64, _i64, _i64, _i64, C.c_double]),
+    "b200boot_host_tile_counts": (_int, [_u64, _i64, _int, _i64, _vp]),
+    "b200boot_host_indices": (_int, [_u64, _i64, _int, _i64, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib() -> C.CDLL:
+    """Loads (once) and returns the library; raises if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise B200BootError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (nvcc, sm_100a).  There is no CPU fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)   # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        if handle.b200boot_version() != ABI_VERSION:
+            raise B200BootError("libb200boot.so ABI version mismatch; rebuild")
+        _lib = handle
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        msg = lib().b200boot_last_error()
+        raise B200BootError(f"libb200boot status {status}: {msg.decode() if msg else ''}")
+
+
+def make_plan(n_rows: int, n_arrays: int) -> Plan:
+    p = Plan()
+    check(lib().b200boot_make_plan(n_rows, n_arrays, C.byref(p)))
+    return p

@@ -1,0 +1,251 @@
+"""Device plumbing: tensors, streams and workspaces around the C ABI.
+
+PyTorch is used for device memory, the current stream and (in _dist.py)
+torch.distributed only; every computation is a libb200boot kernel."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _abi
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def require_cuda():
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise _abi.B200BootError(
+            "no CUDA device: scikits-bootstrap_b200 runs its resampling path on a B200 only "
+            "(there is no CPU fallback)")
+    return torch
+
+
+# bytes moved between host and device by the package (bench.py reads these)
+TRAFFIC = {"h2d": 0, "d2h": 0}
+
+
+def to_host(t) -> np.ndarray:
+    """Device tensor -> numpy array (synchronises), counted as D2H traffic."""
+    TRAFFIC["d2h"] += t.numel() * t.element_size()
+    return t.cpu().numpy()
+
+
+def host_to_device(arr: np.ndarray, device):
+    """Small host array -> device tensor, counted as H2D traffic."""
+    torch = _torch()
+    t = torch.as_tensor(np.ascontiguousarray(arr))
+    TRAFFIC["h2d"] += t.numel() * t.element_size()
+    return t.to(device)
+
+
+def to_device_f64(x, device=None):
+    """array-like / torch tensor -> contiguous float64 CUDA tensor.  float64 CUDA
+    tensors are used in place (no copy)."""
+    torch = require_cuda()
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        arr = np.array(x)            # the reference copies too (bootstrap.py:371, 379)
+        if arr.dtype == object:
+            raise TypeError("data must be numeric")
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if t.device.type != "cuda":
+        if t.dtype != torch.float64:
+            t = t.to(torch.float64)
+        TRAFFIC["h2d"] += t.numel() * 8
+        t = t.to(dev, non_blocking=t.is_pinned())
+    elif t.dtype != torch.float64:
+        t = t.to(torch.float64)
+    return t.contiguous()
+
+
+def stream_ptr() -> int:
+    return _torch().cuda.current_stream().cuda_stream
+
+
+class Workspace:
+    """Grow-only uint8 scratch tensor handed to the library."""
+
+    def __init__(self):
+        self._buf = None
+
+    def get(self, nbytes: int):
+        torch = _torch()
+        nbytes = max(int(nbytes), 256)
+        if self._buf is None or self._buf.numel() < nbytes or self._buf.device.index != torch.cuda.current_device():
+            self._buf = None
+            self._buf = torch.empty(nbytes + 256, dtype=torch.uint8, device="cuda")
+        ptr = self._buf.data_ptr()
+        off = (-ptr) % 256
+        return ptr + off, self._buf.numel() - off
+
+
+_ws = Workspace()
+
+
+def _ptr_array(tensors: Sequence) -> C.Array:
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def workspace_for(stat_id: int, n_rows: int, n_arrays: int, n_cols: int, n_local: int, n_alphas: int):
+    need = _abi.lib().b200boot_workspace_bytes(stat_id, n_rows, n_arrays, n_cols, n_local, n_alphas)
+    return _ws.get(need)
+
+
+def resample_stat(arrays: Sequence, stat_id: int, seed: int, lo: int, hi: int, out=None):
+    """K1 on contiguous float64[N] CUDA tensors -> float64[hi-lo] CUDA tensor."""
+    torch = _torch()
+    n_rows = arrays[0].numel()
+    n_local = hi - lo
+    if out is None:
+        out = torch.empty(n_local, dtype=torch.float64, device=arrays[0].device)
+    ws, wsz = workspace_for(stat_id, n_rows, len(arrays), 1, n_local, 1)
+    ptrs = _ptr_array(arrays)
+    _abi.check(_abi.lib().b200boot_resample_stat(ptrs, len(arrays), n_rows, stat_id, seed, lo, hi,
+                                                 out.data_ptr(), ws, wsz, stream_ptr()))
+    return out
+
+
+def resample_stat_indexed(arrays: Sequence, stat_id: int, indices):
+    """K1i: indices int64[n_sets][N] CUDA tensor -> float64[n_sets]."""
+    torch = _torch()
+    n_rows = arrays[0].numel()
+    n_sets = indices.shape[0]
+    out = torch.empty(n_sets, dtype=torch.float64, device=arrays[0].device)
+    ws, wsz = workspace_for(stat_id, n_rows, len(arrays), 1, n_sets, 1)
+    _abi.check(_abi.lib().b200boot_resample_stat_indexed(_ptr_array(arrays), len(arrays), n_rows, stat_id,
+                                                         indices.data_ptr(), n_sets, out.data_ptr(), ws, wsz,
+                                                         stream_ptr()))
+    return out
+
+
+def resample_median_columns(data2d, seed: int, lo: int, hi: int):
+    """K1m: data float64[N][D] -> float64[D][hi-lo]."""
+    torch = _torch()
+    n_rows, n_cols = data2d.shape
+    out = torch.empty((n_cols, hi - lo), dtype=torch.float64, device=data2d.device)
+    ws, wsz = workspace_for(_abi.STAT_MEDIAN, n_rows, 1, n_cols, hi - lo, 1)
+    _abi.check(_abi.lib().b200boot_resample_median_columns(data2d.data_ptr(), n_rows, n_cols, data2d.stride(0),
+                                                           seed, lo, hi, out.data_ptr(), ws, wsz, stream_ptr()))
+    return out
+
+
+def fill_indices(seed: int, n_rows: int, n_arrays: int, lo: int, hi: int):
+    """K2 -> int64[hi-lo][N] CUDA tensor."""
+    torch = require_cuda()
+    out = torch.empty((hi - lo, n_rows), dtype=torch.int64, device="cuda")
+    plan = _abi.make_plan(n_rows, n_arrays)
+    ws, wsz = _ws.get(plan.n_tiles * (hi - lo) * 4 + 1024)
+    _abi.check(_abi.lib().b200boot_fill_indices(seed, n_rows, n_arrays, lo, hi, out.data_ptr(), ws, wsz,
+                                                stream_ptr()))
+    return out
+
+
+def tile_counts(seed: int, n_rows: int, n_arrays: int, lo: int, hi: int):
+    torch = require_cuda()
+    plan = _abi.make_plan(n_rows, n_arrays)
+    out = torch.empty((plan.n_tiles, hi - lo), dtype=torch.int32, device="cuda")
+    _abi.check(_abi.lib().b200boot_tile_counts(seed, n_rows, n_arrays, lo, hi, out.data_ptr(), stream_ptr()))
+    return out
+
+
+def gather(data, idx):
+    torch = _torch()
+    out = torch.empty(idx.numel(), dtype=torch.float64, device=data.device)
+    _abi.check(_abi.lib().b200boot_gather(data.data_ptr(), data.numel(), idx.data_ptr(), idx.numel(),
+                                          out.data_ptr(), stream_ptr()))
+    return out
+
+
+def jackknife(arrays: Sequence, stat_id: int):
+    """K3 -> float64[8] CUDA tensor (ostat, jmean, d2, d3, accel, ...)."""
+    torch = _torch()
+    n_rows = arrays[0].numel()
+    out = torch.empty(8, dtype=torch.float64, device=arrays[0].device)
+    ws, wsz = workspace_for(stat_id, n_rows, len(arrays), 1, 0, 1)
+    _abi.check(_abi.lib().b200boot_jackknife(_ptr_array(arrays), len(arrays), n_rows, stat_id, out.data_ptr(),
+                                             ws, wsz, stream_ptr()))
+    return out
+
+
+def jackknife_median_columns(data2d):
+    torch = _torch()
+    n_rows, n_cols = data2d.shape
+    out = torch.empty((n_cols, 8), dtype=torch.float64, device=data2d.device)
+    ws, wsz = workspace_for(_abi.STAT_MEDIAN, n_rows, 1, n_cols, 0, 1)
+    _abi.check(_abi.lib().b200boot_jackknife_median_columns(data2d.data_ptr(), n_rows, n_cols, data2d.stride(0),
+                                                            out.data_ptr(), ws, wsz, stream_ptr()))
+    return out
+
+
+def count(stat, op: int, t0, t1=None):
+    """K4 on stat float64[D][n] -> int64[D] CUDA tensor."""
+    torch = _torch()
+    n_cols, n_local = stat.shape
+    out = torch.empty(n_cols, dtype=torch.int64, device=stat.device)
+    _abi.check(_abi.lib().b200boot_count(stat.data_ptr(), n_local, n_cols, op, t0.data_ptr(),
+                                         t1.data_ptr() if t1 is not None else None, out.data_ptr(),
+                                         stream_ptr()))
+    return out
+
+
+class Select:
+    """K5 radix-descent select with an optional hook between the histogram and
+    pick steps (the all-reduce of the sharded path)."""
+
+    def __init__(self, stat, ranks):
+        torch = _torch()
+        self.stat = stat
+        self.n_cols, self.n_local = stat.shape
+        self.ranks = ranks.contiguous()              # int64[A][D] on device
+        self.n_alphas = ranks.shape[0]
+        need = _abi.lib().b200boot_workspace_bytes(_abi.STAT_MEAN, 1, 1, self.n_cols, 1, self.n_alphas)
+        self._buf = torch.empty(need + 256, dtype=torch.uint8, device=stat.device)
+        ptr = self._buf.data_ptr()
+        off = (-ptr) % 256
+        self.ws, self.wsz = ptr + off, self._buf.numel() - off
+
+    def hist_tensor(self):
+        torch = _torch()
+        p = C.c_void_p()
+        n = C.c_int64()
+        _abi.check(_abi.lib().b200boot_select_hist_buffer(self.n_alphas, self.n_cols, self.ws, self.wsz,
+                                                          C.byref(p), C.byref(n)))
+        off = p.value - self._buf.data_ptr()
+        return self._buf[off:off + n.value * 8].view(torch.int64)
+
+    def run(self, between=None):
+        torch = _torch()
+        L, s = _abi.lib(), stream_ptr()
+        out = torch.empty((self.n_alphas, self.n_cols), dtype=torch.float64, device=self.stat.device)
+        if between is None:
+            _abi.check(L.b200boot_select(self.stat.data_ptr(), self.n_local, self.n_cols, self.ranks.data_ptr(),
+                                         self.n_alphas, out.data_ptr(), self.ws, self.wsz, s))
+            return out
+        hist = self.hist_tensor()
+        _abi.check(L.b200boot_select_begin(self.ranks.data_ptr(), self.n_alphas, self.n_cols, self.ws, self.wsz, s))
+        for p in range(8):
+            _abi.check(L.b200boot_select_hist(self.stat.data_ptr(), self.n_local, self.n_cols, self.n_alphas, p,
+                                              self.ws, self.wsz, s))
+            between(hist)
+            _abi.check(L.b200boot_select_pick(self.n_alphas, self.n_cols, p, self.ws, self.wsz, s))
+        _abi.check(L.b200boot_select_end(self.n_alphas, self.n_cols, out.data_ptr(), self.ws, self.wsz, s))
+        return out
+
+
+def sort_columns(stat):
+    """In-place ascending sort of every row of stat float64[D][n]."""
+    n_cols, n = stat.shape
+    ws, wsz = workspace_for(_abi.STAT_MEAN, 1, 1, n_cols, n, 1)
+    _abi.check(_abi.lib().b200boot_sort_columns(stat.data_ptr(), n, n_cols, ws, wsz, stream_ptr()))
+    return stat

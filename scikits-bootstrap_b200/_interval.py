@@ -1,0 +1,89 @@
+"""Host-side interval math: O(len(alphas) * D) scalar work that stays in numpy.
+
+Follows /root/reference/src/scikits/bootstrap/bootstrap.py:
+  :75-79   ncdf  (math.erf based)
+  :83-119  nppf  (Acklam's rational approximation; its ~1e-9 error is part of the
+                  reference's answer, so the same form and constants are used)
+  :583, :627-629  z0 and the adjusted quantile levels
+  :456-480        order-statistic indices and the three instability conditions
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Tuple
+
+import numpy as np
+
+_A_TAIL = (-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e00,
+           -2.549732539343734e00, 4.374664141464968e00, 2.938163982698783e00)
+_B_TAIL = (7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e00,
+           3.754408661907416e00)
+_A_MID = (-3.969683028665376e01, 2.209460984245205e02, -2.759285104469687e02,
+          1.383577518672690e02, -3.066479806614716e01, 2.506628277459239e00)
+_B_MID = (-5.447609879822406e01, 1.615858368580409e02, -1.556989798598866e02,
+          6.680131188771972e01, -1.328068155288572e01)
+_SPLIT_LO, _SPLIT_HI = 0.02425, 0.97575
+_INV_SQRT2_DIV = math.sqrt(2)
+
+
+def _poly(coef, t):
+    r = np.full_like(t, coef[0], dtype=float)
+    for c in coef[1:]:
+        r = r * t + c
+    return r
+
+
+def _tail(t):
+    return _poly(_A_TAIL, t) / (_poly(_B_TAIL, t) * t + 1)
+
+
+def nppf(p) -> np.ndarray:
+    """Inverse standard-normal cdf, Acklam form; -inf / +inf at p == 0 / 1."""
+    p = np.asarray(p, dtype=float)
+    out = np.full(p.shape, np.nan)
+    with np.errstate(all="ignore"):
+        lo = (p > 0) & (p < _SPLIT_LO)
+        out[lo] = _tail(np.sqrt(-2 * np.log(p[lo])))
+        mid = (p >= _SPLIT_LO) & (p <= _SPLIT_HI)
+        q = p[mid] - 0.5
+        s = q * q
+        out[mid] = (_poly(_A_MID, s) * q) / (_poly(_B_MID, s) * s + 1)
+        hi = (p > _SPLIT_HI) & (p < 1)
+        out[hi] = -_tail(np.sqrt(-2 * np.log(1 - p[hi])))
+    out[p == 0] = -np.inf
+    out[p == 1] = np.inf
+    return out
+
+
+def ncdf(x) -> np.ndarray:
+    """Standard-normal cdf through math.erf, element by element."""
+    x = np.asarray(x, dtype=float)
+    out = np.empty(x.shape)
+    oi = out.reshape(-1)
+    for i, v in enumerate(x.reshape(-1)):
+        oi[i] = 0.5 * (1 + math.erf(v / _INV_SQRT2_DIV))
+    return out
+
+
+def bca_levels(less_counts: np.ndarray, n_samples: int, accel: np.ndarray,
+               alphas: np.ndarray) -> np.ndarray:
+    """Adjusted quantile levels: shape alphas.shape + stat shape."""
+    z0 = nppf((1.0 * np.asarray(less_counts)) / n_samples)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        zs = z0 + nppf(alphas).reshape(alphas.shape + (1,) * z0.ndim)
+        return ncdf(z0 + zs / (1 - accel * zs))
+
+
+def order_indices(avals: np.ndarray, n_samples: int) -> Tuple[np.ndarray, List[str]]:
+    """round((n-1)*avals) half-to-even as int (NaN -> 0) and which instability
+    conditions hold: 'nan', then 'extremal' or else 'top10'."""
+    flags: List[str] = []
+    with np.errstate(invalid="ignore"):
+        nvals = np.round((n_samples - 1) * avals)
+        if np.any(np.isnan(nvals)):
+            flags.append("nan")
+        if np.any(nvals == 0) or np.any(nvals == n_samples - 1):
+            flags.append("extremal")
+        elif np.any(nvals < 10) or np.any(nvals >= n_samples - 10):
+            flags.append("top10")
+    return np.nan_to_num(nvals).astype("int"), flags

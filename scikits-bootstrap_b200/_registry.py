@@ -1,0 +1,160 @@
+"""Device statistic registry.
+
+The reference dispatches its compiled fast path by callable identity
+(`statfunction in (np.average, np.mean)`, bootstrap.py:417, 588) and raises for
+anything else (bootstrap.py:426-427).  This registry is the same idea with more
+entries: a callable is recognised by identity, by being one of the exported
+`DeviceStat` objects below, or as `functools.partial(np.<f>, axis=0)`.
+Everything else raises — there is no host fallback.
+
+Every `DeviceStat` is also an ordinary numpy callable, so the very same object
+can be handed to the reference / the CPU oracle for parity checks."""
+from __future__ import annotations
+
+import functools
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import _abi
+
+
+@dataclass(frozen=True)
+class StatSpec:
+    name: str
+    stat_id: int
+    n_arrays: int
+    axis0: bool = False          # column-wise over 2-D data (rows share the index set)
+    independent: bool = False    # defined for multi='independent'
+
+
+class DeviceStat:
+    """A statistic the GPU path implements; callable on numpy arrays as well."""
+
+    def __init__(self, spec: StatSpec, host: Callable, doc: str):
+        self.spec = spec
+        self._host = host
+        self.__doc__ = doc
+        self.__name__ = spec.name
+
+    def __call__(self, *arrays, **kw):
+        return self._host(*arrays, **kw)
+
+    def __repr__(self):
+        return f"<b200 device statistic {self.spec.name}>"
+
+
+def _ratio(a, b):
+    return np.mean(a) / np.mean(b)
+
+
+def _wavg(x, w):
+    x = np.asarray(x, dtype=float)
+    w = np.asarray(w, dtype=float)
+    return np.sum(x * w) / np.sum(w)
+
+
+def _pearson(a, b):
+    return np.corrcoef(a, b)[0, 1]
+
+
+ratio_of_means = DeviceStat(StatSpec("ratio_of_means", _abi.STAT_RATIO_OF_MEANS, 2), _ratio,
+                            "mean(a) / mean(b) of two paired arrays")
+weighted_average = DeviceStat(StatSpec("weighted_average", _abi.STAT_WEIGHTED_AVERAGE, 2), _wavg,
+                              "sum(x*w) / sum(w) of paired (x, w)")
+pearson_r = DeviceStat(StatSpec("pearson_r", _abi.STAT_PEARSON_R, 2), _pearson,
+                       "Pearson correlation of two paired arrays")
+mean_axis0 = DeviceStat(StatSpec("mean_axis0", _abi.STAT_MEAN, 1, axis0=True),
+                        lambda a: np.mean(a, axis=0), "np.mean(a, axis=0) over (N, D) data")
+var_axis0 = DeviceStat(StatSpec("var_axis0", _abi.STAT_VAR, 1, axis0=True),
+                       lambda a: np.var(a, axis=0), "np.var(a, axis=0) over (N, D) data")
+std_axis0 = DeviceStat(StatSpec("std_axis0", _abi.STAT_STD, 1, axis0=True),
+                       lambda a: np.std(a, axis=0), "np.std(a, axis=0) over (N, D) data")
+median_axis0 = DeviceStat(StatSpec("median_axis0", _abi.STAT_MEDIAN, 1, axis0=True),
+                          lambda a: np.median(a, axis=0), "np.median(a, axis=0) over (N, D) data")
+diff_of_means = DeviceStat(StatSpec("diff_of_means", _abi.STAT_MEAN, 2, independent=True),
+                           lambda a, b: np.mean(a) - np.mean(b),
+                           "mean(a) - mean(b); for multi='independent'")
+
+_BY_IDENTITY = {
+    id(np.mean): StatSpec("mean", _abi.STAT_MEAN, 1),
+    id(np.average): StatSpec("mean", _abi.STAT_MEAN, 1),
+    id(np.var): StatSpec("var", _abi.STAT_VAR, 1),
+    id(np.std): StatSpec("std", _abi.STAT_STD, 1),
+    id(np.median): StatSpec("median", _abi.STAT_MEDIAN, 1),
+    id(np.sum): StatSpec("sum", _abi.STAT_SUM, 1),
+}
+_AXIS0 = {
+    id(np.mean): mean_axis0.spec, id(np.average): mean_axis0.spec, id(np.var): var_axis0.spec,
+    id(np.std): std_axis0.spec, id(np.median): median_axis0.spec,
+}
+
+REGISTRY_NAMES = ("np.mean, np.average, np.var, np.std, np.median, np.sum, "
+                  "functools.partial(np.<mean|average|var|std|median>, axis=0), "
+                  "ratio_of_means, weighted_average, pearson_r, mean_axis0, var_axis0, std_axis0, "
+                  "median_axis0, diff_of_means")
+
+
+def lookup(statfunction: Callable) -> Optional[StatSpec]:
+    if isinstance(statfunction, DeviceStat):
+        return statfunction.spec
+    if isinstance(statfunction, functools.partial):
+        if (not statfunction.args and statfunction.keywords == {"axis": 0}
+                and id(statfunction.func) in _AXIS0):
+            return _AXIS0[id(statfunction.func)]
+        return None
+    return _BY_IDENTITY.get(id(statfunction))
+
+
+def require(statfunction: Callable) -> StatSpec:
+    spec = lookup(statfunction)
+    if spec is None:
+        raise NotImplementedError(
+            "statfunction {!r} is not in the device statistic registry and there is no host "
+            "fallback; registered: {}".format(statfunction, REGISTRY_NAMES))
+    return spec
+
+
+# ---- comparison functions for pval ------------------------------------------------
+
+class DeviceCompare:
+    """A pval criterion evaluated on the device (count reduction); also callable
+    on host values."""
+
+    def __init__(self, op: int, t0: float, t1: float = 0.0):
+        self.op, self.t0, self.t1 = op, float(t0), float(t1)
+
+    def __call__(self, s):
+        if self.op == _abi.CMP_LT:
+            return s < self.t0
+        if self.op == _abi.CMP_LE:
+            return s <= self.t0
+        if self.op == _abi.CMP_GT:
+            return s > self.t0
+        if self.op == _abi.CMP_GE:
+            return s >= self.t0
+        return (self.t0 <= s) & (s <= self.t1)
+
+
+def less_than(c):
+    return DeviceCompare(_abi.CMP_LT, c)
+
+
+def less_equal(c):
+    return DeviceCompare(_abi.CMP_LE, c)
+
+
+def greater_than(c):
+    return DeviceCompare(_abi.CMP_GT, c)
+
+
+def greater_equal(c):
+    return DeviceCompare(_abi.CMP_GE, c)
+
+
+def between(lo, hi):
+    return DeviceCompare(_abi.CMP_BETWEEN, lo, hi)
+
+
+positive = greater_than(0.0)   # the reference's default `lambda s: s > 0` (bootstrap.py:793)

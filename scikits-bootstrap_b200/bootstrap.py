@@ -1,0 +1,531 @@
+"""Host-side mirror of the scikits.bootstrap API for the resampling hot path.
+
+Same names, argument meaning and error behaviour as the reference
+(/root/reference/src/scikits/bootstrap/bootstrap.py, cited as bootstrap.py:L):
+
+    ci(data, statfunction, alpha, n_samples, method='pi'|'bca', output, epsilon,
+       multi, return_dist, seed, use_numba)                       bootstrap.py:222-504
+    pval(data, statfunction, compfunction, n_samples, multi, seed)  bootstrap.py:790-866
+    bootstrap_indices / bootstrap_indices_independent             bootstrap.py:667-691
+    jackknife_indices                                             bootstrap.py:694-705
+
+What differs, by design:
+  * the resample loop, jackknife, z0 count and order-statistic pick run as
+    sm_100a kernels (libb200boot.so); there is no CPU path;
+  * `statfunction` must be in the device registry (_registry.py) — anything
+    else raises NotImplementedError, as the reference's use_numba switch raises
+    for unsupported callables (bootstrap.py:426-427);
+  * indices come from Philox4x32-10 keyed by (seed, resample id), not PCG64, so
+    fixed-seed values differ from the reference while the distribution is the same.
+"""
+from __future__ import annotations
+
+import warnings
+from collections.abc import Iterable
+from typing import Any, Callable, Iterator, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _abi, _device, _dist, _interval
+from ._registry import (DeviceCompare, DeviceStat, StatSpec, positive, require)
+
+__all__ = (
+    "ci",
+    "pval",
+    "bootstrap_indices",
+    "bootstrap_indices_independent",
+    "subsample_indices",
+    "jackknife_indices",
+    "bootstrap_indices_moving_block",
+)
+
+__version__ = "0.1.0"
+
+
+class InstabilityWarning(UserWarning):
+    """Issued when results may be unstable."""
+
+
+# Like the reference (bootstrap.py:130): never let these be filtered out.
+warnings.simplefilter("always", InstabilityWarning)
+
+SeedType = Union[None, int, np.ndarray, np.random.SeedSequence, np.random.BitGenerator,
+                 np.random.Generator]
+
+_MASK64 = (1 << 64) - 1
+# key offset between the arrays of multi='independent' (odd 64-bit constant)
+_ARRAY_KEY_STRIDE = 0x9E3779B97F4A7C15
+
+
+def _seed_key(seed: SeedType) -> int:
+    """Maps every seed form numpy's default_rng accepts (bootstrap.py:145-152) to
+    the 64-bit Philox key.  An int in [0, 2^64) is the key itself; a Generator /
+    BitGenerator is advanced by one 64-bit draw (as a Generator passed to the
+    reference is advanced by use)."""
+    if seed is None:
+        key = int(np.random.SeedSequence().generate_state(1, np.uint64)[0])
+        return _dist.broadcast_seed(key)
+    if isinstance(seed, np.random.Generator):
+        return int(seed.integers(0, 1 << 64, dtype=np.uint64))
+    if isinstance(seed, np.random.BitGenerator):
+        return int(np.random.Generator(seed).integers(0, 1 << 64, dtype=np.uint64))
+    if isinstance(seed, np.random.SeedSequence):
+        return int(seed.generate_state(1, np.uint64)[0])
+    if isinstance(seed, (int, np.integer)):
+        s = int(seed)
+        if s < 0:
+            raise ValueError("expected non-negative integer")
+        return s if s <= _MASK64 else int(np.random.SeedSequence(s).generate_state(1, np.uint64)[0])
+    return int(np.random.SeedSequence(seed).generate_state(1, np.uint64)[0])
+
+
+def _is_tensor(x) -> bool:
+    return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+def _normalise(data, multi) -> Tuple[list, Any]:
+    """multi validation and the data -> tuple-of-arrays step (bootstrap.py:362-379).
+    Arrays stay as given (numpy / torch); only shapes are inspected here."""
+    if multi not in [False, True, None, "independent", "paired"]:
+        raise ValueError("Value `{}` for multi is not recognized.".format(multi))
+    if multi is None:
+        multi = bool(isinstance(data, tuple))
+    if multi and isinstance(data, Iterable):
+        arrays = [x if _is_tensor(x) else np.array(x) for x in data]
+        lengths = [int(x.shape[0]) for x in arrays]
+        if len(set(lengths)) > 1 and multi != "independent":
+            raise ValueError(
+                "Data arrays have differing lengths {}, and ".format(lengths)
+                + "multi is not set to 'independent'.")
+    else:
+        arrays = [data if _is_tensor(data) else np.array(data)]
+    return arrays, multi
+
+
+def _check_spec(spec: StatSpec, arrays: Sequence, multi) -> None:
+    if multi == "independent" and not spec.independent:
+        raise NotImplementedError(
+            f"device statistic {spec.name} is not defined for multi='independent'")
+    if spec.independent and multi != "independent":
+        raise NotImplementedError(f"device statistic {spec.name} needs multi='independent'")
+    if len(arrays) != spec.n_arrays:
+        raise ValueError(f"device statistic {spec.name} takes {spec.n_arrays} array(s), "
+                         f"got {len(arrays)}")
+    for a in arrays:
+        nd = len(a.shape)
+        if spec.axis0:
+            if nd not in (1, 2):
+                raise NotImplementedError(f"{spec.name} needs 1-D or (N, D) data, got ndim={nd}")
+        elif nd != 1:
+            raise NotImplementedError(
+                f"device statistic {spec.name} needs 1-D data (got ndim={nd}); use the *_axis0 "
+                "registry statistics or functools.partial(np.<f>, axis=0) for (N, D) data")
+        if a.shape[0] < 1:
+            raise ValueError("data must have at least one row")
+
+
+class _Run:
+    """One resampling job on the current device: statistic vectors are kept
+    column-major, float64[D][n_local]."""
+
+    def __init__(self, spec: StatSpec, arrays: Sequence, multi, n_samples: int, key: int,
+                 indices=None):
+        self.spec, self.multi, self.n_samples, self.key = spec, multi, int(n_samples), key
+        self.indices = indices       # parity mode: caller-supplied index sets (K1i)
+        self.dev = [_device.to_device_f64(a) for a in arrays]
+        self.vector = spec.axis0 and self.dev[0].dim() == 2      # statistic has shape (D,)
+        self.n_cols = self.dev[0].shape[1] if self.vector else 1
+        self.rank, self.world = _dist.world()
+        self.lo, self.hi = _dist.shard_range(self.n_samples, self.rank, self.world)
+        self._columns = None
+        self._jack = None
+
+    # -- data views ------------------------------------------------------------
+    def columns(self):
+        """(N, D) data as D contiguous float64[N] rows (moment statistics per column)."""
+        if self._columns is None:
+            self._columns = self.dev[0].t().contiguous()
+        return self._columns
+
+    # -- K1 ----------------------------------------------------------------------
+    def resample(self):
+        torch = _device._torch()
+        spec, lo, hi = self.spec, self.lo, self.hi
+        if self.indices is not None:
+            return self._resample_indexed()
+        if spec.stat_id == _abi.STAT_MEDIAN:
+            data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
+            return _device.resample_median_columns(data2d, self.key, lo, hi)
+        if spec.independent:
+            # each array has its own key: streams are independent of one another
+            means = [_device.resample_stat([a], _abi.STAT_MEAN, (self.key + k * _ARRAY_KEY_STRIDE) & _MASK64, lo, hi)
+                     for k, a in enumerate(self.dev)]
+            return (means[0] - means[1]).reshape(1, -1)
+        if self.vector:
+            out = torch.empty((self.n_cols, hi - lo), dtype=torch.float64, device=self.dev[0].device)
+            cols = self.columns()
+            for d in range(self.n_cols):
+                _device.resample_stat([cols[d]], spec.stat_id, self.key, lo, hi, out=out[d])
+            return out
+        flat = [a.reshape(-1) for a in self.dev]
+        return _device.resample_stat(flat, spec.stat_id, self.key, lo, hi).reshape(1, -1)
+
+    # -- K1i ---------------------------------------------------------------------
+    def _resample_indexed(self):
+        """Parity mode: gathers with the caller's index sets (e.g. the reference's own
+        PCG64 draws) instead of drawing; moment statistics of 1-D arrays only."""
+        torch = _device._torch()
+        spec = self.spec
+        if _dist.active() or spec.independent or self.vector or spec.stat_id == _abi.STAT_MEDIAN:
+            raise NotImplementedError("index-supplied mode covers paired moment statistics of 1-D arrays")
+        idx = torch.as_tensor(np.ascontiguousarray(self.indices, dtype=np.int64)).to(self.dev[0].device)
+        if idx.dim() != 2 or idx.shape[0] != self.n_samples or idx.shape[1] != self.dev[0].numel():
+            raise ValueError("indices must have shape (n_samples, N)")
+        if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= self.dev[0].numel()):
+            raise IndexError("index out of range")
+        flat = [a.reshape(-1) for a in self.dev]
+        return _device.resample_stat_indexed(flat, spec.stat_id, idx).reshape(1, -1)
+
+    # -- K3 ----------------------------------------------------------------------
+    def jackknife(self):
+        """float64[D][8] on the host: ostat, jmean, d2, d3, accel, ..."""
+        if self._jack is not None:
+            return self._jack
+        torch = _device._torch()
+        spec = self.spec
+        if spec.stat_id == _abi.STAT_MEDIAN:
+            data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
+            j = _device.jackknife_median_columns(data2d)
+        elif spec.independent:
+            j = self._jackknife_independent()
+        elif self.vector:
+            cols = self.columns()
+            j = torch.stack([_device.jackknife([cols[d]], spec.stat_id) for d in range(self.n_cols)])
+        else:
+            j = _device.jackknife([a.reshape(-1) for a in self.dev], spec.stat_id).reshape(1, 8)
+        self._jack = _device.to_host(j)
+        return self._jack
+
+    def _jackknife_independent(self):
+        """diff_of_means under multi='independent': sum_k N_k leave-one-out values,
+        array-major (bootstrap.py:601-607, 708-714).  Deleting row j of array k moves
+        only mean_k, so the pooled jackknife mean is the statistic itself and the
+        deviations are +(a_j - mean_a)/(N_a - 1) and -(b_j - mean_b)/(N_b - 1): the
+        moments follow from each array's own K3 (mean) pass."""
+        torch = _device._torch()
+        a, b = self.dev
+        ma = _device.to_host(_device.jackknife([a], _abi.STAT_MEAN))
+        mb = _device.to_host(_device.jackknife([b], _abi.STAT_MEAN))
+        # per-array K3 (mean): d2_k = sum ((x - m_k)/(N_k-1))^2, d3_k likewise cubed; the b
+        # deviations enter with a minus sign
+        d2 = ma[2] + mb[2]
+        d3 = ma[3] - mb[3]
+        ostat = ma[0] - mb[0]
+        out = np.zeros(8)
+        out[0] = ostat
+        out[1] = ostat          # pooled jackknife mean equals the statistic for this linear form
+        out[2], out[3] = d2, d3
+        with np.errstate(invalid="ignore", divide="ignore"):
+            out[4] = d3 / (6.0 * d2 ** 1.5)
+        return torch.from_numpy(out.reshape(1, 8))
+
+    # -- K4 ----------------------------------------------------------------------
+    def count(self, stat, op: int, t0: np.ndarray, t1: Optional[np.ndarray] = None) -> np.ndarray:
+        torch = _device._torch()
+        t0d = _device.host_to_device(np.asarray(t0, dtype=np.float64), stat.device)
+        t1d = None if t1 is None else _device.host_to_device(np.asarray(t1, dtype=np.float64), stat.device)
+        c = _device.count(stat, op, t0d, t1d)
+        _dist.all_reduce_sum(c)
+        return _device.to_host(c)
+
+    # -- K5 ----------------------------------------------------------------------
+    def select(self, stat, ranks: np.ndarray) -> np.ndarray:
+        """ranks int[A][D] (global, 0-based) -> float64[A][D] order statistics."""
+        torch = _device._torch()
+        r = _device.host_to_device(np.asarray(ranks, dtype=np.int64), stat.device)
+        sel = _device.Select(stat, r)
+        out = sel.run(between=_dist.all_reduce_sum if _dist.active() else None)
+        return _device.to_host(out)
+
+    # -- full sorted distribution (return_dist / host-side compfunctions) --------
+    def sorted_dist(self, stat) -> np.ndarray:
+        full = _dist.all_gather_ragged(stat, self.n_samples).contiguous()
+        _device.sort_columns(full)
+        host = _device.to_host(full)
+        return host.T.copy() if self.vector else host[0].copy()
+
+
+def ci(
+    data,
+    statfunction: Optional[Callable] = None,
+    alpha: Union[float, Iterable] = 0.05,
+    n_samples: int = 10000,
+    method: str = "bca",
+    output: str = "lowhigh",
+    epsilon: float = 0.001,
+    multi=None,
+    return_dist: bool = False,
+    seed: SeedType = None,
+    use_numba: bool = False,
+):
+    """Bootstrap confidence interval of `statfunction` on `data`; drop-in for the
+    reference's `ci` with method 'pi' or 'bca' (bootstrap.py:222-504).
+
+    data: array_like (N, ...) or tuple of array_likes; numpy arrays, sequences,
+        pandas Series and torch tensors (CPU or CUDA; float64 CUDA tensors are used
+        in place).  statfunction: a callable from the device registry (see
+        `scikits_bootstrap_b200.REGISTRY_NAMES`); default np.average.
+    Returns the interval endpoints, and the sorted bootstrap distribution as well
+    when return_dist=True."""
+    return _ci_impl(data, statfunction, alpha, n_samples, method, output, epsilon, multi,
+                    return_dist, seed, use_numba, None)
+
+
+def ci_indexed(data, statfunction=None, indices=None, alpha=0.05, method="bca", output="lowhigh",
+               multi=None, return_dist=False):
+    """Parity mode of `ci`: identical pipeline, but the resamples are the caller's
+    `indices` (int array, shape (n_samples, N)) instead of Philox draws.  Feeding the
+    reference's own `bootstrap_indices` output reproduces the reference's result."""
+    idx = np.asarray(indices if not hasattr(indices, "__next__") else list(indices))
+    return _ci_impl(data, statfunction, alpha, idx.shape[0], method, output, 0.001, multi,
+                    return_dist, 0, False, idx)
+
+
+def _ci_impl(data, statfunction, alpha, n_samples, method, output, epsilon, multi, return_dist,
+             seed, use_numba, indices):
+    """Body shared by ci and ci_indexed (warnings use stacklevel=3: the user's frame)."""
+    # alphas exactly as given, or (alpha/2, 1-alpha/2)             bootstrap.py:353-356
+    if isinstance(alpha, Iterable):
+        alphas = np.array(alpha)
+    else:
+        alphas = np.array([alpha / 2, 1 - alpha / 2])
+
+    arrays, multi = _normalise(data, multi)
+
+    if statfunction is None:
+        statfunction = np.average
+    elif not callable(statfunction):
+        raise TypeError(
+            "statfunction {} is not callable.  If you tried ".format(statfunction)
+            + "calling a function with arguments here, for example, by using "
+            + "statfunction=myfunction(data, arg), then you probably need "
+            + "to wrap your function in a lambda, eg, as "
+            + "statfunction=(lambda data: myfunction(data, arg)). "
+            + "If your function doesn't need any arguments other than the data, "
+            + "you can alternatively use statfunction=myfunction (without "
+            + "parentheses.")
+
+    if method == "abc":                                           # bootstrap.py:400-413
+        if return_dist:
+            raise ValueError(
+                "The ABC method is being used, but return_dist=True. The distribution cannot be"
+                + "returned in this case, because the ABC method doesn't actually calculate it.")
+        if multi == "independent":
+            raise NotImplementedError("multi='independent' is not currently supported for ABC.")
+        raise NotImplementedError(
+            "method='abc' does no resampling and is outside the device hot path; use the "
+            "reference implementation for ABC intervals")
+    if use_numba:                                                 # bootstrap.py:415-437
+        if multi == "independent":
+            raise NotImplementedError(
+                "Numba for independent data is not implemented, because the numba code does not support >1d data yet")
+        if not (statfunction in (np.average, np.mean) and len(arrays) == 1):
+            raise ValueError("Numba can't be used with these values currently.")
+        # accepted for signature parity: the compiled path here is the device path
+    if method not in ("pi", "bca"):
+        raise ValueError("Method {0} is not supported.".format(method))
+    if output not in ("lowhigh", "errorbar"):
+        raise ValueError("Output option {0} is not supported.".format(output))
+
+    spec = require(statfunction)
+    _check_spec(spec, arrays, multi)
+    n_samples = int(n_samples)
+    if n_samples < 1:
+        raise ValueError("n_samples must be positive")
+    key = _seed_key(seed)
+
+    run = _Run(spec, arrays, multi, n_samples, key, indices)
+    stat = run.resample()                                         # float64[D][n_local]
+
+    ostat = None
+    if method == "pi":
+        avals = alphas
+    else:
+        jack = run.jackknife()
+        ostat = jack[:, 0]
+        accel = jack[:, 4]
+        less = run.count(stat, _abi.CMP_LT, ostat)               # strict '<'  bootstrap.py:583
+        if not run.vector:
+            less, accel_s = less[0], accel[0]
+        else:
+            accel_s = accel
+        if np.any(np.isnan(accel_s)):                             # bootstrap.py:616-625
+            nanind = np.nonzero(np.isnan(np.atleast_1d(accel_s)))
+            warnings.warn(
+                "BCa acceleration values for indices {} were undefined. \
+Statistic values were likely all equal. Affected CI will \
+be inaccurate.".format(nanind),
+                InstabilityWarning,
+                stacklevel=3,
+            )
+        avals = _interval.bca_levels(less, n_samples, accel_s, alphas)
+
+    nvals, flags = _interval.order_indices(avals, n_samples)      # bootstrap.py:456-480
+    if "nan" in flags:
+        warnings.warn(
+            "Some values were NaN; results are probably unstable "
+            + "(all values were probably equal)",
+            InstabilityWarning,
+            stacklevel=3,
+        )
+    if "extremal" in flags:
+        warnings.warn(
+            "Some values used extremal samples; " + "results are probably unstable.",
+            InstabilityWarning,
+            stacklevel=3,
+        )
+    elif "top10" in flags:
+        warnings.warn(
+            "Some values used top 10 low/high samples; " + "results may be unstable.",
+            InstabilityWarning,
+            stacklevel=3,
+        )
+
+    # order statistics without sorting: ranks int[A][D]            bootstrap.py:482-490
+    n_alphas = int(np.prod(alphas.shape)) if alphas.ndim else 1
+    flat = nvals.reshape(n_alphas, -1)
+    ranks = np.broadcast_to(flat, (n_alphas, run.n_cols)) if flat.shape[1] == 1 else flat
+    ranks = np.clip(ranks, 0, n_samples - 1)
+    picked = run.select(stat, ranks)                              # float64[A][D]
+
+    if run.vector:
+        vals = picked.reshape(alphas.shape + (run.n_cols,))
+    else:
+        vals = picked[:, 0].reshape(alphas.shape)
+
+    if output == "lowhigh":
+        out = vals
+    else:                                                         # bootstrap.py:491-497
+        if ostat is None:
+            ostat = run.jackknife()[:, 0]
+        o = ostat if run.vector else ostat[0]
+        if nvals.ndim == 1:
+            out = np.abs(o - vals)[np.newaxis].T
+        else:
+            out = np.abs(o - vals).T.squeeze()
+
+    if return_dist:
+        return out, run.sorted_dist(stat)
+    return out
+
+
+def pval(
+    data,
+    statfunction: Callable = np.average,
+    compfunction: Callable[[Any], Any] = positive,
+    n_samples: int = 10000,
+    multi: Optional[bool] = None,
+    seed: SeedType = None,
+):
+    """Bootstrap probability that `compfunction(statfunction(resample))` holds;
+    drop-in for the reference's `pval` (bootstrap.py:790-866).  The default
+    criterion is `s > 0`.  Criteria built with less_than / less_equal /
+    greater_than / greater_equal / between are counted on the device; any other
+    callable is applied on the host to the device-computed statistic values, row
+    by row, as the reference does (bootstrap.py:861)."""
+    return _pval_impl(data, statfunction, compfunction, n_samples, multi, seed, None)
+
+
+def pval_indexed(data, statfunction=np.average, compfunction=positive, indices=None, multi=None):
+    """Parity mode of `pval`: resamples are the caller's `indices` (n_samples, N)."""
+    idx = np.asarray(indices if not hasattr(indices, "__next__") else list(indices))
+    return _pval_impl(data, statfunction, compfunction, idx.shape[0], multi, 0, idx)
+
+
+def _pval_impl(data, statfunction, compfunction, n_samples, multi, seed, indices):
+    if multi is None:
+        multi = bool(isinstance(data, tuple))
+    arrays, multi = _normalise(data, bool(multi))
+    if not callable(statfunction):
+        raise TypeError("statfunction {} is not callable.".format(statfunction))
+    spec = require(statfunction)
+    _check_spec(spec, arrays, multi)
+    n_samples = int(n_samples)
+    key = _seed_key(seed)
+    run = _Run(spec, arrays, multi, n_samples, key, indices)
+    stat = run.resample()
+    if isinstance(compfunction, DeviceCompare):
+        t0 = np.full(run.n_cols, compfunction.t0)
+        t1 = np.full(run.n_cols, compfunction.t1)
+        hits = run.count(stat, compfunction.op, t0, t1)
+        frac = hits / float(n_samples)
+        return frac if run.vector else np.float64(frac[0])
+    dist = run.sorted_dist(stat)
+    return np.mean([compfunction(s) for s in dist], axis=0)
+
+
+def _n_rows(data) -> int:
+    if hasattr(data, "shape"):
+        return int(data.shape[0])
+    return len(data)
+
+
+def _index_batches(key: int, n_rows: int, n_arrays: int, n_samples: int):
+    budget = 64 << 20
+    step = max(1, min(n_samples, budget // (8 * n_rows)))
+    for lo in range(0, n_samples, step):
+        hi = min(n_samples, lo + step)
+        yield _device.to_host(_device.fill_indices(key, n_rows, n_arrays, lo, hi))
+
+
+def bootstrap_indices(data, n_samples: int = 10000, seed: SeedType = None,
+                      n_arrays: int = 1) -> Iterator[np.ndarray]:
+    """Generator of bootstrap index sets for data whose axis 0 delineates points
+    (bootstrap.py:667-680).  Yields int64[N] arrays: exactly the indices the fused
+    kernel draws for resample 0, 1, ... under the same seed, materialised on the
+    device.  Each array is a multiset of N iid uniform row draws listed cell by
+    cell; `n_arrays` selects the shared-memory tile plan of a
+    paired statistic over that many arrays (default 1)."""
+    key = _seed_key(seed)
+    n_rows = _n_rows(data)
+    for batch in _index_batches(key, n_rows, n_arrays, int(n_samples)):
+        for row in batch:
+            yield row
+
+
+def bootstrap_indices_independent(data: Tuple, n_samples: int = 10000,
+                                  seed: SeedType = None) -> Iterator[Tuple[np.ndarray, ...]]:
+    """One index set per array per resample (bootstrap.py:683-691); array k draws
+    from its own Philox key."""
+    key = _seed_key(seed)
+    lens = [_n_rows(x) for x in data]
+    gens = [
+        (row for batch in _index_batches((key + k * _ARRAY_KEY_STRIDE) & _MASK64, n, 1, int(n_samples))
+         for row in batch)
+        for k, n in enumerate(lens)
+    ]
+    for _ in range(int(n_samples)):
+        yield tuple(next(g) for g in gens)
+
+
+def jackknife_indices(data) -> Iterator[np.ndarray]:
+    """Leave-one-out index sets, ascending in the deleted row (bootstrap.py:694-705).
+    Public API only: the device jackknife is closed-form and never builds these."""
+    n = len(data)
+    base = np.arange(0, n)
+    return (np.concatenate((base[:i], base[i + 1:])) for i in range(n))
+
+
+def subsample_indices(data, n_samples: int = 1000, size: float = 0.5, seed: SeedType = None):
+    """Not part of the resampling hot path (bootstrap.py:717-744): not provided."""
+    raise NotImplementedError(
+        "subsample_indices is outside the device hot path of this package (ci/pval never call "
+        "it); see DESIGN.md, 'out of scope'")
+
+
+def bootstrap_indices_moving_block(data, n_samples: int = 10000, block_length: int = 3,
+                                   wrap: bool = False, seed: SeedType = None):
+    """Not part of the resampling hot path (bootstrap.py:747-787): not provided."""
+    raise NotImplementedError(
+        "bootstrap_indices_moving_block is outside the device hot path of this package "
+        "(ci/pval never call it); see DESIGN.md, 'out of scope'")

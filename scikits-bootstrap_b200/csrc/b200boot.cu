@@ -1,0 +1,594 @@
+// libb200boot.so — C ABI (include/b200boot.h) over the sm_100a kernels.
+// Host side only enqueues work on the caller's stream; all scratch comes from
+// the caller's workspace.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "draw.cuh"
+#include "k1_resample.cuh"
+#include "k1m_median.cuh"
+#include "k3_jackknife.cuh"
+#include "k45_interval.cuh"
+#include "stats.cuh"
+
+using namespace b200boot;
+
+namespace {
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// optional event timing of the K1 launch (bench.py)
+struct K1Profile {
+  bool enabled = false;
+  bool valid = false;
+  cudaEvent_t start = nullptr, stop = nullptr;
+};
+K1Profile g_prof;
+
+inline int blocks_for(int64_t n, int threads, int64_t cap) {
+  int64_t b = (n + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > cap) b = cap;
+  return (int)b;
+}
+
+// ---- workspace layouts ---------------------------------------------------------
+struct ResampleWs {
+  int32_t* counts;
+  double* partial;
+  int32_t* work_counter;
+  JackState* jack;
+  double* red;          // block partials of the reductions
+  double* centered[2];
+};
+
+ResampleWs carve_resample(Carver& cv, const Plan& plan, int stat, int64_t n_local) {
+  ResampleWs w{};
+  const int ms = moment_set_of(stat);
+  const int nm = ms == kMomSum ? 1 : (ms == kMomPair5 ? 5 : 2);
+  w.work_counter = cv.take<int32_t>(64);
+  w.jack = cv.take<JackState>(1);
+  w.red = cv.take<double>((size_t)kRedBlocks * kMaxMoments);
+  w.counts = plan.n_tiles > 1 ? cv.take<int32_t>((size_t)plan.n_tiles * n_local) : nullptr;
+  w.partial = cv.take<double>((size_t)plan.n_tiles * nm * std::max<int64_t>(n_local, 1));
+  if (stat_needs_centering(stat))
+    for (int a = 0; a < plan.n_arrays; ++a) w.centered[a] = cv.take<double>((size_t)plan.n_rows);
+  return w;
+}
+
+template <int NV, typename F, typename G>
+int run_reduction(int64_t n, F f, G g, double* red, cudaStream_t s) {
+  reduce_rows_kernel<NV, F><<<kRedBlocks, kRedThreads, 0, s>>>(n, f, red);
+  B2_LAUNCH_CHECK();
+  reduce_final_kernel<NV, G><<<1, kRedThreads, 0, s>>>(red, kRedBlocks, g);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+// Centres the arrays on their means when the statistic asks for it; returns the
+// pointers the moment kernels should read.
+int prepare_rows(const double* const* data, int n_arrays, int64_t n_rows, int stat, ResampleWs& w,
+                 const double** rows, cudaStream_t s) {
+  rows[0] = data[0];
+  rows[1] = n_arrays > 1 ? data[1] : nullptr;
+  B2_CUDA(cudaMemsetAsync(w.jack, 0, sizeof(JackState), s));
+  if (!stat_needs_centering(stat)) return 0;
+  int rc = run_reduction<2>(n_rows, RawSumsF{rows[0], rows[1]}, StoreCentersG{w.jack, (double)n_rows},
+                            w.red, s);
+  if (rc) return rc;
+  for (int a = 0; a < n_arrays; ++a) {
+    center_rows_kernel<<<blocks_for(n_rows, 256, 2368), 256, 0, s>>>(rows[a], w.centered[a], n_rows,
+                                                                    w.jack, a);
+    B2_LAUNCH_CHECK();
+    rows[a] = w.centered[a];
+  }
+  return 0;
+}
+
+int check_moment_stat(int stat, int n_arrays, int64_t n_rows) {
+  if (moment_set_of(stat) < 0)
+    return fail(B200BOOT_EUNSUPPORTED, "statistic id %d is not a moment statistic of the device registry",
+                stat);
+  if (n_arrays != stat_arrays(stat))
+    return fail(B200BOOT_EINVAL, "statistic id %d takes %d array(s), got %d", stat, stat_arrays(stat),
+                n_arrays);
+  if (n_rows < 1 || n_rows >= ((int64_t)1 << 31))
+    return fail(B200BOOT_EINVAL, "n_rows=%lld outside [1, 2^31)", (long long)n_rows);
+  return 0;
+}
+
+template <int MS>
+int launch_k1(const K1Params& P, size_t smem, int grid, cudaStream_t s) {
+  static bool configured[64] = {false};
+  int dev = 0;
+  B2_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    B2_CUDA(cudaFuncSetAttribute(k1_resample_kernel<MS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(kSmemHeader + kSmemDataBytes)));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  k1_resample_kernel<MS><<<grid, kK1Threads, smem, s>>>(P);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+int dispatch_k1(int ms, const K1Params& P, size_t smem, int grid, cudaStream_t s) {
+  switch (ms) {
+    case kMomSum: return launch_k1<kMomSum>(P, smem, grid, s);
+    case kMomSum2: return launch_k1<kMomSum2>(P, smem, grid, s);
+    case kMomAB: return launch_k1<kMomAB>(P, smem, grid, s);
+    case kMomXW: return launch_k1<kMomXW>(P, smem, grid, s);
+    default: return launch_k1<kMomPair5>(P, smem, grid, s);
+  }
+}
+
+template <int MS>
+int launch_k1i(const double* d0, const double* d1, int64_t n_rows, const int64_t* idx, int64_t n_sets,
+               double* partial, cudaStream_t s) {
+  const int grid = blocks_for(n_sets * 32, 256, 148 * 8);
+  k1_indexed_kernel<MS><<<grid, 256, 0, s>>>(d0, d1, n_rows, idx, n_sets, partial);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int MS>
+int jack_passes(const double** rows, int64_t n_rows, int stat, ResampleWs& w, double* out,
+                cudaStream_t s) {
+  const double n = (double)n_rows;
+  int rc = run_reduction<MomTraits<MS>::kMoments>(n_rows, ContributionF<MS>{rows[0], rows[1]},
+                                                  StoreTotalsG<MS>{w.jack, stat, n}, w.red, s);
+  if (rc) return rc;
+  rc = run_reduction<1>(n_rows, JackSumF<MS>{w.jack, stat, n, rows[0], rows[1]}, StoreJmeanG{w.jack, n},
+                        w.red, s);
+  if (rc) return rc;
+  return run_reduction<2>(n_rows, JackDevF<MS>{w.jack, stat, n, rows[0], rows[1]},
+                          StoreAccelG{w.jack, out}, w.red, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200boot_version(void) { return B200BOOT_ABI_VERSION; }
+const char* b200boot_last_error(void) { return err_buf(); }
+
+int b200boot_make_plan(int64_t n_rows, int n_arrays, b200boot_plan* out) {
+  if (!out || n_rows < 1 || n_arrays < 1 || n_arrays > 4)
+    return fail(B200BOOT_EINVAL, "make_plan: bad arguments");
+  const Plan p = make_plan(n_rows, n_arrays);
+  out->log2_tile = p.log2_tile;
+  out->n_arrays = p.n_arrays;
+  out->n_full = p.n_full;
+  out->rem = p.rem;
+  out->n_tiles = p.n_tiles;
+  return 0;
+}
+
+size_t b200boot_workspace_bytes(int stat_id, int64_t n_rows, int n_arrays, int64_t n_cols,
+                                int64_t n_local, int n_alphas) {
+  if (n_rows < 1 || n_arrays < 1 || n_local < 0 || n_cols < 1) return 0;
+  size_t total = 4096;
+  if (stat_id == kStatMedian) {
+    total += median_ws_bytes(n_rows, n_cols, n_local);
+  } else {
+    const Plan plan = make_plan(n_rows, n_arrays);
+    Carver cv(reinterpret_cast<void*>(256), ~(size_t)0 >> 1);
+    carve_resample(cv, plan, stat_id, n_local);
+    total += cv.used;
+  }
+  // select state, or sort keys (padded to a power of two), whichever is larger
+  const size_t sel = select_ws_bytes(std::max(n_alphas, 1), n_cols);
+  int64_t n_pad = 1;
+  while (n_pad < std::max<int64_t>(n_local, 1)) n_pad <<= 1;
+  const size_t srt = pad256((size_t)n_pad * (size_t)n_cols * 8);
+  total += std::max(sel, srt);
+  return total;
+}
+
+int b200boot_resample_stat(const double* const* data, int n_arrays, int64_t n_rows, int stat_id,
+                           uint64_t seed, int64_t resample_lo, int64_t resample_hi,
+                           double* stat_out, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_moment_stat(stat_id, n_arrays, n_rows);
+  if (rc) return rc;
+  const int64_t n_local = resample_hi - resample_lo;
+  if (n_local < 0 || resample_lo < 0) return fail(B200BOOT_EINVAL, "bad resample range");
+  if (n_local == 0) return 0;
+  if (!data || !stat_out) return fail(B200BOOT_EINVAL, "null pointer");
+  cudaStream_t s = as_stream(stream);
+  const Plan plan = make_plan(n_rows, n_arrays);
+  if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
+    return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
+  Carver cv(ws, ws_bytes);
+  ResampleWs w = carve_resample(cv, plan, stat_id, n_local);
+  if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+
+  const double* rows[2];
+  rc = prepare_rows(data, n_arrays, n_rows, stat_id, w, rows, s);
+  if (rc) return rc;
+
+  if (plan.n_tiles > 1) {
+    k0_tile_counts_kernel<<<blocks_for(n_local, 128, 1 << 30), 128, 0, s>>>(seed, resample_lo, n_local,
+                                                                          plan, w.counts);
+    B2_LAUNCH_CHECK();
+  }
+  B2_CUDA(cudaMemsetAsync(w.work_counter, 0, 256, s));
+
+  const int ms = moment_set_of(stat_id);
+  const int nm = ms == kMomSum ? 1 : (ms == kMomPair5 ? 5 : 2);
+  const int sms = sm_count();
+  // resamples per work item: aim at >= 16 items per CTA, whole warps, <= 2048
+  int64_t want_chunks = ((int64_t)sms * 16 + plan.n_tiles - 1) / plan.n_tiles;
+  int64_t chunk = (n_local + want_chunks - 1) / want_chunks;
+  chunk = ((chunk + kK1Warps - 1) / kK1Warps) * kK1Warps;
+  chunk = std::min<int64_t>(std::max<int64_t>(chunk, kK1Warps), 2048);
+  const int64_t n_chunks = (n_local + chunk - 1) / chunk;
+
+  K1Params P{};
+  P.data[0] = rows[0];
+  P.data[1] = rows[1];
+  P.plan = plan;
+  P.seed = seed;
+  P.resample_lo = resample_lo;
+  P.n_local = n_local;
+  P.counts = w.counts;
+  P.partial = w.partial;
+  P.work_counter = w.work_counter;
+  P.chunk = (int32_t)chunk;
+  P.n_chunks = (int32_t)n_chunks;
+  P.n_items = plan.n_tiles * n_chunks;
+  if (P.n_items >= ((int64_t)1 << 31)) return fail(B200BOOT_EINVAL, "too many work items");
+  P.smem_stride = plan.n_full > 0 ? plan.tile() : ((plan.rem + 1) & ~(int64_t)1);
+  const size_t smem = kSmemHeader + (size_t)P.smem_stride * 8 * n_arrays;
+  const int grid = (int)std::min<int64_t>(sms, P.n_items);
+  if (g_prof.enabled) B2_CUDA(cudaEventRecord(g_prof.start, s));
+  rc = dispatch_k1(ms, P, smem, grid, s);
+  if (rc) return rc;
+  if (g_prof.enabled) {
+    B2_CUDA(cudaEventRecord(g_prof.stop, s));
+    g_prof.valid = true;
+  }
+
+  k1_finish_kernel<<<blocks_for(n_local, 256, 1 << 30), 256, 0, s>>>(w.partial, plan.n_tiles, nm, n_local,
+                                                                     stat_id, (double)n_rows, stat_out);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200boot_resample_stat_indexed(const double* const* data, int n_arrays, int64_t n_rows,
+                                   int stat_id, const int64_t* indices, int64_t n_sets,
+                                   double* stat_out, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_moment_stat(stat_id, n_arrays, n_rows);
+  if (rc) return rc;
+  if (n_sets < 0) return fail(B200BOOT_EINVAL, "n_sets < 0");
+  if (n_sets == 0) return 0;
+  if (!data || !indices || !stat_out) return fail(B200BOOT_EINVAL, "null pointer");
+  cudaStream_t s = as_stream(stream);
+  Plan plan = make_plan(n_rows, n_arrays);
+  plan.n_tiles = 1;   // partial layout [m][n_sets]
+  if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
+    return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
+  Carver cv(ws, ws_bytes);
+  ResampleWs w = carve_resample(cv, plan, stat_id, n_sets);
+  if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+  const double* rows[2];
+  rc = prepare_rows(data, n_arrays, n_rows, stat_id, w, rows, s);
+  if (rc) return rc;
+  const int ms = moment_set_of(stat_id);
+  const int nm = ms == kMomSum ? 1 : (ms == kMomPair5 ? 5 : 2);
+  switch (ms) {
+    case kMomSum: rc = launch_k1i<kMomSum>(rows[0], rows[1], n_rows, indices, n_sets, w.partial, s); break;
+    case kMomSum2: rc = launch_k1i<kMomSum2>(rows[0], rows[1], n_rows, indices, n_sets, w.partial, s); break;
+    case kMomAB: rc = launch_k1i<kMomAB>(rows[0], rows[1], n_rows, indices, n_sets, w.partial, s); break;
+    case kMomXW: rc = launch_k1i<kMomXW>(rows[0], rows[1], n_rows, indices, n_sets, w.partial, s); break;
+    default: rc = launch_k1i<kMomPair5>(rows[0], rows[1], n_rows, indices, n_sets, w.partial, s); break;
+  }
+  if (rc) return rc;
+  k1_finish_kernel<<<blocks_for(n_sets, 256, 1 << 30), 256, 0, s>>>(w.partial, 1, nm, n_sets, stat_id,
+                                                                    (double)n_rows, stat_out);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200boot_tile_counts(uint64_t seed, int64_t n_rows, int n_arrays, int64_t resample_lo,
+                         int64_t resample_hi, int32_t* counts, void* stream) {
+  const int64_t n_local = resample_hi - resample_lo;
+  if (n_rows < 1 || n_arrays < 1 || n_local < 0 || !counts) return fail(B200BOOT_EINVAL, "bad arguments");
+  if (n_local == 0) return 0;
+  const Plan plan = make_plan(n_rows, n_arrays);
+  k0_tile_counts_kernel<<<blocks_for(n_local, 128, 1 << 30), 128, 0, as_stream(stream)>>>(
+      seed, resample_lo, n_local, plan, counts);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200boot_fill_indices(uint64_t seed, int64_t n_rows, int n_arrays, int64_t resample_lo,
+                          int64_t resample_hi, int64_t* out, void* ws, size_t ws_bytes,
+                          void* stream) {
+  const int64_t n_local = resample_hi - resample_lo;
+  if (n_rows < 1 || n_rows >= ((int64_t)1 << 31) || n_arrays < 1 || n_local < 0 || !out)
+    return fail(B200BOOT_EINVAL, "bad arguments");
+  if (n_local == 0) return 0;
+  cudaStream_t s = as_stream(stream);
+  const Plan plan = make_plan(n_rows, n_arrays);
+  int32_t* counts = nullptr;
+  if (plan.n_tiles > 1) {
+    if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
+      return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
+    Carver cv(ws, ws_bytes);
+    counts = cv.take<int32_t>((size_t)plan.n_tiles * n_local);
+    if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+    k0_tile_counts_kernel<<<blocks_for(n_local, 128, 1 << 30), 128, 0, s>>>(seed, resample_lo, n_local,
+                                                                          plan, counts);
+    B2_LAUNCH_CHECK();
+  }
+  k2_fill_indices_kernel<<<blocks_for(n_local * 32, 256, 148 * 8), 256, 0, s>>>(plan, seed, resample_lo,
+                                                                               n_local, counts, out);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200boot_gather(const double* data, int64_t n_rows, const int64_t* idx, int64_t n_idx,
+                    double* out, void* stream) {
+  if (!data || !idx || !out || n_rows < 1 || n_idx < 0) return fail(B200BOOT_EINVAL, "bad arguments");
+  if (n_idx == 0) return 0;
+  gather_kernel<<<blocks_for(n_idx, 256, 148 * 16), 256, 0, as_stream(stream)>>>(data, idx, n_idx, out);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200boot_jackknife(const double* const* data, int n_arrays, int64_t n_rows, int stat_id,
+                       double* out, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_moment_stat(stat_id, n_arrays, n_rows);
+  if (rc) return rc;
+  if (!data || !out) return fail(B200BOOT_EINVAL, "null pointer");
+  cudaStream_t s = as_stream(stream);
+  const Plan plan = make_plan(n_rows, n_arrays);
+  if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
+    return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
+  Carver cv(ws, ws_bytes);
+  ResampleWs w = carve_resample(cv, plan, stat_id, 0);
+  if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+  const double* rows[2];
+  rc = prepare_rows(data, n_arrays, n_rows, stat_id, w, rows, s);
+  if (rc) return rc;
+  switch (moment_set_of(stat_id)) {
+    case kMomSum: return jack_passes<kMomSum>(rows, n_rows, stat_id, w, out, s);
+    case kMomSum2: return jack_passes<kMomSum2>(rows, n_rows, stat_id, w, out, s);
+    case kMomAB: return jack_passes<kMomAB>(rows, n_rows, stat_id, w, out, s);
+    case kMomXW: return jack_passes<kMomXW>(rows, n_rows, stat_id, w, out, s);
+    default: return jack_passes<kMomPair5>(rows, n_rows, stat_id, w, out, s);
+  }
+}
+
+int b200boot_count(const double* stat, int64_t n_local, int64_t n_cols, int cmp_op,
+                   const double* t0, const double* t1, int64_t* counts, void* stream) {
+  if (!stat || !t0 || !counts || n_local < 0 || n_cols < 1 || n_cols > 65535 * 64LL)
+    return fail(B200BOOT_EINVAL, "bad arguments");
+  if (cmp_op < 0 || cmp_op > B200BOOT_CMP_BETWEEN) return fail(B200BOOT_EINVAL, "bad comparison op");
+  if (cmp_op == B200BOOT_CMP_BETWEEN && !t1) return fail(B200BOOT_EINVAL, "BETWEEN needs t1");
+  cudaStream_t s = as_stream(stream);
+  B2_CUDA(cudaMemsetAsync(counts, 0, (size_t)n_cols * 8, s));
+  if (n_local == 0) return 0;
+  for (int64_t d0 = 0; d0 < n_cols; d0 += 65535) {
+    const int64_t nd = std::min<int64_t>(65535, n_cols - d0);
+    dim3 grid(blocks_for(n_local, 256 * 8, 64), (unsigned)nd);
+    k4_count_kernel<<<grid, 256, 0, s>>>(stat + d0 * n_local, n_local, cmp_op, t0 + d0, t1 ? t1 + d0 : nullptr,
+                                         reinterpret_cast<unsigned long long*>(counts + d0));
+    B2_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// ---- K5 -----------------------------------------------------------------------
+static int select_state(int n_alphas, int64_t n_cols, void* ws, size_t ws_bytes, SelectState* st) {
+  if (n_alphas < 1 || n_cols < 1) return fail(B200BOOT_EINVAL, "bad select shape");
+  if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
+    return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
+  Carver cv(ws, ws_bytes);
+  *st = select_carve(cv, n_alphas, n_cols);
+  if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+  return 0;
+}
+
+int b200boot_select_begin(const int64_t* ranks, int n_alphas, int64_t n_cols, void* ws,
+                          size_t ws_bytes, void* stream) {
+  SelectState st;
+  int rc = select_state(n_alphas, n_cols, ws, ws_bytes, &st);
+  if (rc) return rc;
+  if (!ranks) return fail(B200BOOT_EINVAL, "null ranks");
+  const int64_t ad = (int64_t)n_alphas * n_cols;
+  k5_begin_kernel<<<blocks_for(ad * 256, 256, 148 * 8), 256, 0, as_stream(stream)>>>(ranks, ad, st);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200boot_select_hist(const double* stat, int64_t n_local, int64_t n_cols, int n_alphas,
+                         int pass, void* ws, size_t ws_bytes, void* stream) {
+  SelectState st;
+  int rc = select_state(n_alphas, n_cols, ws, ws_bytes, &st);
+  if (rc) return rc;
+  if (pass < 0 || pass > 7 || n_local < 0) return fail(B200BOOT_EINVAL, "bad pass / n_local");
+  if (n_local == 0) return 0;
+  if (!stat) return fail(B200BOOT_EINVAL, "null stat");
+  for (int a_lo = 0; a_lo < n_alphas; a_lo += kSelMaxAlphas) {
+    const int a_cnt = std::min(kSelMaxAlphas, n_alphas - a_lo);
+    for (int64_t d0 = 0; d0 < n_cols; d0 += 65535) {
+      const int64_t nd = std::min<int64_t>(65535, n_cols - d0);
+      dim3 grid(blocks_for(n_local, 256 * 8, 64), (unsigned)nd);
+      SelectState sub = st;
+      sub.prefix += d0;
+      sub.krem += d0;
+      sub.hist += d0 * 256;
+      k5_hist_kernel<<<grid, 256, 0, as_stream(stream)>>>(stat + d0 * n_local, n_local, n_cols, a_lo, a_cnt,
+                                                          pass, sub);
+      B2_LAUNCH_CHECK();
+    }
+  }
+  return 0;
+}
+
+int b200boot_select_pick(int n_alphas, int64_t n_cols, int pass, void* ws, size_t ws_bytes,
+                         void* stream) {
+  SelectState st;
+  int rc = select_state(n_alphas, n_cols, ws, ws_bytes, &st);
+  if (rc) return rc;
+  if (pass < 0 || pass > 7) return fail(B200BOOT_EINVAL, "bad pass");
+  const int64_t ad = (int64_t)n_alphas * n_cols;
+  k5_pick_kernel<<<blocks_for(ad, 256, 1 << 30), 256, 0, as_stream(stream)>>>(ad, pass, st);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200boot_select_end(int n_alphas, int64_t n_cols, double* out, void* ws, size_t ws_bytes,
+                        void* stream) {
+  SelectState st;
+  int rc = select_state(n_alphas, n_cols, ws, ws_bytes, &st);
+  if (rc) return rc;
+  if (!out) return fail(B200BOOT_EINVAL, "null out");
+  const int64_t ad = (int64_t)n_alphas * n_cols;
+  k5_end_kernel<<<blocks_for(ad, 256, 1 << 30), 256, 0, as_stream(stream)>>>(ad, st, out);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200boot_select_hist_buffer(int n_alphas, int64_t n_cols, void* ws, size_t ws_bytes,
+                                int64_t** hist, int64_t* n_elems) {
+  SelectState st;
+  int rc = select_state(n_alphas, n_cols, ws, ws_bytes, &st);
+  if (rc) return rc;
+  if (!hist || !n_elems) return fail(B200BOOT_EINVAL, "null out pointer");
+  *hist = st.hist;
+  *n_elems = (int64_t)n_alphas * n_cols * 256;
+  return 0;
+}
+
+int b200boot_select(const double* stat, int64_t n_local, int64_t n_cols, const int64_t* ranks,
+                    int n_alphas, double* out, void* ws, size_t ws_bytes, void* stream) {
+  int rc = b200boot_select_begin(ranks, n_alphas, n_cols, ws, ws_bytes, stream);
+  for (int pass = 0; pass < 8 && !rc; ++pass) {
+    rc = b200boot_select_hist(stat, n_local, n_cols, n_alphas, pass, ws, ws_bytes, stream);
+    if (!rc) rc = b200boot_select_pick(n_alphas, n_cols, pass, ws, ws_bytes, stream);
+  }
+  if (!rc) rc = b200boot_select_end(n_alphas, n_cols, out, ws, ws_bytes, stream);
+  return rc;
+}
+
+int b200boot_sort_columns(double* stat, int64_t n, int64_t n_cols, void* ws, size_t ws_bytes,
+                          void* stream) {
+  if (!stat || n < 0 || n_cols < 1 || n_cols > 65535) return fail(B200BOOT_EINVAL, "bad arguments");
+  if (n <= 1) return 0;
+  cudaStream_t s = as_stream(stream);
+  int64_t n_pad = 1;
+  while (n_pad < n) n_pad <<= 1;
+  if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
+    return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
+  Carver cv(ws, ws_bytes);
+  uint64_t* keys = cv.take<uint64_t>((size_t)n_pad * n_cols);
+  if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+  const dim3 gflat(blocks_for(n_pad, 256 * 4, 4096), (unsigned)n_cols);
+  sort_load_kernel<<<gflat, 256, 0, s>>>(stat, n, n_pad, keys);
+  B2_LAUNCH_CHECK();
+  const int64_t seg = std::min<int64_t>(2048, n_pad);
+  const dim3 glocal((unsigned)(n_pad / seg), (unsigned)n_cols);
+  sort_local_kernel<<<glocal, 1024, 0, s>>>(keys, n_pad, 2, seg, 1);
+  B2_LAUNCH_CHECK();
+  for (int64_t k = seg * 2; k <= n_pad; k <<= 1) {
+    for (int64_t j = k >> 1; j >= 2048; j >>= 1) {
+      sort_step_kernel<<<gflat, 256, 0, s>>>(keys, n_pad, j, k);
+      B2_LAUNCH_CHECK();
+    }
+    sort_local_kernel<<<glocal, 1024, 0, s>>>(keys, n_pad, k, k, 1024);
+    B2_LAUNCH_CHECK();
+  }
+  sort_store_kernel<<<gflat, 256, 0, s>>>(keys, n, n_pad, stat);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- median (K1m / K3m) ----------------------------------------------------------
+int b200boot_resample_median_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld,
+                                     uint64_t seed, int64_t resample_lo, int64_t resample_hi,
+                                     double* stat_out, void* ws, size_t ws_bytes, void* stream) {
+  return median_resample(data, n_rows, n_cols, ld, seed, resample_lo, resample_hi, stat_out, ws,
+                         ws_bytes, as_stream(stream));
+}
+
+int b200boot_jackknife_median_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld,
+                                      double* out, void* ws, size_t ws_bytes, void* stream) {
+  return median_jackknife(data, n_rows, n_cols, ld, out, ws, ws_bytes, as_stream(stream));
+}
+
+// ---- instrumentation ---------------------------------------------------------------
+int64_t b200boot_launch_count(void) { return (int64_t)launch_counter(); }
+
+int b200boot_profile_enable(int on) {
+  if (on && !g_prof.start) {
+    B2_CUDA(cudaEventCreate(&g_prof.start));
+    B2_CUDA(cudaEventCreate(&g_prof.stop));
+  }
+  g_prof.enabled = on != 0;
+  g_prof.valid = false;
+  return 0;
+}
+
+int b200boot_profile_last_k1_ms(float* ms) {
+  if (!ms) return fail(B200BOOT_EINVAL, "null ms");
+  if (!g_prof.valid) return fail(B200BOOT_EINVAL, "no timed K1 launch recorded");
+  B2_CUDA(cudaEventSynchronize(g_prof.stop));
+  B2_CUDA(cudaEventElapsedTime(ms, g_prof.start, g_prof.stop));
+  return 0;
+}
+
+// ---- host probes (CPU test-suite; same sources as the kernels) ------------------
+void b200boot_host_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  const Words4 w = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+  for (int i = 0; i < 4; ++i) out[i] = w.w[i];
+}
+
+int64_t b200boot_host_binomial(uint64_t seed, int64_t resample, int64_t cell, int64_t n, double p) {
+  const Stream s = make_stream(seed, resample, (uint32_t)cell, kPurposeBinomial);
+  if (n <= 0 || p <= 0.0) return 0;
+  if (p >= 1.0) return n;
+  const bool flip = p > 0.5;
+  const double pp = flip ? 1.0 - p : p;
+  const int64_t k = ((double)n * pp >= 10.0) ? binomial_btrs(n, pp, s) : binomial_inversion(n, pp, s);
+  return flip ? n - k : k;
+}
+
+int b200boot_host_tile_counts(uint64_t seed, int64_t n_rows, int n_arrays, int64_t resample,
+                              int32_t* counts) {
+  if (n_rows < 1 || n_arrays < 1 || !counts) return fail(B200BOOT_EINVAL, "bad arguments");
+  const Plan plan = make_plan(n_rows, n_arrays);
+  tile_count_chain<int32_t>(seed, resample, plan, counts, 1);
+  return 0;
+}
+
+int b200boot_host_indices(uint64_t seed, int64_t n_rows, int n_arrays, int64_t resample, int64_t* out) {
+  if (n_rows < 1 || n_rows >= ((int64_t)1 << 31) || n_arrays < 1 || !out)
+    return fail(B200BOOT_EINVAL, "bad arguments");
+  const Plan plan = make_plan(n_rows, n_arrays);
+  std::vector<int32_t> counts((size_t)plan.n_tiles);
+  if (plan.n_tiles > 1)
+    tile_count_chain<int32_t>(seed, resample, plan, counts.data(), 1);
+  else
+    counts[0] = (int32_t)n_rows;
+  int64_t offset = 0;
+  for (int64_t t = 0; t < plan.n_tiles; ++t) {
+    const int64_t n = counts[(size_t)t];
+    const int64_t sz = plan.cell_size(t);
+    const int64_t row0 = t < plan.n_full ? (t << plan.log2_tile) : (plan.n_full << plan.log2_tile);
+    const Stream st = make_stream(seed, resample, (uint32_t)t, kPurposeIndex);
+    auto put = [&](int, int64_t pos, uint32_t idx) { out[offset + pos] = row0 + (int64_t)idx; };
+    if (t < plan.n_full) {
+      for (uint32_t q = 0; (int64_t)q * 8 < n; ++q) pow2_block<true>(st, q, (uint32_t)sz - 1u, n, put);
+    } else {
+      const uint32_t thresh = lemire_threshold((uint32_t)sz);
+      for (uint32_t q = 0; (int64_t)q * 4 < n; ++q) lemire_block<true>(st, q, (uint32_t)sz, thresh, n, put);
+    }
+    offset += n;
+  }
+  return 0;
+}
+
+}  // extern "C"

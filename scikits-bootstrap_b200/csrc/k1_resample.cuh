@@ -1,0 +1,267 @@
+// K0 (tile occupancies), K1 (fused draw + gather + FP64 reduce), K1i (indexed
+// parity mode), K2 (index materialiser) and the moment finisher.
+//
+// Replaces /root/reference/src/scikits/bootstrap/bootstrap.py:429-432 (resample
+// loop) and :677-680 (index generator).  No index array is materialised by K1.
+//
+// Execution shape of K1: persistent CTAs (one per SM, 1024 threads).  A work
+// item is (cell t, chunk of resamples); the CTA bulk-copies cell t (<= 224 KB)
+// into shared memory with cp.async.bulk + mbarrier, then each warp owns one
+// resample at a time: its lanes generate Philox blocks, turn the words into
+// row offsets inside the cell, gather from shared memory and accumulate the
+// statistic's contribution vector in FP64.  A warp-shuffle butterfly produces
+// the per-(cell, resample) partial, later summed over cells in fixed order.
+#pragma once
+#include "common.cuh"
+#include "draw.cuh"
+#include "stats.cuh"
+
+namespace b200boot {
+
+constexpr int kK1Threads = 1024;
+constexpr int kK1Warps = kK1Threads / 32;
+constexpr int kSmemHeader = 128;  // mbarrier + work-item slot
+
+// ------------------------------------------------------------------ K0 --------
+__global__ void __launch_bounds__(128) k0_tile_counts_kernel(uint64_t seed, int64_t resample_lo,
+                                                             int64_t n_local, Plan plan,
+                                                             int32_t* __restrict__ counts) {
+  const int64_t rl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (rl >= n_local) return;
+  tile_count_chain<int32_t>(seed, resample_lo + rl, plan, counts + rl, n_local);
+}
+
+// ------------------------------------------------------------------ K1 --------
+struct K1Params {
+  const double* data[2];
+  Plan plan;
+  uint64_t seed;
+  int64_t resample_lo;
+  int64_t n_local;
+  const int32_t* counts;  // [n_tiles][n_local]; null when the plan has one cell
+  double* partial;        // [(t * NM + m)][n_local]
+  int32_t* work_counter;
+  int32_t chunk;          // resamples per work item
+  int32_t n_chunks;
+  int64_t n_items;
+  int64_t smem_stride;    // elements between arrays in shared memory
+};
+
+// Sums the contribution vectors of the `n` draws of one (resample, cell) across
+// the lanes of a warp.  POW2: 8 indices per Philox block, else 4 (Lemire).
+template <int MS, bool POW2>
+__device__ __forceinline__ void cell_accumulate(const double* __restrict__ s_data,
+                                                int64_t smem_stride, const Stream& st, int64_t n,
+                                                uint32_t size, int lane, double* tot) {
+  constexpr int NA = MomTraits<MS>::kArrays;
+  constexpr int NM = MomTraits<MS>::kMoments;
+  constexpr int W = MomTraits<MS>::kWays;
+  constexpr int PER = POW2 ? 8 : 4;
+  double acc[NM][W];
+#pragma unroll
+  for (int m = 0; m < NM; ++m)
+#pragma unroll
+    for (int w = 0; w < W; ++w) acc[m][w] = 0.0;
+
+  auto take = [&](int j, int64_t /*pos*/, uint32_t idx) {
+    double v[NA], c[NM];
+    v[0] = s_data[idx];
+    if (NA == 2) v[NA - 1] = s_data[smem_stride + idx];
+    contribution<MS>(v, c);
+#pragma unroll
+    for (int m = 0; m < NM; ++m) acc[m][j % W] += c[m];
+  };
+
+  const uint32_t n_full = (uint32_t)(n / PER);
+  const uint32_t mask = size - 1u;
+  const uint32_t thresh = POW2 ? 0u : lemire_threshold(size);
+#pragma unroll 2
+  for (uint32_t q = lane; q < n_full; q += 32) {
+    if (POW2)
+      pow2_block<false>(st, q, mask, n, take);
+    else
+      lemire_block<false>(st, q, size, thresh, n, take);
+  }
+  if ((int64_t)n_full * PER < n && (n_full & 31u) == (uint32_t)lane) {
+    if (POW2)
+      pow2_block<true>(st, n_full, mask, n, take);
+    else
+      lemire_block<true>(st, n_full, size, thresh, n, take);
+  }
+#pragma unroll
+  for (int m = 0; m < NM; ++m) {
+#pragma unroll
+    for (int w = W / 2; w > 0; w >>= 1)
+#pragma unroll
+      for (int i = 0; i < w; ++i) acc[m][i] += acc[m][i + w];
+    tot[m] = warp_sum(acc[m][0]);
+  }
+}
+
+template <int MS>
+__global__ void __launch_bounds__(kK1Threads, 1) k1_resample_kernel(const K1Params P) {
+  constexpr int NA = MomTraits<MS>::kArrays;
+  constexpr int NM = MomTraits<MS>::kMoments;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  volatile int* s_item = reinterpret_cast<volatile int*>(smem_raw + 16);
+  double* s_data = reinterpret_cast<double*>(smem_raw + kSmemHeader);
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  if (tid == 0) mbar_init(bar, 1);
+  __syncthreads();
+
+  uint32_t phase = 0;
+  int64_t resident = -1;
+  for (;;) {
+    if (tid == 0) *s_item = atomicAdd(P.work_counter, 1);
+    __syncthreads();  // publishes the item; every warp is done with the previous one
+    const int64_t item = *s_item;
+    __syncthreads();  // nobody reads the slot after this point
+    if (item >= P.n_items) break;
+    const int64_t t = item / P.n_chunks;
+    const int64_t c = item - t * P.n_chunks;
+    const int64_t sz = P.plan.cell_size(t);
+    const int64_t row0 = t < P.plan.n_full ? (t << P.plan.log2_tile) : (P.plan.n_full << P.plan.log2_tile);
+
+    if (t != resident) {
+      // bulk (TMA) copy of the 16-byte-aligned body, plain loads for what is left
+      bool aligned = true;
+#pragma unroll
+      for (int a = 0; a < NA; ++a)
+        aligned = aligned && ((reinterpret_cast<uintptr_t>(P.data[a] + row0) & 15u) == 0);
+      const uint32_t body_bytes = aligned ? (uint32_t)((sz * 8) & ~(int64_t)15) : 0u;
+      if (body_bytes != 0 && tid == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(bar, body_bytes * NA);
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+          bulk_copy_g2s(s_data + a * P.smem_stride, P.data[a] + row0, body_bytes, bar);
+      }
+      for (int64_t i = body_bytes / 8 + tid; i < sz; i += kK1Threads) {
+#pragma unroll
+        for (int a = 0; a < NA; ++a) s_data[a * P.smem_stride + i] = __ldg(P.data[a] + row0 + i);
+      }
+      if (body_bytes != 0) {
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+      }
+      __syncthreads();
+      resident = t;
+    }
+
+    const int64_t r_begin = c * P.chunk;
+    const int64_t r_end = min(r_begin + (int64_t)P.chunk, P.n_local);
+    const bool pow2 = t < P.plan.n_full;
+    for (int64_t rl = r_begin + warp; rl < r_end; rl += kK1Warps) {
+      const int64_t n = P.counts ? (int64_t)__ldg(P.counts + t * P.n_local + rl) : P.plan.n_rows;
+      const Stream st = make_stream(P.seed, P.resample_lo + rl, (uint32_t)t, kPurposeIndex);
+      double tot[NM];
+      if (pow2)
+        cell_accumulate<MS, true>(s_data, P.smem_stride, st, n, (uint32_t)sz, lane, tot);
+      else
+        cell_accumulate<MS, false>(s_data, P.smem_stride, st, n, (uint32_t)sz, lane, tot);
+      if (lane == 0) {
+#pragma unroll
+        for (int m = 0; m < NM; ++m) P.partial[(t * NM + m) * P.n_local + rl] = tot[m];
+      }
+    }
+  }
+}
+
+// Sums the per-cell partials in cell order and finishes the statistic.
+__global__ void __launch_bounds__(256) k1_finish_kernel(const double* __restrict__ partial,
+                                                        int64_t n_tiles, int nm, int64_t n_local,
+                                                        int stat, double count,
+                                                        double* __restrict__ out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_local) return;
+  double m[kMaxMoments];
+  for (int k = 0; k < nm; ++k) {
+    double acc = 0.0;
+    for (int64_t t = 0; t < n_tiles; ++t) acc += partial[(t * nm + k) * n_local + r];
+    m[k] = acc;
+  }
+  out[r] = finish_stat(stat, m, count);
+}
+
+// ------------------------------------------------------------------ K1i -------
+// Parity mode: index sets supplied by the caller; one warp per set.
+template <int MS>
+__global__ void __launch_bounds__(256) k1_indexed_kernel(const double* __restrict__ d0,
+                                                         const double* __restrict__ d1,
+                                                         int64_t n_rows,
+                                                         const int64_t* __restrict__ indices,
+                                                         int64_t n_sets,
+                                                         double* __restrict__ partial) {
+  constexpr int NA = MomTraits<MS>::kArrays;
+  constexpr int NM = MomTraits<MS>::kMoments;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t set = warp_global; set < n_sets; set += n_warps) {
+    const int64_t* idx = indices + set * n_rows;
+    double acc[NM];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) acc[m] = 0.0;
+    for (int64_t j = lane; j < n_rows; j += 32) {
+      const int64_t i = idx[j];
+      double v[NA], c[NM];
+      v[0] = d0[i];
+      if (NA == 2) v[NA - 1] = d1[i];
+      contribution<MS>(v, c);
+#pragma unroll
+      for (int m = 0; m < NM; ++m) acc[m] += c[m];
+    }
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      const double tot = warp_sum(acc[m]);
+      if (lane == 0) partial[(int64_t)m * n_sets + set] = tot;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K2 --------
+// Writes the canonical index array of each resample: cells in order, inside a
+// cell the draws in stream-position order — exactly what K1 consumes.
+__global__ void __launch_bounds__(256) k2_fill_indices_kernel(Plan plan, uint64_t seed,
+                                                              int64_t resample_lo, int64_t n_local,
+                                                              const int32_t* __restrict__ counts,
+                                                              int64_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t rl = warp_global; rl < n_local; rl += n_warps) {
+    int64_t* row = out + rl * plan.n_rows;
+    int64_t offset = 0;
+    for (int64_t t = 0; t < plan.n_tiles; ++t) {
+      const int64_t n = counts ? (int64_t)counts[t * n_local + rl] : plan.n_rows;
+      const int64_t sz = plan.cell_size(t);
+      const int64_t row0 = t < plan.n_full ? (t << plan.log2_tile) : (plan.n_full << plan.log2_tile);
+      const Stream st = make_stream(seed, resample_lo + rl, (uint32_t)t, kPurposeIndex);
+      auto put = [&](int, int64_t pos, uint32_t idx) { row[offset + pos] = row0 + (int64_t)idx; };
+      if (t < plan.n_full) {
+        const uint32_t nblk = (uint32_t)((n + 7) / 8);
+        for (uint32_t q = lane; q < nblk; q += 32) pow2_block<true>(st, q, (uint32_t)sz - 1u, n, put);
+      } else {
+        const uint32_t nblk = (uint32_t)((n + 3) / 4);
+        const uint32_t thresh = lemire_threshold((uint32_t)sz);
+        for (uint32_t q = lane; q < nblk; q += 32)
+          lemire_block<true>(st, q, (uint32_t)sz, thresh, n, put);
+      }
+      offset += n;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ data,
+                                                     const int64_t* __restrict__ idx, int64_t n_idx,
+                                                     double* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_idx; i += stride)
+    out[i] = data[idx[i]];
+}
+
+}  // namespace b200boot

@@ -1,0 +1,219 @@
+// K4 (count reduction), K5 (radix-descent order-statistic select) and the
+// column sort used only for return_dist=True.
+//
+// Replace, in /root/reference/src/scikits/bootstrap/bootstrap.py:
+//   :583       np.sum(stat < ostat, axis=0)              -> K4
+//   :861-866   np.mean([compfunction(s) ...], axis=0)     -> K4
+//   :445 + :485-490  stat.sort(axis=0); stat[nvals]       -> K5 (no sort)
+//   :445 with return_dist                                  -> sort_columns
+// Statistic vectors are column-major: stat[d * n + r].
+#pragma once
+#include "common.cuh"
+
+namespace b200boot {
+
+// Order-preserving map double -> uint64 (ascending; every NaN maps above +inf,
+// matching numpy's "NaNs sort last").
+__device__ __forceinline__ uint64_t key_of(double x) {
+  uint64_t b = (uint64_t)__double_as_longlong(x);
+  if (x != x) b = 0x7FF8000000000000ull;   // canonical +NaN
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double value_of(uint64_t k) {
+  const uint64_t b = (k & 0x8000000000000000ull) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+// ------------------------------------------------------------------ K4 --------
+__global__ void __launch_bounds__(256) k4_count_kernel(const double* __restrict__ stat, int64_t n,
+                                                       int op, const double* __restrict__ t0,
+                                                       const double* __restrict__ t1,
+                                                       unsigned long long* __restrict__ counts) {
+  const int64_t d = blockIdx.y;
+  const double* col = stat + d * n;
+  const double a = t0[d];
+  const double b = t1 ? t1[d] : 0.0;
+  unsigned int local = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    const double s = col[r];
+    bool hit;
+    switch (op) {
+      case B200BOOT_CMP_LT: hit = s < a; break;
+      case B200BOOT_CMP_LE: hit = s <= a; break;
+      case B200BOOT_CMP_GT: hit = s > a; break;
+      case B200BOOT_CMP_GE: hit = s >= a; break;
+      default: hit = (a <= s) && (s <= b); break;
+    }
+    local += hit ? 1u : 0u;
+  }
+  local = __reduce_add_sync(0xffffffffu, local);
+  __shared__ unsigned int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&s_cnt, local);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_cnt) atomicAdd(counts + d, (unsigned long long)s_cnt);
+}
+
+// ------------------------------------------------------------------ K5 --------
+// State per select (alpha a, column d), index a * n_cols + d:
+//   prefix : key bits fixed so far (MSB first), krem : rank inside that bucket.
+// Pass p (0..7) histograms byte (7 - p) of the keys whose higher bytes equal
+// the prefix; pick() walks the 256 bins and descends.
+constexpr int kSelMaxAlphas = 8;   // per launch; the host loops for more
+
+struct SelectState {
+  uint64_t* prefix;   // [A * D]
+  int64_t* krem;      // [A * D]
+  int64_t* hist;      // [A * D * 256]
+};
+
+inline size_t select_ws_bytes(int n_alphas, int64_t n_cols) {
+  const size_t ad = (size_t)n_alphas * (size_t)n_cols;
+  return pad256(ad * 8) + pad256(ad * 8) + pad256(ad * 256 * 8);
+}
+inline SelectState select_carve(Carver& cv, int n_alphas, int64_t n_cols) {
+  const size_t ad = (size_t)n_alphas * (size_t)n_cols;
+  SelectState s;
+  s.prefix = cv.take<uint64_t>(ad);
+  s.krem = cv.take<int64_t>(ad);
+  s.hist = cv.take<int64_t>(ad * 256);
+  return s;
+}
+
+__global__ void __launch_bounds__(256) k5_begin_kernel(const int64_t* __restrict__ ranks, int64_t ad,
+                                                       SelectState st) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ad) {
+    st.prefix[i] = 0;
+    st.krem[i] = ranks[i];
+  }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = i; j < ad * 256; j += stride) st.hist[j] = 0;
+}
+
+__global__ void __launch_bounds__(256) k5_hist_kernel(const double* __restrict__ stat, int64_t n,
+                                                      int64_t n_cols, int a_lo, int a_cnt, int pass,
+                                                      SelectState st) {
+  __shared__ unsigned int s_hist[kSelMaxAlphas][256];
+  __shared__ uint64_t s_prefix[kSelMaxAlphas];
+  const int64_t d = blockIdx.y;
+  for (int i = threadIdx.x; i < a_cnt * 256; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+  if (threadIdx.x < a_cnt) s_prefix[threadIdx.x] = st.prefix[(int64_t)(a_lo + threadIdx.x) * n_cols + d];
+  __syncthreads();
+  const int shift = 56 - 8 * pass;
+  const double* col = stat + d * n;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    const uint64_t k = key_of(col[r]);
+    const unsigned int digit = (unsigned int)(k >> shift) & 0xFFu;
+    for (int a = 0; a < a_cnt; ++a) {
+      const bool match = pass == 0 || ((k ^ s_prefix[a]) >> (shift + 8)) == 0;
+      if (match) atomicAdd(&s_hist[a][digit], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a_cnt * 256; i += blockDim.x) {
+    const unsigned int v = (&s_hist[0][0])[i];
+    if (v) {
+      const int a = i >> 8, bin = i & 255;
+      atomicAdd(reinterpret_cast<unsigned long long*>(
+                    st.hist + ((int64_t)(a_lo + a) * n_cols + d) * 256 + bin),
+                (unsigned long long)v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k5_pick_kernel(int64_t ad, int pass, SelectState st) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ad) return;
+  int64_t* h = st.hist + i * 256;
+  int64_t k = st.krem[i];
+  int digit = 255;
+  int64_t below = 0;
+  for (int b = 0; b < 256; ++b) {
+    const int64_t c = h[b];
+    if (k < below + c) {
+      digit = b;
+      break;
+    }
+    below += c;
+  }
+  for (int b = 0; b < 256; ++b) h[b] = 0;   // ready for the next pass
+  st.krem[i] = k - below;
+  st.prefix[i] |= (uint64_t)digit << (56 - 8 * pass);
+}
+
+__global__ void __launch_bounds__(256) k5_end_kernel(int64_t ad, SelectState st,
+                                                     double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ad) out[i] = value_of(st.prefix[i]);
+}
+
+// ------------------------------------------------------------------ sort ------
+// Bitonic network over keys padded to a power of two with the maximum key.
+__global__ void __launch_bounds__(256) sort_load_kernel(const double* __restrict__ stat, int64_t n,
+                                                        int64_t n_pad, uint64_t* __restrict__ keys) {
+  const int64_t d = blockIdx.y;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride)
+    keys[d * n_pad + i] = i < n ? key_of(stat[d * n + i]) : ~0ull;
+}
+__global__ void __launch_bounds__(256) sort_step_kernel(uint64_t* __restrict__ keys, int64_t n_pad,
+                                                        int64_t j, int64_t k) {
+  const int64_t d = blockIdx.y;
+  uint64_t* col = keys + d * n_pad;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+    const int64_t partner = i ^ j;
+    if (partner > i) {
+      const uint64_t a = col[i], b = col[partner];
+      const bool ascending = (i & k) == 0;
+      if ((a > b) == ascending) {
+        col[i] = b;
+        col[partner] = a;
+      }
+    }
+  }
+}
+// All steps with j < 1024 of one k-stage (and whole stages with k <= 1024) inside
+// shared memory: one 2048-key segment per CTA.
+__global__ void __launch_bounds__(1024) sort_local_kernel(uint64_t* __restrict__ keys, int64_t n_pad,
+                                                          int64_t k_first, int64_t k_last,
+                                                          int64_t j_first) {
+  __shared__ uint64_t s[2048];
+  const int64_t d = blockIdx.y;
+  uint64_t* col = keys + d * n_pad + (int64_t)blockIdx.x * 2048;
+  const int64_t seg0 = (int64_t)blockIdx.x * 2048;
+  const int64_t seg_n = min((int64_t)2048, n_pad);
+  for (int i = threadIdx.x; i < seg_n; i += 1024) s[i] = col[i];
+  __syncthreads();
+  for (int64_t k = k_first; k <= k_last; k <<= 1) {
+    const int64_t j0 = (k == k_first) ? j_first : (k >> 1);
+    for (int64_t j = j0; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < seg_n; i += 1024) {
+        const int partner = i ^ (int)j;
+        if (partner > i) {
+          const uint64_t a = s[i], b = s[partner];
+          const bool ascending = ((seg0 + i) & k) == 0;
+          if ((a > b) == ascending) {
+            s[i] = b;
+            s[partner] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < seg_n; i += 1024) col[i] = s[i];
+}
+__global__ void __launch_bounds__(256) sort_store_kernel(const uint64_t* __restrict__ keys, int64_t n,
+                                                         int64_t n_pad, double* __restrict__ stat) {
+  const int64_t d = blockIdx.y;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    stat[d * n + i] = value_of(keys[d * n_pad + i]);
+}
+
+}  // namespace b200boot

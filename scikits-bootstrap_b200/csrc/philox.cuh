@@ -1,0 +1,85 @@
+// Philox4x32-10 counter-based generator (Salmon, Moraes, Dror, Shaw; SC'11) and
+// the counter layout every kernel shares.  Host+device so the CPU test-suite can
+// exercise the very same code (b200boot_host_* probes).
+//
+// Replaces numpy's PCG64 stream behind rng.integers at
+// /root/reference/src/scikits/bootstrap/bootstrap.py:677-680: the index of
+// (resample r, cell t, position p) is a pure function of (seed, r, t, p), so any
+// shard of the resample range reproduces the same values on any GPU count.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define B2_HD __host__ __device__ __forceinline__
+#else
+#define B2_HD inline
+#endif
+
+namespace b200boot {
+
+constexpr uint32_t kPhiloxM0 = 0xD2511F53u;
+constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
+constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
+constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
+
+// counter word 3 carries a purpose tag so the streams never overlap
+constexpr uint32_t kPurposeIndex = 0u;     // index words
+constexpr uint32_t kPurposeRedraw = 1u;    // Lemire rejection redraws
+constexpr uint32_t kPurposeBinomial = 2u;  // tile-occupancy uniforms
+
+struct Words4 {
+  uint32_t w[4];
+};
+
+B2_HD Words4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                           uint32_t k1) {
+#pragma unroll
+  for (int round = 0; round < 10; ++round) {
+    const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
+    const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+    k0 += kPhiloxW0;
+    k1 += kPhiloxW1;
+  }
+  Words4 r;
+  r.w[0] = c0;
+  r.w[1] = c1;
+  r.w[2] = c2;
+  r.w[3] = c3;
+  return r;
+}
+
+// Per-(resample, cell) stream descriptor.
+//   key = (seed lo, seed hi)
+//   c0  = block index inside the stream        c1 = cell id
+//   c2  = resample id (low 32)                 c3 = resample id bits 32..47 | purpose << 16
+struct Stream {
+  uint32_t k0, k1, c1, c2, c3;
+};
+
+B2_HD Stream make_stream(uint64_t seed, int64_t resample, uint32_t cell, uint32_t purpose) {
+  Stream s;
+  s.k0 = (uint32_t)seed;
+  s.k1 = (uint32_t)(seed >> 32);
+  s.c1 = cell;
+  s.c2 = (uint32_t)resample;
+  s.c3 = ((uint32_t)((uint64_t)resample >> 32) & 0xFFFFu) | (purpose << 16);
+  return s;
+}
+
+B2_HD Words4 stream_block(const Stream& s, uint32_t block) {
+  return philox4x32_10(block, s.c1, s.c2, s.c3, s.k0, s.k1);
+}
+
+// 53-bit uniform in the open interval (0,1) from two words.
+B2_HD double uniform53(uint32_t hi, uint32_t lo) {
+  const uint64_t m = ((uint64_t)(hi >> 5) << 26) | (uint64_t)(lo >> 6);
+  return ((double)m + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+}  // namespace b200boot

@@ -1,0 +1,469 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Parity has two legs:
+  (i)  index-supplied mode (K1i): the GPU consumes the REFERENCE's own PCG64 index
+       arrays; gathers are bit-exact, statistics agree to 1e-12 relative and the
+       interval endpoints reproduce the reference's golden values;
+  (ii) fused mode (K1): the GPU's own Philox draws, materialised by K2, are fed to
+       the oracle; statistics agree to 1e-12 and endpoints are identical.
+Tolerance: bit-exact for indices/gathers/counts/order statistics; 1e-12 relative
+for FP64 statistics (north_star)."""
+import functools
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_array_equal
+
+import bootstrap_oracle as orc
+import scikits_bootstrap_b200 as boot
+from cases import CASES, DATA20, SEED, STATS, gen_data
+from scikits_bootstrap_b200 import _abi, _device
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+X = [1, 2, 3, 4, 5, 6]
+Y = [2, 1, 2, 5, 1, 2]
+Z = [2, 1, 1, -1, -1, -4, -8]
+
+DEVICE_STATS = {
+    "mean": np.mean, "average": np.average, "var": np.var, "std": np.std, "median": np.median,
+    "ratio_of_means": boot.ratio_of_means, "weighted_average": boot.weighted_average,
+    "pearson_r": boot.pearson_r, "median_axis0": boot.median_axis0, "mean_axis0": boot.mean_axis0,
+    "diff_of_means": boot.diff_of_means,
+}
+JACK = {
+    "mean": orc.jack_mean, "average": orc.jack_mean, "var": orc.jack_var,
+    "std": lambda x: orc.jack_var(x, True), "ratio_of_means": orc.jack_ratio_of_means,
+    "weighted_average": orc.jack_weighted_average, "pearson_r": orc.jack_pearson,
+    "median": orc.jack_median,
+}
+
+
+def torch():
+    import torch as t
+    return t
+
+
+def dev(x, dtype=None):
+    t = torch().as_tensor(np.ascontiguousarray(x)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+def pcg_indices(n, n_samples, seed=SEED):
+    return np.array(list(orc.bootstrap_indices_pcg64(n, n_samples, seed)))
+
+
+# ------------------------------------------------------------------ gathers ------
+
+def test_gather_is_bit_exact():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(100003)
+    x[:4] = [0.0, -0.0, np.inf, 5e-324]
+    idx = rng.integers(0, len(x), 500000)
+    got = _device.gather(dev(x), dev(idx)).cpu().numpy()
+    assert_array_equal(got.view(np.uint64), x[idx].view(np.uint64))
+
+
+# ------------------------------------------------------------------ leg (i) ------
+
+def test_reference_goldens_in_index_supplied_mode():
+    """tests/bootstrap_test.py:163-169, 205-209, 357-363 with the reference's indices."""
+    idx = pcg_indices(20, 10000)
+    r = boot.ci_indexed(DATA20, np.average, idx, alpha=(0.1, 0.2, 0.8, 0.9), method="pi")
+    assert_allclose(r, [0.401879, 0.517506, 0.945416, 1.052798], rtol=1e-6)
+    r = boot.ci_indexed(DATA20, None, idx, alpha=(0.1, 0.2, 0.8, 0.9))
+    assert_allclose(r, [0.386674, 0.506714, 0.935628, 1.039683], rtol=1e-6)
+    r = boot.ci_indexed(DATA20, None, pcg_indices(20, 500), alpha=(0.1, 0.2, 0.8, 0.9))
+    assert_allclose(r, [0.37248, 0.507976, 0.92783, 1.039755], rtol=1e-6)
+
+
+def test_reference_pval_goldens_in_index_supplied_mode():
+    """tests/bootstrap_test.py:396-411."""
+    r = boot.pval_indexed(DATA20, compfunction=lambda s: 0.8 <= s <= 1.2, indices=pcg_indices(20, 500))
+    assert_allclose(r, 0.368)
+    r = boot.pval_indexed(DATA20, compfunction=boot.between(0.8, 1.2), indices=pcg_indices(20, 500))
+    assert_allclose(r, 0.368)
+    r = boot.pval_indexed(Z, indices=pcg_indices(7, 500))
+    assert_allclose(r, 0.096)
+
+
+MOMENT_CASES = [c for c in CASES if c[2] in ("mean", "average", "var", "std", "ratio_of_means",
+                                             "weighted_average", "pearson_r")]
+
+
+@pytest.mark.parametrize("case", MOMENT_CASES, ids=[c[0] for c in MOMENT_CASES])
+def test_index_supplied_matches_reference_fixture(case, golden):
+    name, spec, stat, multi, n, alphas = case
+    tdata = gen_data(spec)
+    data = tdata if multi else tdata[0]
+    f = DEVICE_STATS[stat]
+    idx = pcg_indices(len(tdata[0]), n)
+    for method in ("pi", "bca"):
+        out, dist = boot.ci_indexed(data, f, idx, alpha=alphas, method=method, multi=multi,
+                                    return_dist=True)
+        assert_allclose(dist, golden[f"{name}/dist"], rtol=RTOL, atol=1e-15)
+        assert_allclose(out, golden[f"{name}/{method}/lowhigh"], rtol=RTOL, atol=1e-15)
+        eb = boot.ci_indexed(data, f, idx, alpha=alphas, method=method, multi=multi, output="errorbar")
+        assert eb.shape == golden[f"{name}/{method}/errorbar"].shape
+        assert_allclose(eb, golden[f"{name}/{method}/errorbar"], rtol=1e-9, atol=1e-13)
+    assert_allclose(boot.pval_indexed(data, f, indices=idx, multi=bool(multi)), golden[f"{name}/pval"])
+
+
+# ------------------------------------------------------------------ K2 / K0 ------
+
+@pytest.mark.parametrize("n", [1, 5, 20, 1000, 28672])
+def test_device_indices_match_oracle_single_cell(n):
+    got = np.array(list(boot.bootstrap_indices(np.zeros(n), 37, seed=SEED)))
+    assert got.shape == (37, n) and got.dtype == np.int64
+    for r in (0, 1, 36):
+        assert_array_equal(got[r], orc.device_indices(SEED, r, n, 14))
+
+
+@pytest.mark.parametrize("n,n_arrays", [(40000, 1), (100000, 1), (20000, 2), (16384 * 2, 1)])
+def test_device_indices_match_oracle_tiled(n, n_arrays):
+    plan = _abi.make_plan(n, n_arrays)
+    counts = _device.tile_counts(9, n, n_arrays, 0, 16).cpu().numpy()       # [n_tiles][16]
+    assert (counts.sum(axis=0) == n).all()
+    got = _device.fill_indices(9, n, n_arrays, 0, 16).cpu().numpy()
+    for r in (0, 7, 15):
+        want = orc.device_indices(9, r, n, plan.log2_tile, counts=list(counts[:, r]), n_arrays=n_arrays)
+        assert_array_equal(got[r], want)
+    # host probe (same sources, host libm) normally gives the same occupancies
+    host = np.empty(plan.n_tiles, dtype=np.int32)
+    same = 0
+    for r in range(16):
+        _abi.check(_abi.lib().b200boot_host_tile_counts(9, n, n_arrays, r, host.ctypes.data))
+        same += int((host == counts[:, r]).all())
+    assert same >= 12
+
+
+def test_indices_do_not_depend_on_the_shard():
+    n = 50000
+    full = _device.fill_indices(5, n, 1, 0, 24).cpu().numpy()
+    part = np.concatenate([_device.fill_indices(5, n, 1, lo, hi).cpu().numpy()
+                           for lo, hi in [(0, 5), (5, 6), (6, 24)]])
+    assert_array_equal(full, part)
+
+
+def test_tile_counts_multinomial_on_device():
+    n, m = 10**7, 512
+    cnt = _device.tile_counts(1, n, 1, 0, m).cpu().numpy().astype(float)     # [611][m]
+    assert (cnt.sum(axis=0) == n).all()
+    sizes = np.array([16384] * 610 + [5760])
+    z = (cnt.mean(axis=1) - sizes) / np.sqrt(sizes * (1 - sizes / n) / m)
+    assert np.abs(z).max() < 5.5
+    assert abs(z.std() - 1) < 0.15
+
+
+# ------------------------------------------------------------------ leg (ii) -----
+
+def fused_vs_oracle(tdata, stat_name, n_samples, seed, multi=None, alphas=(0.025, 0.975)):
+    f = DEVICE_STATS[stat_name]
+    data = tdata if multi else tdata[0]
+    idx = np.array(list(boot.bootstrap_indices(tdata[0], n_samples, seed=seed, n_arrays=len(tdata))))
+    want = orc.stat_over_indices(tdata, STATS[stat_name], idx)
+    want.sort(axis=0)
+    for method in ("pi", "bca"):
+        out, dist = boot.ci(data, f, alpha=alphas, n_samples=n_samples, method=method, multi=multi,
+                            seed=seed, return_dist=True)
+        assert_allclose(dist, want, rtol=RTOL, atol=1e-15)
+        jstat = JACK[stat_name](*tdata)
+        ref = orc.ci_from_indices(tdata, STATS[stat_name], idx, alphas, n_samples, method,
+                                  jstat=jstat)
+        assert_allclose(out, ref, rtol=RTOL, atol=1e-15)
+
+
+@pytest.mark.parametrize("stat_name", ["mean", "var", "std"])
+@pytest.mark.parametrize("n", [20, 1000, 28672, 40000])
+def test_fused_single_array(stat_name, n):
+    x = np.random.default_rng(n).standard_normal(n) + 0.5
+    fused_vs_oracle((x,), stat_name, 400, seed=n + 1)
+
+
+@pytest.mark.parametrize("stat_name", ["ratio_of_means", "weighted_average", "pearson_r"])
+@pytest.mark.parametrize("n", [50, 3000, 14336, 30000])
+def test_fused_paired(stat_name, n):
+    rng = np.random.default_rng(n)
+    a = rng.gamma(2, 1, n)
+    b = 0.5 * a + rng.gamma(3, 1, n)
+    fused_vs_oracle((a, b), stat_name, 400, seed=n + 2, multi="paired")
+
+
+def test_fused_odd_sizes_and_unaligned_views():
+    """Remainder cells of odd length and 8-byte-aligned (not 16) device views take
+    the non-TMA load path; results must not change."""
+    base = np.random.default_rng(3).standard_normal(70001)
+    for n in (16385 + 28672, 32769, 70000):
+        x = base[1:1 + n]
+        want = boot.ci(x.copy(), np.mean, n_samples=300, seed=4, return_dist=True)[1]
+        view = dev(base)[1:1 + n]                      # data_ptr is 8 mod 16
+        assert view.data_ptr() % 16 == 8
+        got = boot.ci(view, np.mean, n_samples=300, seed=4, return_dist=True)[1]
+        assert_array_equal(got, want)
+
+
+def test_cfg1_matches_oracle_end_to_end():
+    """BASELINE cfg1: N=1000 f64, np.mean, BCa, n_samples=10000, seed=0."""
+    x = np.random.default_rng(0).standard_normal(1000)
+    fused_vs_oracle((x,), "mean", 10000, seed=0)
+    # statistical agreement with the reference's PCG64 answer [-0.10978462, 0.01280137]
+    out = boot.ci(x, np.mean, method="bca", n_samples=10000, seed=0)
+    se = x.std() / np.sqrt(1000)
+    assert_allclose(out, [-0.10978462, 0.01280137], atol=0.15 * se)
+
+
+# ------------------------------------------------------------------ K3 -----------
+
+@pytest.mark.parametrize("stat_name", ["mean", "var", "std", "ratio_of_means", "weighted_average",
+                                       "pearson_r"])
+@pytest.mark.parametrize("n", [5, 301, 5000])
+def test_jackknife_closed_form(stat_name, n):
+    rng = np.random.default_rng(n)
+    a = rng.gamma(2, 1, n)
+    b = 0.3 * a + rng.gamma(3, 1, n)
+    tdata = (a, b) if DEVICE_STATS[stat_name] in (boot.ratio_of_means, boot.weighted_average,
+                                                  boot.pearson_r) else (a,)
+    spec = boot._registry.require(DEVICE_STATS[stat_name])
+    out = _device.jackknife([dev(t) for t in tdata], spec.stat_id).cpu().numpy()
+    jstat = JACK[stat_name](*tdata)
+    d = jstat.mean() - jstat
+    assert_allclose(out[0], STATS[stat_name](*tdata), rtol=1e-12)
+    assert_allclose(out[1], jstat.mean(), rtol=1e-12)
+    assert_allclose(out[2], np.sum(d ** 2), rtol=1e-7)
+    assert_allclose(out[4], orc.acceleration(jstat), rtol=1e-6, atol=1e-12)
+    if n <= 301:   # and against the reference's O(N^2) loop itself
+        loop = orc.jackknife_stats_loop(tdata, STATS[stat_name])
+        assert_allclose(out[4], orc.acceleration(loop), rtol=1e-6, atol=1e-12)
+
+
+# ------------------------------------------------------------------ K4 / K5 / sort
+
+def _stat_matrix(n_cols, n, seed=0):
+    rng = np.random.default_rng(seed)
+    m = rng.standard_normal((n_cols, n))
+    m[0, : n // 3] = np.round(m[0, : n // 3], 1)          # ties
+    if n > 10:
+        m[-1, 3] = np.nan
+        m[-1, 5] = -0.0
+        m[-1, 6] = 0.0
+        m[-1, 7] = np.inf
+        m[-1, 8] = -np.inf
+    return m
+
+
+@pytest.mark.parametrize("n_cols,n", [(1, 1), (1, 10), (1, 100000), (3, 4097), (70, 1000)])
+def test_select_equals_sorted_pick(n_cols, n):
+    m = _stat_matrix(n_cols, n)
+    srt = np.sort(m, axis=1)
+    rng = np.random.default_rng(1)
+    for n_alphas in (1, 2, 11):
+        ranks = rng.integers(0, n, (n_alphas, n_cols))
+        ranks[0, 0] = 0
+        ranks[-1, -1] = n - 1
+        got = _device.Select(dev(m), dev(ranks)).run().cpu().numpy()
+        want = np.stack([srt[np.arange(n_cols), ranks[a]] for a in range(n_alphas)])
+        assert_array_equal(np.isnan(got), np.isnan(want))
+        ok = ~np.isnan(want)
+        assert_array_equal(got[ok], want[ok])
+
+
+def test_select_with_allreduce_hook_emulating_two_ranks():
+    """Sharded select: histograms of two shards are summed between hist and pick."""
+    m = _stat_matrix(2, 9000)
+    ranks = np.array([[0, 10], [4500, 8999], [123, 7777]])
+    srt = np.sort(m, axis=1)
+    a, b = dev(m[:, :4000].copy()), dev(m[:, 4000:].copy())
+    sa, sb = _device.Select(a, dev(ranks)), _device.Select(b, dev(ranks))
+    L, s = _abi.lib(), _device.stream_ptr()
+    for sel in (sa, sb):
+        _abi.check(L.b200boot_select_begin(sel.ranks.data_ptr(), 3, 2, sel.ws, sel.wsz, s))
+    for p in range(8):
+        for sel in (sa, sb):
+            _abi.check(L.b200boot_select_hist(sel.stat.data_ptr(), sel.n_local, 2, 3, p, sel.ws, sel.wsz, s))
+        tot = sa.hist_tensor() + sb.hist_tensor()
+        sa.hist_tensor().copy_(tot)
+        sb.hist_tensor().copy_(tot)
+        for sel in (sa, sb):
+            _abi.check(L.b200boot_select_pick(3, 2, p, sel.ws, sel.wsz, s))
+    out = torch().empty((3, 2), dtype=torch().float64, device="cuda")
+    _abi.check(L.b200boot_select_end(3, 2, out.data_ptr(), sa.ws, sa.wsz, s))
+    want = np.stack([srt[np.arange(2), ranks[k]] for k in range(3)])
+    assert_array_equal(out.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("op,fn", [(0, np.less), (1, np.less_equal), (2, np.greater), (3, np.greater_equal)])
+def test_count_reduction(op, fn):
+    m = _stat_matrix(5, 33333)
+    t0 = np.array([0.0, 0.1, -0.5, 3.0, 0.0])
+    got = _device.count(dev(m), op, dev(t0)).cpu().numpy()
+    with np.errstate(invalid="ignore"):
+        assert_array_equal(got, fn(m, t0[:, None]).sum(axis=1))
+    got = _device.count(dev(m), 4, dev(t0 - 0.3), dev(t0 + 0.3)).cpu().numpy()
+    with np.errstate(invalid="ignore"):
+        assert_array_equal(got, ((m >= (t0 - 0.3)[:, None]) & (m <= (t0 + 0.3)[:, None])).sum(axis=1))
+
+
+@pytest.mark.parametrize("n_cols,n", [(1, 2), (1, 1000), (1, 2048), (1, 2049), (2, 100000), (9, 5000)])
+def test_sort_columns(n_cols, n):
+    m = _stat_matrix(n_cols, n, seed=2)
+    got = _device.sort_columns(dev(m)).cpu().numpy()
+    want = np.sort(m, axis=1)
+    assert_array_equal(np.isnan(got), np.isnan(want))
+    assert_array_equal(got[~np.isnan(want)], want[~np.isnan(want)])
+
+
+# ------------------------------------------------------------------ API behaviour -
+
+def test_reference_property_tests():
+    """Seed-independent properties from tests/bootstrap_test.py:171-195, 365-370."""
+    out, dist = boot.ci(DATA20, return_dist=True, method="pi", alpha=[0.1, 0.9], n_samples=100)
+    assert out[0] == dist[10] and out[1] == dist[89]
+    assert_allclose(boot.ci(DATA20, seed=SEED), boot.ci(DATA20, alpha=(0.025, 1 - 0.025), seed=SEED))
+    assert_allclose(boot.ci(DATA20, method="pi", seed=SEED),
+                    boot.ci(DATA20, method="pi", alpha=(0.025, 1 - 0.025), seed=SEED))
+    a = boot.ci(DATA20, seed=SEED)
+    b = boot.ci(DATA20, output="errorbar", seed=SEED)
+    assert b.shape == (2, 1)
+    assert_allclose(b.T, abs(np.average(DATA20) - a)[np.newaxis])
+
+
+def test_warnings_match_reference():
+    """tests/bootstrap_test.py:250-260."""
+    with pytest.warns(boot.InstabilityWarning, match="(NaN|all equal)"):
+        boot.ci(np.ones(20), seed=SEED)
+    with pytest.warns(boot.InstabilityWarning, match="extremal"):
+        boot.ci([1, 2], n_samples=10, seed=SEED)
+    with pytest.warns(boot.InstabilityWarning, match="top 10"):
+        boot.ci(np.arange(1, 20), n_samples=50, seed=SEED)
+
+
+def test_input_forms_agree():
+    import pandas as pd
+    x = DATA20
+    want = boot.ci(x, np.mean, seed=5, n_samples=2000)
+    assert_array_equal(boot.ci(list(x), np.mean, seed=5, n_samples=2000), want)
+    assert_array_equal(boot.ci(pd.Series(x, index=np.arange(50, 70)), np.mean, seed=5, n_samples=2000), want)
+    assert_array_equal(boot.ci(torch().as_tensor(x), np.mean, seed=5, n_samples=2000), want)
+    assert_array_equal(boot.ci(dev(x), np.mean, seed=5, n_samples=2000), want)
+    assert_array_equal(boot.ci(x, np.mean, seed=np.random.default_rng(1), n_samples=2000),
+                       boot.ci(x, np.mean, seed=np.random.default_rng(1), n_samples=2000))
+    xi = np.arange(1, 20)                      # integer input -> float64 statistic
+    assert boot.ci(xi, np.mean, seed=1, n_samples=500).dtype == np.float64
+    x32 = x.astype(np.float32)
+    assert_allclose(boot.ci(x32, np.mean, seed=5, n_samples=2000),
+                    boot.ci(x32.astype(np.float64), np.mean, seed=5, n_samples=2000))
+
+
+def test_paired_tuple_equals_axis0_columns():
+    """A (N, D) array under an axis-0 statistic shares one index set across columns
+    (bootstrap.py:431): each column equals the 1-D run with the same seed."""
+    rng = np.random.default_rng(8)
+    m = rng.standard_normal((64, 5))
+    for f, g in [(boot.mean_axis0, np.mean), (functools.partial(np.std, axis=0), np.std)]:
+        out, dist = boot.ci(m, f, alpha=(0.1, 0.9), n_samples=1500, seed=3, return_dist=True)
+        assert out.shape == (2, 5) and dist.shape == (1500, 5)
+        eb = boot.ci(m, f, alpha=(0.1, 0.9), n_samples=1500, seed=3, output="errorbar")
+        assert eb.shape == (5, 2)
+        for d in range(5):
+            o1, d1 = boot.ci(m[:, d], g, alpha=(0.1, 0.9), n_samples=1500, seed=3, return_dist=True)
+            assert_array_equal(out[:, d], o1)
+            assert_array_equal(dist[:, d], d1)
+
+
+def test_pval_device_and_host_criteria_agree():
+    x = np.array(Z, dtype=float)
+    p1 = boot.pval(x, n_samples=4000, seed=2)
+    p2 = boot.pval(x, compfunction=lambda s: s > 0, n_samples=4000, seed=2)
+    _, dist = boot.ci(x, np.average, method="pi", n_samples=4000, seed=2, return_dist=True)
+    assert p1 == p2 == np.mean(dist > 0)          # pval and ci share the stream
+    assert isinstance(p1, np.float64)
+    p3 = boot.pval(x, compfunction=boot.between(-2.0, -1.0), n_samples=4000, seed=2)
+    assert p3 == np.mean((dist >= -2.0) & (dist <= -1.0))
+
+
+def test_independent_mode():
+    """multi='independent' (bootstrap.py:438-444, 601-607) against the oracle on the
+    device's own per-array index streams."""
+    a = np.random.default_rng(20).gamma(2, 1, 60)
+    b = np.random.default_rng(21).gamma(3, 1, 45)
+    n = 1500
+    idx = list(boot.bootstrap_indices_independent((a, b), n, seed=11))
+    f = STATS["diff_of_means"]
+    for method in ("pi", "bca"):
+        want = orc.ci_from_indices((a, b), f, idx, (0.025, 0.975), n, method, multi="independent")
+        got = boot.ci((a, b), boot.diff_of_means, n_samples=n, multi="independent", seed=11, method=method)
+        assert_allclose(got, want, rtol=RTOL)
+    # statistical agreement with the reference golden (tests/bootstrap_test.py:240-248)
+    got = boot.ci((X, Z), boot.diff_of_means, n_samples=20000, multi="independent", seed=1)
+    assert_allclose(got, [2.547619, 7.97619], atol=0.25)
+
+
+# ------------------------------------------------------------------ sharding -----
+
+def test_shards_reproduce_the_single_gpu_statistics():
+    """Emulates 1/2/4/8 ranks on one GPU: the union of the shards' statistic vectors
+    is bit-identical to the unsharded vector."""
+    from scikits_bootstrap_b200 import _dist
+    x = dev(np.random.default_rng(1).standard_normal(100000) + 1.0)
+    n = 203
+    full = _device.resample_stat([x], _abi.STAT_MEAN, 42, 0, n).cpu().numpy()
+    for world in (2, 4, 8):
+        parts = []
+        for rank in range(world):
+            lo, hi = _dist.shard_range(n, rank, world)
+            parts.append(_device.resample_stat([x], _abi.STAT_MEAN, 42, lo, hi).cpu().numpy())
+        assert_array_equal(np.concatenate(parts), full)
+
+
+# ------------------------------------------------------------------ statistics ---
+
+def test_philox_path_agrees_statistically_with_pcg64_path():
+    """Two-sample KS between the device's bootstrap distribution and the oracle's
+    PCG64 one (the reference compares its own two generators at rtol=1e-2,
+    tests/bootstrap_test.py:51-58)."""
+    from scipy import stats as sps
+    x = np.random.default_rng(3).gamma(2.0, 1.0, 200)
+    n = 20000
+    _, d_gpu = boot.ci(x, np.mean, method="pi", n_samples=n, seed=1, return_dist=True)
+    d_ref = orc.stat_over_indices((x,), np.mean, orc.bootstrap_indices_pcg64(200, n, 2))
+    assert sps.ks_2samp(d_gpu, d_ref).pvalue > 1e-4
+    assert_allclose(boot.ci(x, np.mean, n_samples=n, seed=1), orc.ci(x, np.mean, n_samples=n, seed=2), rtol=1e-2)
+
+
+def test_coverage_of_the_tiled_path():
+    """Nominal 90 % percentile intervals for the mean cover the truth ~90 % of the
+    time when N spans several cells (tile-multinomial draws)."""
+    rng = np.random.default_rng(12)
+    hits, trials, n = 0, 120, 40000
+    for k in range(trials):
+        x = rng.standard_normal(n)
+        lo, hi = boot.ci(x, np.mean, alpha=0.1, method="pi", n_samples=400, seed=k)
+        hits += lo <= 0.0 <= hi
+    assert 0.80 <= hits / trials <= 0.97
+
+
+# ------------------------------------------------------------------ full size ----
+
+def test_full_size_properties_cfg5():
+    """BASELINE cfg5 shape (N=1e7) at a reduced resample count: size-independent
+    properties — affine equivariance of the mean under the same seed, the bootstrap
+    mean/variance identities, and shard independence."""
+    n, m = 10**7, 1024
+    x = np.random.default_rng(5).standard_normal(n) + 1.0
+    xd = dev(x)
+    s1 = _device.resample_stat([xd], _abi.STAT_MEAN, 7, 0, m).cpu().numpy()
+    s2 = _device.resample_stat([xd * 2.0 + 3.0], _abi.STAT_MEAN, 7, 0, m).cpu().numpy()
+    assert_allclose(s2, 2.0 * s1 + 3.0, rtol=1e-13)
+    se = x.std() / np.sqrt(n)
+    assert abs(s1.mean() - x.mean()) < 5 * se / np.sqrt(m)
+    assert abs(s1.std() / se - 1) < 0.12
+    part = _device.resample_stat([xd], _abi.STAT_MEAN, 7, 300, 420).cpu().numpy()
+    assert_array_equal(part, s1[300:420])
+    # materialised indices of one resample reproduce its statistic
+    idx = _device.fill_indices(7, n, 1, 5, 6).cpu().numpy()[0]
+    assert idx.min() >= 0 and idx.max() < n
+    assert_allclose(x[idx].mean(), s1[5], rtol=1e-12)
+    lo, hi = boot.ci(xd, np.mean, n_samples=m, seed=7)
+    assert lo < x.mean() < hi and (hi - lo) < 6 * se

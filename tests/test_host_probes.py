@@ -1,0 +1,212 @@
+"""CPU checks of the pieces that do not need a GPU: the C ABI surface, and the
+generator / sampler code the kernels share with the host probes
+(b200boot_host_*, compiled from the same __host__ __device__ sources)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+from scipy import stats as sps
+
+import bootstrap_oracle as orc
+import scikits_bootstrap_b200 as boot
+from scikits_bootstrap_b200 import _abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported_and_bound():
+    hdr = open(os.path.join(ROOT, "include", "b200boot.h")).read()
+    declared = set(re.findall(r"\b(b200boot_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"b200boot_status", "b200boot_stat", "b200boot_cmp", "b200boot_plan"}
+    assert len(declared) >= 20
+    assert declared == set(_abi.SIGNATURES), declared ^ set(_abi.SIGNATURES)
+    nm = subprocess.run(["nm", "-D", "--defined-only", _abi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (b200boot_[a-z0-9_]+)", nm))
+    assert declared <= exported, declared - exported
+    assert _abi.lib().b200boot_version() == 1
+
+
+def test_errors_do_not_cross_abi_as_exceptions():
+    L = _abi.lib()
+    assert L.b200boot_make_plan(0, 1, C.byref(_abi.Plan())) == -1
+    assert b"make_plan" in L.b200boot_last_error()
+    with pytest.raises(_abi.B200BootError):
+        _abi.check(L.b200boot_make_plan(-5, 1, C.byref(_abi.Plan())))
+
+
+def _philox(c, k):
+    out = (C.c_uint32 * 4)()
+    _abi.lib().b200boot_host_philox4x32((C.c_uint32 * 4)(*c), (C.c_uint32 * 2)(*k), out)
+    return list(out)
+
+
+def test_philox_kat_through_library():
+    assert _philox([0] * 4, [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert _philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert _philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        c = [int(v) for v in rng.integers(0, 2**32, 4)]
+        k = [int(v) for v in rng.integers(0, 2**32, 2)]
+        assert _philox(c, k) == [int(v) for v in orc.philox4x32_10(np.array([c], dtype=np.uint64), k)[0]]
+
+
+def _host_indices(seed, n, n_arrays, r):
+    out = np.empty(n, dtype=np.int64)
+    _abi.check(_abi.lib().b200boot_host_indices(seed, n, n_arrays, r, out.ctypes.data))
+    return out
+
+
+def _host_counts(seed, n, n_arrays, r):
+    p = _abi.make_plan(n, n_arrays)
+    out = np.empty(p.n_tiles, dtype=np.int32)
+    _abi.check(_abi.lib().b200boot_host_tile_counts(seed, n, n_arrays, r, out.ctypes.data))
+    return out
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 20, 1000, 28672])
+def test_single_cell_indices_match_oracle(n):
+    for seed, r in [(0, 0), (1234567890, 7), (2**63 + 5, 2**33 + 1)]:
+        got = _host_indices(seed, n, 1, r)
+        want = orc.device_indices(seed, r, n, 14)
+        np.testing.assert_array_equal(got, want)
+        assert got.min() >= 0 and got.max() < n
+
+
+def test_lemire_redraw_path_matches_oracle():
+    # size 3*2^30 rejects a word with probability 1/4: exercises the redraw stream
+    n = 3 << 30
+    hit = 0
+    for r in range(3):
+        want = orc.cell_draws_lemire(11, r, 0, 64, n)
+        # reproduce through the library one block at a time via philox probe
+        words = [w for q in range(16) for w in _philox([q, 0, r, 0], [11, 0])]
+        thresh = (1 << 32) % n
+        for p, w in enumerate(words):
+            if (w * n) & 0xFFFFFFFF < thresh:
+                hit += 1
+            else:
+                assert want[p] == (w * n) >> 32
+        assert want.min() >= 0 and want.max() < n
+    assert hit > 20
+
+
+@pytest.mark.parametrize("n,n_arrays", [(28673, 1), (40000, 1), (16384 * 3, 1), (20000, 2), (100000, 1)])
+def test_tiled_indices_match_oracle_given_counts(n, n_arrays):
+    plan = _abi.make_plan(n, n_arrays)
+    assert plan.n_tiles > 1
+    for seed, r in [(3, 0), (99, 12345)]:
+        counts = _host_counts(seed, n, n_arrays, r)
+        assert counts.sum() == n and (counts >= 0).all()
+        got = _host_indices(seed, n, n_arrays, r)
+        want = orc.device_indices(seed, r, n, plan.log2_tile, counts=list(counts), n_arrays=n_arrays)
+        np.testing.assert_array_equal(got, want)
+
+
+def test_plan_shapes():
+    p = _abi.make_plan(10**7, 1)
+    assert (p.log2_tile, p.n_full, p.rem, p.n_tiles) == (14, 610, 5760, 611)
+    p = _abi.make_plan(10**6, 2)
+    assert (p.log2_tile, p.n_full, p.rem, p.n_tiles) == (13, 122, 576, 123)
+    p = _abi.make_plan(1000, 1)
+    assert (p.n_full, p.rem, p.n_tiles) == (0, 1000, 1)
+    assert orc.tile_plan(10**7, 14) == [16384] * 610 + [5760]
+
+
+@pytest.mark.parametrize("n,p", [(10**7, 16384 / 10**7), (10**7, 0.5), (50000, 0.3), (1000, 0.003),
+                                 (40, 0.2), (100, 0.97), (17, 0.5), (10**6, 1 - 1e-5)])
+def test_binomial_sampler_distribution(n, p):
+    L = _abi.lib()
+    m = 20000
+    xs = np.array([L.b200boot_host_binomial(5, r, 3, n, p) for r in range(m)])
+    assert xs.min() >= 0 and xs.max() <= n
+    mean, var = n * p, n * p * (1 - p)
+    assert abs(xs.mean() - mean) < 5 * np.sqrt(var / m) + 1e-9
+    assert abs(xs.var() - var) < 6 * var * np.sqrt(2.0 / m) + 1e-9
+    # chi-square against the exact pmf on ~20 equiprobable bins
+    qs = np.unique(sps.binom.ppf(np.linspace(0, 1, 21)[1:-1], n, p))
+    edges = np.concatenate(([-0.5], qs + 0.5, [n + 0.5]))
+    obs = np.histogram(xs, bins=edges)[0]
+    cdf = sps.binom.cdf(np.floor(edges[1:-1]), n, p)
+    exp = np.diff(np.concatenate(([0.0], cdf, [1.0]))) * m
+    keep = exp > 5
+    chi2 = ((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum()
+    assert chi2 < sps.chi2.ppf(1 - 1e-6, max(keep.sum() - 1, 1))
+
+
+def test_tile_counts_are_multinomial():
+    n, m = 100000, 4000           # 6 full tiles of 16384 + remainder 1696
+    plan = _abi.make_plan(n, 1)
+    sizes = np.array([16384] * 6 + [1696])
+    assert plan.n_tiles == 7
+    cnt = np.array([_host_counts(21, n, 1, r) for r in range(m)], dtype=float)
+    assert (cnt.sum(axis=1) == n).all()
+    pr = sizes / n
+    z = (cnt.mean(axis=0) - n * pr) / np.sqrt(n * pr * (1 - pr) / m)
+    assert np.abs(z).max() < 5
+    # covariance of two cells: -n p_i p_j
+    cov = np.cov(cnt[:, 0], cnt[:, 1])[0, 1]
+    assert abs(cov - (-n * pr[0] * pr[1])) < 6 * n * pr[0] * (1 - pr[0]) / np.sqrt(m)
+
+
+def test_tiled_draws_are_uniform_over_rows():
+    n, m = 40000, 300             # 2 full tiles + remainder 7232
+    hist = np.zeros(n)
+    for r in range(m):
+        hist += np.bincount(_host_indices(77, n, 1, r), minlength=n)
+    chi2 = ((hist - m) ** 2 / m).sum()
+    assert abs(chi2 - (n - 1)) < 6 * np.sqrt(2 * (n - 1))
+    # cell boundaries carry no bias
+    for lo, hi in [(0, 16384), (16384, 32768), (32768, n)]:
+        share = hist[lo:hi].sum() / (n * m)
+        assert abs(share - (hi - lo) / n) < 5 * np.sqrt((hi - lo) / n / (n * m))
+
+
+def test_registry_and_errors_without_gpu():
+    import functools
+    from scikits_bootstrap_b200 import _registry as reg
+    assert reg.lookup(np.mean).stat_id == _abi.STAT_MEAN
+    assert reg.lookup(np.average).stat_id == _abi.STAT_MEAN
+    assert reg.lookup(functools.partial(np.median, axis=0)).axis0
+    assert reg.lookup(lambda x: x.mean()) is None
+    x = np.arange(10.0)
+    with pytest.raises(NotImplementedError, match="device statistic registry"):
+        boot.ci(x, lambda a: np.mean(a))
+    with pytest.raises(ValueError, match=r"Value `wrong` for multi is not recognized."):
+        boot.ci(x, multi="wrong")
+    with pytest.raises(ValueError, match=r"Method invalid is not supported"):
+        boot.ci(x, method="invalid")
+    with pytest.raises(ValueError, match=r"Output option invalid is not supported"):
+        boot.ci(x, output="invalid")
+    with pytest.raises(TypeError):
+        boot.ci(x, "average")
+    with pytest.raises(ValueError):
+        boot.ci(([1, 2, 3], [1, 2]), boot.ratio_of_means, multi="paired")
+    with pytest.raises(ValueError):
+        boot.ci(x, method="abc", return_dist=True)
+    with pytest.raises(NotImplementedError, match="not currently supported"):
+        boot.ci((x, x), multi="independent", method="abc")
+    with pytest.raises(NotImplementedError, match="Numba for independent data"):
+        boot.ci((x, x), multi="independent", use_numba=True)
+    with pytest.raises(ValueError, match="Numba can't be used"):
+        boot.ci(x, np.median, use_numba=True)
+    np.testing.assert_array_equal(np.array(list(boot.jackknife_indices(np.array([1, 2, 3])))),
+                                  [[1, 2], [0, 2], [0, 1]])     # bootstrap_test.py:110-112
+
+
+def test_interval_math_matches_oracle(golden):
+    from scikits_bootstrap_b200 import _interval as iv
+    np.testing.assert_array_equal(iv.nppf(golden["nppf/p"]), golden["nppf/val"])
+    np.testing.assert_array_equal(iv.ncdf(golden["ncdf/x"]), golden["ncdf/val"])
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        n = int(rng.integers(50, 5000))
+        av = rng.random((3, 4))
+        a, fa = iv.order_indices(av, n)
+        b, fb = orc.order_indices(av, n)
+        np.testing.assert_array_equal(a, b)
+        assert fa == fb
