@@ -335,8 +335,10 @@ def test_warnings_match_reference():
         boot.ci(np.ones(20), seed=SEED)
     with pytest.warns(boot.InstabilityWarning, match="extremal"):
         boot.ci([1, 2], n_samples=10, seed=SEED)
-    with pytest.warns(boot.InstabilityWarning, match="top 10"):
-        boot.ci(np.arange(1, 20), n_samples=50, seed=SEED)
+    with pytest.warns(boot.InstabilityWarning, match="top 10"):     # seed-independent under 'pi'
+        boot.ci(np.arange(1, 20), n_samples=50, seed=SEED, method="pi")
+    with pytest.warns(boot.InstabilityWarning, match="top 10"):     # the reference's own draws
+        boot.ci_indexed(np.arange(1, 20), None, pcg_indices(19, 50))
 
 
 def test_input_forms_agree():
