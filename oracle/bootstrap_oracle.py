@@ -520,3 +520,58 @@ def device_indices(seed: int, resample: int, n_obs: int, log2_tile: int,
             loc = cell_draws_lemire(seed, resample, cell_base + t, cnt, sz)
         parts.append(loc + t * m)
     return np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+
+
+# --------------------------------------------------------------------------
+# K5 restatement: exact k-th order statistic by an 8-pass MSB radix descent over
+# order-preserving uint64 keys (csrc/k45_interval.cuh).  Equivalent to
+# `stat.sort(axis=0); stat[k]` (bootstrap.py:445, 485-490); used to check the
+# device select and to drive the sharded protocol on CPU (gloo) in the tests.
+# --------------------------------------------------------------------------
+
+def radix_key(x: np.ndarray) -> np.ndarray:
+    x = np.asarray(x, dtype=np.float64)
+    b = x.view(np.uint64).copy()
+    b[np.isnan(x)] = np.uint64(0x7FF8000000000000)
+    neg = (b >> np.uint64(63)).astype(bool)
+    return np.where(neg, ~b, b | np.uint64(1 << 63))
+
+
+def radix_value(k: np.ndarray) -> np.ndarray:
+    k = np.asarray(k, dtype=np.uint64)
+    pos = (k >> np.uint64(63)).astype(bool)
+    b = np.where(pos, k & np.uint64((1 << 63) - 1), ~k)
+    return b.view(np.float64)
+
+
+class RadixSelectState:
+    """Host twin of the device select state for a single column."""
+
+    def __init__(self, local_values: np.ndarray, ranks: Sequence[int]):
+        self.keys = radix_key(local_values)
+        self.prefix = np.zeros(len(ranks), dtype=np.uint64)
+        self.krem = np.array(ranks, dtype=np.int64)
+        self.hist = np.zeros((len(ranks), 256), dtype=np.int64)
+
+    def do_hist(self, p: int) -> None:
+        shift = np.uint64(56 - 8 * p)
+        digit = ((self.keys >> shift) & np.uint64(0xFF)).astype(np.int64)
+        for a in range(len(self.krem)):
+            if p == 0:
+                m = np.ones(len(self.keys), dtype=bool)
+            else:
+                m = ((self.keys ^ self.prefix[a]) >> (shift + np.uint64(8))) == 0
+            self.hist[a] += np.bincount(digit[m], minlength=256)
+
+    def do_pick(self, p: int) -> None:
+        for a in range(len(self.krem)):
+            cum = np.cumsum(self.hist[a])
+            digit = int(np.searchsorted(cum, self.krem[a], side="right"))
+            digit = min(digit, 255)
+            below = cum[digit - 1] if digit > 0 else 0
+            self.krem[a] -= below
+            self.prefix[a] |= np.uint64(digit) << np.uint64(56 - 8 * p)
+        self.hist[:] = 0
+
+    def result(self) -> np.ndarray:
+        return radix_value(self.prefix)

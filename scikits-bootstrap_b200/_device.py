@@ -224,23 +224,28 @@ class Select:
         off = p.value - self._buf.data_ptr()
         return self._buf[off:off + n.value * 8].view(torch.int64)
 
-    def run(self, between=None):
+    def run(self, sharded: bool = False):
+        """sharded=False: one library call.  sharded=True: the same passes with the
+        histogram all-reduced across ranks between hist and pick (_dist)."""
+        from . import _dist
         torch = _torch()
         L, s = _abi.lib(), stream_ptr()
         out = torch.empty((self.n_alphas, self.n_cols), dtype=torch.float64, device=self.stat.device)
-        if between is None:
+        if not sharded:
             _abi.check(L.b200boot_select(self.stat.data_ptr(), self.n_local, self.n_cols, self.ranks.data_ptr(),
                                          self.n_alphas, out.data_ptr(), self.ws, self.wsz, s))
             return out
-        hist = self.hist_tensor()
-        _abi.check(L.b200boot_select_begin(self.ranks.data_ptr(), self.n_alphas, self.n_cols, self.ws, self.wsz, s))
-        for p in range(8):
-            _abi.check(L.b200boot_select_hist(self.stat.data_ptr(), self.n_local, self.n_cols, self.n_alphas, p,
-                                              self.ws, self.wsz, s))
-            between(hist)
-            _abi.check(L.b200boot_select_pick(self.n_alphas, self.n_cols, p, self.ws, self.wsz, s))
-        _abi.check(L.b200boot_select_end(self.n_alphas, self.n_cols, out.data_ptr(), self.ws, self.wsz, s))
-        return out
+        a, d, ws, wsz = self.n_alphas, self.n_cols, self.ws, self.wsz
+
+        def end():
+            _abi.check(L.b200boot_select_end(a, d, out.data_ptr(), ws, wsz, s))
+            return out
+
+        return _dist.radix_select_passes(
+            begin=lambda: _abi.check(L.b200boot_select_begin(self.ranks.data_ptr(), a, d, ws, wsz, s)),
+            hist=lambda p: _abi.check(L.b200boot_select_hist(self.stat.data_ptr(), self.n_local, d, a, p, ws, wsz, s)),
+            pick=lambda p: _abi.check(L.b200boot_select_pick(a, d, p, ws, wsz, s)),
+            end=end, hist_buffer=self.hist_tensor())
 
 
 def sort_columns(stat):

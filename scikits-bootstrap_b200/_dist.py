@@ -52,6 +52,19 @@ def all_reduce_sum(t) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_group)
 
 
+def radix_select_passes(begin, hist, pick, end, hist_buffer=None):
+    """Drives the 8-pass MSB radix descent of K5: begin(); then per pass hist(p) on the
+    local shard, SUM all-reduce of the histogram buffer across ranks, pick(p); end().
+    The callables wrap the C-ABI steps (b200boot_select_begin/hist/pick/end)."""
+    begin()
+    for p in range(8):
+        hist(p)
+        if hist_buffer is not None:
+            all_reduce_sum(hist_buffer)
+        pick(p)
+    return end()
+
+
 def all_gather_ragged(t, n_total: int, dim: int = -1):
     """Concatenates the ranks' shards (contiguous id ranges) along the last dim."""
     if not _enabled:

@@ -244,7 +244,7 @@ class _Run:
         torch = _device._torch()
         r = _device.host_to_device(np.asarray(ranks, dtype=np.int64), stat.device)
         sel = _device.Select(stat, r)
-        out = sel.run(between=_dist.all_reduce_sum if _dist.active() else None)
+        out = sel.run(sharded=_dist.active())
         return _device.to_host(out)
 
     # -- full sorted distribution (return_dist / host-side compfunctions) --------
