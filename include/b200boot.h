@@ -108,6 +108,11 @@ int b200boot_resample_median_columns(const double* data, int64_t n_rows, int64_t
                                      uint64_t seed, int64_t resample_lo, int64_t resample_hi,
                                      double* stat_out, void* ws, size_t ws_bytes, void* stream);
 
+/* K1m in parity mode: index sets supplied by the caller, int64[n_sets][N]. */
+int b200boot_resample_median_columns_indexed(const double* data, int64_t n_rows, int64_t n_cols,
+                                             int64_t ld, const int64_t* indices, int64_t n_sets,
+                                             double* stat_out, void* ws, size_t ws_bytes, void* stream);
+
 /* K2 — materialises exactly the indices K1 draws; backs the Python
  * `bootstrap_indices` iterator (bootstrap.py:667-680).
  * out: int64[resample_hi - resample_lo][N] row-major.  `n_arrays` selects the

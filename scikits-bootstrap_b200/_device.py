@@ -140,6 +140,19 @@ def resample_median_columns(data2d, seed: int, lo: int, hi: int):
     return out
 
 
+def resample_median_columns_indexed(data2d, indices):
+    """K1m parity mode: indices int64[n_sets][N] -> float64[D][n_sets]."""
+    torch = _torch()
+    n_rows, n_cols = data2d.shape
+    n_sets = indices.shape[0]
+    out = torch.empty((n_cols, n_sets), dtype=torch.float64, device=data2d.device)
+    ws, wsz = workspace_for(_abi.STAT_MEDIAN, n_rows, 1, n_cols, n_sets, 1)
+    _abi.check(_abi.lib().b200boot_resample_median_columns_indexed(
+        data2d.data_ptr(), n_rows, n_cols, data2d.stride(0), indices.data_ptr(), n_sets, out.data_ptr(),
+        ws, wsz, stream_ptr()))
+    return out
+
+
 def fill_indices(seed: int, n_rows: int, n_arrays: int, lo: int, hi: int):
     """K2 -> int64[hi-lo][N] CUDA tensor."""
     torch = require_cuda()

@@ -176,13 +176,21 @@ class _Run:
         PCG64 draws) instead of drawing; moment statistics of 1-D arrays only."""
         torch = _device._torch()
         spec = self.spec
-        if _dist.active() or spec.independent or self.vector or spec.stat_id == _abi.STAT_MEDIAN:
-            raise NotImplementedError("index-supplied mode covers paired moment statistics of 1-D arrays")
+        if _dist.active() or spec.independent:
+            raise NotImplementedError("index-supplied mode covers paired (non-sharded) statistics")
+        n_rows = self.dev[0].shape[0]
         idx = torch.as_tensor(np.ascontiguousarray(self.indices, dtype=np.int64)).to(self.dev[0].device)
-        if idx.dim() != 2 or idx.shape[0] != self.n_samples or idx.shape[1] != self.dev[0].numel():
+        if idx.dim() != 2 or idx.shape[0] != self.n_samples or idx.shape[1] != n_rows:
             raise ValueError("indices must have shape (n_samples, N)")
-        if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= self.dev[0].numel()):
+        if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= n_rows):
             raise IndexError("index out of range")
+        if spec.stat_id == _abi.STAT_MEDIAN:
+            data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
+            return _device.resample_median_columns_indexed(data2d, idx)
+        if self.vector:
+            cols = self.columns()
+            return torch.stack([_device.resample_stat_indexed([cols[d]], spec.stat_id, idx)
+                                for d in range(self.n_cols)])
         flat = [a.reshape(-1) for a in self.dev]
         return _device.resample_stat_indexed(flat, spec.stat_id, idx).reshape(1, -1)
 

@@ -514,6 +514,14 @@ int b200boot_resample_median_columns(const double* data, int64_t n_rows, int64_t
                          ws_bytes, as_stream(stream));
 }
 
+int b200boot_resample_median_columns_indexed(const double* data, int64_t n_rows, int64_t n_cols,
+                                             int64_t ld, const int64_t* indices, int64_t n_sets,
+                                             double* stat_out, void* ws, size_t ws_bytes, void* stream) {
+  if (!indices) return fail(B200BOOT_EINVAL, "null indices");
+  return median_resample(data, n_rows, n_cols, ld, 0, 0, n_sets, stat_out, ws, ws_bytes,
+                         as_stream(stream), indices);
+}
+
 int b200boot_jackknife_median_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld,
                                       double* out, void* ws, size_t ws_bytes, void* stream) {
   return median_jackknife(data, n_rows, n_cols, ld, out, ws, ws_bytes, as_stream(stream));

@@ -1,18 +1,449 @@
-// K1m / K3m — column-batched resample median (stub until the rank-space kernels land).
+// K1m / K3m — column-batched resample median in rank space.
+//
+// Replaces `statfunction(x[indices])` with np.median(axis=0) over (N, D) data
+// (/root/reference/src/scikits/bootstrap/bootstrap.py:431: all columns share one
+// index set per resample) and the leave-one-out loop (:595-599) for the median.
+//
+// Each column is sorted once (bitonic on (key, row) pairs).  A resample is then
+// described by the draw-count vector c[row] (shared by all columns); the median
+// of the resampled column is the sorted value at the first sorted position whose
+// cumulative count exceeds the middle rank (mean of the two middle ranks for
+// even N, as np.median).  A CTA keeps the sorted-order row permutation of a group
+// of columns in shared memory, rebuilds c[] for a few resamples at a time from
+// the same Philox/Lemire stream K1 and K2 use for single-cell plans, and each
+// warp scans one (resample, column) pair.
 #pragma once
 #include "common.cuh"
+#include "draw.cuh"
+#include "k45_interval.cuh"
 
 namespace b200boot {
 
-inline size_t median_ws_bytes(int64_t, int64_t, int64_t) { return 0; }
+constexpr int kMedThreads = 1024;
+constexpr int kMedWarps = kMedThreads / 32;
+constexpr int kMedBatch = 4;              // max resamples whose count vectors are resident at once
+constexpr int64_t kMedMaxRows = kSmemDataBytes / 8;   // single-cell plans only (28 672 rows)
 
-inline int median_resample(const double*, int64_t, int64_t, int64_t, uint64_t, int64_t, int64_t, double*,
-                           void*, size_t, cudaStream_t) {
-  return fail(B200BOOT_EUNSUPPORTED, "median kernels not built yet");
+// ---- per-column (key, row) bitonic sort -------------------------------------------
+__device__ __forceinline__ bool pair_gt(uint64_t ka, uint32_t ia, uint64_t kb, uint32_t ib) {
+  return ka > kb || (ka == kb && ia > ib);
 }
-inline int median_jackknife(const double*, int64_t, int64_t, int64_t, double*, void*, size_t,
-                            cudaStream_t) {
-  return fail(B200BOOT_EUNSUPPORTED, "median kernels not built yet");
+
+// keys[d][i] = key(data[i][d]), idx[d][i] = i; padding sorts last
+__global__ void __launch_bounds__(256) psort_load_kernel(const double* __restrict__ data, int64_t n,
+                                                         int64_t n_cols, int64_t ld, int64_t n_pad,
+                                                         uint64_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ idx) {
+  const int64_t total = n_pad * n_cols;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t d = e % n_cols, i = e / n_cols;      // d fastest: coalesced reads of a row
+    keys[d * n_pad + i] = i < n ? key_of(data[i * ld + d]) : ~0ull;
+    idx[d * n_pad + i] = i < n ? (uint32_t)i : 0xFFFFFFFFu;
+  }
+}
+
+__global__ void __launch_bounds__(256) psort_step_kernel(uint64_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ idx, int64_t n_pad,
+                                                         int64_t j, int64_t k) {
+  const int64_t d = blockIdx.y;
+  uint64_t* kc = keys + d * n_pad;
+  uint32_t* ic = idx + d * n_pad;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+    const int64_t p = i ^ j;
+    if (p > i) {
+      const uint64_t a = kc[i], b = kc[p];
+      const uint32_t ia = ic[i], ib = ic[p];
+      const bool ascending = (i & k) == 0;
+      if (pair_gt(a, ia, b, ib) == ascending) {
+        kc[i] = b; kc[p] = a;
+        ic[i] = ib; ic[p] = ia;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) psort_local_kernel(uint64_t* __restrict__ keys,
+                                                           uint32_t* __restrict__ idx, int64_t n_pad,
+                                                           int64_t k_first, int64_t k_last,
+                                                           int64_t j_first) {
+  __shared__ uint64_t sk[2048];
+  __shared__ uint32_t si[2048];
+  const int64_t d = blockIdx.y;
+  const int64_t seg0 = (int64_t)blockIdx.x * 2048;
+  uint64_t* kc = keys + d * n_pad + seg0;
+  uint32_t* ic = idx + d * n_pad + seg0;
+  const int seg_n = (int)min((int64_t)2048, n_pad);
+  for (int i = threadIdx.x; i < seg_n; i += 1024) {
+    sk[i] = kc[i];
+    si[i] = ic[i];
+  }
+  __syncthreads();
+  for (int64_t k = k_first; k <= k_last; k <<= 1) {
+    const int64_t j0 = (k == k_first) ? j_first : (k >> 1);
+    for (int64_t j = j0; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < seg_n; i += 1024) {
+        const int p = i ^ (int)j;
+        if (p > i) {
+          const uint64_t a = sk[i], b = sk[p];
+          const uint32_t ia = si[i], ib = si[p];
+          const bool ascending = ((seg0 + i) & k) == 0;
+          if (pair_gt(a, ia, b, ib) == ascending) {
+            sk[i] = b; sk[p] = a;
+            si[i] = ib; si[p] = ia;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < seg_n; i += 1024) {
+    kc[i] = sk[i];
+    ic[i] = si[i];
+  }
+}
+
+// sorted values and the row permutation in "lane-segment" order:
+// position s = lane * L + i is stored at perm_t[d][i * 32 + lane]; slots past N
+// point at the always-zero count slot N.
+__global__ void __launch_bounds__(256) median_pack_kernel(const uint64_t* __restrict__ keys,
+                                                          const uint32_t* __restrict__ idx, int64_t n,
+                                                          int64_t n_pad, int seg_len,
+                                                          double* __restrict__ sorted_vals,
+                                                          uint16_t* __restrict__ perm_t) {
+  const int64_t d = blockIdx.y;
+  const int64_t slots = (int64_t)seg_len * 32;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += stride) {
+    const int lane = (int)(s / seg_len), i = (int)(s % seg_len);
+    perm_t[d * slots + (int64_t)i * 32 + lane] = s < n ? (uint16_t)idx[d * n_pad + s] : (uint16_t)n;
+    if (s < n) sorted_vals[d * n + s] = value_of(keys[d * n_pad + s]);
+  }
+}
+
+// ---- K1m ---------------------------------------------------------------------------
+struct K1mParams {
+  const double* sorted_vals;   // [D][N]
+  const uint16_t* perm_t;      // [D][L*32]
+  int64_t n_rows, n_cols;
+  int32_t seg_len;             // L = ceil(N / 32)
+  int32_t cols_per_item;       // columns whose permutation is resident per item
+  int32_t n_colchunks;
+  int32_t rchunk, n_rchunks;   // resamples per item
+  int64_t n_items;
+  uint64_t seed;
+  int64_t resample_lo, n_local;
+  double* out;                 // [D][n_local]
+  int32_t* work_counter;
+  int32_t count_words;         // uint32 words per count vector ((N + 2) / 2 rounded up)
+  int32_t batch;               // resamples per count-vector batch (<= kMedBatch)
+  const int64_t* indices;      // parity mode: caller-supplied index sets [n_local][N], else null
+};
+
+// first sorted position whose cumulative draw count exceeds k
+__device__ __forceinline__ int median_find(const uint16_t* __restrict__ cnt,
+                                           const uint16_t* __restrict__ pt, int seg_len, int lane,
+                                           uint32_t incl, uint32_t sum, uint32_t k) {
+  const uint32_t hit = __ballot_sync(0xffffffffu, incl > k);
+  const int seg = __ffs(hit) - 1;                       // segment (lane) holding the crossing
+  uint32_t running = __shfl_sync(0xffffffffu, incl - sum, seg);
+  for (int c0 = 0; c0 < seg_len; c0 += 32) {
+    const int i = c0 + lane;
+    uint32_t v = i < seg_len ? (uint32_t)cnt[pt[i * 32 + seg]] : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
+      if (lane >= off) inc += o;
+    }
+    inc += running;
+    const uint32_t h = __ballot_sync(0xffffffffu, inc > k);
+    if (h) return seg * seg_len + c0 + __ffs(h) - 1;
+    running = __shfl_sync(0xffffffffu, inc, 31);
+  }
+  return seg * seg_len + seg_len - 1;   // unreachable when counts sum to N
+}
+
+__global__ void __launch_bounds__(kMedThreads, 1) k1m_median_kernel(const K1mParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  volatile int* s_item = reinterpret_cast<volatile int*>(smem_raw);
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem_raw + 128);                 // [kMedBatch][count_words]
+  uint16_t* s_perm = reinterpret_cast<uint16_t*>(s_cnt + P.batch * P.count_words);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t slots = (int64_t)P.seg_len * 32;
+  const int n = (int)P.n_rows;
+  const uint32_t thresh = lemire_threshold((uint32_t)n);
+  const int n_blocks = (n + 3) / 4;
+  const uint32_t k_hi = (uint32_t)(n / 2);                       // upper middle rank (0-based)
+  const bool even = (n & 1) == 0;
+
+  int resident = -1;
+  for (;;) {
+    if (tid == 0) *s_item = atomicAdd(P.work_counter, 1);
+    __syncthreads();
+    const int64_t item = *s_item;
+    __syncthreads();
+    if (item >= P.n_items) break;
+    const int cc = (int)(item / P.n_rchunks);
+    const int rc = (int)(item - (int64_t)cc * P.n_rchunks);
+    const int64_t d0 = (int64_t)cc * P.cols_per_item;
+    const int dc = (int)min((int64_t)P.cols_per_item, P.n_cols - d0);
+    if (cc != resident) {
+      const uint16_t* src = P.perm_t + d0 * slots;
+      for (int64_t e = tid; e < (int64_t)dc * slots; e += kMedThreads) s_perm[e] = src[e];
+      resident = cc;
+      __syncthreads();
+    }
+    const int64_t r_begin = (int64_t)rc * P.rchunk;
+    const int64_t r_end = min(r_begin + (int64_t)P.rchunk, P.n_local);
+    for (int64_t rb = r_begin; rb < r_end; rb += P.batch) {
+      const int nb = (int)min((int64_t)P.batch, r_end - rb);
+      for (int e = tid; e < nb * P.count_words; e += kMedThreads) s_cnt[e] = 0u;
+      __syncthreads();
+      if (P.indices) {   // parity mode: count the caller's indices
+        for (int e = tid; e < nb * n; e += kMedThreads) {
+          const int b = e / n, pos = e - b * n;
+          const uint32_t idx = (uint32_t)P.indices[(rb + b) * (int64_t)n + pos];
+          atomicAdd(s_cnt + b * P.count_words + (idx >> 1), 1u << ((idx & 1u) * 16));
+        }
+      }
+      // draw-count vectors: the single-cell Lemire stream of K1/K2 (cell 0)
+      for (int e = tid; !P.indices && e < nb * n_blocks; e += kMedThreads) {
+        const int b = e / n_blocks, q = e - b * n_blocks;
+        const Stream st = make_stream(P.seed, P.resample_lo + rb + b, 0u, kPurposeIndex);
+        uint32_t* cb = s_cnt + b * P.count_words;
+        lemire_block<true>(st, (uint32_t)q, (uint32_t)n, thresh, (int64_t)n,
+                           [&](int, int64_t, uint32_t idx) { atomicAdd(cb + (idx >> 1), 1u << ((idx & 1u) * 16)); });
+      }
+      __syncthreads();
+      for (int p = warp; p < nb * dc; p += kMedWarps) {
+        const int b = p / dc, j = p - b * dc;
+        const uint16_t* cnt = reinterpret_cast<const uint16_t*>(s_cnt + b * P.count_words);
+        const uint16_t* pt = s_perm + (int64_t)j * slots;
+        uint32_t sum = 0;
+        for (int i = 0; i < P.seg_len; ++i) sum += (uint32_t)cnt[pt[i * 32 + lane]];
+        uint32_t incl = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+          if (lane >= off) incl += o;
+        }
+        const int s_hi = median_find(cnt, pt, P.seg_len, lane, incl, sum, k_hi);
+        const double* sv = P.sorted_vals + (d0 + j) * P.n_rows;
+        double med = sv[s_hi];
+        if (even) {
+          const int s_lo = median_find(cnt, pt, P.seg_len, lane, incl, sum, k_hi - 1u);
+          med = (sv[s_lo] + med) / 2.0;
+        }
+        if (lane == 0) P.out[(d0 + j) * P.n_local + rb + b] = med;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---- K3m: leave-one-out medians by rank of the deleted row ---------------------------
+__device__ __forceinline__ double loo_median(const double* __restrict__ sv, int64_t n, int64_t r) {
+  const int64_t m = n - 1;
+  if (m <= 0) return NAN;
+  auto kth = [&](int64_t k) { return sv[k < r ? k : k + 1]; };
+  return (m & 1) ? kth(m / 2) : (kth(m / 2 - 1) + kth(m / 2)) / 2.0;
+}
+
+__device__ __forceinline__ double block_sum_256(double v, double* s_red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < 8; ++w) t += s_red[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(256) k3m_jackknife_median_kernel(const double* __restrict__ sorted_vals,
+                                                                   int64_t n, double* __restrict__ out) {
+  __shared__ double s_red[8];
+  const int64_t d = blockIdx.x;
+  const double* sv = sorted_vals + d * n;
+  double acc = 0.0;
+  for (int64_t r = threadIdx.x; r < n; r += 256) acc += loo_median(sv, n, r);
+  const double jmean = block_sum_256(acc, s_red) / (double)n;
+  double a2 = 0.0, a3 = 0.0;
+  for (int64_t r = threadIdx.x; r < n; r += 256) {
+    const double dv = jmean - loo_median(sv, n, r);
+    a2 += dv * dv;
+    a3 += dv * dv * dv;
+  }
+  const double d2 = block_sum_256(a2, s_red);
+  const double d3 = block_sum_256(a3, s_red);
+  if (threadIdx.x == 0) {
+    double* o = out + d * 8;
+    o[0] = (n & 1) ? sv[n / 2] : (sv[n / 2 - 1] + sv[n / 2]) / 2.0;
+    o[1] = jmean;
+    o[2] = d2;
+    o[3] = d3;
+    o[4] = d3 / (6.0 * pow(d2, 1.5));
+    o[5] = o[6] = o[7] = 0.0;
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------
+struct MedianWs {
+  int32_t* work_counter;
+  uint64_t* keys;
+  uint32_t* idx;
+  double* sorted_vals;
+  uint16_t* perm_t;
+  int64_t n_pad;
+  int seg_len;
+};
+
+inline MedianWs median_carve(Carver& cv, int64_t n_rows, int64_t n_cols) {
+  MedianWs w{};
+  w.n_pad = 1;
+  while (w.n_pad < n_rows) w.n_pad <<= 1;
+  w.seg_len = (int)((n_rows + 31) / 32);
+  w.work_counter = cv.take<int32_t>(64);
+  w.keys = cv.take<uint64_t>((size_t)w.n_pad * n_cols);
+  w.idx = cv.take<uint32_t>((size_t)w.n_pad * n_cols);
+  w.sorted_vals = cv.take<double>((size_t)n_rows * n_cols);
+  w.perm_t = cv.take<uint16_t>((size_t)w.seg_len * 32 * n_cols);
+  return w;
+}
+
+inline size_t median_ws_bytes(int64_t n_rows, int64_t n_cols, int64_t) {
+  Carver cv(reinterpret_cast<void*>(256), ~(size_t)0 >> 1);
+  median_carve(cv, n_rows, n_cols);
+  return cv.used;
+}
+
+inline int median_check(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, void* ws) {
+  if (!data || n_rows < 1 || n_cols < 1 || ld < n_cols) return fail(B200BOOT_EINVAL, "median: bad arguments");
+  if (n_rows > kMedMaxRows)
+    return fail(B200BOOT_EUNSUPPORTED,
+                "median: n_rows=%lld exceeds the shared-memory-resident limit of %lld rows",
+                (long long)n_rows, (long long)kMedMaxRows);
+  if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
+    return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
+  return 0;
+}
+
+// sorts every column and packs sorted values + permutation into the workspace
+inline int median_prepare(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, MedianWs& w,
+                          cudaStream_t s) {
+  const int64_t n_pad = w.n_pad;
+  const int64_t total = n_pad * n_cols;
+  int64_t lb = (total + 255) / 256;
+  if (lb > 148 * 32) lb = 148 * 32;
+  psort_load_kernel<<<(int)lb, 256, 0, s>>>(data, n_rows, n_cols, ld, n_pad, w.keys, w.idx);
+  B2_LAUNCH_CHECK();
+  const int64_t seg = n_pad < 2048 ? n_pad : 2048;
+  for (int64_t d0 = 0; d0 < n_cols; d0 += 65535) {
+    const unsigned nd = (unsigned)(n_cols - d0 < 65535 ? n_cols - d0 : 65535);
+    uint64_t* kc = w.keys + d0 * n_pad;
+    uint32_t* ic = w.idx + d0 * n_pad;
+    const dim3 glocal((unsigned)(n_pad / seg), nd);
+    int64_t fb = (n_pad + 1023) / 1024;
+    if (fb > 1024) fb = 1024;
+    const dim3 gflat((unsigned)fb, nd);
+    if (n_pad > 1) {
+      psort_local_kernel<<<glocal, 1024, 0, s>>>(kc, ic, n_pad, 2, seg, 1);
+      B2_LAUNCH_CHECK();
+    }
+    for (int64_t k = seg * 2; k <= n_pad; k <<= 1) {
+      for (int64_t j = k >> 1; j >= 2048; j >>= 1) {
+        psort_step_kernel<<<gflat, 256, 0, s>>>(kc, ic, n_pad, j, k);
+        B2_LAUNCH_CHECK();
+      }
+      psort_local_kernel<<<glocal, 1024, 0, s>>>(kc, ic, n_pad, k, k, 1024);
+      B2_LAUNCH_CHECK();
+    }
+    const dim3 gpack((unsigned)((w.seg_len * 32 + 255) / 256), nd);
+    median_pack_kernel<<<gpack, 256, 0, s>>>(kc, ic, n_rows, n_pad, w.seg_len, w.sorted_vals + d0 * n_rows,
+                                             w.perm_t + d0 * w.seg_len * 32);
+    B2_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+inline int median_resample(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, uint64_t seed,
+                           int64_t resample_lo, int64_t resample_hi, double* stat_out, void* ws,
+                           size_t ws_bytes, cudaStream_t s, const int64_t* indices = nullptr) {
+  int rc = median_check(data, n_rows, n_cols, ld, ws);
+  if (rc) return rc;
+  const int64_t n_local = resample_hi - resample_lo;
+  if (n_local < 0 || resample_lo < 0) return fail(B200BOOT_EINVAL, "bad resample range");
+  if (n_local == 0) return 0;
+  if (!stat_out) return fail(B200BOOT_EINVAL, "null output");
+  Carver cv(ws, ws_bytes);
+  MedianWs w = median_carve(cv, n_rows, n_cols);
+  if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+  rc = median_prepare(data, n_rows, n_cols, ld, w, s);
+  if (rc) return rc;
+
+  K1mParams P{};
+  P.sorted_vals = w.sorted_vals;
+  P.perm_t = w.perm_t;
+  P.n_rows = n_rows;
+  P.n_cols = n_cols;
+  P.seg_len = w.seg_len;
+  P.count_words = (int32_t)(((n_rows + 2) / 2 + 31) & ~(int64_t)31);
+  P.batch = (int64_t)kMedBatch * P.count_words * 4 <= 64 * 1024 ? kMedBatch : 1;
+  const int64_t cnt_bytes = (int64_t)P.batch * P.count_words * 4;
+  const int64_t perm_bytes = (int64_t)w.seg_len * 32 * 2;
+  int64_t cpi = (kSmemDataBytes - 128 - cnt_bytes) / perm_bytes;
+  if (cpi < 1) return fail(B200BOOT_EUNSUPPORTED, "median: column does not fit in shared memory");
+  cpi = std::min<int64_t>(std::min<int64_t>(cpi, 64), n_cols);
+  P.cols_per_item = (int32_t)cpi;
+  P.n_colchunks = (int32_t)((n_cols + cpi - 1) / cpi);
+  const int sms = sm_count();
+  int64_t want_r = ((int64_t)sms * 8 + P.n_colchunks - 1) / P.n_colchunks;
+  int64_t rchunk = (n_local + want_r - 1) / want_r;
+  rchunk = ((rchunk + P.batch - 1) / P.batch) * P.batch;
+  P.rchunk = (int32_t)std::min<int64_t>(std::max<int64_t>(rchunk, P.batch), 1 << 20);
+  P.n_rchunks = (int32_t)((n_local + P.rchunk - 1) / P.rchunk);
+  P.n_items = (int64_t)P.n_colchunks * P.n_rchunks;
+  if (P.n_items >= ((int64_t)1 << 31)) return fail(B200BOOT_EINVAL, "too many work items");
+  P.seed = seed;
+  P.resample_lo = resample_lo;
+  P.n_local = n_local;
+  P.out = stat_out;
+  P.work_counter = w.work_counter;
+  P.indices = indices;
+  B2_CUDA(cudaMemsetAsync(w.work_counter, 0, 256, s));
+  const size_t smem = 128 + (size_t)cnt_bytes + (size_t)cpi * perm_bytes;
+  static bool configured[64] = {false};
+  int dev = 0;
+  B2_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    B2_CUDA(cudaFuncSetAttribute(k1m_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(kSmemHeader + kSmemDataBytes)));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  const int grid = (int)std::min<int64_t>(sms, P.n_items);
+  k1m_median_kernel<<<grid, kMedThreads, smem, s>>>(P);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+inline int median_jackknife(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, double* out,
+                            void* ws, size_t ws_bytes, cudaStream_t s) {
+  int rc = median_check(data, n_rows, n_cols, ld, ws);
+  if (rc) return rc;
+  if (!out) return fail(B200BOOT_EINVAL, "null output");
+  Carver cv(ws, ws_bytes);
+  MedianWs w = median_carve(cv, n_rows, n_cols);
+  if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+  rc = median_prepare(data, n_rows, n_cols, ld, w, s);
+  if (rc) return rc;
+  for (int64_t d0 = 0; d0 < n_cols; d0 += 1 << 30) {
+    const int64_t nd = std::min<int64_t>((int64_t)1 << 30, n_cols - d0);
+    k3m_jackknife_median_kernel<<<(unsigned)nd, 256, 0, s>>>(w.sorted_vals + d0 * n_rows, n_rows,
+                                                             out + d0 * 8);
+    B2_LAUNCH_CHECK();
+  }
+  return 0;
 }
 
 }  // namespace b200boot

@@ -89,8 +89,7 @@ def test_reference_pval_goldens_in_index_supplied_mode():
     assert_allclose(r, 0.096)
 
 
-MOMENT_CASES = [c for c in CASES if c[2] in ("mean", "average", "var", "std", "ratio_of_means",
-                                             "weighted_average", "pearson_r")]
+MOMENT_CASES = [c for c in CASES if c[3] != "independent"]      # incl. median and (N, D) cases
 
 
 @pytest.mark.parametrize("case", MOMENT_CASES, ids=[c[0] for c in MOMENT_CASES])
@@ -189,6 +188,63 @@ def test_fused_paired(stat_name, n):
     a = rng.gamma(2, 1, n)
     b = 0.5 * a + rng.gamma(3, 1, n)
     fused_vs_oracle((a, b), stat_name, 400, seed=n + 2, multi="paired")
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 20, 301, 1000, 1024, 1025, 5000, 28672])
+def test_fused_median_1d(n):
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n) if n % 3 else np.round(rng.standard_normal(n), 1)     # ties too
+    m = 300
+    idx = np.array(list(boot.bootstrap_indices(x, m, seed=n)))
+    want = np.sort(orc.stat_over_indices((x,), np.median, idx))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out, dist = boot.ci(x, np.median, n_samples=m, seed=n, method="pi", return_dist=True)
+    assert_array_equal(dist, want)                       # order statistics: bit-exact
+    if n >= 20:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            got = boot.ci(x, np.median, n_samples=m, seed=n, method="bca")
+            ref = orc.ci_from_indices((x,), np.median, idx, (0.025, 0.975), m, "bca", jstat=orc.jack_median(x))
+        assert_array_equal(got, ref)
+
+
+def test_fused_median_columns_share_the_index_set():
+    """cfg4 shape in miniature: (N, D) data, median over axis 0, BCa, plus pval."""
+    rng = np.random.default_rng(4)
+    data = rng.standard_normal((1000, 70))
+    m = 400
+    out, dist = boot.ci(data, boot.median_axis0, n_samples=m, seed=9, return_dist=True)
+    assert out.shape == (2, 70) and dist.shape == (m, 70)
+    idx = np.array(list(boot.bootstrap_indices(data, m, seed=9)))
+    want = orc.stat_over_indices((data,), STATS["median_axis0"], idx)
+    want.sort(axis=0)
+    assert_array_equal(dist, want)
+    jst = np.stack([orc.jack_median(data[:, d]) for d in range(70)], axis=1)
+    ref = orc.ci_from_indices((data,), STATS["median_axis0"], idx, (0.025, 0.975), m, "bca", jstat=jst)
+    assert_array_equal(out, ref)
+    for d in (0, 33, 69):                                 # column d == the 1-D run with the same seed
+        assert_array_equal(boot.ci(data[:, d], np.median, n_samples=m, seed=9), out[:, d])
+    p = boot.pval(data, functools.partial(np.median, axis=0), n_samples=m, seed=9)
+    assert_array_equal(p, (want > 0).mean(axis=0))
+
+
+@pytest.mark.parametrize("n", [2, 3, 10, 301, 1000])
+def test_jackknife_median_closed_form(n):
+    rng = np.random.default_rng(n)
+    data = np.round(rng.standard_normal((n, 3)), 1 if n > 100 else 6)
+    out = _device.jackknife_median_columns(dev(data)).cpu().numpy()
+    for d in range(3):
+        j = orc.jack_median(data[:, d])
+        assert_allclose(out[d, 0], np.median(data[:, d]), rtol=0, atol=0)
+        assert_allclose(out[d, 1], j.mean(), rtol=1e-12, atol=1e-15)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            a = orc.acceleration(j)
+        if np.isfinite(a):
+            assert_allclose(out[d, 4], a, rtol=1e-6, atol=1e-12)
+        if n <= 301:
+            assert_array_equal(j, orc.jackknife_stats_loop((data[:, d],), np.median))
 
 
 def test_fused_odd_sizes_and_unaligned_views():
