@@ -241,7 +241,8 @@ def test_jackknife_median_closed_form(n):
         assert_allclose(out[d, 1], j.mean(), rtol=1e-12, atol=1e-15)
         with np.errstate(invalid="ignore", divide="ignore"):
             a = orc.acceleration(j)
-        if np.isfinite(a):
+        # all-equal leave-one-out medians (ties): 0/0 here, rounding noise in numpy's mean
+        if np.isfinite(a) and np.sum((j.mean() - j) ** 2) > 1e-20:
             assert_allclose(out[d, 4], a, rtol=1e-6, atol=1e-12)
         if n <= 301:
             assert_array_equal(j, orc.jackknife_stats_loop((data[:, d],), np.median))
