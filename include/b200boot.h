@@ -121,10 +121,12 @@ int b200boot_fill_indices(uint64_t seed, int64_t n_rows, int n_arrays, int64_t r
                           int64_t resample_hi, int64_t* out, void* ws, size_t ws_bytes,
                           void* stream);
 
-/* Tile occupancies of the multinomial chain (K0), for inspection and tests:
- * counts int32[n_tiles][n_local].  Only meaningful when the plan has > 1 tile. */
+/* Occupancies of the multinomial chain (K0), for inspection and tests:
+ * counts int32[n_tiles][n_local]; class_counts (may be NULL) int32[n_full][n_local][16],
+ * the split of every full tile's draws over its 16 shared-memory bank classes.
+ * Only meaningful when the plan has > 1 tile. */
 int b200boot_tile_counts(uint64_t seed, int64_t n_rows, int n_arrays, int64_t resample_lo,
-                         int64_t resample_hi, int32_t* counts, void* stream);
+                         int64_t resample_hi, int32_t* counts, int32_t* class_counts, void* stream);
 
 /* Plain gather out[i] = data[idx[i]] (bit-exactness probe for bootstrap.py:431). */
 int b200boot_gather(const double* data, int64_t n_rows, const int64_t* idx, int64_t n_idx,
@@ -188,6 +190,8 @@ int64_t b200boot_host_binomial(uint64_t seed, int64_t resample, int64_t cell, in
                                double p);
 int b200boot_host_tile_counts(uint64_t seed, int64_t n_rows, int n_arrays, int64_t resample,
                               int32_t* counts /* [n_tiles] */);
+int b200boot_host_class_counts(uint64_t seed, int64_t resample, int64_t tile, int64_t n_tile_draws,
+                               int32_t* counts16);
 int b200boot_host_indices(uint64_t seed, int64_t n_rows, int n_arrays, int64_t resample,
                           int64_t* out /* [n_rows] */);
 

@@ -449,16 +449,27 @@ def seed_key(seed: int) -> Tuple[int, int]:
     return (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
 
 
-def cell_draws_pow2(seed: int, resample: int, cell: int, n_draws: int, log2_size: int) -> np.ndarray:
-    """Indices in [0, 2^log2_size) for one (resample, cell): each Philox block
-    gives 8 indices; word w yields (w & mask) then (w >> 16) & mask."""
-    nblk = (n_draws + 7) // 8
-    words = philox4x32_10(_ctr(np.arange(nblk), cell, resample, PURPOSE_INDEX), seed_key(seed))
-    mask = np.uint32((1 << log2_size) - 1)
-    lo = words & mask
-    hi = (words >> np.uint32(16)) & mask
-    idx = np.stack((lo, hi), axis=-1).reshape(nblk, 8)   # w0lo,w0hi,w1lo,w1hi,...
-    return idx.reshape(-1)[:n_draws].astype(np.int64)
+N_CLASSES = 16                 # csrc/draw.cuh: kClasses (shared-memory bank pairs)
+CLASS_DRAWS_PER_BLOCK = 12
+
+
+def class_cell_id(tile: int, c: int) -> int:
+    return 0x80000000 | ((tile << 4) & 0x7FFFFFF0) | c
+
+
+def class_draws(seed: int, resample: int, tile: int, c: int, n_draws: int, log2_tile: int) -> np.ndarray:
+    """Rows (inside the tile) drawn for bank class c of full tile `tile`: each Philox
+    word gives three (log2_tile-4)-bit row numbers j_A=(w>>7)&m, j_B=(w>>17)&m,
+    j_C=rotl(w,5)&m; the row is j*16 + c.  12 draws per block."""
+    nblk = (n_draws + CLASS_DRAWS_PER_BLOCK - 1) // CLASS_DRAWS_PER_BLOCK
+    words = philox4x32_10(_ctr(np.arange(nblk), class_cell_id(tile, c), resample, PURPOSE_INDEX),
+                          seed_key(seed)).astype(np.uint32)
+    m = np.uint32((1 << (log2_tile - 4)) - 1)
+    ja = (words >> np.uint32(7)) & m
+    jb = (words >> np.uint32(17)) & m
+    jc = ((words << np.uint32(5)) | (words >> np.uint32(27))) & m
+    j = np.stack((ja, jb, jc), axis=-1).reshape(nblk, 12)      # w0:A,B,C, w1:A,B,C, ...
+    return (j.reshape(-1)[:n_draws].astype(np.int64)) * N_CLASSES + c
 
 
 def cell_draws_lemire(seed: int, resample: int, cell: int, n_draws: int, size: int) -> np.ndarray:
@@ -503,10 +514,12 @@ def tile_plan(n_obs: int, log2_tile: int, n_arrays: int = 1):
 
 def device_indices(seed: int, resample: int, n_obs: int, log2_tile: int,
                    counts: Sequence[int] | None = None, cell_base: int = 0,
-                   n_arrays: int = 1) -> np.ndarray:
-    """The canonical index array of resample `resample`: tiles in order, within a
-    tile the draws in position order.  `counts` are the tile occupancies (from
-    the device multinomial chain); with a single tile the count is n_obs."""
+                   n_arrays: int = 1, class_counts=None) -> np.ndarray:
+    """The canonical index array of resample `resample`: cells in order; a full tile
+    lists its 16 bank classes in order, each class its draws in stream order; a
+    general cell lists its Lemire draws in stream order.  `counts` are the tile
+    occupancies and `class_counts[t][c]` the class split of full tile t (both come
+    from the device multinomial chains); with a single cell the count is n_obs."""
     sizes = tile_plan(n_obs, log2_tile, n_arrays)
     if len(sizes) == 1:
         return cell_draws_lemire(seed, resample, cell_base, n_obs, n_obs)
@@ -515,10 +528,12 @@ def device_indices(seed: int, resample: int, n_obs: int, log2_tile: int,
     parts = []
     for t, (sz, cnt) in enumerate(zip(sizes, counts)):
         if sz == m:
-            loc = cell_draws_pow2(seed, resample, cell_base + t, cnt, log2_tile)
+            cc = class_counts[t]
+            assert sum(cc) == cnt
+            for c in range(N_CLASSES):
+                parts.append(class_draws(seed, resample, t, c, int(cc[c]), log2_tile) + t * m)
         else:
-            loc = cell_draws_lemire(seed, resample, cell_base + t, cnt, sz)
-        parts.append(loc + t * m)
+            parts.append(cell_draws_lemire(seed, resample, cell_base + t, cnt, sz) + t * m)
     return np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
 
 

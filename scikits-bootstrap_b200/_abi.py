@@ -40,7 +40,7 @@ SIGNATURES = {
     "b200boot_resample_median_columns": (_int, [_vp, _i64, _i64, _i64, _u64, _i64, _i64, _vp, _vp, _sz, _vp]),
     "b200boot_resample_median_columns_indexed": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
     "b200boot_fill_indices": (_int, [_u64, _i64, _int, _i64, _i64, _vp, _vp, _sz, _vp]),
-    "b200boot_tile_counts": (_int, [_u64, _i64, _int, _i64, _i64, _vp, _vp]),
+    "b200boot_tile_counts": (_int, [_u64, _i64, _int, _i64, _i64, _vp, _vp, _vp]),
     "b200boot_gather": (_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "b200boot_jackknife": (_int, [_vp, _int, _i64, _int, _vp, _vp, _sz, _vp]),
     "b200boot_jackknife_median_columns": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
@@ -58,6 +58,7 @@ SIGNATURES = {
     "b200boot_host_philox4x32": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "b200boot_host_binomial": (_i64, [_u64, _i64, _i64, _i64, C.c_double]),
     "b200boot_host_tile_counts": (_int, [_u64, _i64, _int, _i64, _vp]),
+    "b200boot_host_class_counts": (_int, [_u64, _i64, _i64, _i64, _vp]),
     "b200boot_host_indices": (_int, [_u64, _i64, _int, _i64, _vp]),
 }
 

@@ -158,18 +158,21 @@ def fill_indices(seed: int, n_rows: int, n_arrays: int, lo: int, hi: int):
     torch = require_cuda()
     out = torch.empty((hi - lo, n_rows), dtype=torch.int64, device="cuda")
     plan = _abi.make_plan(n_rows, n_arrays)
-    ws, wsz = _ws.get(plan.n_tiles * (hi - lo) * 4 + 1024)
+    ws, wsz = _ws.get(plan.n_tiles * (hi - lo) * 4 * 17 + 4096)
     _abi.check(_abi.lib().b200boot_fill_indices(seed, n_rows, n_arrays, lo, hi, out.data_ptr(), ws, wsz,
                                                 stream_ptr()))
     return out
 
 
-def tile_counts(seed: int, n_rows: int, n_arrays: int, lo: int, hi: int):
+def tile_counts(seed: int, n_rows: int, n_arrays: int, lo: int, hi: int, with_classes: bool = False):
+    """K0 occupancies: int32[n_tiles][hi-lo] (and int32[n_full][hi-lo][16] class counts)."""
     torch = require_cuda()
     plan = _abi.make_plan(n_rows, n_arrays)
     out = torch.empty((plan.n_tiles, hi - lo), dtype=torch.int32, device="cuda")
-    _abi.check(_abi.lib().b200boot_tile_counts(seed, n_rows, n_arrays, lo, hi, out.data_ptr(), stream_ptr()))
-    return out
+    cls = torch.empty((plan.n_full, hi - lo, 16), dtype=torch.int32, device="cuda") if with_classes else None
+    _abi.check(_abi.lib().b200boot_tile_counts(seed, n_rows, n_arrays, lo, hi, out.data_ptr(),
+                                               cls.data_ptr() if cls is not None else None, stream_ptr()))
+    return (out, cls) if with_classes else out
 
 
 def gather(data, idx):

@@ -36,6 +36,7 @@ inline int blocks_for(int64_t n, int threads, int64_t cap) {
 // ---- workspace layouts ---------------------------------------------------------
 struct ResampleWs {
   int32_t* counts;
+  int32_t* cls;         // [n_full][n_local][16]
   double* partial;
   int32_t* work_counter;
   JackState* jack;
@@ -51,6 +52,7 @@ ResampleWs carve_resample(Carver& cv, const Plan& plan, int stat, int64_t n_loca
   w.jack = cv.take<JackState>(1);
   w.red = cv.take<double>((size_t)kRedBlocks * kMaxMoments);
   w.counts = plan.n_tiles > 1 ? cv.take<int32_t>((size_t)plan.n_tiles * n_local) : nullptr;
+  w.cls = plan.n_full > 0 ? cv.take<int32_t>((size_t)plan.n_full * n_local * kClasses) : nullptr;
   w.partial = cv.take<double>((size_t)plan.n_tiles * nm * std::max<int64_t>(n_local, 1));
   if (stat_needs_centering(stat))
     for (int a = 0; a < plan.n_arrays; ++a) w.centered[a] = cv.take<double>((size_t)plan.n_rows);
@@ -82,6 +84,23 @@ int prepare_rows(const double* const* data, int n_arrays, int64_t n_rows, int st
                                                                     w.jack, a);
     B2_LAUNCH_CHECK();
     rows[a] = w.centered[a];
+  }
+  return 0;
+}
+
+// K0: tile occupancies, then the 16-way class split of every full tile
+int launch_occupancies(uint64_t seed, int64_t resample_lo, int64_t n_local, const Plan& plan,
+                       int32_t* counts, int32_t* cls, cudaStream_t s) {
+  if (plan.n_tiles <= 1) return 0;
+  k0_tile_counts_kernel<<<blocks_for(n_local, 128, 1 << 30), 128, 0, s>>>(seed, resample_lo, n_local, plan,
+                                                                        counts);
+  B2_LAUNCH_CHECK();
+  if (plan.n_full > 0 && cls) {
+    const int64_t total = plan.n_full * n_local;
+    if (total >= ((int64_t)1 << 37)) return fail(B200BOOT_EINVAL, "too many (tile, resample) pairs");
+    k0_class_counts_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(seed, resample_lo, n_local,
+                                                                          plan.n_full, counts, cls);
+    B2_LAUNCH_CHECK();
   }
   return 0;
 }
@@ -207,11 +226,8 @@ int b200boot_resample_stat(const double* const* data, int n_arrays, int64_t n_ro
   rc = prepare_rows(data, n_arrays, n_rows, stat_id, w, rows, s);
   if (rc) return rc;
 
-  if (plan.n_tiles > 1) {
-    k0_tile_counts_kernel<<<blocks_for(n_local, 128, 1 << 30), 128, 0, s>>>(seed, resample_lo, n_local,
-                                                                          plan, w.counts);
-    B2_LAUNCH_CHECK();
-  }
+  rc = launch_occupancies(seed, resample_lo, n_local, plan, w.counts, w.cls, s);
+  if (rc) return rc;
   B2_CUDA(cudaMemsetAsync(w.work_counter, 0, 256, s));
 
   const int ms = moment_set_of(stat_id);
@@ -232,6 +248,8 @@ int b200boot_resample_stat(const double* const* data, int n_arrays, int64_t n_ro
   P.resample_lo = resample_lo;
   P.n_local = n_local;
   P.counts = w.counts;
+  P.cls = w.cls;
+  P.rk = make_round_keys(seed);
   P.partial = w.partial;
   P.work_counter = w.work_counter;
   P.chunk = (int32_t)chunk;
@@ -291,15 +309,12 @@ int b200boot_resample_stat_indexed(const double* const* data, int n_arrays, int6
 }
 
 int b200boot_tile_counts(uint64_t seed, int64_t n_rows, int n_arrays, int64_t resample_lo,
-                         int64_t resample_hi, int32_t* counts, void* stream) {
+                         int64_t resample_hi, int32_t* counts, int32_t* class_counts, void* stream) {
   const int64_t n_local = resample_hi - resample_lo;
   if (n_rows < 1 || n_arrays < 1 || n_local < 0 || !counts) return fail(B200BOOT_EINVAL, "bad arguments");
   if (n_local == 0) return 0;
   const Plan plan = make_plan(n_rows, n_arrays);
-  k0_tile_counts_kernel<<<blocks_for(n_local, 128, 1 << 30), 128, 0, as_stream(stream)>>>(
-      seed, resample_lo, n_local, plan, counts);
-  B2_LAUNCH_CHECK();
-  return 0;
+  return launch_occupancies(seed, resample_lo, n_local, plan, counts, class_counts, as_stream(stream));
 }
 
 int b200boot_fill_indices(uint64_t seed, int64_t n_rows, int n_arrays, int64_t resample_lo,
@@ -312,18 +327,19 @@ int b200boot_fill_indices(uint64_t seed, int64_t n_rows, int n_arrays, int64_t r
   cudaStream_t s = as_stream(stream);
   const Plan plan = make_plan(n_rows, n_arrays);
   int32_t* counts = nullptr;
+  int32_t* cls = nullptr;
   if (plan.n_tiles > 1) {
     if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
       return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
     Carver cv(ws, ws_bytes);
     counts = cv.take<int32_t>((size_t)plan.n_tiles * n_local);
+    cls = cv.take<int32_t>((size_t)plan.n_full * n_local * kClasses);
     if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
-    k0_tile_counts_kernel<<<blocks_for(n_local, 128, 1 << 30), 128, 0, s>>>(seed, resample_lo, n_local,
-                                                                          plan, counts);
-    B2_LAUNCH_CHECK();
+    int rc = launch_occupancies(seed, resample_lo, n_local, plan, counts, cls, s);
+    if (rc) return rc;
   }
   k2_fill_indices_kernel<<<blocks_for(n_local * 32, 256, 148 * 8), 256, 0, s>>>(plan, seed, resample_lo,
-                                                                               n_local, counts, out);
+                                                                               n_local, counts, cls, out);
   B2_LAUNCH_CHECK();
   return 0;
 }
@@ -572,6 +588,13 @@ int b200boot_host_tile_counts(uint64_t seed, int64_t n_rows, int n_arrays, int64
   return 0;
 }
 
+int b200boot_host_class_counts(uint64_t seed, int64_t resample, int64_t tile, int64_t n_tile_draws,
+                               int32_t* counts16) {
+  if (!counts16 || tile < 0 || n_tile_draws < 0) return fail(B200BOOT_EINVAL, "bad arguments");
+  class_count_chain<int32_t>(seed, resample, tile, n_tile_draws, counts16, 1);
+  return 0;
+}
+
 int b200boot_host_indices(uint64_t seed, int64_t n_rows, int n_arrays, int64_t resample, int64_t* out) {
   if (n_rows < 1 || n_rows >= ((int64_t)1 << 31) || n_arrays < 1 || !out)
     return fail(B200BOOT_EINVAL, "bad arguments");
@@ -581,20 +604,28 @@ int b200boot_host_indices(uint64_t seed, int64_t n_rows, int n_arrays, int64_t r
     tile_count_chain<int32_t>(seed, resample, plan, counts.data(), 1);
   else
     counts[0] = (int32_t)n_rows;
+  const uint32_t m7 = ((1u << (plan.log2_tile - 4)) - 1u) << 7;
   int64_t offset = 0;
   for (int64_t t = 0; t < plan.n_tiles; ++t) {
     const int64_t n = counts[(size_t)t];
     const int64_t sz = plan.cell_size(t);
     const int64_t row0 = t < plan.n_full ? (t << plan.log2_tile) : (plan.n_full << plan.log2_tile);
-    const Stream st = make_stream(seed, resample, (uint32_t)t, kPurposeIndex);
     auto put = [&](int, int64_t pos, uint32_t idx) { out[offset + pos] = row0 + (int64_t)idx; };
     if (t < plan.n_full) {
-      for (uint32_t q = 0; (int64_t)q * 8 < n; ++q) pow2_block<true>(st, q, (uint32_t)sz - 1u, n, put);
+      int32_t cls[kClasses];
+      class_count_chain<int32_t>(seed, resample, t, n, cls, 1);
+      for (int c = 0; c < kClasses; ++c) {
+        const Stream st = make_stream(seed, resample, class_cell_id(t, c), kPurposeIndex);
+        for (uint32_t q = 0; (int64_t)q * kClassDrawsPerBlock < cls[c]; ++q)
+          class_block<true>(st, q, m7, c, (int64_t)cls[c], put);
+        offset += cls[c];
+      }
     } else {
+      const Stream st = make_stream(seed, resample, (uint32_t)t, kPurposeIndex);
       const uint32_t thresh = lemire_threshold((uint32_t)sz);
       for (uint32_t q = 0; (int64_t)q * 4 < n; ++q) lemire_block<true>(st, q, (uint32_t)sz, thresh, n, put);
+      offset += n;
     }
-    offset += n;
   }
   return 0;
 }

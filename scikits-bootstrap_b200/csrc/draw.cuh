@@ -43,8 +43,7 @@ inline Plan make_plan(int64_t n_rows, int n_arrays) {
 }
 
 // ---- draws inside one cell --------------------------------------------------
-// Power-of-two cell: a Philox block yields 8 indices, word w -> (w & mask) and
-// ((w >> 16) & mask).  Exactly uniform, no rejection.  log2 size <= 16.
+// Full power-of-two tiles are drawn per bank class (see class_block below).
 //
 // General cell of `size` rows: one word per index, Lemire multiply-shift
 // idx = (w * size) >> 32; words whose low product is < 2^32 mod size are
@@ -69,24 +68,13 @@ B2_HD_NOINLINE uint32_t lemire_redraw(Stream rs, uint32_t position, uint32_t siz
   }
 }
 
-// Calls f(j, position, index) for draw j = 0..7 of block `q` of a pow2 cell.
-// CHECK = false promises that the whole block lies below n_draws.
-template <bool CHECK, typename F>
-B2_HD void pow2_block(const Stream& s, uint32_t q, uint32_t mask, int64_t n_draws, F&& f) {
-  const Words4 w = stream_block(s, q);
-  const int64_t base = (int64_t)q * 8;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if (!CHECK || base + 2 * j < n_draws) f(2 * j, base + 2 * j, w.w[j] & mask);
-    if (!CHECK || base + 2 * j + 1 < n_draws) f(2 * j + 1, base + 2 * j + 1, (w.w[j] >> 16) & mask);
-  }
-}
-
-// Same for a general cell: draws j = 0..3 of block `q`.
+// Calls f(j, position, index) for draw j = 0..3 of block `q` of a general cell.
+// CHECK = false promises that the whole block lies below n_draws.  `rk`, when
+// given, must hold the round keys of the stream's seed (hoisted by the caller).
 template <bool CHECK, typename F>
 B2_HD void lemire_block(const Stream& s, uint32_t q, uint32_t size, uint32_t thresh,
-                        int64_t n_draws, F&& f) {
-  const Words4 w = stream_block(s, q);
+                        int64_t n_draws, F&& f, const RoundKeys* rk = nullptr) {
+  const Words4 w = rk ? stream_block(s, q, *rk) : stream_block(s, q);
   const int64_t base = (int64_t)q * 4;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -100,6 +88,67 @@ B2_HD void lemire_block(const Stream& s, uint32_t q, uint32_t size, uint32_t thr
 }
 
 B2_HD uint32_t lemire_threshold(uint32_t size) { return (uint32_t)(0u - size) % size; }
+
+// ---- bank classes of a full tile -------------------------------------------------
+// A full tile of 2^L rows is cut into 16 classes by (row mod 16): class c owns the
+// rows whose float64 sits in shared-memory bank pair (2c, 2c+1).  A lane that only
+// ever reads its own class never conflicts with the other 15 lanes of its half-warp.
+// The draws of a tile are therefore split over the classes (multinomial, 16 equal
+// cells; class_count_chain) and each class has its own stream, cell id
+// 0x80000000 | t << 4 | c.  A Philox word yields three (L-4)-bit row numbers j:
+//   j_A = (w >> 7) & m,  j_B = (w >> 17) & m,  j_C = rotl(w, 5) & m      (m = 2^(L-4) - 1)
+// i.e. 12 draws per block; the row inside the tile is j * 16 + c.
+constexpr int kClasses = 16;
+constexpr int kClassDrawsPerBlock = 12;
+
+B2_HD uint32_t class_cell_id(int64_t t, int c) { return 0x80000000u | ((uint32_t)t << 4) | (uint32_t)c; }
+
+B2_HD uint32_t rotl32(uint32_t x, int r) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(x, x, r);
+#else
+  return (x << r) | (x >> (32 - r));
+#endif
+}
+
+// the three row numbers of word w, pre-shifted by 7 (j << 7 = byte offset of row j of
+// class 0 for 8-byte elements); m7 = m << 7
+B2_HD void class_fields_shifted(uint32_t w, uint32_t m7, uint32_t* f) {
+  f[0] = w & m7;
+  f[1] = (w >> 10) & m7;
+  f[2] = rotl32(w, 12) & m7;
+}
+
+// Calls f(j, position, row_in_tile) for draw j = 0..11 of block q of class c.
+template <bool CHECK, typename F>
+B2_HD void class_block(const Stream& s, uint32_t q, uint32_t m7, int c, int64_t n_draws, F&& f) {
+  const Words4 w = stream_block(s, q);
+  const int64_t base = (int64_t)q * kClassDrawsPerBlock;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t fld[3];
+    class_fields_shifted(w.w[i], m7, fld);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      if (!CHECK || base + 3 * i + k < n_draws)
+        f(3 * i + k, base + 3 * i + k, (fld[k] >> 7) * kClasses + (uint32_t)c);
+  }
+}
+
+// Splits the n_t draws of full tile t over its 16 equal classes (conditional
+// binomials with p = 1 / (16 - c)); out[c * stride].
+template <typename I>
+B2_HD void class_count_chain(uint64_t seed, int64_t resample, int64_t t, int64_t n_t, I* out,
+                             int64_t stride) {
+  int64_t n_left = n_t;
+  for (int c = 0; c + 1 < kClasses; ++c) {
+    const Stream s = make_stream(seed, resample, class_cell_id(t, c), kPurposeBinomial);
+    const int64_t k = binomial_ratio(n_left, 1, kClasses - c, s);
+    out[c * stride] = (I)k;
+    n_left -= k;
+  }
+  out[(kClasses - 1) * stride] = (I)n_left;
+}
 
 // ---- tile occupancies -------------------------------------------------------
 // counts[t * stride] for t in [0, n_tiles): conditional-binomial chain over the

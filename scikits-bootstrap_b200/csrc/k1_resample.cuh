@@ -11,6 +11,8 @@
 // row offsets inside the cell, gather from shared memory and accumulate the
 // statistic's contribution vector in FP64.  A warp-shuffle butterfly produces
 // the per-(cell, resample) partial, later summed over cells in fixed order.
+// In a full tile each lane is tied to one shared-memory bank pair (bank class),
+// so the gathers are conflict-free; see draw.cuh.
 #pragma once
 #include "common.cuh"
 #include "draw.cuh"
@@ -31,6 +33,17 @@ __global__ void __launch_bounds__(128) k0_tile_counts_kernel(uint64_t seed, int6
   tile_count_chain<int32_t>(seed, resample_lo + rl, plan, counts + rl, n_local);
 }
 
+// class occupancies of the full tiles: cls[(t * n_local + r) * 16 + c]
+__global__ void __launch_bounds__(128) k0_class_counts_kernel(uint64_t seed, int64_t resample_lo,
+                                                              int64_t n_local, int64_t n_full,
+                                                              const int32_t* __restrict__ counts,
+                                                              int32_t* __restrict__ cls) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_full * n_local) return;
+  const int64_t t = e / n_local, rl = e - t * n_local;
+  class_count_chain<int32_t>(seed, resample_lo + rl, t, (int64_t)counts[e], cls + e * kClasses, 1);
+}
+
 // ------------------------------------------------------------------ K1 --------
 struct K1Params {
   const double* data[2];
@@ -39,6 +52,8 @@ struct K1Params {
   int64_t resample_lo;
   int64_t n_local;
   const int32_t* counts;  // [n_tiles][n_local]; null when the plan has one cell
+  const int32_t* cls;     // [n_full][n_local][16] class occupancies of the full tiles
+  RoundKeys rk;           // Philox round keys of `seed` (constant-bank operands)
   double* partial;        // [(t * NM + m)][n_local]
   int32_t* work_counter;
   int32_t chunk;          // resamples per work item
@@ -47,55 +62,96 @@ struct K1Params {
   int64_t smem_stride;    // elements between arrays in shared memory
 };
 
-// Sums the contribution vectors of the `n` draws of one (resample, cell) across
-// the lanes of a warp.  POW2: 8 indices per Philox block, else 4 (Lemire).
-template <int MS, bool POW2>
-__device__ __forceinline__ void cell_accumulate(const double* __restrict__ s_data,
-                                                int64_t smem_stride, const Stream& st, int64_t n,
-                                                uint32_t size, int lane, double* tot) {
-  constexpr int NA = MomTraits<MS>::kArrays;
-  constexpr int NM = MomTraits<MS>::kMoments;
-  constexpr int W = MomTraits<MS>::kWays;
-  constexpr int PER = POW2 ? 8 : 4;
+// Accumulator bank of one lane: W independent FP64 chains per moment, combined in a
+// fixed order (deterministic bits).
+template <int MS>
+struct LaneAcc {
+  static constexpr int NA = MomTraits<MS>::kArrays;
+  static constexpr int NM = MomTraits<MS>::kMoments;
+  static constexpr int W = MomTraits<MS>::kWays;
   double acc[NM][W];
+  __device__ __forceinline__ void clear() {
 #pragma unroll
-  for (int m = 0; m < NM; ++m)
+    for (int m = 0; m < NM; ++m)
 #pragma unroll
-    for (int w = 0; w < W; ++w) acc[m][w] = 0.0;
-
-  auto take = [&](int j, int64_t /*pos*/, uint32_t idx) {
+      for (int w = 0; w < W; ++w) acc[m][w] = 0.0;
+  }
+  // row at byte offset `off` of the resident cell
+  __device__ __forceinline__ void take(int j, const unsigned char* __restrict__ s_bytes,
+                                       uint32_t stride_bytes, uint32_t off) {
     double v[NA], c[NM];
-    v[0] = s_data[idx];
-    if (NA == 2) v[NA - 1] = s_data[smem_stride + idx];
+    v[0] = *reinterpret_cast<const double*>(s_bytes + off);
+    if (NA == 2) v[NA - 1] = *reinterpret_cast<const double*>(s_bytes + stride_bytes + off);
     contribution<MS>(v, c);
 #pragma unroll
     for (int m = 0; m < NM; ++m) acc[m][j % W] += c[m];
-  };
+  }
+  __device__ __forceinline__ void finish(double* tot) {
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+#pragma unroll
+      for (int w = W / 2; w > 0; w >>= 1)
+#pragma unroll
+        for (int i = 0; i < w; ++i) acc[m][i] += acc[m][i + w];
+      tot[m] = warp_sum(acc[m][0]);
+    }
+  }
+};
 
-  const uint32_t n_full = (uint32_t)(n / PER);
-  const uint32_t mask = size - 1u;
-  const uint32_t thresh = POW2 ? 0u : lemire_threshold(size);
+// Full tile: lane = (class c = lane & 15, half h = lane >> 4).  The lane draws the
+// blocks q = h, h+2, ... of its class stream; every LDS.64 of a half-warp touches 16
+// distinct bank pairs (conflict-free).  12 draws per Philox block.
+template <int MS>
+__device__ __forceinline__ void class_accumulate(const unsigned char* __restrict__ s_bytes,
+                                                 uint32_t stride_bytes, const RoundKeys& rk,
+                                                 const Stream& st, int64_t n_c, uint32_t m7,
+                                                 uint32_t cbits, uint32_t h, double* tot) {
+  LaneAcc<MS> A;
+  A.clear();
+  const uint32_t n_full = (uint32_t)(n_c / kClassDrawsPerBlock);
 #pragma unroll 2
-  for (uint32_t q = lane; q < n_full; q += 32) {
-    if (POW2)
-      pow2_block<false>(st, q, mask, n, take);
-    else
-      lemire_block<false>(st, q, size, thresh, n, take);
-  }
-  if ((int64_t)n_full * PER < n && (n_full & 31u) == (uint32_t)lane) {
-    if (POW2)
-      pow2_block<true>(st, n_full, mask, n, take);
-    else
-      lemire_block<true>(st, n_full, size, thresh, n, take);
-  }
+  for (uint32_t q = h; q < n_full; q += 2) {
+    const Words4 w = stream_block(st, q, rk);
 #pragma unroll
-  for (int m = 0; m < NM; ++m) {
+    for (int i = 0; i < 4; ++i) {
+      uint32_t f[3];
+      class_fields_shifted(w.w[i], m7, f);
 #pragma unroll
-    for (int w = W / 2; w > 0; w >>= 1)
-#pragma unroll
-      for (int i = 0; i < w; ++i) acc[m][i] += acc[m][i + w];
-    tot[m] = warp_sum(acc[m][0]);
+      for (int k = 0; k < 3; ++k) A.take(3 * i + k, s_bytes, stride_bytes, f[k] | cbits);
+    }
   }
+  const int64_t done = (int64_t)n_full * kClassDrawsPerBlock;
+  if (done < n_c && (n_full & 1u) == h) {
+    const Words4 w = stream_block(st, n_full, rk);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t f[3];
+      class_fields_shifted(w.w[i], m7, f);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (done + 3 * i + k < n_c) A.take(3 * i + k, s_bytes, stride_bytes, f[k] | cbits);
+    }
+  }
+  A.finish(tot);
+}
+
+// General cell (single-cell plans and the remainder cell): lanes take the blocks
+// q = lane, lane+32, ... of the cell stream; 4 Lemire draws per block.
+template <int MS>
+__device__ __forceinline__ void lemire_accumulate(const unsigned char* __restrict__ s_bytes,
+                                                  uint32_t stride_bytes, const RoundKeys& rk,
+                                                  const Stream& st, int64_t n, uint32_t size, int lane,
+                                                  double* tot) {
+  LaneAcc<MS> A;
+  A.clear();
+  auto take = [&](int j, int64_t, uint32_t idx) { A.take(j, s_bytes, stride_bytes, idx * 8u); };
+  const uint32_t n_full = (uint32_t)(n / 4);
+  const uint32_t thresh = lemire_threshold(size);
+#pragma unroll 2
+  for (uint32_t q = lane; q < n_full; q += 32) lemire_block<false>(st, q, size, thresh, n, take, &rk);
+  if ((int64_t)n_full * 4 < n && (n_full & 31u) == (uint32_t)lane)
+    lemire_block<true>(st, n_full, size, thresh, n, take, &rk);
+  A.finish(tot);
 }
 
 template <int MS>
@@ -106,6 +162,9 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_resample_kernel(const K1Para
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   volatile int* s_item = reinterpret_cast<volatile int*>(smem_raw + 16);
   double* s_data = reinterpret_cast<double*>(smem_raw + kSmemHeader);
+  const unsigned char* s_bytes = smem_raw + kSmemHeader;
+  const uint32_t stride_bytes = (uint32_t)(P.smem_stride * 8);
+  const uint32_t m7 = ((1u << (P.plan.log2_tile - 4)) - 1u) << 7;   // class row mask, pre-shifted
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -154,15 +213,20 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_resample_kernel(const K1Para
 
     const int64_t r_begin = c * P.chunk;
     const int64_t r_end = min(r_begin + (int64_t)P.chunk, P.n_local);
-    const bool pow2 = t < P.plan.n_full;
+    const bool full_tile = t < P.plan.n_full;
     for (int64_t rl = r_begin + warp; rl < r_end; rl += kK1Warps) {
-      const int64_t n = P.counts ? (int64_t)__ldg(P.counts + t * P.n_local + rl) : P.plan.n_rows;
-      const Stream st = make_stream(P.seed, P.resample_lo + rl, (uint32_t)t, kPurposeIndex);
       double tot[NM];
-      if (pow2)
-        cell_accumulate<MS, true>(s_data, P.smem_stride, st, n, (uint32_t)sz, lane, tot);
-      else
-        cell_accumulate<MS, false>(s_data, P.smem_stride, st, n, (uint32_t)sz, lane, tot);
+      if (full_tile) {
+        const int c = lane & (kClasses - 1);
+        const int64_t n_c = (int64_t)__ldg(P.cls + (t * P.n_local + rl) * kClasses + c);
+        const Stream st = make_stream(P.seed, P.resample_lo + rl, class_cell_id(t, c), kPurposeIndex);
+        class_accumulate<MS>(s_bytes, stride_bytes, P.rk, st, n_c, m7, (uint32_t)c << 3,
+                             (uint32_t)lane >> 4, tot);
+      } else {
+        const int64_t n = P.counts ? (int64_t)__ldg(P.counts + t * P.n_local + rl) : P.plan.n_rows;
+        const Stream st = make_stream(P.seed, P.resample_lo + rl, (uint32_t)t, kPurposeIndex);
+        lemire_accumulate<MS>(s_bytes, stride_bytes, P.rk, st, n, (uint32_t)sz, lane, tot);
+      }
       if (lane == 0) {
 #pragma unroll
         for (int m = 0; m < NM; ++m) P.partial[(t * NM + m) * P.n_local + rl] = tot[m];
@@ -229,29 +293,36 @@ __global__ void __launch_bounds__(256) k1_indexed_kernel(const double* __restric
 __global__ void __launch_bounds__(256) k2_fill_indices_kernel(Plan plan, uint64_t seed,
                                                               int64_t resample_lo, int64_t n_local,
                                                               const int32_t* __restrict__ counts,
+                                                              const int32_t* __restrict__ cls,
                                                               int64_t* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const uint32_t m7 = ((1u << (plan.log2_tile - 4)) - 1u) << 7;
   for (int64_t rl = warp_global; rl < n_local; rl += n_warps) {
     int64_t* row = out + rl * plan.n_rows;
     int64_t offset = 0;
     for (int64_t t = 0; t < plan.n_tiles; ++t) {
-      const int64_t n = counts ? (int64_t)counts[t * n_local + rl] : plan.n_rows;
       const int64_t sz = plan.cell_size(t);
       const int64_t row0 = t < plan.n_full ? (t << plan.log2_tile) : (plan.n_full << plan.log2_tile);
-      const Stream st = make_stream(seed, resample_lo + rl, (uint32_t)t, kPurposeIndex);
       auto put = [&](int, int64_t pos, uint32_t idx) { row[offset + pos] = row0 + (int64_t)idx; };
       if (t < plan.n_full) {
-        const uint32_t nblk = (uint32_t)((n + 7) / 8);
-        for (uint32_t q = lane; q < nblk; q += 32) pow2_block<true>(st, q, (uint32_t)sz - 1u, n, put);
+        for (int c = 0; c < kClasses; ++c) {
+          const int64_t n_c = cls[(t * n_local + rl) * kClasses + c];
+          const Stream st = make_stream(seed, resample_lo + rl, class_cell_id(t, c), kPurposeIndex);
+          const uint32_t nblk = (uint32_t)((n_c + kClassDrawsPerBlock - 1) / kClassDrawsPerBlock);
+          for (uint32_t q = lane; q < nblk; q += 32) class_block<true>(st, q, m7, c, n_c, put);
+          offset += n_c;
+        }
       } else {
+        const int64_t n = counts ? (int64_t)counts[t * n_local + rl] : plan.n_rows;
+        const Stream st = make_stream(seed, resample_lo + rl, (uint32_t)t, kPurposeIndex);
         const uint32_t nblk = (uint32_t)((n + 3) / 4);
         const uint32_t thresh = lemire_threshold((uint32_t)sz);
         for (uint32_t q = lane; q < nblk; q += 32)
           lemire_block<true>(st, q, (uint32_t)sz, thresh, n, put);
+        offset += n;
       }
-      offset += n;
     }
   }
 }

@@ -54,6 +54,45 @@ B2_HD Words4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, u
   return r;
 }
 
+// Round keys hoisted out of the rounds: they depend on the seed only, so a kernel
+// computes them once and every xor takes them as warp-uniform operands.
+struct RoundKeys {
+  uint32_t k0[10], k1[10];
+};
+
+B2_HD RoundKeys make_round_keys(uint64_t seed) {
+  RoundKeys rk;
+  uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    rk.k0[i] = a;
+    rk.k1[i] = b;
+    a += kPhiloxW0;
+    b += kPhiloxW1;
+  }
+  return rk;
+}
+
+B2_HD Words4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const RoundKeys& rk) {
+#pragma unroll
+  for (int round = 0; round < 10; ++round) {
+    const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
+    const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk.k0[round];
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ rk.k1[round];
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+  }
+  Words4 r;
+  r.w[0] = c0;
+  r.w[1] = c1;
+  r.w[2] = c2;
+  r.w[3] = c3;
+  return r;
+}
+
 // Per-(resample, cell) stream descriptor.
 //   key = (seed lo, seed hi)
 //   c0  = block index inside the stream        c1 = cell id
@@ -74,6 +113,10 @@ B2_HD Stream make_stream(uint64_t seed, int64_t resample, uint32_t cell, uint32_
 
 B2_HD Words4 stream_block(const Stream& s, uint32_t block) {
   return philox4x32_10(block, s.c1, s.c2, s.c3, s.k0, s.k1);
+}
+// same stream with pre-expanded round keys (rk must come from the stream's seed)
+B2_HD Words4 stream_block(const Stream& s, uint32_t block, const RoundKeys& rk) {
+  return philox4x32_10(block, s.c1, s.c2, s.c3, rk);
 }
 
 // 53-bit uniform in the open interval (0,1) from two words.

@@ -123,11 +123,14 @@ def test_device_indices_match_oracle_single_cell(n):
 @pytest.mark.parametrize("n,n_arrays", [(40000, 1), (100000, 1), (20000, 2), (16384 * 2, 1)])
 def test_device_indices_match_oracle_tiled(n, n_arrays):
     plan = _abi.make_plan(n, n_arrays)
-    counts = _device.tile_counts(9, n, n_arrays, 0, 16).cpu().numpy()       # [n_tiles][16]
+    counts, cls = _device.tile_counts(9, n, n_arrays, 0, 16, with_classes=True)
+    counts, cls = counts.cpu().numpy(), cls.cpu().numpy()             # [n_tiles][16], [n_full][16][16]
     assert (counts.sum(axis=0) == n).all()
+    assert (cls.sum(axis=2) == counts[:plan.n_full]).all() and (cls >= 0).all()
     got = _device.fill_indices(9, n, n_arrays, 0, 16).cpu().numpy()
     for r in (0, 7, 15):
-        want = orc.device_indices(9, r, n, plan.log2_tile, counts=list(counts[:, r]), n_arrays=n_arrays)
+        want = orc.device_indices(9, r, n, plan.log2_tile, counts=list(counts[:, r]), n_arrays=n_arrays,
+                                  class_counts=cls[:, r, :])
         assert_array_equal(got[r], want)
     # host probe (same sources, host libm) normally gives the same occupancies
     host = np.empty(plan.n_tiles, dtype=np.int32)
@@ -154,6 +157,12 @@ def test_tile_counts_multinomial_on_device():
     z = (cnt.mean(axis=1) - sizes) / np.sqrt(sizes * (1 - sizes / n) / m)
     assert np.abs(z).max() < 5.5
     assert abs(z.std() - 1) < 0.15
+    # 16-way bank-class split of each full tile
+    _, cls = _device.tile_counts(1, n, 1, 0, 64, with_classes=True)
+    cls = cls.cpu().numpy().astype(float)                                    # [610][64][16]
+    tile_n = cls.sum(axis=2, keepdims=True)
+    zc = (cls - tile_n / 16) / np.sqrt(tile_n * (1 / 16) * (15 / 16))
+    assert abs(zc.mean()) < 0.01 and abs(zc.std() - 1) < 0.01 and np.abs(zc).max() < 6.5
 
 
 # ------------------------------------------------------------------ leg (ii) -----

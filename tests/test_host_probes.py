@@ -68,6 +68,14 @@ def _host_counts(seed, n, n_arrays, r):
     return out
 
 
+def _host_class_counts(seed, n, n_arrays, r, counts):
+    p = _abi.make_plan(n, n_arrays)
+    out = np.empty((p.n_full, 16), dtype=np.int32)
+    for t in range(p.n_full):
+        _abi.check(_abi.lib().b200boot_host_class_counts(seed, r, t, int(counts[t]), out[t].ctypes.data))
+    return out
+
+
 @pytest.mark.parametrize("n", [1, 2, 5, 20, 1000, 28672])
 def test_single_cell_indices_match_oracle(n):
     for seed, r in [(0, 0), (1234567890, 7), (2**63 + 5, 2**33 + 1)]:
@@ -102,8 +110,11 @@ def test_tiled_indices_match_oracle_given_counts(n, n_arrays):
     for seed, r in [(3, 0), (99, 12345)]:
         counts = _host_counts(seed, n, n_arrays, r)
         assert counts.sum() == n and (counts >= 0).all()
+        cls = _host_class_counts(seed, n, n_arrays, r, counts)
+        assert (cls.sum(axis=1) == counts[:plan.n_full]).all() and (cls >= 0).all()
         got = _host_indices(seed, n, n_arrays, r)
-        want = orc.device_indices(seed, r, n, plan.log2_tile, counts=list(counts), n_arrays=n_arrays)
+        want = orc.device_indices(seed, r, n, plan.log2_tile, counts=list(counts), n_arrays=n_arrays,
+                                  class_counts=cls)
         np.testing.assert_array_equal(got, want)
 
 
@@ -151,6 +162,20 @@ def test_tile_counts_are_multinomial():
     # covariance of two cells: -n p_i p_j
     cov = np.cov(cnt[:, 0], cnt[:, 1])[0, 1]
     assert abs(cov - (-n * pr[0] * pr[1])) < 6 * n * pr[0] * (1 - pr[0]) / np.sqrt(m)
+
+
+def test_class_counts_are_multinomial():
+    m = 3000
+    out = np.empty((m, 16), dtype=np.int32)
+    for r in range(m):
+        _abi.check(_abi.lib().b200boot_host_class_counts(4, r, 7, 16384, out[r].ctypes.data))
+    assert (out.sum(axis=1) == 16384).all()
+    z = (out.mean(axis=0) - 1024) / np.sqrt(1024 * (15 / 16) / m)
+    assert np.abs(z).max() < 5
+    v = out.var(axis=0) / (1024 * 15 / 16)
+    assert np.abs(v - 1).max() < 0.2
+    cov = np.cov(out[:, 0], out[:, 15])[0, 1]
+    assert abs(cov + 64) < 6 * 960 / np.sqrt(m)
 
 
 def test_tiled_draws_are_uniform_over_rows():
