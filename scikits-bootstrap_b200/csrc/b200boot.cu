@@ -98,8 +98,9 @@ int launch_occupancies(uint64_t seed, int64_t resample_lo, int64_t n_local, cons
   if (plan.n_full > 0 && cls) {
     const int64_t total = plan.n_full * n_local;
     if (total >= ((int64_t)1 << 37)) return fail(B200BOOT_EINVAL, "too many (tile, resample) pairs");
-    k0_class_counts_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(seed, resample_lo, n_local,
-                                                                          plan.n_full, counts, cls);
+    const int64_t blocks = std::min<int64_t>((total + 127) / 128, (int64_t)sm_count() * 64);
+    k0_class_counts_kernel<<<(unsigned)blocks, 128, 0, s>>>(seed, resample_lo, n_local, plan.n_full, counts,
+                                                            cls);
     B2_LAUNCH_CHECK();
   }
   return 0;
@@ -117,19 +118,41 @@ int check_moment_stat(int stat, int n_arrays, int64_t n_rows) {
   return 0;
 }
 
-template <int MS>
-int launch_k1(const K1Params& P, size_t smem, int grid, cudaStream_t s) {
+// FAST: the cell's shared-window address is a compile-time constant (see kFastSmemBase)
+template <int MS, bool FAST>
+int launch_k1_variant(const K1Params& P, size_t smem, int grid, cudaStream_t s) {
   static bool configured[64] = {false};
   int dev = 0;
   B2_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    B2_CUDA(cudaFuncSetAttribute(k1_resample_kernel<MS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B2_CUDA(cudaFuncSetAttribute(k1_resample_kernel<MS, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(kSmemHeader + kSmemDataBytes)));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  k1_resample_kernel<MS><<<grid, kK1Threads, smem, s>>>(P);
+  k1_resample_kernel<MS, FAST><<<grid, kK1Threads, smem, s>>>(P);
   B2_LAUNCH_CHECK();
   return 0;
+}
+
+inline bool fast_smem_addressing() {
+  static int cached[64] = {0};   // 0 unknown, 1 yes, 2 no
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+  if (cached[dev] == 0) {
+    int reserved = 0;
+    const bool ok = cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, dev) == cudaSuccess &&
+                    reserved == 1024;
+    cached[dev] = ok ? 1 : 2;
+  }
+  return cached[dev] == 1;
+}
+
+template <int MS>
+int launch_k1(const K1Params& P, size_t smem, int grid, cudaStream_t s) {
+  // the 2-array fast variant also assumes 2^13-row tiles (kFastStride2)
+  const bool fast = fast_smem_addressing() && P.plan.n_full > 0 &&
+                    (MomTraits<MS>::kArrays == 1 || P.plan.log2_tile == 13);
+  return fast ? launch_k1_variant<MS, true>(P, smem, grid, s) : launch_k1_variant<MS, false>(P, smem, grid, s);
 }
 
 int dispatch_k1(int ms, const K1Params& P, size_t smem, int grid, cudaStream_t s) {
@@ -233,11 +256,12 @@ int b200boot_resample_stat(const double* const* data, int n_arrays, int64_t n_ro
   const int ms = moment_set_of(stat_id);
   const int nm = ms == kMomSum ? 1 : (ms == kMomPair5 ? 5 : 2);
   const int sms = sm_count();
-  // resamples per work item: aim at >= 16 items per CTA, whole warps, <= 2048
-  int64_t want_chunks = ((int64_t)sms * 16 + plan.n_tiles - 1) / plan.n_tiles;
+  // resamples per work item: aim at >= 32 items per CTA (tail balance), whole warps,
+  // <= 512 (an item then lasts ~0.5 ms; reloading the cell costs ~3 us)
+  int64_t want_chunks = ((int64_t)sms * 32 + plan.n_tiles - 1) / plan.n_tiles;
   int64_t chunk = (n_local + want_chunks - 1) / want_chunks;
   chunk = ((chunk + kK1Warps - 1) / kK1Warps) * kK1Warps;
-  chunk = std::min<int64_t>(std::max<int64_t>(chunk, kK1Warps), 2048);
+  chunk = std::min<int64_t>(std::max<int64_t>(chunk, kK1Warps), 512);
   const int64_t n_chunks = (n_local + chunk - 1) / chunk;
 
   K1Params P{};

@@ -35,36 +35,82 @@ B2_HD double stirling_tail(double k) {
       default: return 0.008330563433357696;
     }
   }
-  const double kp1 = k + 1.0;
-  const double kp1sq = kp1 * kp1;
-  return (1.0 / 12 - (1.0 / 360 - 1.0 / 1260 / kp1sq) / kp1sq) / kp1;
+  const double r = 1.0 / (k + 1.0);      // one division; Horner in r^2
+  const double r2 = r * r;
+  return r * (1.0 / 12 - r2 * (1.0 / 360 - r2 * (1.0 / 1260)));
+}
+
+// ---- BTRS in pieces, so the sequential sampler below and the lane state machine of
+// the class-split kernel (k1_resample.cuh) run the very same arithmetic ---------------
+struct BtrsConsts {
+  double nd, b, a, c, v_r, alpha, r, m;
+};
+
+// constants of Bin(n, p), 0 < p <= 1/2, n*p >= 10;  r = p / (1 - p) is passed in
+B2_HD BtrsConsts btrs_setup(int64_t n, double p, double r) {
+  BtrsConsts k;
+  k.nd = (double)n;
+  const double spq = sqrt(k.nd * p * (1.0 - p));
+  k.b = 1.15 + 2.53 * spq;
+  k.a = -0.0873 + 0.0248 * k.b + 0.01 * p;
+  k.c = k.nd * p + 0.5;
+  const double inv_b = 1.0 / k.b;
+  k.v_r = 0.92 - 4.2 * inv_b;
+  k.alpha = (2.83 + 5.1 * inv_b) * spq;
+  k.r = r;
+  k.m = floor((k.nd + 1.0) * p);
+  return k;
+}
+
+// One proposal from the words of attempt block w.  Returns +1 accepted by the squeeze
+// (~86 % of proposals), 0 needs the full test (out: k, inv_us, v), -1 rejected (k out
+// of range).
+B2_HD int btrs_propose(const BtrsConsts& q, const Words4& w, double* k_out, double* inv_us_out,
+                       double* v_out) {
+  const double u = uniform53(w.w[0], w.w[1]) - 0.5;
+  const double v = uniform53(w.w[2], w.w[3]);
+  const double us = 0.5 - fabs(u);
+  const double inv_us = 1.0 / us;
+  const double k = floor((2.0 * q.a * inv_us + q.b) * u + q.c);
+  *k_out = k;
+  *inv_us_out = inv_us;
+  *v_out = v;
+  if (us >= 0.07 && v <= q.v_r) return 1;
+  if (k < 0.0 || k > q.nd) return -1;
+  return 0;
+}
+
+// attempt-independent part of the acceptance bound
+B2_HD double btrs_head(const BtrsConsts& q) {
+  return (q.m + 0.5) * log((q.m + 1.0) / (q.r * (q.nd - q.m + 1.0))) + stirling_tail(q.m) +
+         stirling_tail(q.nd - q.m);
+}
+
+// full acceptance test of proposal k
+B2_HD bool btrs_accept(const BtrsConsts& q, double head, double k, double inv_us, double v) {
+  const double lhs = log(v * q.alpha / (q.a * inv_us * inv_us + q.b));
+  const double nk1 = q.nd - k + 1.0;
+  const double bound = head + (q.nd + 1.0) * log((q.nd - q.m + 1.0) / nk1) +
+                       (k + 0.5) * log(q.r * nk1 / (k + 1.0)) - stirling_tail(k) - stirling_tail(q.nd - k);
+  return lhs <= bound;
 }
 
 // Bin(n, p) for 0 < p <= 1/2 and n*p >= 10.
 B2_HD int64_t binomial_btrs(int64_t n, double p, const Stream& s) {
-  const double nd = (double)n;
-  const double spq = sqrt(nd * p * (1.0 - p));
-  const double b = 1.15 + 2.53 * spq;
-  const double a = -0.0873 + 0.0248 * b + 0.01 * p;
-  const double c = nd * p + 0.5;
-  const double v_r = 0.92 - 4.2 / b;
-  const double alpha = (2.83 + 5.1 / b) * spq;
-  const double r = p / (1.0 - p);
-  const double m = floor((nd + 1.0) * p);
+  const BtrsConsts q = btrs_setup(n, p, p / (1.0 - p));
+  double head = 0.0;
+  bool have_head = false;
   for (uint32_t attempt = 0;; ++attempt) {
     const Words4 w = stream_block(s, attempt);
-    const double u = uniform53(w.w[0], w.w[1]) - 0.5;
-    double v = uniform53(w.w[2], w.w[3]);
-    const double us = 0.5 - fabs(u);
-    const double k = floor((2.0 * a / us + b) * u + c);
-    if (us >= 0.07 && v <= v_r) return (int64_t)k;   // squeeze: ~86 % of attempts
-    if (k < 0.0 || k > nd) continue;
-    v = log(v * alpha / (a / (us * us) + b));
-    const double bound = (m + 0.5) * log((m + 1.0) / (r * (nd - m + 1.0))) +
-                         (nd + 1.0) * log((nd - m + 1.0) / (nd - k + 1.0)) +
-                         (k + 0.5) * log(r * (nd - k + 1.0) / (k + 1.0)) + stirling_tail(m) +
-                         stirling_tail(nd - m) - stirling_tail(k) - stirling_tail(nd - k);
-    if (v <= bound) return (int64_t)k;
+    double k, inv_us, v;
+    const int verdict = btrs_propose(q, w, &k, &inv_us, &v);
+    if (verdict > 0) return (int64_t)k;
+    if (verdict < 0) continue;
+    if (!have_head) {
+      head = btrs_head(q);
+      have_head = true;
+    }
+    if (btrs_accept(q, head, k, inv_us, v)) return (int64_t)k;
   }
 }
 

@@ -115,7 +115,14 @@ B2_HD uint32_t rotl32(uint32_t x, int r) {
 // class 0 for 8-byte elements); m7 = m << 7
 B2_HD void class_fields_shifted(uint32_t w, uint32_t m7, uint32_t* f) {
   f[0] = w & m7;
+#if defined(__CUDA_ARCH__)
+  // w >> 10 as a multiply-high keeps this shift off the (busier) ALU pipe
+  uint32_t hi;
+  asm("mul.hi.u32 %0, %1, 4194304;" : "=r"(hi) : "r"(w));
+  f[1] = hi & m7;
+#else
   f[1] = (w >> 10) & m7;
+#endif
   f[2] = rotl32(w, 12) & m7;
 }
 

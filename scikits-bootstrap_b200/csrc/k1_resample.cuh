@@ -23,6 +23,13 @@ namespace b200boot {
 constexpr int kK1Threads = 1024;
 constexpr int kK1Warps = kK1Threads / 32;
 constexpr int kSmemHeader = 128;  // mbarrier + work-item slot
+// sm_90+/sm_100: the first 1 KB of the shared window is reserved by the system, so a
+// kernel without static shared memory finds its dynamic shared memory at 0x400.  The
+// FAST kernel variant bakes cell address = 0x400 + header into LDS immediates (the
+// host selects it only when cudaDevAttrReservedSharedMemoryPerBlock == 1024 and the
+// kernel traps if the assumption does not hold).
+constexpr int kFastSmemBase = 1024 + kSmemHeader;
+constexpr int kFastStride2 = 8 << 13;   // bytes between the two arrays of a 2-array full tile
 
 // ------------------------------------------------------------------ K0 --------
 __global__ void __launch_bounds__(128) k0_tile_counts_kernel(uint64_t seed, int64_t resample_lo,
@@ -33,15 +40,20 @@ __global__ void __launch_bounds__(128) k0_tile_counts_kernel(uint64_t seed, int6
   tile_count_chain<int32_t>(seed, resample_lo + rl, plan, counts + rl, n_local);
 }
 
-// class occupancies of the full tiles: cls[(t * n_local + r) * 16 + c]
+// Class occupancies of the full tiles: cls[(t * n_local + r) * 16 + c]; one thread
+// walks the 15-step conditional-binomial chain of one (tile, resample) pair.
+// (A lane state machine that advances each lane independently was measured slower:
+// 123 registers and the FP64 pipe stays the limiter; see DESIGN.md.)
 __global__ void __launch_bounds__(128) k0_class_counts_kernel(uint64_t seed, int64_t resample_lo,
                                                               int64_t n_local, int64_t n_full,
                                                               const int32_t* __restrict__ counts,
                                                               int32_t* __restrict__ cls) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_full * n_local) return;
-  const int64_t t = e / n_local, rl = e - t * n_local;
-  class_count_chain<int32_t>(seed, resample_lo + rl, t, (int64_t)counts[e], cls + e * kClasses, 1);
+  const int64_t total = n_full * n_local;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t t = e / n_local, rl = e - t * n_local;
+    class_count_chain<int32_t>(seed, resample_lo + rl, t, (int64_t)__ldg(counts + e), cls + e * kClasses, 1);
+  }
 }
 
 // ------------------------------------------------------------------ K1 --------
@@ -86,6 +98,18 @@ struct LaneAcc {
 #pragma unroll
     for (int m = 0; m < NM; ++m) acc[m][j % W] += c[m];
   }
+  // Fast addressing: `off` is the byte offset inside array 0 and the shared-window
+  // address of the cell is the compile-time constant kFastSmemBase, so the load is a
+  // single LDS.64 [R + imm] with no address arithmetic.
+  __device__ __forceinline__ void take_fast(int j, uint32_t off) {
+    double v[NA], c[NM];
+    asm("ld.shared.f64 %0, [%1+%2];" : "=d"(v[0]) : "r"(off), "n"(kFastSmemBase));
+    if (NA == 2)
+      asm("ld.shared.f64 %0, [%1+%2];" : "=d"(v[NA - 1]) : "r"(off), "n"(kFastSmemBase + kFastStride2));
+    contribution<MS>(v, c);
+#pragma unroll
+    for (int m = 0; m < NM; ++m) acc[m][j % W] += c[m];
+  }
   __device__ __forceinline__ void finish(double* tot) {
 #pragma unroll
     for (int m = 0; m < NM; ++m) {
@@ -101,7 +125,7 @@ struct LaneAcc {
 // Full tile: lane = (class c = lane & 15, half h = lane >> 4).  The lane draws the
 // blocks q = h, h+2, ... of its class stream; every LDS.64 of a half-warp touches 16
 // distinct bank pairs (conflict-free).  12 draws per Philox block.
-template <int MS>
+template <int MS, bool FAST>
 __device__ __forceinline__ void class_accumulate(const unsigned char* __restrict__ s_bytes,
                                                  uint32_t stride_bytes, const RoundKeys& rk,
                                                  const Stream& st, int64_t n_c, uint32_t m7,
@@ -117,7 +141,12 @@ __device__ __forceinline__ void class_accumulate(const unsigned char* __restrict
       uint32_t f[3];
       class_fields_shifted(w.w[i], m7, f);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) A.take(3 * i + k, s_bytes, stride_bytes, f[k] | cbits);
+      for (int k = 0; k < 3; ++k) {
+        if (FAST)
+          A.take_fast(3 * i + k, f[k] | cbits);
+        else
+          A.take(3 * i + k, s_bytes, stride_bytes, f[k] | cbits);
+      }
     }
   }
   const int64_t done = (int64_t)n_full * kClassDrawsPerBlock;
@@ -154,7 +183,7 @@ __device__ __forceinline__ void lemire_accumulate(const unsigned char* __restric
   A.finish(tot);
 }
 
-template <int MS>
+template <int MS, bool FAST>
 __global__ void __launch_bounds__(kK1Threads, 1) k1_resample_kernel(const K1Params P) {
   constexpr int NA = MomTraits<MS>::kArrays;
   constexpr int NM = MomTraits<MS>::kMoments;
@@ -169,6 +198,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_resample_kernel(const K1Para
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
+  if (FAST && smem_u32(smem_raw) != 1024u) __trap();   // fast addressing assumption
   if (tid == 0) mbar_init(bar, 1);
   __syncthreads();
 
@@ -220,7 +250,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_resample_kernel(const K1Para
         const int c = lane & (kClasses - 1);
         const int64_t n_c = (int64_t)__ldg(P.cls + (t * P.n_local + rl) * kClasses + c);
         const Stream st = make_stream(P.seed, P.resample_lo + rl, class_cell_id(t, c), kPurposeIndex);
-        class_accumulate<MS>(s_bytes, stride_bytes, P.rk, st, n_c, m7, (uint32_t)c << 3,
+        class_accumulate<MS, FAST>(s_bytes, stride_bytes, P.rk, st, n_c, m7, (uint32_t)c << 3,
                              (uint32_t)lane >> 4, tot);
       } else {
         const int64_t n = P.counts ? (int64_t)__ldg(P.counts + t * P.n_local + rl) : P.plan.n_rows;
