@@ -80,37 +80,54 @@ B2_HD int btrs_propose(const BtrsConsts& q, const Words4& w, double* k_out, doub
   return 0;
 }
 
-// attempt-independent part of the acceptance bound
-B2_HD double btrs_head(const BtrsConsts& q) {
-  return (q.m + 0.5) * log((q.m + 1.0) / (q.r * (q.nd - q.m + 1.0))) + stirling_tail(q.m) +
-         stirling_tail(q.nd - q.m);
+// The full acceptance test is  log(v*alpha/(a/us^2+b)) <= head + t2 + t3  with four
+// terms of one shape, A*log(B/C) + sg*(tail(D)+tail(E)):
+//   term 0 (lhs)  A=1      B=v*alpha      C=a/us^2+b       sg=0
+//   term 1 (head) A=m+1/2  B=m+1          C=r(n-m+1)       sg=+1  D=m  E=n-m
+//   term 2        A=n+1    B=n-m+1        C=n-k+1          sg=0
+//   term 3        A=k+1/2  B=r(n-k+1)     C=k+1            sg=-1  D=k  E=n-k
+// Kept as one function so a warp can evaluate the terms of several pending proposals
+// side by side (k0_class_counts_kernel) with the arithmetic of the sequential sampler.
+B2_HD double btrs_term(int which, double nd, double m, double r, double k, double lhs_num,
+                       double lhs_den) {
+  double A, B, C, D, E, sg;
+  if (which == 0) {
+    A = 1.0; B = lhs_num; C = lhs_den; D = 100.0; E = 100.0; sg = 0.0;
+  } else if (which == 1) {
+    A = m + 0.5; B = m + 1.0; C = r * (nd - m + 1.0); D = m; E = nd - m; sg = 1.0;
+  } else if (which == 2) {
+    A = nd + 1.0; B = nd - m + 1.0; C = nd - k + 1.0; D = 100.0; E = 100.0; sg = 0.0;
+  } else {
+    A = k + 0.5; B = r * (nd - k + 1.0); C = k + 1.0; D = k; E = nd - k; sg = -1.0;
+  }
+  return A * log(B / C) + sg * (stirling_tail(D) + stirling_tail(E));
+}
+
+B2_HD void btrs_lhs_args(const BtrsConsts& q, double inv_us, double v, double* num, double* den) {
+  *num = v * q.alpha;
+  *den = q.a * inv_us * inv_us + q.b;
 }
 
 // full acceptance test of proposal k
-B2_HD bool btrs_accept(const BtrsConsts& q, double head, double k, double inv_us, double v) {
-  const double lhs = log(v * q.alpha / (q.a * inv_us * inv_us + q.b));
-  const double nk1 = q.nd - k + 1.0;
-  const double bound = head + (q.nd + 1.0) * log((q.nd - q.m + 1.0) / nk1) +
-                       (k + 0.5) * log(q.r * nk1 / (k + 1.0)) - stirling_tail(k) - stirling_tail(q.nd - k);
-  return lhs <= bound;
+B2_HD bool btrs_accept(const BtrsConsts& q, double k, double inv_us, double v) {
+  double num, den;
+  btrs_lhs_args(q, inv_us, v, &num, &den);
+  const double t0 = btrs_term(0, q.nd, q.m, q.r, k, num, den);
+  const double t1 = btrs_term(1, q.nd, q.m, q.r, k, num, den);
+  const double t2 = btrs_term(2, q.nd, q.m, q.r, k, num, den);
+  const double t3 = btrs_term(3, q.nd, q.m, q.r, k, num, den);
+  return t0 <= (t1 + t2) + t3;
 }
 
 // Bin(n, p) for 0 < p <= 1/2 and n*p >= 10.
 B2_HD int64_t binomial_btrs(int64_t n, double p, const Stream& s) {
   const BtrsConsts q = btrs_setup(n, p, p / (1.0 - p));
-  double head = 0.0;
-  bool have_head = false;
   for (uint32_t attempt = 0;; ++attempt) {
     const Words4 w = stream_block(s, attempt);
     double k, inv_us, v;
     const int verdict = btrs_propose(q, w, &k, &inv_us, &v);
     if (verdict > 0) return (int64_t)k;
-    if (verdict < 0) continue;
-    if (!have_head) {
-      head = btrs_head(q);
-      have_head = true;
-    }
-    if (btrs_accept(q, head, k, inv_us, v)) return (int64_t)k;
+    if (verdict == 0 && btrs_accept(q, k, inv_us, v)) return (int64_t)k;
   }
 }
 

@@ -42,8 +42,11 @@ __global__ void __launch_bounds__(128) k0_tile_counts_kernel(uint64_t seed, int6
 
 // Class occupancies of the full tiles: cls[(t * n_local + r) * 16 + c]; one thread
 // walks the 15-step conditional-binomial chain of one (tile, resample) pair.
-// (A lane state machine that advances each lane independently was measured slower:
-// 123 registers and the FP64 pipe stays the limiter; see DESIGN.md.)
+// Measured alternatives that were NOT faster on B200 (42 ms at cfg5 either way, see
+// DESIGN.md): a per-lane state machine that lets lanes advance independently (123
+// registers, 55 ms), and a warp-cooperative evaluation of the full acceptance test
+// (thread efficiency 12 -> 20 of 32, same time: the kernel is bound by issue slots of
+// the divergent proposal rounds, not by the FP64 pipe).
 __global__ void __launch_bounds__(128) k0_class_counts_kernel(uint64_t seed, int64_t resample_lo,
                                                               int64_t n_local, int64_t n_full,
                                                               const int32_t* __restrict__ counts,
