@@ -102,17 +102,32 @@ def workspace_for(stat_id: int, n_rows: int, n_arrays: int, n_cols: int, n_local
     return _ws.get(need)
 
 
+def _ws_budget() -> int:
+    """Upper bound on the scratch a single K1 call may use (bytes); larger jobs are
+    processed as consecutive resample sub-ranges, which cannot change the result
+    because every resample depends only on (seed, resample id)."""
+    import os
+    return int(os.environ.get("B200BOOT_WS_BYTES", 12 << 30))
+
+
 def resample_stat(arrays: Sequence, stat_id: int, seed: int, lo: int, hi: int, out=None):
     """K1 on contiguous float64[N] CUDA tensors -> float64[hi-lo] CUDA tensor."""
     torch = _torch()
+    L = _abi.lib()
     n_rows = arrays[0].numel()
     n_local = hi - lo
     if out is None:
         out = torch.empty(n_local, dtype=torch.float64, device=arrays[0].device)
-    ws, wsz = workspace_for(stat_id, n_rows, len(arrays), 1, n_local, 1)
+    step = max(n_local, 1)
+    budget = _ws_budget()
+    while step > 32 and L.b200boot_workspace_bytes(stat_id, n_rows, len(arrays), 1, step, 1) > budget:
+        step = (step + 1) // 2
     ptrs = _ptr_array(arrays)
-    _abi.check(_abi.lib().b200boot_resample_stat(ptrs, len(arrays), n_rows, stat_id, seed, lo, hi,
-                                                 out.data_ptr(), ws, wsz, stream_ptr()))
+    for a in range(lo, hi, step):
+        b = min(hi, a + step)
+        ws, wsz = workspace_for(stat_id, n_rows, len(arrays), 1, b - a, 1)
+        _abi.check(L.b200boot_resample_stat(ptrs, len(arrays), n_rows, stat_id, seed, a, b,
+                                            out[a - lo:].data_ptr(), ws, wsz, stream_ptr()))
     return out
 
 

@@ -485,6 +485,15 @@ def test_shards_reproduce_the_single_gpu_statistics():
         assert_array_equal(np.concatenate(parts), full)
 
 
+def test_workspace_budget_chunks_do_not_change_results(monkeypatch):
+    """Large jobs are run as consecutive resample sub-ranges under a scratch budget."""
+    x = dev(np.random.default_rng(2).standard_normal(70000))
+    full = _device.resample_stat([x], _abi.STAT_MEAN, 3, 0, 900).cpu().numpy()
+    monkeypatch.setenv("B200BOOT_WS_BYTES", str(4 << 20))
+    part = _device.resample_stat([x], _abi.STAT_MEAN, 3, 0, 900).cpu().numpy()
+    assert_array_equal(part, full)
+
+
 # ------------------------------------------------------------------ statistics ---
 
 def test_philox_path_agrees_statistically_with_pcg64_path():
