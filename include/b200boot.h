@@ -113,6 +113,18 @@ int b200boot_resample_median_columns_indexed(const double* data, int64_t n_rows,
                                              int64_t ld, const int64_t* indices, int64_t n_sets,
                                              double* stat_out, void* ws, size_t ws_bytes, void* stream);
 
+/* K1mt — median of a long 1-D array in rank space (n_rows beyond the 28 672-row
+ * resident limit of K1m).  `sorted_vals` is the data sorted ascending (e.g. by
+ * b200boot_sort_columns); the resample is sorted_vals[indices] with `indices` exactly
+ * what b200boot_fill_indices yields for (seed, n_rows, 1 array).  Only the tile that
+ * holds the middle rank is drawn: O(n_tiles + tile) work per resample.
+ * stat_out: float64[resample_hi - resample_lo]. */
+int b200boot_resample_median_sorted(const double* sorted_vals, int64_t n_rows, uint64_t seed,
+                                    int64_t resample_lo, int64_t resample_hi, double* stat_out, void* ws,
+                                    size_t ws_bytes, void* stream);
+/* K3m on a sorted 1-D array of any length: out float64[8] as b200boot_jackknife. */
+int b200boot_jackknife_median_sorted(const double* sorted_vals, int64_t n_rows, double* out, void* stream);
+
 /* K2 — materialises exactly the indices K1 draws; backs the Python
  * `bootstrap_indices` iterator (bootstrap.py:667-680).
  * out: int64[resample_hi - resample_lo][N] row-major.  `n_arrays` selects the

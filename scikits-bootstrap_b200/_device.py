@@ -168,6 +168,35 @@ def resample_median_columns_indexed(data2d, indices):
     return out
 
 
+MEDIAN_RESIDENT_ROWS = 28672     # csrc/k1m_median.cuh: kMedMaxRows
+
+
+def sorted_copy(x1d):
+    """Ascending device sort of a 1-D float64 tensor (copy)."""
+    s = x1d.reshape(1, -1).clone()
+    sort_columns(s)
+    return s.reshape(-1)
+
+
+def resample_median_sorted(sorted_vals, seed: int, lo: int, hi: int):
+    """K1mt: median of sorted_vals[bootstrap indices] for resamples [lo, hi) -> float64[1][hi-lo]."""
+    torch = _torch()
+    n_rows = sorted_vals.numel()
+    out = torch.empty((1, hi - lo), dtype=torch.float64, device=sorted_vals.device)
+    ws, wsz = workspace_for(_abi.STAT_MEDIAN, n_rows, 1, 1, hi - lo, 1)
+    _abi.check(_abi.lib().b200boot_resample_median_sorted(sorted_vals.data_ptr(), n_rows, seed, lo, hi,
+                                                          out.data_ptr(), ws, wsz, stream_ptr()))
+    return out
+
+
+def jackknife_median_sorted(sorted_vals):
+    torch = _torch()
+    out = torch.empty((1, 8), dtype=torch.float64, device=sorted_vals.device)
+    _abi.check(_abi.lib().b200boot_jackknife_median_sorted(sorted_vals.data_ptr(), sorted_vals.numel(),
+                                                           out.data_ptr(), stream_ptr()))
+    return out
+
+
 def fill_indices(seed: int, n_rows: int, n_arrays: int, lo: int, hi: int):
     """K2 -> int64[hi-lo][N] CUDA tensor."""
     torch = require_cuda()

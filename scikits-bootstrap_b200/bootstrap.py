@@ -139,6 +139,7 @@ class _Run:
         self.lo, self.hi = _dist.shard_range(self.n_samples, self.rank, self.world)
         self._columns = None
         self._jack = None
+        self._sorted_vals = None
 
     # -- data views ------------------------------------------------------------
     def columns(self):
@@ -147,6 +148,27 @@ class _Run:
             self._columns = self.dev[0].t().contiguous()
         return self._columns
 
+    # -- long 1-D median: rank-space path over the sorted data --------------------
+    def _long_median(self) -> bool:
+        """np.median over more rows than fit in shared memory: the resample is taken in
+        rank space, i.e. it is sorted(x)[bootstrap_indices(...)] (same distribution as
+        x[bootstrap_indices(...)] for this permutation-invariant statistic)."""
+        if self.spec.stat_id != _abi.STAT_MEDIAN or self.dev[0].shape[0] <= _device.MEDIAN_RESIDENT_ROWS:
+            return False
+        if self.vector and self.n_cols > 1:
+            raise NotImplementedError(
+                "median over (N, D) data with D > 1 needs N <= {} rows (columns share one index set "
+                "in row space)".format(_device.MEDIAN_RESIDENT_ROWS))
+        if self.indices is not None:
+            raise NotImplementedError("index-supplied median needs N <= {} rows".format(
+                _device.MEDIAN_RESIDENT_ROWS))
+        return True
+
+    def _sorted(self):
+        if self._sorted_vals is None:
+            self._sorted_vals = _device.sorted_copy(self.dev[0].reshape(-1))
+        return self._sorted_vals
+
     # -- K1 ----------------------------------------------------------------------
     def resample(self):
         torch = _device._torch()
@@ -154,6 +176,8 @@ class _Run:
         if self.indices is not None:
             return self._resample_indexed()
         if spec.stat_id == _abi.STAT_MEDIAN:
+            if self._long_median():
+                return _device.resample_median_sorted(self._sorted(), self.key, lo, hi)
             data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
             return _device.resample_median_columns(data2d, self.key, lo, hi)
         if spec.independent:
@@ -202,8 +226,11 @@ class _Run:
         torch = _device._torch()
         spec = self.spec
         if spec.stat_id == _abi.STAT_MEDIAN:
-            data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
-            j = _device.jackknife_median_columns(data2d)
+            if self._long_median():
+                j = _device.jackknife_median_sorted(self._sorted())
+            else:
+                data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
+                j = _device.jackknife_median_columns(data2d)
         elif spec.independent:
             j = self._jackknife_independent()
         elif self.vector:

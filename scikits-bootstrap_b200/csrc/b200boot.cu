@@ -179,7 +179,7 @@ int jack_passes(const double** rows, int64_t n_rows, int stat, ResampleWs& w, do
                 cudaStream_t s) {
   const double n = (double)n_rows;
   int rc = run_reduction<MomTraits<MS>::kMoments>(n_rows, ContributionF<MS>{rows[0], rows[1]},
-                                                  StoreTotalsG<MS>{w.jack, stat, n}, w.red, s);
+                                                  StoreTotalsG<MS>{w.jack, stat, n, rows[0], rows[1]}, w.red, s);
   if (rc) return rc;
   rc = run_reduction<1>(n_rows, JackSumF<MS>{w.jack, stat, n, rows[0], rows[1]}, StoreJmeanG{w.jack, n},
                         w.red, s);
@@ -565,6 +565,17 @@ int b200boot_resample_median_columns_indexed(const double* data, int64_t n_rows,
 int b200boot_jackknife_median_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld,
                                       double* out, void* ws, size_t ws_bytes, void* stream) {
   return median_jackknife(data, n_rows, n_cols, ld, out, ws, ws_bytes, as_stream(stream));
+}
+
+int b200boot_resample_median_sorted(const double* sorted_vals, int64_t n_rows, uint64_t seed,
+                                    int64_t resample_lo, int64_t resample_hi, double* stat_out, void* ws,
+                                    size_t ws_bytes, void* stream) {
+  return median_resample_sorted(sorted_vals, n_rows, seed, resample_lo, resample_hi, stat_out, ws, ws_bytes,
+                                as_stream(stream));
+}
+
+int b200boot_jackknife_median_sorted(const double* sorted_vals, int64_t n_rows, double* out, void* stream) {
+  return median_jackknife_sorted(sorted_vals, n_rows, out, as_stream(stream));
 }
 
 // ---- instrumentation ---------------------------------------------------------------

@@ -15,6 +15,7 @@
 #pragma once
 #include "common.cuh"
 #include "draw.cuh"
+#include "k1_resample.cuh"
 #include "k45_interval.cuh"
 
 namespace b200boot {
@@ -266,9 +267,12 @@ __global__ void __launch_bounds__(256) k3m_jackknife_median_kernel(const double*
   __shared__ double s_red[8];
   const int64_t d = blockIdx.x;
   const double* sv = sorted_vals + d * n;
+  // accumulate relative to the first leave-one-out value: identical values give
+  // d == 0 exactly (undefined acceleration) rather than rounding noise
+  const double u = loo_median(sv, n, 0);
   double acc = 0.0;
-  for (int64_t r = threadIdx.x; r < n; r += 256) acc += loo_median(sv, n, r);
-  const double jmean = block_sum_256(acc, s_red) / (double)n;
+  for (int64_t r = threadIdx.x; r < n; r += 256) acc += loo_median(sv, n, r) - u;
+  const double jmean = u + block_sum_256(acc, s_red) / (double)n;
   double a2 = 0.0, a3 = 0.0;
   for (int64_t r = threadIdx.x; r < n; r += 256) {
     const double dv = jmean - loo_median(sv, n, r);
@@ -285,6 +289,156 @@ __global__ void __launch_bounds__(256) k3m_jackknife_median_kernel(const double*
     o[3] = d3;
     o[4] = d3 / (6.0 * pow(d2, 1.5));
     o[5] = o[6] = o[7] = 0.0;
+  }
+}
+
+// ---- K1mt: median of a long 1-D array in rank space ----------------------------------
+// For N beyond the shared-memory-resident limit the data are sorted once and the tile
+// plan of K1 is laid over the SORTED array.  The median's tile follows from the tile
+// occupancies alone (prefix sum over the K0 counts); only that one tile's draws are
+// generated (same class / Lemire streams as K1 and K2) and histogrammed over the
+// tile's positions, and a scan finds the sorted position holding the middle rank.
+// Cost per resample is O(T + tile) instead of O(N).  The resample is, by
+// construction, sorted(x)[bootstrap_indices(...)]: see DESIGN.md.
+constexpr int kMtThreads = 256;
+
+struct K1mtParams {
+  const double* sorted_vals;   // [N] ascending
+  Plan plan;
+  uint64_t seed;
+  int64_t resample_lo, n_local;
+  const int32_t* counts;       // [n_tiles][n_local]
+  double* out;                 // [n_local]
+};
+
+// CTA-wide exclusive scan of one value per thread; returns the exclusive prefix and the
+// total through *total (s_scan holds kMtThreads / 32 + 1 words)
+__device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t* s_scan, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
+    if (lane >= off) inc += o;
+  }
+  __syncthreads();
+  if (lane == 31) s_scan[warp] = inc;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+  for (int w = 0; w < kMtThreads / 32; ++w) {
+    const uint32_t x = s_scan[w];
+    if (w < warp) base += x;
+    tot += x;
+  }
+  *total = tot;
+  return base + inc - v;
+}
+
+__global__ void __launch_bounds__(kMtThreads) k1mt_median_tiled_kernel(const K1mtParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw);              // packed u16 pairs, tile/2 words
+  __shared__ uint32_t s_scan[kMtThreads / 32 + 1];
+  __shared__ int32_t s_cls[kClasses];
+  __shared__ int32_t s_blk[kClasses + 1];
+  __shared__ long long s_found[2];                                       // tile, draws before it
+  __shared__ int s_pos;
+  const int tid = threadIdx.x;
+  const Plan& plan = P.plan;
+  const int64_t n = plan.n_rows;
+  const int64_t tile = plan.tile();
+  const uint32_t m7 = ((1u << (plan.log2_tile - 4)) - 1u) << 7;
+  const int n_ranks = (n & 1) ? 1 : 2;
+  const int64_t rank0 = (n & 1) ? n / 2 : n / 2 - 1;                      // 0-based middle rank(s)
+
+  for (int64_t rl = blockIdx.x; rl < P.n_local; rl += gridDim.x) {
+    const int64_t r = P.resample_lo + rl;
+    int64_t hist_tile = -1;
+    double vals[2] = {0.0, 0.0};
+    for (int which = 0; which < n_ranks; ++which) {
+      const int64_t rank = rank0 + which;
+      // (a) tile holding the rank: first t with cumulative occupancy > rank
+      if (tid == 0) s_found[0] = -1;
+      __syncthreads();
+      int64_t carried = 0;
+      for (int64_t t0 = 0; t0 < plan.n_tiles; t0 += kMtThreads) {
+        const int64_t t = t0 + tid;
+        const uint32_t c = t < plan.n_tiles ? (uint32_t)__ldg(P.counts + t * P.n_local + rl) : 0u;
+        uint32_t total;
+        const uint32_t excl = cta_exclusive_scan(c, s_scan, &total);
+        const int64_t before = carried + excl;
+        if (t < plan.n_tiles && before <= rank && rank < before + (int64_t)c) {
+          s_found[0] = t;
+          s_found[1] = before;
+        }
+        carried += total;
+        __syncthreads();
+        if (s_found[0] >= 0) break;
+      }
+      const int64_t t_star = s_found[0];
+      const uint32_t j = (uint32_t)(rank - s_found[1]);                    // rank inside the tile
+      const int64_t sz = plan.cell_size(t_star);
+      // (b) histogram of the tile's draws over its positions
+      if (t_star != hist_tile) {
+        const int words = (int)((sz + 2) / 2);
+        for (int i = tid; i < words; i += kMtThreads) s_hist[i] = 0u;
+        const int64_t n_t = (int64_t)__ldg(P.counts + t_star * P.n_local + rl);
+        if (t_star < plan.n_full) {
+          if (tid == 0) {
+            class_count_chain<int32_t>(P.seed, r, t_star, n_t, s_cls, 1);
+            int acc = 0;
+            for (int c = 0; c < kClasses; ++c) {
+              s_blk[c] = acc;
+              acc += (s_cls[c] + kClassDrawsPerBlock - 1) / kClassDrawsPerBlock;
+            }
+            s_blk[kClasses] = acc;
+          }
+          __syncthreads();
+          const int n_blocks = s_blk[kClasses];
+          for (int b = tid; b < n_blocks; b += kMtThreads) {
+            int c = 0;
+            while (b >= s_blk[c + 1]) ++c;
+            const Stream st = make_stream(P.seed, r, class_cell_id(t_star, c), kPurposeIndex);
+            class_block<true>(st, (uint32_t)(b - s_blk[c]), m7, c, (int64_t)s_cls[c],
+                              [&](int, int64_t, uint32_t idx) { atomicAdd(s_hist + (idx >> 1), 1u << ((idx & 1u) * 16)); });
+          }
+        } else {
+          __syncthreads();
+          const Stream st = make_stream(P.seed, r, (uint32_t)t_star, kPurposeIndex);
+          const uint32_t thresh = lemire_threshold((uint32_t)sz);
+          const int n_blocks = (int)((n_t + 3) / 4);
+          for (int b = tid; b < n_blocks; b += kMtThreads)
+            lemire_block<true>(st, (uint32_t)b, (uint32_t)sz, thresh, n_t,
+                               [&](int, int64_t, uint32_t idx) { atomicAdd(s_hist + (idx >> 1), 1u << ((idx & 1u) * 16)); });
+        }
+        __syncthreads();
+        hist_tile = t_star;
+      }
+      // (c) first position whose cumulative count exceeds j
+      const uint16_t* h16 = reinterpret_cast<const uint16_t*>(s_hist);
+      const int per = (int)((sz + kMtThreads - 1) / kMtThreads);
+      const int p0 = tid * per;
+      uint32_t mine = 0;
+      for (int i = 0; i < per; ++i)
+        if (p0 + i < sz) mine += h16[p0 + i];
+      uint32_t total;
+      const uint32_t excl = cta_exclusive_scan(mine, s_scan, &total);
+      if (excl <= j && j < excl + mine) {
+        uint32_t run = excl;
+        for (int i = 0; i < per; ++i) {
+          run += h16[p0 + i];
+          if (run > j) {
+            s_pos = p0 + i;
+            break;
+          }
+        }
+      }
+      __syncthreads();
+      const int64_t row0 = t_star < plan.n_full ? (t_star << plan.log2_tile) : (plan.n_full << plan.log2_tile);
+      vals[which] = P.sorted_vals[row0 + s_pos];
+      __syncthreads();
+    }
+    if (tid == 0) P.out[rl] = n_ranks == 1 ? vals[0] : (vals[0] + vals[1]) / 2.0;
+    (void)tile;
   }
 }
 
@@ -312,7 +466,11 @@ inline MedianWs median_carve(Carver& cv, int64_t n_rows, int64_t n_cols) {
   return w;
 }
 
-inline size_t median_ws_bytes(int64_t n_rows, int64_t n_cols, int64_t) {
+inline size_t median_ws_bytes(int64_t n_rows, int64_t n_cols, int64_t n_local) {
+  if (n_rows > kMedMaxRows) {   // sorted 1-D path: tile occupancies only
+    const Plan plan = make_plan(n_rows, 1);
+    return pad256((size_t)plan.n_tiles * (size_t)(n_local > 0 ? n_local : 1) * 4);
+  }
   Carver cv(reinterpret_cast<void*>(256), ~(size_t)0 >> 1);
   median_carve(cv, n_rows, n_cols);
   return cv.used;
@@ -423,6 +581,55 @@ inline int median_resample(const double* data, int64_t n_rows, int64_t n_cols, i
   }
   const int grid = (int)std::min<int64_t>(sms, P.n_items);
   k1m_median_kernel<<<grid, kMedThreads, smem, s>>>(P);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+// Median of a long sorted 1-D array (n_rows beyond the resident limit).
+inline int median_resample_sorted(const double* sorted_vals, int64_t n_rows, uint64_t seed,
+                                  int64_t resample_lo, int64_t resample_hi, double* stat_out, void* ws,
+                                  size_t ws_bytes, cudaStream_t s) {
+  if (!sorted_vals || !stat_out || n_rows < 1 || n_rows >= ((int64_t)1 << 31))
+    return fail(B200BOOT_EINVAL, "median_sorted: bad arguments");
+  const int64_t n_local = resample_hi - resample_lo;
+  if (n_local < 0 || resample_lo < 0) return fail(B200BOOT_EINVAL, "bad resample range");
+  if (n_local == 0) return 0;
+  const Plan plan = make_plan(n_rows, 1);
+  if (plan.n_tiles <= 1)
+    return fail(B200BOOT_EINVAL, "median_sorted is for multi-tile plans; use resample_median_columns");
+  if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
+    return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
+  Carver cv(ws, ws_bytes);
+  int32_t* counts = cv.take<int32_t>((size_t)plan.n_tiles * n_local);
+  if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+  k0_tile_counts_kernel<<<(unsigned)((n_local + 127) / 128), 128, 0, s>>>(seed, resample_lo, n_local, plan,
+                                                                        counts);
+  B2_LAUNCH_CHECK();
+  K1mtParams P{};
+  P.sorted_vals = sorted_vals;
+  P.plan = plan;
+  P.seed = seed;
+  P.resample_lo = resample_lo;
+  P.n_local = n_local;
+  P.counts = counts;
+  P.out = stat_out;
+  const size_t smem = (size_t)(plan.tile() + 2) * 2 + 16;
+  static bool configured[64] = {false};
+  int dev = 0;
+  B2_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    B2_CUDA(cudaFuncSetAttribute(k1mt_median_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  const int grid = (int)std::min<int64_t>((int64_t)sm_count() * 6, n_local);
+  k1mt_median_tiled_kernel<<<grid, kMtThreads, smem, s>>>(P);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+inline int median_jackknife_sorted(const double* sorted_vals, int64_t n_rows, double* out, cudaStream_t s) {
+  if (!sorted_vals || !out || n_rows < 1) return fail(B200BOOT_EINVAL, "bad arguments");
+  k3m_jackknife_median_kernel<<<1, 256, 0, s>>>(sorted_vals, n_rows, out);
   B2_LAUNCH_CHECK();
   return 0;
 }

@@ -19,6 +19,7 @@ struct JackState {
   double center[2];          // per-array mean used for pre-centring
   double tot[kMaxMoments];   // contribution totals over all rows
   double ostat;              // statistic on the data itself
+  double j0;                 // leave-one-out statistic of row 0 (shift of the jackknife mean)
   double jmean;              // mean of the leave-one-out statistics
   double d2, d3;             // sum (jmean - j_i)^2, ^3
   double accel;              // d3 / (6 d2^1.5)
@@ -125,9 +126,20 @@ struct StoreTotalsG {
   JackState* st;
   int stat;
   double n;
+  const double* d0;
+  const double* d1;
   __device__ void operator()(const double* tot) const {
     for (int k = 0; k < MomTraits<MS>::kMoments; ++k) st->tot[k] = tot[k];
     st->ostat = finish_stat(stat, tot, n);
+    // leave-one-out value of row 0: the jackknife mean is accumulated relative to it,
+    // so identical leave-one-out values give d == 0 exactly (acceleration undefined,
+    // as the reference intends: bootstrap.py:616-625) instead of rounding noise
+    double v[2], c[kMaxMoments], m[kMaxMoments];
+    v[0] = d0[0];
+    v[1] = (MomTraits<MS>::kArrays == 2) ? d1[0] : 0.0;
+    contribution<MS>(v, c);
+    for (int k = 0; k < MomTraits<MS>::kMoments; ++k) m[k] = tot[k] - c[k];
+    st->j0 = finish_stat(stat, m, n - 1.0);
   }
 };
 
@@ -151,13 +163,13 @@ struct JackSumF {
   const double* d0;
   const double* d1;
   __device__ void operator()(int64_t i, double* v) const {
-    v[0] = leave_one_out<MS>(st, stat, n, d0, d1, i);
+    v[0] = leave_one_out<MS>(st, stat, n, d0, d1, i) - st->j0;
   }
 };
 struct StoreJmeanG {
   JackState* st;
   double n;
-  __device__ void operator()(const double* tot) const { st->jmean = tot[0] / n; }
+  __device__ void operator()(const double* tot) const { st->jmean = st->j0 + tot[0] / n; }
 };
 
 template <int MS>

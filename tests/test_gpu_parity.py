@@ -219,6 +219,28 @@ def test_fused_median_1d(n):
         assert_array_equal(got, ref)
 
 
+@pytest.mark.parametrize("n", [28673, 40000, 100001, 16384 * 4])
+def test_long_median_runs_in_rank_space(n):
+    """Beyond the resident limit the median is taken over sorted(x)[bootstrap_indices]:
+    only the tile holding the middle rank is drawn (K1mt)."""
+    import warnings
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n) if n % 2 else np.round(rng.standard_normal(n), 3)      # ties too
+    m = 200
+    idx = np.array(list(boot.bootstrap_indices(x, m, seed=n)))
+    xs = np.sort(x)
+    want = np.sort(np.median(xs[idx], axis=1))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out, dist = boot.ci(x, np.median, n_samples=m, seed=n, method="pi", return_dist=True)
+        assert_array_equal(dist, want)
+        got = boot.ci(x, np.median, n_samples=m, seed=n, method="bca")
+        ref = orc.ci_from_indices((xs,), np.median, idx, (0.025, 0.975), m, "bca", jstat=orc.jack_median(xs))
+    assert_array_equal(got, ref)
+    with pytest.raises(NotImplementedError):
+        boot.ci(np.stack([x, x], axis=1), boot.median_axis0, n_samples=10)
+
+
 def test_fused_median_columns_share_the_index_set():
     """cfg4 shape in miniature: (N, D) data, median over axis 0, BCa, plus pval."""
     rng = np.random.default_rng(4)
