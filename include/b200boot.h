@@ -133,6 +133,19 @@ int b200boot_fill_indices(uint64_t seed, int64_t n_rows, int n_arrays, int64_t r
                           int64_t resample_hi, int64_t* out, void* ws, size_t ws_bytes,
                           void* stream);
 
+/* K2b — moving-block bootstrap index sets (bootstrap.py:747-787): ceil(N/L) block
+ * starts per resample, uniform on [0, N) when `wrap` else on [0, N-L) as numpy's
+ * half-open draw gives; indices start+0..L-1 (mod N when wrapping), truncated to N.
+ * out: int64[resample_hi - resample_lo][N]. */
+int b200boot_fill_moving_block(uint64_t seed, int64_t n_rows, int64_t block_length, int wrap,
+                               int64_t resample_lo, int64_t resample_hi, int64_t* out, void* stream);
+
+/* K2c — subsamples without replacement (bootstrap.py:717-744): per sample the first
+ * `size` entries of a uniform random permutation of 0..N-1 (argsort of 63-bit Philox
+ * keys).  out: int64[sample_hi - sample_lo][size]; ws: 12 bytes per padded row entry. */
+int b200boot_fill_subsample(uint64_t seed, int64_t n_rows, int64_t size, int64_t sample_lo,
+                            int64_t sample_hi, int64_t* out, void* ws, size_t ws_bytes, void* stream);
+
 /* Occupancies of the multinomial chain (K0), for inspection and tests:
  * counts int32[n_tiles][n_local]; class_counts (may be NULL) int32[n_full][n_local][16],
  * the split of every full tile's draws over its 16 shared-memory bank classes.

@@ -472,13 +472,14 @@ def class_draws(seed: int, resample: int, tile: int, c: int, n_draws: int, log2_
     return (j.reshape(-1)[:n_draws].astype(np.int64)) * N_CLASSES + c
 
 
-def cell_draws_lemire(seed: int, resample: int, cell: int, n_draws: int, size: int) -> np.ndarray:
+def cell_draws_lemire(seed: int, resample: int, cell: int, n_draws: int, size: int,
+                      purpose: int = 0) -> np.ndarray:
     """Indices in [0, size) for one (resample, cell): one 32-bit word per index,
     Lemire multiply-shift; a word whose low product falls below 2^32 mod size is
     rejected and redrawn from the PURPOSE_REDRAW stream keyed by the position."""
     nblk = (n_draws + 3) // 4
     key = seed_key(seed)
-    words = philox4x32_10(_ctr(np.arange(nblk), cell, resample, PURPOSE_INDEX), key)
+    words = philox4x32_10(_ctr(np.arange(nblk), cell, resample, purpose), key)
     words = words.reshape(-1)[:n_draws].astype(np.uint64)
     prod = words * np.uint64(size)
     idx = (prod >> np.uint64(32)).astype(np.int64)
@@ -535,6 +536,56 @@ def device_indices(seed: int, resample: int, n_obs: int, log2_tile: int,
         else:
             parts.append(cell_draws_lemire(seed, resample, cell_base + t, cnt, sz) + t * m)
     return np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+
+
+# --------------------------------------------------------------------------
+# Moving-block and subsample plans: reference restatements (PCG64) and the device
+# streams (csrc/k1_resample.cuh: k2_moving_block_kernel, k2_shuffle_keys_kernel).
+# --------------------------------------------------------------------------
+
+PURPOSE_BLOCK = 3
+PURPOSE_SHUFFLE = 4
+
+
+def moving_block_indices_pcg64(n_obs: int, n_samples: int, block_length: int = 3, wrap: bool = False,
+                               seed=None) -> Iterator[np.ndarray]:
+    """bootstrap.py:772-787: ceil(N/L) block starts from rng.integers(0, last_block),
+    expanded to start+0..L-1, cut to N (mod N when wrapping)."""
+    rng = np.random.default_rng(seed)
+    n_blocks = -(-n_obs // block_length)
+    last_block = n_obs if wrap else n_obs - block_length
+    steps = np.arange(block_length)
+    for _ in range(n_samples):
+        starts = rng.integers(0, last_block, size=n_blocks)
+        idx = (starts[:, None] + steps[None, :]).ravel()[:n_obs]
+        yield np.mod(idx, n_obs) if wrap else idx
+
+
+def subsample_indices_pcg64(n_obs: int, n_samples: int, size: int, seed=None) -> np.ndarray:
+    """bootstrap.py:741-744 for an absolute size: shuffle each row, keep the first `size`."""
+    rng = np.random.default_rng(seed)
+    base = np.tile(np.arange(n_obs), (n_samples, 1))
+    for row in base:
+        rng.shuffle(row)
+    return base[:, :size]
+
+
+def device_moving_block(seed: int, resample: int, n_obs: int, block_length: int, wrap: bool) -> np.ndarray:
+    n_blocks = -(-n_obs // block_length)
+    bound = n_obs if wrap else n_obs - block_length
+    starts = cell_draws_lemire(seed, resample, 0, n_blocks, bound, purpose=PURPOSE_BLOCK)
+    idx = (starts[:, None] + np.arange(block_length)[None, :]).ravel()[:n_obs]
+    return np.mod(idx, n_obs) if wrap else idx
+
+
+def device_subsample(seed: int, sample: int, n_obs: int, size: int) -> np.ndarray:
+    """First `size` rows of the permutation that sorts the 63-bit Philox keys
+    (ties broken by row number)."""
+    nblk = (n_obs + 1) // 2
+    w = philox4x32_10(_ctr(np.arange(nblk), 0, sample, PURPOSE_SHUFFLE), seed_key(seed)).astype(np.uint64)
+    keys = np.stack(((w[:, 0] << np.uint64(32)) | w[:, 1], (w[:, 2] << np.uint64(32)) | w[:, 3]), axis=1)
+    keys = (keys.reshape(-1)[:n_obs]) >> np.uint64(1)
+    return np.lexsort((np.arange(n_obs), keys))[:size].astype(np.int64)
 
 
 # --------------------------------------------------------------------------

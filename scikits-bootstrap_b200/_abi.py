@@ -42,6 +42,8 @@ SIGNATURES = {
     "b200boot_resample_median_sorted": (_int, [_vp, _i64, _u64, _i64, _i64, _vp, _vp, _sz, _vp]),
     "b200boot_jackknife_median_sorted": (_int, [_vp, _i64, _vp, _vp]),
     "b200boot_fill_indices": (_int, [_u64, _i64, _int, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "b200boot_fill_moving_block": (_int, [_u64, _i64, _i64, _int, _i64, _i64, _vp, _vp]),
+    "b200boot_fill_subsample": (_int, [_u64, _i64, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
     "b200boot_tile_counts": (_int, [_u64, _i64, _int, _i64, _i64, _vp, _vp, _vp]),
     "b200boot_gather": (_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "b200boot_jackknife": (_int, [_vp, _int, _i64, _int, _vp, _vp, _sz, _vp]),

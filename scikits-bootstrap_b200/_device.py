@@ -208,6 +208,28 @@ def fill_indices(seed: int, n_rows: int, n_arrays: int, lo: int, hi: int):
     return out
 
 
+def fill_moving_block(seed: int, n_rows: int, block_length: int, wrap: bool, lo: int, hi: int):
+    """K2b -> int64[hi-lo][N] CUDA tensor."""
+    torch = require_cuda()
+    out = torch.empty((hi - lo, n_rows), dtype=torch.int64, device="cuda")
+    _abi.check(_abi.lib().b200boot_fill_moving_block(seed, n_rows, block_length, int(bool(wrap)), lo, hi,
+                                                     out.data_ptr(), stream_ptr()))
+    return out
+
+
+def fill_subsample(seed: int, n_rows: int, size: int, lo: int, hi: int):
+    """K2c -> int64[hi-lo][size] CUDA tensor."""
+    torch = require_cuda()
+    out = torch.empty((hi - lo, size), dtype=torch.int64, device="cuda")
+    n_pad = 1
+    while n_pad < n_rows:
+        n_pad <<= 1
+    ws, wsz = _ws.get(n_pad * (hi - lo) * 12 + 4096)
+    _abi.check(_abi.lib().b200boot_fill_subsample(seed, n_rows, size, lo, hi, out.data_ptr(), ws, wsz,
+                                                  stream_ptr()))
+    return out
+
+
 def tile_counts(seed: int, n_rows: int, n_arrays: int, lo: int, hi: int, with_classes: bool = False):
     """K0 occupancies: int32[n_tiles][hi-lo] (and int32[n_full][hi-lo][16] class counts)."""
     torch = require_cuda()

@@ -552,15 +552,48 @@ def jackknife_indices(data) -> Iterator[np.ndarray]:
 
 
 def subsample_indices(data, n_samples: int = 1000, size: float = 0.5, seed: SeedType = None):
-    """Not part of the resampling hot path (bootstrap.py:717-744): not provided."""
-    raise NotImplementedError(
-        "subsample_indices is outside the device hot path of this package (ci/pval never call "
-        "it); see DESIGN.md, 'out of scope'")
+    """Indices of `n_samples` subsamples without replacement, an int64 array of shape
+    (n_samples, size) (bootstrap.py:717-744).  size >= 1 is an absolute size, 0 < size < 1
+    a fraction of the data, -1 the data size itself (permuted samples).  Each row holds
+    the first `size` entries of a uniform random permutation drawn on the device."""
+    n_rows = len(data)
+    if size == -1:
+        size = n_rows
+    elif 0 < size < 1:
+        size = int(round(size * n_rows))
+    elif size < 1:
+        raise ValueError("size cannot be {0}".format(size))
+    elif size > n_rows:
+        raise ValueError(f"Size {size} is larger than data size {n_rows}.")
+    size = int(size)
+    key = _seed_key(seed)
+    n_samples = int(n_samples)
+    if size < 1 or n_samples < 1:
+        return np.zeros((max(n_samples, 0), max(size, 0)), dtype=np.int64)
+    n_pad = 1
+    while n_pad < n_rows:
+        n_pad <<= 1
+    step = max(1, min(n_samples, 65535, (256 << 20) // (12 * n_pad)))
+    parts = [_device.to_host(_device.fill_subsample(key, n_rows, size, lo, min(n_samples, lo + step)))
+             for lo in range(0, n_samples, step)]
+    return np.concatenate(parts, axis=0)
 
 
 def bootstrap_indices_moving_block(data, n_samples: int = 10000, block_length: int = 3,
-                                   wrap: bool = False, seed: SeedType = None):
-    """Not part of the resampling hot path (bootstrap.py:747-787): not provided."""
-    raise NotImplementedError(
-        "bootstrap_indices_moving_block is outside the device hot path of this package "
-        "(ci/pval never call it); see DESIGN.md, 'out of scope'")
+                                   wrap: bool = False, seed: SeedType = None) -> Iterator[np.ndarray]:
+    """Generator of moving-block bootstrap index sets (bootstrap.py:747-787): blocks of
+    `block_length` consecutive points starting at uniformly drawn positions, concatenated
+    and cut to the data length; with wrap=True blocks may start anywhere and wrap around
+    the end.  Block starts are Philox draws made on the device."""
+    key = _seed_key(seed)
+    n_rows = _n_rows(data)
+    block_length = int(block_length)
+    bound = n_rows if wrap else n_rows - block_length
+    if block_length < 1 or bound < 1:
+        raise ValueError("low >= high")          # numpy's error for an empty start range (:783)
+    n_samples = int(n_samples)
+    step = max(1, min(n_samples, (64 << 20) // (8 * n_rows)))
+    for lo in range(0, n_samples, step):
+        hi = min(n_samples, lo + step)
+        for row in _device.to_host(_device.fill_moving_block(key, n_rows, block_length, wrap, lo, hi)):
+            yield row

@@ -368,6 +368,48 @@ int b200boot_fill_indices(uint64_t seed, int64_t n_rows, int n_arrays, int64_t r
   return 0;
 }
 
+int b200boot_fill_moving_block(uint64_t seed, int64_t n_rows, int64_t block_length, int wrap,
+                               int64_t resample_lo, int64_t resample_hi, int64_t* out, void* stream) {
+  const int64_t n_local = resample_hi - resample_lo;
+  if (n_rows < 1 || n_rows >= ((int64_t)1 << 31) || block_length < 1 || n_local < 0 || !out)
+    return fail(B200BOOT_EINVAL, "bad arguments");
+  // numpy draws starts from [0, N) when wrapping, else from [0, N - L)  (bootstrap.py:777-783)
+  const int64_t start_bound = wrap ? n_rows : n_rows - block_length;
+  if (start_bound < 1) return fail(B200BOOT_EINVAL, "low >= high: no admissible block start");
+  if (n_local == 0) return 0;
+  k2_moving_block_kernel<<<blocks_for(n_local * 32, 256, 148 * 8), 256, 0, as_stream(stream)>>>(
+      seed, n_rows, block_length, start_bound, wrap ? 1 : 0, resample_lo, n_local, out);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200boot_fill_subsample(uint64_t seed, int64_t n_rows, int64_t size, int64_t sample_lo,
+                            int64_t sample_hi, int64_t* out, void* ws, size_t ws_bytes, void* stream) {
+  const int64_t n_local = sample_hi - sample_lo;
+  if (n_rows < 1 || n_rows >= ((int64_t)1 << 31) || size < 1 || size > n_rows || n_local < 0 || !out)
+    return fail(B200BOOT_EINVAL, "bad arguments");
+  if (n_local == 0) return 0;
+  if (n_local > 65535) return fail(B200BOOT_EINVAL, "at most 65535 samples per call");
+  cudaStream_t s = as_stream(stream);
+  int64_t n_pad = 1;
+  while (n_pad < n_rows) n_pad <<= 1;
+  if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
+    return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
+  Carver cv(ws, ws_bytes);
+  uint64_t* keys = cv.take<uint64_t>((size_t)n_pad * n_local);
+  uint32_t* idx = cv.take<uint32_t>((size_t)n_pad * n_local);
+  if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+  k2_shuffle_keys_kernel<<<blocks_for(((n_pad + 1) / 2) * n_local, 256, 148 * 16), 256, 0, s>>>(
+      seed, n_rows, n_pad, sample_lo, n_local, keys, idx);
+  B2_LAUNCH_CHECK();
+  int rc = psort_pairs(keys, idx, n_pad, (unsigned)n_local, s);
+  if (rc) return rc;
+  k2_subsample_store_kernel<<<blocks_for(size * n_local, 256, 148 * 16), 256, 0, s>>>(idx, n_pad, size,
+                                                                                      n_local, out);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
 int b200boot_gather(const double* data, int64_t n_rows, const int64_t* idx, int64_t n_idx,
                     double* out, void* stream) {
   if (!data || !idx || !out || n_rows < 1 || n_idx < 0) return fail(B200BOOT_EINVAL, "bad arguments");

@@ -360,6 +360,76 @@ __global__ void __launch_bounds__(256) k2_fill_indices_kernel(Plan plan, uint64_
   }
 }
 
+// ------------------------------------------------------------------ K2b -------
+// Moving-block bootstrap indices (bootstrap.py:747-787): per resample ceil(N/L)
+// block starts uniform on [0, start_bound) — Lemire draws from the kPurposeBlock
+// stream — expanded to start+0..L-1, truncated to N, taken mod N when wrapping.
+__global__ void __launch_bounds__(256) k2_moving_block_kernel(uint64_t seed, int64_t n_rows,
+                                                              int64_t block_length, int64_t start_bound,
+                                                              int wrap, int64_t resample_lo,
+                                                              int64_t n_local, int64_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_blocks = (n_rows + block_length - 1) / block_length;
+  const uint32_t thresh = lemire_threshold((uint32_t)start_bound);
+  for (int64_t rl = warp_global; rl < n_local; rl += n_warps) {
+    int64_t* row = out + rl * n_rows;
+    const Stream st = make_stream(seed, resample_lo + rl, 0u, kPurposeBlock);
+    const uint32_t n_q = (uint32_t)((n_blocks + 3) / 4);
+    for (uint32_t q = lane; q < n_q; q += 32) {
+      lemire_block<true>(st, q, (uint32_t)start_bound, thresh, n_blocks,
+                         [&](int, int64_t b, uint32_t start) {
+                           for (int64_t k = 0; k < block_length; ++k) {
+                             const int64_t pos = b * block_length + k;
+                             if (pos >= n_rows) break;
+                             const int64_t v = (int64_t)start + k;
+                             row[pos] = wrap ? v % n_rows : v;
+                           }
+                         });
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K2c -------
+// Sort keys of a random permutation: keys[d][i] = 64 random bits of (seed, sample d,
+// position i); padding sorts last.  Sorting (key, i) pairs per sample (psort kernels)
+// and keeping the first `size` row numbers gives a uniform subsample without
+// replacement (bootstrap.py:717-744).
+__global__ void __launch_bounds__(256) k2_shuffle_keys_kernel(uint64_t seed, int64_t n_rows,
+                                                              int64_t n_pad, int64_t sample_lo,
+                                                              int64_t n_local, uint64_t* __restrict__ keys,
+                                                              uint32_t* __restrict__ idx) {
+  const int64_t per = (n_pad + 1) / 2;                      // Philox blocks per sample (2 keys each)
+  const int64_t total = per * n_local;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t d = e / per, q = e - d * per;
+    const Stream st = make_stream(seed, sample_lo + d, 0u, kPurposeShuffle);
+    const Words4 w = stream_block(st, (uint32_t)q);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t i = 2 * q + h;
+      if (i < n_pad) {
+        const uint64_t key = ((uint64_t)w.w[2 * h] << 32) | w.w[2 * h + 1];
+        keys[d * n_pad + i] = i < n_rows ? (key >> 1) : ~0ull;      // top bit clear: below the padding
+        idx[d * n_pad + i] = i < n_rows ? (uint32_t)i : 0xFFFFFFFFu;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k2_subsample_store_kernel(const uint32_t* __restrict__ idx,
+                                                                 int64_t n_pad, int64_t size,
+                                                                 int64_t n_local, int64_t* __restrict__ out) {
+  const int64_t total = size * n_local;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t d = e / size, i = e - d * size;
+    out[e] = (int64_t)idx[d * n_pad + i];
+  }
+}
+
 __global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ data,
                                                      const int64_t* __restrict__ idx, int64_t n_idx,
                                                      double* __restrict__ out) {

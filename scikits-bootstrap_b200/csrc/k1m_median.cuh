@@ -487,6 +487,27 @@ inline int median_check(const double* data, int64_t n_rows, int64_t n_cols, int6
   return 0;
 }
 
+// bitonic sort of (key, idx) pairs: n_seq sequences of n_pad (power of two) pairs each
+inline int psort_pairs(uint64_t* keys, uint32_t* idx, int64_t n_pad, unsigned n_seq, cudaStream_t s) {
+  if (n_pad <= 1) return 0;
+  const int64_t seg = n_pad < 2048 ? n_pad : 2048;
+  const dim3 glocal((unsigned)(n_pad / seg), n_seq);
+  int64_t fb = (n_pad + 1023) / 1024;
+  if (fb > 1024) fb = 1024;
+  const dim3 gflat((unsigned)fb, n_seq);
+  psort_local_kernel<<<glocal, 1024, 0, s>>>(keys, idx, n_pad, 2, seg, 1);
+  B2_LAUNCH_CHECK();
+  for (int64_t k = seg * 2; k <= n_pad; k <<= 1) {
+    for (int64_t j = k >> 1; j >= 2048; j >>= 1) {
+      psort_step_kernel<<<gflat, 256, 0, s>>>(keys, idx, n_pad, j, k);
+      B2_LAUNCH_CHECK();
+    }
+    psort_local_kernel<<<glocal, 1024, 0, s>>>(keys, idx, n_pad, k, k, 1024);
+    B2_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
 // sorts every column and packs sorted values + permutation into the workspace
 inline int median_prepare(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, MedianWs& w,
                           cudaStream_t s) {
@@ -496,27 +517,12 @@ inline int median_prepare(const double* data, int64_t n_rows, int64_t n_cols, in
   if (lb > 148 * 32) lb = 148 * 32;
   psort_load_kernel<<<(int)lb, 256, 0, s>>>(data, n_rows, n_cols, ld, n_pad, w.keys, w.idx);
   B2_LAUNCH_CHECK();
-  const int64_t seg = n_pad < 2048 ? n_pad : 2048;
   for (int64_t d0 = 0; d0 < n_cols; d0 += 65535) {
     const unsigned nd = (unsigned)(n_cols - d0 < 65535 ? n_cols - d0 : 65535);
     uint64_t* kc = w.keys + d0 * n_pad;
     uint32_t* ic = w.idx + d0 * n_pad;
-    const dim3 glocal((unsigned)(n_pad / seg), nd);
-    int64_t fb = (n_pad + 1023) / 1024;
-    if (fb > 1024) fb = 1024;
-    const dim3 gflat((unsigned)fb, nd);
-    if (n_pad > 1) {
-      psort_local_kernel<<<glocal, 1024, 0, s>>>(kc, ic, n_pad, 2, seg, 1);
-      B2_LAUNCH_CHECK();
-    }
-    for (int64_t k = seg * 2; k <= n_pad; k <<= 1) {
-      for (int64_t j = k >> 1; j >= 2048; j >>= 1) {
-        psort_step_kernel<<<gflat, 256, 0, s>>>(kc, ic, n_pad, j, k);
-        B2_LAUNCH_CHECK();
-      }
-      psort_local_kernel<<<glocal, 1024, 0, s>>>(kc, ic, n_pad, k, k, 1024);
-      B2_LAUNCH_CHECK();
-    }
+    int rc = psort_pairs(kc, ic, n_pad, nd, s);
+    if (rc) return rc;
     const dim3 gpack((unsigned)((w.seg_len * 32 + 255) / 256), nd);
     median_pack_kernel<<<gpack, 256, 0, s>>>(kc, ic, n_rows, n_pad, w.seg_len, w.sorted_vals + d0 * n_rows,
                                              w.perm_t + d0 * w.seg_len * 32);

@@ -26,6 +26,8 @@ constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
 constexpr uint32_t kPurposeIndex = 0u;     // index words
 constexpr uint32_t kPurposeRedraw = 1u;    // Lemire rejection redraws
 constexpr uint32_t kPurposeBinomial = 2u;  // tile-occupancy uniforms
+constexpr uint32_t kPurposeBlock = 3u;     // moving-block start draws
+constexpr uint32_t kPurposeShuffle = 4u;   // subsample sort keys
 
 struct Words4 {
   uint32_t w[4];

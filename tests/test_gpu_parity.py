@@ -490,6 +490,61 @@ def test_independent_mode():
     assert_allclose(got, [2.547619, 7.97619], atol=0.25)
 
 
+# ------------------------------------------------------------------ other plans --
+
+@pytest.mark.parametrize("n,L,wrap", [(5, 3, False), (4, 3, True), (1000, 7, False), (1000, 7, True), (40001, 50, True)])
+def test_moving_block_indices(n, L, wrap):
+    """bootstrap.py:747-787 on the device stream: bit-equal to the oracle's restatement
+    of that stream, same block structure as the reference's generator."""
+    got = np.array(list(boot.bootstrap_indices_moving_block(np.zeros(n), 9, block_length=L, wrap=wrap, seed=77)))
+    assert got.shape == (9, n) and got.dtype == np.int64
+    for r in (0, 4, 8):
+        assert_array_equal(got[r], orc.device_moving_block(77, r, n, L, wrap))
+    assert got.min() >= 0 and got.max() < n
+    body = got[:, : (n // L) * L].reshape(9, -1, L)
+    step = np.diff(body, axis=2)
+    assert np.all((step == 1) | (step == 1 - n))         # consecutive inside a block (mod N)
+    if not wrap:
+        assert body[:, :, 0].max() < n - L                # numpy's half-open start range
+    with pytest.raises(ValueError):
+        list(boot.bootstrap_indices_moving_block(np.zeros(3), 2, block_length=3))
+
+
+def test_moving_block_starts_are_uniform():
+    n, L = 64, 4
+    got = np.array(list(boot.bootstrap_indices_moving_block(np.zeros(n), 4000, block_length=L, wrap=True, seed=3)))
+    starts = got[:, ::L].ravel()
+    cnt = np.bincount(starts, minlength=n)
+    chi2 = ((cnt - cnt.mean()) ** 2 / cnt.mean()).sum()
+    assert chi2 < 130                                      # dof 63
+
+
+def test_subsample_indices():
+    """bootstrap.py:717-744 / bootstrap_test.py:114-138."""
+    idx = boot.subsample_indices(DATA20, 1000, 0.5, seed=5)
+    assert idx.shape == (1000, 10) and idx.dtype == np.int64
+    assert all(len(np.unique(r)) == 10 for r in idx)
+    for r in (0, 500, 999):
+        assert_array_equal(idx[r], orc.device_subsample(5, r, 20, 10))
+    assert all(len(np.unique(r)) == 10 for r in boot.subsample_indices(DATA20, 50, 10))
+    perm = boot.subsample_indices(np.arange(0, 50), 300, -1, seed=1)
+    assert perm.shape == (300, 50) and np.all(np.sort(perm, axis=1) == np.arange(50))
+    assert not np.all(perm[0] == perm[1:])
+    # every position equally likely to hold every row
+    first = np.bincount(perm[:, 0], minlength=50)
+    big = boot.subsample_indices(np.arange(0, 50), 20000, 1, seed=2)[:, 0]
+    cnt = np.bincount(big, minlength=50)
+    assert ((cnt - 400.0) ** 2 / 400.0).sum() < 110        # dof 49
+    assert first.sum() == 300
+    with pytest.raises(ValueError):
+        boot.subsample_indices(DATA20, 1000, 30)
+    with pytest.raises(ValueError, match="size cannot be -5"):
+        boot.subsample_indices(DATA20, size=-5)
+    big = boot.subsample_indices(np.zeros(5000), 3, 0.5, seed=9)      # beyond one shared-memory segment
+    assert big.shape == (3, 2500) and all(len(np.unique(r)) == 2500 for r in big)
+    assert_array_equal(big[2], orc.device_subsample(9, 2, 5000, 2500))
+
+
 # ------------------------------------------------------------------ sharding -----
 
 def test_shards_reproduce_the_single_gpu_statistics():
