@@ -28,6 +28,10 @@ constexpr int kSmemHeader = 128;  // mbarrier + work-item slot
 // FAST kernel variant bakes cell address = 0x400 + header into LDS immediates (the
 // host selects it only when cudaDevAttrReservedSharedMemoryPerBlock == 1024 and the
 // kernel traps if the assumption does not hold).
+#ifndef B2_CLASS_UNROLL
+#define B2_CLASS_UNROLL 1   // measured on B200: 1 -> 82.7 ms, 2 -> 85.3, 3 -> 87.9, 4 -> 87.1 (cfg5 / 5)
+#endif
+constexpr int kClassUnroll = B2_CLASS_UNROLL;   // Philox blocks in flight per lane in the class loop
 constexpr int kFastSmemBase = 1024 + kSmemHeader;
 constexpr int kFastStride2 = 8 << 13;   // bytes between the two arrays of a 2-array full tile
 
@@ -136,7 +140,7 @@ __device__ __forceinline__ void class_accumulate(const unsigned char* __restrict
   LaneAcc<MS> A;
   A.clear();
   const uint32_t n_full = (uint32_t)(n_c / kClassDrawsPerBlock);
-#pragma unroll 2
+#pragma unroll(kClassUnroll)
   for (uint32_t q = h; q < n_full; q += 2) {
     const Words4 w = stream_block(st, q, rk);
 #pragma unroll

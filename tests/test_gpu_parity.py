@@ -429,6 +429,37 @@ def test_warnings_match_reference():
         boot.ci_indexed(np.arange(1, 20), None, pcg_indices(19, 50))
 
 
+def test_edge_shapes():
+    """Smallest inputs, single resample, odd alpha shapes, non-finite data."""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = boot.ci([3.5], np.mean, n_samples=5, seed=1, method="pi")
+        assert_array_equal(out, [3.5, 3.5])
+        out, dist = boot.ci([1.0, 2.0, 4.0], np.mean, n_samples=1, seed=1, method="pi", return_dist=True)
+        assert dist.shape == (1,) and out[0] == out[1] == dist[0]
+        out = boot.ci(DATA20, np.mean, alpha=[0.5], n_samples=101, seed=2, method="pi")
+        assert out.shape == (1,)
+        a2 = np.array([[0.1, 0.9], [0.2, 0.8]])
+        out = boot.ci(DATA20, np.mean, alpha=a2, n_samples=200, seed=2, method="pi")
+        flat = boot.ci(DATA20, np.mean, alpha=a2.ravel(), n_samples=200, seed=2, method="pi")
+        assert out.shape == (2, 2) and np.array_equal(out.ravel(), flat)
+        x = DATA20.copy()
+        x[3] = np.nan
+        out, dist = boot.ci(x, np.mean, n_samples=300, seed=3, method="pi", return_dist=True)
+        k = int(np.isnan(dist).sum())
+        assert 0 < k < 300 and np.all(np.isnan(dist[-k:])) and not np.isnan(dist[:-k]).any()   # NaNs sort last
+        idx = np.array(list(boot.bootstrap_indices(x, 300, seed=3)))
+        assert k == int(np.isnan(x[idx].mean(axis=1)).sum())
+        x[3] = np.inf
+        _, dist = boot.ci(x, np.mean, n_samples=300, seed=3, method="pi", return_dist=True)
+        assert np.isinf(dist[-1]) and np.isfinite(dist[0])
+    with pytest.raises(ValueError):
+        boot.ci(DATA20, np.mean, n_samples=0)
+    with pytest.raises(ValueError):
+        boot.ci(np.zeros(0), np.mean)
+
+
 def test_input_forms_agree():
     import pandas as pd
     x = DATA20
