@@ -37,6 +37,9 @@ inline int blocks_for(int64_t n, int threads, int64_t cap) {
 struct ResampleWs {
   int32_t* counts;
   int32_t* cls;         // [n_full][n_local][16]
+  int32_t* left;        // class-chain scratch: remainders, deferred list, per-step counters
+  int32_t* pending;
+  int32_t* n_pending;
   double* partial;
   int32_t* work_counter;
   JackState* jack;
@@ -53,6 +56,11 @@ ResampleWs carve_resample(Carver& cv, const Plan& plan, int stat, int64_t n_loca
   w.red = cv.take<double>((size_t)kRedBlocks * kMaxMoments);
   w.counts = plan.n_tiles > 1 ? cv.take<int32_t>((size_t)plan.n_tiles * n_local) : nullptr;
   w.cls = plan.n_full > 0 ? cv.take<int32_t>((size_t)plan.n_full * n_local * kClasses) : nullptr;
+  if (plan.n_full > 0) {
+    w.left = cv.take<int32_t>((size_t)plan.n_full * std::max<int64_t>(n_local, 1));
+    w.pending = cv.take<int32_t>((size_t)plan.n_full * std::max<int64_t>(n_local, 1));
+    w.n_pending = cv.take<int32_t>(64);
+  }
   w.partial = cv.take<double>((size_t)plan.n_tiles * nm * std::max<int64_t>(n_local, 1));
   if (stat_needs_centering(stat))
     for (int a = 0; a < plan.n_arrays; ++a) w.centered[a] = cv.take<double>((size_t)plan.n_rows);
@@ -88,20 +96,37 @@ int prepare_rows(const double* const* data, int n_arrays, int64_t n_rows, int st
   return 0;
 }
 
-// K0: tile occupancies, then the 16-way class split of every full tile
+// K0: tile occupancies, then the 16-way class split of every full tile.  With chain
+// scratch (left / pending / n_pending) the split runs as 15 propose + resolve steps,
+// otherwise as one thread-per-pair chain kernel; both give the same values.
 int launch_occupancies(uint64_t seed, int64_t resample_lo, int64_t n_local, const Plan& plan,
-                       int32_t* counts, int32_t* cls, cudaStream_t s) {
+                       int32_t* counts, int32_t* cls, cudaStream_t s, int32_t* left = nullptr,
+                       int32_t* pending = nullptr, int32_t* n_pending = nullptr) {
   if (plan.n_tiles <= 1) return 0;
   k0_tile_counts_kernel<<<blocks_for(n_local, 128, 1 << 30), 128, 0, s>>>(seed, resample_lo, n_local, plan,
                                                                         counts);
   B2_LAUNCH_CHECK();
   if (plan.n_full > 0 && cls) {
     const int64_t total = plan.n_full * n_local;
-    if (total >= ((int64_t)1 << 37)) return fail(B200BOOT_EINVAL, "too many (tile, resample) pairs");
-    const int64_t blocks = std::min<int64_t>((total + 127) / 128, (int64_t)sm_count() * 64);
-    k0_class_counts_kernel<<<(unsigned)blocks, 128, 0, s>>>(seed, resample_lo, n_local, plan.n_full, counts,
-                                                            cls);
-    B2_LAUNCH_CHECK();
+    if (total >= ((int64_t)1 << 31)) return fail(B200BOOT_EINVAL, "too many (tile, resample) pairs");
+    if (left && pending && n_pending) {
+      B2_CUDA(cudaMemsetAsync(n_pending, 0, 64 * sizeof(int32_t), s));
+      const unsigned pb = (unsigned)((total + 255) / 256);
+      const unsigned rb = (unsigned)std::min<int64_t>((total / 8 + 127) / 128 + 1, (int64_t)sm_count() * 32);
+      for (int c = 0; c + 1 < kClasses; ++c) {
+        k0_class_step_propose_kernel<<<pb, 256, 0, s>>>(seed, resample_lo, n_local, plan.n_full, c, counts,
+                                                        left, cls, pending, n_pending + c);
+        B2_LAUNCH_CHECK();
+        k0_class_step_resolve_kernel<<<rb, 128, 0, s>>>(seed, resample_lo, n_local, c, left, cls, pending,
+                                                        n_pending + c);
+        B2_LAUNCH_CHECK();
+      }
+    } else {
+      const int64_t blocks = std::min<int64_t>((total + 127) / 128, (int64_t)sm_count() * 64);
+      k0_class_counts_kernel<<<(unsigned)blocks, 128, 0, s>>>(seed, resample_lo, n_local, plan.n_full, counts,
+                                                              cls);
+      B2_LAUNCH_CHECK();
+    }
   }
   return 0;
 }
@@ -249,7 +274,7 @@ int b200boot_resample_stat(const double* const* data, int n_arrays, int64_t n_ro
   rc = prepare_rows(data, n_arrays, n_rows, stat_id, w, rows, s);
   if (rc) return rc;
 
-  rc = launch_occupancies(seed, resample_lo, n_local, plan, w.counts, w.cls, s);
+  rc = launch_occupancies(seed, resample_lo, n_local, plan, w.counts, w.cls, s, w.left, w.pending, w.n_pending);
   if (rc) return rc;
   B2_CUDA(cudaMemsetAsync(w.work_counter, 0, 256, s));
 

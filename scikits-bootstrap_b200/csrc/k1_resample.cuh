@@ -63,6 +63,77 @@ __global__ void __launch_bounds__(128) k0_class_counts_kernel(uint64_t seed, int
   }
 }
 
+// Two-kernel form of the class chains used by the resample path: at chain step c every
+// (tile, resample) pair makes its FIRST proposal (setup + one BTRS proposal + squeeze,
+// no divergence); the ~14 % of pairs whose proposal needs the full acceptance test (or
+// whose occupancy is tiny) are appended to a compact list and resolved by a second
+// kernel in which every lane is on the expensive path.  Step c+1 then starts from the
+// updated remainders.  Values are identical to class_count_chain: the resolver simply
+// replays binomial_ratio from attempt 0.
+__global__ void __launch_bounds__(256) k0_class_step_propose_kernel(
+    uint64_t seed, int64_t resample_lo, int64_t n_local, int64_t n_full, int c,
+    const int32_t* __restrict__ counts, int32_t* __restrict__ left, int32_t* __restrict__ cls,
+    int32_t* __restrict__ pending, int32_t* __restrict__ n_pending) {
+  const int64_t total = n_full * n_local;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int den = kClasses - c;
+  const double p = 1.0 / (double)den;
+  bool defer = false;
+  if (e < total) {
+    const int64_t n_left = c == 0 ? (int64_t)__ldg(counts + e) : (int64_t)left[e];
+    int64_t k = -1;
+    if (n_left <= 0) {
+      k = 0;
+    } else if ((double)n_left * p < 10.0) {
+      defer = true;
+    } else {
+      const int64_t t = e / n_local, rl = e - t * n_local;
+      const Stream st = make_stream(seed, resample_lo + rl, class_cell_id(t, c), kPurposeBinomial);
+      const BtrsConsts q = btrs_setup(n_left, p, p / (1.0 - p));
+      double kd, inv_us, v;
+      if (btrs_propose(q, stream_block(st, 0u), &kd, &inv_us, &v) > 0)
+        k = (int64_t)kd;
+      else
+        defer = true;
+    }
+    if (!defer) {
+      cls[e * kClasses + c] = (int32_t)k;
+      left[e] = (int32_t)(n_left - k);
+      if (c == kClasses - 2) cls[e * kClasses + c + 1] = (int32_t)(n_left - k);
+    } else if (c == 0) {
+      left[e] = (int32_t)n_left;         // the resolver reads the remainder from `left`
+    }
+  }
+  // block-aggregated append of the deferred pairs
+  __shared__ int s_base, s_count;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  int slot = 0;
+  if (defer) slot = atomicAdd(&s_count, 1);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_count > 0) s_base = atomicAdd(n_pending, s_count);
+  __syncthreads();
+  if (defer) pending[s_base + slot] = (int32_t)e;      // e < 2^31 (checked by the host)
+}
+
+__global__ void __launch_bounds__(128) k0_class_step_resolve_kernel(
+    uint64_t seed, int64_t resample_lo, int64_t n_local, int c, int32_t* __restrict__ left,
+    int32_t* __restrict__ cls, const int32_t* __restrict__ pending, const int32_t* __restrict__ n_pending) {
+  const int n = *n_pending;
+  const int den = kClasses - c;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t e = pending[i];
+    const int64_t t = e / n_local, rl = e - t * n_local;
+    const int64_t n_left = left[e];
+    const Stream st = make_stream(seed, resample_lo + rl, class_cell_id(t, c), kPurposeBinomial);
+    const int64_t k = binomial_ratio(n_left, 1, den, st);
+    cls[e * kClasses + c] = (int32_t)k;
+    left[e] = (int32_t)(n_left - k);
+    if (c == kClasses - 2) cls[e * kClasses + c + 1] = (int32_t)(n_left - k);
+  }
+}
+
 // ------------------------------------------------------------------ K1 --------
 struct K1Params {
   const double* data[2];
