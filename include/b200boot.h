@@ -100,6 +100,21 @@ int b200boot_resample_stat_indexed(const double* const* data, int n_arrays, int6
                                    int stat_id, const int64_t* indices, int64_t n_sets,
                                    double* stat_out, void* ws, size_t ws_bytes, void* stream);
 
+/* K1c — column-batched moment statistics (mean / sum / var / std) over data
+ * float64[N][n_cols] row-major (ld = row stride): all columns share one index set per
+ * resample (bootstrap.py:431 on 2-D data).  Available when a row-major block of W >= 4
+ * columns fits in shared memory (b200boot_columns_block_width > 0, i.e. N <= 7168);
+ * column d of the result equals the 1-D run on column d.
+ * stat_out: float64[n_cols][n_local]; ws: b200boot_workspace_bytes(stat, N, 1, n_cols, ...). */
+int b200boot_columns_block_width(int stat_id, int64_t n_rows);
+int b200boot_resample_stat_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld,
+                                   int stat_id, uint64_t seed, int64_t resample_lo, int64_t resample_hi,
+                                   double* stat_out, void* ws, size_t ws_bytes, void* stream);
+/* K3c — closed-form jackknife of those statistics for every column (any N):
+ * out float64[n_cols][8] as b200boot_jackknife. */
+int b200boot_jackknife_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, int stat_id,
+                               double* out, void* stream);
+
 /* K1m — column-batched order statistic: data float64[N][n_cols] row-major
  * (ld = row stride in elements); every column shares one index set per
  * resample, as x[indices] does for 2-D data at bootstrap.py:431.

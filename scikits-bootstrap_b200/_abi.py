@@ -37,6 +37,9 @@ SIGNATURES = {
     "b200boot_workspace_bytes": (_sz, [_int, _i64, _int, _i64, _i64, _int]),
     "b200boot_resample_stat": (_int, [_vp, _int, _i64, _int, _u64, _i64, _i64, _vp, _vp, _sz, _vp]),
     "b200boot_resample_stat_indexed": (_int, [_vp, _int, _i64, _int, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "b200boot_columns_block_width": (_int, [_int, _i64]),
+    "b200boot_resample_stat_columns": (_int, [_vp, _i64, _i64, _i64, _int, _u64, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "b200boot_jackknife_columns": (_int, [_vp, _i64, _i64, _i64, _int, _vp, _vp]),
     "b200boot_resample_median_columns": (_int, [_vp, _i64, _i64, _i64, _u64, _i64, _i64, _vp, _vp, _sz, _vp]),
     "b200boot_resample_median_columns_indexed": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
     "b200boot_resample_median_sorted": (_int, [_vp, _i64, _u64, _i64, _i64, _vp, _vp, _sz, _vp]),

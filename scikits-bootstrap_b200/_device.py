@@ -144,6 +144,32 @@ def resample_stat_indexed(arrays: Sequence, stat_id: int, indices):
     return out
 
 
+def columns_block_width(stat_id: int, n_rows: int) -> int:
+    return _abi.lib().b200boot_columns_block_width(stat_id, n_rows)
+
+
+def resample_stat_columns(data2d, stat_id: int, seed: int, lo: int, hi: int):
+    """K1c: data float64[N][D] -> float64[D][hi-lo] (all columns share the index set)."""
+    torch = _torch()
+    n_rows, n_cols = data2d.shape
+    out = torch.empty((n_cols, hi - lo), dtype=torch.float64, device=data2d.device)
+    ws, wsz = workspace_for(stat_id, n_rows, 1, max(n_cols, 2), hi - lo, 1)
+    _abi.check(_abi.lib().b200boot_resample_stat_columns(data2d.data_ptr(), n_rows, n_cols, data2d.stride(0),
+                                                         stat_id, seed, lo, hi, out.data_ptr(), ws, wsz,
+                                                         stream_ptr()))
+    return out
+
+
+def jackknife_columns(data2d, stat_id: int):
+    """K3c: float64[D][8] (ostat, jmean, d2, d3, accel, centre, ...) per column."""
+    torch = _torch()
+    n_rows, n_cols = data2d.shape
+    out = torch.empty((n_cols, 8), dtype=torch.float64, device=data2d.device)
+    _abi.check(_abi.lib().b200boot_jackknife_columns(data2d.data_ptr(), n_rows, n_cols, data2d.stride(0),
+                                                     stat_id, out.data_ptr(), stream_ptr()))
+    return out
+
+
 def resample_median_columns(data2d, seed: int, lo: int, hi: int):
     """K1m: data float64[N][D] -> float64[D][hi-lo]."""
     torch = _torch()

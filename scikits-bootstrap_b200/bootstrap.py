@@ -185,6 +185,8 @@ class _Run:
             means = [_device.resample_stat([a], _abi.STAT_MEAN, (self.key + k * _ARRAY_KEY_STRIDE) & _MASK64, lo, hi)
                      for k, a in enumerate(self.dev)]
             return (means[0] - means[1]).reshape(1, -1)
+        if self.vector and _device.columns_block_width(spec.stat_id, self.dev[0].shape[0]) > 0:
+            return _device.resample_stat_columns(self.dev[0], spec.stat_id, self.key, lo, hi)   # K1c
         if self.vector:
             out = torch.empty((self.n_cols, hi - lo), dtype=torch.float64, device=self.dev[0].device)
             cols = self.columns()
@@ -234,8 +236,7 @@ class _Run:
         elif spec.independent:
             j = self._jackknife_independent()
         elif self.vector:
-            cols = self.columns()
-            j = torch.stack([_device.jackknife([cols[d]], spec.stat_id) for d in range(self.n_cols)])
+            j = _device.jackknife_columns(self.dev[0], spec.stat_id)                               # K3c
         else:
             j = _device.jackknife([a.reshape(-1) for a in self.dev], spec.stat_id).reshape(1, 8)
         self._jack = _device.to_host(j)

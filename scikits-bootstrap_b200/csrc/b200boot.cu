@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "draw.cuh"
 #include "k1_resample.cuh"
+#include "k1c_columns.cuh"
 #include "k1m_median.cuh"
 #include "k3_jackknife.cuh"
 #include "k45_interval.cuh"
@@ -238,6 +239,8 @@ size_t b200boot_workspace_bytes(int stat_id, int64_t n_rows, int n_arrays, int64
   size_t total = 4096;
   if (stat_id == kStatMedian) {
     total += median_ws_bytes(n_rows, n_cols, n_local);
+  } else if (n_cols > 1) {
+    total += columns_ws_bytes(n_cols);
   } else {
     const Plan plan = make_plan(n_rows, n_arrays);
     Carver cv(reinterpret_cast<void*>(256), ~(size_t)0 >> 1);
@@ -632,6 +635,26 @@ int b200boot_resample_median_columns_indexed(const double* data, int64_t n_rows,
 int b200boot_jackknife_median_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld,
                                       double* out, void* ws, size_t ws_bytes, void* stream) {
   return median_jackknife(data, n_rows, n_cols, ld, out, ws, ws_bytes, as_stream(stream));
+}
+
+int b200boot_columns_block_width(int stat_id, int64_t n_rows) {
+  return columns_supported(stat_id, n_rows) ? column_block_width(n_rows) : 0;
+}
+
+int b200boot_resample_stat_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld,
+                                   int stat_id, uint64_t seed, int64_t resample_lo, int64_t resample_hi,
+                                   double* stat_out, void* ws, size_t ws_bytes, void* stream) {
+  return columns_resample(data, n_rows, n_cols, ld, stat_id, seed, resample_lo, resample_hi, stat_out, ws,
+                          ws_bytes, as_stream(stream));
+}
+
+int b200boot_jackknife_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, int stat_id,
+                               double* out, void* stream) {
+  if (!data || !out || n_rows < 1 || n_cols < 1 || ld < n_cols) return fail(B200BOOT_EINVAL, "bad arguments");
+  const int ms = moment_set_of(stat_id);
+  if (ms != kMomSum && ms != kMomSum2)
+    return fail(B200BOOT_EUNSUPPORTED, "statistic %d is not a single-array moment statistic", stat_id);
+  return columns_jackknife(data, n_rows, n_cols, ld, stat_id, nullptr, out, as_stream(stream));
 }
 
 int b200boot_resample_median_sorted(const double* sorted_vals, int64_t n_rows, uint64_t seed,

@@ -487,10 +487,39 @@ def test_paired_tuple_equals_axis0_columns():
         assert out.shape == (2, 5) and dist.shape == (1500, 5)
         eb = boot.ci(m, f, alpha=(0.1, 0.9), n_samples=1500, seed=3, output="errorbar")
         assert eb.shape == (5, 2)
-        for d in range(5):
+        for d in range(5):       # same draws; the two kernels sum in different orders
             o1, d1 = boot.ci(m[:, d], g, alpha=(0.1, 0.9), n_samples=1500, seed=3, return_dist=True)
-            assert_array_equal(out[:, d], o1)
-            assert_array_equal(dist[:, d], d1)
+            assert_allclose(out[:, d], o1, rtol=RTOL, atol=1e-15)
+            assert_allclose(dist[:, d], d1, rtol=RTOL, atol=1e-15)
+
+
+@pytest.mark.parametrize("shape", [(20, 3), (896, 33), (1000, 70), (3000, 9), (7168, 5), (7169, 3)])
+@pytest.mark.parametrize("name", ["mean_axis0", "std_axis0"])
+def test_column_batched_moments(shape, name):
+    """(N, D) data, axis-0 moment statistic: K1c / K3c (row-major blocks of W columns in
+    shared memory; beyond 7168 rows a per-column loop) against the oracle on the
+    device's own index sets, BCa endpoints included."""
+    import warnings
+    n, dcols = shape
+    rng = np.random.default_rng(n + dcols)
+    data = rng.standard_normal((n, dcols)) * rng.uniform(0.5, 2.0, dcols) + rng.uniform(-3, 3, dcols)
+    f = {"mean_axis0": boot.mean_axis0, "std_axis0": functools.partial(np.std, axis=0)}[name]
+    g = {"mean_axis0": lambda a: np.mean(a, axis=0), "std_axis0": lambda a: np.std(a, axis=0)}[name]
+    m = 300
+    idx = np.array(list(boot.bootstrap_indices(data, m, seed=11)))
+    want = orc.stat_over_indices((data,), g, idx)
+    want.sort(axis=0)
+    jk = orc.jack_mean if name == "mean_axis0" else (lambda x: orc.jack_var(x, True))
+    jst = np.stack([jk(data[:, d]) for d in range(dcols)], axis=1)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out, dist = boot.ci(data, f, n_samples=m, seed=11, return_dist=True)
+        ref = orc.ci_from_indices((data,), g, idx, (0.025, 0.975), m, "bca", jstat=jst)
+    assert dist.shape == (m, dcols)
+    assert_allclose(dist, want, rtol=RTOL, atol=1e-15)
+    assert_allclose(out, ref, rtol=RTOL, atol=1e-15)
+    p = boot.pval(data, f, boot.greater_than(0.5), n_samples=m, seed=11)
+    assert_array_equal(p, (want > 0.5).mean(axis=0))
 
 
 def test_pval_device_and_host_criteria_agree():

@@ -191,6 +191,33 @@ def test_tiled_draws_are_uniform_over_rows():
         assert abs(share - (hi - lo) / n) < 5 * np.sqrt((hi - lo) / n / (n * m))
 
 
+def test_tiled_draws_have_iid_multiplicities():
+    """Row multiplicities of a resample must look like N iid uniform draws:
+    #rows drawn k times ~ N * Binomial(N, 1/N).pmf(k); in particular a fraction 1 - 1/e of
+    the rows is hit.  Sensitive to any over- or under-dispersion the tile / bank-class
+    multinomial splits could introduce."""
+    n, m = 100000, 40           # 6 full tiles + remainder; 16 classes per full tile
+    mult = np.zeros(8)
+    distinct = []
+    for r in range(m):
+        c = np.bincount(_host_indices(123, n, 1, r), minlength=n)
+        distinct.append((c > 0).mean())
+        mult += np.bincount(np.minimum(c, 7), minlength=8)
+    pmf = sps.binom.pmf(np.arange(7), n, 1.0 / n)
+    exp = np.concatenate((pmf, [1 - pmf.sum()])) * n * m
+    chi2 = ((mult - exp) ** 2 / exp).sum()
+    assert chi2 < sps.chi2.ppf(1 - 1e-5, 7), (chi2, mult, exp)
+    # Var(#distinct)/N = e^-1 (1 - 2 e^-1) ~ 0.0972 for iid draws
+    d = np.array(distinct)
+    assert abs(d.mean() - (1 - np.exp(-1))) < 5 * np.sqrt(0.0972 / n / m)
+    assert 0.4 < d.var() * n / 0.0972 < 2.0
+    # occupancy of an arbitrary row block (crossing a tile and several classes): Binomial(N, B/N)
+    occ = np.array([np.count_nonzero((lambda i: (i >= 16000) & (i < 17000))(_host_indices(5, n, 1, r)))
+                    for r in range(200)])
+    assert abs(occ.mean() - 1000) < 5 * np.sqrt(1000 / 200)
+    assert 0.7 < occ.var() / (1000 * (1 - 0.01)) < 1.4
+
+
 def test_registry_and_errors_without_gpu():
     import functools
     from scikits_bootstrap_b200 import _registry as reg
