@@ -105,20 +105,27 @@ __global__ void __launch_bounds__(1024) psort_local_kernel(uint64_t* __restrict_
   }
 }
 
-// sorted values and the row permutation in "lane-segment" order:
-// position s = lane * L + i is stored at perm_t[d][i * 32 + lane]; slots past N
-// point at the always-zero count slot N.
+// Sorted values and the row permutation of every column in two shared-memory friendly
+// layouts.  Sorted positions are cut into 32 lane segments of `seg` (even) positions:
+// position s = lane * seg + i.
+//   pairs[d][(i/2) * 32 + lane] (u32): rows at positions i (low half) and i+1 (high half)
+//   lin  [d][s]                 (u16): row at position s
+// Slots past N point at the always-zero count slot N.
 __global__ void __launch_bounds__(256) median_pack_kernel(const uint64_t* __restrict__ keys,
                                                           const uint32_t* __restrict__ idx, int64_t n,
-                                                          int64_t n_pad, int seg_len,
+                                                          int64_t n_pad, int seg,
                                                           double* __restrict__ sorted_vals,
-                                                          uint16_t* __restrict__ perm_t) {
+                                                          uint32_t* __restrict__ pairs,
+                                                          uint16_t* __restrict__ lin) {
   const int64_t d = blockIdx.y;
-  const int64_t slots = (int64_t)seg_len * 32;
+  const int64_t slots = (int64_t)seg * 32;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  uint16_t* pr = reinterpret_cast<uint16_t*>(pairs + d * (slots / 2));
   for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += stride) {
-    const int lane = (int)(s / seg_len), i = (int)(s % seg_len);
-    perm_t[d * slots + (int64_t)i * 32 + lane] = s < n ? (uint16_t)idx[d * n_pad + s] : (uint16_t)n;
+    const int lane = (int)(s / seg), i = (int)(s % seg);
+    const uint16_t row = s < n ? (uint16_t)idx[d * n_pad + s] : (uint16_t)n;
+    pr[((int64_t)(i >> 1) * 32 + lane) * 2 + (i & 1)] = row;
+    lin[d * slots + s] = row;
     if (s < n) sorted_vals[d * n + s] = value_of(keys[d * n_pad + s]);
   }
 }
@@ -126,9 +133,10 @@ __global__ void __launch_bounds__(256) median_pack_kernel(const uint64_t* __rest
 // ---- K1m ---------------------------------------------------------------------------
 struct K1mParams {
   const double* sorted_vals;   // [D][N]
-  const uint16_t* perm_t;      // [D][L*32]
+  const uint32_t* pairs;       // [D][seg * 16]
+  const uint16_t* lin;         // [D][seg * 32]
   int64_t n_rows, n_cols;
-  int32_t seg_len;             // L = ceil(N / 32)
+  int32_t seg;                 // positions per lane segment (even)
   int32_t cols_per_item;       // columns whose permutation is resident per item
   int32_t n_colchunks;
   int32_t rchunk, n_rchunks;   // resamples per item
@@ -137,22 +145,23 @@ struct K1mParams {
   int64_t resample_lo, n_local;
   double* out;                 // [D][n_local]
   int32_t* work_counter;
-  int32_t count_words;         // uint32 words per count vector ((N + 2) / 2 rounded up)
-  int32_t batch;               // resamples per count-vector batch (<= kMedBatch)
+  int32_t count_words;         // uint32 words of one count table: ceil((N + 1) * B / 2), padded
   const int64_t* indices;      // parity mode: caller-supplied index sets [n_local][N], else null
 };
 
-// first sorted position whose cumulative draw count exceeds k
+// First sorted position whose cumulative draw count (resample b of the batch) exceeds k.
+// incl / excl: the lane's inclusive / exclusive segment prefix for that resample.
+template <int B>
 __device__ __forceinline__ int median_find(const uint16_t* __restrict__ cnt,
-                                           const uint16_t* __restrict__ pt, int seg_len, int lane,
-                                           uint32_t incl, uint32_t sum, uint32_t k) {
+                                           const uint16_t* __restrict__ lin, int seg_len, int lane,
+                                           int b, uint32_t incl, uint32_t excl, uint32_t k) {
   const uint32_t hit = __ballot_sync(0xffffffffu, incl > k);
-  const int seg = __ffs(hit) - 1;                       // segment (lane) holding the crossing
-  uint32_t running = __shfl_sync(0xffffffffu, incl - sum, seg);
+  const int seg = __ffs(hit) - 1;                       // lane segment holding the crossing
+  uint32_t running = __shfl_sync(0xffffffffu, excl, seg);
+  const uint16_t* ls = lin + seg * seg_len;
   for (int c0 = 0; c0 < seg_len; c0 += 32) {
     const int i = c0 + lane;
-    uint32_t v = i < seg_len ? (uint32_t)cnt[pt[i * 32 + seg]] : 0u;
-    uint32_t inc = v;
+    uint32_t inc = i < seg_len ? (uint32_t)cnt[(int)ls[i] * B + b] : 0u;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
       const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
@@ -166,18 +175,25 @@ __device__ __forceinline__ int median_find(const uint16_t* __restrict__ cnt,
   return seg * seg_len + seg_len - 1;   // unreachable when counts sum to N
 }
 
+// B = resamples whose draw-count tables are interleaved in shared memory
+// (cnt[row * B + b], u16): one wide load per sorted position serves B resamples and the
+// B segment sums are carried packed (two u16 per 32-bit add).
+template <int B>
 __global__ void __launch_bounds__(kMedThreads, 1) k1m_median_kernel(const K1mParams P) {
+  static_assert(B == 4 || B == 1, "batch of 4 (interleaved) or 1");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   volatile int* s_item = reinterpret_cast<volatile int*>(smem_raw);
-  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem_raw + 128);                 // [kMedBatch][count_words]
-  uint16_t* s_perm = reinterpret_cast<uint16_t*>(s_cnt + P.batch * P.count_words);
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem_raw + 128);                 // count table
+  uint32_t* s_pairs = s_cnt + P.count_words;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t slots = (int64_t)P.seg_len * 32;
+  const int seg_len = P.seg;
+  const int pair_words = seg_len * 16;             // per column
   const int n = (int)P.n_rows;
   const uint32_t thresh = lemire_threshold((uint32_t)n);
   const int n_blocks = (n + 3) / 4;
-  const uint32_t k_hi = (uint32_t)(n / 2);                       // upper middle rank (0-based)
+  const uint32_t k_hi = (uint32_t)(n / 2);         // upper middle rank (0-based)
   const bool even = (n & 1) == 0;
+  const uint16_t* cnt16 = reinterpret_cast<const uint16_t*>(s_cnt);
 
   int resident = -1;
   for (;;) {
@@ -190,54 +206,84 @@ __global__ void __launch_bounds__(kMedThreads, 1) k1m_median_kernel(const K1mPar
     const int rc = (int)(item - (int64_t)cc * P.n_rchunks);
     const int64_t d0 = (int64_t)cc * P.cols_per_item;
     const int dc = (int)min((int64_t)P.cols_per_item, P.n_cols - d0);
+    uint16_t* s_lin = reinterpret_cast<uint16_t*>(s_pairs + (size_t)P.cols_per_item * pair_words);
     if (cc != resident) {
-      const uint16_t* src = P.perm_t + d0 * slots;
-      for (int64_t e = tid; e < (int64_t)dc * slots; e += kMedThreads) s_perm[e] = src[e];
+      const uint32_t* src = P.pairs + d0 * pair_words;
+      for (int64_t e = tid; e < (int64_t)dc * pair_words; e += kMedThreads) s_pairs[e] = src[e];
+      const uint32_t* lsrc = reinterpret_cast<const uint32_t*>(P.lin + d0 * (int64_t)seg_len * 32);
+      uint32_t* ldst = reinterpret_cast<uint32_t*>(s_lin);
+      for (int64_t e = tid; e < (int64_t)dc * pair_words; e += kMedThreads) ldst[e] = lsrc[e];
       resident = cc;
       __syncthreads();
     }
     const int64_t r_begin = (int64_t)rc * P.rchunk;
     const int64_t r_end = min(r_begin + (int64_t)P.rchunk, P.n_local);
-    for (int64_t rb = r_begin; rb < r_end; rb += P.batch) {
-      const int nb = (int)min((int64_t)P.batch, r_end - rb);
-      for (int e = tid; e < nb * P.count_words; e += kMedThreads) s_cnt[e] = 0u;
+    for (int64_t rb = r_begin; rb < r_end; rb += B) {
+      const int nb = (int)min((int64_t)B, r_end - rb);
+      for (int e = tid; e < P.count_words; e += kMedThreads) s_cnt[e] = 0u;
       __syncthreads();
+      auto bump = [&](int b, uint32_t row) {
+        const uint32_t slot = row * B + b;
+        atomicAdd(s_cnt + (slot >> 1), 1u << ((slot & 1u) * 16));
+      };
       if (P.indices) {   // parity mode: count the caller's indices
         for (int e = tid; e < nb * n; e += kMedThreads) {
           const int b = e / n, pos = e - b * n;
-          const uint32_t idx = (uint32_t)P.indices[(rb + b) * (int64_t)n + pos];
-          atomicAdd(s_cnt + b * P.count_words + (idx >> 1), 1u << ((idx & 1u) * 16));
+          bump(b, (uint32_t)P.indices[(rb + b) * (int64_t)n + pos]);
         }
-      }
-      // draw-count vectors: the single-cell Lemire stream of K1/K2 (cell 0)
-      for (int e = tid; !P.indices && e < nb * n_blocks; e += kMedThreads) {
-        const int b = e / n_blocks, q = e - b * n_blocks;
-        const Stream st = make_stream(P.seed, P.resample_lo + rb + b, 0u, kPurposeIndex);
-        uint32_t* cb = s_cnt + b * P.count_words;
-        lemire_block<true>(st, (uint32_t)q, (uint32_t)n, thresh, (int64_t)n,
-                           [&](int, int64_t, uint32_t idx) { atomicAdd(cb + (idx >> 1), 1u << ((idx & 1u) * 16)); });
+      } else {           // the single-cell Lemire stream of K1 / K2 (cell 0)
+        for (int e = tid; e < nb * n_blocks; e += kMedThreads) {
+          const int b = e / n_blocks, q = e - b * n_blocks;
+          const Stream st = make_stream(P.seed, P.resample_lo + rb + b, 0u, kPurposeIndex);
+          lemire_block<true>(st, (uint32_t)q, (uint32_t)n, thresh, (int64_t)n,
+                             [&](int, int64_t, uint32_t idx) { bump(b, idx); });
+        }
       }
       __syncthreads();
-      for (int p = warp; p < nb * dc; p += kMedWarps) {
-        const int b = p / dc, j = p - b * dc;
-        const uint16_t* cnt = reinterpret_cast<const uint16_t*>(s_cnt + b * P.count_words);
-        const uint16_t* pt = s_perm + (int64_t)j * slots;
-        uint32_t sum = 0;
-        for (int i = 0; i < P.seg_len; ++i) sum += (uint32_t)cnt[pt[i * 32 + lane]];
-        uint32_t incl = sum;
+      for (int j = warp; j < dc; j += kMedWarps) {
+        const uint32_t* pp = s_pairs + (size_t)j * pair_words;
+        const uint16_t* lin = s_lin + (size_t)j * seg_len * 32;
+        // packed segment sums: resamples (0,1) in acc0, (2,3) in acc1
+        uint32_t acc0 = 0u, acc1 = 0u;
+        for (int i2 = 0; i2 < seg_len / 2; ++i2) {
+          const uint32_t two = pp[i2 * 32 + lane];
+          const uint32_t r0 = two & 0xFFFFu, r1 = two >> 16;
+          if (B == 4) {
+            const uint2 a = *reinterpret_cast<const uint2*>(cnt16 + r0 * 4);
+            const uint2 c = *reinterpret_cast<const uint2*>(cnt16 + r1 * 4);
+            acc0 += a.x + c.x;
+            acc1 += a.y + c.y;
+          } else {
+            acc0 += (uint32_t)cnt16[r0] + (uint32_t)cnt16[r1];
+          }
+        }
+        // packed inclusive scans over the lanes (totals are N < 2^16: no carry between halves)
+        uint32_t inc0 = acc0, inc1 = acc1;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
-          const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
-          if (lane >= off) incl += o;
+          const uint32_t o0 = __shfl_up_sync(0xffffffffu, inc0, off);
+          const uint32_t o1 = __shfl_up_sync(0xffffffffu, inc1, off);
+          if (lane >= off) {
+            inc0 += o0;
+            inc1 += o1;
+          }
         }
-        const int s_hi = median_find(cnt, pt, P.seg_len, lane, incl, sum, k_hi);
         const double* sv = P.sorted_vals + (d0 + j) * P.n_rows;
-        double med = sv[s_hi];
-        if (even) {
-          const int s_lo = median_find(cnt, pt, P.seg_len, lane, incl, sum, k_hi - 1u);
-          med = (sv[s_lo] + med) / 2.0;
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+          if (b < nb) {
+            const uint32_t pi = (b < 2) ? inc0 : inc1, pa = (b < 2) ? acc0 : acc1;
+            const uint32_t incl = (b & 1) ? (pi >> 16) : (pi & 0xFFFFu);
+            const uint32_t sum = (b & 1) ? (pa >> 16) : (pa & 0xFFFFu);
+            const int s_hi = median_find<B>(cnt16, lin, seg_len, lane, b, incl, incl - sum, k_hi);
+            double med = sv[s_hi];
+            if (even) {
+              const int s_lo = median_find<B>(cnt16, lin, seg_len, lane, b, incl, incl - sum, k_hi - 1u);
+              med = (sv[s_lo] + med) / 2.0;
+            }
+            if (lane == 0) P.out[(d0 + j) * P.n_local + rb + b] = med;
+          }
         }
-        if (lane == 0) P.out[(d0 + j) * P.n_local + rb + b] = med;
       }
       __syncthreads();
     }
@@ -448,21 +494,23 @@ struct MedianWs {
   uint64_t* keys;
   uint32_t* idx;
   double* sorted_vals;
-  uint16_t* perm_t;
+  uint32_t* pairs;
+  uint16_t* lin;
   int64_t n_pad;
-  int seg_len;
+  int seg;          // positions per lane segment, even
 };
 
 inline MedianWs median_carve(Carver& cv, int64_t n_rows, int64_t n_cols) {
   MedianWs w{};
   w.n_pad = 1;
   while (w.n_pad < n_rows) w.n_pad <<= 1;
-  w.seg_len = (int)((n_rows + 31) / 32);
+  w.seg = (int)(((n_rows + 31) / 32 + 1) & ~(int64_t)1);
   w.work_counter = cv.take<int32_t>(64);
   w.keys = cv.take<uint64_t>((size_t)w.n_pad * n_cols);
   w.idx = cv.take<uint32_t>((size_t)w.n_pad * n_cols);
   w.sorted_vals = cv.take<double>((size_t)n_rows * n_cols);
-  w.perm_t = cv.take<uint16_t>((size_t)w.seg_len * 32 * n_cols);
+  w.pairs = cv.take<uint32_t>((size_t)w.seg * 16 * n_cols);
+  w.lin = cv.take<uint16_t>((size_t)w.seg * 32 * n_cols);
   return w;
 }
 
@@ -523,9 +571,9 @@ inline int median_prepare(const double* data, int64_t n_rows, int64_t n_cols, in
     uint32_t* ic = w.idx + d0 * n_pad;
     int rc = psort_pairs(kc, ic, n_pad, nd, s);
     if (rc) return rc;
-    const dim3 gpack((unsigned)((w.seg_len * 32 + 255) / 256), nd);
-    median_pack_kernel<<<gpack, 256, 0, s>>>(kc, ic, n_rows, n_pad, w.seg_len, w.sorted_vals + d0 * n_rows,
-                                             w.perm_t + d0 * w.seg_len * 32);
+    const dim3 gpack((unsigned)((w.seg * 32 + 255) / 256), nd);
+    median_pack_kernel<<<gpack, 256, 0, s>>>(kc, ic, n_rows, n_pad, w.seg, w.sorted_vals + d0 * n_rows,
+                                             w.pairs + d0 * w.seg * 16, w.lin + d0 * w.seg * 32);
     B2_LAUNCH_CHECK();
   }
   return 0;
@@ -548,24 +596,26 @@ inline int median_resample(const double* data, int64_t n_rows, int64_t n_cols, i
 
   K1mParams P{};
   P.sorted_vals = w.sorted_vals;
-  P.perm_t = w.perm_t;
+  P.pairs = w.pairs;
+  P.lin = w.lin;
   P.n_rows = n_rows;
   P.n_cols = n_cols;
-  P.seg_len = w.seg_len;
-  P.count_words = (int32_t)(((n_rows + 2) / 2 + 31) & ~(int64_t)31);
-  P.batch = (int64_t)kMedBatch * P.count_words * 4 <= 64 * 1024 ? kMedBatch : 1;
-  const int64_t cnt_bytes = (int64_t)P.batch * P.count_words * 4;
-  const int64_t perm_bytes = (int64_t)w.seg_len * 32 * 2;
+  P.seg = w.seg;
+  // four interleaved count tables when they fit in 64 KB, else one resample at a time
+  const int batch = (n_rows + 1) * 8 <= 64 * 1024 ? 4 : 1;
+  P.count_words = (int32_t)((((n_rows + 1) * batch + 1) / 2 + 31) & ~(int64_t)31);
+  const int64_t cnt_bytes = (int64_t)P.count_words * 4;
+  const int64_t perm_bytes = (int64_t)w.seg * 32 * 4;      // pairs + linear copy
   int64_t cpi = (kSmemDataBytes - 128 - cnt_bytes) / perm_bytes;
   if (cpi < 1) return fail(B200BOOT_EUNSUPPORTED, "median: column does not fit in shared memory");
-  cpi = std::min<int64_t>(std::min<int64_t>(cpi, 64), n_cols);
+  cpi = std::min<int64_t>(std::min<int64_t>(cpi, 32), n_cols);
   P.cols_per_item = (int32_t)cpi;
   P.n_colchunks = (int32_t)((n_cols + cpi - 1) / cpi);
   const int sms = sm_count();
   int64_t want_r = ((int64_t)sms * 8 + P.n_colchunks - 1) / P.n_colchunks;
   int64_t rchunk = (n_local + want_r - 1) / want_r;
-  rchunk = ((rchunk + P.batch - 1) / P.batch) * P.batch;
-  P.rchunk = (int32_t)std::min<int64_t>(std::max<int64_t>(rchunk, P.batch), 1 << 20);
+  rchunk = ((rchunk + batch - 1) / batch) * batch;
+  P.rchunk = (int32_t)std::min<int64_t>(std::max<int64_t>(rchunk, batch), 1 << 20);
   P.n_rchunks = (int32_t)((n_local + P.rchunk - 1) / P.rchunk);
   P.n_items = (int64_t)P.n_colchunks * P.n_rchunks;
   if (P.n_items >= ((int64_t)1 << 31)) return fail(B200BOOT_EINVAL, "too many work items");
@@ -581,12 +631,17 @@ inline int median_resample(const double* data, int64_t n_rows, int64_t n_cols, i
   int dev = 0;
   B2_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    B2_CUDA(cudaFuncSetAttribute(k1m_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B2_CUDA(cudaFuncSetAttribute(k1m_median_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(kSmemHeader + kSmemDataBytes)));
+    B2_CUDA(cudaFuncSetAttribute(k1m_median_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(kSmemHeader + kSmemDataBytes)));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   const int grid = (int)std::min<int64_t>(sms, P.n_items);
-  k1m_median_kernel<<<grid, kMedThreads, smem, s>>>(P);
+  if (batch == 4)
+    k1m_median_kernel<4><<<grid, kMedThreads, smem, s>>>(P);
+  else
+    k1m_median_kernel<1><<<grid, kMedThreads, smem, s>>>(P);
   B2_LAUNCH_CHECK();
   return 0;
 }
