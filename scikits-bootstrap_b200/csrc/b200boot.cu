@@ -38,6 +38,7 @@ inline int blocks_for(int64_t n, int threads, int64_t cap) {
 struct ResampleWs {
   int32_t* counts;
   int32_t* cls;         // [n_full][n_local][16]
+  int32_t* gcounts;     // [n_groups][n_local] level-1 occupancies
   int32_t* left;        // class-chain scratch: remainders, deferred list, per-step counters
   int32_t* pending;
   int32_t* n_pending;
@@ -56,6 +57,7 @@ ResampleWs carve_resample(Carver& cv, const Plan& plan, int stat, int64_t n_loca
   w.jack = cv.take<JackState>(1);
   w.red = cv.take<double>((size_t)kRedBlocks * kMaxMoments);
   w.counts = plan.n_tiles > 1 ? cv.take<int32_t>((size_t)plan.n_tiles * n_local) : nullptr;
+  w.gcounts = plan.n_tiles > 1 ? cv.take<int32_t>((size_t)n_tile_groups(plan) * std::max<int64_t>(n_local, 1)) : nullptr;
   w.cls = plan.n_full > 0 ? cv.take<int32_t>((size_t)plan.n_full * n_local * kClasses) : nullptr;
   if (plan.n_full > 0) {
     w.left = cv.take<int32_t>((size_t)plan.n_full * std::max<int64_t>(n_local, 1));
@@ -102,11 +104,23 @@ int prepare_rows(const double* const* data, int n_arrays, int64_t n_rows, int st
 // otherwise as one thread-per-pair chain kernel; both give the same values.
 int launch_occupancies(uint64_t seed, int64_t resample_lo, int64_t n_local, const Plan& plan,
                        int32_t* counts, int32_t* cls, cudaStream_t s, int32_t* left = nullptr,
-                       int32_t* pending = nullptr, int32_t* n_pending = nullptr) {
+                       int32_t* pending = nullptr, int32_t* n_pending = nullptr, int32_t* gcounts = nullptr) {
   if (plan.n_tiles <= 1) return 0;
-  k0_tile_counts_kernel<<<blocks_for(n_local, 128, 1 << 30), 128, 0, s>>>(seed, resample_lo, n_local, plan,
-                                                                        counts);
-  B2_LAUNCH_CHECK();
+  if (gcounts) {
+    const int64_t ng = n_tile_groups(plan);
+    if (ng > 1) {
+      k0_group_counts_kernel<<<blocks_for(n_local, 128, 1 << 30), 128, 0, s>>>(seed, resample_lo, n_local, plan,
+                                                                             gcounts);
+      B2_LAUNCH_CHECK();
+    }
+    k0_tiles_in_groups_kernel<<<blocks_for(ng * n_local, 128, 1 << 30), 128, 0, s>>>(seed, resample_lo, n_local,
+                                                                                    plan, gcounts, counts);
+    B2_LAUNCH_CHECK();
+  } else {
+    k0_tile_counts_kernel<<<blocks_for(n_local, 128, 1 << 30), 128, 0, s>>>(seed, resample_lo, n_local, plan,
+                                                                          counts);
+    B2_LAUNCH_CHECK();
+  }
   if (plan.n_full > 0 && cls) {
     const int64_t total = plan.n_full * n_local;
     if (total >= ((int64_t)1 << 31)) return fail(B200BOOT_EINVAL, "too many (tile, resample) pairs");
@@ -277,7 +291,8 @@ int b200boot_resample_stat(const double* const* data, int n_arrays, int64_t n_ro
   rc = prepare_rows(data, n_arrays, n_rows, stat_id, w, rows, s);
   if (rc) return rc;
 
-  rc = launch_occupancies(seed, resample_lo, n_local, plan, w.counts, w.cls, s, w.left, w.pending, w.n_pending);
+  rc = launch_occupancies(seed, resample_lo, n_local, plan, w.counts, w.cls, s, w.left, w.pending, w.n_pending,
+                          w.gcounts);
   if (rc) return rc;
   B2_CUDA(cudaMemsetAsync(w.work_counter, 0, 256, s));
 

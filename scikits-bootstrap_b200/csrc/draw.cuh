@@ -158,14 +158,47 @@ B2_HD void class_count_chain(uint64_t seed, int64_t resample, int64_t t, int64_t
 }
 
 // ---- tile occupancies -------------------------------------------------------
-// counts[t * stride] for t in [0, n_tiles): conditional-binomial chain over the
-// cells in order; the last cell takes what is left.
+// counts[t * stride] for t in [0, n_tiles): the multinomial over the cells is sampled
+// in two levels so that no chain is longer than ~2 x 32 steps: first the occupancies
+// of groups of kTileGroup consecutive cells (conditional binomials over the groups,
+// cell id 0x40000000 | g), then inside each group a chain over its cells (cell id t);
+// the last group / cell takes what is left.  Plans with at most kTileGroup cells have
+// a single group and only the inner chain.
+constexpr int kTileGroup = 32;
+
+B2_HD uint32_t group_cell_id(int64_t g) { return 0x40000000u | (uint32_t)g; }
+B2_HD int64_t n_tile_groups(const Plan& plan) { return (plan.n_tiles + kTileGroup - 1) / kTileGroup; }
+
+// rows covered by cells [t0, t1)
+B2_HD int64_t rows_of_cells(const Plan& plan, int64_t t0, int64_t t1) {
+  const int64_t full = (t1 < plan.n_full ? t1 : plan.n_full) - (t0 < plan.n_full ? t0 : plan.n_full);
+  return full * plan.tile() + ((t1 > plan.n_full && t0 <= plan.n_full) ? plan.rem : 0);
+}
+
+// level 1: draws per group; gcounts[g * stride]
 template <typename I>
-B2_HD void tile_count_chain(uint64_t seed, int64_t resample, const Plan& plan, I* counts,
-                            int64_t stride) {
-  int64_t n_left = plan.n_rows;   // draws still to place
-  int64_t rows_left = plan.n_rows;
-  for (int64_t t = 0; t + 1 < plan.n_tiles; ++t) {
+B2_HD void group_count_chain(uint64_t seed, int64_t resample, const Plan& plan, I* gcounts, int64_t stride) {
+  const int64_t ng = n_tile_groups(plan);
+  int64_t n_left = plan.n_rows, rows_left = plan.n_rows;
+  for (int64_t g = 0; g + 1 < ng; ++g) {
+    const int64_t rows = rows_of_cells(plan, g * kTileGroup, (g + 1) * kTileGroup);
+    const Stream s = make_stream(seed, resample, group_cell_id(g), kPurposeBinomial);
+    const int64_t k = binomial_ratio(n_left, rows, rows_left, s);
+    gcounts[g * stride] = (I)k;
+    n_left -= k;
+    rows_left -= rows;
+  }
+  gcounts[(ng - 1) * stride] = (I)n_left;
+}
+
+// level 2: the n_group draws of group g over its cells; counts[t * stride]
+template <typename I>
+B2_HD void tile_chain_in_group(uint64_t seed, int64_t resample, const Plan& plan, int64_t g,
+                               int64_t n_group, I* counts, int64_t stride) {
+  const int64_t t0 = g * kTileGroup;
+  const int64_t t1 = (t0 + kTileGroup < plan.n_tiles) ? t0 + kTileGroup : plan.n_tiles;
+  int64_t n_left = n_group, rows_left = rows_of_cells(plan, t0, t1);
+  for (int64_t t = t0; t + 1 < t1; ++t) {
     const int64_t sz = plan.cell_size(t);
     const Stream s = make_stream(seed, resample, (uint32_t)t, kPurposeBinomial);
     const int64_t k = binomial_ratio(n_left, sz, rows_left, s);
@@ -173,7 +206,26 @@ B2_HD void tile_count_chain(uint64_t seed, int64_t resample, const Plan& plan, I
     n_left -= k;
     rows_left -= sz;
   }
-  counts[(plan.n_tiles - 1) * stride] = (I)n_left;
+  counts[(t1 - 1) * stride] = (I)n_left;
+}
+
+// both levels, sequentially (host probes, single-thread uses)
+template <typename I>
+B2_HD void tile_count_chain(uint64_t seed, int64_t resample, const Plan& plan, I* counts,
+                            int64_t stride) {
+  const int64_t ng = n_tile_groups(plan);
+  int64_t n_left = plan.n_rows, rows_left = plan.n_rows;
+  for (int64_t g = 0; g < ng; ++g) {
+    int64_t n_g = n_left;
+    if (g + 1 < ng) {
+      const int64_t rows = rows_of_cells(plan, g * kTileGroup, (g + 1) * kTileGroup);
+      const Stream s = make_stream(seed, resample, group_cell_id(g), kPurposeBinomial);
+      n_g = binomial_ratio(n_left, rows, rows_left, s);
+      n_left -= n_g;
+      rows_left -= rows;
+    }
+    tile_chain_in_group<I>(seed, resample, plan, g, n_g, counts, stride);
+  }
 }
 
 }  // namespace b200boot

@@ -36,12 +36,35 @@ constexpr int kFastSmemBase = 1024 + kSmemHeader;
 constexpr int kFastStride2 = 8 << 13;   // bytes between the two arrays of a 2-array full tile
 
 // ------------------------------------------------------------------ K0 --------
+// one thread per resample walks both levels (inspection API, small jobs)
 __global__ void __launch_bounds__(128) k0_tile_counts_kernel(uint64_t seed, int64_t resample_lo,
                                                              int64_t n_local, Plan plan,
                                                              int32_t* __restrict__ counts) {
   const int64_t rl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (rl >= n_local) return;
   tile_count_chain<int32_t>(seed, resample_lo + rl, plan, counts + rl, n_local);
+}
+
+// two-kernel form: level 1 per resample, then level 2 per (group, resample) — chains of
+// at most 32 steps and n_groups times the parallelism
+__global__ void __launch_bounds__(128) k0_group_counts_kernel(uint64_t seed, int64_t resample_lo,
+                                                              int64_t n_local, Plan plan,
+                                                              int32_t* __restrict__ gcounts) {
+  const int64_t rl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (rl >= n_local) return;
+  group_count_chain<int32_t>(seed, resample_lo + rl, plan, gcounts + rl, n_local);
+}
+
+__global__ void __launch_bounds__(128) k0_tiles_in_groups_kernel(uint64_t seed, int64_t resample_lo,
+                                                                 int64_t n_local, Plan plan,
+                                                                 const int32_t* __restrict__ gcounts,
+                                                                 int32_t* __restrict__ counts) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t ng = n_tile_groups(plan);
+  if (e >= ng * n_local) return;
+  const int64_t g = e / n_local, rl = e - g * n_local;
+  const int64_t n_g = ng > 1 ? (int64_t)gcounts[e] : plan.n_rows;
+  tile_chain_in_group<int32_t>(seed, resample_lo + rl, plan, g, n_g, counts + rl, n_local);
 }
 
 // Class occupancies of the full tiles: cls[(t * n_local + r) * 16 + c]; one thread

@@ -164,6 +164,30 @@ def test_tile_counts_are_multinomial():
     assert abs(cov - (-n * pr[0] * pr[1])) < 6 * n * pr[0] * (1 - pr[0]) / np.sqrt(m)
 
 
+def test_tile_counts_two_level_chain():
+    """More than 32 cells: occupancies are sampled per group of 32 cells, then inside each
+    group; marginals, within-group and across-group covariances must stay multinomial."""
+    n = 16384 * 70 + 999                 # 70 full tiles + remainder = 71 cells = 3 groups
+    m = 1500
+    plan = _abi.make_plan(n, 1)
+    assert plan.n_tiles == 71
+    cnt = np.array([_host_counts(8, n, 1, r) for r in range(m)], dtype=float)
+    assert (cnt.sum(axis=1) == n).all()
+    sizes = np.array([16384] * 70 + [999], dtype=float)
+    pr = sizes / n
+    z = (cnt.mean(axis=0) - n * pr) / np.sqrt(n * pr * (1 - pr) / m)
+    assert np.abs(z).max() < 5 and abs(z.std() - 1) < 0.3
+    v = cnt.var(axis=0) / (n * pr * (1 - pr))
+    assert np.abs(v - 1).max() < 0.25
+    for i, j in [(0, 1), (0, 40), (31, 32), (10, 69)]:          # same group / different groups
+        cov = np.cov(cnt[:, i], cnt[:, j])[0, 1]
+        assert abs(cov + n * pr[i] * pr[j]) < 6 * n * pr[i] / np.sqrt(m)
+    g = cnt[:, :32].sum(axis=1)                                  # a whole group is binomial too
+    pg = sizes[:32].sum() / n
+    assert abs(g.mean() - n * pg) < 5 * np.sqrt(n * pg * (1 - pg) / m)
+    assert 0.8 < g.var() / (n * pg * (1 - pg)) < 1.25
+
+
 def test_class_counts_are_multinomial():
     m = 3000
     out = np.empty((m, 16), dtype=np.int32)
