@@ -294,10 +294,15 @@ def main():
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         local_points = points / world
         achieved = local_points * BYTES_PER_POINT / (k1_mean_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, ncu = None, None
         tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            prof = json.load(open(tpath))
+            traffic = prof.get("dram_bytes_per_launch")
+            # the kernel serves rows from shared memory: what binds it, from the committed
+            # ncu capture (profiles/), not re-measured here
+            ncu = {k: prof[k] for k in ("issue_slots_active_pct", "smem_wavefront_pipe_pct", "alu_pipe_pct",
+                                        "fp64_pipe_pct", "points_per_clk_per_sm", "source") if k in prof}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -305,7 +310,7 @@ def main():
             "config": workload_config({"parallelism": f"resample-shard x{world}", "result": [float(v) for v in result]}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "kernel": "k1_resample_kernel<kMomSum>",
-                         "kernel_ms": k1_mean_ms, "peak_source": peak_src,
+                         "kernel_ms": k1_mean_ms, "peak_source": peak_src, "ncu_shared_memory_regime": ncu,
                          "note": "algorithmic 8 B per resampled point; rows are staged in shared memory, so "
                                  "DRAM traffic is far below the algorithmic bytes and frac may exceed 1"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
