@@ -87,7 +87,32 @@ class Workspace:
         return ptr + off, self._buf.numel() - off
 
 
-_ws = Workspace()
+class _PerThreadWorkspace:
+    """One grow-only workspace per Python thread (calls from different threads may run
+    on different streams and must not share scratch)."""
+
+    def __init__(self):
+        import threading
+        self._local = threading.local()
+
+    def get(self, nbytes: int):
+        ws = getattr(self._local, "ws", None)
+        if ws is None:
+            ws = self._local.ws = Workspace()
+        return ws.get(nbytes)
+
+
+_ws = _PerThreadWorkspace()
+
+
+def device_context(arrays):
+    """Context manager selecting the CUDA device the job runs on: the device of the first
+    CUDA tensor among the inputs, else the current device."""
+    torch = require_cuda()
+    for a in arrays:
+        if isinstance(a, torch.Tensor) and a.device.type == "cuda":
+            return torch.cuda.device(a.device)
+    return torch.cuda.device(torch.cuda.current_device())
 
 
 def _ptr_array(tensors: Sequence) -> C.Array:

@@ -380,6 +380,13 @@ def _ci_impl(data, statfunction, alpha, n_samples, method, output, epsilon, mult
         raise ValueError("n_samples must be positive")
     key = _seed_key(seed)
 
+    with _device.device_context(arrays):
+        return _ci_on_device(spec, arrays, multi, n_samples, key, indices, alphas, method, output,
+                             return_dist)
+
+
+def _ci_on_device(spec, arrays, multi, n_samples, key, indices, alphas, method, output, return_dist):
+    """Device part of ci (warnings use stacklevel=4: the user's frame)."""
     run = _Run(spec, arrays, multi, n_samples, key, indices)
     stat = run.resample()                                         # float64[D][n_local]
 
@@ -402,7 +409,7 @@ def _ci_impl(data, statfunction, alpha, n_samples, method, output, epsilon, mult
 Statistic values were likely all equal. Affected CI will \
 be inaccurate.".format(nanind),
                 InstabilityWarning,
-                stacklevel=3,
+                stacklevel=4,
             )
         avals = _interval.bca_levels(less, n_samples, accel_s, alphas)
 
@@ -412,19 +419,19 @@ be inaccurate.".format(nanind),
             "Some values were NaN; results are probably unstable "
             + "(all values were probably equal)",
             InstabilityWarning,
-            stacklevel=3,
+            stacklevel=4,
         )
     if "extremal" in flags:
         warnings.warn(
             "Some values used extremal samples; " + "results are probably unstable.",
             InstabilityWarning,
-            stacklevel=3,
+            stacklevel=4,
         )
     elif "top10" in flags:
         warnings.warn(
             "Some values used top 10 low/high samples; " + "results may be unstable.",
             InstabilityWarning,
-            stacklevel=3,
+            stacklevel=4,
         )
 
     # order statistics without sorting: ranks int[A][D]            bootstrap.py:482-490
@@ -488,6 +495,11 @@ def _pval_impl(data, statfunction, compfunction, n_samples, multi, seed, indices
     _check_spec(spec, arrays, multi)
     n_samples = int(n_samples)
     key = _seed_key(seed)
+    with _device.device_context(arrays):
+        return _pval_on_device(spec, arrays, multi, n_samples, key, indices, compfunction)
+
+
+def _pval_on_device(spec, arrays, multi, n_samples, key, indices, compfunction):
     run = _Run(spec, arrays, multi, n_samples, key, indices)
     stat = run.resample()
     if isinstance(compfunction, DeviceCompare):

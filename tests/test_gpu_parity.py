@@ -477,6 +477,33 @@ def test_input_forms_agree():
                     boot.ci(x32.astype(np.float64), np.mean, seed=5, n_samples=2000))
 
 
+def test_input_on_another_device_and_threads():
+    """A CUDA tensor on a non-current device runs there; concurrent calls from Python
+    threads use separate scratch."""
+    import threading
+    want = boot.ci(DATA20, np.mean, seed=5, n_samples=2000)
+    if torch().cuda.device_count() >= 2:
+        x1 = torch().as_tensor(DATA20).to("cuda:1")
+        assert torch().cuda.current_device() == 0
+        assert_array_equal(boot.ci(x1, np.mean, seed=5, n_samples=2000), want)
+        assert torch().cuda.current_device() == 0
+    big = np.random.default_rng(0).standard_normal(60000)
+    ref = [boot.ci(big, np.mean, seed=s, n_samples=500, method="pi") for s in range(4)]
+    got = [None] * 4
+
+    def work(i):
+        with torch().cuda.stream(torch().cuda.Stream()):
+            got[i] = boot.ci(big, np.mean, seed=i, n_samples=500, method="pi")
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for a, b in zip(got, ref):
+        assert_array_equal(a, b)
+
+
 def test_paired_tuple_equals_axis0_columns():
     """A (N, D) array under an axis-0 statistic shares one index set across columns
     (bootstrap.py:431): each column equals the 1-D run with the same seed."""
