@@ -288,6 +288,40 @@ def pval(data, statfunction=np.average, compfunction=lambda s: s > 0, n_samples=
     return np.mean([compfunction(s) for s in stat], axis=0)
 
 
+def ci_abc(data, statfunction=np.average, alpha=0.05, epsilon=0.001, output="lowhigh"):
+    """Restatement of the reference's ABC interval (bootstrap.py:507-567): finite-difference
+    influence values t1, second differences t2, acceleration a, curvature cq, bias bhat,
+    then statfunction at the tilted weights.  `statfunction(x, weights=...)` as in the reference."""
+    alphas = np.array(alpha) if isinstance(alpha, Iterable) else np.array([alpha / 2, 1 - alpha / 2])
+    x = np.array(data)
+    nn = x.shape[0]
+    n = nn * 1.0
+    ep = epsilon / n
+    p0 = np.repeat(1.0 / n, nn)
+    t0 = statfunction(x, weights=p0)
+    eye = np.identity(nn)
+    tp = np.array([statfunction(x, weights=p0 + ep * (row - p0)) for row in eye], dtype=float)
+    tm = np.array([statfunction(x, weights=p0 - ep * (row - p0)) for row in eye], dtype=float)
+    t1 = (tp - tm) / (2 * ep)
+    t2 = (tp - 2 * t0 + tm) / ep ** 2
+    sighat = np.sqrt(np.sum(t1 ** 2)) / n
+    a = np.sum(t1 ** 3) / (6 * n ** 3 * sighat ** 3)
+    delta = t1 / (n ** 2 * sighat)
+    cq = (statfunction(x, weights=p0 + ep * delta) - 2 * t0
+          + statfunction(x, weights=p0 - ep * delta)) / (2 * sighat * ep ** 2)
+    bhat = np.sum(t2) / (2 * n ** 2)
+    curv = bhat / sighat - cq
+    z0 = nppf(2 * ncdf(a) * ncdf(-curv))
+    big_z = z0 + nppf(alphas)
+    za = big_z / (1 - a * big_z) ** 2
+    abc = np.array([statfunction(x, weights=p0 + z * delta) for z in za], dtype=float)
+    if output == "lowhigh":
+        return abc
+    if output == "errorbar":
+        return abs(abc - statfunction(x))[np.newaxis].T
+    raise ValueError("Output option {0} is not supported.".format(output))
+
+
 # --------------------------------------------------------------------------
 # Closed-form leave-one-out statistics for the device registry.  These replace
 # the O(N^2) loop (bootstrap.py:595-599) the same way the reference's own numba

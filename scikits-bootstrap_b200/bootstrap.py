@@ -27,7 +27,7 @@ from typing import Any, Callable, Iterator, Optional, Sequence, Tuple, Union
 import numpy as np
 
 from . import _abi, _device, _dist, _interval
-from ._registry import (DeviceCompare, DeviceStat, StatSpec, positive, require)
+from ._registry import (DeviceCompare, DeviceStat, StatSpec, lookup, positive, require)
 
 __all__ = (
     "ci",
@@ -317,6 +317,45 @@ def ci(
                     return_dist, seed, use_numba, None)
 
 
+def _ci_abc(arrays, statfunction, alphas, output):
+    """ABC interval (bootstrap.py:507-567) for the statistic the reference's ABC supports
+    among the registry: the weighted mean, np.average (the reference calls
+    `statfunction(x, weights=...)`; np.mean & co. fail its weights probe with the TypeError
+    reproduced below).
+
+    For the weighted mean the finite-difference quantities of the reference have closed
+    forms — t1_i = x_i - mean, t2 = 0, cq = 0 — so the interval follows from the first
+    three central sums, which come from the device (K3).  This is the epsilon -> well-
+    conditioned limit of the reference's formulas: the reference's own result carries the
+    rounding noise of its second differences (2e-7 relative at N = 20, 5e-4 at N = 1000 with
+    the default epsilon; 1e-9 agreement at epsilon = 0.01), see DESIGN.md."""
+    if statfunction is not np.average:
+        if lookup(statfunction) is not None or statfunction is np.mean:
+            raise TypeError("statfunction does not accept correct arguments for ABC")
+        raise NotImplementedError(
+            "method='abc' is available for the weighted mean (np.average) only; "
+            "statfunction {!r} is not in the device registry".format(statfunction))
+    if len(arrays) != 1 or len(arrays[0].shape) != 1:
+        raise NotImplementedError("method='abc' needs a single 1-D array")
+    with _device.device_context(arrays):
+        x = _device.to_device_f64(arrays[0]).reshape(-1)
+        j = _device.to_host(_device.jackknife([x], _abi.STAT_MEAN))
+    n = float(x.numel())
+    t0 = j[0]
+    s2 = j[2] * (n - 1.0) ** 2           # sum (x - mean)^2   (K3: d_i = (x_i - mean)/(N-1))
+    s3 = j[3] * (n - 1.0) ** 3           # sum (x - mean)^3
+    sighat = np.sqrt(s2) / n
+    with np.errstate(invalid="ignore", divide="ignore"):
+        a = s3 / (6 * n ** 3 * sighat ** 3)
+        z0 = _interval.nppf(2 * _interval.ncdf(a) * _interval.ncdf(-0.0))
+        big_z = z0 + _interval.nppf(alphas)
+        za = big_z / (1 - a * big_z) ** 2
+        abc = t0 + za * s2 / (n ** 2 * sighat)
+    if output == "lowhigh":
+        return abc
+    return np.abs(abc - t0)[np.newaxis].T
+
+
 def ci_indexed(data, statfunction=None, indices=None, alpha=0.05, method="bca", output="lowhigh",
                multi=None, return_dist=False):
     """Parity mode of `ci`: identical pipeline, but the resamples are the caller's
@@ -358,9 +397,9 @@ def _ci_impl(data, statfunction, alpha, n_samples, method, output, epsilon, mult
                 + "returned in this case, because the ABC method doesn't actually calculate it.")
         if multi == "independent":
             raise NotImplementedError("multi='independent' is not currently supported for ABC.")
-        raise NotImplementedError(
-            "method='abc' does no resampling and is outside the device hot path; use the "
-            "reference implementation for ABC intervals")
+        if output not in ("lowhigh", "errorbar"):
+            raise ValueError("Output option {0} is not supported.".format(output))
+        return _ci_abc(arrays, statfunction, alphas, output)
     if use_numba:                                                 # bootstrap.py:415-437
         if multi == "independent":
             raise NotImplementedError(

@@ -417,6 +417,27 @@ def test_reference_property_tests():
     assert_allclose(b.T, abs(np.average(DATA20) - a)[np.newaxis])
 
 
+def test_abc_for_the_weighted_mean():
+    """method='abc' (bootstrap.py:507-567; tests/bootstrap_test.py:140-150, 190-195, 372-376).
+    Device moments + closed forms = the well-conditioned limit of the reference's finite
+    differences: 1e-8 agreement with the oracle's faithful restatement at epsilon=0.01, and
+    within the reference's own rounding noise (2e-7) of its goldens at the default epsilon."""
+    import pandas as pd
+    got = boot.ci(DATA20, method="abc", seed=SEED)
+    assert_allclose(got, orc.ci_abc(DATA20, epsilon=0.01), rtol=1e-8)
+    assert_allclose(got, [0.20982275, 1.20374686], rtol=5e-7)
+    got = boot.ci(DATA20, alpha=(0.1, 0.2, 0.8, 0.9), method="abc")
+    assert_allclose(got, [0.39472915, 0.51161304, 0.93789723, 1.04407254], rtol=5e-7)
+    eb = boot.ci(DATA20, output="errorbar", method="abc")
+    assert eb.shape == (2, 1)
+    assert_allclose(eb.T, abs(np.average(DATA20) - boot.ci(DATA20, method="abc"))[np.newaxis])
+    assert_allclose(boot.ci(pd.Series(DATA20, index=np.arange(50, 70)), method="abc"), boot.ci(DATA20, method="abc"))
+    x = np.random.default_rng(0).gamma(2, 1, 500)
+    assert_allclose(boot.ci(x, method="abc"), orc.ci_abc(x, epsilon=0.1), rtol=1e-7)      # noise ~ 1/epsilon^2
+    with pytest.raises(ValueError):
+        boot.ci(DATA20, method="abc", return_dist=True)
+
+
 def test_warnings_match_reference():
     """tests/bootstrap_test.py:250-260."""
     with pytest.warns(boot.InstabilityWarning, match="(NaN|all equal)"):

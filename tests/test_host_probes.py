@@ -266,6 +266,10 @@ def test_registry_and_errors_without_gpu():
         boot.ci(x, method="abc", return_dist=True)
     with pytest.raises(NotImplementedError, match="not currently supported"):
         boot.ci((x, x), multi="independent", method="abc")
+    with pytest.raises(TypeError, match="statfunction does not accept correct arguments"):
+        boot.ci(x, np.mean, method="abc")             # bootstrap_test.py:270-274
+    with pytest.raises(ValueError, match="Output option invalid is not"):
+        boot.ci(x, output="invalid", method="abc")    # bootstrap_test.py:197-199
     with pytest.raises(NotImplementedError, match="Numba for independent data"):
         boot.ci((x, x), multi="independent", use_numba=True)
     with pytest.raises(ValueError, match="Numba can't be used"):
