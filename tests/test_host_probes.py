@@ -29,6 +29,24 @@ def test_header_symbols_exported_and_bound():
     assert _abi.lib().b200boot_version() == 1
 
 
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No CPU fallback: without the built library every entry point raises."""
+    monkeypatch.setattr(_abi, "_lib", None)
+    monkeypatch.setattr(_abi, "LIB_PATH", str(tmp_path / "libb200boot.so"))
+    with pytest.raises(_abi.B200BootError, match="no CPU fallback"):
+        _abi.lib()
+    with pytest.raises(_abi.B200BootError):
+        _abi.make_plan(1000, 1)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "scikits-bootstrap_b200")
+    for name in os.listdir(pkg):
+        if name.endswith(".py"):
+            src = open(os.path.join(pkg, name)).read()
+            assert "bootstrap_oracle" not in src and "import oracle" not in src and "/root/reference" not in src
+
+
 def test_errors_do_not_cross_abi_as_exceptions():
     L = _abi.lib()
     assert L.b200boot_make_plan(0, 1, C.byref(_abi.Plan())) == -1
