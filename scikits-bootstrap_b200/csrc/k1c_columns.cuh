@@ -88,26 +88,50 @@ __global__ void __launch_bounds__(kColThreads, 1) k1c_columns_kernel(const K1cPa
       const int64_t rl = rl0 + grp;
       const bool live = rl < r_end;
       const Stream st = make_stream(P.seed, P.resample_lo + (live ? rl : r_begin), 0u, kPurposeIndex);
-      double acc[NM][2];
+      double acc[NM][4];
 #pragma unroll
-      for (int m = 0; m < NM; ++m) acc[m][0] = acc[m][1] = 0.0;
-      for (uint32_t q0 = 0; q0 < n_blocks; q0 += W) {
-        // lane `col` of the group draws block q0 + col (4 row numbers)
+      for (int m = 0; m < NM; ++m)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[m][j] = 0.0;
+      // this lane's column inside a row; rows are W * 8 bytes apart
+      const unsigned char* col_base = reinterpret_cast<const unsigned char*>(s_tile) + col * 8;
+      constexpr uint32_t kRowBytes = W * 8;
+      const int src0 = grp * W;
+      // groups of W whole blocks (4 W draws): no bound checks, fully unrolled
+      const uint32_t n_whole = n / 4;                    // blocks with 4 valid draws
+      uint32_t q0 = 0;
+      for (; q0 + W <= n_whole; q0 += W) {
+        uint32_t mine[4];
+        lemire_block<false>(st, q0 + (uint32_t)col, n, thresh, (int64_t)n,
+                            [&](int j, int64_t, uint32_t idx) { mine[j] = idx * kRowBytes; }, &P.rk);
+#pragma unroll
+        for (int src = 0; src < W; ++src) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t off = __shfl_sync(0xffffffffu, mine[j], src0 + src);
+            const double v = *reinterpret_cast<const double*>(col_base + off);
+            acc[0][j] += v;
+            if (NM == 2) acc[NM - 1][j] += v * v;
+          }
+        }
+      }
+      // what is left: fewer than W whole blocks and possibly one partial block
+      if (q0 < n_blocks) {
         uint32_t mine[4] = {0u, 0u, 0u, 0u};
         const uint32_t q = q0 + (uint32_t)col;
         if (q < n_blocks)
           lemire_block<true>(st, q, n, thresh, (int64_t)n,
-                             [&](int j, int64_t, uint32_t idx) { mine[j] = idx; }, &P.rk);
-        const int n_src = (int)min((uint32_t)W, n_blocks - q0);
+                             [&](int j, int64_t, uint32_t idx) { mine[j] = idx * kRowBytes; }, &P.rk);
+        const int n_src = (int)(n_blocks - q0);
         for (int src = 0; src < n_src; ++src) {
           const uint32_t base = (q0 + (uint32_t)src) * 4u;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint32_t idx = __shfl_sync(0xffffffffu, mine[j], grp * W + src);
+            const uint32_t off = __shfl_sync(0xffffffffu, mine[j], src0 + src);
             if (base + j < n) {
-              const double v = s_tile[(size_t)idx * W + col];
-              acc[0][j & 1] += v;
-              if (NM == 2) acc[NM - 1][j & 1] += v * v;
+              const double v = *reinterpret_cast<const double*>(col_base + off);
+              acc[0][j] += v;
+              if (NM == 2) acc[NM - 1][j] += v * v;
             }
           }
         }
@@ -115,7 +139,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k1c_columns_kernel(const K1cPa
       if (live && d0 + col < P.n_cols) {
         double m[kMaxMoments];
 #pragma unroll
-        for (int k = 0; k < NM; ++k) m[k] = acc[k][0] + acc[k][1];
+        for (int k = 0; k < NM; ++k) m[k] = (acc[k][0] + acc[k][1]) + (acc[k][2] + acc[k][3]);
         P.out[(d0 + col) * P.n_local + rl] = finish_stat(P.stat, m, (double)n);
       }
     }
