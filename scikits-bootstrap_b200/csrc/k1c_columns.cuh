@@ -101,15 +101,25 @@ __global__ void __launch_bounds__(kColThreads, 1) k1c_columns_kernel(const K1cPa
       const uint32_t n_whole = n / 4;                    // blocks with 4 valid draws
       uint32_t q0 = 0;
       for (; q0 + W <= n_whole; q0 += W) {
-        uint32_t mine[4];
+        // row numbers are < 2^16: two per 32-bit word halve the shuffle traffic (shuffles
+        // share the LSU data pipe with the row reads, which is what binds this kernel)
+        uint32_t pair01 = 0u, pair23 = 0u;
         lemire_block<false>(st, q0 + (uint32_t)col, n, thresh, (int64_t)n,
-                            [&](int j, int64_t, uint32_t idx) { mine[j] = idx * kRowBytes; }, &P.rk);
+                            [&](int j, int64_t, uint32_t idx) {
+                              if (j == 0) pair01 = idx;
+                              if (j == 1) pair01 |= idx << 16;
+                              if (j == 2) pair23 = idx;
+                              if (j == 3) pair23 |= idx << 16;
+                            }, &P.rk);
 #pragma unroll
         for (int src = 0; src < W; ++src) {
+          const uint32_t p01 = __shfl_sync(0xffffffffu, pair01, src0 + src);
+          const uint32_t p23 = __shfl_sync(0xffffffffu, pair23, src0 + src);
+          const uint32_t off[4] = {(p01 & 0xFFFFu) * kRowBytes, (p01 >> 16) * kRowBytes,
+                                   (p23 & 0xFFFFu) * kRowBytes, (p23 >> 16) * kRowBytes};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint32_t off = __shfl_sync(0xffffffffu, mine[j], src0 + src);
-            const double v = *reinterpret_cast<const double*>(col_base + off);
+            const double v = *reinterpret_cast<const double*>(col_base + off[j]);
             acc[0][j] += v;
             if (NM == 2) acc[NM - 1][j] += v * v;
           }
