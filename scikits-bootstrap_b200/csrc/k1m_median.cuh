@@ -22,7 +22,6 @@ namespace b200boot {
 
 constexpr int kMedThreads = 1024;
 constexpr int kMedWarps = kMedThreads / 32;
-constexpr int kMedBatch = 4;              // max resamples whose count vectors are resident at once
 constexpr int64_t kMedMaxRows = kSmemDataBytes / 8;   // single-cell plans only (28 672 rows)
 
 // ---- per-column (key, row) bitonic sort -------------------------------------------
@@ -180,7 +179,8 @@ __device__ __forceinline__ int median_find(const uint16_t* __restrict__ cnt,
 // B segment sums are carried packed (two u16 per 32-bit add).
 template <int B>
 __global__ void __launch_bounds__(kMedThreads, 1) k1m_median_kernel(const K1mParams P) {
-  static_assert(B == 4 || B == 1, "batch of 4 (interleaved) or 1");
+  static_assert(B == 8 || B == 4 || B == 1, "batch of 8 / 4 (interleaved) or 1");
+  constexpr int NP = B == 1 ? 1 : B / 2;           // packed u16-pair accumulators
   extern __shared__ __align__(128) unsigned char smem_raw[];
   volatile int* s_item = reinterpret_cast<volatile int*>(smem_raw);
   uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem_raw + 128);                 // count table
@@ -243,36 +243,46 @@ __global__ void __launch_bounds__(kMedThreads, 1) k1m_median_kernel(const K1mPar
       for (int j = warp; j < dc; j += kMedWarps) {
         const uint32_t* pp = s_pairs + (size_t)j * pair_words;
         const uint16_t* lin = s_lin + (size_t)j * seg_len * 32;
-        // packed segment sums: resamples (0,1) in acc0, (2,3) in acc1
-        uint32_t acc0 = 0u, acc1 = 0u;
+        // packed segment sums: resamples (2p, 2p+1) in acc[p]
+        uint32_t acc[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) acc[p] = 0u;
         for (int i2 = 0; i2 < seg_len / 2; ++i2) {
           const uint32_t two = pp[i2 * 32 + lane];
           const uint32_t r0 = two & 0xFFFFu, r1 = two >> 16;
-          if (B == 4) {
+          if (B == 8) {
+            const uint4 a = *reinterpret_cast<const uint4*>(cnt16 + r0 * 8);
+            const uint4 c = *reinterpret_cast<const uint4*>(cnt16 + r1 * 8);
+            acc[0] += a.x + c.x;
+            acc[1 % NP] += a.y + c.y;
+            acc[2 % NP] += a.z + c.z;
+            acc[3 % NP] += a.w + c.w;
+          } else if (B == 4) {
             const uint2 a = *reinterpret_cast<const uint2*>(cnt16 + r0 * 4);
             const uint2 c = *reinterpret_cast<const uint2*>(cnt16 + r1 * 4);
-            acc0 += a.x + c.x;
-            acc1 += a.y + c.y;
+            acc[0] += a.x + c.x;
+            acc[1 % NP] += a.y + c.y;
           } else {
-            acc0 += (uint32_t)cnt16[r0] + (uint32_t)cnt16[r1];
+            acc[0] += (uint32_t)cnt16[r0] + (uint32_t)cnt16[r1];
           }
         }
         // packed inclusive scans over the lanes (totals are N < 2^16: no carry between halves)
-        uint32_t inc0 = acc0, inc1 = acc1;
+        uint32_t inc[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) inc[p] = acc[p];
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
-          const uint32_t o0 = __shfl_up_sync(0xffffffffu, inc0, off);
-          const uint32_t o1 = __shfl_up_sync(0xffffffffu, inc1, off);
-          if (lane >= off) {
-            inc0 += o0;
-            inc1 += o1;
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc[p], off);
+            if (lane >= off) inc[p] += o;
           }
         }
         const double* sv = P.sorted_vals + (d0 + j) * P.n_rows;
 #pragma unroll
         for (int b = 0; b < B; ++b) {
           if (b < nb) {
-            const uint32_t pi = (b < 2) ? inc0 : inc1, pa = (b < 2) ? acc0 : acc1;
+            const uint32_t pi = inc[(b / 2) % NP], pa = acc[(b / 2) % NP];
             const uint32_t incl = (b & 1) ? (pi >> 16) : (pi & 0xFFFFu);
             const uint32_t sum = (b & 1) ? (pa >> 16) : (pa & 0xFFFFu);
             const int s_hi = median_find<B>(cnt16, lin, seg_len, lane, b, incl, incl - sum, k_hi);
@@ -601,8 +611,8 @@ inline int median_resample(const double* data, int64_t n_rows, int64_t n_cols, i
   P.n_rows = n_rows;
   P.n_cols = n_cols;
   P.seg = w.seg;
-  // four interleaved count tables when they fit in 64 KB, else one resample at a time
-  const int batch = (n_rows + 1) * 8 <= 64 * 1024 ? 4 : 1;
+  // eight / four interleaved count tables when they fit in 64 KB, else one resample at a time
+  const int batch = (n_rows + 1) * 16 <= 64 * 1024 ? 8 : ((n_rows + 1) * 8 <= 64 * 1024 ? 4 : 1);
   P.count_words = (int32_t)((((n_rows + 1) * batch + 1) / 2 + 31) & ~(int64_t)31);
   const int64_t cnt_bytes = (int64_t)P.count_words * 4;
   const int64_t perm_bytes = (int64_t)w.seg * 32 * 4;      // pairs + linear copy
@@ -631,6 +641,8 @@ inline int median_resample(const double* data, int64_t n_rows, int64_t n_cols, i
   int dev = 0;
   B2_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !configured[dev]) {
+    B2_CUDA(cudaFuncSetAttribute(k1m_median_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(kSmemHeader + kSmemDataBytes)));
     B2_CUDA(cudaFuncSetAttribute(k1m_median_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(kSmemHeader + kSmemDataBytes)));
     B2_CUDA(cudaFuncSetAttribute(k1m_median_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -638,7 +650,9 @@ inline int median_resample(const double* data, int64_t n_rows, int64_t n_cols, i
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   const int grid = (int)std::min<int64_t>(sms, P.n_items);
-  if (batch == 4)
+  if (batch == 8)
+    k1m_median_kernel<8><<<grid, kMedThreads, smem, s>>>(P);
+  else if (batch == 4)
     k1m_median_kernel<4><<<grid, kMedThreads, smem, s>>>(P);
   else
     k1m_median_kernel<1><<<grid, kMedThreads, smem, s>>>(P);
