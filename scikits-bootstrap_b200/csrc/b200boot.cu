@@ -174,15 +174,24 @@ int launch_k1_variant(const K1Params& P, size_t smem, int grid, cudaStream_t s) 
   return 0;
 }
 
+// One-time probe per device (synchronises once): is the dynamic shared memory of a kernel
+// without static shared memory at 0x400, as the FAST variants assume?
 inline bool fast_smem_addressing() {
   static int cached[64] = {0};   // 0 unknown, 1 yes, 2 no
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
   if (cached[dev] == 0) {
+    cached[dev] = 2;
     int reserved = 0;
-    const bool ok = cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, dev) == cudaSuccess &&
-                    reserved == 1024;
-    cached[dev] = ok ? 1 : 2;
+    uint32_t* d_out = nullptr;
+    uint32_t h_out = 0;
+    if (cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, dev) == cudaSuccess &&
+        reserved == 1024 && cudaMalloc(&d_out, sizeof(uint32_t)) == cudaSuccess) {
+      probe_dynamic_smem_base_kernel<<<1, 32, 1024>>>(d_out);
+      if (cudaMemcpy(&h_out, d_out, sizeof(uint32_t), cudaMemcpyDeviceToHost) == cudaSuccess && h_out == 1024u)
+        cached[dev] = 1;
+      cudaFree(d_out);
+    }
   }
   return cached[dev] == 1;
 }

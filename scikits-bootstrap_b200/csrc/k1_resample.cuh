@@ -25,15 +25,21 @@ constexpr int kK1Warps = kK1Threads / 32;
 constexpr int kSmemHeader = 128;  // mbarrier + work-item slot
 // sm_90+/sm_100: the first 1 KB of the shared window is reserved by the system, so a
 // kernel without static shared memory finds its dynamic shared memory at 0x400.  The
-// FAST kernel variant bakes cell address = 0x400 + header into LDS immediates (the
-// host selects it only when cudaDevAttrReservedSharedMemoryPerBlock == 1024 and the
-// kernel traps if the assumption does not hold).
+// FAST kernel variant bakes cell address = 0x400 + header into LDS immediates.  The host
+// selects it only after a one-time probe kernel has confirmed, on this device, that the
+// dynamic shared memory of a static-shared-free kernel starts at 0x400
+// (probe_dynamic_smem_base_kernel); the kernel still traps if the assumption is violated.
 #ifndef B2_CLASS_UNROLL
 #define B2_CLASS_UNROLL 1   // measured on B200: 1 -> 82.7 ms, 2 -> 85.3, 3 -> 87.9, 4 -> 87.1 (cfg5 / 5)
 #endif
 constexpr int kClassUnroll = B2_CLASS_UNROLL;   // Philox blocks in flight per lane in the class loop
 constexpr int kFastSmemBase = 1024 + kSmemHeader;
 constexpr int kFastStride2 = 8 << 13;   // bytes between the two arrays of a 2-array full tile
+
+__global__ void probe_dynamic_smem_base_kernel(uint32_t* out) {
+  extern __shared__ __align__(128) unsigned char probe_smem[];
+  if (threadIdx.x == 0) *out = smem_u32(probe_smem);
+}
 
 // ------------------------------------------------------------------ K0 --------
 // one thread per resample walks both levels (inspection API, small jobs)
