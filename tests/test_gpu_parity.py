@@ -694,6 +694,37 @@ def test_philox_path_agrees_statistically_with_pcg64_path():
     assert_allclose(boot.ci(x, np.mean, n_samples=n, seed=1), orc.ci(x, np.mean, n_samples=n, seed=2), rtol=1e-2)
 
 
+@pytest.mark.parametrize("stat_name", ["var", "std", "median", "ratio_of_means", "weighted_average", "pearson_r"])
+def test_every_registry_statistic_agrees_statistically_with_pcg64(stat_name):
+    """Two-sample KS of the device's bootstrap distribution against the oracle's PCG64 one,
+    per registry statistic (the mean is covered above)."""
+    from scipy import stats as sps
+    rng = np.random.default_rng(31)
+    n_obs, n = 150, 6000
+    a = rng.gamma(2.0, 1.0, n_obs)
+    b = 0.4 * a + rng.gamma(3.0, 1.0, n_obs)
+    paired = stat_name in ("ratio_of_means", "weighted_average", "pearson_r")
+    tdata = (a, b) if paired else (a,)
+    data = tdata if paired else a
+    _, d_gpu = boot.ci(data, DEVICE_STATS[stat_name], method="pi", n_samples=n, seed=7, return_dist=True)
+    d_ref = orc.stat_over_indices(tdata, STATS[stat_name], orc.bootstrap_indices_pcg64(n_obs, n, 8))
+    assert sps.ks_2samp(d_gpu, d_ref).pvalue > 1e-4
+    assert abs(d_gpu.mean() - d_ref.mean()) < 6 * d_ref.std() / np.sqrt(n / 2)
+
+
+def test_tiled_path_agrees_statistically_with_pcg64():
+    """Same for N spanning several cells and bank classes (tile-multinomial draws), mean and std."""
+    from scipy import stats as sps
+    x = np.random.default_rng(32).gamma(2.0, 1.0, 40000)
+    n = 3000
+    idx = orc.bootstrap_indices_pcg64(40000, n, 9)
+    ref = np.array([[x[i].mean(), x[i].std()] for i in idx])
+    for col, f in ((0, np.mean), (1, np.std)):
+        _, d_gpu = boot.ci(x, f, method="pi", n_samples=n, seed=10, return_dist=True)
+        assert sps.ks_2samp(d_gpu, ref[:, col]).pvalue > 1e-4
+        assert abs(d_gpu.std() / ref[:, col].std() - 1) < 0.08
+
+
 def test_coverage_of_the_tiled_path():
     """Nominal 90 % percentile intervals for the mean cover the truth ~90 % of the
     time when N spans several cells (tile-multinomial draws)."""
