@@ -725,6 +725,30 @@ def test_tiled_path_agrees_statistically_with_pcg64():
         assert abs(d_gpu.std() / ref[:, col].std() - 1) < 0.08
 
 
+def test_bca_coverage_matches_the_pcg64_path():
+    """Coverage of nominal 90 % BCa intervals for the mean of skewed data (N = 30): the device
+    (Philox) and the oracle (PCG64) must cover the truth equally often on the same data sets,
+    and their endpoints must agree to bootstrap noise."""
+    import warnings
+    rng = np.random.default_rng(44)
+    trials, n_obs, n = 250, 30, 1000
+    hit_gpu = hit_ref = 0
+    diffs = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for k in range(trials):
+            x = rng.exponential(1.0, n_obs)
+            lo, hi = boot.ci(x, np.mean, alpha=0.1, n_samples=n, seed=k)
+            rlo, rhi = orc.ci(x, np.mean, alpha=0.1, n_samples=n, seed=10_000 + k)
+            hit_gpu += lo <= 1.0 <= hi
+            hit_ref += rlo <= 1.0 <= rhi
+            diffs.append([(lo - rlo) / x.std(), (hi - rhi) / x.std()])
+    assert abs(hit_gpu - hit_ref) <= 12                       # same data: differences are rare
+    assert 0.78 <= hit_gpu / trials <= 0.95
+    d = np.array(diffs)
+    assert np.abs(d.mean(axis=0)).max() < 0.01 and d.std(axis=0).max() < 0.05
+
+
 def test_coverage_of_the_tiled_path():
     """Nominal 90 % percentile intervals for the mean cover the truth ~90 % of the
     time when N spans several cells (tile-multinomial draws)."""
