@@ -203,6 +203,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     N_ROWS, N_SAMPLES = args.n_rows, args.n_samples
+    args.warmup = max(args.warmup, 3)      # timing rule: at least 3 warm-up steps (reported as run)
 
     if args.impl == "reference":
         run_reference_arm(args)
