@@ -81,17 +81,23 @@ B2_HD double finish_stat(int stat, const double* m, double cnt) {
     case kStatMean: return m[0] / cnt;
     case kStatSum: return m[0];
     case kStatVar: case kStatStd: {
+      // rows are pre-centred on the data mean, so mu is small and the subtraction is
+      // benign; what is left below the rounding floor of the two terms (a resample of
+      // identical rows) is noise and is returned as the exact 0 numpy's two-pass gives
       const double mu = m[0] / cnt;
       double v = m[1] / cnt - mu * mu;
+      if (v <= 8.0 * 2.220446049250313e-16 * mu * mu) v = 0.0;
       if (stat == kStatVar) return v;
-      return sqrt(v < 0.0 ? 0.0 : v);
+      return sqrt(v);
     }
     case kStatRatio: return (m[0] / cnt) / (m[1] / cnt);
     case kStatWavg: return m[0] / m[1];
     case kStatPearson: {
-      const double saa = m[2] - m[0] * m[0] / cnt;
-      const double sbb = m[3] - m[1] * m[1] / cnt;
+      double saa = m[2] - m[0] * m[0] / cnt;
+      double sbb = m[3] - m[1] * m[1] / cnt;
       const double sab = m[4] - m[0] * m[1] / cnt;
+      if (saa <= 8.0 * 2.220446049250313e-16 * m[0] * m[0] / cnt) saa = 0.0;   // constant resample: r undefined
+      if (sbb <= 8.0 * 2.220446049250313e-16 * m[1] * m[1] / cnt) sbb = 0.0;
       return sab / sqrt(saa * sbb);
     }
     default: return NAN;

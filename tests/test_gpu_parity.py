@@ -292,6 +292,40 @@ def test_fused_odd_sizes_and_unaligned_views():
         assert_array_equal(got, want)
 
 
+def test_fuzz_shapes_against_oracle():
+    """Random sizes around every internal boundary (cell capacity, tile and class sizes, block
+    lengths, odd/even, one- and two-array plans): the fused kernels must reproduce the oracle on
+    the device's own index sets."""
+    import warnings
+    rng = np.random.default_rng(2024)
+    special = [1, 2, 3, 4, 5, 11, 12, 13, 31, 32, 33, 47, 48, 49, 191, 192, 193, 1023, 1024, 1025, 14335, 14336,
+               14337, 16383, 16384, 16385, 28671, 28672, 28673, 32767, 32768, 32769, 45055, 49152, 57343]
+    sizes = special + [int(v) for v in rng.integers(1, 60000, 25)]
+    names = ["mean", "var", "std", "ratio_of_means", "weighted_average", "pearson_r", "median"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for k, n in enumerate(sizes):
+            name = names[k % len(names)]
+            paired = name in ("ratio_of_means", "weighted_average", "pearson_r")
+            if name == "pearson_r" and n < 3:
+                name, paired = "mean", False
+            a = rng.gamma(2.0, 1.0, n) + 0.1
+            b = 0.3 * a + rng.gamma(3.0, 1.0, n) + 0.1
+            tdata = (a, b) if paired else (a,)
+            m = int(rng.integers(1, 40))
+            seed = int(rng.integers(0, 2**62))
+            idx = np.array(list(boot.bootstrap_indices(a, m, seed=seed, n_arrays=len(tdata)))).reshape(m, n)
+            assert idx.min() >= 0 and idx.max() < n
+            src = tuple(np.sort(t) for t in tdata) if (name == "median" and n > 28672) else tdata
+            want = np.sort(orc.stat_over_indices(src, STATS[name], idx))
+            _, dist = boot.ci(tdata if paired else a, DEVICE_STATS[name], n_samples=m, seed=seed, method="pi",
+                              return_dist=True, multi="paired" if paired else None)
+            if name == "median":
+                assert_array_equal(dist, want, err_msg=f"{name} n={n} m={m}")
+            else:
+                assert_allclose(dist, want, rtol=1e-11, atol=1e-13, err_msg=f"{name} n={n} m={m}")
+
+
 def test_cfg1_matches_oracle_end_to_end():
     """BASELINE cfg1: N=1000 f64, np.mean, BCa, n_samples=10000, seed=0."""
     x = np.random.default_rng(0).standard_normal(1000)
