@@ -326,6 +326,50 @@ def test_fuzz_shapes_against_oracle():
                 assert_allclose(dist, want, rtol=1e-11, atol=1e-13, err_msg=f"{name} n={n} m={m}")
 
 
+def test_fuzz_column_kernels_against_oracle():
+    """(N, D) data around the column-block widths (896 / 1792 / 3584 / 7168 rows), the median
+    batch limits (4095 / 8191 rows) and odd / even segment lengths: K1c, K3c, K1m, K3m and the
+    BCa tail against the oracle on the device's own index sets."""
+    import warnings
+    rng = np.random.default_rng(77)
+    shapes = [(2, 1), (3, 2), (31, 33), (32, 5), (33, 64), (63, 3), (64, 2), (65, 1), (895, 3), (896, 34), (897, 2),
+              (1792, 17), (1793, 2), (3584, 9), (3585, 2), (4094, 2), (4095, 3), (4096, 2), (7168, 5), (7169, 2),
+              (8191, 2), (8192, 2), (12000, 3)] + [(int(rng.integers(2, 9000)), int(rng.integers(1, 40))) for _ in range(8)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for k, (n, dcols) in enumerate(shapes):
+            data = np.round(rng.standard_normal((n, dcols)) * rng.uniform(0.5, 2, dcols) + rng.uniform(-2, 2, dcols),
+                            3 if k % 3 == 0 else 12)                       # some with ties
+            m = int(rng.integers(2, 30))
+            seed = int(rng.integers(0, 2**62))
+            idx = np.array(list(boot.bootstrap_indices(data, m, seed=seed))).reshape(m, n)
+            name = ["mean_axis0", "median_axis0", "std_axis0"][k % 3]
+            f = {"mean_axis0": boot.mean_axis0, "median_axis0": boot.median_axis0, "std_axis0": boot.std_axis0}[name]
+            g = {"mean_axis0": lambda t: np.mean(t, axis=0), "median_axis0": lambda t: np.median(t, axis=0),
+                 "std_axis0": lambda t: np.std(t, axis=0)}[name]
+            want = orc.stat_over_indices((data,), g, idx)
+            want.sort(axis=0)
+            _, dist = boot.ci(data, f, n_samples=m, seed=seed, method="pi", return_dist=True)
+            msg = f"{name} shape=({n},{dcols}) m={m}"
+            if name == "median_axis0":
+                assert_array_equal(dist, want, err_msg=msg)
+            else:
+                assert_allclose(dist, want, rtol=1e-11, atol=1e-13, err_msg=msg)
+            # jackknife pieces per column (K3c / K3m) against the closed forms
+            jk = {"mean_axis0": orc.jack_mean, "median_axis0": orc.jack_median,
+                  "std_axis0": lambda x: orc.jack_var(x, True)}[name]
+            spec = boot._registry.require(f)
+            jd = (_device.jackknife_median_columns(dev(data)) if name == "median_axis0"
+                  else _device.jackknife_columns(dev(data), spec.stat_id)).cpu().numpy()
+            for d in range(0, dcols, max(1, dcols // 3)):
+                j = jk(data[:, d])
+                assert_allclose(jd[d, 0], g(data)[d], rtol=1e-12, atol=1e-14, err_msg=msg)
+                assert_allclose(jd[d, 1], j.mean(), rtol=1e-11, atol=1e-13, err_msg=msg)
+                d2 = np.sum((j.mean() - j) ** 2)
+                if d2 > 1e-18:
+                    assert_allclose(jd[d, 2], d2, rtol=1e-6, err_msg=msg)
+
+
 def test_cfg1_matches_oracle_end_to_end():
     """BASELINE cfg1: N=1000 f64, np.mean, BCa, n_samples=10000, seed=0."""
     x = np.random.default_rng(0).standard_normal(1000)
