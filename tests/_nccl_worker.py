@@ -1,0 +1,55 @@
+"""Worker for tests/test_gpu_multi.py: one of `world` GPU ranks over NCCL.  Every case is
+run sharded over the ranks and again unsharded on this rank; the results must be identical."""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import scikits_bootstrap_b200 as boot  # noqa: E402
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    warnings.simplefilter("ignore")
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(50001) + 1.0
+    a, b = rng.gamma(2, 1, 20000), rng.gamma(3, 1, 20000)
+    table = rng.standard_normal((500, 37))
+    cases = [
+        lambda: boot.ci(x, np.mean, n_samples=1003, seed=3),
+        lambda: boot.ci(x, np.std, n_samples=1003, seed=3, alpha=(0.05, 0.5, 0.95), method="pi"),
+        lambda: boot.ci((a, b), boot.pearson_r, n_samples=777, seed=4),
+        lambda: boot.ci(table, boot.median_axis0, n_samples=501, seed=5),
+        lambda: boot.ci(table, boot.mean_axis0, n_samples=501, seed=5, output="errorbar"),
+        lambda: boot.ci(x, np.median, n_samples=333, seed=6),
+        lambda: boot.ci((a[:60], b[:45]), boot.diff_of_means, n_samples=999, seed=7, multi="independent"),
+        lambda: boot.pval(table, boot.mean_axis0, boot.greater_than(0.01), n_samples=501, seed=8),
+        lambda: boot.pval(x, np.mean, lambda s: s > 1.0, n_samples=501, seed=8),
+        lambda: boot.ci(x[:2000], np.mean, n_samples=801, seed=9, return_dist=True)[1],
+        lambda: boot.ci(x, np.mean, n_samples=64, seed=None),          # seed agreed through a broadcast
+    ]
+    boot.distributed.enable()
+    sharded = [np.asarray(c()) for c in cases[:-1]]
+    free = np.asarray(cases[-1]())
+    gathered = [None] * dist.get_world_size()
+    dist.all_gather_object(gathered, free.tolist())
+    assert all(g == gathered[0] for g in gathered), gathered
+    boot.distributed.disable()
+    for i, c in enumerate(cases[:-1]):
+        alone = np.asarray(c())
+        np.testing.assert_array_equal(sharded[i], alone, err_msg=f"case {i}")
+    dist.barrier()
+    dist.destroy_process_group()
+    print(f"rank {local} ok")
+
+
+if __name__ == "__main__":
+    main()
