@@ -27,13 +27,17 @@ X = [1, 2, 3, 4, 5, 6]
 Y = [2, 1, 2, 5, 1, 2]
 Z = [2, 1, 1, -1, -1, -4, -8]
 
+STATS = dict(STATS, sum=np.sum)
+
 DEVICE_STATS = {
+    "sum": np.sum,
     "mean": np.mean, "average": np.average, "var": np.var, "std": np.std, "median": np.median,
     "ratio_of_means": boot.ratio_of_means, "weighted_average": boot.weighted_average,
     "pearson_r": boot.pearson_r, "median_axis0": boot.median_axis0, "mean_axis0": boot.mean_axis0,
     "diff_of_means": boot.diff_of_means,
 }
 JACK = {
+    "sum": lambda x: np.sum(x) - np.asarray(x, dtype=float),
     "mean": orc.jack_mean, "average": orc.jack_mean, "var": orc.jack_var,
     "std": lambda x: orc.jack_var(x, True), "ratio_of_means": orc.jack_ratio_of_means,
     "weighted_average": orc.jack_weighted_average, "pearson_r": orc.jack_pearson,
@@ -183,7 +187,7 @@ def fused_vs_oracle(tdata, stat_name, n_samples, seed, multi=None, alphas=(0.025
         assert_allclose(out, ref, rtol=RTOL, atol=1e-15)
 
 
-@pytest.mark.parametrize("stat_name", ["mean", "var", "std"])
+@pytest.mark.parametrize("stat_name", ["mean", "var", "std", "sum"])
 @pytest.mark.parametrize("n", [20, 1000, 28672, 40000])
 def test_fused_single_array(stat_name, n):
     x = np.random.default_rng(n).standard_normal(n) + 0.5
