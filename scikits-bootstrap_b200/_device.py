@@ -229,11 +229,12 @@ def sorted_copy(x1d):
     return s.reshape(-1)
 
 
-def resample_median_sorted(sorted_vals, seed: int, lo: int, hi: int):
+def resample_median_sorted(sorted_vals, seed: int, lo: int, hi: int, out=None):
     """K1mt: median of sorted_vals[bootstrap indices] for resamples [lo, hi) -> float64[1][hi-lo]."""
     torch = _torch()
     n_rows = sorted_vals.numel()
-    out = torch.empty((1, hi - lo), dtype=torch.float64, device=sorted_vals.device)
+    if out is None:
+        out = torch.empty((1, hi - lo), dtype=torch.float64, device=sorted_vals.device)
     ws, wsz = workspace_for(_abi.STAT_MEDIAN, n_rows, 1, 1, hi - lo, 1)
     _abi.check(_abi.lib().b200boot_resample_median_sorted(sorted_vals.data_ptr(), n_rows, seed, lo, hi,
                                                           out.data_ptr(), ws, wsz, stream_ptr()))

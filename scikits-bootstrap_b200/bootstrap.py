@@ -152,21 +152,28 @@ class _Run:
     def _long_median(self) -> bool:
         """np.median over more rows than fit in shared memory: the resample is taken in
         rank space, i.e. it is sorted(x)[bootstrap_indices(...)] (same distribution as
-        x[bootstrap_indices(...)] for this permutation-invariant statistic)."""
+        x[bootstrap_indices(...)] for this permutation-invariant statistic).  With D > 1
+        columns each column is resampled in its own rank space with the same index sets:
+        every column's bootstrap distribution (all that ci and pval read) is exact, but
+        the rows of the returned distribution are not row-aligned across columns."""
         if self.spec.stat_id != _abi.STAT_MEDIAN or self.dev[0].shape[0] <= _device.MEDIAN_RESIDENT_ROWS:
             return False
-        if self.vector and self.n_cols > 1:
-            raise NotImplementedError(
-                "median over (N, D) data with D > 1 needs N <= {} rows (columns share one index set "
-                "in row space)".format(_device.MEDIAN_RESIDENT_ROWS))
         if self.indices is not None:
             raise NotImplementedError("index-supplied median needs N <= {} rows".format(
                 _device.MEDIAN_RESIDENT_ROWS))
         return True
 
     def _sorted(self):
+        """float64[D][N]: every column ascending."""
         if self._sorted_vals is None:
-            self._sorted_vals = _device.sorted_copy(self.dev[0].reshape(-1))
+            if self.vector:
+                s = self.dev[0].t().contiguous()
+                if s.data_ptr() == self.dev[0].data_ptr():
+                    s = s.clone()
+            else:
+                s = self.dev[0].reshape(1, -1).clone()
+            _device.sort_columns(s)
+            self._sorted_vals = s
         return self._sorted_vals
 
     # -- K1 ----------------------------------------------------------------------
@@ -177,7 +184,11 @@ class _Run:
             return self._resample_indexed()
         if spec.stat_id == _abi.STAT_MEDIAN:
             if self._long_median():
-                return _device.resample_median_sorted(self._sorted(), self.key, lo, hi)
+                cols = self._sorted()
+                out = torch.empty((self.n_cols, hi - lo), dtype=torch.float64, device=cols.device)
+                for d in range(self.n_cols):
+                    _device.resample_median_sorted(cols[d], self.key, lo, hi, out=out[d:d + 1])
+                return out
             data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
             return _device.resample_median_columns(data2d, self.key, lo, hi)
         if spec.independent:
@@ -229,7 +240,7 @@ class _Run:
         spec = self.spec
         if spec.stat_id == _abi.STAT_MEDIAN:
             if self._long_median():
-                j = _device.jackknife_median_sorted(self._sorted())
+                j = torch.cat([_device.jackknife_median_sorted(c) for c in self._sorted()])
             else:
                 data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
                 j = _device.jackknife_median_columns(data2d)

@@ -241,8 +241,28 @@ def test_long_median_runs_in_rank_space(n):
         got = boot.ci(x, np.median, n_samples=m, seed=n, method="bca")
         ref = orc.ci_from_indices((xs,), np.median, idx, (0.025, 0.975), m, "bca", jstat=orc.jack_median(xs))
     assert_array_equal(got, ref)
-    with pytest.raises(NotImplementedError):
-        boot.ci(np.stack([x, x], axis=1), boot.median_axis0, n_samples=10)
+
+
+def test_long_median_over_columns():
+    """(N, D) data with more rows than the resident limit: every column is resampled in its
+    own rank space with the same index sets, so column d equals the 1-D run on data[:, d]."""
+    import warnings
+    rng = np.random.default_rng(12)
+    data = rng.standard_normal((30001, 3))
+    data[:, 1] = np.round(data[:, 1], 2)
+    m = 300
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out, dist = boot.ci(data, boot.median_axis0, n_samples=m, seed=5, return_dist=True)
+        eb = boot.ci(dev(data), functools.partial(np.median, axis=0), n_samples=m, seed=5, output="errorbar")
+        p = boot.pval(data, boot.median_axis0, boot.greater_than(0.005), n_samples=m, seed=5)
+        assert out.shape == (2, 3) and dist.shape == (m, 3) and eb.shape == (3, 2)
+        for d in range(3):
+            o1, d1 = boot.ci(data[:, d], np.median, n_samples=m, seed=5, return_dist=True)
+            assert_array_equal(out[:, d], o1)
+            assert_array_equal(dist[:, d], d1)
+            assert_array_equal(eb[d], np.abs(np.median(data[:, d]) - o1))
+            assert p[d] == (d1 > 0.005).mean()
 
 
 def test_fused_median_columns_share_the_index_set():
