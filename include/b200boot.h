@@ -51,7 +51,12 @@ typedef enum b200boot_stat {
   B200BOOT_STAT_WEIGHTED_AVERAGE = 4, /* sum(x*w)/sum(w), 2 paired arrays (x, w)  */
   B200BOOT_STAT_PEARSON_R = 5,        /* corrcoef(a,b)[0,1], 2 paired arrays      */
   B200BOOT_STAT_MEDIAN = 6,           /* np.median, per column                    */
-  B200BOOT_STAT_SUM = 7               /* np.sum, 1 array                          */
+  B200BOOT_STAT_SUM = 7,              /* np.sum, 1 array                          */
+  B200BOOT_STAT_SLOPE = 8,            /* np.polyfit(a, b, 1)[0], 2 paired arrays  */
+  B200BOOT_STAT_INTERCEPT = 9,        /* np.polyfit(a, b, 1)[1], 2 paired arrays  */
+  B200BOOT_STAT_LINEAR_FIT = 10       /* np.polyfit(a, b, 1): TWO outputs per resample (the
+                                       * statistic of the reference's paired tests,
+                                       * test_bootstrap.py:211-238, 286-355)     */
 } b200boot_stat;
 
 /* Comparison operators for b200boot_count (bootstrap.py:583 uses LT; pval's
@@ -88,14 +93,15 @@ size_t b200boot_workspace_bytes(int stat_id, int64_t n_rows, int n_arrays, int64
  * `data` is a HOST array of n_arrays device pointers to contiguous float64[N].
  * Resample ids [resample_lo, resample_hi) are this caller's shard; the value of
  * resample r depends only on (seed, r), never on the shard boundaries.
- * stat_out: float64[resample_hi - resample_lo]. */
+ * stat_out: float64[resample_hi - resample_lo]; for a statistic with n_out outputs
+ * (B200BOOT_STAT_LINEAR_FIT: 2) float64[n_out][resample_hi - resample_lo]. */
 int b200boot_resample_stat(const double* const* data, int n_arrays, int64_t n_rows, int stat_id,
                            uint64_t seed, int64_t resample_lo, int64_t resample_hi,
                            double* stat_out, void* ws, size_t ws_bytes, void* stream);
 
 /* K1i — parity mode: the caller supplies the index arrays (e.g. the reference's
  * own PCG64 draws).  Replaces bootstrap.py:431 only.  indices: int64[n_sets][N]
- * row-major, values in [0, N).  stat_out: float64[n_sets]. */
+ * row-major, values in [0, N).  stat_out: float64[n_sets] ([n_out][n_sets]). */
 int b200boot_resample_stat_indexed(const double* const* data, int n_arrays, int64_t n_rows,
                                    int stat_id, const int64_t* indices, int64_t n_sets,
                                    double* stat_out, void* ws, size_t ws_bytes, void* stream);
@@ -176,7 +182,8 @@ int b200boot_gather(const double* data, int64_t n_rows, const int64_t* idx, int6
  * bootstrap.py:595-599 and the moments at bootstrap.py:609-615.
  * out (device) float64[8]: [0] statistic on the full data (bootstrap.py:580),
  * [1] mean of the jackknife statistics, [2] sum d^2, [3] sum d^3,
- * [4] acceleration a = [3] / (6 * [2]^1.5); d = jmean - jstat_i. */
+ * [4] acceleration a = [3] / (6 * [2]^1.5); d = jmean - jstat_i.
+ * A statistic with n_out outputs fills float64[n_out][8]. */
 int b200boot_jackknife(const double* const* data, int n_arrays, int64_t n_rows, int stat_id,
                        double* out, void* ws, size_t ws_bytes, void* stream);
 

@@ -374,6 +374,25 @@ def jack_pearson(a, b):
     return (sab - sa * sb / m) / np.sqrt((saa - sa * sa / m) * (sbb - sb * sb / m))
 
 
+def jack_linear_fit(a, b):
+    """Leave-one-out np.polyfit(a, b, 1) = [slope, intercept] from centred sums minus the
+    i-th terms -> float64[N][2]."""
+    a = np.asarray(a, dtype=float)
+    b = np.asarray(b, dtype=float)
+    n = len(a)
+    ma, mb = a.mean(), b.mean()
+    da = a - ma
+    db = b - mb
+    m = n - 1
+    sa = -da
+    sb = -db
+    saa = np.sum(da * da) - da * da
+    sab = np.sum(da * db) - da * db
+    slope = (sab - sa * sb / m) / (saa - sa * sa / m)
+    intercept = (mb + sb / m) - slope * (ma + sa / m)
+    return np.stack([slope, intercept], axis=1)
+
+
 def jack_median(x):
     """Leave-one-out medians take at most three distinct values, by rank of the
     deleted element in the sorted data."""

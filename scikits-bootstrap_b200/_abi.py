@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_PKG_DIR, "libb200boot.so")
 ABI_VERSION = 1
 
 STAT_MEAN, STAT_VAR, STAT_STD, STAT_RATIO_OF_MEANS, STAT_WEIGHTED_AVERAGE, STAT_PEARSON_R, \
-    STAT_MEDIAN, STAT_SUM = range(8)
+    STAT_MEDIAN, STAT_SUM, STAT_SLOPE, STAT_INTERCEPT, STAT_LINEAR_FIT = range(11)
+STAT_OUTPUTS = {STAT_LINEAR_FIT: 2}      # outputs per resample where not 1
 CMP_LT, CMP_LE, CMP_GT, CMP_GE, CMP_BETWEEN = range(5)
 
 

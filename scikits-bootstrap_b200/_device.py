@@ -136,13 +136,16 @@ def _ws_budget() -> int:
 
 
 def resample_stat(arrays: Sequence, stat_id: int, seed: int, lo: int, hi: int, out=None):
-    """K1 on contiguous float64[N] CUDA tensors -> float64[hi-lo] CUDA tensor."""
+    """K1 on contiguous float64[N] CUDA tensors -> float64[hi-lo] CUDA tensor
+    (float64[n_out][hi-lo] for a statistic with several outputs)."""
     torch = _torch()
     L = _abi.lib()
     n_rows = arrays[0].numel()
     n_local = hi - lo
+    n_out = _abi.STAT_OUTPUTS.get(stat_id, 1)
     if out is None:
-        out = torch.empty(n_local, dtype=torch.float64, device=arrays[0].device)
+        shape = n_local if n_out == 1 else (n_out, n_local)
+        out = torch.empty(shape, dtype=torch.float64, device=arrays[0].device)
     step = max(n_local, 1)
     budget = _ws_budget()
     while step > 32 and L.b200boot_workspace_bytes(stat_id, n_rows, len(arrays), 1, step, 1) > budget:
@@ -151,17 +154,22 @@ def resample_stat(arrays: Sequence, stat_id: int, seed: int, lo: int, hi: int, o
     for a in range(lo, hi, step):
         b = min(hi, a + step)
         ws, wsz = workspace_for(stat_id, n_rows, len(arrays), 1, b - a, 1)
+        whole = n_out == 1 or (a == lo and b == hi)
+        dst = out[a - lo:] if n_out == 1 else (out if whole else out.new_empty((n_out, b - a)))
         _abi.check(L.b200boot_resample_stat(ptrs, len(arrays), n_rows, stat_id, seed, a, b,
-                                            out[a - lo:].data_ptr(), ws, wsz, stream_ptr()))
+                                            dst.data_ptr(), ws, wsz, stream_ptr()))
+        if not whole:
+            out[:, a - lo:b - lo] = dst
     return out
 
 
 def resample_stat_indexed(arrays: Sequence, stat_id: int, indices):
-    """K1i: indices int64[n_sets][N] CUDA tensor -> float64[n_sets]."""
+    """K1i: indices int64[n_sets][N] CUDA tensor -> float64[n_sets] ([n_out][n_sets])."""
     torch = _torch()
     n_rows = arrays[0].numel()
     n_sets = indices.shape[0]
-    out = torch.empty(n_sets, dtype=torch.float64, device=arrays[0].device)
+    n_out = _abi.STAT_OUTPUTS.get(stat_id, 1)
+    out = torch.empty(n_sets if n_out == 1 else (n_out, n_sets), dtype=torch.float64, device=arrays[0].device)
     ws, wsz = workspace_for(stat_id, n_rows, len(arrays), 1, n_sets, 1)
     _abi.check(_abi.lib().b200boot_resample_stat_indexed(_ptr_array(arrays), len(arrays), n_rows, stat_id,
                                                          indices.data_ptr(), n_sets, out.data_ptr(), ws, wsz,
@@ -302,10 +310,12 @@ def gather(data, idx):
 
 
 def jackknife(arrays: Sequence, stat_id: int):
-    """K3 -> float64[8] CUDA tensor (ostat, jmean, d2, d3, accel, ...)."""
+    """K3 -> float64[8] CUDA tensor (ostat, jmean, d2, d3, accel, ...); [n_out][8] for a
+    statistic with several outputs."""
     torch = _torch()
     n_rows = arrays[0].numel()
-    out = torch.empty(8, dtype=torch.float64, device=arrays[0].device)
+    n_out = _abi.STAT_OUTPUTS.get(stat_id, 1)
+    out = torch.empty(8 if n_out == 1 else (n_out, 8), dtype=torch.float64, device=arrays[0].device)
     ws, wsz = workspace_for(stat_id, n_rows, len(arrays), 1, 0, 1)
     _abi.check(_abi.lib().b200boot_jackknife(_ptr_array(arrays), len(arrays), n_rows, stat_id, out.data_ptr(),
                                              ws, wsz, stream_ptr()))

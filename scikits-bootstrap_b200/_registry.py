@@ -27,6 +27,7 @@ class StatSpec:
     n_arrays: int
     axis0: bool = False          # column-wise over 2-D data (rows share the index set)
     independent: bool = False    # defined for multi='independent'
+    n_out: int = 1               # length of the statistic's value (1: scalar)
 
 
 class DeviceStat:
@@ -65,6 +66,14 @@ weighted_average = DeviceStat(StatSpec("weighted_average", _abi.STAT_WEIGHTED_AV
                               "sum(x*w) / sum(w) of paired (x, w)")
 pearson_r = DeviceStat(StatSpec("pearson_r", _abi.STAT_PEARSON_R, 2), _pearson,
                        "Pearson correlation of two paired arrays")
+linear_fit = DeviceStat(StatSpec("linear_fit", _abi.STAT_LINEAR_FIT, 2, n_out=2),
+                        lambda a, b: np.polyfit(a, b, 1),
+                        "np.polyfit(a, b, 1) = [slope, intercept] of the least-squares line through paired "
+                        "(a, b) (the statistic of the reference's paired tests)")
+fit_slope = DeviceStat(StatSpec("fit_slope", _abi.STAT_SLOPE, 2), lambda a, b: np.polyfit(a, b, 1)[0],
+                       "np.polyfit(a, b, 1)[0]")
+fit_intercept = DeviceStat(StatSpec("fit_intercept", _abi.STAT_INTERCEPT, 2),
+                           lambda a, b: np.polyfit(a, b, 1)[1], "np.polyfit(a, b, 1)[1]")
 mean_axis0 = DeviceStat(StatSpec("mean_axis0", _abi.STAT_MEAN, 1, axis0=True),
                         lambda a: np.mean(a, axis=0), "np.mean(a, axis=0) over (N, D) data")
 var_axis0 = DeviceStat(StatSpec("var_axis0", _abi.STAT_VAR, 1, axis0=True),
@@ -92,7 +101,7 @@ _AXIS0 = {
 
 REGISTRY_NAMES = ("np.mean, np.average, np.var, np.std, np.median, np.sum, "
                   "functools.partial(np.<mean|average|var|std|median>, axis=0), "
-                  "ratio_of_means, weighted_average, pearson_r, mean_axis0, var_axis0, std_axis0, "
+                  "ratio_of_means, weighted_average, pearson_r, linear_fit, fit_slope, fit_intercept, mean_axis0, var_axis0, std_axis0, "
                   "median_axis0, diff_of_means")
 
 

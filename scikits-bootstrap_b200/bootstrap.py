@@ -133,8 +133,9 @@ class _Run:
         self.spec, self.multi, self.n_samples, self.key = spec, multi, int(n_samples), key
         self.indices = indices       # parity mode: caller-supplied index sets (K1i)
         self.dev = [_device.to_device_f64(a) for a in arrays]
-        self.vector = spec.axis0 and self.dev[0].dim() == 2      # statistic has shape (D,)
-        self.n_cols = self.dev[0].shape[1] if self.vector else 1
+        # the statistic has shape (D,): one value per data column, or a multi-output statistic
+        self.vector = (spec.axis0 and self.dev[0].dim() == 2) or spec.n_out > 1
+        self.n_cols = spec.n_out if spec.n_out > 1 else (self.dev[0].shape[1] if self.vector else 1)
         self.rank, self.world = _dist.world()
         self.lo, self.hi = _dist.shard_range(self.n_samples, self.rank, self.world)
         self._columns = None
@@ -196,6 +197,8 @@ class _Run:
             means = [_device.resample_stat([a], _abi.STAT_MEAN, (self.key + k * _ARRAY_KEY_STRIDE) & _MASK64, lo, hi)
                      for k, a in enumerate(self.dev)]
             return (means[0] - means[1]).reshape(1, -1)
+        if spec.n_out > 1:
+            return _device.resample_stat([a.reshape(-1) for a in self.dev], spec.stat_id, self.key, lo, hi)
         if self.vector and _device.columns_block_width(spec.stat_id, self.dev[0].shape[0]) > 0:
             return _device.resample_stat_columns(self.dev[0], spec.stat_id, self.key, lo, hi)   # K1c
         if self.vector:
@@ -224,12 +227,12 @@ class _Run:
         if spec.stat_id == _abi.STAT_MEDIAN:
             data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
             return _device.resample_median_columns_indexed(data2d, idx)
-        if self.vector:
+        if self.vector and spec.n_out == 1:
             cols = self.columns()
             return torch.stack([_device.resample_stat_indexed([cols[d]], spec.stat_id, idx)
                                 for d in range(self.n_cols)])
         flat = [a.reshape(-1) for a in self.dev]
-        return _device.resample_stat_indexed(flat, spec.stat_id, idx).reshape(1, -1)
+        return _device.resample_stat_indexed(flat, spec.stat_id, idx).reshape(self.n_cols, -1)
 
     # -- K3 ----------------------------------------------------------------------
     def jackknife(self):
@@ -246,10 +249,10 @@ class _Run:
                 j = _device.jackknife_median_columns(data2d)
         elif spec.independent:
             j = self._jackknife_independent()
-        elif self.vector:
+        elif self.vector and spec.n_out == 1:
             j = _device.jackknife_columns(self.dev[0], spec.stat_id)                               # K3c
         else:
-            j = _device.jackknife([a.reshape(-1) for a in self.dev], spec.stat_id).reshape(1, 8)
+            j = _device.jackknife([a.reshape(-1) for a in self.dev], spec.stat_id).reshape(self.n_cols, 8)
         self._jack = _device.to_host(j)
         return self._jack
 

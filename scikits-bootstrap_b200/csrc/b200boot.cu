@@ -344,7 +344,8 @@ int b200boot_resample_stat(const double* const* data, int n_arrays, int64_t n_ro
   }
 
   k1_finish_kernel<<<blocks_for(n_local, 256, 1 << 30), 256, 0, s>>>(w.partial, plan.n_tiles, nm, n_local,
-                                                                     stat_id, (double)n_rows, stat_out);
+                                                                     stat_id, (double)n_rows, w.jack->center,
+                                                                     stat_out);
   B2_LAUNCH_CHECK();
   return 0;
 }
@@ -379,7 +380,7 @@ int b200boot_resample_stat_indexed(const double* const* data, int n_arrays, int6
   }
   if (rc) return rc;
   k1_finish_kernel<<<blocks_for(n_sets, 256, 1 << 30), 256, 0, s>>>(w.partial, 1, nm, n_sets, stat_id,
-                                                                    (double)n_rows, stat_out);
+                                                                    (double)n_rows, w.jack->center, stat_out);
   B2_LAUNCH_CHECK();
   return 0;
 }
@@ -491,7 +492,12 @@ int b200boot_jackknife(const double* const* data, int n_arrays, int64_t n_rows, 
     case kMomSum2: return jack_passes<kMomSum2>(rows, n_rows, stat_id, w, out, s);
     case kMomAB: return jack_passes<kMomAB>(rows, n_rows, stat_id, w, out, s);
     case kMomXW: return jack_passes<kMomXW>(rows, n_rows, stat_id, w, out, s);
-    default: return jack_passes<kMomPair5>(rows, n_rows, stat_id, w, out, s);
+    default:
+      for (int o = 0; o < stat_outputs(stat_id); ++o) {   // out[o][8]
+        rc = jack_passes<kMomPair5>(rows, n_rows, stat_component(stat_id, o), w, out + 8 * o, s);
+        if (rc) return rc;
+      }
+      return 0;
   }
 }
 

@@ -372,10 +372,12 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_resample_kernel(const K1Para
   }
 }
 
-// Sums the per-cell partials in cell order and finishes the statistic.
+// Sums the per-cell partials in cell order and finishes the statistic (out[o][n_local] for a
+// statistic with several outputs).
 __global__ void __launch_bounds__(256) k1_finish_kernel(const double* __restrict__ partial,
                                                         int64_t n_tiles, int nm, int64_t n_local,
                                                         int stat, double count,
+                                                        const double* __restrict__ center,
                                                         double* __restrict__ out) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_local) return;
@@ -385,7 +387,9 @@ __global__ void __launch_bounds__(256) k1_finish_kernel(const double* __restrict
     for (int64_t t = 0; t < n_tiles; ++t) acc += partial[(t * nm + k) * n_local + r];
     m[k] = acc;
   }
-  out[r] = finish_stat(stat, m, count);
+  const int n_out = stat_outputs(stat);
+  for (int o = 0; o < n_out; ++o)
+    out[(int64_t)o * n_local + r] = finish_stat(stat_component(stat, o), m, count, center);
 }
 
 // ------------------------------------------------------------------ K1i -------

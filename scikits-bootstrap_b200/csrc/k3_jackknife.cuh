@@ -130,7 +130,7 @@ struct StoreTotalsG {
   const double* d1;
   __device__ void operator()(const double* tot) const {
     for (int k = 0; k < MomTraits<MS>::kMoments; ++k) st->tot[k] = tot[k];
-    st->ostat = finish_stat(stat, tot, n);
+    st->ostat = finish_stat(stat, tot, n, st->center);
     // leave-one-out value of row 0: the jackknife mean is accumulated relative to it,
     // so identical leave-one-out values give d == 0 exactly (acceleration undefined,
     // as the reference intends: bootstrap.py:616-625) instead of rounding noise
@@ -139,7 +139,7 @@ struct StoreTotalsG {
     v[1] = (MomTraits<MS>::kArrays == 2) ? d1[0] : 0.0;
     contribution<MS>(v, c);
     for (int k = 0; k < MomTraits<MS>::kMoments; ++k) m[k] = tot[k] - c[k];
-    st->j0 = finish_stat(stat, m, n - 1.0);
+    st->j0 = finish_stat(stat, m, n - 1.0, st->center);
   }
 };
 
@@ -152,7 +152,7 @@ __device__ __forceinline__ double leave_one_out(const JackState* st, int stat, d
   contribution<MS>(v, c);
 #pragma unroll
   for (int k = 0; k < MomTraits<MS>::kMoments; ++k) m[k] = st->tot[k] - c[k];
-  return finish_stat(stat, m, n - 1.0);
+  return finish_stat(stat, m, n - 1.0, st->center);
 }
 
 template <int MS>

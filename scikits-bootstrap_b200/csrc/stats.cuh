@@ -55,7 +55,10 @@ B2_HD void contribution(const double* v, double* c) {
 // stat ids mirror b200boot_stat in include/b200boot.h
 enum StatId : int {
   kStatMean = 0, kStatVar = 1, kStatStd = 2, kStatRatio = 3, kStatWavg = 4,
-  kStatPearson = 5, kStatMedian = 6, kStatSum = 7
+  kStatPearson = 5, kStatMedian = 6, kStatSum = 7,
+  kStatSlope = 8,       // least-squares line b ~ slope * a + intercept through paired (a, b):
+  kStatIntercept = 9,   //   np.polyfit(a, b, 1) = [slope, intercept]
+  kStatLinFit = 10      // both, as a statistic with two outputs
 };
 
 inline int moment_set_of(int stat) {
@@ -64,19 +67,23 @@ inline int moment_set_of(int stat) {
     case kStatVar: case kStatStd: return kMomSum2;
     case kStatRatio: return kMomAB;
     case kStatWavg: return kMomXW;
-    case kStatPearson: return kMomPair5;
+    case kStatPearson: case kStatSlope: case kStatIntercept: case kStatLinFit: return kMomPair5;
     default: return -1;
   }
 }
 inline bool stat_needs_centering(int stat) {
-  return stat == kStatVar || stat == kStatStd || stat == kStatPearson;
+  return stat == kStatVar || stat == kStatStd || moment_set_of(stat) == kMomPair5;
 }
 inline int stat_arrays(int stat) {
-  return (stat == kStatRatio || stat == kStatWavg || stat == kStatPearson) ? 2 : 1;
+  return (stat == kStatRatio || stat == kStatWavg || moment_set_of(stat) == kMomPair5) ? 2 : 1;
 }
+// outputs per resample, and the scalar statistic behind output o
+B2_HD int stat_outputs(int stat) { return stat == kStatLinFit ? 2 : 1; }
+B2_HD int stat_component(int stat, int o) { return stat == kStatLinFit ? kStatSlope + o : stat; }
 
-// statistic from summed contributions m[] over `cnt` rows
-B2_HD double finish_stat(int stat, const double* m, double cnt) {
+// statistic from summed contributions m[] over `cnt` rows; `center` = the per-array means the
+// rows were pre-centred on (only the intercept needs them back)
+B2_HD double finish_stat(int stat, const double* m, double cnt, const double* center = nullptr) {
   switch (stat) {
     case kStatMean: return m[0] / cnt;
     case kStatSum: return m[0];
@@ -99,6 +106,15 @@ B2_HD double finish_stat(int stat, const double* m, double cnt) {
       if (saa <= 8.0 * 2.220446049250313e-16 * m[0] * m[0] / cnt) saa = 0.0;   // constant resample: r undefined
       if (sbb <= 8.0 * 2.220446049250313e-16 * m[1] * m[1] / cnt) sbb = 0.0;
       return sab / sqrt(saa * sbb);
+    }
+    case kStatSlope: case kStatIntercept: {
+      double saa = m[2] - m[0] * m[0] / cnt;
+      const double sab = m[4] - m[0] * m[1] / cnt;
+      if (saa <= 8.0 * 2.220446049250313e-16 * m[0] * m[0] / cnt) saa = 0.0;   // constant abscissa: no line
+      const double slope = sab / saa;
+      if (stat == kStatSlope) return slope;
+      const double ca = center ? center[0] : 0.0, cb = center ? center[1] : 0.0;
+      return (cb + m[1] / cnt) - slope * (ca + m[0] / cnt);
     }
     default: return NAN;
   }

@@ -27,20 +27,20 @@ X = [1, 2, 3, 4, 5, 6]
 Y = [2, 1, 2, 5, 1, 2]
 Z = [2, 1, 1, -1, -1, -4, -8]
 
-STATS = dict(STATS, sum=np.sum)
+STATS = dict(STATS, sum=np.sum, linear_fit=lambda a, b: np.polyfit(a, b, 1))
 
 DEVICE_STATS = {
     "sum": np.sum,
     "mean": np.mean, "average": np.average, "var": np.var, "std": np.std, "median": np.median,
     "ratio_of_means": boot.ratio_of_means, "weighted_average": boot.weighted_average,
-    "pearson_r": boot.pearson_r, "median_axis0": boot.median_axis0, "mean_axis0": boot.mean_axis0,
+    "pearson_r": boot.pearson_r, "linear_fit": boot.linear_fit, "median_axis0": boot.median_axis0, "mean_axis0": boot.mean_axis0,
     "diff_of_means": boot.diff_of_means,
 }
 JACK = {
     "sum": lambda x: np.sum(x) - np.asarray(x, dtype=float),
     "mean": orc.jack_mean, "average": orc.jack_mean, "var": orc.jack_var,
     "std": lambda x: orc.jack_var(x, True), "ratio_of_means": orc.jack_ratio_of_means,
-    "weighted_average": orc.jack_weighted_average, "pearson_r": orc.jack_pearson,
+    "weighted_average": orc.jack_weighted_average, "pearson_r": orc.jack_pearson, "linear_fit": orc.jack_linear_fit,
     "median": orc.jack_median,
 }
 
@@ -171,7 +171,7 @@ def test_tile_counts_multinomial_on_device():
 
 # ------------------------------------------------------------------ leg (ii) -----
 
-def fused_vs_oracle(tdata, stat_name, n_samples, seed, multi=None, alphas=(0.025, 0.975)):
+def fused_vs_oracle(tdata, stat_name, n_samples, seed, multi=None, alphas=(0.025, 0.975), RTOL=RTOL):
     f = DEVICE_STATS[stat_name]
     data = tdata if multi else tdata[0]
     idx = np.array(list(boot.bootstrap_indices(tdata[0], n_samples, seed=seed, n_arrays=len(tdata))))
@@ -201,6 +201,32 @@ def test_fused_paired(stat_name, n):
     a = rng.gamma(2, 1, n)
     b = 0.5 * a + rng.gamma(3, 1, n)
     fused_vs_oracle((a, b), stat_name, 400, seed=n + 2, multi="paired")
+
+
+@pytest.mark.parametrize("n", [10, 50, 3000, 14336, 30000])
+def test_fused_linear_fit(n):
+    """np.polyfit(a, b, 1): a statistic with two outputs per resample (slope, intercept) from one
+    pass over the five centred moment sums; numpy solves the same least squares by SVD, hence
+    the looser tolerance."""
+    rng = np.random.default_rng(n)
+    a = rng.gamma(2, 1, n) + 10.0
+    b = 0.5 * a + rng.gamma(3, 1, n)
+    fused_vs_oracle((a, b), "linear_fit", 300, seed=n + 3, multi="paired", RTOL=1e-9)
+    m = 300
+    both, dist = boot.ci((a, b), boot.linear_fit, n_samples=m, seed=n, return_dist=True)
+    assert both.shape == (2, 2) and dist.shape == (m, 2)
+    assert_array_equal(both[:, 0], boot.ci((a, b), boot.fit_slope, n_samples=m, seed=n))
+    assert_array_equal(both[:, 1], boot.ci((a, b), boot.fit_intercept, n_samples=m, seed=n))
+    p = boot.pval((a, b), boot.linear_fit, boot.greater_than(0.5), n_samples=m, seed=n)
+    assert_array_equal(p, (dist > 0.5).mean(axis=0))
+    # chunked by a small workspace budget: same values
+    import os
+    os.environ["B200BOOT_WS_BYTES"] = str(1 << 20)
+    try:
+        again = boot.ci((a, b), boot.linear_fit, n_samples=m, seed=n, return_dist=True)[1]
+    finally:
+        del os.environ["B200BOOT_WS_BYTES"]
+    assert_array_equal(again, dist)
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 20, 301, 1000, 1024, 1025, 5000, 28672])

@@ -5,8 +5,9 @@ Substitutions, each noted where it happens:
   * fixed-seed goldens pin numpy's PCG64 stream; they are checked in index-supplied mode
     (the GPU consumes the reference's own index arrays), or as properties of the device
     stream when the golden is an index array itself;
-  * statistics given as lambdas / np.polyfit are replaced by registry statistics with the
-    same structure (the device path has no host fallback for arbitrary callables).
+  * statistics given as lambdas are replaced by registry statistics with the same structure
+    (the device path has no host fallback for arbitrary callables); np.polyfit(a, b, 1) is
+    the registry's linear_fit.
 """
 import numpy as np
 import pytest
@@ -138,7 +139,23 @@ class TestCI:
         results = boot.ci_indexed(self.data, None, self.ref_indices(20, 10000), alpha=(0.1, 0.2, 0.8, 0.9))
         assert_allclose(results, np.array([0.386674, 0.506714, 0.935628, 1.039683]), rtol=1e-6)
 
-    def test_bca_multi_multialpha(self):                      # test:211-238 (polyfit -> paired registry stats)
+    def test_bca_multi_multialpha(self):                      # test:211-238 (polyfit = linear_fit)
+        kw = dict(alpha=(0.1, 0.2, 0.8, 0.9), n_samples=1000, seed=self.seed)
+        results1 = boot.ci((self.x, self.y), boot.linear_fit, **kw)
+        results2 = boot.ci((self.x, self.y), boot.linear_fit, multi="paired", **kw)
+        results3 = boot.ci((self.x, self.y), boot.linear_fit, output="errorbar", **kw)
+        assert results1.shape == (4, 2) and results3.shape == (2, 4)
+        assert_allclose(results1, results2)
+        assert_allclose(np.abs(np.polyfit(self.x, self.y, 1) - results1), results3.T)
+        # the same statistic on the reference's own index draws, against the reference algorithm.
+        # Percentile ranks only: on this 6-point integer data 19 of the 1000 resamples reproduce
+        # the data's own fit, so BCa's count of `stat < ostat` (bootstrap.py:583) is decided by
+        # rounding noise in the reference itself (SVD vs moment sums differ in the last bit).
+        idx = self.ref_indices(6, 1000)
+        got = boot.ci_indexed((self.x, self.y), boot.linear_fit, idx, alpha=(0.1, 0.2, 0.8, 0.9), method="pi")
+        want = orc.ci_from_indices((np.array(self.x, float), np.array(self.y, float)),
+                                   lambda a, b: np.polyfit(a, b, 1), idx, (0.1, 0.2, 0.8, 0.9), 1000, "pi")
+        assert_allclose(got, want, rtol=1e-9, atol=1e-12)
         for statfun in (boot.pearson_r, boot.ratio_of_means):
             kw = dict(alpha=(0.1, 0.2, 0.8, 0.9), n_samples=1000, seed=self.seed)
             results1 = boot.ci((self.x, self.y), statfun, **kw)
@@ -204,6 +221,10 @@ class TestCI:
         self._vector_stat_columns("pi")
 
     def _vector_stat_columns(self, method):
+        kw = dict(alpha=(0.1, 0.2, 0.8, 0.9), n_samples=2000, method=method, seed=self.seed)
+        both = boot.ci((self.x, self.y), boot.linear_fit, **kw)
+        assert_allclose(both[:, 0], boot.ci((self.x, self.y), boot.fit_slope, **kw))
+        assert_allclose(both[:, 1], boot.ci((self.x, self.y), boot.fit_intercept, **kw))
         table = np.vstack((self.x, self.y)).T.astype(float)
         results1 = boot.ci(table, boot.mean_axis0, alpha=(0.1, 0.2, 0.8, 0.9), n_samples=2000, method=method,
                            seed=self.seed)
