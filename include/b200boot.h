@@ -121,18 +121,35 @@ int b200boot_resample_stat_columns(const double* data, int64_t n_rows, int64_t n
 int b200boot_jackknife_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, int stat_id,
                                double* out, void* stream);
 
+/* Which order statistics make a rank statistic.  np.median is the mean of the two middle
+ * order statistics; np.quantile / np.percentile (method 'linear') interpolate between
+ * ranks floor(h) and floor(h) + 1, h = (N - 1) q, with numpy's _lerp.  The caller fixes
+ * ranks and weight (it knows numpy's rounding of h) for a sample of N rows and for a
+ * leave-one-out sample of N - 1 rows (used by the jackknife entry points only).
+ * Every median entry point takes `rule`; NULL means np.median. */
+typedef struct b200boot_rank_rule {
+  int64_t k_lo, k_hi;          /* 0-based ranks, k_lo <= k_hi <= k_lo + 1, k_hi < N            */
+  double gamma;                /* weight of the upper rank (mode 1)                           */
+  int64_t loo_k_lo, loo_k_hi;  /* the same for N - 1 rows                                     */
+  double loo_gamma;
+  int32_t mode;                /* 0: (lo + hi) / 2 as np.median; 1: numpy 'linear' interpolation */
+  int32_t reserved;
+} b200boot_rank_rule;
+
 /* K1m — column-batched order statistic: data float64[N][n_cols] row-major
  * (ld = row stride in elements); every column shares one index set per
  * resample, as x[indices] does for 2-D data at bootstrap.py:431.
  * stat_out: float64[n_cols][n_local] (column-major as everywhere). */
 int b200boot_resample_median_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld,
                                      uint64_t seed, int64_t resample_lo, int64_t resample_hi,
-                                     double* stat_out, void* ws, size_t ws_bytes, void* stream);
+                                     double* stat_out, void* ws, size_t ws_bytes, void* stream,
+                                     const b200boot_rank_rule* rule);
 
 /* K1m in parity mode: index sets supplied by the caller, int64[n_sets][N]. */
 int b200boot_resample_median_columns_indexed(const double* data, int64_t n_rows, int64_t n_cols,
                                              int64_t ld, const int64_t* indices, int64_t n_sets,
-                                             double* stat_out, void* ws, size_t ws_bytes, void* stream);
+                                             double* stat_out, void* ws, size_t ws_bytes, void* stream,
+                                             const b200boot_rank_rule* rule);
 
 /* K1mt — median of a long 1-D array in rank space (n_rows beyond the 28 672-row
  * resident limit of K1m).  `sorted_vals` is the data sorted ascending (e.g. by
@@ -142,9 +159,10 @@ int b200boot_resample_median_columns_indexed(const double* data, int64_t n_rows,
  * stat_out: float64[resample_hi - resample_lo]. */
 int b200boot_resample_median_sorted(const double* sorted_vals, int64_t n_rows, uint64_t seed,
                                     int64_t resample_lo, int64_t resample_hi, double* stat_out, void* ws,
-                                    size_t ws_bytes, void* stream);
+                                    size_t ws_bytes, void* stream, const b200boot_rank_rule* rule);
 /* K3m on a sorted 1-D array of any length: out float64[8] as b200boot_jackknife. */
-int b200boot_jackknife_median_sorted(const double* sorted_vals, int64_t n_rows, double* out, void* stream);
+int b200boot_jackknife_median_sorted(const double* sorted_vals, int64_t n_rows, double* out, void* stream,
+                                     const b200boot_rank_rule* rule);
 
 /* K2 — materialises exactly the indices K1 draws; backs the Python
  * `bootstrap_indices` iterator (bootstrap.py:667-680).
@@ -189,7 +207,8 @@ int b200boot_jackknife(const double* const* data, int n_arrays, int64_t n_rows, 
 
 /* Column-batched K3 for the median: out float64[n_cols][8]. */
 int b200boot_jackknife_median_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld,
-                                      double* out, void* ws, size_t ws_bytes, void* stream);
+                                      double* out, void* ws, size_t ws_bytes, void* stream,
+                                      const b200boot_rank_rule* rule);
 
 /* K4 — count reduction per column: counts[d] = #{ r : stat[d][r] cmp t0[d] (,t1[d]) }.
  * Replaces np.sum(stat < ostat, axis=0) at bootstrap.py:583 and the pval mean

@@ -374,6 +374,31 @@ def jack_pearson(a, b):
     return (sab - sa * sb / m) / np.sqrt((saa - sa * sa / m) * (sbb - sb * sb / m))
 
 
+def jack_quantile(x, q):
+    """Leave-one-out np.quantile(., q) (method 'linear'): like the median, the value depends
+    only on whether the deleted element's rank is below, between or above the two order
+    statistics the quantile of an (N-1)-sample reads."""
+    x = np.asarray(x, dtype=float)
+    n = len(x)
+    order = np.argsort(x, kind="stable")
+    s = x[order]
+    rank = np.empty(n, dtype=np.int64)
+    rank[order] = np.arange(n)
+    m = n - 1
+    vi = (m - 1) * np.float64(q)                  # numpy: _QuantileMethods['linear']
+    if vi >= m - 1:
+        k_lo = k_hi = m - 1
+        gamma = np.float64(0.0)
+    else:
+        k_lo = int(np.floor(vi))
+        k_hi = k_lo + 1
+        gamma = vi - k_lo
+    kth = lambda k: s[np.where(k < rank, k, k + 1)]          # k-th order statistic without `rank`
+    a, b = kth(k_lo), kth(k_hi)
+    diff = b - a                                             # numpy: _lerp
+    return np.where(gamma >= 0.5, b - diff * (1 - gamma), a + diff * gamma)
+
+
 def jack_linear_fit(a, b):
     """Leave-one-out np.polyfit(a, b, 1) = [slope, intercept] from centred sums minus the
     i-th terms -> float64[N][2]."""

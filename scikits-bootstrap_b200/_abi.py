@@ -24,6 +24,13 @@ class Plan(C.Structure):
                 ("rem", C.c_int64), ("n_tiles", C.c_int64)]
 
 
+class RankRule(C.Structure):
+    """include/b200boot.h: b200boot_rank_rule."""
+    _fields_ = [("k_lo", C.c_int64), ("k_hi", C.c_int64), ("gamma", C.c_double),
+                ("loo_k_lo", C.c_int64), ("loo_k_hi", C.c_int64), ("loo_gamma", C.c_double),
+                ("mode", C.c_int32), ("reserved", C.c_int32)]
+
+
 class B200BootError(RuntimeError):
     """A libb200boot call returned a non-zero status."""
 
@@ -41,17 +48,17 @@ SIGNATURES = {
     "b200boot_columns_block_width": (_int, [_int, _i64]),
     "b200boot_resample_stat_columns": (_int, [_vp, _i64, _i64, _i64, _int, _u64, _i64, _i64, _vp, _vp, _sz, _vp]),
     "b200boot_jackknife_columns": (_int, [_vp, _i64, _i64, _i64, _int, _vp, _vp]),
-    "b200boot_resample_median_columns": (_int, [_vp, _i64, _i64, _i64, _u64, _i64, _i64, _vp, _vp, _sz, _vp]),
-    "b200boot_resample_median_columns_indexed": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
-    "b200boot_resample_median_sorted": (_int, [_vp, _i64, _u64, _i64, _i64, _vp, _vp, _sz, _vp]),
-    "b200boot_jackknife_median_sorted": (_int, [_vp, _i64, _vp, _vp]),
+    "b200boot_resample_median_columns": (_int, [_vp, _i64, _i64, _i64, _u64, _i64, _i64, _vp, _vp, _sz, _vp, _vp]),
+    "b200boot_resample_median_columns_indexed": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _sz, _vp, _vp]),
+    "b200boot_resample_median_sorted": (_int, [_vp, _i64, _u64, _i64, _i64, _vp, _vp, _sz, _vp, _vp]),
+    "b200boot_jackknife_median_sorted": (_int, [_vp, _i64, _vp, _vp, _vp]),
     "b200boot_fill_indices": (_int, [_u64, _i64, _int, _i64, _i64, _vp, _vp, _sz, _vp]),
     "b200boot_fill_moving_block": (_int, [_u64, _i64, _i64, _int, _i64, _i64, _vp, _vp]),
     "b200boot_fill_subsample": (_int, [_u64, _i64, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
     "b200boot_tile_counts": (_int, [_u64, _i64, _int, _i64, _i64, _vp, _vp, _vp]),
     "b200boot_gather": (_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "b200boot_jackknife": (_int, [_vp, _int, _i64, _int, _vp, _vp, _sz, _vp]),
-    "b200boot_jackknife_median_columns": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "b200boot_jackknife_median_columns": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp, _vp]),
     "b200boot_count": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _vp]),
     "b200boot_select": (_int, [_vp, _i64, _i64, _vp, _int, _vp, _vp, _sz, _vp]),
     "b200boot_select_begin": (_int, [_vp, _int, _i64, _vp, _sz, _vp]),

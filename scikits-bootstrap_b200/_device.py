@@ -203,18 +203,49 @@ def jackknife_columns(data2d, stat_id: int):
     return out
 
 
-def resample_median_columns(data2d, seed: int, lo: int, hi: int):
+def rank_rule(n_rows: int, q):
+    """The order statistics behind np.quantile(x, q) (method 'linear') for samples of n_rows
+    and n_rows - 1 rows, with numpy's own rounding of the virtual index (n - 1) * q
+    (numpy/lib/_function_base_impl.py: _QuantileMethods['linear'], _get_indexes, _get_gamma).
+    None (np.median) -> NULL."""
+    if q is None:
+        return None
+    import ctypes as C
+    import numpy as np
+    r = _abi.RankRule()
+    r.mode = 1
+    for n, pre in ((n_rows, ""), (max(n_rows - 1, 1), "loo_")):
+        vi = (n - 1) * np.float64(q)
+        lo = int(np.floor(vi))
+        if vi >= n - 1:                      # at or above the last rank: the maximum itself
+            k_lo = k_hi = n - 1
+            gamma = 0.0
+        else:
+            k_lo, k_hi, gamma = lo, lo + 1, float(vi - lo)
+        setattr(r, pre + "k_lo", k_lo)
+        setattr(r, pre + "k_hi", k_hi)
+        setattr(r, pre + "gamma", gamma)
+    return r
+
+
+def _rule_ptr(rule):
+    import ctypes as C
+    return None if rule is None else C.cast(C.pointer(rule), C.c_void_p)
+
+
+def resample_median_columns(data2d, seed: int, lo: int, hi: int, rule=None):
     """K1m: data float64[N][D] -> float64[D][hi-lo]."""
     torch = _torch()
     n_rows, n_cols = data2d.shape
     out = torch.empty((n_cols, hi - lo), dtype=torch.float64, device=data2d.device)
     ws, wsz = workspace_for(_abi.STAT_MEDIAN, n_rows, 1, n_cols, hi - lo, 1)
     _abi.check(_abi.lib().b200boot_resample_median_columns(data2d.data_ptr(), n_rows, n_cols, data2d.stride(0),
-                                                           seed, lo, hi, out.data_ptr(), ws, wsz, stream_ptr()))
+                                                           seed, lo, hi, out.data_ptr(), ws, wsz, stream_ptr(),
+                                                           _rule_ptr(rule)))
     return out
 
 
-def resample_median_columns_indexed(data2d, indices):
+def resample_median_columns_indexed(data2d, indices, rule=None):
     """K1m parity mode: indices int64[n_sets][N] -> float64[D][n_sets]."""
     torch = _torch()
     n_rows, n_cols = data2d.shape
@@ -223,7 +254,7 @@ def resample_median_columns_indexed(data2d, indices):
     ws, wsz = workspace_for(_abi.STAT_MEDIAN, n_rows, 1, n_cols, n_sets, 1)
     _abi.check(_abi.lib().b200boot_resample_median_columns_indexed(
         data2d.data_ptr(), n_rows, n_cols, data2d.stride(0), indices.data_ptr(), n_sets, out.data_ptr(),
-        ws, wsz, stream_ptr()))
+        ws, wsz, stream_ptr(), _rule_ptr(rule)))
     return out
 
 
@@ -237,7 +268,7 @@ def sorted_copy(x1d):
     return s.reshape(-1)
 
 
-def resample_median_sorted(sorted_vals, seed: int, lo: int, hi: int, out=None):
+def resample_median_sorted(sorted_vals, seed: int, lo: int, hi: int, out=None, rule=None):
     """K1mt: median of sorted_vals[bootstrap indices] for resamples [lo, hi) -> float64[1][hi-lo]."""
     torch = _torch()
     n_rows = sorted_vals.numel()
@@ -245,15 +276,16 @@ def resample_median_sorted(sorted_vals, seed: int, lo: int, hi: int, out=None):
         out = torch.empty((1, hi - lo), dtype=torch.float64, device=sorted_vals.device)
     ws, wsz = workspace_for(_abi.STAT_MEDIAN, n_rows, 1, 1, hi - lo, 1)
     _abi.check(_abi.lib().b200boot_resample_median_sorted(sorted_vals.data_ptr(), n_rows, seed, lo, hi,
-                                                          out.data_ptr(), ws, wsz, stream_ptr()))
+                                                          out.data_ptr(), ws, wsz, stream_ptr(),
+                                                          _rule_ptr(rule)))
     return out
 
 
-def jackknife_median_sorted(sorted_vals):
+def jackknife_median_sorted(sorted_vals, rule=None):
     torch = _torch()
     out = torch.empty((1, 8), dtype=torch.float64, device=sorted_vals.device)
     _abi.check(_abi.lib().b200boot_jackknife_median_sorted(sorted_vals.data_ptr(), sorted_vals.numel(),
-                                                           out.data_ptr(), stream_ptr()))
+                                                           out.data_ptr(), stream_ptr(), _rule_ptr(rule)))
     return out
 
 
@@ -322,13 +354,14 @@ def jackknife(arrays: Sequence, stat_id: int):
     return out
 
 
-def jackknife_median_columns(data2d):
+def jackknife_median_columns(data2d, rule=None):
     torch = _torch()
     n_rows, n_cols = data2d.shape
     out = torch.empty((n_cols, 8), dtype=torch.float64, device=data2d.device)
     ws, wsz = workspace_for(_abi.STAT_MEDIAN, n_rows, 1, n_cols, 0, 1)
     _abi.check(_abi.lib().b200boot_jackknife_median_columns(data2d.data_ptr(), n_rows, n_cols, data2d.stride(0),
-                                                            out.data_ptr(), ws, wsz, stream_ptr()))
+                                                            out.data_ptr(), ws, wsz, stream_ptr(),
+                                                            _rule_ptr(rule)))
     return out
 
 

@@ -28,6 +28,7 @@ class StatSpec:
     axis0: bool = False          # column-wise over 2-D data (rows share the index set)
     independent: bool = False    # defined for multi='independent'
     n_out: int = 1               # length of the statistic's value (1: scalar)
+    q: Optional[float] = None    # rank statistics: None = np.median, else np.quantile(x, q)
 
 
 class DeviceStat:
@@ -86,6 +87,55 @@ diff_of_means = DeviceStat(StatSpec("diff_of_means", _abi.STAT_MEAN, 2, independ
                            lambda a, b: np.mean(a) - np.mean(b),
                            "mean(a) - mean(b); for multi='independent'")
 
+def _quantile_spec(q, axis0: bool) -> StatSpec:
+    q = float(q)
+    if not 0.0 <= q <= 1.0:
+        raise ValueError("Quantiles must be in the range [0, 1]")          # numpy's message
+    return StatSpec("quantile_axis0" if axis0 else "quantile", _abi.STAT_MEDIAN, 1, axis0=axis0, q=q)
+
+
+def quantile(q) -> DeviceStat:
+    """np.quantile(x, q) (default method 'linear') of a 1-D array, as a device statistic."""
+    spec = _quantile_spec(q, False)
+    return DeviceStat(spec, lambda a: np.quantile(a, spec.q), f"np.quantile(x, {spec.q})")
+
+
+def quantile_axis0(q) -> DeviceStat:
+    """np.quantile(a, q, axis=0) over (N, D) data."""
+    spec = _quantile_spec(q, True)
+    return DeviceStat(spec, lambda a: np.quantile(a, spec.q, axis=0), f"np.quantile(a, {spec.q}, axis=0)")
+
+
+def percentile(p) -> DeviceStat:
+    """np.percentile(x, p): the quantile p / 100."""
+    return quantile(np.true_divide(p, 100))
+
+
+def percentile_axis0(p) -> DeviceStat:
+    """np.percentile(a, p, axis=0) over (N, D) data."""
+    return quantile_axis0(np.true_divide(p, 100))
+
+
+def _partial_quantile(part: functools.partial) -> Optional[StatSpec]:
+    """functools.partial(np.quantile | np.percentile, q=..[, axis=0][, method='linear'])."""
+    kw = dict(part.keywords)
+    if part.args or "q" not in kw or not np.isscalar(kw["q"]):
+        return None
+    if kw.pop("method", "linear") != "linear":
+        return None
+    q = kw.pop("q")
+    axis0 = False
+    if "axis" in kw:
+        if kw.pop("axis") != 0:
+            return None
+        axis0 = True
+    if kw:
+        return None
+    if part.func is np.percentile:
+        q = np.true_divide(q, 100)
+    return _quantile_spec(q, axis0)
+
+
 _BY_IDENTITY = {
     id(np.mean): StatSpec("mean", _abi.STAT_MEAN, 1),
     id(np.average): StatSpec("mean", _abi.STAT_MEAN, 1),
@@ -101,6 +151,8 @@ _AXIS0 = {
 
 REGISTRY_NAMES = ("np.mean, np.average, np.var, np.std, np.median, np.sum, "
                   "functools.partial(np.<mean|average|var|std|median>, axis=0), "
+                  "quantile(q), percentile(p), quantile_axis0(q), percentile_axis0(p), "
+                  "functools.partial(np.<quantile|percentile>, q=...[, axis=0]), "
                   "ratio_of_means, weighted_average, pearson_r, linear_fit, fit_slope, fit_intercept, mean_axis0, var_axis0, std_axis0, "
                   "median_axis0, diff_of_means")
 
@@ -109,6 +161,8 @@ def lookup(statfunction: Callable) -> Optional[StatSpec]:
     if isinstance(statfunction, DeviceStat):
         return statfunction.spec
     if isinstance(statfunction, functools.partial):
+        if statfunction.func is np.quantile or statfunction.func is np.percentile:
+            return _partial_quantile(statfunction)
         if (not statfunction.args and statfunction.keywords == {"axis": 0}
                 and id(statfunction.func) in _AXIS0):
             return _AXIS0[id(statfunction.func)]

@@ -141,6 +141,8 @@ class _Run:
         self._columns = None
         self._jack = None
         self._sorted_vals = None
+        # rank statistics: which order statistics (None: np.median's)
+        self.rule = _device.rank_rule(self.dev[0].shape[0], spec.q) if spec.stat_id == _abi.STAT_MEDIAN else None
 
     # -- data views ------------------------------------------------------------
     def columns(self):
@@ -188,10 +190,10 @@ class _Run:
                 cols = self._sorted()
                 out = torch.empty((self.n_cols, hi - lo), dtype=torch.float64, device=cols.device)
                 for d in range(self.n_cols):
-                    _device.resample_median_sorted(cols[d], self.key, lo, hi, out=out[d:d + 1])
+                    _device.resample_median_sorted(cols[d], self.key, lo, hi, out=out[d:d + 1], rule=self.rule)
                 return out
             data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
-            return _device.resample_median_columns(data2d, self.key, lo, hi)
+            return _device.resample_median_columns(data2d, self.key, lo, hi, rule=self.rule)
         if spec.independent:
             # each array has its own key: streams are independent of one another
             means = [_device.resample_stat([a], _abi.STAT_MEAN, (self.key + k * _ARRAY_KEY_STRIDE) & _MASK64, lo, hi)
@@ -226,7 +228,7 @@ class _Run:
             raise IndexError("index out of range")
         if spec.stat_id == _abi.STAT_MEDIAN:
             data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
-            return _device.resample_median_columns_indexed(data2d, idx)
+            return _device.resample_median_columns_indexed(data2d, idx, rule=self.rule)
         if self.vector and spec.n_out == 1:
             cols = self.columns()
             return torch.stack([_device.resample_stat_indexed([cols[d]], spec.stat_id, idx)
@@ -243,10 +245,10 @@ class _Run:
         spec = self.spec
         if spec.stat_id == _abi.STAT_MEDIAN:
             if self._long_median():
-                j = torch.cat([_device.jackknife_median_sorted(c) for c in self._sorted()])
+                j = torch.cat([_device.jackknife_median_sorted(c, rule=self.rule) for c in self._sorted()])
             else:
                 data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
-                j = _device.jackknife_median_columns(data2d)
+                j = _device.jackknife_median_columns(data2d, rule=self.rule)
         elif spec.independent:
             j = self._jackknife_independent()
         elif self.vector and spec.n_out == 1:

@@ -646,25 +646,53 @@ int b200boot_sort_columns(double* stat, int64_t n, int64_t n_cols, void* ws, siz
   return 0;
 }
 
-// ---- median (K1m / K3m) ----------------------------------------------------------
+// ---- median and quantiles (K1m / K3m) ------------------------------------------------
+namespace {
+// full-sample and leave-one-out rules from the ABI struct (NULL: np.median)
+int rank_rules(const b200boot_rank_rule* rule, int64_t n_rows, RankRule* full, RankRule* loo) {
+  if (!rule) {
+    *full = median_rule(n_rows);
+    *loo = median_rule(n_rows > 1 ? n_rows - 1 : 1);
+    return 0;
+  }
+  *full = RankRule{rule->k_lo, rule->k_hi, rule->gamma, rule->mode};
+  *loo = RankRule{rule->loo_k_lo, rule->loo_k_hi, rule->loo_gamma, rule->mode};
+  const int64_t m = n_rows > 1 ? n_rows - 1 : 1;
+  const bool ok = (rule->mode == 0 || rule->mode == 1) && full->k_lo >= 0 && full->k_lo <= full->k_hi &&
+                  full->k_hi <= full->k_lo + 1 && full->k_hi < n_rows && loo->k_lo >= 0 &&
+                  loo->k_lo <= loo->k_hi && loo->k_hi <= loo->k_lo + 1 && loo->k_hi < m &&
+                  full->gamma >= 0.0 && full->gamma <= 1.0 && loo->gamma >= 0.0 && loo->gamma <= 1.0;
+  return ok ? 0 : fail(B200BOOT_EINVAL, "rank rule: ranks outside the sample or weight outside [0, 1]");
+}
+}  // namespace
+
 int b200boot_resample_median_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld,
                                      uint64_t seed, int64_t resample_lo, int64_t resample_hi,
-                                     double* stat_out, void* ws, size_t ws_bytes, void* stream) {
+                                     double* stat_out, void* ws, size_t ws_bytes, void* stream,
+                                     const b200boot_rank_rule* rule) {
+  RankRule full, loo;
+  if (int rc = rank_rules(rule, n_rows, &full, &loo)) return rc;
   return median_resample(data, n_rows, n_cols, ld, seed, resample_lo, resample_hi, stat_out, ws,
-                         ws_bytes, as_stream(stream));
+                         ws_bytes, as_stream(stream), full);
 }
 
 int b200boot_resample_median_columns_indexed(const double* data, int64_t n_rows, int64_t n_cols,
                                              int64_t ld, const int64_t* indices, int64_t n_sets,
-                                             double* stat_out, void* ws, size_t ws_bytes, void* stream) {
+                                             double* stat_out, void* ws, size_t ws_bytes, void* stream,
+                                             const b200boot_rank_rule* rule) {
   if (!indices) return fail(B200BOOT_EINVAL, "null indices");
+  RankRule full, loo;
+  if (int rc = rank_rules(rule, n_rows, &full, &loo)) return rc;
   return median_resample(data, n_rows, n_cols, ld, 0, 0, n_sets, stat_out, ws, ws_bytes,
-                         as_stream(stream), indices);
+                         as_stream(stream), full, indices);
 }
 
 int b200boot_jackknife_median_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld,
-                                      double* out, void* ws, size_t ws_bytes, void* stream) {
-  return median_jackknife(data, n_rows, n_cols, ld, out, ws, ws_bytes, as_stream(stream));
+                                      double* out, void* ws, size_t ws_bytes, void* stream,
+                                      const b200boot_rank_rule* rule) {
+  RankRule full, loo;
+  if (int rc = rank_rules(rule, n_rows, &full, &loo)) return rc;
+  return median_jackknife(data, n_rows, n_cols, ld, out, ws, ws_bytes, as_stream(stream), full, loo);
 }
 
 int b200boot_columns_block_width(int stat_id, int64_t n_rows) {
@@ -689,13 +717,18 @@ int b200boot_jackknife_columns(const double* data, int64_t n_rows, int64_t n_col
 
 int b200boot_resample_median_sorted(const double* sorted_vals, int64_t n_rows, uint64_t seed,
                                     int64_t resample_lo, int64_t resample_hi, double* stat_out, void* ws,
-                                    size_t ws_bytes, void* stream) {
+                                    size_t ws_bytes, void* stream, const b200boot_rank_rule* rule) {
+  RankRule full, loo;
+  if (int rc = rank_rules(rule, n_rows, &full, &loo)) return rc;
   return median_resample_sorted(sorted_vals, n_rows, seed, resample_lo, resample_hi, stat_out, ws, ws_bytes,
-                                as_stream(stream));
+                                as_stream(stream), full);
 }
 
-int b200boot_jackknife_median_sorted(const double* sorted_vals, int64_t n_rows, double* out, void* stream) {
-  return median_jackknife_sorted(sorted_vals, n_rows, out, as_stream(stream));
+int b200boot_jackknife_median_sorted(const double* sorted_vals, int64_t n_rows, double* out, void* stream,
+                                     const b200boot_rank_rule* rule) {
+  RankRule full, loo;
+  if (int rc = rank_rules(rule, n_rows, &full, &loo)) return rc;
+  return median_jackknife_sorted(sorted_vals, n_rows, out, as_stream(stream), full, loo);
 }
 
 // ---- instrumentation ---------------------------------------------------------------

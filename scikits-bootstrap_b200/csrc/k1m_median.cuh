@@ -129,6 +129,27 @@ __global__ void __launch_bounds__(256) median_pack_kernel(const uint64_t* __rest
   }
 }
 
+// ---- which order statistics make the statistic ----------------------------------------
+// np.median is the mean of the two middle order statistics (one for odd N); np.quantile /
+// np.percentile (method 'linear') interpolate between order statistics floor(h) and
+// floor(h) + 1, h = (N - 1) q.  The host fixes the ranks and the weight (it knows numpy's
+// rounding of h); the kernels fetch the two order statistics and combine them here.
+struct RankRule {
+  int64_t k_lo, k_hi;   // 0-based ranks, k_lo <= k_hi <= k_lo + 1
+  double gamma;         // interpolation weight h - floor(h)   (mode 1)
+  int32_t mode;         // 0: mean of the two (np.median), 1: numpy's _lerp
+};
+inline RankRule median_rule(int64_t n) { return RankRule{(n - 1) / 2, n / 2, 0.5, 0}; }
+
+__device__ __forceinline__ double rank_combine(const RankRule& r, double a, double b) {
+  if (r.mode == 0) return (a + b) / 2.0;
+  // numpy/lib/_function_base_impl.py _lerp: a + (b - a) t, or b - (b - a)(1 - t) for t >= 0.5;
+  // explicit roundings so that no multiply-add is contracted
+  const double diff = __dsub_rn(b, a);
+  return r.gamma >= 0.5 ? __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, r.gamma)))
+                        : __dadd_rn(a, __dmul_rn(diff, r.gamma));
+}
+
 // ---- K1m ---------------------------------------------------------------------------
 struct K1mParams {
   const double* sorted_vals;   // [D][N]
@@ -146,6 +167,7 @@ struct K1mParams {
   int32_t* work_counter;
   int32_t count_words;         // uint32 words of one count table: ceil((N + 1) * B / 2), padded
   const int64_t* indices;      // parity mode: caller-supplied index sets [n_local][N], else null
+  RankRule rule;
 };
 
 // First sorted position whose cumulative draw count (resample b of the batch) exceeds k.
@@ -191,8 +213,8 @@ __global__ void __launch_bounds__(kMedThreads, 1) k1m_median_kernel(const K1mPar
   const int n = (int)P.n_rows;
   const uint32_t thresh = lemire_threshold((uint32_t)n);
   const int n_blocks = (n + 3) / 4;
-  const uint32_t k_hi = (uint32_t)(n / 2);         // upper middle rank (0-based)
-  const bool even = (n & 1) == 0;
+  const uint32_t k_hi = (uint32_t)P.rule.k_hi, k_lo = (uint32_t)P.rule.k_lo;
+  const bool two = k_lo != k_hi;                   // e.g. the two middle ranks of an even N
   const uint16_t* cnt16 = reinterpret_cast<const uint16_t*>(s_cnt);
 
   int resident = -1;
@@ -287,9 +309,9 @@ __global__ void __launch_bounds__(kMedThreads, 1) k1m_median_kernel(const K1mPar
             const uint32_t sum = (b & 1) ? (pa >> 16) : (pa & 0xFFFFu);
             const int s_hi = median_find<B>(cnt16, lin, seg_len, lane, b, incl, incl - sum, k_hi);
             double med = sv[s_hi];
-            if (even) {
-              const int s_lo = median_find<B>(cnt16, lin, seg_len, lane, b, incl, incl - sum, k_hi - 1u);
-              med = (sv[s_lo] + med) / 2.0;
+            if (two) {
+              const int s_lo = median_find<B>(cnt16, lin, seg_len, lane, b, incl, incl - sum, k_lo);
+              med = rank_combine(P.rule, sv[s_lo], med);
             }
             if (lane == 0) P.out[(d0 + j) * P.n_local + rb + b] = med;
           }
@@ -301,11 +323,13 @@ __global__ void __launch_bounds__(kMedThreads, 1) k1m_median_kernel(const K1mPar
 }
 
 // ---- K3m: leave-one-out medians by rank of the deleted row ---------------------------
-__device__ __forceinline__ double loo_median(const double* __restrict__ sv, int64_t n, int64_t r) {
+__device__ __forceinline__ double loo_median(const double* __restrict__ sv, int64_t n, int64_t r,
+                                             const RankRule& loo) {
   const int64_t m = n - 1;
   if (m <= 0) return NAN;
   auto kth = [&](int64_t k) { return sv[k < r ? k : k + 1]; };
-  return (m & 1) ? kth(m / 2) : (kth(m / 2 - 1) + kth(m / 2)) / 2.0;
+  const double hi = kth(loo.k_hi);
+  return loo.k_lo == loo.k_hi ? hi : rank_combine(loo, kth(loo.k_lo), hi);
 }
 
 __device__ __forceinline__ double block_sum_256(double v, double* s_red) {
@@ -319,19 +343,21 @@ __device__ __forceinline__ double block_sum_256(double v, double* s_red) {
 }
 
 __global__ void __launch_bounds__(256) k3m_jackknife_median_kernel(const double* __restrict__ sorted_vals,
-                                                                   int64_t n, double* __restrict__ out) {
+                                                                   int64_t n, const RankRule full,
+                                                                   const RankRule loo,
+                                                                   double* __restrict__ out) {
   __shared__ double s_red[8];
   const int64_t d = blockIdx.x;
   const double* sv = sorted_vals + d * n;
   // accumulate relative to the first leave-one-out value: identical values give
   // d == 0 exactly (undefined acceleration) rather than rounding noise
-  const double u = loo_median(sv, n, 0);
+  const double u = loo_median(sv, n, 0, loo);
   double acc = 0.0;
-  for (int64_t r = threadIdx.x; r < n; r += 256) acc += loo_median(sv, n, r) - u;
+  for (int64_t r = threadIdx.x; r < n; r += 256) acc += loo_median(sv, n, r, loo) - u;
   const double jmean = u + block_sum_256(acc, s_red) / (double)n;
   double a2 = 0.0, a3 = 0.0;
   for (int64_t r = threadIdx.x; r < n; r += 256) {
-    const double dv = jmean - loo_median(sv, n, r);
+    const double dv = jmean - loo_median(sv, n, r, loo);
     a2 += dv * dv;
     a3 += dv * dv * dv;
   }
@@ -339,7 +365,7 @@ __global__ void __launch_bounds__(256) k3m_jackknife_median_kernel(const double*
   const double d3 = block_sum_256(a3, s_red);
   if (threadIdx.x == 0) {
     double* o = out + d * 8;
-    o[0] = (n & 1) ? sv[n / 2] : (sv[n / 2 - 1] + sv[n / 2]) / 2.0;
+    o[0] = full.k_lo == full.k_hi ? sv[full.k_hi] : rank_combine(full, sv[full.k_lo], sv[full.k_hi]);
     o[1] = jmean;
     o[2] = d2;
     o[3] = d3;
@@ -365,6 +391,7 @@ struct K1mtParams {
   int64_t resample_lo, n_local;
   const int32_t* counts;       // [n_tiles][n_local]
   double* out;                 // [n_local]
+  RankRule rule;
 };
 
 // CTA-wide exclusive scan of one value per thread; returns the exclusive prefix and the
@@ -403,8 +430,8 @@ __global__ void __launch_bounds__(kMtThreads) k1mt_median_tiled_kernel(const K1m
   const int64_t n = plan.n_rows;
   const int64_t tile = plan.tile();
   const uint32_t m7 = ((1u << (plan.log2_tile - 4)) - 1u) << 7;
-  const int n_ranks = (n & 1) ? 1 : 2;
-  const int64_t rank0 = (n & 1) ? n / 2 : n / 2 - 1;                      // 0-based middle rank(s)
+  const int n_ranks = P.rule.k_lo == P.rule.k_hi ? 1 : 2;
+  const int64_t rank0 = P.rule.k_lo;                                      // 0-based rank(s) wanted
 
   for (int64_t rl = blockIdx.x; rl < P.n_local; rl += gridDim.x) {
     const int64_t r = P.resample_lo + rl;
@@ -493,8 +520,9 @@ __global__ void __launch_bounds__(kMtThreads) k1mt_median_tiled_kernel(const K1m
       vals[which] = P.sorted_vals[row0 + s_pos];
       __syncthreads();
     }
-    if (tid == 0) P.out[rl] = n_ranks == 1 ? vals[0] : (vals[0] + vals[1]) / 2.0;
+    if (tid == 0) P.out[rl] = n_ranks == 1 ? vals[0] : rank_combine(P.rule, vals[0], vals[1]);
     (void)tile;
+    (void)n;
   }
 }
 
@@ -591,7 +619,8 @@ inline int median_prepare(const double* data, int64_t n_rows, int64_t n_cols, in
 
 inline int median_resample(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, uint64_t seed,
                            int64_t resample_lo, int64_t resample_hi, double* stat_out, void* ws,
-                           size_t ws_bytes, cudaStream_t s, const int64_t* indices = nullptr) {
+                           size_t ws_bytes, cudaStream_t s, const RankRule& rule,
+                           const int64_t* indices = nullptr) {
   int rc = median_check(data, n_rows, n_cols, ld, ws);
   if (rc) return rc;
   const int64_t n_local = resample_hi - resample_lo;
@@ -635,6 +664,7 @@ inline int median_resample(const double* data, int64_t n_rows, int64_t n_cols, i
   P.out = stat_out;
   P.work_counter = w.work_counter;
   P.indices = indices;
+  P.rule = rule;
   B2_CUDA(cudaMemsetAsync(w.work_counter, 0, 256, s));
   const size_t smem = 128 + (size_t)cnt_bytes + (size_t)cpi * perm_bytes;
   static bool configured[64] = {false};
@@ -663,7 +693,7 @@ inline int median_resample(const double* data, int64_t n_rows, int64_t n_cols, i
 // Median of a long sorted 1-D array (n_rows beyond the resident limit).
 inline int median_resample_sorted(const double* sorted_vals, int64_t n_rows, uint64_t seed,
                                   int64_t resample_lo, int64_t resample_hi, double* stat_out, void* ws,
-                                  size_t ws_bytes, cudaStream_t s) {
+                                  size_t ws_bytes, cudaStream_t s, const RankRule& rule) {
   if (!sorted_vals || !stat_out || n_rows < 1 || n_rows >= ((int64_t)1 << 31))
     return fail(B200BOOT_EINVAL, "median_sorted: bad arguments");
   const int64_t n_local = resample_hi - resample_lo;
@@ -688,6 +718,7 @@ inline int median_resample_sorted(const double* sorted_vals, int64_t n_rows, uin
   P.n_local = n_local;
   P.counts = counts;
   P.out = stat_out;
+  P.rule = rule;
   const size_t smem = (size_t)(plan.tile() + 2) * 2 + 16;
   static bool configured[64] = {false};
   int dev = 0;
@@ -702,15 +733,17 @@ inline int median_resample_sorted(const double* sorted_vals, int64_t n_rows, uin
   return 0;
 }
 
-inline int median_jackknife_sorted(const double* sorted_vals, int64_t n_rows, double* out, cudaStream_t s) {
+inline int median_jackknife_sorted(const double* sorted_vals, int64_t n_rows, double* out, cudaStream_t s,
+                                   const RankRule& full, const RankRule& loo) {
   if (!sorted_vals || !out || n_rows < 1) return fail(B200BOOT_EINVAL, "bad arguments");
-  k3m_jackknife_median_kernel<<<1, 256, 0, s>>>(sorted_vals, n_rows, out);
+  k3m_jackknife_median_kernel<<<1, 256, 0, s>>>(sorted_vals, n_rows, full, loo, out);
   B2_LAUNCH_CHECK();
   return 0;
 }
 
 inline int median_jackknife(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, double* out,
-                            void* ws, size_t ws_bytes, cudaStream_t s) {
+                            void* ws, size_t ws_bytes, cudaStream_t s, const RankRule& full,
+                            const RankRule& loo) {
   int rc = median_check(data, n_rows, n_cols, ld, ws);
   if (rc) return rc;
   if (!out) return fail(B200BOOT_EINVAL, "null output");
@@ -721,7 +754,7 @@ inline int median_jackknife(const double* data, int64_t n_rows, int64_t n_cols, 
   if (rc) return rc;
   for (int64_t d0 = 0; d0 < n_cols; d0 += 1 << 30) {
     const int64_t nd = std::min<int64_t>((int64_t)1 << 30, n_cols - d0);
-    k3m_jackknife_median_kernel<<<(unsigned)nd, 256, 0, s>>>(w.sorted_vals + d0 * n_rows, n_rows,
+    k3m_jackknife_median_kernel<<<(unsigned)nd, 256, 0, s>>>(w.sorted_vals + d0 * n_rows, n_rows, full, loo,
                                                              out + d0 * 8);
     B2_LAUNCH_CHECK();
   }

@@ -269,6 +269,79 @@ def test_long_median_runs_in_rank_space(n):
     assert_array_equal(got, ref)
 
 
+@pytest.mark.parametrize("q", [0.0, 0.1, 0.25, 1.0 / 3.0, 0.5, 0.9, 0.975, 1.0])
+@pytest.mark.parametrize("n", [1, 2, 3, 20, 301, 1000, 5000, 28672])
+def test_fused_quantile_1d(n, q):
+    """np.quantile(x, q) (method 'linear') in rank space: the two order statistics are found
+    exactly and combined with numpy's own interpolation formula -> bit-exact."""
+    import warnings
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n) if n % 3 else np.round(rng.standard_normal(n), 1)     # ties too
+    m = 200
+    idx = np.array(list(boot.bootstrap_indices(x, m, seed=n)))
+    want = np.sort(np.quantile(x[idx], q, axis=1))
+    stat = boot.quantile(q)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out, dist = boot.ci(x, stat, n_samples=m, seed=n, method="pi", return_dist=True)
+        assert_array_equal(dist, want)
+        if n >= 20:
+            got = boot.ci(x, functools.partial(np.quantile, q=q), n_samples=m, seed=n, method="bca")
+            ref = orc.ci_from_indices((x,), lambda u: np.quantile(u, q), idx, (0.025, 0.975), m, "bca",
+                                      jstat=orc.jack_quantile(x, q))
+            assert_array_equal(got, ref)
+            assert_array_equal(boot.ci_indexed(x, stat, idx, method="bca"), ref)
+
+
+def test_fused_quantile_columns_and_percentile():
+    import warnings
+    rng = np.random.default_rng(44)
+    data = rng.standard_normal((700, 37))
+    data[:, 5] = np.round(data[:, 5], 1)
+    m = 300
+    idx = np.array(list(boot.bootstrap_indices(data, m, seed=3)))
+    for p in (5, 50, 90):
+        f = functools.partial(np.percentile, q=p, axis=0)
+        want = np.sort(np.stack([f(data[i]) for i in idx]), axis=0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out, dist = boot.ci(data, f, n_samples=m, seed=3, return_dist=True)
+            assert_array_equal(dist, want)
+            jst = np.stack([orc.jack_quantile(data[:, d], np.true_divide(p, 100)) for d in range(37)], axis=1)
+            ref = orc.ci_from_indices((data,), f, idx, (0.025, 0.975), m, "bca", jstat=jst)
+            # identical leave-one-out values (the tied column): the acceleration is 0/0 here and
+            # rounding noise of np.mean in numpy, so only the other columns are comparable
+            ok = np.ptp(jst, axis=0) > 0
+            assert ok.sum() >= 36
+            assert_array_equal(out[:, ok], ref[:, ok])
+            assert_array_equal(boot.ci(data, boot.percentile_axis0(p), n_samples=m, seed=3), out)
+            assert_array_equal(boot.ci(data[:, 7], boot.percentile(p), n_samples=m, seed=3), out[:, 7])
+    with pytest.raises(ValueError):
+        boot.quantile(1.5)
+    with pytest.raises(NotImplementedError):
+        boot.ci(data[:, 0], functools.partial(np.quantile, q=0.5, method="nearest"), n_samples=10)
+
+
+@pytest.mark.parametrize("n", [28673, 50001])
+def test_long_quantile_runs_in_rank_space(n):
+    import warnings
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n)
+    xs = np.sort(x)
+    m = 200
+    idx = np.array(list(boot.bootstrap_indices(x, m, seed=n)))
+    for q in (0.02, 0.5, 0.9, 1.0):
+        want = np.sort(np.quantile(xs[idx], q, axis=1))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out, dist = boot.ci(x, boot.quantile(q), n_samples=m, seed=n, method="pi", return_dist=True)
+            assert_array_equal(dist, want)
+            got = boot.ci(x, boot.quantile(q), n_samples=m, seed=n, method="bca")
+            ref = orc.ci_from_indices((xs,), lambda u: np.quantile(u, q), idx, (0.025, 0.975), m, "bca",
+                                      jstat=orc.jack_quantile(xs, q))
+        assert_array_equal(got, ref)
+
+
 def test_long_median_over_columns():
     """(N, D) data with more rows than the resident limit: every column is resampled in its
     own rank space with the same index sets, so column d equals the 1-D run on data[:, d]."""
