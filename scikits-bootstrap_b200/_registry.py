@@ -136,6 +136,18 @@ def _partial_quantile(part: functools.partial) -> Optional[StatSpec]:
     return _quantile_spec(q, axis0)
 
 
+def diff_of(statfunction) -> DeviceStat:
+    """s(a) - s(b) for two INDEPENDENT samples (multi='independent'; the arrays may differ in
+    length), s any scalar single-array statistic of the registry: np.mean, np.var, np.std,
+    np.sum, np.median, quantile(q), percentile(p).  diff_of(np.mean) is diff_of_means."""
+    inner = require(statfunction)
+    if inner.n_arrays != 1 or inner.axis0 or inner.n_out != 1 or inner.independent:
+        raise NotImplementedError(f"diff_of needs a scalar statistic of one 1-D array, got {inner.name}")
+    host = statfunction
+    return DeviceStat(StatSpec(f"diff_of({inner.name})", inner.stat_id, 2, independent=True, q=inner.q),
+                      lambda a, b: host(a) - host(b), f"{inner.name}(a) - {inner.name}(b) of independent samples")
+
+
 _BY_IDENTITY = {
     id(np.mean): StatSpec("mean", _abi.STAT_MEAN, 1),
     id(np.average): StatSpec("mean", _abi.STAT_MEAN, 1),
@@ -154,7 +166,7 @@ REGISTRY_NAMES = ("np.mean, np.average, np.var, np.std, np.median, np.sum, "
                   "quantile(q), percentile(p), quantile_axis0(q), percentile_axis0(p), "
                   "functools.partial(np.<quantile|percentile>, q=...[, axis=0]), "
                   "ratio_of_means, weighted_average, pearson_r, linear_fit, fit_slope, fit_intercept, mean_axis0, var_axis0, std_axis0, "
-                  "median_axis0, diff_of_means")
+                  "median_axis0, diff_of_means, diff_of(<scalar statistic>)")
 
 
 def lookup(statfunction: Callable) -> Optional[StatSpec]:

@@ -141,6 +141,7 @@ class _Run:
         self._columns = None
         self._jack = None
         self._sorted_vals = None
+        self._parts = None
         # rank statistics: which order statistics (None: np.median's)
         self.rule = _device.rank_rule(self.dev[0].shape[0], spec.q) if spec.stat_id == _abi.STAT_MEDIAN else None
 
@@ -185,6 +186,9 @@ class _Run:
         spec, lo, hi = self.spec, self.lo, self.hi
         if self.indices is not None:
             return self._resample_indexed()
+        if spec.independent:
+            a, b = (p.resample() for p in self.parts())
+            return a - b
         if spec.stat_id == _abi.STAT_MEDIAN:
             if self._long_median():
                 cols = self._sorted()
@@ -194,11 +198,6 @@ class _Run:
                 return out
             data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
             return _device.resample_median_columns(data2d, self.key, lo, hi, rule=self.rule)
-        if spec.independent:
-            # each array has its own key: streams are independent of one another
-            means = [_device.resample_stat([a], _abi.STAT_MEAN, (self.key + k * _ARRAY_KEY_STRIDE) & _MASK64, lo, hi)
-                     for k, a in enumerate(self.dev)]
-            return (means[0] - means[1]).reshape(1, -1)
         if spec.n_out > 1:
             return _device.resample_stat([a.reshape(-1) for a in self.dev], spec.stat_id, self.key, lo, hi)
         if self.vector and _device.columns_block_width(spec.stat_id, self.dev[0].shape[0]) > 0:
@@ -243,14 +242,14 @@ class _Run:
             return self._jack
         torch = _device._torch()
         spec = self.spec
-        if spec.stat_id == _abi.STAT_MEDIAN:
+        if spec.independent:
+            j = self._jackknife_independent()
+        elif spec.stat_id == _abi.STAT_MEDIAN:
             if self._long_median():
                 j = torch.cat([_device.jackknife_median_sorted(c, rule=self.rule) for c in self._sorted()])
             else:
                 data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
                 j = _device.jackknife_median_columns(data2d, rule=self.rule)
-        elif spec.independent:
-            j = self._jackknife_independent()
         elif self.vector and spec.n_out == 1:
             j = _device.jackknife_columns(self.dev[0], spec.stat_id)                               # K3c
         else:
@@ -258,25 +257,34 @@ class _Run:
         self._jack = _device.to_host(j)
         return self._jack
 
+    def parts(self):
+        """multi='independent': one single-array job per data array, each with its own Philox
+        key (its index stream is independent of the others: bootstrap.py:683-691)."""
+        if self._parts is None:
+            inner = StatSpec(self.spec.name, self.spec.stat_id, 1, q=self.spec.q)
+            self._parts = [_Run(inner, [a], False, self.n_samples, (self.key + k * _ARRAY_KEY_STRIDE) & _MASK64)
+                           for k, a in enumerate(self.dev)]
+        return self._parts
+
     def _jackknife_independent(self):
-        """diff_of_means under multi='independent': sum_k N_k leave-one-out values,
-        array-major (bootstrap.py:601-607, 708-714).  Deleting row j of array k moves
-        only mean_k, so the pooled jackknife mean is the statistic itself and the
-        deviations are +(a_j - mean_a)/(N_a - 1) and -(b_j - mean_b)/(N_b - 1): the
-        moments follow from each array's own K3 (mean) pass."""
+        """s(a) - s(b) under multi='independent': sum_k N_k leave-one-out values, array-major
+        (bootstrap.py:601-607, 708-714).  Deleting row j of array k moves only s_k, so with each
+        array's own K3 summary (statistic s_k, jackknife mean m_k, and the sums d2_k, d3_k of
+        squared / cubed deviations m_k - loo_k[j]) the pooled moments are closed forms: the
+        pooled mean is J = (N_a (m_a - s_b) + N_b (s_a - m_b)) / (N_a + N_b); the deviations are
+        c_a + (m_a - loo_a[j]) and c_b - (m_b - loo_b[j]) with c_a = J - (m_a - s_b),
+        c_b = J - (s_a - m_b), and sum_j (m_k - loo_k[j]) = 0."""
         torch = _device._torch()
-        a, b = self.dev
-        ma = _device.to_host(_device.jackknife([a], _abi.STAT_MEAN))
-        mb = _device.to_host(_device.jackknife([b], _abi.STAT_MEAN))
-        # per-array K3 (mean): d2_k = sum ((x - m_k)/(N_k-1))^2, d3_k likewise cubed; the b
-        # deviations enter with a minus sign
-        d2 = ma[2] + mb[2]
-        d3 = ma[3] - mb[3]
-        ostat = ma[0] - mb[0]
+        (sa, ma, d2a, d3a), (sb, mb, d2b, d3b) = (p.jackknife()[0, :4] for p in self.parts())
+        na, nb = (float(a.shape[0]) for a in self.dev)
+        ostat = sa - sb
+        jmean = (na * (ma - sb) + nb * (sa - mb)) / (na + nb)
+        ca = jmean - (ma - sb)
+        cb = jmean - (sa - mb)
+        d2 = (na * ca * ca + d2a) + (nb * cb * cb + d2b)
+        d3 = (na * ca ** 3 + 3.0 * ca * d2a + d3a) + (nb * cb ** 3 + 3.0 * cb * d2b - d3b)
         out = np.zeros(8)
-        out[0] = ostat
-        out[1] = ostat          # pooled jackknife mean equals the statistic for this linear form
-        out[2], out[3] = d2, d3
+        out[0], out[1], out[2], out[3] = ostat, jmean, d2, d3
         with np.errstate(invalid="ignore", divide="ignore"):
             out[4] = d3 / (6.0 * d2 ** 1.5)
         return torch.from_numpy(out.reshape(1, 8))
@@ -530,7 +538,9 @@ def pval(
     criterion is `s > 0`.  Criteria built with less_than / less_equal /
     greater_than / greater_equal / between are counted on the device; any other
     callable is applied on the host to the device-computed statistic values, row
-    by row, as the reference does (bootstrap.py:861)."""
+    by row, as the reference does (bootstrap.py:861).  Beyond the reference (whose
+    pval treats any truthy `multi` as paired, bootstrap.py:841-850): multi='independent'
+    resamples each array on its own, as `ci` does."""
     return _pval_impl(data, statfunction, compfunction, n_samples, multi, seed, None)
 
 
@@ -543,7 +553,7 @@ def pval_indexed(data, statfunction=np.average, compfunction=positive, indices=N
 def _pval_impl(data, statfunction, compfunction, n_samples, multi, seed, indices):
     if multi is None:
         multi = bool(isinstance(data, tuple))
-    arrays, multi = _normalise(data, bool(multi))
+    arrays, multi = _normalise(data, multi if multi == "independent" else bool(multi))
     if not callable(statfunction):
         raise TypeError("statfunction {} is not callable.".format(statfunction))
     spec = require(statfunction)

@@ -34,6 +34,10 @@ def main():
         lambda: boot.pval(table, boot.mean_axis0, boot.greater_than(0.01), n_samples=501, seed=8),
         lambda: boot.pval(x, np.mean, lambda s: s > 1.0, n_samples=501, seed=8),
         lambda: boot.ci(x[:2000], np.mean, n_samples=801, seed=9, return_dist=True)[1],
+        lambda: boot.ci((a, b), boot.linear_fit, n_samples=555, seed=10),
+        lambda: boot.ci(x, boot.percentile(90), n_samples=333, seed=11),
+        lambda: boot.ci(table, boot.quantile_axis0(0.25), n_samples=301, seed=12),
+        lambda: boot.ci((a[:6000], x), boot.diff_of(np.median), n_samples=401, seed=13, multi="independent"),
         lambda: boot.ci(x, np.mean, n_samples=64, seed=None),          # seed agreed through a broadcast
     ]
     boot.distributed.enable()

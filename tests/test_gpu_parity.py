@@ -799,6 +799,36 @@ def test_independent_mode():
     assert_allclose(got, [2.547619, 7.97619], atol=0.25)
 
 
+@pytest.mark.parametrize("name,stat", [("mean", np.mean), ("median", np.median), ("std", np.std), ("var", np.var),
+                                       ("sum", np.sum), ("q80", functools.partial(np.quantile, q=0.8))])
+@pytest.mark.parametrize("na,nb", [(60, 45), (301, 300), (30000, 1000)])
+def test_independent_difference_of_statistics(name, stat, na, nb):
+    """diff_of(s): s(a) - s(b) of independent samples; the pooled jackknife (N_a + N_b
+    leave-one-out values, bootstrap.py:601-607) comes from the two per-array K3 summaries."""
+    a = np.random.default_rng(na).gamma(2, 1, na)
+    b = np.random.default_rng(nb + 1).gamma(3, 1, nb)
+    n = 600
+    f = lambda u, v: stat(u) - stat(v)
+    dstat = boot.diff_of(stat)
+    idx = list(boot.bootstrap_indices_independent((a, b), n, seed=13))
+    if name in ("median", "q80") and na > 28672:      # rank-space path: indices address sorted(a)
+        a = np.sort(a)
+    want_dist = np.sort([f(a[i], b[j]) for i, j in idx])
+    out, dist = boot.ci((a, b), dstat, n_samples=n, multi="independent", seed=13, method="pi", return_dist=True)
+    assert_allclose(dist, want_dist, rtol=1e-11, atol=1e-13)
+    # closed-form per-array leave-one-out values, pooled array-major as the reference does
+    jack1 = {"mean": orc.jack_mean, "median": orc.jack_median, "std": lambda x: orc.jack_var(x, True),
+             "var": orc.jack_var, "sum": lambda x: np.sum(x) - x, "q80": lambda x: orc.jack_quantile(x, 0.8)}[name]
+    jstat = np.concatenate([jack1(a) - stat(b), stat(a) - jack1(b)])
+    if na <= 301:
+        assert_allclose(jstat, orc.jackknife_stats_independent_loop((a, b), f), rtol=1e-9, atol=1e-12)
+    want = orc.ci_from_indices((a, b), f, idx, (0.025, 0.975), n, "bca", multi="independent", jstat=jstat)
+    got = boot.ci((a, b), dstat, n_samples=n, multi="independent", seed=13, method="bca")
+    assert_allclose(got, want, rtol=1e-11, atol=1e-13)
+    p = boot.pval((a, b), dstat, boot.less_than(0.0), n_samples=n, multi="independent", seed=13)
+    assert p == np.mean(dist < 0.0)
+
+
 # ------------------------------------------------------------------ other plans --
 
 @pytest.mark.parametrize("n,L,wrap", [(5, 3, False), (4, 3, True), (1000, 7, False), (1000, 7, True), (40001, 50, True)])
