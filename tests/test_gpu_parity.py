@@ -1015,3 +1015,20 @@ def test_full_size_properties_cfg5():
     assert_allclose(x[idx].mean(), s1[5], rtol=1e-12)
     lo, hi = boot.ci(xd, np.mean, n_samples=m, seed=7)
     assert lo < x.mean() < hi and (hi - lo) < 6 * se
+
+
+def test_very_long_array_two_level_tile_chains():
+    """N = 2e8 (12 208 tiles, two-level occupancy chains, 1.6 GB of data created on the
+    device): the interval must bracket the mean with the width the standard error implies,
+    and the rank-space median path must run at this length too."""
+    import torch
+    n, m = 200_000_000, 500
+    x = torch.randn(n, dtype=torch.float64, device="cuda") + 1.0
+    mu = float(x.mean())
+    se = float(x.std()) / np.sqrt(n)
+    lo, hi = boot.ci(x, np.mean, n_samples=m, seed=1)
+    assert lo < mu < hi and 3.0 < (hi - lo) / se < 5.0
+    again = boot.ci(x, np.mean, n_samples=m, seed=1)
+    assert_array_equal(again, [lo, hi])
+    mlo, mhi = boot.ci(x, np.median, n_samples=m, seed=1)
+    assert mlo < 1.0 + 5 * se and mhi > 1.0 - 5 * se and 3.0 < (mhi - mlo) / (1.2533 * se) < 5.0
