@@ -56,6 +56,56 @@ def test_errors_do_not_cross_abi_as_exceptions():
         _abi.check(L.b200boot_make_plan(-5, 1, C.byref(_abi.Plan())))
 
 
+def test_abi_argument_validation_returns_status_codes():
+    """Every entry point validates before it touches CUDA, so the status codes of
+    include/b200boot.h can be checked without a GPU: pointers below are fakes that
+    are never dereferenced on these paths."""
+    L = _abi.lib()
+    EINVAL, EWORKSPACE, EUNSUPPORTED = -1, -3, -4
+    fake = 1 << 20                                    # 256-byte aligned, never dereferenced
+    ptrs = (C.c_void_p * 2)(fake, fake)
+    rs = L.b200boot_resample_stat
+    assert rs(ptrs, 1, 1000, 99, 0, 0, 10, fake, fake, 1 << 30, None) == EUNSUPPORTED
+    assert b"registry" in L.b200boot_last_error()
+    assert rs(ptrs, 2, 1000, _abi.STAT_MEAN, 0, 0, 10, fake, fake, 1 << 30, None) == EINVAL      # takes 1 array
+    assert rs(ptrs, 1, 1000, _abi.STAT_PEARSON_R, 0, 0, 10, fake, fake, 1 << 30, None) == EINVAL  # takes 2
+    assert rs(ptrs, 1, 0, _abi.STAT_MEAN, 0, 0, 10, fake, fake, 1 << 30, None) == EINVAL
+    assert rs(ptrs, 1, 1 << 31, _abi.STAT_MEAN, 0, 0, 10, fake, fake, 1 << 30, None) == EINVAL
+    assert rs(ptrs, 1, 1000, _abi.STAT_MEAN, 0, 10, 5, fake, fake, 1 << 30, None) == EINVAL       # hi < lo
+    assert rs(ptrs, 1, 1000, _abi.STAT_MEAN, 0, 0, 0, fake, fake, 1 << 30, None) == 0             # empty shard
+    assert rs(ptrs, 1, 1000, _abi.STAT_MEAN, 0, 0, 10, None, fake, 1 << 30, None) == EINVAL       # null output
+    assert rs(ptrs, 1, 1000, _abi.STAT_MEAN, 0, 0, 10, fake, fake + 8, 1 << 30, None) == EWORKSPACE
+    assert b"aligned" in L.b200boot_last_error()
+    assert rs(ptrs, 1, 1000, _abi.STAT_MEAN, 0, 0, 10, fake, fake, 64, None) == EWORKSPACE
+    assert b"too small" in L.b200boot_last_error()
+    need = L.b200boot_workspace_bytes(_abi.STAT_MEAN, 10**7, 1, 1, 1000, 2)
+    assert need > 611 * 1000 * 4 * 17                 # tile + class occupancies at least
+    assert L.b200boot_workspace_bytes(_abi.STAT_MEAN, 0, 1, 1, 10, 2) == 0
+
+    # rank rule of the median / quantile entry points
+    rule = _abi.RankRule(k_lo=5, k_hi=7, gamma=0.5, loo_k_lo=4, loo_k_hi=5, loo_gamma=0.5, mode=1)
+    rp = C.cast(C.pointer(rule), C.c_void_p)
+    rm = L.b200boot_resample_median_columns
+    assert rm(fake, 100, 1, 1, 0, 0, 10, fake, fake, 1 << 30, None, rp) == EINVAL                 # k_hi > k_lo + 1
+    rule.k_hi = 100
+    rule.k_lo = 99
+    assert rm(fake, 100, 1, 1, 0, 0, 10, fake, fake, 1 << 30, None, rp) == EINVAL                 # rank outside the sample
+    rule.k_lo, rule.k_hi, rule.gamma = 5, 6, 1.5
+    assert rm(fake, 100, 1, 1, 0, 0, 10, fake, fake, 1 << 30, None, rp) == EINVAL
+    assert rm(fake, 40000, 1, 1, 0, 0, 10, fake, fake, 1 << 30, None, None) == EUNSUPPORTED       # beyond resident rows
+    assert L.b200boot_resample_median_sorted(fake, 1000, 0, 0, 10, fake, fake, 1 << 30, None, None) == EINVAL  # one tile
+
+    assert L.b200boot_count(fake, 10, 1, 9, fake, None, fake, None) == EINVAL                     # bad operator
+    assert L.b200boot_count(fake, 10, 1, _abi.CMP_BETWEEN, fake, None, fake, None) == EINVAL      # needs t1
+    assert L.b200boot_fill_moving_block(0, 5, 5, 0, 0, 3, fake, None) == EINVAL                   # no admissible start
+    assert L.b200boot_fill_subsample(0, 10, 11, 0, 3, fake, fake, 1 << 30, None) == EINVAL        # size > N
+    assert L.b200boot_fill_indices(0, 0, 1, 0, 3, fake, fake, 1 << 30, None) == EINVAL
+    assert L.b200boot_jackknife_columns(fake, 10, 3, 2, _abi.STAT_MEAN, fake, None) == EINVAL     # ld < n_cols
+    assert L.b200boot_jackknife_columns(fake, 10, 3, 3, _abi.STAT_PEARSON_R, fake, None) == EUNSUPPORTED
+    assert L.b200boot_columns_block_width(_abi.STAT_MEAN, 100000) == 0                            # beyond K1c rows
+    assert L.b200boot_columns_block_width(_abi.STAT_MEAN, 1000) in (4, 8, 16, 32)
+
+
 def _philox(c, k):
     out = (C.c_uint32 * 4)()
     _abi.lib().b200boot_host_philox4x32((C.c_uint32 * 4)(*c), (C.c_uint32 * 2)(*k), out)
