@@ -239,9 +239,15 @@ __device__ __forceinline__ void class_accumulate(const unsigned char* __restrict
                                                  uint32_t cbits, uint32_t h, double* tot) {
   LaneAcc<MS> A;
   A.clear();
-  const uint32_t n_full = (uint32_t)(n_c / kClassDrawsPerBlock);
+  // The lane owns blocks q = h, h+2, ... of the ceil(n_c / 12) blocks of its class.  All but
+  // its last one are whole and run unpredicated; the last one (whole or partial) runs in a
+  // predicated epilogue that every lane of the warp enters together, so a partial block
+  // never costs a separate, half-empty pass.
+  const uint32_t n_blocks = (uint32_t)((n_c + kClassDrawsPerBlock - 1) / kClassDrawsPerBlock);
+  const uint32_t owned = n_blocks > h ? (n_blocks - h + 1u) >> 1 : 0u;
+  const uint32_t q_last = h + 2u * (owned - 1u);          // meaningful when owned > 0
 #pragma unroll(kClassUnroll)
-  for (uint32_t q = h; q < n_full; q += 2) {
+  for (uint32_t q = h; q < q_last && owned != 0u; q += 2) {
     const Words4 w = stream_block(st, q, rk);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -256,16 +262,21 @@ __device__ __forceinline__ void class_accumulate(const unsigned char* __restrict
       }
     }
   }
-  const int64_t done = (int64_t)n_full * kClassDrawsPerBlock;
-  if (done < n_c && (n_full & 1u) == h) {
-    const Words4 w = stream_block(st, n_full, rk);
+  if (owned != 0u) {
+    const int valid = (int)min((int64_t)kClassDrawsPerBlock, n_c - (int64_t)q_last * kClassDrawsPerBlock);
+    const Words4 w = stream_block(st, q_last, rk);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       uint32_t f[3];
       class_fields_shifted(w.w[i], m7, f);
 #pragma unroll
       for (int k = 0; k < 3; ++k)
-        if (done + 3 * i + k < n_c) A.take(3 * i + k, s_bytes, stride_bytes, f[k] | cbits);
+        if (3 * i + k < valid) {
+          if (FAST)
+            A.take_fast(3 * i + k, f[k] | cbits);
+          else
+            A.take(3 * i + k, s_bytes, stride_bytes, f[k] | cbits);
+        }
     }
   }
   A.finish(tot);
