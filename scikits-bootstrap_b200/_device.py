@@ -67,7 +67,12 @@ def to_device_f64(x, device=None):
 
 
 def stream_ptr() -> int:
-    return _torch().cuda.current_stream().cuda_stream
+    """Raw handle of torch's current CUDA stream on the current device."""
+    torch = _torch()
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)      # ~1 us; the public path costs ~15 us
+    if raw is not None:
+        return raw(torch.cuda.current_device())
+    return torch.cuda.current_stream().cuda_stream
 
 
 class Workspace:

@@ -37,9 +37,50 @@ def _tail(t):
     return _poly(_A_TAIL, t) / (_poly(_B_TAIL, t) * t + 1)
 
 
+def _horner(coef, t):
+    r = coef[0]
+    for c in coef[1:]:
+        r = r * t + c
+    return r
+
+
+def _nppf_scalar(p: float) -> float:
+    """One element of nppf in Python floats: the same IEEE operations in the same order as
+    the array form below (np.log on a float64 scalar runs the same ufunc loop; sqrt is
+    correctly rounded everywhere), so the two agree bit for bit — tests/test_host_probes.py."""
+    if p != p:
+        return math.nan
+    if p <= 0.0:
+        return -math.inf if p == 0.0 else math.nan
+    if p >= 1.0:
+        return math.inf if p == 1.0 else math.nan
+    if p < _SPLIT_LO:
+        t = math.sqrt(-2 * float(np.log(np.float64(p))))
+        return _horner(_A_TAIL, t) / (_horner(_B_TAIL, t) * t + 1)
+    if p <= _SPLIT_HI:
+        q = p - 0.5
+        s = q * q
+        return (_horner(_A_MID, s) * q) / (_horner(_B_MID, s) * s + 1)
+    t = math.sqrt(-2 * float(np.log(np.float64(1 - p))))
+    return -(_horner(_A_TAIL, t) / (_horner(_B_TAIL, t) * t + 1))
+
+
+_SCALAR_LIMIT = 16     # below this many elements the per-element path beats numpy's masks
+
+
 def nppf(p) -> np.ndarray:
     """Inverse standard-normal cdf, Acklam form; -inf / +inf at p == 0 / 1."""
     p = np.asarray(p, dtype=float)
+    if p.size <= _SCALAR_LIMIT:
+        out = np.empty(p.shape)
+        flat = out.reshape(-1)
+        for i, v in enumerate(p.reshape(-1).tolist()):
+            flat[i] = _nppf_scalar(v)
+        return out
+    return _nppf_array(p)
+
+
+def _nppf_array(p: np.ndarray) -> np.ndarray:
     out = np.full(p.shape, np.nan)
     with np.errstate(all="ignore"):
         lo = (p > 0) & (p < _SPLIT_LO)
@@ -77,6 +118,38 @@ def bca_levels(less_counts: np.ndarray, n_samples: int, accel: np.ndarray,
 def order_indices(avals: np.ndarray, n_samples: int) -> Tuple[np.ndarray, List[str]]:
     """round((n-1)*avals) half-to-even as int (NaN -> 0) and which instability
     conditions hold: 'nan', then 'extremal' or else 'top10'."""
+    avals = np.asarray(avals, dtype=float)
+    if avals.size <= _SCALAR_LIMIT:
+        # a handful of levels: Python's round() is half-to-even like np.round, and
+        # (n - 1) * a is the same IEEE product
+        top = n_samples - 1
+        vals = [top * a for a in avals.reshape(-1).tolist()]
+        if all(v != v or abs(v) < 4.0e18 for v in vals):       # else: numpy's own int conversion
+            nan = extremal = top10 = False
+            ints = []
+            for v in vals:
+                if v != v:
+                    nan = True
+                    ints.append(0)
+                    continue
+                k = round(v)
+                ints.append(k)
+                if k == 0 or k == top:
+                    extremal = True
+                elif k < 10 or k >= n_samples - 10:
+                    top10 = True
+            flags: List[str] = []
+            if nan:
+                flags.append("nan")
+            if extremal:
+                flags.append("extremal")
+            elif top10:
+                flags.append("top10")
+            return np.array(ints, dtype="int").reshape(avals.shape), flags
+    return _order_indices_array(avals, n_samples)
+
+
+def _order_indices_array(avals: np.ndarray, n_samples: int) -> Tuple[np.ndarray, List[str]]:
     flags: List[str] = []
     with np.errstate(invalid="ignore"):
         nvals = np.round((n_samples - 1) * avals)

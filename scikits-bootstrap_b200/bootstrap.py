@@ -238,8 +238,25 @@ class _Run:
     # -- K3 ----------------------------------------------------------------------
     def jackknife(self):
         """float64[D][8] on the host: ostat, jmean, d2, d3, accel, ..."""
-        if self._jack is not None:
-            return self._jack
+        if self._jack is None:
+            self._jack = _device.to_host(self._jackknife_tensor())
+        return self._jack
+
+    def jackknife_and_less(self, stat):
+        """BCa inputs: the jackknife summary (host, float64[D][8]) and #{stat < ostat} per
+        column (bootstrap.py:583).  For a scalar statistic the count kernel reads ostat
+        straight from the jackknife output on the device, so the two results come back
+        with one wait instead of a host round trip in between."""
+        if self.n_cols == 1 and not self.spec.independent and self._jack is None:
+            jd = self._jackknife_tensor()
+            c = _device.count(stat, _abi.CMP_LT, jd)              # &jd[0][0] is ostat
+            _dist.all_reduce_sum(c)
+            self._jack = _device.to_host(jd)
+            return self._jack, _device.to_host(c)
+        jack = self.jackknife()
+        return jack, self.count(stat, _abi.CMP_LT, jack[:, 0])
+
+    def _jackknife_tensor(self):
         torch = _device._torch()
         spec = self.spec
         if spec.independent:
@@ -254,8 +271,7 @@ class _Run:
             j = _device.jackknife_columns(self.dev[0], spec.stat_id)                               # K3c
         else:
             j = _device.jackknife([a.reshape(-1) for a in self.dev], spec.stat_id).reshape(self.n_cols, 8)
-        self._jack = _device.to_host(j)
-        return self._jack
+        return j
 
     def parts(self):
         """multi='independent': one single-array job per data array, each with its own Philox
@@ -457,10 +473,9 @@ def _ci_on_device(spec, arrays, multi, n_samples, key, indices, alphas, method, 
     if method == "pi":
         avals = alphas
     else:
-        jack = run.jackknife()
+        jack, less = run.jackknife_and_less(stat)                 # strict '<'  bootstrap.py:583
         ostat = jack[:, 0]
         accel = jack[:, 4]
-        less = run.count(stat, _abi.CMP_LT, ostat)               # strict '<'  bootstrap.py:583
         if not run.vector:
             less, accel_s = less[0], accel[0]
         else:

@@ -605,6 +605,17 @@ int b200boot_select_hist_buffer(int n_alphas, int64_t n_cols, void* ws, size_t w
 
 int b200boot_select(const double* stat, int64_t n_local, int64_t n_cols, const int64_t* ranks,
                     int n_alphas, double* out, void* ws, size_t ws_bytes, void* stream) {
+  if (stat && ranks && out && n_alphas >= 1 && n_cols >= 1 && n_cols <= kSelSmallMaxCols && n_local >= 1 &&
+      n_local <= kSelSmallMaxRows) {
+    // short columns: the whole descent in one launch per group of selects
+    for (int a0 = 0; a0 < n_alphas; a0 += kSelMaxAlphas) {
+      const int ac = std::min(kSelMaxAlphas, n_alphas - a0);
+      k5_select_small_kernel<<<(unsigned)n_cols, kSelSmallThreads, 0, as_stream(stream)>>>(
+          stat, n_local, n_cols, ranks, a0, ac, out);
+      B2_LAUNCH_CHECK();
+    }
+    return 0;
+  }
   int rc = b200boot_select_begin(ranks, n_alphas, n_cols, ws, ws_bytes, stream);
   for (int pass = 0; pass < 8 && !rc; ++pass) {
     rc = b200boot_select_hist(stat, n_local, n_cols, n_alphas, pass, ws, ws_bytes, stream);

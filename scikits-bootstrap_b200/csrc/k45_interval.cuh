@@ -151,6 +151,75 @@ __global__ void __launch_bounds__(256) k5_end_kernel(int64_t ad, SelectState st,
   if (i < ad) out[i] = value_of(st.prefix[i]);
 }
 
+// Whole radix descent of one short column inside one CTA (one launch instead of
+// begin + 8 x (hist + pick) + end): the small-problem path, where launch count is
+// what the call costs.  Warp a walks the bins of select a; same results as the
+// multi-launch path (both are exact).
+constexpr int kSelSmallThreads = 1024;
+constexpr int64_t kSelSmallMaxRows = 32768;
+constexpr int64_t kSelSmallMaxCols = 64;
+
+__global__ void __launch_bounds__(kSelSmallThreads) k5_select_small_kernel(
+    const double* __restrict__ stat, int64_t n, int64_t n_cols, const int64_t* __restrict__ ranks,
+    int a_lo, int a_cnt, double* __restrict__ out) {
+  __shared__ unsigned int s_hist[kSelMaxAlphas][256];
+  __shared__ uint64_t s_prefix[kSelMaxAlphas];
+  __shared__ long long s_krem[kSelMaxAlphas];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t d = blockIdx.x;
+  const double* col = stat + d * n;
+  if (tid < a_cnt) {
+    s_prefix[tid] = 0;
+    s_krem[tid] = ranks[(int64_t)(a_lo + tid) * n_cols + d];
+  }
+  for (int pass = 0; pass < 8; ++pass) {
+    for (int i = tid; i < a_cnt * 256; i += kSelSmallThreads) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    const int shift = 56 - 8 * pass;
+    for (int64_t r = tid; r < n; r += kSelSmallThreads) {
+      const uint64_t k = key_of(col[r]);
+      const unsigned int digit = (unsigned int)(k >> shift) & 0xFFu;
+      for (int a = 0; a < a_cnt; ++a)
+        if (pass == 0 || ((k ^ s_prefix[a]) >> (shift + 8)) == 0) atomicAdd(&s_hist[a][digit], 1u);
+    }
+    __syncthreads();
+    if (warp < a_cnt) {
+      // lane l owns bins 8l .. 8l+7; first bin whose cumulative count exceeds krem
+      const long long k = s_krem[warp];
+      unsigned int mine = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) mine += s_hist[warp][lane * 8 + b];
+      unsigned int inc = mine;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const unsigned int o = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += o;
+      }
+      const unsigned int hit = __ballot_sync(0xffffffffu, (long long)inc > k);
+      const int owner = hit ? __ffs(hit) - 1 : 31;
+      if (lane == owner) {
+        long long below = (long long)inc;      // no bin found (rank beyond the column): as k5_pick
+        int digit = 255;
+        if (hit) {
+          below = (long long)(inc - mine);
+          for (int b = 0; b < 8; ++b) {
+            const long long c = s_hist[warp][lane * 8 + b];
+            if (k < below + c) {
+              digit = lane * 8 + b;
+              break;
+            }
+            below += c;
+          }
+        }
+        s_krem[warp] = k - below;
+        s_prefix[warp] |= (uint64_t)digit << shift;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < a_cnt) out[(int64_t)(a_lo + tid) * n_cols + d] = value_of(s_prefix[tid]);
+}
+
 // ------------------------------------------------------------------ sort ------
 // Bitonic network over keys padded to a power of two with the maximum key.
 __global__ void __launch_bounds__(256) sort_load_kernel(const double* __restrict__ stat, int64_t n,

@@ -351,6 +351,18 @@ def test_interval_math_matches_oracle(golden):
     from scikits_bootstrap_b200 import _interval as iv
     np.testing.assert_array_equal(iv.nppf(golden["nppf/p"]), golden["nppf/val"])
     np.testing.assert_array_equal(iv.ncdf(golden["ncdf/x"]), golden["ncdf/val"])
+    # the per-element path taken for a handful of levels equals the array path bit for bit,
+    # on the reference's own grid and across the three branches and their edges
+    grid = np.asarray(golden["nppf/p"], dtype=float).reshape(-1)
+    rng = np.random.default_rng(1)
+    grid = np.concatenate([grid, rng.random(20000), rng.random(5000) * 0.03, 1 - rng.random(5000) * 0.03,
+                           [0.0, 1.0, 0.02425, 0.97575, 0.5, 1e-300, 1 - 1e-16, np.nan]])
+    with np.errstate(all="ignore"):
+        want = iv._nppf_array(grid)
+    got = np.array([iv._nppf_scalar(float(v)) for v in grid])
+    np.testing.assert_array_equal(got, want)
+    for k in range(0, 64, 7):
+        np.testing.assert_array_equal(iv.nppf(grid[k:k + 5]), want[k:k + 5])
     rng = np.random.default_rng(0)
     for _ in range(50):
         n = int(rng.integers(50, 5000))
@@ -359,3 +371,24 @@ def test_interval_math_matches_oracle(golden):
         b, fb = orc.order_indices(av, n)
         np.testing.assert_array_equal(a, b)
         assert fa == fb
+    # few levels take a per-element path: same integers and flags as the array form on exact
+    # grid points, half-way cases (round half to even), NaN, the ends and out-of-range levels
+    for t in range(3000):
+        n = int(rng.integers(2, 3000))
+        av = rng.random(int(rng.integers(1, 9)))
+        mode = t % 6
+        if mode == 1:
+            av[rng.integers(av.size)] = np.nan
+        elif mode == 2:
+            av = np.round(av * (n - 1)) / (n - 1)
+        elif mode == 3:
+            av = (np.floor(av * (n - 1)) + 0.5) / (n - 1)
+        elif mode == 4:
+            av[rng.integers(av.size)] = rng.choice([0.0, 1.0, 1e-9, 1 - 1e-9])
+        elif mode == 5:
+            av = av * 3 - 1
+        a, fa = iv.order_indices(av, n)
+        with np.errstate(all="ignore"):
+            b, fb = iv._order_indices_array(av, n)
+        np.testing.assert_array_equal(a, b)
+        assert fa == fb and a.dtype == b.dtype
