@@ -449,6 +449,49 @@ def test_fuzz_shapes_against_oracle():
                 assert_allclose(dist, want, rtol=1e-11, atol=1e-13, err_msg=f"{name} n={n} m={m}")
 
 
+def test_fuzz_newer_statistics_against_numpy():
+    """The same fuzz for the statistics added after the first registry: quantiles (bit-exact),
+    the two-output linear fit, and differences of independent samples."""
+    import warnings
+    rng = np.random.default_rng(77)
+    special = [2, 3, 4, 5, 12, 13, 33, 193, 1025, 14337, 16385, 28671, 28672, 28673, 32769, 49152]
+    sizes = special + [int(v) for v in rng.integers(2, 60000, 14)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for k, n in enumerate(sizes):
+            a = np.round(rng.gamma(2.0, 1.0, n) + 0.1, int(rng.integers(1, 12)))
+            b = 0.3 * a + rng.gamma(3.0, 1.0, n) + 0.1
+            m = int(rng.integers(1, 30))
+            seed = int(rng.integers(0, 2**62))
+            kind = k % 3
+            if kind == 0:                      # quantile
+                q = float(rng.choice([0.0, 1.0, 0.5, rng.random(), rng.random()]))
+                idx = np.array(list(boot.bootstrap_indices(a, m, seed=seed))).reshape(m, n)
+                src = np.sort(a) if n > 28672 else a
+                want = np.sort(np.quantile(src[idx], q, axis=1))
+                _, dist = boot.ci(a, boot.quantile(q), n_samples=m, seed=seed, method="pi", return_dist=True)
+                assert_array_equal(dist, want, err_msg=f"quantile q={q} n={n} m={m}")
+            elif kind == 1 and n >= 3:         # linear fit
+                idx = np.array(list(boot.bootstrap_indices(a, m, seed=seed, n_arrays=2))).reshape(m, n)
+                keep = np.array([np.ptp(a[i]) > 0 for i in idx])      # a constant abscissa has no line
+                want = np.array([np.polyfit(a[i], b[i], 1) for i in idx[keep]])
+                _, dist = boot.ci((a, b), boot.linear_fit, n_samples=m, seed=seed, method="pi", return_dist=True)
+                got = _device.resample_stat([dev(a), dev(b)], _abi.STAT_LINEAR_FIT, boot.bootstrap._seed_key(seed),
+                                            0, m).cpu().numpy().T
+                assert_allclose(got[keep], want, rtol=1e-7, atol=1e-9, err_msg=f"linear_fit n={n} m={m}")
+                assert_array_equal(np.sort(got, axis=0), dist)
+            else:                              # difference of independent medians / stds
+                nb = int(rng.integers(2, 3000))
+                c = rng.standard_normal(nb)
+                f = [np.median, np.std][k % 2]
+                idx = list(boot.bootstrap_indices_independent((a, c), m, seed=seed))
+                src = np.sort(a) if (f is np.median and n > 28672) else a
+                want = np.sort([f(src[i]) - f(c[j]) for i, j in idx])
+                _, dist = boot.ci((a, c), boot.diff_of(f), n_samples=m, seed=seed, method="pi", return_dist=True,
+                                  multi="independent")
+                assert_allclose(dist, want, rtol=1e-10, atol=1e-12, err_msg=f"diff_of n={n} nb={nb} m={m}")
+
+
 def test_fuzz_column_kernels_against_oracle():
     """(N, D) data around the column-block widths (896 / 1792 / 3584 / 7168 rows), the median
     batch limits (4095 / 8191 rows) and odd / even segment lengths: K1c, K3c, K1m, K3m and the
