@@ -51,10 +51,13 @@ def to_device_f64(x, device=None):
     if isinstance(x, torch.Tensor):
         t = x
     else:
-        arr = np.array(x)            # the reference copies too (bootstrap.py:371, 379)
+        arr = np.asarray(x)          # no host copy: the transfer below is the copy
         if arr.dtype == object:
             raise TypeError("data must be numeric")
-        t = torch.from_numpy(np.ascontiguousarray(arr))
+        arr = np.ascontiguousarray(arr)
+        if not arr.flags.writeable:      # torch.from_numpy wants a writable buffer (it is only read)
+            arr = arr.copy()
+        t = torch.from_numpy(arr)
     dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
     if t.device.type != "cuda":
         if t.dtype != torch.float64:

@@ -85,20 +85,22 @@ def _is_tensor(x) -> bool:
 
 def _normalise(data, multi) -> Tuple[list, Any]:
     """multi validation and the data -> tuple-of-arrays step (bootstrap.py:362-379).
-    Arrays stay as given (numpy / torch); only shapes are inspected here."""
+    Arrays stay as given (numpy / torch); only shapes are inspected here.  The reference
+    copies its inputs at this point (np.array); here the copy that isolates the call from
+    the caller's buffer is the host-to-device transfer itself, so no host copy is made."""
     if multi not in [False, True, None, "independent", "paired"]:
         raise ValueError("Value `{}` for multi is not recognized.".format(multi))
     if multi is None:
         multi = bool(isinstance(data, tuple))
     if multi and isinstance(data, Iterable):
-        arrays = [x if _is_tensor(x) else np.array(x) for x in data]
+        arrays = [x if _is_tensor(x) else np.asarray(x) for x in data]
         lengths = [int(x.shape[0]) for x in arrays]
         if len(set(lengths)) > 1 and multi != "independent":
             raise ValueError(
                 "Data arrays have differing lengths {}, and ".format(lengths)
                 + "multi is not set to 'independent'.")
     else:
-        arrays = [data if _is_tensor(data) else np.array(data)]
+        arrays = [data if _is_tensor(data) else np.asarray(data)]
     return arrays, multi
 
 
