@@ -107,25 +107,72 @@ __global__ void __launch_bounds__(1024) psort_local_kernel(uint64_t* __restrict_
 // Sorted values and the row permutation of every column in two shared-memory friendly
 // layouts.  Sorted positions are cut into 32 lane segments of `seg` (even) positions:
 // position s = lane * seg + i.
-//   pairs[d][(i/2) * 32 + lane] (u32): rows at positions i (low half) and i+1 (high half)
+//   pairs[d][k * 32 + lane] (u32): two rows of lane's segment (low / high half), in the
+//                               bank-friendly visiting order of median_schedule_kernel
 //   lin  [d][s]                 (u16): row at position s
 // Slots past N point at the always-zero count slot N.
 __global__ void __launch_bounds__(256) median_pack_kernel(const uint64_t* __restrict__ keys,
                                                           const uint32_t* __restrict__ idx, int64_t n,
                                                           int64_t n_pad, int seg,
                                                           double* __restrict__ sorted_vals,
-                                                          uint32_t* __restrict__ pairs,
                                                           uint16_t* __restrict__ lin) {
   const int64_t d = blockIdx.y;
   const int64_t slots = (int64_t)seg * 32;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  uint16_t* pr = reinterpret_cast<uint16_t*>(pairs + d * (slots / 2));
   for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += stride) {
-    const int lane = (int)(s / seg), i = (int)(s % seg);
-    const uint16_t row = s < n ? (uint16_t)idx[d * n_pad + s] : (uint16_t)n;
-    pr[((int64_t)(i >> 1) * 32 + lane) * 2 + (i & 1)] = row;
-    lin[d * slots + s] = row;
+    lin[d * slots + s] = s < n ? (uint16_t)idx[d * n_pad + s] : (uint16_t)n;
     if (s < n) sorted_vals[d * n + s] = value_of(keys[d * n_pad + s]);
+  }
+}
+
+// The segment sums do not care in which order a lane visits the positions of its own
+// segment, so the visiting order is chosen to keep the count-table gathers of K1m off each
+// other's banks.  With B interleaved tables a row's counts are one 2B-byte load; the lanes
+// that share a shared-memory wavefront (8 for 16-byte loads, 16 for 8-byte, 32 for 2-byte)
+// are conflict-free when their rows differ in `bank_key`.  Lane l therefore wants key
+// (step + l) mod M for its first row of a step and (step + l + M/2) mod M for the second;
+// rows are handed out per key in sorted order while they last, what is left fills the gaps.
+__device__ __forceinline__ int bank_key(uint32_t row, int batch) {
+  return batch == 8 ? (int)(row & 7u) : (batch == 4 ? (int)(row & 15u) : (int)((row >> 1) & 31u));
+}
+
+__global__ void __launch_bounds__(128) median_schedule_kernel(const uint32_t* __restrict__ idx, int64_t n,
+                                                              int64_t n_pad, int seg, int batch,
+                                                              int64_t n_cols, uint32_t* __restrict__ pairs) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_cols * 32) return;
+  const int64_t d = g >> 5;
+  const int lane = (int)(g & 31);
+  const int M = batch == 8 ? 8 : (batch == 4 ? 16 : 32);
+  const int64_t base = (int64_t)lane * seg;
+  const uint32_t* col = idx + d * n_pad;
+  auto row_at = [&](int p) -> uint32_t { return base + p < n ? col[base + p] : (uint32_t)n; };
+  uint16_t* pr = reinterpret_cast<uint16_t*>(pairs + d * ((int64_t)seg * 16));
+  auto slot_ptr = [&](int s) -> uint16_t* { return pr + ((int64_t)(s >> 1) * 32 + lane) * 2 + (s & 1); };
+
+  int cursor[32];   // next unused position of each key inside the segment (seg: none left)
+  for (int k = 0; k < M; ++k) cursor[k] = seg;
+  for (int p = seg - 1; p >= 0; --p) cursor[bank_key(row_at(p), batch)] = p;
+  for (int s = 0; s < seg; ++s) {
+    const int want = ((s >> 1) + lane + (s & 1) * (M / 2)) & (M - 1);
+    const int p = cursor[want];
+    if (p < seg) {
+      *slot_ptr(s) = (uint16_t)row_at(p);
+      int q = p + 1;
+      while (q < seg && bank_key(row_at(q), batch) != want) ++q;
+      cursor[want] = q;
+    } else {
+      *slot_ptr(s) = 0xFFFFu;   // gap, filled below
+    }
+  }
+  int s = 0;
+  for (int k = 0; k < M; ++k) {
+    for (int p = cursor[k]; p < seg; ++p) {
+      const uint32_t r = row_at(p);
+      if (bank_key(r, batch) != k) continue;
+      while (*slot_ptr(s) != 0xFFFFu) ++s;
+      *slot_ptr(s) = (uint16_t)r;
+    }
   }
 }
 
@@ -172,10 +219,15 @@ struct K1mParams {
 
 // First sorted position whose cumulative draw count (resample b of the batch) exceeds k.
 // incl / excl: the lane's inclusive / exclusive segment prefix for that resample.
+// With k2 >= k (the second rank of an even-N median or of an interpolated quantile) the
+// same pass also looks for the first position whose cumulative count exceeds k2 and
+// returns it through *pos2 — or -1 when that position lies beyond the chunk that holds
+// the first one (the caller then searches for it separately; rare).
 template <int B>
 __device__ __forceinline__ int median_find(const uint16_t* __restrict__ cnt,
                                            const uint16_t* __restrict__ lin, int seg_len, int lane,
-                                           int b, uint32_t incl, uint32_t excl, uint32_t k) {
+                                           int b, uint32_t incl, uint32_t excl, uint32_t k,
+                                           uint32_t k2 = 0, int* pos2 = nullptr) {
   const uint32_t hit = __ballot_sync(0xffffffffu, incl > k);
   const int seg = __ffs(hit) - 1;                       // lane segment holding the crossing
   uint32_t running = __shfl_sync(0xffffffffu, excl, seg);
@@ -190,9 +242,16 @@ __device__ __forceinline__ int median_find(const uint16_t* __restrict__ cnt,
     }
     inc += running;
     const uint32_t h = __ballot_sync(0xffffffffu, inc > k);
-    if (h) return seg * seg_len + c0 + __ffs(h) - 1;
+    if (h) {
+      if (pos2) {
+        const uint32_t h2 = __ballot_sync(0xffffffffu, inc > k2);
+        *pos2 = h2 ? seg * seg_len + c0 + __ffs(h2) - 1 : -1;
+      }
+      return seg * seg_len + c0 + __ffs(h) - 1;
+    }
     running = __shfl_sync(0xffffffffu, inc, 31);
   }
+  if (pos2) *pos2 = -1;
   return seg * seg_len + seg_len - 1;   // unreachable when counts sum to N
 }
 
@@ -307,11 +366,15 @@ __global__ void __launch_bounds__(kMedThreads, 1) k1m_median_kernel(const K1mPar
             const uint32_t pi = inc[(b / 2) % NP], pa = acc[(b / 2) % NP];
             const uint32_t incl = (b & 1) ? (pi >> 16) : (pi & 0xFFFFu);
             const uint32_t sum = (b & 1) ? (pa >> 16) : (pa & 0xFFFFu);
-            const int s_hi = median_find<B>(cnt16, lin, seg_len, lane, b, incl, incl - sum, k_hi);
-            double med = sv[s_hi];
+            double med;
             if (two) {
-              const int s_lo = median_find<B>(cnt16, lin, seg_len, lane, b, incl, incl - sum, k_lo);
-              med = rank_combine(P.rule, sv[s_lo], med);
+              // one pass finds the lower rank and, almost always, the upper one next to it
+              int s_hi;
+              const int s_lo = median_find<B>(cnt16, lin, seg_len, lane, b, incl, incl - sum, k_lo, k_hi, &s_hi);
+              if (s_hi < 0) s_hi = median_find<B>(cnt16, lin, seg_len, lane, b, incl, incl - sum, k_hi);
+              med = rank_combine(P.rule, sv[s_lo], sv[s_hi]);
+            } else {
+              med = sv[median_find<B>(cnt16, lin, seg_len, lane, b, incl, incl - sum, k_hi)];
             }
             if (lane == 0) P.out[(d0 + j) * P.n_local + rb + b] = med;
           }
@@ -595,6 +658,11 @@ inline int psort_pairs(uint64_t* keys, uint32_t* idx, int64_t n_pad, unsigned n_
 }
 
 // sorts every column and packs sorted values + permutation into the workspace
+inline int median_batch(int64_t n_rows) {
+  // eight / four interleaved count tables when they fit in 64 KB, else one resample at a time
+  return (n_rows + 1) * 16 <= 64 * 1024 ? 8 : ((n_rows + 1) * 8 <= 64 * 1024 ? 4 : 1);
+}
+
 inline int median_prepare(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, MedianWs& w,
                           cudaStream_t s) {
   const int64_t n_pad = w.n_pad;
@@ -611,7 +679,10 @@ inline int median_prepare(const double* data, int64_t n_rows, int64_t n_cols, in
     if (rc) return rc;
     const dim3 gpack((unsigned)((w.seg * 32 + 255) / 256), nd);
     median_pack_kernel<<<gpack, 256, 0, s>>>(kc, ic, n_rows, n_pad, w.seg, w.sorted_vals + d0 * n_rows,
-                                             w.pairs + d0 * w.seg * 16, w.lin + d0 * w.seg * 32);
+                                             w.lin + d0 * w.seg * 32);
+    B2_LAUNCH_CHECK();
+    median_schedule_kernel<<<(unsigned)(((int64_t)nd * 32 + 127) / 128), 128, 0, s>>>(
+        ic, n_rows, n_pad, w.seg, median_batch(n_rows), (int64_t)nd, w.pairs + d0 * w.seg * 16);
     B2_LAUNCH_CHECK();
   }
   return 0;
@@ -640,8 +711,7 @@ inline int median_resample(const double* data, int64_t n_rows, int64_t n_cols, i
   P.n_rows = n_rows;
   P.n_cols = n_cols;
   P.seg = w.seg;
-  // eight / four interleaved count tables when they fit in 64 KB, else one resample at a time
-  const int batch = (n_rows + 1) * 16 <= 64 * 1024 ? 8 : ((n_rows + 1) * 8 <= 64 * 1024 ? 4 : 1);
+  const int batch = median_batch(n_rows);
   P.count_words = (int32_t)((((n_rows + 1) * batch + 1) / 2 + 31) & ~(int64_t)31);
   const int64_t cnt_bytes = (int64_t)P.count_words * 4;
   const int64_t perm_bytes = (int64_t)w.seg * 32 * 4;      // pairs + linear copy
