@@ -255,6 +255,76 @@ __device__ __forceinline__ int median_find(const uint16_t* __restrict__ cnt,
   return seg * seg_len + seg_len - 1;   // unreachable when counts sum to N
 }
 
+// Four resamples at a time for short segments (seg_len <= 64): eight lanes per resample,
+// sub-lane u of group g scanning positions u*P .. u*P+P-1 (P = ceil(seg_len / 8)) of the
+// segment that holds resample (b0 + g)'s crossing.  incl4 / excl4: this lane's inclusive /
+// exclusive segment prefixes for resamples b0 .. b0+3.  Every lane returns the positions
+// found for ITS group's resample; *pos_hi = -1 when the second rank lies beyond that
+// segment (the caller falls back to median_find for it).
+template <int B>
+__device__ __forceinline__ int median_find4(const uint16_t* __restrict__ cnt,
+                                            const uint16_t* __restrict__ lin, int seg_len, int lane, int b0,
+                                            const uint32_t* incl4, const uint32_t* excl4, uint32_t k_lo,
+                                            uint32_t k_hi, bool two, int* pos_hi) {
+  const int g = lane >> 3, u = lane & 7;
+  int my_seg = 0;
+  uint32_t my_run = 0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const uint32_t hit = __ballot_sync(0xffffffffu, incl4[r] > k_lo);
+    const int sg = hit ? __ffs(hit) - 1 : 0;
+    const uint32_t run = __shfl_sync(0xffffffffu, excl4[r], sg);
+    if (g == r) {
+      my_seg = sg;
+      my_run = run;
+    }
+  }
+  const int P = (seg_len + 7) >> 3;
+  const uint16_t* ls = lin + my_seg * seg_len;
+  const int p0 = u * P;
+  uint32_t c[8];
+  uint32_t local = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    c[i] = (i < P && p0 + i < seg_len) ? (uint32_t)cnt[(int)ls[p0 + i] * B + (b0 + g)] : 0u;
+    local += c[i];
+  }
+  uint32_t inc = local;
+#pragma unroll
+  for (int off = 1; off < 8; off <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off, 8);
+    if (u >= off) inc += o;
+  }
+  const uint32_t cum_incl = my_run + inc, cum_excl = cum_incl - local;
+  // walk of the owning sub-lane: first of its positions whose cumulative count exceeds k
+  auto walk = [&](uint32_t k) {
+    uint32_t running = cum_excl;
+    int pos = p0 + P - 1;
+    bool found = false;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      running += c[i];
+      if (!found && i < P && running > k) {
+        pos = p0 + i;
+        found = true;
+      }
+    }
+    return pos;
+  };
+  const uint32_t m_lo = (__ballot_sync(0xffffffffu, cum_incl > k_lo) >> (8 * g)) & 0xFFu;
+  const int own_lo = m_lo ? __ffs(m_lo) - 1 : 7;
+  const int pl = __shfl_sync(0xffffffffu, walk(k_lo), 8 * g + own_lo);
+  int ph = -1;
+  if (two) {
+    const uint32_t m_hi = (__ballot_sync(0xffffffffu, cum_incl > k_hi) >> (8 * g)) & 0xFFu;
+    const int own_hi = m_hi ? __ffs(m_hi) - 1 : 7;
+    const int w = __shfl_sync(0xffffffffu, walk(k_hi), 8 * g + own_hi);
+    ph = m_hi ? my_seg * seg_len + w : -1;
+  }
+  *pos_hi = ph;
+  return my_seg * seg_len + pl;
+}
+
 // B = resamples whose draw-count tables are interleaved in shared memory
 // (cnt[row * B + b], u16): one wide load per sorted position serves B resamples and the
 // B segment sums are carried packed (two u16 per 32-bit add).
@@ -360,23 +430,58 @@ __global__ void __launch_bounds__(kMedThreads, 1) k1m_median_kernel(const K1mPar
           }
         }
         const double* sv = P.sorted_vals + (d0 + j) * P.n_rows;
+        auto prefix_of = [&](int b, uint32_t* incl, uint32_t* excl) {
+          const uint32_t pi = inc[(b / 2) % NP], pa = acc[(b / 2) % NP];
+          *incl = (b & 1) ? (pi >> 16) : (pi & 0xFFFFu);
+          *excl = *incl - ((b & 1) ? (pa >> 16) : (pa & 0xFFFFu));
+        };
+        if (B >= 4 && seg_len <= 64) {
+          // short segments: four resamples per pass, eight lanes each
 #pragma unroll
-        for (int b = 0; b < B; ++b) {
-          if (b < nb) {
-            const uint32_t pi = inc[(b / 2) % NP], pa = acc[(b / 2) % NP];
-            const uint32_t incl = (b & 1) ? (pi >> 16) : (pi & 0xFFFFu);
-            const uint32_t sum = (b & 1) ? (pa >> 16) : (pa & 0xFFFFu);
-            double med;
-            if (two) {
-              // one pass finds the lower rank and, almost always, the upper one next to it
+          for (int b0 = 0; b0 < B; b0 += 4) {
+            if (b0 < nb) {
+              uint32_t incl4[4], excl4[4];
+#pragma unroll
+              for (int r = 0; r < 4; ++r) prefix_of(b0 + r, &incl4[r], &excl4[r]);
               int s_hi;
-              const int s_lo = median_find<B>(cnt16, lin, seg_len, lane, b, incl, incl - sum, k_lo, k_hi, &s_hi);
-              if (s_hi < 0) s_hi = median_find<B>(cnt16, lin, seg_len, lane, b, incl, incl - sum, k_hi);
-              med = rank_combine(P.rule, sv[s_lo], sv[s_hi]);
-            } else {
-              med = sv[median_find<B>(cnt16, lin, seg_len, lane, b, incl, incl - sum, k_hi)];
+              const int s_lo = median_find4<B>(cnt16, lin, seg_len, lane, b0, incl4, excl4, k_lo, k_hi, two, &s_hi);
+              const int g = lane >> 3;
+              const bool valid = b0 + g < nb;
+              if (two) {
+                // second rank beyond the crossing segment (rare): full-warp search for that resample
+                const uint32_t miss = __ballot_sync(0xffffffffu, valid && s_hi < 0);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  if ((miss >> (8 * r)) & 1u) {
+                    const int f = median_find<B>(cnt16, lin, seg_len, lane, b0 + r, incl4[r], excl4[r], k_hi);
+                    if (g == r) s_hi = f;
+                  }
+                }
+              }
+              if (valid && (lane & 7) == 0) {
+                const double med = two ? rank_combine(P.rule, sv[s_lo], sv[s_hi]) : sv[s_lo];
+                P.out[(d0 + j) * P.n_local + rb + b0 + g] = med;
+              }
             }
-            if (lane == 0) P.out[(d0 + j) * P.n_local + rb + b] = med;
+          }
+        } else {
+#pragma unroll
+          for (int b = 0; b < B; ++b) {
+            if (b < nb) {
+              uint32_t incl, excl;
+              prefix_of(b, &incl, &excl);
+              double med;
+              if (two) {
+                // one pass finds the lower rank and, almost always, the upper one next to it
+                int s_hi;
+                const int s_lo = median_find<B>(cnt16, lin, seg_len, lane, b, incl, excl, k_lo, k_hi, &s_hi);
+                if (s_hi < 0) s_hi = median_find<B>(cnt16, lin, seg_len, lane, b, incl, excl, k_hi);
+                med = rank_combine(P.rule, sv[s_lo], sv[s_hi]);
+              } else {
+                med = sv[median_find<B>(cnt16, lin, seg_len, lane, b, incl, excl, k_hi)];
+              }
+              if (lane == 0) P.out[(d0 + j) * P.n_local + rb + b] = med;
+            }
           }
         }
       }
