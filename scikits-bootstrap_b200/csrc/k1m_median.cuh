@@ -215,6 +215,9 @@ struct K1mParams {
   int32_t count_words;         // uint32 words of one count table: ceil((N + 1) * B / 2), padded
   const int64_t* indices;      // parity mode: caller-supplied index sets [n_local][N], else null
   RankRule rule;
+  int32_t tables;              // short-column kernel: groups of 8 count tables resident at once
+  int32_t col_block;           // short-column kernel: columns per work item
+  int32_t n_colblocks;
 };
 
 // First sorted position whose cumulative draw count (resample b of the batch) exceeds k.
@@ -487,6 +490,141 @@ __global__ void __launch_bounds__(kMedThreads, 1) k1m_median_kernel(const K1mPar
       }
       __syncthreads();
     }
+  }
+}
+
+// ---- K1m for short columns (segments of at most 64 positions, eight interleaved tables) ----
+// The draw-count tables depend on the resample only, so rebuilding them for every group of
+// resident columns (k1m_median_kernel) repeats the index draws D/32 times.  Here a work item
+// is (block of many columns) x (T*8 resamples): the CTA builds T groups of eight interleaved
+// tables once, then every warp walks its columns of the block: the column's sorted-order
+// permutation is read straight from global memory (coalesced; `lin` is staged in a private
+// 64*seg-byte slice for the searches) and used against all T table groups.
+__global__ void __launch_bounds__(kMedThreads, 1) k1m_short_kernel(const K1mParams P) {
+  constexpr int B = 8, NP = 4;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  volatile int* s_item = reinterpret_cast<volatile int*>(smem_raw);
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem_raw + 128);                 // T table groups
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int seg_len = P.seg;
+  const int pair_words = seg_len * 16;             // per column (pairs, and lin as u32 words)
+  uint32_t* s_lin32 = s_cnt + (size_t)P.tables * P.count_words + (size_t)warp * pair_words;
+  const uint16_t* s_lin = reinterpret_cast<const uint16_t*>(s_lin32);
+  const int n = (int)P.n_rows;
+  const uint32_t thresh = lemire_threshold((uint32_t)n);
+  const int n_blocks = (n + 3) / 4;
+  const uint32_t k_hi = (uint32_t)P.rule.k_hi, k_lo = (uint32_t)P.rule.k_lo;
+  const bool two = k_lo != k_hi;
+  const int res_per_item = P.tables * B;
+
+  for (;;) {
+    if (tid == 0) *s_item = atomicAdd(P.work_counter, 1);
+    __syncthreads();
+    const int64_t item = *s_item;
+    __syncthreads();
+    if (item >= P.n_items) break;
+    const int rc = (int)(item / P.n_colblocks);
+    const int cb = (int)(item - (int64_t)rc * P.n_colblocks);
+    const int64_t r_begin = (int64_t)rc * res_per_item;
+    const int nres = (int)min((int64_t)res_per_item, P.n_local - r_begin);
+    const int64_t c_begin = (int64_t)cb * P.col_block;
+    const int64_t c_end = min(c_begin + (int64_t)P.col_block, P.n_cols);
+
+    for (int e = tid; e < P.tables * P.count_words; e += kMedThreads) s_cnt[e] = 0u;
+    __syncthreads();
+    auto bump = [&](int r, uint32_t row) {       // resample r of the item: table group r / 8, slot r % 8
+      const uint32_t slot = row * B + (uint32_t)(r & 7);
+      atomicAdd(s_cnt + (size_t)(r >> 3) * P.count_words + (slot >> 1), 1u << ((slot & 1u) * 16));
+    };
+    if (P.indices) {
+      for (int e = tid; e < nres * n; e += kMedThreads) {
+        const int r = e / n, pos = e - r * n;
+        bump(r, (uint32_t)P.indices[(r_begin + r) * (int64_t)n + pos]);
+      }
+    } else {
+      for (int e = tid; e < nres * n_blocks; e += kMedThreads) {
+        const int r = e / n_blocks, q = e - r * n_blocks;
+        const Stream st = make_stream(P.seed, P.resample_lo + r_begin + r, 0u, kPurposeIndex);
+        lemire_block<true>(st, (uint32_t)q, (uint32_t)n, thresh, (int64_t)n,
+                           [&](int, int64_t, uint32_t idx) { bump(r, idx); });
+      }
+    }
+    __syncthreads();
+
+    const int n_groups = (nres + B - 1) / B;
+    for (int64_t j = c_begin + warp; j < c_end; j += kMedWarps) {
+      // stage this column's linear permutation in the warp's slice
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(P.lin + j * (int64_t)seg_len * 32);
+        uint4* dst = reinterpret_cast<uint4*>(s_lin32);
+        for (int w = lane; w < pair_words / 4; w += 32) dst[w] = __ldg(src + w);
+      }
+      __syncwarp();
+      const uint32_t* pp = P.pairs + j * (int64_t)pair_words;
+      const double* sv = P.sorted_vals + j * P.n_rows;
+      for (int t = 0; t < n_groups; ++t) {
+        const int nb = min(B, nres - t * B);
+        const uint16_t* cnt16 = reinterpret_cast<const uint16_t*>(s_cnt + (size_t)t * P.count_words);
+        uint32_t acc[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) acc[p] = 0u;
+#pragma unroll 4
+        for (int i2 = 0; i2 < seg_len / 2; ++i2) {
+          const uint32_t pr = __ldg(pp + i2 * 32 + lane);
+          const uint32_t r0 = pr & 0xFFFFu, r1 = pr >> 16;
+          const uint4 a = *reinterpret_cast<const uint4*>(cnt16 + r0 * 8);
+          const uint4 c = *reinterpret_cast<const uint4*>(cnt16 + r1 * 8);
+          acc[0] += a.x + c.x;
+          acc[1] += a.y + c.y;
+          acc[2] += a.z + c.z;
+          acc[3] += a.w + c.w;
+        }
+        uint32_t inc[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) inc[p] = acc[p];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc[p], off);
+            if (lane >= off) inc[p] += o;
+          }
+        }
+#pragma unroll
+        for (int b0 = 0; b0 < B; b0 += 4) {
+          if (b0 < nb) {
+            uint32_t incl4[4], excl4[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const int b = b0 + r;
+              const uint32_t pi = inc[b / 2], pa = acc[b / 2];
+              incl4[r] = (b & 1) ? (pi >> 16) : (pi & 0xFFFFu);
+              excl4[r] = incl4[r] - ((b & 1) ? (pa >> 16) : (pa & 0xFFFFu));
+            }
+            int s_hi;
+            const int s_lo = median_find4<B>(cnt16, s_lin, seg_len, lane, b0, incl4, excl4, k_lo, k_hi, two, &s_hi);
+            const int g = lane >> 3;
+            const bool valid = b0 + g < nb;
+            if (two) {
+              const uint32_t miss = __ballot_sync(0xffffffffu, valid && s_hi < 0);
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                if ((miss >> (8 * r)) & 1u) {
+                  const int f = median_find<B>(cnt16, s_lin, seg_len, lane, b0 + r, incl4[r], excl4[r], k_hi);
+                  if (g == r) s_hi = f;
+                }
+              }
+            }
+            if (valid && (lane & 7) == 0) {
+              const double med = two ? rank_combine(P.rule, sv[s_lo], sv[s_hi]) : sv[s_lo];
+              P.out[j * P.n_local + r_begin + t * B + b0 + g] = med;
+            }
+          }
+        }
+      }
+      __syncwarp();   // the slice is overwritten by the next column
+    }
+    __syncthreads();
   }
 }
 
@@ -820,19 +958,7 @@ inline int median_resample(const double* data, int64_t n_rows, int64_t n_cols, i
   P.count_words = (int32_t)((((n_rows + 1) * batch + 1) / 2 + 31) & ~(int64_t)31);
   const int64_t cnt_bytes = (int64_t)P.count_words * 4;
   const int64_t perm_bytes = (int64_t)w.seg * 32 * 4;      // pairs + linear copy
-  int64_t cpi = (kSmemDataBytes - 128 - cnt_bytes) / perm_bytes;
-  if (cpi < 1) return fail(B200BOOT_EUNSUPPORTED, "median: column does not fit in shared memory");
-  cpi = std::min<int64_t>(std::min<int64_t>(cpi, 32), n_cols);
-  P.cols_per_item = (int32_t)cpi;
-  P.n_colchunks = (int32_t)((n_cols + cpi - 1) / cpi);
   const int sms = sm_count();
-  int64_t want_r = ((int64_t)sms * 8 + P.n_colchunks - 1) / P.n_colchunks;
-  int64_t rchunk = (n_local + want_r - 1) / want_r;
-  rchunk = ((rchunk + batch - 1) / batch) * batch;
-  P.rchunk = (int32_t)std::min<int64_t>(std::max<int64_t>(rchunk, batch), 1 << 20);
-  P.n_rchunks = (int32_t)((n_local + P.rchunk - 1) / P.rchunk);
-  P.n_items = (int64_t)P.n_colchunks * P.n_rchunks;
-  if (P.n_items >= ((int64_t)1 << 31)) return fail(B200BOOT_EINVAL, "too many work items");
   P.seed = seed;
   P.resample_lo = resample_lo;
   P.n_local = n_local;
@@ -841,7 +967,6 @@ inline int median_resample(const double* data, int64_t n_rows, int64_t n_cols, i
   P.indices = indices;
   P.rule = rule;
   B2_CUDA(cudaMemsetAsync(w.work_counter, 0, 256, s));
-  const size_t smem = 128 + (size_t)cnt_bytes + (size_t)cpi * perm_bytes;
   static bool configured[64] = {false};
   int dev = 0;
   B2_CUDA(cudaGetDevice(&dev));
@@ -852,8 +977,46 @@ inline int median_resample(const double* data, int64_t n_rows, int64_t n_cols, i
                                  (int)(kSmemHeader + kSmemDataBytes)));
     B2_CUDA(cudaFuncSetAttribute(k1m_median_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(kSmemHeader + kSmemDataBytes)));
+    B2_CUDA(cudaFuncSetAttribute(k1m_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(kSmemHeader + kSmemDataBytes)));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
+
+  // short columns: tables for many resamples stay resident, columns stream through
+  const int64_t slice_bytes = (int64_t)w.seg * 64 * kMedWarps;            // one lin slice per warp
+  const int64_t tables = std::min<int64_t>(8, (kSmemDataBytes - 128 - slice_bytes) / cnt_bytes);
+  if (batch == 8 && w.seg <= 64 && tables >= 2) {
+    P.tables = (int32_t)tables;
+    const int64_t res_per_item = tables * 8;
+    P.n_rchunks = (int32_t)((n_local + res_per_item - 1) / res_per_item);
+    int64_t ncb = ((int64_t)sms * 4 + P.n_rchunks - 1) / P.n_rchunks;
+    ncb = std::max<int64_t>(1, std::min<int64_t>(ncb, (n_cols + kMedWarps - 1) / kMedWarps));
+    int64_t cbk = (n_cols + ncb - 1) / ncb;
+    cbk = ((cbk + kMedWarps - 1) / kMedWarps) * kMedWarps;
+    P.col_block = (int32_t)cbk;
+    P.n_colblocks = (int32_t)((n_cols + cbk - 1) / cbk);
+    P.n_items = (int64_t)P.n_rchunks * P.n_colblocks;
+    if (P.n_items >= ((int64_t)1 << 31)) return fail(B200BOOT_EINVAL, "too many work items");
+    const size_t smem = 128 + (size_t)tables * cnt_bytes + (size_t)slice_bytes;
+    const int grid = (int)std::min<int64_t>(sms, P.n_items);
+    k1m_short_kernel<<<grid, kMedThreads, smem, s>>>(P);
+    B2_LAUNCH_CHECK();
+    return 0;
+  }
+
+  int64_t cpi = (kSmemDataBytes - 128 - cnt_bytes) / perm_bytes;
+  if (cpi < 1) return fail(B200BOOT_EUNSUPPORTED, "median: column does not fit in shared memory");
+  cpi = std::min<int64_t>(std::min<int64_t>(cpi, 32), n_cols);
+  P.cols_per_item = (int32_t)cpi;
+  P.n_colchunks = (int32_t)((n_cols + cpi - 1) / cpi);
+  int64_t want_r = ((int64_t)sms * 8 + P.n_colchunks - 1) / P.n_colchunks;
+  int64_t rchunk = (n_local + want_r - 1) / want_r;
+  rchunk = ((rchunk + batch - 1) / batch) * batch;
+  P.rchunk = (int32_t)std::min<int64_t>(std::max<int64_t>(rchunk, batch), 1 << 20);
+  P.n_rchunks = (int32_t)((n_local + P.rchunk - 1) / P.rchunk);
+  P.n_items = (int64_t)P.n_colchunks * P.n_rchunks;
+  if (P.n_items >= ((int64_t)1 << 31)) return fail(B200BOOT_EINVAL, "too many work items");
+  const size_t smem = 128 + (size_t)cnt_bytes + (size_t)cpi * perm_bytes;
   const int grid = (int)std::min<int64_t>(sms, P.n_items);
   if (batch == 8)
     k1m_median_kernel<8><<<grid, kMedThreads, smem, s>>>(P);
