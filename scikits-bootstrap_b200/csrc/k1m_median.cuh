@@ -264,7 +264,7 @@ __device__ __forceinline__ int median_find(const uint16_t* __restrict__ cnt,
 // exclusive segment prefixes for resamples b0 .. b0+3.  Every lane returns the positions
 // found for ITS group's resample; *pos_hi = -1 when the second rank lies beyond that
 // segment (the caller falls back to median_find for it).
-template <int B>
+template <int B, int PMAX>
 __device__ __forceinline__ int median_find4(const uint16_t* __restrict__ cnt,
                                             const uint16_t* __restrict__ lin, int seg_len, int lane, int b0,
                                             const uint32_t* incl4, const uint32_t* excl4, uint32_t k_lo,
@@ -282,14 +282,15 @@ __device__ __forceinline__ int median_find4(const uint16_t* __restrict__ cnt,
       my_run = run;
     }
   }
-  const int P = (seg_len + 7) >> 3;
-  const uint16_t* ls = lin + my_seg * seg_len;
-  const int p0 = u * P;
-  uint32_t c[8];
+  const int P = (seg_len + 7) >> 3;              // <= PMAX
+  const uint16_t* ls = lin + my_seg * seg_len + u * P;
+  const uint16_t* cb = cnt + (b0 + g);
+  const int left = seg_len - u * P;              // positions of the segment from this sub-lane on
+  uint32_t c[PMAX];
   uint32_t local = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    c[i] = (i < P && p0 + i < seg_len) ? (uint32_t)cnt[(int)ls[p0 + i] * B + (b0 + g)] : 0u;
+  for (int i = 0; i < PMAX; ++i) {
+    c[i] = (i < P && i < left) ? (uint32_t)cb[(int)ls[i] * B] : 0u;
     local += c[i];
   }
   uint32_t inc = local;
@@ -298,34 +299,36 @@ __device__ __forceinline__ int median_find4(const uint16_t* __restrict__ cnt,
     const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off, 8);
     if (u >= off) inc += o;
   }
-  const uint32_t cum_incl = my_run + inc, cum_excl = cum_incl - local;
-  // walk of the owning sub-lane: first of its positions whose cumulative count exceeds k
-  auto walk = [&](uint32_t k) {
-    uint32_t running = cum_excl;
-    int pos = p0 + P - 1;
-    bool found = false;
+  const uint32_t cum_incl = my_run + inc;
+  // every sub-lane walks its own positions once for both ranks; the owners' results are taken
+  uint32_t running = cum_incl - local;
+  int w_lo = P - 1, w_hi = P - 1;
+  bool f_lo = false, f_hi = false;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      running += c[i];
-      if (!found && i < P && running > k) {
-        pos = p0 + i;
-        found = true;
-      }
+  for (int i = 0; i < PMAX; ++i) {
+    running += c[i];
+    if (!f_lo && running > k_lo) {
+      w_lo = i;
+      f_lo = true;
     }
-    return pos;
-  };
+    if (!f_hi && running > k_hi) {
+      w_hi = i;
+      f_hi = true;
+    }
+  }
+  const int base = my_seg * seg_len + u * P;
   const uint32_t m_lo = (__ballot_sync(0xffffffffu, cum_incl > k_lo) >> (8 * g)) & 0xFFu;
   const int own_lo = m_lo ? __ffs(m_lo) - 1 : 7;
-  const int pl = __shfl_sync(0xffffffffu, walk(k_lo), 8 * g + own_lo);
+  const int pl = __shfl_sync(0xffffffffu, base + w_lo, 8 * g + own_lo);
   int ph = -1;
   if (two) {
     const uint32_t m_hi = (__ballot_sync(0xffffffffu, cum_incl > k_hi) >> (8 * g)) & 0xFFu;
     const int own_hi = m_hi ? __ffs(m_hi) - 1 : 7;
-    const int w = __shfl_sync(0xffffffffu, walk(k_hi), 8 * g + own_hi);
-    ph = m_hi ? my_seg * seg_len + w : -1;
+    const int w = __shfl_sync(0xffffffffu, base + w_hi, 8 * g + own_hi);
+    ph = m_hi ? w : -1;
   }
   *pos_hi = ph;
-  return my_seg * seg_len + pl;
+  return pl;
 }
 
 // B = resamples whose draw-count tables are interleaved in shared memory
@@ -447,7 +450,9 @@ __global__ void __launch_bounds__(kMedThreads, 1) k1m_median_kernel(const K1mPar
 #pragma unroll
               for (int r = 0; r < 4; ++r) prefix_of(b0 + r, &incl4[r], &excl4[r]);
               int s_hi;
-              const int s_lo = median_find4<B>(cnt16, lin, seg_len, lane, b0, incl4, excl4, k_lo, k_hi, two, &s_hi);
+              const int s_lo = seg_len <= 32
+                                   ? median_find4<B, 4>(cnt16, lin, seg_len, lane, b0, incl4, excl4, k_lo, k_hi, two, &s_hi)
+                                   : median_find4<B, 8>(cnt16, lin, seg_len, lane, b0, incl4, excl4, k_lo, k_hi, two, &s_hi);
               const int g = lane >> 3;
               const bool valid = b0 + g < nb;
               if (two) {
@@ -602,7 +607,9 @@ __global__ void __launch_bounds__(kMedThreads, 1) k1m_short_kernel(const K1mPara
               excl4[r] = incl4[r] - ((b & 1) ? (pa >> 16) : (pa & 0xFFFFu));
             }
             int s_hi;
-            const int s_lo = median_find4<B>(cnt16, s_lin, seg_len, lane, b0, incl4, excl4, k_lo, k_hi, two, &s_hi);
+            const int s_lo = seg_len <= 32
+                                 ? median_find4<B, 4>(cnt16, s_lin, seg_len, lane, b0, incl4, excl4, k_lo, k_hi, two, &s_hi)
+                                 : median_find4<B, 8>(cnt16, s_lin, seg_len, lane, b0, incl4, excl4, k_lo, k_hi, two, &s_hi);
             const int g = lane >> 3;
             const bool valid = b0 + g < nb;
             if (two) {
