@@ -139,11 +139,14 @@ typedef struct b200boot_rank_rule {
 /* K1m — column-batched order statistic: data float64[N][n_cols] row-major
  * (ld = row stride in elements); every column shares one index set per
  * resample, as x[indices] does for 2-D data at bootstrap.py:431.
- * stat_out: float64[n_cols][n_local] (column-major as everywhere). */
+ * stat_out: float64[n_cols][n_local] (column-major as everywhere).
+ * jack_out (optional, may be NULL): float64[n_cols][8] as b200boot_jackknife_median_columns —
+ * the columns are sorted for the resampling anyway, so the leave-one-out summary
+ * (bootstrap.py:595-615) comes with one more small launch instead of a second sort. */
 int b200boot_resample_median_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld,
                                      uint64_t seed, int64_t resample_lo, int64_t resample_hi,
                                      double* stat_out, void* ws, size_t ws_bytes, void* stream,
-                                     const b200boot_rank_rule* rule);
+                                     const b200boot_rank_rule* rule, double* jack_out);
 
 /* K1m in parity mode: index sets supplied by the caller, int64[n_sets][N]. */
 int b200boot_resample_median_columns_indexed(const double* data, int64_t n_rows, int64_t n_cols,

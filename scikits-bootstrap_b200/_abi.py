@@ -48,7 +48,7 @@ SIGNATURES = {
     "b200boot_columns_block_width": (_int, [_int, _i64]),
     "b200boot_resample_stat_columns": (_int, [_vp, _i64, _i64, _i64, _int, _u64, _i64, _i64, _vp, _vp, _sz, _vp]),
     "b200boot_jackknife_columns": (_int, [_vp, _i64, _i64, _i64, _int, _vp, _vp]),
-    "b200boot_resample_median_columns": (_int, [_vp, _i64, _i64, _i64, _u64, _i64, _i64, _vp, _vp, _sz, _vp, _vp]),
+    "b200boot_resample_median_columns": (_int, [_vp, _i64, _i64, _i64, _u64, _i64, _i64, _vp, _vp, _sz, _vp, _vp, _vp]),
     "b200boot_resample_median_columns_indexed": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _sz, _vp, _vp]),
     "b200boot_resample_median_sorted": (_int, [_vp, _i64, _u64, _i64, _i64, _vp, _vp, _sz, _vp, _vp]),
     "b200boot_jackknife_median_sorted": (_int, [_vp, _i64, _vp, _vp, _vp]),

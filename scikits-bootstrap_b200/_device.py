@@ -241,16 +241,19 @@ def _rule_ptr(rule):
     return None if rule is None else C.cast(C.pointer(rule), C.c_void_p)
 
 
-def resample_median_columns(data2d, seed: int, lo: int, hi: int, rule=None):
-    """K1m: data float64[N][D] -> float64[D][hi-lo]."""
+def resample_median_columns(data2d, seed: int, lo: int, hi: int, rule=None, with_jackknife: bool = False):
+    """K1m: data float64[N][D] -> float64[D][hi-lo]; with_jackknife: also the K3m summary
+    float64[D][8] of the same (already sorted) columns, returned as a second tensor."""
     torch = _torch()
     n_rows, n_cols = data2d.shape
     out = torch.empty((n_cols, hi - lo), dtype=torch.float64, device=data2d.device)
+    jack = torch.empty((n_cols, 8), dtype=torch.float64, device=data2d.device) if with_jackknife else None
     ws, wsz = workspace_for(_abi.STAT_MEDIAN, n_rows, 1, n_cols, hi - lo, 1)
     _abi.check(_abi.lib().b200boot_resample_median_columns(data2d.data_ptr(), n_rows, n_cols, data2d.stride(0),
                                                            seed, lo, hi, out.data_ptr(), ws, wsz, stream_ptr(),
-                                                           _rule_ptr(rule)))
-    return out
+                                                           _rule_ptr(rule),
+                                                           jack.data_ptr() if with_jackknife else None))
+    return (out, jack) if with_jackknife else out
 
 
 def resample_median_columns_indexed(data2d, indices, rule=None):

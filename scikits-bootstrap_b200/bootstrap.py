@@ -144,6 +144,7 @@ class _Run:
         self._jack = None
         self._sorted_vals = None
         self._parts = None
+        self._jack_dev = None
         # rank statistics: which order statistics (None: np.median's)
         self.rule = _device.rank_rule(self.dev[0].shape[0], spec.q) if spec.stat_id == _abi.STAT_MEDIAN else None
 
@@ -199,6 +200,11 @@ class _Run:
                     _device.resample_median_sorted(cols[d], self.key, lo, hi, out=out[d:d + 1], rule=self.rule)
                 return out
             data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
+            if hi > lo:
+                # the columns are sorted for the resampling anyway: take the jackknife summary along
+                out, self._jack_dev = _device.resample_median_columns(data2d, self.key, lo, hi, rule=self.rule,
+                                                                      with_jackknife=True)
+                return out
             return _device.resample_median_columns(data2d, self.key, lo, hi, rule=self.rule)
         if spec.n_out > 1:
             return _device.resample_stat([a.reshape(-1) for a in self.dev], spec.stat_id, self.key, lo, hi)
@@ -266,6 +272,8 @@ class _Run:
         elif spec.stat_id == _abi.STAT_MEDIAN:
             if self._long_median():
                 j = torch.cat([_device.jackknife_median_sorted(c, rule=self.rule) for c in self._sorted()])
+            elif self._jack_dev is not None:
+                j = self._jack_dev
             else:
                 data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
                 j = _device.jackknife_median_columns(data2d, rule=self.rule)

@@ -680,11 +680,11 @@ int rank_rules(const b200boot_rank_rule* rule, int64_t n_rows, RankRule* full, R
 int b200boot_resample_median_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld,
                                      uint64_t seed, int64_t resample_lo, int64_t resample_hi,
                                      double* stat_out, void* ws, size_t ws_bytes, void* stream,
-                                     const b200boot_rank_rule* rule) {
+                                     const b200boot_rank_rule* rule, double* jack_out) {
   RankRule full, loo;
   if (int rc = rank_rules(rule, n_rows, &full, &loo)) return rc;
   return median_resample(data, n_rows, n_cols, ld, seed, resample_lo, resample_hi, stat_out, ws,
-                         ws_bytes, as_stream(stream), full);
+                         ws_bytes, as_stream(stream), full, nullptr, jack_out, &loo);
 }
 
 int b200boot_resample_median_columns_indexed(const double* data, int64_t n_rows, int64_t n_cols,

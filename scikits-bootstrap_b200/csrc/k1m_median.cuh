@@ -941,7 +941,8 @@ inline int median_prepare(const double* data, int64_t n_rows, int64_t n_cols, in
 inline int median_resample(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, uint64_t seed,
                            int64_t resample_lo, int64_t resample_hi, double* stat_out, void* ws,
                            size_t ws_bytes, cudaStream_t s, const RankRule& rule,
-                           const int64_t* indices = nullptr) {
+                           const int64_t* indices = nullptr, double* jack_out = nullptr,
+                           const RankRule* loo = nullptr) {
   int rc = median_check(data, n_rows, n_cols, ld, ws);
   if (rc) return rc;
   const int64_t n_local = resample_hi - resample_lo;
@@ -953,6 +954,14 @@ inline int median_resample(const double* data, int64_t n_rows, int64_t n_cols, i
   if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
   rc = median_prepare(data, n_rows, n_cols, ld, w, s);
   if (rc) return rc;
+  if (jack_out && loo) {   // the sorted columns are at hand: K3m costs one small launch
+    for (int64_t d0 = 0; d0 < n_cols; d0 += 1 << 30) {
+      const int64_t nd = std::min<int64_t>((int64_t)1 << 30, n_cols - d0);
+      k3m_jackknife_median_kernel<<<(unsigned)nd, 256, 0, s>>>(w.sorted_vals + d0 * n_rows, n_rows, rule, *loo,
+                                                               jack_out + d0 * 8);
+      B2_LAUNCH_CHECK();
+    }
+  }
 
   K1mParams P{};
   P.sorted_vals = w.sorted_vals;

@@ -86,13 +86,13 @@ def test_abi_argument_validation_returns_status_codes():
     rule = _abi.RankRule(k_lo=5, k_hi=7, gamma=0.5, loo_k_lo=4, loo_k_hi=5, loo_gamma=0.5, mode=1)
     rp = C.cast(C.pointer(rule), C.c_void_p)
     rm = L.b200boot_resample_median_columns
-    assert rm(fake, 100, 1, 1, 0, 0, 10, fake, fake, 1 << 30, None, rp) == EINVAL                 # k_hi > k_lo + 1
+    assert rm(fake, 100, 1, 1, 0, 0, 10, fake, fake, 1 << 30, None, rp, None) == EINVAL           # k_hi > k_lo + 1
     rule.k_hi = 100
     rule.k_lo = 99
-    assert rm(fake, 100, 1, 1, 0, 0, 10, fake, fake, 1 << 30, None, rp) == EINVAL                 # rank outside the sample
+    assert rm(fake, 100, 1, 1, 0, 0, 10, fake, fake, 1 << 30, None, rp, None) == EINVAL           # rank outside the sample
     rule.k_lo, rule.k_hi, rule.gamma = 5, 6, 1.5
-    assert rm(fake, 100, 1, 1, 0, 0, 10, fake, fake, 1 << 30, None, rp) == EINVAL
-    assert rm(fake, 40000, 1, 1, 0, 0, 10, fake, fake, 1 << 30, None, None) == EUNSUPPORTED       # beyond resident rows
+    assert rm(fake, 100, 1, 1, 0, 0, 10, fake, fake, 1 << 30, None, rp, None) == EINVAL
+    assert rm(fake, 40000, 1, 1, 0, 0, 10, fake, fake, 1 << 30, None, None, None) == EUNSUPPORTED # beyond resident rows
     assert L.b200boot_resample_median_sorted(fake, 1000, 0, 0, 10, fake, fake, 1 << 30, None, None) == EINVAL  # one tile
 
     assert L.b200boot_count(fake, 10, 1, 9, fake, None, fake, None) == EINVAL                     # bad operator
