@@ -99,6 +99,15 @@ int b200boot_resample_stat(const double* const* data, int n_arrays, int64_t n_ro
                            uint64_t seed, int64_t resample_lo, int64_t resample_hi,
                            double* stat_out, void* ws, size_t ws_bytes, void* stream);
 
+/* The same with the data possibly still in flight: `data_ready_event` (a cudaEvent_t, or
+ * NULL) is recorded by the caller after its host-to-device copy of `data` on another stream.
+ * The occupancy chains (which do not read the data) are enqueued first; everything that
+ * reads the data waits for the event on `stream`. */
+int b200boot_resample_stat_after(const double* const* data, int n_arrays, int64_t n_rows, int stat_id,
+                                 uint64_t seed, int64_t resample_lo, int64_t resample_hi,
+                                 double* stat_out, void* ws, size_t ws_bytes, void* stream,
+                                 void* data_ready_event);
+
 /* K1i — parity mode: the caller supplies the index arrays (e.g. the reference's
  * own PCG64 draws).  Replaces bootstrap.py:431 only.  indices: int64[n_sets][N]
  * row-major, values in [0, N).  stat_out: float64[n_sets] ([n_out][n_sets]). */

@@ -44,6 +44,32 @@ def host_to_device(arr: np.ndarray, device):
     return t.to(device)
 
 
+_copy_streams = {}
+
+
+def to_device_f64_async(x, device=None):
+    """Like to_device_f64, but a pinned host tensor is copied on a side stream: returns
+    (tensor, event) where `event` (or None) is recorded after the copy.  Work that does
+    not read the data can be enqueued before the consumer waits for the event."""
+    torch = require_cuda()
+    if not (isinstance(x, torch.Tensor) and x.device.type == "cpu" and x.is_pinned()
+            and x.dtype == torch.float64 and x.is_contiguous()):
+        return to_device_f64(x, device), None
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    side = _copy_streams.get(dev.index)
+    if side is None:
+        side = _copy_streams[dev.index] = torch.cuda.Stream(device=dev)
+    dst = torch.empty(x.shape, dtype=torch.float64, device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))      # the block may have pending users there
+    with torch.cuda.stream(side):
+        dst.copy_(x, non_blocking=True)
+    dst.record_stream(side)
+    event = torch.cuda.Event()
+    event.record(side)
+    TRAFFIC["h2d"] += x.numel() * 8
+    return dst, event
+
+
 def to_device_f64(x, device=None):
     """array-like / torch tensor -> contiguous float64 CUDA tensor.  float64 CUDA
     tensors are used in place (no copy)."""
@@ -143,7 +169,7 @@ def _ws_budget() -> int:
     return int(os.environ.get("B200BOOT_WS_BYTES", 12 << 30))
 
 
-def resample_stat(arrays: Sequence, stat_id: int, seed: int, lo: int, hi: int, out=None):
+def resample_stat(arrays: Sequence, stat_id: int, seed: int, lo: int, hi: int, out=None, ready=None):
     """K1 on contiguous float64[N] CUDA tensors -> float64[hi-lo] CUDA tensor
     (float64[n_out][hi-lo] for a statistic with several outputs)."""
     torch = _torch()
@@ -164,8 +190,11 @@ def resample_stat(arrays: Sequence, stat_id: int, seed: int, lo: int, hi: int, o
         ws, wsz = workspace_for(stat_id, n_rows, len(arrays), 1, b - a, 1)
         whole = n_out == 1 or (a == lo and b == hi)
         dst = out[a - lo:] if n_out == 1 else (out if whole else out.new_empty((n_out, b - a)))
-        _abi.check(L.b200boot_resample_stat(ptrs, len(arrays), n_rows, stat_id, seed, a, b,
-                                            dst.data_ptr(), ws, wsz, stream_ptr()))
+        # `ready`: event recorded after the arrays' host-to-device copy on another stream; the
+        # first sub-range waits for it (after its occupancy chains), later ones follow in order
+        ev = ready.cuda_event if (ready is not None and a == lo) else None
+        _abi.check(L.b200boot_resample_stat_after(ptrs, len(arrays), n_rows, stat_id, seed, a, b,
+                                                  dst.data_ptr(), ws, wsz, stream_ptr(), ev))
         if not whole:
             out[:, a - lo:b - lo] = dst
     return out

@@ -134,7 +134,11 @@ class _Run:
                  indices=None):
         self.spec, self.multi, self.n_samples, self.key = spec, multi, int(n_samples), key
         self.indices = indices       # parity mode: caller-supplied index sets (K1i)
-        self.dev = [_device.to_device_f64(a) for a in arrays]
+        # pinned host tensors are copied on a side stream; `_ready` is recorded after the copies
+        pairs = [_device.to_device_f64_async(a) for a in arrays]
+        self.dev = [t for t, _ in pairs]
+        events = [e for _, e in pairs if e is not None]
+        self._ready = events[-1] if events else None      # one side stream: the last event covers all
         # the statistic has shape (D,): one value per data column, or a multi-output statistic
         self.vector = (spec.axis0 and self.dev[0].dim() == 2) or spec.n_out > 1
         self.n_cols = spec.n_out if spec.n_out > 1 else (self.dev[0].shape[1] if self.vector else 1)
@@ -187,6 +191,12 @@ class _Run:
     def resample(self):
         torch = _device._torch()
         spec, lo, hi = self.spec, self.lo, self.hi
+        ready, self._ready = self._ready, None
+        plain = (self.indices is None and not spec.independent and spec.stat_id != _abi.STAT_MEDIAN
+                 and not self.vector and hi > lo)
+        if ready is not None and not plain:
+            torch.cuda.current_stream().wait_event(ready)     # only the plain K1 path overlaps the copy
+            ready = None
         if self.indices is not None:
             return self._resample_indexed()
         if spec.independent:
@@ -217,7 +227,7 @@ class _Run:
                 _device.resample_stat([cols[d]], spec.stat_id, self.key, lo, hi, out=out[d])
             return out
         flat = [a.reshape(-1) for a in self.dev]
-        return _device.resample_stat(flat, spec.stat_id, self.key, lo, hi).reshape(1, -1)
+        return _device.resample_stat(flat, spec.stat_id, self.key, lo, hi, ready=ready).reshape(1, -1)
 
     # -- K1i ---------------------------------------------------------------------
     def _resample_indexed(self):

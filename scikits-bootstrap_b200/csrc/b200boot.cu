@@ -282,6 +282,14 @@ size_t b200boot_workspace_bytes(int stat_id, int64_t n_rows, int n_arrays, int64
 int b200boot_resample_stat(const double* const* data, int n_arrays, int64_t n_rows, int stat_id,
                            uint64_t seed, int64_t resample_lo, int64_t resample_hi,
                            double* stat_out, void* ws, size_t ws_bytes, void* stream) {
+  return b200boot_resample_stat_after(data, n_arrays, n_rows, stat_id, seed, resample_lo, resample_hi, stat_out,
+                                      ws, ws_bytes, stream, nullptr);
+}
+
+int b200boot_resample_stat_after(const double* const* data, int n_arrays, int64_t n_rows, int stat_id,
+                                 uint64_t seed, int64_t resample_lo, int64_t resample_hi,
+                                 double* stat_out, void* ws, size_t ws_bytes, void* stream,
+                                 void* data_ready_event) {
   int rc = check_moment_stat(stat_id, n_arrays, n_rows);
   if (rc) return rc;
   const int64_t n_local = resample_hi - resample_lo;
@@ -296,6 +304,13 @@ int b200boot_resample_stat(const double* const* data, int n_arrays, int64_t n_ro
   ResampleWs w = carve_resample(cv, plan, stat_id, n_local);
   if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
 
+  // The occupancy chains do not read the data: when the caller is still copying it in on
+  // another stream, only what follows them waits for the copy.
+  cudaEvent_t ready = reinterpret_cast<cudaEvent_t>(data_ready_event);
+  if (ready && stat_needs_centering(stat_id)) {   // the centring pass reads the data first
+    B2_CUDA(cudaStreamWaitEvent(s, ready, 0));
+    ready = nullptr;
+  }
   const double* rows[2];
   rc = prepare_rows(data, n_arrays, n_rows, stat_id, w, rows, s);
   if (rc) return rc;
@@ -304,6 +319,7 @@ int b200boot_resample_stat(const double* const* data, int n_arrays, int64_t n_ro
                           w.gcounts);
   if (rc) return rc;
   B2_CUDA(cudaMemsetAsync(w.work_counter, 0, 256, s));
+  if (ready) B2_CUDA(cudaStreamWaitEvent(s, ready, 0));
 
   const int ms = moment_set_of(stat_id);
   const int nm = ms == kMomSum ? 1 : (ms == kMomPair5 ? 5 : 2);

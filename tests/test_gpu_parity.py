@@ -1075,3 +1075,24 @@ def test_very_long_array_two_level_tile_chains():
     assert_array_equal(again, [lo, hi])
     mlo, mhi = boot.ci(x, np.median, n_samples=m, seed=1)
     assert mlo < 1.0 + 5 * se and mhi > 1.0 - 5 * se and 3.0 < (mhi - mlo) / (1.2533 * se) < 5.0
+
+
+def test_pinned_host_tensors_copy_overlaps_but_results_do_not_change():
+    """Pinned host tensors are copied on a side stream while the occupancy chains (which do not
+    read the data) are already running; every statistic must see the complete data."""
+    import torch
+    rng = np.random.default_rng(8)
+    for n in (1000, 300_000, 3_000_000):
+        a = rng.gamma(2.0, 1.0, n)
+        b = 0.5 * a + rng.gamma(3.0, 1.0, n)
+        pa, pb = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()
+        for rep in range(3):                      # repeated: the destination block is recycled
+            assert_array_equal(boot.ci(pa, np.mean, n_samples=300, seed=rep), boot.ci(a, np.mean, n_samples=300, seed=rep))
+        assert_array_equal(boot.ci(pa, np.std, n_samples=300, seed=2), boot.ci(a, np.std, n_samples=300, seed=2))
+        assert_array_equal(boot.ci((pa, pb), boot.pearson_r, n_samples=300, seed=3),
+                           boot.ci((a, b), boot.pearson_r, n_samples=300, seed=3))
+        assert_array_equal(boot.ci((pa, pb), boot.linear_fit, n_samples=300, seed=3),
+                           boot.ci((a, b), boot.linear_fit, n_samples=300, seed=3))
+        assert_array_equal(boot.ci(pa, np.median, n_samples=300, seed=4), boot.ci(a, np.median, n_samples=300, seed=4))
+        assert boot.pval(pa, np.mean, boot.greater_than(2.0), n_samples=300, seed=5) == \
+            boot.pval(a, np.mean, boot.greater_than(2.0), n_samples=300, seed=5)
