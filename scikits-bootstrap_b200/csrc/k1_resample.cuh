@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) k0_class_step_propose_kernel(
   if (defer) pending[s_base + slot] = (int32_t)e;      // e < 2^31 (checked by the host)
 }
 
-__global__ void __launch_bounds__(128) k0_class_step_resolve_kernel(
+__global__ void __launch_bounds__(128, 8) k0_class_step_resolve_kernel(
     uint64_t seed, int64_t resample_lo, int64_t n_local, int c, int32_t* __restrict__ left,
     int32_t* __restrict__ cls, const int32_t* __restrict__ pending, const int32_t* __restrict__ n_pending) {
   const int n = *n_pending;
