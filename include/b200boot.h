@@ -145,6 +145,22 @@ typedef struct b200boot_rank_rule {
   int32_t reserved;
 } b200boot_rank_rule;
 
+/* K6 — multi-column moment statistics as (count matrix) x (data) GEMM.  For (N, D) data the
+ * column sums of resample r are sum_i c[r][i] * x[i][:], c[r][i] = multiplicity of row i in
+ * resample r (all columns share the index set, bootstrap.py:431): one FP64 GEMM
+ * C[n x N] * X[N x D] replaces the gather of bootstrap.py:429-432 for every column at once.
+ * The GEMM is a plain library DGEMM issued by the caller between these two calls;
+ * the library supplies the count matrix (multiplicities of exactly the indices
+ * b200boot_fill_indices yields, N <= 28 672) and the finisher. */
+int b200boot_gemm_supported(int stat_id, int64_t n_rows);
+/* out: float64[resample_hi - resample_lo][N] row-major */
+int b200boot_count_matrix(uint64_t seed, int64_t n_rows, int64_t resample_lo, int64_t resample_hi,
+                          double* out, void* stream);
+/* s1: float64[n_cols][n_local] = X^T C^T (in place -> the statistic); s2: the same for the squares of
+ * the column-centred data (B200BOOT_STAT_VAR / _STD, where s1 is of the centred data too), else NULL */
+int b200boot_finish_columns(int stat_id, int64_t n_rows, int64_t n_cols, int64_t n_local, double* s1,
+                            const double* s2, void* stream);
+
 /* K1m — column-batched order statistic: data float64[N][n_cols] row-major
  * (ld = row stride in elements); every column shares one index set per
  * resample, as x[indices] does for 2-D data at bootstrap.py:431.

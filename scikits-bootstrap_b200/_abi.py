@@ -44,6 +44,9 @@ SIGNATURES = {
     "b200boot_make_plan": (_int, [_i64, _int, C.POINTER(Plan)]),
     "b200boot_workspace_bytes": (_sz, [_int, _i64, _int, _i64, _i64, _int]),
     "b200boot_resample_stat": (_int, [_vp, _int, _i64, _int, _u64, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "b200boot_gemm_supported": (_int, [_int, _i64]),
+    "b200boot_count_matrix": (_int, [_u64, _i64, _i64, _i64, _vp, _vp]),
+    "b200boot_finish_columns": (_int, [_int, _i64, _i64, _i64, _vp, _vp, _vp]),
     "b200boot_resample_stat_after": (_int, [_vp, _int, _i64, _int, _u64, _i64, _i64, _vp, _vp, _sz, _vp, _vp]),
     "b200boot_resample_stat_indexed": (_int, [_vp, _int, _i64, _int, _vp, _i64, _vp, _vp, _sz, _vp]),
     "b200boot_columns_block_width": (_int, [_int, _i64]),

@@ -230,6 +230,47 @@ def resample_stat_columns(data2d, stat_id: int, seed: int, lo: int, hi: int):
     return out
 
 
+GEMM_MIN_COLS = 32           # below this the gather kernels win (K1c serves 32 columns per draw)
+_GEMM_COUNT_BYTES = 1 << 30  # count-matrix chunk
+
+
+def gemm_supported(stat_id: int, n_rows: int) -> bool:
+    return bool(_abi.lib().b200boot_gemm_supported(stat_id, n_rows))
+
+
+def resample_stat_gemm(data2d, stat_id: int, seed: int, lo: int, hi: int):
+    """K6: data float64[N][D] -> float64[D][hi-lo].  Column sums of every resample as one FP64
+    GEMM (library DGEMM through torch.mm) of the data with the resamples' count matrix; var / std
+    use the column-centred data and its squares, as K1c does."""
+    torch = _torch()
+    L = _abi.lib()
+    n_rows, n_cols = data2d.shape
+    n_local = hi - lo
+    out = torch.empty((n_cols, n_local), dtype=torch.float64, device=data2d.device)
+    two = stat_id in (_abi.STAT_VAR, _abi.STAT_STD)
+    x = data2d - data2d.mean(dim=0, keepdim=True) if two else data2d
+    xt = x.t()                                                    # [D][N] view: cuBLAS takes the transpose flag
+    x2t = (x * x).t() if two else None
+    second = torch.empty_like(out) if two else None
+    step = max(1, min(n_local, _GEMM_COUNT_BYTES // (8 * n_rows)))
+    counts = torch.empty((step, n_rows), dtype=torch.float64, device=data2d.device)
+    for a in range(lo, hi, step):
+        b = min(hi, a + step)
+        c = counts[:b - a]
+        _abi.check(L.b200boot_count_matrix(seed, n_rows, a, b, c.data_ptr(), stream_ptr()))
+        if step == n_local:                                       # one chunk: write in place
+            torch.mm(xt, c.t(), out=out)
+            if two:
+                torch.mm(x2t, c.t(), out=second)
+        else:
+            out[:, a - lo:b - lo] = xt @ c.t()
+            if two:
+                second[:, a - lo:b - lo] = x2t @ c.t()
+    _abi.check(L.b200boot_finish_columns(stat_id, n_rows, n_cols, n_local, out.data_ptr(),
+                                         second.data_ptr() if two else None, stream_ptr()))
+    return out
+
+
 def jackknife_columns(data2d, stat_id: int):
     """K3c: float64[D][8] (ostat, jmean, d2, d3, accel, centre, ...) per column."""
     torch = _torch()

@@ -218,6 +218,9 @@ class _Run:
             return _device.resample_median_columns(data2d, self.key, lo, hi, rule=self.rule)
         if spec.n_out > 1:
             return _device.resample_stat([a.reshape(-1) for a in self.dev], spec.stat_id, self.key, lo, hi)
+        if (self.vector and self.n_cols >= _device.GEMM_MIN_COLS and hi > lo
+                and _device.gemm_supported(spec.stat_id, self.dev[0].shape[0])):
+            return _device.resample_stat_gemm(self.dev[0], spec.stat_id, self.key, lo, hi)     # K6
         if self.vector and _device.columns_block_width(spec.stat_id, self.dev[0].shape[0]) > 0:
             return _device.resample_stat_columns(self.dev[0], spec.stat_id, self.key, lo, hi)   # K1c
         if self.vector:

@@ -9,6 +9,7 @@
 #include "k1_resample.cuh"
 #include "k1c_columns.cuh"
 #include "k1m_median.cuh"
+#include "k6_gemm.cuh"
 #include "k3_jackknife.cuh"
 #include "k45_interval.cuh"
 #include "stats.cuh"
@@ -756,6 +757,47 @@ int b200boot_jackknife_median_sorted(const double* sorted_vals, int64_t n_rows, 
   RankRule full, loo;
   if (int rc = rank_rules(rule, n_rows, &full, &loo)) return rc;
   return median_jackknife_sorted(sorted_vals, n_rows, out, as_stream(stream), full, loo);
+}
+
+// ---- K6: count matrix and finisher around a library DGEMM ------------------------------
+int b200boot_gemm_supported(int stat_id, int64_t n_rows) { return gemm_supported(stat_id, n_rows) ? 1 : 0; }
+
+int b200boot_count_matrix(uint64_t seed, int64_t n_rows, int64_t resample_lo, int64_t resample_hi,
+                          double* out, void* stream) {
+  const int64_t n_local = resample_hi - resample_lo;
+  if (!out || n_rows < 1 || n_local < 0 || resample_lo < 0) return fail(B200BOOT_EINVAL, "bad arguments");
+  if (n_rows > kSmemDataBytes / 8)
+    return fail(B200BOOT_EUNSUPPORTED, "count matrix: n_rows=%lld beyond the single-cell limit", (long long)n_rows);
+  if (n_local == 0) return 0;
+  static bool configured[64] = {false};
+  int dev = 0;
+  B2_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    B2_CUDA(cudaFuncSetAttribute(k6_count_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(kSmemHeader + kSmemDataBytes)));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  const size_t smem = (size_t)n_rows * 4;
+  const int per_sm = (int)std::max<int64_t>(1, std::min<int64_t>(4, (int64_t)(200 * 1024) / (int64_t)std::max<size_t>(smem, 1)));
+  const int grid = (int)std::min<int64_t>((int64_t)sm_count() * per_sm, n_local);
+  k6_count_matrix_kernel<<<grid, kK6Threads, smem, as_stream(stream)>>>(seed, n_rows, resample_lo, n_local, out);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200boot_finish_columns(int stat_id, int64_t n_rows, int64_t n_cols, int64_t n_local, double* s1,
+                            const double* s2, void* stream) {
+  if (!s1 || n_rows < 1 || n_cols < 1 || n_local < 0) return fail(B200BOOT_EINVAL, "bad arguments");
+  const int ms = moment_set_of(stat_id);
+  if (ms != kMomSum && ms != kMomSum2)
+    return fail(B200BOOT_EUNSUPPORTED, "statistic %d is not a single-array moment statistic", stat_id);
+  if (ms == kMomSum2 && !s2) return fail(B200BOOT_EINVAL, "var / std need the second-moment sums");
+  const int64_t total = n_cols * n_local;
+  if (total == 0) return 0;
+  k6_finish_kernel<<<blocks_for(total, 256, 148 * 16), 256, 0, as_stream(stream)>>>(stat_id, (double)n_rows, total,
+                                                                                  s1, s2);
+  B2_LAUNCH_CHECK();
+  return 0;
 }
 
 // ---- instrumentation ---------------------------------------------------------------

@@ -1096,3 +1096,36 @@ def test_pinned_host_tensors_copy_overlaps_but_results_do_not_change():
         assert_array_equal(boot.ci(pa, np.median, n_samples=300, seed=4), boot.ci(a, np.median, n_samples=300, seed=4))
         assert boot.pval(pa, np.mean, boot.greater_than(2.0), n_samples=300, seed=5) == \
             boot.pval(a, np.mean, boot.greater_than(2.0), n_samples=300, seed=5)
+
+
+@pytest.mark.parametrize("n,d", [(50, 32), (1000, 100), (7169, 40), (28672, 33)])
+def test_count_matrix_gemm_columns(n, d):
+    """K6: the column sums of every resample as (count matrix) x (data).  The count matrix holds the
+    multiplicities of exactly the indices bootstrap_indices yields; statistics agree with numpy on
+    those indices and with the gather kernels (different summation order: 1e-12)."""
+    rng = np.random.default_rng(n + d)
+    data = rng.standard_normal((n, d)) + 3.0
+    m = 64
+    idx = np.array(list(boot.bootstrap_indices(data, m, seed=21)))
+    import torch
+    c = torch.empty((m, n), dtype=torch.float64, device="cuda")
+    _abi.check(_abi.lib().b200boot_count_matrix(21, n, 0, m, c.data_ptr(), _device.stream_ptr()))
+    want_counts = np.stack([np.bincount(i, minlength=n) for i in idx]).astype(float)
+    assert_array_equal(c.cpu().numpy(), want_counts)
+    part = torch.empty((10, n), dtype=torch.float64, device="cuda")
+    _abi.check(_abi.lib().b200boot_count_matrix(21, n, 30, 40, part.data_ptr(), _device.stream_ptr()))
+    assert_array_equal(part.cpu().numpy(), want_counts[30:40])
+    xd = dev(data)
+    for stat_id, f in ((_abi.STAT_MEAN, np.mean), (_abi.STAT_SUM, np.sum), (_abi.STAT_VAR, np.var), (_abi.STAT_STD, np.std)):
+        got = _device.resample_stat_gemm(xd, stat_id, 21, 0, m).cpu().numpy()          # [D][m]
+        want = np.stack([f(data[i], axis=0) for i in idx], axis=1)
+        assert_allclose(got, want, rtol=1e-11, atol=1e-13)
+        if _device.columns_block_width(stat_id, n) > 0:
+            gather = _device.resample_stat_columns(xd, stat_id, 21, 0, m).cpu().numpy()
+            assert_allclose(got, gather, rtol=1e-11, atol=1e-13)
+    assert _device.gemm_supported(_abi.STAT_MEAN, 28672) and not _device.gemm_supported(_abi.STAT_MEAN, 28673)
+    assert not _device.gemm_supported(_abi.STAT_MEDIAN, 100)
+    # the public call takes this path for D >= 32 and equals the per-column 1-D runs
+    out = boot.ci(data, boot.mean_axis0, n_samples=200, seed=5)
+    one = boot.ci(data[:, 3], np.mean, n_samples=200, seed=5)
+    assert_allclose(out[:, 3], one, rtol=1e-12, atol=1e-15)

@@ -102,6 +102,11 @@ def test_abi_argument_validation_returns_status_codes():
     assert L.b200boot_fill_indices(0, 0, 1, 0, 3, fake, fake, 1 << 30, None) == EINVAL
     assert L.b200boot_jackknife_columns(fake, 10, 3, 2, _abi.STAT_MEAN, fake, None) == EINVAL     # ld < n_cols
     assert L.b200boot_jackknife_columns(fake, 10, 3, 3, _abi.STAT_PEARSON_R, fake, None) == EUNSUPPORTED
+    assert L.b200boot_count_matrix(0, 40000, 0, 3, fake, None) == EUNSUPPORTED                   # beyond one cell
+    assert L.b200boot_count_matrix(0, 100, 5, 3, fake, None) == EINVAL
+    assert L.b200boot_finish_columns(_abi.STAT_VAR, 100, 3, 10, fake, None, None) == EINVAL       # needs s2
+    assert L.b200boot_finish_columns(_abi.STAT_PEARSON_R, 100, 3, 10, fake, fake, None) == EUNSUPPORTED
+    assert L.b200boot_gemm_supported(_abi.STAT_STD, 28672) == 1 and L.b200boot_gemm_supported(_abi.STAT_STD, 28673) == 0
     assert L.b200boot_columns_block_width(_abi.STAT_MEAN, 100000) == 0                            # beyond K1c rows
     assert L.b200boot_columns_block_width(_abi.STAT_MEAN, 1000) in (4, 8, 16, 32)
 
