@@ -156,6 +156,10 @@ int b200boot_gemm_supported(int stat_id, int64_t n_rows);
 /* out: float64[resample_hi - resample_lo][N] row-major */
 int b200boot_count_matrix(uint64_t seed, int64_t n_rows, int64_t resample_lo, int64_t resample_hi,
                           double* out, void* stream);
+/* The count matrix of caller-supplied index sets, int64[n_sets][N] (e.g. from b200boot_fill_indices
+ * for data longer than one cell): out float64[n_sets][N], overwritten. */
+int b200boot_counts_from_indices(const int64_t* indices, int64_t n_sets, int64_t n_rows, double* out,
+                                 void* stream);
 /* s1: float64[n_cols][n_local] = X^T C^T (in place -> the statistic); s2: the same for the squares of
  * the column-centred data (B200BOOT_STAT_VAR / _STD, where s1 is of the centred data too), else NULL */
 int b200boot_finish_columns(int stat_id, int64_t n_rows, int64_t n_cols, int64_t n_local, double* s1,

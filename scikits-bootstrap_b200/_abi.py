@@ -46,6 +46,7 @@ SIGNATURES = {
     "b200boot_resample_stat": (_int, [_vp, _int, _i64, _int, _u64, _i64, _i64, _vp, _vp, _sz, _vp]),
     "b200boot_gemm_supported": (_int, [_int, _i64]),
     "b200boot_count_matrix": (_int, [_u64, _i64, _i64, _i64, _vp, _vp]),
+    "b200boot_counts_from_indices": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "b200boot_finish_columns": (_int, [_int, _i64, _i64, _i64, _vp, _vp, _vp]),
     "b200boot_resample_stat_after": (_int, [_vp, _int, _i64, _int, _u64, _i64, _i64, _vp, _vp, _sz, _vp, _vp]),
     "b200boot_resample_stat_indexed": (_int, [_vp, _int, _i64, _int, _vp, _i64, _vp, _vp, _sz, _vp]),

@@ -235,7 +235,9 @@ _GEMM_COUNT_BYTES = 1 << 30  # count-matrix chunk
 
 
 def gemm_supported(stat_id: int, n_rows: int) -> bool:
-    return bool(_abi.lib().b200boot_gemm_supported(stat_id, n_rows))
+    """K6 covers mean / sum / var / std for any N: one-cell data build the count matrix
+    directly, longer data through the materialised indices of the tiled plan (K2)."""
+    return stat_id in (_abi.STAT_MEAN, _abi.STAT_SUM, _abi.STAT_VAR, _abi.STAT_STD) and 1 <= n_rows < 2**31
 
 
 def resample_stat_gemm(data2d, stat_id: int, seed: int, lo: int, hi: int):
@@ -252,12 +254,20 @@ def resample_stat_gemm(data2d, stat_id: int, seed: int, lo: int, hi: int):
     xt = x.t()                                                    # [D][N] view: cuBLAS takes the transpose flag
     x2t = (x * x).t() if two else None
     second = torch.empty_like(out) if two else None
-    step = max(1, min(n_local, _GEMM_COUNT_BYTES // (8 * n_rows)))
+    import os
+    budget = int(os.environ.get("B200BOOT_GEMM_COUNT_BYTES", _GEMM_COUNT_BYTES))
+    step = max(1, min(n_local, budget // (8 * n_rows)))
     counts = torch.empty((step, n_rows), dtype=torch.float64, device=data2d.device)
+    one_cell = bool(L.b200boot_gemm_supported(stat_id, n_rows))
     for a in range(lo, hi, step):
         b = min(hi, a + step)
         c = counts[:b - a]
-        _abi.check(L.b200boot_count_matrix(seed, n_rows, a, b, c.data_ptr(), stream_ptr()))
+        if one_cell:
+            _abi.check(L.b200boot_count_matrix(seed, n_rows, a, b, c.data_ptr(), stream_ptr()))
+        else:
+            idx = fill_indices(seed, n_rows, 1, a, b)
+            _abi.check(L.b200boot_counts_from_indices(idx.data_ptr(), b - a, n_rows, c.data_ptr(), stream_ptr()))
+            del idx
         if step == n_local:                                       # one chunk: write in place
             torch.mm(xt, c.t(), out=out)
             if two:

@@ -785,6 +785,18 @@ int b200boot_count_matrix(uint64_t seed, int64_t n_rows, int64_t resample_lo, in
   return 0;
 }
 
+int b200boot_counts_from_indices(const int64_t* indices, int64_t n_sets, int64_t n_rows, double* out,
+                                 void* stream) {
+  if (!indices || !out || n_sets < 0 || n_rows < 1) return fail(B200BOOT_EINVAL, "bad arguments");
+  if (n_sets == 0) return 0;
+  cudaStream_t s = as_stream(stream);
+  B2_CUDA(cudaMemsetAsync(out, 0, (size_t)n_sets * (size_t)n_rows * 8, s));
+  k6_counts_from_indices_kernel<<<blocks_for(n_sets * n_rows, 256, 148 * 16), 256, 0, s>>>(indices, n_sets, n_rows,
+                                                                                         out);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
 int b200boot_finish_columns(int stat_id, int64_t n_rows, int64_t n_cols, int64_t n_local, double* s1,
                             const double* s2, void* stream) {
   if (!s1 || n_rows < 1 || n_cols < 1 || n_local < 0) return fail(B200BOOT_EINVAL, "bad arguments");

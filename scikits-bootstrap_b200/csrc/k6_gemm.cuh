@@ -41,6 +41,19 @@ __global__ void __launch_bounds__(kK6Threads) k6_count_matrix_kernel(uint64_t se
   }
 }
 
+// Count matrix from materialised index sets (any N: the tiled plans of K2): out[r][i] += 1 for
+// every index i of set r.  `out` must be zeroed by the caller; FP64 atomics land in L2.
+__global__ void __launch_bounds__(256) k6_counts_from_indices_kernel(const int64_t* __restrict__ idx,
+                                                                     int64_t n_sets, int64_t n_rows,
+                                                                     double* __restrict__ out) {
+  const int64_t total = n_sets * n_rows;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t r = e / n_rows;
+    atomicAdd(out + r * n_rows + idx[e], 1.0);
+  }
+}
+
 // s1 [D][n_local] holds sum_i c x (in place -> the statistic); s2 (var / std) holds
 // sum_i c x^2 of the column-centred data.
 __global__ void __launch_bounds__(256) k6_finish_kernel(int stat, double count, int64_t total,

@@ -1123,9 +1123,33 @@ def test_count_matrix_gemm_columns(n, d):
         if _device.columns_block_width(stat_id, n) > 0:
             gather = _device.resample_stat_columns(xd, stat_id, 21, 0, m).cpu().numpy()
             assert_allclose(got, gather, rtol=1e-11, atol=1e-13)
-    assert _device.gemm_supported(_abi.STAT_MEAN, 28672) and not _device.gemm_supported(_abi.STAT_MEAN, 28673)
-    assert not _device.gemm_supported(_abi.STAT_MEDIAN, 100)
+    L = _abi.lib()
+    assert L.b200boot_gemm_supported(_abi.STAT_MEAN, 28672) == 1 and L.b200boot_gemm_supported(_abi.STAT_MEAN, 28673) == 0
+    assert _device.gemm_supported(_abi.STAT_MEAN, 10**6) and not _device.gemm_supported(_abi.STAT_MEDIAN, 100)
     # the public call takes this path for D >= 32 and equals the per-column 1-D runs
     out = boot.ci(data, boot.mean_axis0, n_samples=200, seed=5)
     one = boot.ci(data[:, 3], np.mean, n_samples=200, seed=5)
     assert_allclose(out[:, 3], one, rtol=1e-12, atol=1e-15)
+
+
+def test_count_matrix_gemm_long_columns():
+    """Beyond one cell the count matrix comes from the materialised indices of the tiled plan."""
+    rng = np.random.default_rng(3)
+    n, d, m = 40001, 35, 40
+    data = rng.standard_normal((n, d)) + 1.0
+    idx = np.array(list(boot.bootstrap_indices(data, m, seed=8)))
+    xd = dev(data)
+    for stat_id, f in ((_abi.STAT_MEAN, np.mean), (_abi.STAT_STD, np.std)):
+        got = _device.resample_stat_gemm(xd, stat_id, 8, 0, m).cpu().numpy()
+        want = np.stack([f(data[i], axis=0) for i in idx], axis=1)
+        assert_allclose(got, want, rtol=1e-11, atol=1e-13)
+    import os
+    os.environ["B200BOOT_GEMM_COUNT_BYTES"] = str(8 * n * 7)          # chunks of 7 resamples
+    try:
+        chunked = _device.resample_stat_gemm(xd, _abi.STAT_MEAN, 8, 0, m).cpu().numpy()
+    finally:
+        del os.environ["B200BOOT_GEMM_COUNT_BYTES"]
+    assert_allclose(chunked, np.stack([data[i].mean(axis=0) for i in idx], axis=1), rtol=1e-11, atol=1e-13)
+    out = boot.ci(data, boot.mean_axis0, n_samples=100, seed=5, method="pi")
+    one = boot.ci(data[:, 7], np.mean, n_samples=100, seed=5, method="pi")
+    assert_allclose(out[:, 7], one, rtol=1e-12, atol=1e-15)
