@@ -219,8 +219,11 @@ class _Run:
         if spec.n_out > 1:
             return _device.resample_stat([a.reshape(-1) for a in self.dev], spec.stat_id, self.key, lo, hi)
         if (self.vector and self.n_cols >= _device.GEMM_MIN_COLS and hi > lo
-                and _device.gemm_supported(spec.stat_id, self.dev[0].shape[0])):
-            return _device.resample_stat_gemm(self.dev[0], spec.stat_id, self.key, lo, hi)     # K6
+                and _device.gemm_supported(spec.stat_id, self.dev[0].shape[0])
+                and bool(torch.isfinite(self.dev[0]).all())):
+            # K6.  Only for finite data: in a product 0 * nan is nan, so a row that a resample
+            # does not draw would still poison it, unlike the gather x[indices] (bootstrap.py:431)
+            return _device.resample_stat_gemm(self.dev[0], spec.stat_id, self.key, lo, hi)
         if self.vector and _device.columns_block_width(spec.stat_id, self.dev[0].shape[0]) > 0:
             return _device.resample_stat_columns(self.dev[0], spec.stat_id, self.key, lo, hi)   # K1c
         if self.vector:

@@ -1153,3 +1153,22 @@ def test_count_matrix_gemm_long_columns():
     out = boot.ci(data, boot.mean_axis0, n_samples=100, seed=5, method="pi")
     one = boot.ci(data[:, 7], np.mean, n_samples=100, seed=5, method="pi")
     assert_allclose(out[:, 7], one, rtol=1e-12, atol=1e-15)
+
+
+def test_wide_table_with_nan_keeps_gather_semantics():
+    """0 * nan is nan in a matrix product, so the GEMM form would poison every resample; data with
+    non-finite entries take the gather kernels, where only resamples that draw the row see it."""
+    rng = np.random.default_rng(5)
+    data = rng.standard_normal((200, 40))
+    data[17, 3] = np.nan
+    data[60, 9] = np.inf
+    m = 300
+    idx = np.array(list(boot.bootstrap_indices(data, m, seed=2)))
+    with np.errstate(invalid="ignore"):
+        want = np.sort(np.stack([data[i].mean(axis=0) for i in idx]), axis=0)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _, dist = boot.ci(data, boot.mean_axis0, n_samples=m, seed=2, method="pi", return_dist=True)
+    assert np.isfinite(dist[:, 3]).sum() == np.isfinite(want[:, 3]).sum() > 0
+    assert_allclose(dist, want, rtol=1e-12, atol=1e-15, equal_nan=True)
