@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) k5_end_kernel(int64_t ad, SelectState st,
 // multi-launch path (both are exact).
 constexpr int kSelSmallThreads = 1024;
 constexpr int64_t kSelSmallMaxRows = 32768;
-constexpr int64_t kSelSmallMaxCols = 64;
+constexpr int64_t kSelSmallMaxCols = (int64_t)1 << 30;
 
 __global__ void __launch_bounds__(kSelSmallThreads) k5_select_small_kernel(
     const double* __restrict__ stat, int64_t n, int64_t n_cols, const int64_t* __restrict__ ranks,
