@@ -231,6 +231,17 @@ def resample_stat_columns(data2d, stat_id: int, seed: int, lo: int, hi: int):
 
 
 GEMM_MIN_COLS = 32           # below this the gather kernels win (K1c serves 32 columns per draw)
+
+
+def gemm_pays(n_rows: int, n_cols: int) -> bool:
+    """Measured crossover of the GEMM form against the gather kernels (mean, n = 2e4 resamples):
+    K6 is nearly flat in the number of columns, K1c grows in steps of 8 columns and with N.
+    One-cell data: from 8 columns on once N * D >= 20 000 (N = 7000: D = 8 -> 0.73 vs 1.19 ms;
+    N = 1000: D = 24 -> 0.20 vs 0.26 ms, D = 16 -> 0.19 vs 0.17 ms); longer data, where the
+    alternative is one K1 pass per column and the count matrix goes through K2: 32 columns."""
+    if n_rows <= MEDIAN_RESIDENT_ROWS:
+        return n_cols >= 8 and n_rows * n_cols >= 20000
+    return n_cols >= GEMM_MIN_COLS
 _GEMM_COUNT_BYTES = 1 << 30  # count-matrix chunk
 
 

@@ -218,7 +218,7 @@ class _Run:
             return _device.resample_median_columns(data2d, self.key, lo, hi, rule=self.rule)
         if spec.n_out > 1:
             return _device.resample_stat([a.reshape(-1) for a in self.dev], spec.stat_id, self.key, lo, hi)
-        if (self.vector and self.n_cols >= _device.GEMM_MIN_COLS and hi > lo
+        if (self.vector and _device.gemm_pays(self.dev[0].shape[0], self.n_cols) and hi > lo
                 and _device.gemm_supported(spec.stat_id, self.dev[0].shape[0])
                 and bool(torch.isfinite(self.dev[0]).all())):
             # K6.  Only for finite data: in a product 0 * nan is nan, so a row that a resample
