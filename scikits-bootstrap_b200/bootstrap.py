@@ -53,6 +53,8 @@ SeedType = Union[None, int, np.ndarray, np.random.SeedSequence, np.random.BitGen
                  np.random.Generator]
 
 _MASK64 = (1 << 64) - 1
+# sharded runs gather statistic vectors up to this size instead of reducing counts and histograms
+_GATHER_LIMIT_BYTES = 32 << 20
 # key offset between the arrays of multi='independent' (odd 64-bit constant)
 _ARRAY_KEY_STRIDE = 0x9E3779B97F4A7C15
 
@@ -149,6 +151,7 @@ class _Run:
         self._sorted_vals = None
         self._parts = None
         self._jack_dev = None
+        self._local = False          # sharded run whose statistic vector was gathered: finish without collectives
         # rank statistics: which order statistics (None: np.median's)
         self.rule = _device.rank_rule(self.dev[0].shape[0], spec.q) if spec.stat_id == _abi.STAT_MEDIAN else None
 
@@ -274,7 +277,7 @@ class _Run:
         if self.n_cols == 1 and not self.spec.independent and self._jack is None:
             jd = self._jackknife_tensor()
             c = _device.count(stat, _abi.CMP_LT, jd)              # &jd[0][0] is ostat
-            _dist.all_reduce_sum(c)
+            self._reduce(c)
             self._jack = _device.to_host(jd)
             return self._jack, _device.to_host(c)
         jack = self.jackknife()
@@ -331,13 +334,28 @@ class _Run:
             out[4] = d3 / (6.0 * d2 ** 1.5)
         return torch.from_numpy(out.reshape(1, 8))
 
+    # -- sharded runs with a small statistic vector ---------------------------------
+    def gather_small(self, stat):
+        """Every rank takes the whole statistic vector (one all-gather) when it is small and
+        finishes on its own: one collective instead of an all-reduce per count and per radix
+        pass.  The gathered vector is ordered by resample id, i.e. it IS the unsharded run's."""
+        if (_dist.active() and not self._local
+                and self.n_samples * self.n_cols * 8 <= _GATHER_LIMIT_BYTES):
+            self._local = True
+            return _dist.all_gather_ragged(stat, self.n_samples).contiguous()
+        return stat
+
+    def _reduce(self, c):
+        if not self._local:
+            _dist.all_reduce_sum(c)
+
     # -- K4 ----------------------------------------------------------------------
     def count(self, stat, op: int, t0: np.ndarray, t1: Optional[np.ndarray] = None) -> np.ndarray:
         torch = _device._torch()
         t0d = _device.host_to_device(np.asarray(t0, dtype=np.float64), stat.device)
         t1d = None if t1 is None else _device.host_to_device(np.asarray(t1, dtype=np.float64), stat.device)
         c = _device.count(stat, op, t0d, t1d)
-        _dist.all_reduce_sum(c)
+        self._reduce(c)
         return _device.to_host(c)
 
     # -- K5 ----------------------------------------------------------------------
@@ -346,12 +364,12 @@ class _Run:
         torch = _device._torch()
         r = _device.host_to_device(np.asarray(ranks, dtype=np.int64), stat.device)
         sel = _device.Select(stat, r)
-        out = sel.run(sharded=_dist.active())
+        out = sel.run(sharded=_dist.active() and not self._local)
         return _device.to_host(out)
 
     # -- full sorted distribution (return_dist / host-side compfunctions) --------
     def sorted_dist(self, stat) -> np.ndarray:
-        full = _dist.all_gather_ragged(stat, self.n_samples).contiguous()
+        full = stat.clone() if self._local else _dist.all_gather_ragged(stat, self.n_samples).contiguous()
         _device.sort_columns(full)
         host = _device.to_host(full)
         return host.T.copy() if self.vector else host[0].copy()
@@ -493,7 +511,7 @@ def _ci_impl(data, statfunction, alpha, n_samples, method, output, epsilon, mult
 def _ci_on_device(spec, arrays, multi, n_samples, key, indices, alphas, method, output, return_dist):
     """Device part of ci (warnings use stacklevel=4: the user's frame)."""
     run = _Run(spec, arrays, multi, n_samples, key, indices)
-    stat = run.resample()                                         # float64[D][n_local]
+    stat = run.gather_small(run.resample())                       # float64[D][n_local]
 
     ostat = None
     if method == "pi":
@@ -607,7 +625,7 @@ def _pval_impl(data, statfunction, compfunction, n_samples, multi, seed, indices
 
 def _pval_on_device(spec, arrays, multi, n_samples, key, indices, compfunction):
     run = _Run(spec, arrays, multi, n_samples, key, indices)
-    stat = run.resample()
+    stat = run.gather_small(run.resample())
     if isinstance(compfunction, DeviceCompare):
         t0 = np.full(run.n_cols, compfunction.t0)
         t1 = np.full(run.n_cols, compfunction.t1)

@@ -42,6 +42,14 @@ def main():
     ]
     boot.distributed.enable()
     sharded = [np.asarray(c()) for c in cases[:-1]]
+    # small statistic vectors are gathered and finished locally; with the limit at zero the same
+    # calls go through the all-reduced counts and radix histograms instead
+    limit = boot.bootstrap._GATHER_LIMIT_BYTES
+    boot.bootstrap._GATHER_LIMIT_BYTES = 0
+    reduced = [np.asarray(c()) for c in cases[:-1]]
+    boot.bootstrap._GATHER_LIMIT_BYTES = limit
+    for i, (got_gathered, got_reduced) in enumerate(zip(sharded, reduced)):      # (not a, b: the cases close over those)
+        np.testing.assert_array_equal(got_gathered, got_reduced, err_msg=f"gather vs reduce, case {i}")
     free = np.asarray(cases[-1]())
     gathered = [None] * dist.get_world_size()
     dist.all_gather_object(gathered, free.tolist())
