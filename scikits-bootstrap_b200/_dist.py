@@ -2,10 +2,13 @@
 
 Resample ids are independent units: rank g of G owns the contiguous id range
 [g*n/G, (g+1)*n/G) — a contiguous Philox counter range — and the data is
-replicated.  The only exchanges are integer all-reduces (SUM): the z0 / pval
-counts and the per-pass radix histograms of the order-statistic select, plus an
-all-gather of the statistic shards when the caller asks for the distribution.
-Integer sums are order-independent, so results are bit-identical for any G."""
+replicated.  A small statistic vector (the usual case) is all-gathered once and
+every rank finishes on the whole vector, which is the unsharded run's by
+construction; a large one stays sharded and the only exchanges are integer
+all-reduces (SUM): the z0 / pval counts and the per-pass radix histograms of the
+order-statistic select, plus an all-gather of the shards when the caller asks for
+the distribution.  Integer sums are order-independent, so either way results are
+bit-identical for any G."""
 from __future__ import annotations
 
 from typing import Optional, Tuple
