@@ -627,7 +627,9 @@ int b200boot_select(const double* stat, int64_t n_local, int64_t n_cols, const i
     // short columns: the whole descent in one launch per group of selects
     for (int a0 = 0; a0 < n_alphas; a0 += kSelMaxAlphas) {
       const int ac = std::min(kSelMaxAlphas, n_alphas - a0);
-      k5_select_small_kernel<<<(unsigned)n_cols, kSelSmallThreads, 0, as_stream(stream)>>>(
+      // 8 warps walk the bins of up to 8 selects; more threads only pay off for longer columns
+      const int threads = n_local <= 2048 ? 256 : (n_local <= 8192 ? 512 : kSelSmallThreads);
+      k5_select_small_kernel<<<(unsigned)n_cols, threads, 0, as_stream(stream)>>>(
           stat, n_local, n_cols, ranks, a0, ac, out);
       B2_LAUNCH_CHECK();
     }

@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(kSelSmallThreads) k5_select_small_kernel(
   __shared__ uint64_t s_prefix[kSelMaxAlphas];
   __shared__ long long s_krem[kSelMaxAlphas];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthreads = blockDim.x;                 // 256 .. 1024 by column length, >= 32 * a_cnt
   const int64_t d = blockIdx.x;
   const double* col = stat + d * n;
   if (tid < a_cnt) {
@@ -173,10 +174,10 @@ __global__ void __launch_bounds__(kSelSmallThreads) k5_select_small_kernel(
     s_krem[tid] = ranks[(int64_t)(a_lo + tid) * n_cols + d];
   }
   for (int pass = 0; pass < 8; ++pass) {
-    for (int i = tid; i < a_cnt * 256; i += kSelSmallThreads) (&s_hist[0][0])[i] = 0;
+    for (int i = tid; i < a_cnt * 256; i += nthreads) (&s_hist[0][0])[i] = 0;
     __syncthreads();
     const int shift = 56 - 8 * pass;
-    for (int64_t r = tid; r < n; r += kSelSmallThreads) {
+    for (int64_t r = tid; r < n; r += nthreads) {
       const uint64_t k = key_of(col[r]);
       const unsigned int digit = (unsigned int)(k >> shift) & 0xFFu;
       for (int a = 0; a < a_cnt; ++a)
