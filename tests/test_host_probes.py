@@ -397,3 +397,70 @@ def test_interval_math_matches_oracle(golden):
             b, fb = iv._order_indices_array(av, n)
         np.testing.assert_array_equal(a, b)
         assert fa == fb and a.dtype == b.dtype
+
+
+def test_rank_rule_reproduces_numpy_quantile_bitwise():
+    """The host fixes which two order statistics np.quantile(x, q) reads and the weight between
+    them (_device.rank_rule); the kernels only fetch and combine.  Applying the rule on the host
+    with numpy's _lerp formula must give np.quantile itself, bit for bit, for samples of n and of
+    n - 1 values (the leave-one-out rule)."""
+    rule = lambda n, q: _device_mod().rank_rule(n, q)
+    rng = np.random.default_rng(0)
+
+    def lerp(a, b, t):
+        d = b - a
+        return b - d * (1 - t) if t >= 0.5 else a + d * t
+
+    qs = [0.0, 1.0, 0.5, 0.25, 0.1, 0.9, 0.975, 1 / 3, 2 / 3, 1e-9, 1 - 1e-9]
+    for n in [1, 2, 3, 4, 5, 7, 10, 11, 100, 101, 1000, 4097, 28672, 100003]:
+        x = np.sort(rng.standard_normal(n))
+        for q in qs + list(rng.random(6)):
+            r = rule(n, q)
+            assert 0 <= r.k_lo <= r.k_hi <= min(r.k_lo + 1, n - 1) and r.mode == 1
+            got = x[r.k_hi] if r.k_lo == r.k_hi else lerp(x[r.k_lo], x[r.k_hi], r.gamma)
+            assert got == np.quantile(x, q), (n, q)
+            if n > 1:
+                y = x[:-1]
+                got = y[r.loo_k_hi] if r.loo_k_lo == r.loo_k_hi else lerp(y[r.loo_k_lo], y[r.loo_k_hi], r.loo_gamma)
+                assert got == np.quantile(y, q), (n, q, "loo")
+    assert rule(10, None) is None                      # np.median: the library's own rule
+
+
+def test_registry_recognises_quantiles_fits_and_differences():
+    import functools
+    reg = _registry_mod()
+    spec = reg.lookup(functools.partial(np.percentile, q=90))
+    assert spec.stat_id == _abi.STAT_MEDIAN and spec.q == 0.9 and not spec.axis0
+    spec = reg.lookup(functools.partial(np.quantile, q=0.25, axis=0, method="linear"))
+    assert spec.q == 0.25 and spec.axis0
+    assert reg.lookup(functools.partial(np.quantile, q=0.5, method="nearest")) is None
+    assert reg.lookup(functools.partial(np.quantile, q=0.5, axis=1)) is None
+    assert reg.lookup(functools.partial(np.quantile, q=[0.1, 0.9])) is None
+    with pytest.raises(ValueError, match="range"):
+        reg.quantile(1.5)
+    assert reg.percentile(50).spec.q == 0.5
+    fit = reg.linear_fit
+    assert fit.spec.n_out == 2 and fit.spec.n_arrays == 2 and fit.spec.stat_id == _abi.STAT_LINEAR_FIT
+    a, b = np.arange(10.0), np.arange(10.0) * 2 + 1
+    np.testing.assert_allclose(fit(a, b), [2.0, 1.0], atol=1e-12)
+    d = reg.diff_of(np.median)
+    assert d.spec.independent and d.spec.stat_id == _abi.STAT_MEDIAN and d(a, b) == np.median(a) - np.median(b)
+    assert reg.diff_of(reg.quantile(0.8)).spec.q == 0.8
+    with pytest.raises(NotImplementedError):
+        reg.diff_of(reg.pearson_r)
+    with pytest.raises(NotImplementedError):
+        reg.require(lambda v: v.mean())
+    # which form serves (N, D) moment statistics: the measured crossover
+    dev = _device_mod()
+    assert dev.gemm_pays(1000, 10000) and dev.gemm_pays(7000, 8) and dev.gemm_pays(100000, 32)
+    assert not dev.gemm_pays(1000, 16) and not dev.gemm_pays(7000, 4) and not dev.gemm_pays(100000, 31)
+
+
+def _device_mod():
+    from scikits_bootstrap_b200 import _device
+    return _device
+
+
+def _registry_mod():
+    from scikits_bootstrap_b200 import _registry
+    return _registry
