@@ -26,6 +26,10 @@ STATS = {
     "median_axis0": lambda a: np.median(a, axis=0),
     "mean_axis0": lambda a: np.mean(a, axis=0),
     "diff_of_means": lambda a, b: np.mean(a) - np.mean(b),
+    # the statistic of the reference's paired tests (tests/bootstrap_test.py:211-238, 286-355)
+    "linear_fit": lambda a, b: np.polyfit(a, b, 1),
+    "percentile90": lambda x: np.percentile(x, 90),
+    "quantile25_axis0": lambda a: np.quantile(a, 0.25, axis=0),
 }
 
 
@@ -69,4 +73,7 @@ CASES = [
     ("normal2d_mean_axis0", ("normal2d", 9, 64, 5), "mean_axis0", None, 1500, (0.1, 0.9)),
     ("indep_diff", ("gamma2_unequal", 20, 21, 60, 45), "diff_of_means", "independent", 1500,
      (0.025, 0.975)),
+    ("gamma200_polyfit", ("gamma2", 22, 23, 200), "linear_fit", "paired", 2000, (0.025, 0.975)),
+    ("normal300_p90", ("normal", 24, 300), "percentile90", None, 2000, (0.025, 0.975)),
+    ("normal2d_q25_axis0", ("normal2d", 25, 101, 7), "quantile25_axis0", None, 1500, (0.05, 0.95)),
 ]

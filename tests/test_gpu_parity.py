@@ -35,6 +35,7 @@ DEVICE_STATS = {
     "ratio_of_means": boot.ratio_of_means, "weighted_average": boot.weighted_average,
     "pearson_r": boot.pearson_r, "linear_fit": boot.linear_fit, "median_axis0": boot.median_axis0, "mean_axis0": boot.mean_axis0,
     "diff_of_means": boot.diff_of_means,
+    "percentile90": boot.percentile(90), "quantile25_axis0": boot.quantile_axis0(0.25),
 }
 JACK = {
     "sum": lambda x: np.sum(x) - np.asarray(x, dtype=float),
@@ -103,11 +104,13 @@ def test_index_supplied_matches_reference_fixture(case, golden):
     data = tdata if multi else tdata[0]
     f = DEVICE_STATS[stat]
     idx = pcg_indices(len(tdata[0]), n)
+    # np.polyfit solves its least squares by SVD, the device from centred moment sums
+    rtol = 1e-9 if stat == "linear_fit" else RTOL
     for method in ("pi", "bca"):
         out, dist = boot.ci_indexed(data, f, idx, alpha=alphas, method=method, multi=multi,
                                     return_dist=True)
-        assert_allclose(dist, golden[f"{name}/dist"], rtol=RTOL, atol=1e-15)
-        assert_allclose(out, golden[f"{name}/{method}/lowhigh"], rtol=RTOL, atol=1e-15)
+        assert_allclose(dist, golden[f"{name}/dist"], rtol=rtol, atol=1e-15)
+        assert_allclose(out, golden[f"{name}/{method}/lowhigh"], rtol=rtol, atol=1e-15)
         eb = boot.ci_indexed(data, f, idx, alpha=alphas, method=method, multi=multi, output="errorbar")
         assert eb.shape == golden[f"{name}/{method}/errorbar"].shape
         assert_allclose(eb, golden[f"{name}/{method}/errorbar"], rtol=1e-9, atol=1e-13)
