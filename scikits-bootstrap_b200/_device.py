@@ -363,13 +363,6 @@ def resample_median_columns_indexed(data2d, indices, rule=None):
 MEDIAN_RESIDENT_ROWS = 28672     # csrc/k1m_median.cuh: kMedMaxRows
 
 
-def sorted_copy(x1d):
-    """Ascending device sort of a 1-D float64 tensor (copy)."""
-    s = x1d.reshape(1, -1).clone()
-    sort_columns(s)
-    return s.reshape(-1)
-
-
 def resample_median_sorted(sorted_vals, seed: int, lo: int, hi: int, out=None, rule=None):
     """K1mt: median of sorted_vals[bootstrap indices] for resamples [lo, hi) -> float64[1][hi-lo]."""
     torch = _torch()
