@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(256) k6_counts_from_indices_kernel(const int64
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
     const int64_t r = e / n_rows;
-    atomicAdd(out + r * n_rows + idx[e], 1.0);
+    const int64_t i = idx[e];
+    if ((uint64_t)i < (uint64_t)n_rows) atomicAdd(out + r * n_rows + i, 1.0);   // out-of-range entries are ignored
   }
 }
 
