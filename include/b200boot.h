@@ -79,6 +79,8 @@ typedef struct b200boot_plan {
 } b200boot_plan;
 
 int b200boot_version(void);
+/* Philox4x32 rounds of every stream of this build (7; 10 with -DB2_PHILOX_ROUNDS=10). */
+int b200boot_philox_rounds(void);
 const char* b200boot_last_error(void);
 
 /* Tile plan for N rows of `n_arrays` paired float64 arrays. */
@@ -224,6 +226,14 @@ int b200boot_fill_subsample(uint64_t seed, int64_t n_rows, int64_t size, int64_t
 int b200boot_tile_counts(uint64_t seed, int64_t n_rows, int n_arrays, int64_t resample_lo,
                          int64_t resample_hi, int32_t* counts, int32_t* class_counts, void* stream);
 
+/* The same occupancies as the resample path computes them (two-level tile chains, class split
+ * tree level by level): class_counts uint16[n_full][n_local][16].  Values equal
+ * b200boot_tile_counts'.  ws: b200boot_tile_counts_packed_ws_bytes(n_rows, n_arrays, n_local). */
+size_t b200boot_tile_counts_packed_ws_bytes(int64_t n_rows, int n_arrays, int64_t n_local);
+int b200boot_tile_counts_packed(uint64_t seed, int64_t n_rows, int n_arrays, int64_t resample_lo,
+                                int64_t resample_hi, int32_t* counts, uint16_t* class_counts,
+                                void* ws, size_t ws_bytes, void* stream);
+
 /* Plain gather out[i] = data[idx[i]] (bit-exactness probe for bootstrap.py:431). */
 int b200boot_gather(const double* data, int64_t n_rows, const int64_t* idx, int64_t n_idx,
                     double* out, void* stream);
@@ -283,9 +293,12 @@ int b200boot_profile_last_k1_ms(float* ms);
 
 /* Host-side probes built from the same __host__ __device__ sources as the
  * kernels (no GPU needed); used by the CPU test-suite only. */
-void b200boot_host_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void b200boot_host_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);   /* 10 rounds */
+void b200boot_host_philox4x32_r(int rounds /* 7 or 10 */, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 int64_t b200boot_host_binomial(uint64_t seed, int64_t resample, int64_t cell, int64_t n,
                                double p);
+/* Bin(n, 1/2) as the nodes of the bank-class split tree draw it (popcount below 20, BTRS above) */
+int64_t b200boot_host_binomial_half(uint64_t seed, int64_t resample, int64_t cell, int64_t n);
 int b200boot_host_tile_counts(uint64_t seed, int64_t n_rows, int n_arrays, int64_t resample,
                               int32_t* counts /* [n_tiles] */);
 int b200boot_host_class_counts(uint64_t seed, int64_t resample, int64_t tile, int64_t n_tile_draws,

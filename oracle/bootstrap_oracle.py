@@ -485,11 +485,16 @@ PHILOX_W1 = 0xBB67AE85
 _U32 = np.uint64(0xFFFFFFFF)
 
 
-def philox4x32_10(ctr: np.ndarray, key: Tuple[int, int]) -> np.ndarray:
+# Rounds of the device streams (csrc/philox.cuh: B2_PHILOX_ROUNDS, default 7); a test run
+# against a library built with another count sets this from b200boot_philox_rounds().
+PHILOX_ROUNDS = 7
+
+
+def philox4x32(ctr: np.ndarray, key: Tuple[int, int], rounds: int = None) -> np.ndarray:
     """ctr: (..., 4) uint32 counters; key: (k0, k1).  Returns (..., 4) uint32."""
     c = np.asarray(ctr, dtype=np.uint64).copy()
     k0, k1 = int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF
-    for _ in range(10):
+    for _ in range(PHILOX_ROUNDS if rounds is None else rounds):
         p0 = PHILOX_M0 * c[..., 0]
         p1 = PHILOX_M1 * c[..., 2]
         n0 = (p1 >> np.uint64(32)) ^ c[..., 1] ^ np.uint64(k0)
@@ -500,6 +505,10 @@ def philox4x32_10(ctr: np.ndarray, key: Tuple[int, int]) -> np.ndarray:
         k0 = (k0 + PHILOX_W0) & 0xFFFFFFFF
         k1 = (k1 + PHILOX_W1) & 0xFFFFFFFF
     return c.astype(np.uint32)
+
+
+def philox4x32_10(ctr: np.ndarray, key: Tuple[int, int]) -> np.ndarray:
+    return philox4x32(ctr, key, 10)
 
 
 # Counter layout (must match csrc/philox.cuh):
@@ -540,7 +549,7 @@ def class_draws(seed: int, resample: int, tile: int, c: int, n_draws: int, log2_
     word gives three (log2_tile-4)-bit row numbers j_A=(w>>7)&m, j_B=(w>>17)&m,
     j_C=rotl(w,5)&m; the row is j*16 + c.  12 draws per block."""
     nblk = (n_draws + CLASS_DRAWS_PER_BLOCK - 1) // CLASS_DRAWS_PER_BLOCK
-    words = philox4x32_10(_ctr(np.arange(nblk), class_cell_id(tile, c), resample, PURPOSE_INDEX),
+    words = philox4x32(_ctr(np.arange(nblk), class_cell_id(tile, c), resample, PURPOSE_INDEX),
                           seed_key(seed)).astype(np.uint32)
     m = np.uint32((1 << (log2_tile - 4)) - 1)
     ja = (words >> np.uint32(7)) & m
@@ -557,7 +566,7 @@ def cell_draws_lemire(seed: int, resample: int, cell: int, n_draws: int, size: i
     rejected and redrawn from the PURPOSE_REDRAW stream keyed by the position."""
     nblk = (n_draws + 3) // 4
     key = seed_key(seed)
-    words = philox4x32_10(_ctr(np.arange(nblk), cell, resample, purpose), key)
+    words = philox4x32(_ctr(np.arange(nblk), cell, resample, purpose), key)
     words = words.reshape(-1)[:n_draws].astype(np.uint64)
     prod = words * np.uint64(size)
     idx = (prod >> np.uint64(32)).astype(np.int64)
@@ -568,7 +577,7 @@ def cell_draws_lemire(seed: int, resample: int, cell: int, n_draws: int, size: i
         while True:
             c = _ctr(np.array([p]), cell, resample, PURPOSE_REDRAW)
             c[..., 3] |= np.uint64((attempt // 4) << 20)
-            w = int(philox4x32_10(c, key)[0, attempt % 4])
+            w = int(philox4x32(c, key)[0, attempt % 4])
             pr = w * size
             if (pr & 0xFFFFFFFF) >= thresh:
                 idx[p] = pr >> 32
@@ -660,7 +669,7 @@ def device_subsample(seed: int, sample: int, n_obs: int, size: int) -> np.ndarra
     """First `size` rows of the permutation that sorts the 63-bit Philox keys
     (ties broken by row number)."""
     nblk = (n_obs + 1) // 2
-    w = philox4x32_10(_ctr(np.arange(nblk), 0, sample, PURPOSE_SHUFFLE), seed_key(seed)).astype(np.uint64)
+    w = philox4x32(_ctr(np.arange(nblk), 0, sample, PURPOSE_SHUFFLE), seed_key(seed)).astype(np.uint64)
     keys = np.stack(((w[:, 0] << np.uint64(32)) | w[:, 1], (w[:, 2] << np.uint64(32)) | w[:, 3]), axis=1)
     keys = (keys.reshape(-1)[:n_obs]) >> np.uint64(1)
     return np.lexsort((np.arange(n_obs), keys))[:size].astype(np.int64)

@@ -9,7 +9,8 @@ import os
 import threading
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libb200boot.so")
+# B200BOOT_LIB_PATH: development aid (tools/k1_variants.py times experimental builds)
+LIB_PATH = os.environ.get("B200BOOT_LIB_PATH") or os.path.join(_PKG_DIR, "libb200boot.so")
 
 ABI_VERSION = 1
 
@@ -40,6 +41,7 @@ _vp, _i64, _u64, _int, _sz = C.c_void_p, C.c_int64, C.c_uint64, C.c_int, C.c_siz
 # name -> (restype, argtypes); mirrors include/b200boot.h one to one
 SIGNATURES = {
     "b200boot_version": (_int, []),
+    "b200boot_philox_rounds": (_int, []),
     "b200boot_last_error": (C.c_char_p, []),
     "b200boot_make_plan": (_int, [_i64, _int, C.POINTER(Plan)]),
     "b200boot_workspace_bytes": (_sz, [_int, _i64, _int, _i64, _i64, _int]),
@@ -61,6 +63,8 @@ SIGNATURES = {
     "b200boot_fill_moving_block": (_int, [_u64, _i64, _i64, _int, _i64, _i64, _vp, _vp]),
     "b200boot_fill_subsample": (_int, [_u64, _i64, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
     "b200boot_tile_counts": (_int, [_u64, _i64, _int, _i64, _i64, _vp, _vp, _vp]),
+    "b200boot_tile_counts_packed_ws_bytes": (_sz, [_i64, _int, _i64]),
+    "b200boot_tile_counts_packed": (_int, [_u64, _i64, _int, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "b200boot_gather": (_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "b200boot_jackknife": (_int, [_vp, _int, _i64, _int, _vp, _vp, _sz, _vp]),
     "b200boot_jackknife_median_columns": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp, _vp]),
@@ -76,7 +80,9 @@ SIGNATURES = {
     "b200boot_profile_enable": (_int, [_int]),
     "b200boot_profile_last_k1_ms": (_int, [C.POINTER(C.c_float)]),
     "b200boot_host_philox4x32": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "b200boot_host_philox4x32_r": (None, [_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "b200boot_host_binomial": (_i64, [_u64, _i64, _i64, _i64, C.c_double]),
+    "b200boot_host_binomial_half": (_i64, [_u64, _i64, _i64, _i64]),
     "b200boot_host_tile_counts": (_int, [_u64, _i64, _int, _i64, _vp]),
     "b200boot_host_class_counts": (_int, [_u64, _i64, _i64, _i64, _vp]),
     "b200boot_host_indices": (_int, [_u64, _i64, _int, _i64, _vp]),

@@ -428,6 +428,19 @@ def tile_counts(seed: int, n_rows: int, n_arrays: int, lo: int, hi: int, with_cl
     return (out, cls) if with_classes else out
 
 
+def tile_counts_packed(seed: int, n_rows: int, n_arrays: int, lo: int, hi: int):
+    """K0 as the resample path runs it: int32[n_tiles][hi-lo], uint16[n_full][hi-lo][16]."""
+    torch = require_cuda()
+    plan = _abi.make_plan(n_rows, n_arrays)
+    L = _abi.lib()
+    out = torch.empty((plan.n_tiles, hi - lo), dtype=torch.int32, device="cuda")
+    cls = torch.empty((plan.n_full, hi - lo, 16), dtype=torch.uint16, device="cuda")
+    ws = torch.empty(L.b200boot_tile_counts_packed_ws_bytes(n_rows, n_arrays, hi - lo), dtype=torch.uint8, device="cuda")
+    _abi.check(L.b200boot_tile_counts_packed(seed, n_rows, n_arrays, lo, hi, out.data_ptr(), cls.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), stream_ptr()))
+    return out, cls
+
+
 def gather(data, idx):
     torch = _torch()
     out = torch.empty(idx.numel(), dtype=torch.float64, device=data.device)

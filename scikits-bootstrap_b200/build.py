@@ -37,22 +37,26 @@ def needs_build() -> bool:
     return any(os.path.getmtime(s) > built for s in _sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compiles csrc/b200boot.cu into libb200boot.so; returns the library path."""
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """Compiles csrc/b200boot.cu into libb200boot.so; returns the library path.
+    `defines` (e.g. ["B2_K1_PIPE=1"]) and `out` build an experimental variant elsewhere."""
+    if out is None and not defines and not force and not needs_build():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found; cannot build libb200boot.so")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB_PATH, os.path.join(CSRC, "b200boot.cu")]
+        ["-D" + d for d in defines] + ["-o", out or LIB_PATH, os.path.join(CSRC, "b200boot.cu")]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
     if verbose:
         print(proc.stderr)
-    return LIB_PATH
+    return out or LIB_PATH
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[2:] for a in sys.argv[1:] if a.startswith("-o")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs,
+                out=outs[0] if outs else None))

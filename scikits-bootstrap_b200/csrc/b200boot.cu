@@ -38,11 +38,10 @@ inline int blocks_for(int64_t n, int threads, int64_t cap) {
 // ---- workspace layouts ---------------------------------------------------------
 struct ResampleWs {
   int32_t* counts;
-  int32_t* cls;         // [n_full][n_local][16]
+  uint16_t* cls;        // [n_full][n_local][16]
   int32_t* gcounts;     // [n_groups][n_local] level-1 occupancies
-  int32_t* left;        // class-chain scratch: remainders, deferred list, per-step counters
-  int32_t* pending;
-  int32_t* n_pending;
+  HalfConsts* half_table;   // BTRS constants of Bin(n, 1/2), n < kHalfTableSize
+  int32_t* overflow;    // set when a class count did not fit its uint16 slot
   double* partial;
   int32_t* work_counter;
   JackState* jack;
@@ -55,16 +54,13 @@ ResampleWs carve_resample(Carver& cv, const Plan& plan, int stat, int64_t n_loca
   const int ms = moment_set_of(stat);
   const int nm = ms == kMomSum ? 1 : (ms == kMomPair5 ? 5 : 2);
   w.work_counter = cv.take<int32_t>(64);
+  w.overflow = cv.take<int32_t>(64);          // directly behind the work counter: one memset clears both
   w.jack = cv.take<JackState>(1);
   w.red = cv.take<double>((size_t)kRedBlocks * kMaxMoments);
   w.counts = plan.n_tiles > 1 ? cv.take<int32_t>((size_t)plan.n_tiles * n_local) : nullptr;
   w.gcounts = plan.n_tiles > 1 ? cv.take<int32_t>((size_t)n_tile_groups(plan) * std::max<int64_t>(n_local, 1)) : nullptr;
-  w.cls = plan.n_full > 0 ? cv.take<int32_t>((size_t)plan.n_full * n_local * kClasses) : nullptr;
-  if (plan.n_full > 0) {
-    w.left = cv.take<int32_t>((size_t)plan.n_full * std::max<int64_t>(n_local, 1));
-    w.pending = cv.take<int32_t>((size_t)plan.n_full * std::max<int64_t>(n_local, 1));
-    w.n_pending = cv.take<int32_t>(64);
-  }
+  w.cls = plan.n_full > 0 ? cv.take<uint16_t>((size_t)plan.n_full * n_local * kClasses) : nullptr;
+  w.half_table = plan.n_full > 0 ? cv.take<HalfConsts>((size_t)kHalfTableSize) : nullptr;
   w.partial = cv.take<double>((size_t)plan.n_tiles * nm * std::max<int64_t>(n_local, 1));
   if (stat_needs_centering(stat))
     for (int a = 0; a < plan.n_arrays; ++a) w.centered[a] = cv.take<double>((size_t)plan.n_rows);
@@ -100,12 +96,9 @@ int prepare_rows(const double* const* data, int n_arrays, int64_t n_rows, int st
   return 0;
 }
 
-// K0: tile occupancies, then the 16-way class split of every full tile.  With chain
-// scratch (left / pending / n_pending) the split runs as 15 propose + resolve steps,
-// otherwise as one thread-per-pair chain kernel; both give the same values.
-int launch_occupancies(uint64_t seed, int64_t resample_lo, int64_t n_local, const Plan& plan,
-                       int32_t* counts, int32_t* cls, cudaStream_t s, int32_t* left = nullptr,
-                       int32_t* pending = nullptr, int32_t* n_pending = nullptr, int32_t* gcounts = nullptr) {
+// K0, tile level: occupancies of the cells (two-level chains when `gcounts` is given).
+int launch_tile_occupancies(uint64_t seed, int64_t resample_lo, int64_t n_local, const Plan& plan,
+                            int32_t* counts, int32_t* gcounts, cudaStream_t s) {
   if (plan.n_tiles <= 1) return 0;
   if (gcounts) {
     const int64_t ng = n_tile_groups(plan);
@@ -122,27 +115,41 @@ int launch_occupancies(uint64_t seed, int64_t resample_lo, int64_t n_local, cons
                                                                           counts);
     B2_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+// K0 as the inspection API and K2 see it: tile occupancies, then the 16-way class split of
+// every full tile as int32 records (one thread per pair walks the split tree).
+int launch_occupancies(uint64_t seed, int64_t resample_lo, int64_t n_local, const Plan& plan,
+                       int32_t* counts, int32_t* cls, cudaStream_t s) {
+  int rc = launch_tile_occupancies(seed, resample_lo, n_local, plan, counts, nullptr, s);
+  if (rc) return rc;
+  if (plan.n_full > 0 && cls) {
+    const int64_t total = plan.n_full * n_local;
+    const int64_t blocks = std::min<int64_t>((total + 127) / 128, (int64_t)sm_count() * 64);
+    k0_class_counts_kernel<<<(unsigned)blocks, 128, 0, s>>>(seed, resample_lo, n_local, plan.n_full, counts, cls);
+    B2_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// K0 of the resample path: two-level tile chains, then the class split tree level by level
+// (k0_class_tree_kernel) into uint16 records.  Same values as launch_occupancies.
+int launch_occupancies_fast(uint64_t seed, int64_t resample_lo, int64_t n_local, const Plan& plan,
+                            int32_t* counts, int32_t* gcounts, uint16_t* cls, HalfConsts* half_table,
+                            int32_t* overflow, cudaStream_t s) {
+  int rc = launch_tile_occupancies(seed, resample_lo, n_local, plan, counts, gcounts, s);
+  if (rc) return rc;
   if (plan.n_full > 0 && cls) {
     const int64_t total = plan.n_full * n_local;
     if (total >= ((int64_t)1 << 31)) return fail(B200BOOT_EINVAL, "too many (tile, resample) pairs");
-    if (left && pending && n_pending) {
-      B2_CUDA(cudaMemsetAsync(n_pending, 0, 64 * sizeof(int32_t), s));
-      const unsigned pb = (unsigned)((total + 255) / 256);
-      const unsigned rb = (unsigned)std::min<int64_t>((total / 8 + 127) / 128 + 1, (int64_t)sm_count() * 32);
-      for (int c = 0; c + 1 < kClasses; ++c) {
-        k0_class_step_propose_kernel<<<pb, 256, 0, s>>>(seed, resample_lo, n_local, plan.n_full, c, counts,
-                                                        left, cls, pending, n_pending + c);
-        B2_LAUNCH_CHECK();
-        k0_class_step_resolve_kernel<<<rb, 128, 0, s>>>(seed, resample_lo, n_local, c, left, cls, pending,
-                                                        n_pending + c);
-        B2_LAUNCH_CHECK();
-      }
-    } else {
-      const int64_t blocks = std::min<int64_t>((total + 127) / 128, (int64_t)sm_count() * 64);
-      k0_class_counts_kernel<<<(unsigned)blocks, 128, 0, s>>>(seed, resample_lo, n_local, plan.n_full, counts,
-                                                              cls);
-      B2_LAUNCH_CHECK();
-    }
+    k0_half_table_kernel<<<kHalfTableSize / 256, 256, 0, s>>>(half_table);
+    B2_LAUNCH_CHECK();
+    const int64_t n_batches = (total + kTreeBatch - 1) / kTreeBatch;
+    const int grid = (int)std::min<int64_t>(n_batches, (int64_t)sm_count() * 32);
+    k0_class_tree_kernel<<<grid, kTreeThreads, 0, s>>>(seed, resample_lo, n_local, plan.n_full, counts, half_table,
+                                                       cls, overflow);
+    B2_LAUNCH_CHECK();
   }
   return 0;
 }
@@ -243,6 +250,7 @@ int jack_passes(const double** rows, int64_t n_rows, int stat, ResampleWs& w, do
 extern "C" {
 
 int b200boot_version(void) { return B200BOOT_ABI_VERSION; }
+int b200boot_philox_rounds(void) { return kPhiloxRounds; }
 const char* b200boot_last_error(void) { return err_buf(); }
 
 int b200boot_make_plan(int64_t n_rows, int n_arrays, b200boot_plan* out) {
@@ -316,10 +324,10 @@ int b200boot_resample_stat_after(const double* const* data, int n_arrays, int64_
   rc = prepare_rows(data, n_arrays, n_rows, stat_id, w, rows, s);
   if (rc) return rc;
 
-  rc = launch_occupancies(seed, resample_lo, n_local, plan, w.counts, w.cls, s, w.left, w.pending, w.n_pending,
-                          w.gcounts);
+  B2_CUDA(cudaMemsetAsync(w.work_counter, 0, 512, s));   // work counter and (next 256 B) the overflow flag
+  rc = launch_occupancies_fast(seed, resample_lo, n_local, plan, w.counts, w.gcounts, w.cls, w.half_table,
+                               w.overflow, s);
   if (rc) return rc;
-  B2_CUDA(cudaMemsetAsync(w.work_counter, 0, 256, s));
   if (ready) B2_CUDA(cudaStreamWaitEvent(s, ready, 0));
 
   const int ms = moment_set_of(stat_id);
@@ -329,8 +337,9 @@ int b200boot_resample_stat_after(const double* const* data, int n_arrays, int64_
   // <= 512 (an item then lasts ~0.5 ms; reloading the cell costs ~3 us)
   int64_t want_chunks = ((int64_t)sms * 32 + plan.n_tiles - 1) / plan.n_tiles;
   int64_t chunk = (n_local + want_chunks - 1) / want_chunks;
-  chunk = ((chunk + kK1Warps - 1) / kK1Warps) * kK1Warps;
-  chunk = std::min<int64_t>(std::max<int64_t>(chunk, kK1Warps), 512);
+  const int64_t per_pass = kK1Warps * (B2_K1_PAIR ? 2 : 1);   // resamples a CTA works on at a time
+  chunk = ((chunk + per_pass - 1) / per_pass) * per_pass;
+  chunk = std::min<int64_t>(std::max<int64_t>(chunk, per_pass), 512);
   const int64_t n_chunks = (n_local + chunk - 1) / chunk;
 
   K1Params P{};
@@ -362,7 +371,7 @@ int b200boot_resample_stat_after(const double* const* data, int n_arrays, int64_
 
   k1_finish_kernel<<<blocks_for(n_local, 256, 1 << 30), 256, 0, s>>>(w.partial, plan.n_tiles, nm, n_local,
                                                                      stat_id, (double)n_rows, w.jack->center,
-                                                                     stat_out);
+                                                                     stat_out, w.overflow);
   B2_LAUNCH_CHECK();
   return 0;
 }
@@ -397,7 +406,7 @@ int b200boot_resample_stat_indexed(const double* const* data, int n_arrays, int6
   }
   if (rc) return rc;
   k1_finish_kernel<<<blocks_for(n_sets, 256, 1 << 30), 256, 0, s>>>(w.partial, 1, nm, n_sets, stat_id,
-                                                                    (double)n_rows, w.jack->center, stat_out);
+                                                                    (double)n_rows, w.jack->center, stat_out, nullptr);
   B2_LAUNCH_CHECK();
   return 0;
 }
@@ -409,6 +418,32 @@ int b200boot_tile_counts(uint64_t seed, int64_t n_rows, int n_arrays, int64_t re
   if (n_local == 0) return 0;
   const Plan plan = make_plan(n_rows, n_arrays);
   return launch_occupancies(seed, resample_lo, n_local, plan, counts, class_counts, as_stream(stream));
+}
+
+size_t b200boot_tile_counts_packed_ws_bytes(int64_t n_rows, int n_arrays, int64_t n_local) {
+  if (n_rows < 1 || n_arrays < 1 || n_local < 0) return 0;
+  const Plan plan = make_plan(n_rows, n_arrays);
+  return 4096 + pad256((size_t)n_tile_groups(plan) * std::max<int64_t>(n_local, 1) * 4) +
+         pad256((size_t)kHalfTableSize * sizeof(HalfConsts));
+}
+
+int b200boot_tile_counts_packed(uint64_t seed, int64_t n_rows, int n_arrays, int64_t resample_lo,
+                                int64_t resample_hi, int32_t* counts, uint16_t* class_counts,
+                                void* ws, size_t ws_bytes, void* stream) {
+  const int64_t n_local = resample_hi - resample_lo;
+  if (n_rows < 1 || n_arrays < 1 || n_local < 0 || !counts) return fail(B200BOOT_EINVAL, "bad arguments");
+  if (n_local == 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
+    return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
+  const Plan plan = make_plan(n_rows, n_arrays);
+  Carver cv(ws, ws_bytes);
+  int32_t* overflow = cv.take<int32_t>(64);
+  int32_t* gcounts = cv.take<int32_t>((size_t)n_tile_groups(plan) * n_local);
+  HalfConsts* table = cv.take<HalfConsts>((size_t)kHalfTableSize);
+  if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+  cudaStream_t s = as_stream(stream);
+  B2_CUDA(cudaMemsetAsync(overflow, 0, 256, s));
+  return launch_occupancies_fast(seed, resample_lo, n_local, plan, counts, gcounts, class_counts, table, overflow, s);
 }
 
 int b200boot_fill_indices(uint64_t seed, int64_t n_rows, int n_arrays, int64_t resample_lo,
@@ -841,6 +876,12 @@ void b200boot_host_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint
   for (int i = 0; i < 4; ++i) out[i] = w.w[i];
 }
 
+void b200boot_host_philox4x32_r(int rounds, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  const Words4 w = rounds == 7 ? philox4x32_r<7>(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1])
+                               : philox4x32_r<10>(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+  for (int i = 0; i < 4; ++i) out[i] = w.w[i];
+}
+
 int64_t b200boot_host_binomial(uint64_t seed, int64_t resample, int64_t cell, int64_t n, double p) {
   const Stream s = make_stream(seed, resample, (uint32_t)cell, kPurposeBinomial);
   if (n <= 0 || p <= 0.0) return 0;
@@ -849,6 +890,11 @@ int64_t b200boot_host_binomial(uint64_t seed, int64_t resample, int64_t cell, in
   const double pp = flip ? 1.0 - p : p;
   const int64_t k = ((double)n * pp >= 10.0) ? binomial_btrs(n, pp, s) : binomial_inversion(n, pp, s);
   return flip ? n - k : k;
+}
+
+int64_t b200boot_host_binomial_half(uint64_t seed, int64_t resample, int64_t cell, int64_t n) {
+  if (n <= 0) return 0;
+  return binomial_half(n, make_stream(seed, resample, (uint32_t)cell, kPurposeBinomial));
 }
 
 int b200boot_host_tile_counts(uint64_t seed, int64_t n_rows, int n_arrays, int64_t resample,
@@ -862,7 +908,7 @@ int b200boot_host_tile_counts(uint64_t seed, int64_t n_rows, int n_arrays, int64
 int b200boot_host_class_counts(uint64_t seed, int64_t resample, int64_t tile, int64_t n_tile_draws,
                                int32_t* counts16) {
   if (!counts16 || tile < 0 || n_tile_draws < 0) return fail(B200BOOT_EINVAL, "bad arguments");
-  class_count_chain<int32_t>(seed, resample, tile, n_tile_draws, counts16, 1);
+  class_count_tree<int32_t>(seed, resample, tile, n_tile_draws, counts16, 1);
   return 0;
 }
 
@@ -884,7 +930,7 @@ int b200boot_host_indices(uint64_t seed, int64_t n_rows, int n_arrays, int64_t r
     auto put = [&](int, int64_t pos, uint32_t idx) { out[offset + pos] = row0 + (int64_t)idx; };
     if (t < plan.n_full) {
       int32_t cls[kClasses];
-      class_count_chain<int32_t>(seed, resample, t, n, cls, 1);
+      class_count_tree<int32_t>(seed, resample, t, n, cls, 1);
       for (int c = 0; c < kClasses; ++c) {
         const Stream st = make_stream(seed, resample, class_cell_id(t, c), kPurposeIndex);
         for (uint32_t q = 0; (int64_t)q * kClassDrawsPerBlock < cls[c]; ++q)

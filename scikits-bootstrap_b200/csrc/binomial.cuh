@@ -166,4 +166,77 @@ B2_HD int64_t binomial_ratio(int64_t n, int64_t num, int64_t den, const Stream& 
   return flip ? n - k : k;
 }
 
+// ---- Bin(n, 1/2): the node sampler of the bank-class split tree ---------------------------
+// Every split of the class tree (draw.cuh, class_count_tree) is an even split, so one
+// sampler with p = 1/2 serves all of them and its BTRS constants depend on n alone:
+// kernels read them from a table built once per call by the same function (half_setup), so
+// table and direct evaluation agree bit for bit.
+//   n <  kHalfBtrsMin: the number of set bits among n random bits (exact, no rejection);
+//   n >= kHalfBtrsMin: BTRS with p = 1/2, r = 1 — the same arithmetic as binomial_btrs.
+constexpr int64_t kHalfBtrsMin = 20;      // n * p >= 10
+
+struct HalfConsts {
+  double b, a, v_r, alpha;
+};
+
+B2_HD HalfConsts half_setup(int64_t n) {
+  const BtrsConsts q = btrs_setup(n, 0.5, 1.0);
+  HalfConsts h;
+  h.b = q.b;
+  h.a = q.a;
+  h.v_r = q.v_r;
+  h.alpha = q.alpha;
+  return h;
+}
+
+B2_HD BtrsConsts half_consts(int64_t n, const HalfConsts& h) {
+  BtrsConsts q;
+  q.nd = (double)n;
+  q.b = h.b;
+  q.a = h.a;
+  q.c = q.nd * 0.5 + 0.5;
+  q.v_r = h.v_r;
+  q.alpha = h.alpha;
+  q.r = 1.0;
+  q.m = floor((q.nd + 1.0) * 0.5);
+  return q;
+}
+
+B2_HD int popcount32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __popc(x);
+#else
+  return __builtin_popcount(x);
+#endif
+}
+
+// n < kHalfBtrsMin
+B2_HD int64_t binomial_half_small(int64_t n, const Words4& w) {
+  return n <= 0 ? 0 : (int64_t)popcount32(w.w[0] & ((1u << (int)n) - 1u));
+}
+
+// First attempt only: the value if block 0 settles it (small n, or a proposal accepted by
+// the squeeze), -1 if the node needs the full sampler (binomial_half).
+B2_HD int64_t binomial_half_first(int64_t n, const BtrsConsts& q, const Words4& w) {
+  if (n < kHalfBtrsMin) return binomial_half_small(n, w);
+  double k, inv_us, v;
+  return btrs_propose(q, w, &k, &inv_us, &v) > 0 ? (int64_t)k : -1;
+}
+
+// Bin(n, 1/2); `q` must be half_consts(n, half_setup(n) or its table entry)
+B2_HD int64_t binomial_half(int64_t n, const BtrsConsts& q, const Stream& s) {
+  if (n < kHalfBtrsMin) return binomial_half_small(n, stream_block(s, 0u));
+  for (uint32_t attempt = 0;; ++attempt) {
+    const Words4 w = stream_block(s, attempt);
+    double k, inv_us, v;
+    const int verdict = btrs_propose(q, w, &k, &inv_us, &v);
+    if (verdict > 0) return (int64_t)k;
+    if (verdict == 0 && btrs_accept(q, k, inv_us, v)) return (int64_t)k;
+  }
+}
+
+B2_HD int64_t binomial_half(int64_t n, const Stream& s) {
+  return binomial_half(n, half_consts(n, n >= kHalfBtrsMin ? half_setup(n) : HalfConsts{}), s);
+}
+
 }  // namespace b200boot

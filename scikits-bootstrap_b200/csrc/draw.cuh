@@ -94,10 +94,13 @@ B2_HD uint32_t lemire_threshold(uint32_t size) { return (uint32_t)(0u - size) % 
 // rows whose float64 sits in shared-memory bank pair (2c, 2c+1).  A lane that only
 // ever reads its own class never conflicts with the other 15 lanes of its half-warp.
 // The draws of a tile are therefore split over the classes (multinomial, 16 equal
-// cells; class_count_chain) and each class has its own stream, cell id
+// cells; class_count_tree) and each class has its own stream, cell id
 // 0x80000000 | t << 4 | c.  A Philox word yields three (L-4)-bit row numbers j:
 //   j_A = (w >> 7) & m,  j_B = (w >> 17) & m,  j_C = rotl(w, 5) & m      (m = 2^(L-4) - 1)
 // i.e. 12 draws per block; the row inside the tile is j * 16 + c.
+#ifndef B2_K1_SHF
+#define B2_K1_SHF 1     // field shifts on the ALU pipe, not as multiply-high (measured: -0.8 %)
+#endif
 constexpr int kClasses = 16;
 constexpr int kClassDrawsPerBlock = 12;
 
@@ -115,8 +118,8 @@ B2_HD uint32_t rotl32(uint32_t x, int r) {
 // class 0 for 8-byte elements); m7 = m << 7
 B2_HD void class_fields_shifted(uint32_t w, uint32_t m7, uint32_t* f) {
   f[0] = w & m7;
-#if defined(__CUDA_ARCH__)
-  // w >> 10 as a multiply-high keeps this shift off the (busier) ALU pipe
+#if defined(__CUDA_ARCH__) && !B2_K1_SHF
+  // w >> 10 as a multiply-high: off the ALU pipe, onto the one the Philox multiplies use
   uint32_t hi;
   asm("mul.hi.u32 %0, %1, 4194304;" : "=r"(hi) : "r"(w));
   f[1] = hi & m7;
@@ -142,19 +145,32 @@ B2_HD void class_block(const Stream& s, uint32_t q, uint32_t m7, int c, int64_t 
   }
 }
 
-// Splits the n_t draws of full tile t over its 16 equal classes (conditional
-// binomials with p = 1 / (16 - c)); out[c * stride].
+// Splits the n_t draws of full tile t over its 16 equal classes by a binary tree of even
+// splits: node (level l, index j) holds the draws of the classes [j * 16 >> l, (j+1) * 16 >> l)
+// and hands Bin(n, 1/2) of them to its lower half.  15 nodes, heap numbering
+// node = 2^l + j, each with its own stream (cell id 0x80000000 | t << 4 | node, purpose
+// binomial).  All nodes of a level are independent, so a kernel can run a level densely
+// (k0_class_tree_kernel); this sequential form is what K2, the host probes and single threads
+// use, and gives the same values.  out[c * stride].
+B2_HD uint32_t class_node_cell_id(int64_t t, int node) { return 0x80000000u | ((uint32_t)t << 4) | (uint32_t)node; }
+
 template <typename I>
-B2_HD void class_count_chain(uint64_t seed, int64_t resample, int64_t t, int64_t n_t, I* out,
-                             int64_t stride) {
-  int64_t n_left = n_t;
-  for (int c = 0; c + 1 < kClasses; ++c) {
-    const Stream s = make_stream(seed, resample, class_cell_id(t, c), kPurposeBinomial);
-    const int64_t k = binomial_ratio(n_left, 1, kClasses - c, s);
-    out[c * stride] = (I)k;
-    n_left -= k;
+B2_HD void class_count_tree(uint64_t seed, int64_t resample, int64_t t, int64_t n_t, I* out,
+                            int64_t stride) {
+  int64_t cnt[kClasses];
+  cnt[0] = n_t;
+  for (int node = 1; node < kClasses; ++node) {          // heap order: parents before children
+    int level = 0;
+    while ((2 << level) <= node) ++level;
+    const int span = kClasses >> level;                  // classes under a node of this level
+    const int first = (node - (1 << level)) * span;
+    const int64_t n = cnt[first];
+    const Stream s = make_stream(seed, resample, class_node_cell_id(t, node), kPurposeBinomial);
+    const int64_t k = binomial_half(n, s);
+    cnt[first] = k;
+    cnt[first + span / 2] = n - k;
   }
-  out[(kClasses - 1) * stride] = (I)n_left;
+  for (int c = 0; c < kClasses; ++c) out[c * stride] = (I)cnt[c];
 }
 
 // ---- tile occupancies -------------------------------------------------------

@@ -29,6 +29,12 @@ constexpr int kSmemHeader = 128;  // mbarrier + work-item slot
 // selects it only after a one-time probe kernel has confirmed, on this device, that the
 // dynamic shared memory of a static-shared-free kernel starts at 0x400
 // (probe_dynamic_smem_base_kernel); the kernel still traps if the assumption is violated.
+#ifndef B2_K1_PIPE
+#define B2_K1_PIPE 0
+#endif
+#ifndef B2_K1_PAIR
+#define B2_K1_PAIR 1    // two resamples per warp in full tiles (measured: -1.0 %)
+#endif
 #ifndef B2_CLASS_UNROLL
 #define B2_CLASS_UNROLL 1   // measured on B200: 1 -> 82.7 ms, 2 -> 85.3, 3 -> 87.9, 4 -> 87.1 (cfg5 / 5)
 #endif
@@ -73,13 +79,8 @@ __global__ void __launch_bounds__(128) k0_tiles_in_groups_kernel(uint64_t seed, 
   tile_chain_in_group<int32_t>(seed, resample_lo + rl, plan, g, n_g, counts + rl, n_local);
 }
 
-// Class occupancies of the full tiles: cls[(t * n_local + r) * 16 + c]; one thread
-// walks the 15-step conditional-binomial chain of one (tile, resample) pair.
-// Measured alternatives that were NOT faster on B200 (42 ms at cfg5 either way, see
-// DESIGN.md): a per-lane state machine that lets lanes advance independently (123
-// registers, 55 ms), and a warp-cooperative evaluation of the full acceptance test
-// (thread efficiency 12 -> 20 of 32, same time: the kernel is bound by issue slots of
-// the divergent proposal rounds, not by the FP64 pipe).
+// Class occupancies of the full tiles, inspection / K2 form: cls[(t * n_local + r) * 16 + c]
+// as int32; one thread walks the 15-node split tree of one (tile, resample) pair.
 __global__ void __launch_bounds__(128) k0_class_counts_kernel(uint64_t seed, int64_t resample_lo,
                                                               int64_t n_local, int64_t n_full,
                                                               const int32_t* __restrict__ counts,
@@ -88,78 +89,117 @@ __global__ void __launch_bounds__(128) k0_class_counts_kernel(uint64_t seed, int
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
     const int64_t t = e / n_local, rl = e - t * n_local;
-    class_count_chain<int32_t>(seed, resample_lo + rl, t, (int64_t)__ldg(counts + e), cls + e * kClasses, 1);
+    class_count_tree<int32_t>(seed, resample_lo + rl, t, (int64_t)__ldg(counts + e), cls + e * kClasses, 1);
   }
 }
 
-// Two-kernel form of the class chains used by the resample path: at chain step c every
-// (tile, resample) pair makes its FIRST proposal (setup + one BTRS proposal + squeeze,
-// no divergence); the ~14 % of pairs whose proposal needs the full acceptance test (or
-// whose occupancy is tiny) are appended to a compact list and resolved by a second
-// kernel in which every lane is on the expensive path.  Step c+1 then starts from the
-// updated remainders.  Values are identical to class_count_chain: the resolver simply
-// replays binomial_ratio from attempt 0.
-__global__ void __launch_bounds__(256) k0_class_step_propose_kernel(
-    uint64_t seed, int64_t resample_lo, int64_t n_local, int64_t n_full, int c,
-    const int32_t* __restrict__ counts, int32_t* __restrict__ left, int32_t* __restrict__ cls,
-    int32_t* __restrict__ pending, int32_t* __restrict__ n_pending) {
+// BTRS constants of Bin(n, 1/2) for every n below kHalfTableSize (entries below kHalfBtrsMin
+// are never read).  32 B per entry, 1 MB: L2-resident for the tree kernel.
+constexpr int kHalfTableSize = 32768;
+__global__ void __launch_bounds__(256) k0_half_table_kernel(HalfConsts* __restrict__ table) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < kHalfTableSize) table[n] = half_setup(n < kHalfBtrsMin ? kHalfBtrsMin : n);
+}
+
+// Resample-path form of the class split: a CTA takes a batch of (tile, resample) pairs, keeps
+// their 16-slot records in shared memory and walks the four levels of the split tree.  At a
+// level every node of the batch is independent: all threads first make the FIRST proposal of
+// their nodes (table lookup + one BTRS proposal + squeeze; dense, no divergence); the ~14 %
+// of nodes that need the full acceptance test go to a shared-memory queue and are then
+// resolved with every lane on the expensive path (binomial_half replays attempt 0).  One
+// launch, no global scratch; values are those of class_count_tree.  Output records are uint16
+// (a count beyond 65535 — never for 2^14-row tiles — saturates and raises *overflow, which the
+// finisher turns into NaN statistics).
+constexpr int kTreeThreads = 256;
+#ifndef B2_TREE_BATCH
+#define B2_TREE_BATCH 512
+#endif
+constexpr int kTreeBatch = B2_TREE_BATCH;  // pairs per CTA pass (node numbers of a level fit 16 bits)
+constexpr int kTreeRecStride = kClasses + 1;   // odd stride: slot reads of consecutive pairs spread over banks
+
+__device__ __forceinline__ BtrsConsts half_consts_lookup(int64_t n, const HalfConsts* __restrict__ table) {
+  if (n < kHalfBtrsMin) return half_consts(n, HalfConsts{});
+  if (n < kHalfTableSize) {
+    const double2 lo = __ldg(reinterpret_cast<const double2*>(table + n));
+    const double2 hi = __ldg(reinterpret_cast<const double2*>(table + n) + 1);
+    return half_consts(n, HalfConsts{lo.x, lo.y, hi.x, hi.y});
+  }
+  return half_consts(n, half_setup(n));
+}
+
+__global__ void __launch_bounds__(kTreeThreads, 3) k0_class_tree_kernel(
+    uint64_t seed, int64_t resample_lo, int64_t n_local, int64_t n_full,
+    const int32_t* __restrict__ counts, const HalfConsts* __restrict__ table,
+    uint16_t* __restrict__ cls, int32_t* __restrict__ overflow) {
+  __shared__ uint32_t s_rec[kTreeBatch * kTreeRecStride];
+  __shared__ uint32_t s_tile[kTreeBatch], s_res[kTreeBatch];
+  __shared__ uint16_t s_queue[kTreeBatch * 8];
+  __shared__ int s_qn[2];                  // queue length, one counter per level parity
+  const int tid = threadIdx.x;
   const int64_t total = n_full * n_local;
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int den = kClasses - c;
-  const double p = 1.0 / (double)den;
-  bool defer = false;
-  if (e < total) {
-    const int64_t n_left = c == 0 ? (int64_t)__ldg(counts + e) : (int64_t)left[e];
-    int64_t k = -1;
-    if (n_left <= 0) {
-      k = 0;
-    } else if ((double)n_left * p < 10.0) {
-      defer = true;
-    } else {
-      const int64_t t = e / n_local, rl = e - t * n_local;
-      const Stream st = make_stream(seed, resample_lo + rl, class_cell_id(t, c), kPurposeBinomial);
-      const BtrsConsts q = btrs_setup(n_left, p, p / (1.0 - p));
-      double kd, inv_us, v;
-      if (btrs_propose(q, stream_block(st, 0u), &kd, &inv_us, &v) > 0)
-        k = (int64_t)kd;
-      else
-        defer = true;
+  const int64_t n_batches = (total + kTreeBatch - 1) / kTreeBatch;
+  for (int64_t batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+    const int64_t e0 = batch * kTreeBatch;
+    const int np = (int)min((int64_t)kTreeBatch, total - e0);
+    for (int p = tid; p < np; p += kTreeThreads) {
+      const int64_t e = e0 + p;
+      const int64_t t = e / n_local;
+      s_tile[p] = (uint32_t)t;
+      s_res[p] = (uint32_t)(e - t * n_local);
+      s_rec[p * kTreeRecStride] = (uint32_t)__ldg(counts + e);
     }
-    if (!defer) {
-      cls[e * kClasses + c] = (int32_t)k;
-      left[e] = (int32_t)(n_left - k);
-      if (c == kClasses - 2) cls[e * kClasses + c + 1] = (int32_t)(n_left - k);
-    } else if (c == 0) {
-      left[e] = (int32_t)n_left;         // the resolver reads the remainder from `left`
+    if (tid == 0) s_qn[0] = 0;
+    __syncthreads();
+#pragma unroll 1
+    for (int level = 0; level < 4; ++level) {
+      int* qn_ptr = &s_qn[level & 1];
+      const int span = kClasses >> level;
+      const int n_nodes = np << level;
+      for (int i = tid; i < n_nodes; i += kTreeThreads) {
+        const int p = i >> level, j = i & ((1 << level) - 1);
+        uint32_t* slot = s_rec + p * kTreeRecStride + j * span;
+        const int64_t n = (int64_t)*slot;
+        const Stream st = make_stream(seed, resample_lo + (int64_t)s_res[p],
+                                      class_node_cell_id((int64_t)s_tile[p], (1 << level) + j), kPurposeBinomial);
+        const int64_t k = binomial_half_first(n, half_consts_lookup(n, table), stream_block(st, 0u));
+        if (k >= 0) {
+          slot[0] = (uint32_t)k;
+          slot[span / 2] = (uint32_t)(n - k);
+        } else {
+          s_queue[atomicAdd(qn_ptr, 1)] = (uint16_t)i;
+        }
+      }
+      __syncthreads();
+      const int qn = *qn_ptr;
+      if (tid == 0) s_qn[(level + 1) & 1] = 0;   // nobody touches the other counter during this level
+      for (int q = tid; q < qn; q += kTreeThreads) {
+        const int i = s_queue[q];
+        const int p = i >> level, j = i & ((1 << level) - 1);
+        uint32_t* slot = s_rec + p * kTreeRecStride + j * span;
+        const int64_t n = (int64_t)*slot;
+        const Stream st = make_stream(seed, resample_lo + (int64_t)s_res[p],
+                                      class_node_cell_id((int64_t)s_tile[p], (1 << level) + j), kPurposeBinomial);
+        const int64_t k = binomial_half(n, half_consts_lookup(n, table), st);
+        slot[0] = (uint32_t)k;
+        slot[span / 2] = (uint32_t)(n - k);
+      }
+      __syncthreads();
     }
-  }
-  // block-aggregated append of the deferred pairs
-  __shared__ int s_base, s_count;
-  if (threadIdx.x == 0) s_count = 0;
-  __syncthreads();
-  int slot = 0;
-  if (defer) slot = atomicAdd(&s_count, 1);
-  __syncthreads();
-  if (threadIdx.x == 0 && s_count > 0) s_base = atomicAdd(n_pending, s_count);
-  __syncthreads();
-  if (defer) pending[s_base + slot] = (int32_t)e;      // e < 2^31 (checked by the host)
-}
-
-__global__ void __launch_bounds__(128, 8) k0_class_step_resolve_kernel(
-    uint64_t seed, int64_t resample_lo, int64_t n_local, int c, int32_t* __restrict__ left,
-    int32_t* __restrict__ cls, const int32_t* __restrict__ pending, const int32_t* __restrict__ n_pending) {
-  const int n = *n_pending;
-  const int den = kClasses - c;
-  const int stride = gridDim.x * blockDim.x;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int64_t e = pending[i];
-    const int64_t t = e / n_local, rl = e - t * n_local;
-    const int64_t n_left = left[e];
-    const Stream st = make_stream(seed, resample_lo + rl, class_cell_id(t, c), kPurposeBinomial);
-    const int64_t k = binomial_ratio(n_left, 1, den, st);
-    cls[e * kClasses + c] = (int32_t)k;
-    left[e] = (int32_t)(n_left - k);
-    if (c == kClasses - 2) cls[e * kClasses + c + 1] = (int32_t)(n_left - k);
+    // packed store: two classes per 32-bit word, coalesced over the batch
+    uint32_t* out = reinterpret_cast<uint32_t*>(cls + e0 * kClasses);
+    bool sat = false;
+    for (int i = tid; i < np * (kClasses / 2); i += kTreeThreads) {
+      const int p = i >> 3, c = (i & 7) * 2;
+      uint32_t lo = s_rec[p * kTreeRecStride + c], hi = s_rec[p * kTreeRecStride + c + 1];
+      if (lo > 65535u || hi > 65535u) {
+        sat = true;
+        lo = min(lo, 65535u);
+        hi = min(hi, 65535u);
+      }
+      out[i] = lo | (hi << 16);
+    }
+    if (sat) atomicExch(overflow, 1);
+    __syncthreads();   // records are reloaded by the next batch
   }
 }
 
@@ -171,7 +211,7 @@ struct K1Params {
   int64_t resample_lo;
   int64_t n_local;
   const int32_t* counts;  // [n_tiles][n_local]; null when the plan has one cell
-  const int32_t* cls;     // [n_full][n_local][16] class occupancies of the full tiles
+  const uint16_t* cls;    // [n_full][n_local][16] class occupancies of the full tiles
   RoundKeys rk;           // Philox round keys of `seed` (constant-bank operands)
   double* partial;        // [(t * NM + m)][n_local]
   int32_t* work_counter;
@@ -210,6 +250,10 @@ struct LaneAcc {
   // single LDS.64 [R + imm] with no address arithmetic.
   __device__ __forceinline__ void take_fast(int j, uint32_t off) {
     double v[NA], c[NM];
+    // Pure asm (so the compiler schedules the twelve gathers of a block freely).  What keeps
+    // it behind the barrier that publishes a freshly copied cell is a data dependency: `off`
+    // contains the lane's class bits, which the kernel passes through an ordered
+    // (volatile, memory-clobbering) empty asm right after that barrier (publish_token).
     asm("ld.shared.f64 %0, [%1+%2];" : "=d"(v[0]) : "r"(off), "n"(kFastSmemBase));
     if (NA == 2)
       asm("ld.shared.f64 %0, [%1+%2];" : "=d"(v[NA - 1]) : "r"(off), "n"(kFastSmemBase + kFastStride2));
@@ -217,6 +261,8 @@ struct LaneAcc {
 #pragma unroll
     for (int m = 0; m < NM; ++m) acc[m][j % W] += c[m];
   }
+  // lane total -> sum over the warp (HALF: over the lane's half-warp)
+  template <bool HALF = false>
   __device__ __forceinline__ void finish(double* tot) {
 #pragma unroll
     for (int m = 0; m < NM; ++m) {
@@ -224,47 +270,80 @@ struct LaneAcc {
       for (int w = W / 2; w > 0; w >>= 1)
 #pragma unroll
         for (int i = 0; i < w; ++i) acc[m][i] += acc[m][i + w];
-      tot[m] = warp_sum(acc[m][0]);
+      double v = acc[m][0];
+#pragma unroll
+      for (int off = HALF ? 8 : 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      tot[m] = v;
     }
   }
 };
 
-// Full tile: lane = (class c = lane & 15, half h = lane >> 4).  The lane draws the
-// blocks q = h, h+2, ... of its class stream; every LDS.64 of a half-warp touches 16
-// distinct bank pairs (conflict-free).  12 draws per Philox block.
+// Returns x unchanged, but as a value the compiler must consider (re)defined here, after every
+// earlier memory operation and barrier: anything computed from it cannot be hoisted above.
+__device__ __forceinline__ uint32_t publish_token(uint32_t x) {
+  asm volatile("" : "+r"(x) : : "memory");
+  return x;
+}
+
+// Full tile: lane = (class c = lane & 15, half h = lane >> 4); every LDS.64 of a half-warp
+// touches 16 distinct bank pairs (conflict-free).  12 draws per Philox block.  The lane
+// draws the blocks q0, q0 + qstep, ... below n_blocks of its class stream:
+//   split mode (qstep 2): both halves work on one resample, h takes every second block;
+//   pair mode  (qstep 1): each half-warp owns its own resample (two resamples per warp), so
+//                         the per-resample prologue / epilogue / butterfly is paid once per
+//                         ~85 blocks instead of once per ~43.
+template <int MS, bool FAST>
+__device__ __forceinline__ void class_take12(LaneAcc<MS>& A, const Words4& w, uint32_t m7, uint32_t cbits,
+                                             const unsigned char* __restrict__ s_bytes,
+                                             uint32_t stride_bytes) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t f[3];
+    class_fields_shifted(w.w[i], m7, f);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (FAST)
+        A.take_fast(3 * i + k, f[k] | cbits);
+      else
+        A.take(3 * i + k, s_bytes, stride_bytes, f[k] | cbits);
+    }
+  }
+}
+
 template <int MS, bool FAST>
 __device__ __forceinline__ void class_accumulate(const unsigned char* __restrict__ s_bytes,
                                                  uint32_t stride_bytes, const RoundKeys& rk,
-                                                 const Stream& st, int64_t n_c, uint32_t m7,
-                                                 uint32_t cbits, uint32_t h, double* tot) {
-  LaneAcc<MS> A;
+                                                 const Stream& st, uint32_t n_c, uint32_t m7,
+                                                 uint32_t cbits, uint32_t q0, uint32_t qstep,
+                                                 LaneAcc<MS>& A) {
   A.clear();
-  // The lane owns blocks q = h, h+2, ... of the ceil(n_c / 12) blocks of its class.  All but
-  // its last one are whole and run unpredicated; the last one (whole or partial) runs in a
-  // predicated epilogue that every lane of the warp enters together, so a partial block
-  // never costs a separate, half-empty pass.
-  const uint32_t n_blocks = (uint32_t)((n_c + kClassDrawsPerBlock - 1) / kClassDrawsPerBlock);
-  const uint32_t owned = n_blocks > h ? (n_blocks - h + 1u) >> 1 : 0u;
-  const uint32_t q_last = h + 2u * (owned - 1u);          // meaningful when owned > 0
-#pragma unroll(kClassUnroll)
-  for (uint32_t q = h; q < q_last && owned != 0u; q += 2) {
-    const Words4 w = stream_block(st, q, rk);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint32_t f[3];
-      class_fields_shifted(w.w[i], m7, f);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        if (FAST)
-          A.take_fast(3 * i + k, f[k] | cbits);
-        else
-          A.take(3 * i + k, s_bytes, stride_bytes, f[k] | cbits);
-      }
-    }
+  // All owned blocks but the last are whole and run unpredicated; the last one (whole or
+  // partial) runs in a predicated epilogue that every lane of the warp enters together, so a
+  // partial block never costs a separate, half-empty pass.
+  const uint32_t n_blocks = (n_c + (uint32_t)kClassDrawsPerBlock - 1u) / (uint32_t)kClassDrawsPerBlock;
+  const uint32_t owned = n_blocks > q0 ? (n_blocks - q0 + qstep - 1u) / qstep : 0u;
+  const uint32_t q_last = q0 + qstep * (owned - 1u);          // meaningful when owned > 0
+#if B2_K1_PIPE
+  // software pipeline: the Philox rounds of block q + qstep are independent of the gathers
+  // of block q, so one loop body carries both and the instruction mix of a warp is uniform
+  // (multiplies, logic, loads and FP64 adds interleaved) instead of alternating between a
+  // multiply-bound and a load-bound phase
+  Words4 w = stream_block(st, q0, rk);
+  for (uint32_t q = q0; q < q_last && owned != 0u; q += qstep) {
+    const Words4 wn = stream_block(st, q + qstep, rk);
+    class_take12<MS, FAST>(A, w, m7, cbits, s_bytes, stride_bytes);
+    w = wn;
   }
+#else
+#pragma unroll(kClassUnroll)
+  for (uint32_t q = q0; q < q_last && owned != 0u; q += qstep) {
+    const Words4 w = stream_block(st, q, rk);
+    class_take12<MS, FAST>(A, w, m7, cbits, s_bytes, stride_bytes);
+  }
+  const Words4 w = stream_block(st, q_last, rk);
+#endif
   if (owned != 0u) {
-    const int valid = (int)min((int64_t)kClassDrawsPerBlock, n_c - (int64_t)q_last * kClassDrawsPerBlock);
-    const Words4 w = stream_block(st, q_last, rk);
+    const int valid = (int)min((uint32_t)kClassDrawsPerBlock, n_c - q_last * (uint32_t)kClassDrawsPerBlock);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       uint32_t f[3];
@@ -279,7 +358,6 @@ __device__ __forceinline__ void class_accumulate(const unsigned char* __restrict
         }
     }
   }
-  A.finish(tot);
 }
 
 // General cell (single-cell plans and the remainder cell): lanes take the blocks
@@ -358,18 +436,44 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_resample_kernel(const K1Para
       __syncthreads();
       resident = t;
     }
+    // the lane's class bits (byte offset of its bank pair), tied to this point of the program
+    const uint32_t cbits = publish_token((uint32_t)(lane & (kClasses - 1)) << 3);
 
     const int64_t r_begin = c * P.chunk;
     const int64_t r_end = min(r_begin + (int64_t)P.chunk, P.n_local);
     const bool full_tile = t < P.plan.n_full;
+#if B2_K1_PAIR
+    if (full_tile) {
+      // two resamples per warp: half-warp h owns resample rl0 + h, lane c of it the class c
+      const int c = lane & (kClasses - 1);
+      const int64_t h = lane >> 4;
+      for (int64_t rl0 = r_begin + 2 * warp; rl0 < r_end; rl0 += 2 * kK1Warps) {
+        const int64_t rl = rl0 + h;
+        const bool live = rl < r_end;
+        const uint32_t n_c = live ? (uint32_t)__ldg(P.cls + (t * P.n_local + rl) * kClasses + c) : 0u;
+        const Stream st = make_stream(P.seed, P.resample_lo + rl, class_cell_id(t, c), kPurposeIndex);
+        LaneAcc<MS> A;
+        class_accumulate<MS, FAST>(s_bytes, stride_bytes, P.rk, st, n_c, m7, cbits, 0u, 1u, A);
+        double tot[NM];
+        A.template finish<true>(tot);
+        if (c == 0 && live) {
+#pragma unroll
+          for (int m = 0; m < NM; ++m) P.partial[(t * NM + m) * P.n_local + rl] = tot[m];
+        }
+      }
+      continue;
+    }
+#endif
     for (int64_t rl = r_begin + warp; rl < r_end; rl += kK1Warps) {
       double tot[NM];
       if (full_tile) {
         const int c = lane & (kClasses - 1);
-        const int64_t n_c = (int64_t)__ldg(P.cls + (t * P.n_local + rl) * kClasses + c);
+        const uint32_t n_c = (uint32_t)__ldg(P.cls + (t * P.n_local + rl) * kClasses + c);
         const Stream st = make_stream(P.seed, P.resample_lo + rl, class_cell_id(t, c), kPurposeIndex);
-        class_accumulate<MS, FAST>(s_bytes, stride_bytes, P.rk, st, n_c, m7, (uint32_t)c << 3,
-                             (uint32_t)lane >> 4, tot);
+        LaneAcc<MS> A;
+        class_accumulate<MS, FAST>(s_bytes, stride_bytes, P.rk, st, n_c, m7, cbits,
+                                   (uint32_t)lane >> 4, 2u, A);
+        A.finish(tot);
       } else {
         const int64_t n = P.counts ? (int64_t)__ldg(P.counts + t * P.n_local + rl) : P.plan.n_rows;
         const Stream st = make_stream(P.seed, P.resample_lo + rl, (uint32_t)t, kPurposeIndex);
@@ -389,9 +493,12 @@ __global__ void __launch_bounds__(256) k1_finish_kernel(const double* __restrict
                                                         int64_t n_tiles, int nm, int64_t n_local,
                                                         int stat, double count,
                                                         const double* __restrict__ center,
-                                                        double* __restrict__ out) {
+                                                        double* __restrict__ out,
+                                                        const int32_t* __restrict__ overflow) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_local) return;
+  // a class count that did not fit its slot (see k0_class_tree_kernel): no valid statistic
+  const bool poisoned = overflow != nullptr && *overflow != 0;
   double m[kMaxMoments];
   for (int k = 0; k < nm; ++k) {
     double acc = 0.0;
@@ -400,7 +507,7 @@ __global__ void __launch_bounds__(256) k1_finish_kernel(const double* __restrict
   }
   const int n_out = stat_outputs(stat);
   for (int o = 0; o < n_out; ++o)
-    out[(int64_t)o * n_local + r] = finish_stat(stat_component(stat, o), m, count, center);
+    out[(int64_t)o * n_local + r] = poisoned ? nan("") : finish_stat(stat_component(stat, o), m, count, center);
 }
 
 // ------------------------------------------------------------------ K1i -------

@@ -780,7 +780,7 @@ __global__ void __launch_bounds__(kMtThreads) k1mt_median_tiled_kernel(const K1m
         const int64_t n_t = (int64_t)__ldg(P.counts + t_star * P.n_local + rl);
         if (t_star < plan.n_full) {
           if (tid == 0) {
-            class_count_chain<int32_t>(P.seed, r, t_star, n_t, s_cls, 1);
+            class_count_tree<int32_t>(P.seed, r, t_star, n_t, s_cls, 1);
             int acc = 0;
             for (int c = 0; c < kClasses; ++c) {
               s_blk[c] = acc;

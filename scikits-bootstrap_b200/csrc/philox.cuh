@@ -1,4 +1,4 @@
-// Philox4x32-10 counter-based generator (Salmon, Moraes, Dror, Shaw; SC'11) and
+// Philox4x32 counter-based generator (Salmon, Moraes, Dror, Shaw; SC'11; 7 rounds, see below) and
 // the counter layout every kernel shares.  Host+device so the CPU test-suite can
 // exercise the very same code (b200boot_host_* probes).
 //
@@ -33,10 +33,22 @@ struct Words4 {
   uint32_t w[4];
 };
 
-B2_HD Words4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                           uint32_t k1) {
+// Rounds used by every stream of the library: Philox4x32-7, the smallest round count the
+// SC'11 paper reports as Crush-resistant (it passes SmallCrush, Crush and BigCrush; -10 is
+// Random123's default and adds a safety margin).  Three rounds fewer are worth 20 % of the
+// whole resample kernel on B200 (profiles/r02_k1_variants.md), the
+// multiplies of the rounds being its busiest pipe.  -DB2_PHILOX_ROUNDS=10 builds the library
+// with the margin; b200boot_philox_rounds() reports what a build uses.
+#ifndef B2_PHILOX_ROUNDS
+#define B2_PHILOX_ROUNDS 7
+#endif
+constexpr int kPhiloxRounds = B2_PHILOX_ROUNDS;
+
+template <int ROUNDS>
+B2_HD Words4 philox4x32_r(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                          uint32_t k1) {
 #pragma unroll
-  for (int round = 0; round < 10; ++round) {
+  for (int round = 0; round < ROUNDS; ++round) {
     const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
     const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
     const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -54,6 +66,10 @@ B2_HD Words4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, u
   r.w[2] = c2;
   r.w[3] = c3;
   return r;
+}
+B2_HD Words4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                           uint32_t k1) {
+  return philox4x32_r<10>(c0, c1, c2, c3, k0, k1);
 }
 
 // Round keys hoisted out of the rounds: they depend on the seed only, so a kernel
@@ -75,9 +91,9 @@ B2_HD RoundKeys make_round_keys(uint64_t seed) {
   return rk;
 }
 
-B2_HD Words4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const RoundKeys& rk) {
+B2_HD Words4 philox4x32_keys(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const RoundKeys& rk) {
 #pragma unroll
-  for (int round = 0; round < 10; ++round) {
+  for (int round = 0; round < kPhiloxRounds; ++round) {
     const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
     const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
     const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk.k0[round];
@@ -114,11 +130,11 @@ B2_HD Stream make_stream(uint64_t seed, int64_t resample, uint32_t cell, uint32_
 }
 
 B2_HD Words4 stream_block(const Stream& s, uint32_t block) {
-  return philox4x32_10(block, s.c1, s.c2, s.c3, s.k0, s.k1);
+  return philox4x32_r<kPhiloxRounds>(block, s.c1, s.c2, s.c3, s.k0, s.k1);
 }
 // same stream with pre-expanded round keys (rk must come from the stream's seed)
 B2_HD Words4 stream_block(const Stream& s, uint32_t block, const RoundKeys& rk) {
-  return philox4x32_10(block, s.c1, s.c2, s.c3, rk);
+  return philox4x32_keys(block, s.c1, s.c2, s.c3, rk);
 }
 
 // 53-bit uniform in the open interval (0,1) from two words.

@@ -13,6 +13,13 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests", "golde
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the oracle's restatement of the device streams follows the round count of the built library
+    try:
+        import bootstrap_oracle as orc
+        from scikits_bootstrap_b200 import _abi
+        orc.PHILOX_ROUNDS = int(_abi.lib().b200boot_philox_rounds())
+    except Exception:  # library not built: the tests that need it fail on their own
+        pass
 
 
 def pytest_collection_modifyitems(config, items):

@@ -79,7 +79,7 @@ def test_abi_argument_validation_returns_status_codes():
     assert rs(ptrs, 1, 1000, _abi.STAT_MEAN, 0, 0, 10, fake, fake, 64, None) == EWORKSPACE
     assert b"too small" in L.b200boot_last_error()
     need = L.b200boot_workspace_bytes(_abi.STAT_MEAN, 10**7, 1, 1, 1000, 2)
-    assert need > 611 * 1000 * 4 * 17                 # tile + class occupancies at least
+    assert need > 611 * 1000 * (4 + 16 * 2)           # tile (int32) + class (uint16 x 16) occupancies at least
     assert L.b200boot_workspace_bytes(_abi.STAT_MEAN, 0, 1, 1, 10, 2) == 0
 
     # rank rule of the median / quantile entry points
@@ -127,6 +127,24 @@ def test_philox_kat_through_library():
         c = [int(v) for v in rng.integers(0, 2**32, 4)]
         k = [int(v) for v in rng.integers(0, 2**32, 2)]
         assert _philox(c, k) == [int(v) for v in orc.philox4x32_10(np.array([c], dtype=np.uint64), k)[0]]
+        assert _philox_r(7, c, k) == [int(v) for v in orc.philox4x32(np.array([c], dtype=np.uint64), k, 7)[0]]
+
+
+def _philox_r(rounds, c, k):
+    out = (C.c_uint32 * 4)()
+    _abi.lib().b200boot_host_philox4x32_r(rounds, (C.c_uint32 * 4)(*c), (C.c_uint32 * 2)(*k), out)
+    return list(out)
+
+
+def test_philox7_kat_through_library():
+    """Random123 kat_vectors, `philox4x32 7` lines — the round count of the library's streams."""
+    assert _abi.lib().b200boot_philox_rounds() in (7, 10)
+    assert orc.PHILOX_ROUNDS == _abi.lib().b200boot_philox_rounds()
+    assert _philox_r(7, [0] * 4, [0, 0]) == [0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48]
+    assert _philox_r(7, [0xffffffff] * 4, [0xffffffff] * 2) == [0x5207ddc2, 0x45165e59, 0x4d8ee751, 0x8c52f662]
+    assert _philox_r(7, [0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0x4dfccaba, 0x190a87f0, 0xc47362ba, 0xb6b5242a]
+    assert _philox_r(10, [0] * 4, [0, 0]) == _philox([0] * 4, [0, 0])
 
 
 def _host_indices(seed, n, n_arrays, r):
@@ -166,7 +184,7 @@ def test_lemire_redraw_path_matches_oracle():
     for r in range(3):
         want = orc.cell_draws_lemire(11, r, 0, 64, n)
         # reproduce through the library one block at a time via philox probe
-        words = [w for q in range(16) for w in _philox([q, 0, r, 0], [11, 0])]
+        words = [w for q in range(16) for w in _philox_r(orc.PHILOX_ROUNDS, [q, 0, r, 0], [11, 0])]
         thresh = (1 << 32) % n
         for p, w in enumerate(words):
             if (w * n) & 0xFFFFFFFF < thresh:
@@ -221,6 +239,29 @@ def test_binomial_sampler_distribution(n, p):
     keep = exp > 5
     chi2 = ((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum()
     assert chi2 < sps.chi2.ppf(1 - 1e-6, max(keep.sum() - 1, 1))
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 19, 20, 21, 100, 1024, 16384, 40000])
+def test_even_split_sampler_distribution(n):
+    """Bin(n, 1/2) of the class split tree: set bits of n random bits below 20, BTRS above."""
+    L = _abi.lib()
+    m = 20000
+    xs = np.array([L.b200boot_host_binomial_half(11, r, 5, n) for r in range(m)])
+    assert xs.min() >= 0 and xs.max() <= n
+    assert L.b200boot_host_binomial_half(11, 0, 5, 0) == 0
+    mean, var = n / 2, n / 4
+    assert abs(xs.mean() - mean) < 5 * np.sqrt(var / m)
+    assert abs(xs.var() - var) < 6 * var * np.sqrt(2.0 / m)
+    qs = np.unique(sps.binom.ppf(np.linspace(0, 1, 21)[1:-1], n, 0.5))
+    edges = np.concatenate(([-0.5], qs + 0.5, [n + 0.5]))
+    obs = np.histogram(xs, bins=edges)[0]
+    cdf = sps.binom.cdf(np.floor(edges[1:-1]), n, 0.5)
+    exp = np.diff(np.concatenate(([0.0], cdf, [1.0]))) * m
+    keep = exp > 5
+    chi2 = ((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum()
+    assert chi2 < sps.chi2.ppf(1 - 1e-6, max(keep.sum() - 1, 1))
+    # symmetric: k and n - k equally likely
+    assert abs((xs > n / 2).mean() - (xs < n / 2).mean()) < 5 / np.sqrt(m)
 
 
 def test_tile_counts_are_multinomial():

@@ -1,10 +1,14 @@
-"""Times individual library stages with CUDA events (development aid, not the bench)."""
-import sys, os, time
+"""Times individual library stages with CUDA events (development aid, not the bench).
+
+    python tools/microbench.py [n_samples] [--check]      # cfg5 data, N = 1e7
+"""
+import json, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import scikits_bootstrap_b200 as boot
 from scikits_bootstrap_b200 import _abi, _device
+import ctypes as C
 
 
 def timed(fn, reps=3):
@@ -18,18 +22,39 @@ def timed(fn, reps=3):
 
 
 def main():
-    n, m = 10**7, int(sys.argv[1]) if len(sys.argv) > 1 else 100000
-    plan = _abi.make_plan(n, 1)
-    counts = torch.empty((plan.n_tiles, m), dtype=torch.int32, device="cuda")
-    cls = torch.empty((plan.n_full, m, 16), dtype=torch.int32, device="cuda")
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    n, m = 10**7, int(args[0]) if args else 20000
     L = _abi.lib()
-    s = _device.stream_ptr()
-    t_all = timed(lambda: _abi.check(L.b200boot_tile_counts(1, n, 1, 0, m, counts.data_ptr(), cls.data_ptr(), s)))
-    t_tiles = timed(lambda: _abi.check(L.b200boot_tile_counts(1, n, 1, 0, m, counts.data_ptr(), None, s)))
-    print(f"K0 tile chain {t_tiles:.2f} ms, K0 + class split {t_all:.2f} ms (class split {t_all - t_tiles:.2f} ms)")
+    res = {"lib": os.path.basename(_abi.LIB_PATH), "n_samples": m}
+    res["k0_ms"] = timed(lambda: _device.tile_counts_packed(1, n, 1, 0, m))
     x = torch.from_numpy(np.random.default_rng(5).standard_normal(n) + 1.0).cuda()
-    t = timed(lambda: _device.resample_stat([x], _abi.STAT_MEAN, 1, 0, m))
-    print(f"resample_stat total {t:.2f} ms -> {n * m / t / 1e9:.1f} Gpts/s")
+    L.b200boot_profile_enable(1)
+    k1 = []
+    def run():
+        out = _device.resample_stat([x], _abi.STAT_MEAN, 1, 0, m)
+        ms = C.c_float()
+        _abi.check(L.b200boot_profile_last_k1_ms(C.byref(ms)))
+        k1.append(ms.value)
+        return out
+    res["total_ms"] = timed(run)
+    res["k1_ms"] = min(k1)
+    res["gpts_per_s"] = n * m / res["total_ms"] / 1e6
+    stat = run()
+    torch.cuda.synchronize()
+    res["stat_mean"] = float(stat.mean())
+    res["stat_std"] = float(stat.std())
+    res["stat0"] = [float(v) for v in stat[:3]]
+    if "--check" in sys.argv:
+        # fast K0 == sequential K0, and K1 == sum over the materialised indices
+        c1, k1c = _device.tile_counts_packed(7, n, 1, 0, 96)
+        c0, k0c = _device.tile_counts(7, n, 1, 0, 96, with_classes=True)
+        res["k0_tiles_equal"] = bool((c0 == c1).all())
+        res["k0_classes_equal"] = bool((k0c == k1c.to(torch.int32)).all())
+        idx = _device.fill_indices(1, n, 1, 0, 4)
+        want = x[idx].mean(dim=1)
+        got = _device.resample_stat([x], _abi.STAT_MEAN, 1, 0, 4)
+        res["k1_vs_indices_relerr"] = float(((got.flatten() - want) / want).abs().max())
+    print(json.dumps(res))
 
 
 if __name__ == "__main__":

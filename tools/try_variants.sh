@@ -1,9 +1,8 @@
 #!/bin/bash
-# runs tools/microbench.py against alternative builds of the library (development aid)
-cp scikits-bootstrap_b200/libb200boot.so /tmp/lib_base.so
-echo "== base"; python tools/microbench.py 20000 2>&1 | grep resample
+# runs tools/microbench.py against the library and every variants_tmp/*.so (development aid)
+cd "$(dirname "$0")/.."
+N=${1:-20000}
+echo "== base"; python tools/microbench.py $N --check 2>&1 | tail -1
 for f in variants_tmp/*.so; do
-  cp $f scikits-bootstrap_b200/libb200boot.so
-  echo "== $f"; python tools/microbench.py 20000 2>&1 | grep resample
+  echo "== $f"; B200BOOT_LIB_PATH=$PWD/$f python tools/microbench.py $N --check 2>&1 | tail -1
 done
-cp /tmp/lib_base.so scikits-bootstrap_b200/libb200boot.so
