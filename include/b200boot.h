@@ -290,6 +290,8 @@ int b200boot_sort_columns(double* stat, int64_t n, int64_t n_cols, void* ws, siz
 int64_t b200boot_launch_count(void);
 int b200boot_profile_enable(int on);
 int b200boot_profile_last_k1_ms(float* ms);
+/* the occupancy kernels (K0) and the K1 launch of the calling thread's last resample call */
+int b200boot_profile_last_ms(float* k0_ms, float* k1_ms);
 
 /* Host-side probes built from the same __host__ __device__ sources as the
  * kernels (no GPU needed); used by the CPU test-suite only. */

@@ -79,6 +79,7 @@ SIGNATURES = {
     "b200boot_launch_count": (_i64, []),
     "b200boot_profile_enable": (_int, [_int]),
     "b200boot_profile_last_k1_ms": (_int, [C.POINTER(C.c_float)]),
+    "b200boot_profile_last_ms": (_int, [C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "b200boot_host_philox4x32": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "b200boot_host_philox4x32_r": (None, [_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "b200boot_host_binomial": (_i64, [_u64, _i64, _i64, _i64, C.c_double]),

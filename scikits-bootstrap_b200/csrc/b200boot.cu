@@ -20,13 +20,14 @@ namespace {
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
-// optional event timing of the K1 launch (bench.py)
+// optional event timing of the occupancy kernels (K0) and of the K1 launch on the caller's
+// stream (bench.py); per host thread, like the calls it times
 struct K1Profile {
   bool enabled = false;
   bool valid = false;
-  cudaEvent_t start = nullptr, stop = nullptr;
+  cudaEvent_t begin = nullptr, start = nullptr, stop = nullptr;   // K0 from begin to start, K1 from start to stop
 };
-K1Profile g_prof;
+thread_local K1Profile g_prof;
 
 inline int blocks_for(int64_t n, int threads, int64_t cap) {
   int64_t b = (n + threads - 1) / threads;
@@ -40,7 +41,7 @@ struct ResampleWs {
   int32_t* counts;
   uint16_t* cls;        // [n_full][n_local][16]
   int32_t* gcounts;     // [n_groups][n_local] level-1 occupancies
-  HalfConsts* half_table;   // BTRS constants of Bin(n, 1/2), n < kHalfTableSize
+  HalfTables half_tables;   // BTRS constants of Bin(n, 1/2) and log(n!), n < kHalfTableSize
   int32_t* overflow;    // set when a class count did not fit its uint16 slot
   double* partial;
   int32_t* work_counter;
@@ -48,6 +49,13 @@ struct ResampleWs {
   double* red;          // block partials of the reductions
   double* centered[2];
 };
+
+HalfTables take_half_tables(Carver& cv) {
+  HalfTables t;
+  t.consts = cv.take<HalfConsts>((size_t)kHalfTableSize);
+  t.log_fact = cv.take<double>((size_t)kHalfTableSize);
+  return t;
+}
 
 ResampleWs carve_resample(Carver& cv, const Plan& plan, int stat, int64_t n_local) {
   ResampleWs w{};
@@ -60,7 +68,7 @@ ResampleWs carve_resample(Carver& cv, const Plan& plan, int stat, int64_t n_loca
   w.counts = plan.n_tiles > 1 ? cv.take<int32_t>((size_t)plan.n_tiles * n_local) : nullptr;
   w.gcounts = plan.n_tiles > 1 ? cv.take<int32_t>((size_t)n_tile_groups(plan) * std::max<int64_t>(n_local, 1)) : nullptr;
   w.cls = plan.n_full > 0 ? cv.take<uint16_t>((size_t)plan.n_full * n_local * kClasses) : nullptr;
-  w.half_table = plan.n_full > 0 ? cv.take<HalfConsts>((size_t)kHalfTableSize) : nullptr;
+  if (plan.n_full > 0) w.half_tables = take_half_tables(cv);
   w.partial = cv.take<double>((size_t)plan.n_tiles * nm * std::max<int64_t>(n_local, 1));
   if (stat_needs_centering(stat))
     for (int a = 0; a < plan.n_arrays; ++a) w.centered[a] = cv.take<double>((size_t)plan.n_rows);
@@ -136,18 +144,18 @@ int launch_occupancies(uint64_t seed, int64_t resample_lo, int64_t n_local, cons
 // K0 of the resample path: two-level tile chains, then the class split tree level by level
 // (k0_class_tree_kernel) into uint16 records.  Same values as launch_occupancies.
 int launch_occupancies_fast(uint64_t seed, int64_t resample_lo, int64_t n_local, const Plan& plan,
-                            int32_t* counts, int32_t* gcounts, uint16_t* cls, HalfConsts* half_table,
+                            int32_t* counts, int32_t* gcounts, uint16_t* cls, HalfTables half_tables,
                             int32_t* overflow, cudaStream_t s) {
   int rc = launch_tile_occupancies(seed, resample_lo, n_local, plan, counts, gcounts, s);
   if (rc) return rc;
   if (plan.n_full > 0 && cls) {
     const int64_t total = plan.n_full * n_local;
     if (total >= ((int64_t)1 << 31)) return fail(B200BOOT_EINVAL, "too many (tile, resample) pairs");
-    k0_half_table_kernel<<<kHalfTableSize / 256, 256, 0, s>>>(half_table);
+    k0_half_table_kernel<<<kHalfTableSize / 256, 256, 0, s>>>(half_tables);
     B2_LAUNCH_CHECK();
     const int64_t n_batches = (total + kTreeBatch - 1) / kTreeBatch;
     const int grid = (int)std::min<int64_t>(n_batches, (int64_t)sm_count() * 32);
-    k0_class_tree_kernel<<<grid, kTreeThreads, 0, s>>>(seed, resample_lo, n_local, plan.n_full, counts, half_table,
+    k0_class_tree_kernel<<<grid, kTreeThreads, 0, s>>>(seed, resample_lo, n_local, plan.n_full, counts, half_tables,
                                                        cls, overflow);
     B2_LAUNCH_CHECK();
   }
@@ -169,39 +177,47 @@ int check_moment_stat(int stat, int n_arrays, int64_t n_rows) {
 // FAST: the cell's shared-window address is a compile-time constant (see kFastSmemBase)
 template <int MS, bool FAST>
 int launch_k1_variant(const K1Params& P, size_t smem, int grid, cudaStream_t s) {
-  static bool configured[64] = {false};
-  int dev = 0;
-  B2_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
-    B2_CUDA(cudaFuncSetAttribute(k1_resample_kernel<MS, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(kSmemHeader + kSmemDataBytes)));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
-  }
+  static PerDeviceOnce configured;     // one per <MS, FAST> instantiation
+  B2_CUDA(configured.run([] {
+    return cudaFuncSetAttribute(k1_resample_kernel<MS, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(kSmemHeader + kSmemDataBytes));
+  }));
   k1_resample_kernel<MS, FAST><<<grid, kK1Threads, smem, s>>>(P);
   B2_LAUNCH_CHECK();
   return 0;
 }
 
-// One-time probe per device (synchronises once): is the dynamic shared memory of a kernel
-// without static shared memory at 0x400, as the FAST variants assume?
+// One-time probe per device, under std::call_once: is the dynamic shared memory of a kernel
+// without static shared memory at 0x400, as the FAST variants assume?  The probe runs on its
+// own non-blocking stream with a pinned result word, so it neither touches the legacy
+// stream nor allocates device memory; any failure selects the generic-address variants.
 inline bool fast_smem_addressing() {
-  static int cached[64] = {0};   // 0 unknown, 1 yes, 2 no
+  static PerDeviceOnce probed;
+  static std::atomic<int> verdict[kMaxDevices];   // 0 unknown / no, 1 yes
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
-  if (cached[dev] == 0) {
-    cached[dev] = 2;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return false;
+  probed.run([dev] {
     int reserved = 0;
-    uint32_t* d_out = nullptr;
-    uint32_t h_out = 0;
-    if (cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, dev) == cudaSuccess &&
-        reserved == 1024 && cudaMalloc(&d_out, sizeof(uint32_t)) == cudaSuccess) {
-      probe_dynamic_smem_base_kernel<<<1, 32, 1024>>>(d_out);
-      if (cudaMemcpy(&h_out, d_out, sizeof(uint32_t), cudaMemcpyDeviceToHost) == cudaSuccess && h_out == 1024u)
-        cached[dev] = 1;
-      cudaFree(d_out);
+    if (cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, dev) != cudaSuccess ||
+        reserved != 1024)
+      return cudaSuccess;
+    uint32_t* h_out = nullptr;
+    cudaStream_t ps = nullptr;
+    if (cudaHostAlloc(&h_out, sizeof(uint32_t), cudaHostAllocMapped) == cudaSuccess) {
+      uint32_t* d_out = nullptr;
+      *h_out = 0;
+      if (cudaHostGetDevicePointer(&d_out, h_out, 0) == cudaSuccess &&
+          cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking) == cudaSuccess) {
+        probe_dynamic_smem_base_kernel<<<1, 32, 1024, ps>>>(d_out);
+        if (cudaStreamSynchronize(ps) == cudaSuccess && *h_out == 1024u) verdict[dev].store(1);
+        cudaStreamDestroy(ps);
+      }
+      cudaFreeHost(h_out);
     }
-  }
-  return cached[dev] == 1;
+    cudaGetLastError();   // a failed probe must not leave a sticky-looking error for the caller
+    return cudaSuccess;
+  });
+  return verdict[dev].load() == 1;
 }
 
 template <int MS>
@@ -325,7 +341,8 @@ int b200boot_resample_stat_after(const double* const* data, int n_arrays, int64_
   if (rc) return rc;
 
   B2_CUDA(cudaMemsetAsync(w.work_counter, 0, 512, s));   // work counter and (next 256 B) the overflow flag
-  rc = launch_occupancies_fast(seed, resample_lo, n_local, plan, w.counts, w.gcounts, w.cls, w.half_table,
+  if (g_prof.enabled) B2_CUDA(cudaEventRecord(g_prof.begin, s));
+  rc = launch_occupancies_fast(seed, resample_lo, n_local, plan, w.counts, w.gcounts, w.cls, w.half_tables,
                                w.overflow, s);
   if (rc) return rc;
   if (ready) B2_CUDA(cudaStreamWaitEvent(s, ready, 0));
@@ -424,7 +441,7 @@ size_t b200boot_tile_counts_packed_ws_bytes(int64_t n_rows, int n_arrays, int64_
   if (n_rows < 1 || n_arrays < 1 || n_local < 0) return 0;
   const Plan plan = make_plan(n_rows, n_arrays);
   return 4096 + pad256((size_t)n_tile_groups(plan) * std::max<int64_t>(n_local, 1) * 4) +
-         pad256((size_t)kHalfTableSize * sizeof(HalfConsts));
+         pad256((size_t)kHalfTableSize * sizeof(HalfConsts)) + pad256((size_t)kHalfTableSize * sizeof(double));
 }
 
 int b200boot_tile_counts_packed(uint64_t seed, int64_t n_rows, int n_arrays, int64_t resample_lo,
@@ -439,7 +456,7 @@ int b200boot_tile_counts_packed(uint64_t seed, int64_t n_rows, int n_arrays, int
   Carver cv(ws, ws_bytes);
   int32_t* overflow = cv.take<int32_t>(64);
   int32_t* gcounts = cv.take<int32_t>((size_t)n_tile_groups(plan) * n_local);
-  HalfConsts* table = cv.take<HalfConsts>((size_t)kHalfTableSize);
+  const HalfTables table = take_half_tables(cv);
   if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
   cudaStream_t s = as_stream(stream);
   B2_CUDA(cudaMemsetAsync(overflow, 0, 256, s));
@@ -806,14 +823,11 @@ int b200boot_count_matrix(uint64_t seed, int64_t n_rows, int64_t resample_lo, in
   if (n_rows > kSmemDataBytes / 8)
     return fail(B200BOOT_EUNSUPPORTED, "count matrix: n_rows=%lld beyond the single-cell limit", (long long)n_rows);
   if (n_local == 0) return 0;
-  static bool configured[64] = {false};
-  int dev = 0;
-  B2_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
-    B2_CUDA(cudaFuncSetAttribute(k6_count_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(kSmemHeader + kSmemDataBytes)));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
-  }
+  static PerDeviceOnce configured;
+  B2_CUDA(configured.run([] {
+    return cudaFuncSetAttribute(k6_count_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(kSmemHeader + kSmemDataBytes));
+  }));
   const size_t smem = (size_t)n_rows * 4;
   const int per_sm = (int)std::max<int64_t>(1, std::min<int64_t>(4, (int64_t)(200 * 1024) / (int64_t)std::max<size_t>(smem, 1)));
   const int grid = (int)std::min<int64_t>((int64_t)sm_count() * per_sm, n_local);
@@ -850,10 +864,11 @@ int b200boot_finish_columns(int stat_id, int64_t n_rows, int64_t n_cols, int64_t
 }
 
 // ---- instrumentation ---------------------------------------------------------------
-int64_t b200boot_launch_count(void) { return (int64_t)launch_counter(); }
+int64_t b200boot_launch_count(void) { return (int64_t)launch_counter().load(std::memory_order_relaxed); }
 
 int b200boot_profile_enable(int on) {
   if (on && !g_prof.start) {
+    B2_CUDA(cudaEventCreate(&g_prof.begin));
     B2_CUDA(cudaEventCreate(&g_prof.start));
     B2_CUDA(cudaEventCreate(&g_prof.stop));
   }
@@ -867,6 +882,15 @@ int b200boot_profile_last_k1_ms(float* ms) {
   if (!g_prof.valid) return fail(B200BOOT_EINVAL, "no timed K1 launch recorded");
   B2_CUDA(cudaEventSynchronize(g_prof.stop));
   B2_CUDA(cudaEventElapsedTime(ms, g_prof.start, g_prof.stop));
+  return 0;
+}
+
+int b200boot_profile_last_ms(float* k0_ms, float* k1_ms) {
+  if (!k0_ms || !k1_ms) return fail(B200BOOT_EINVAL, "null ms");
+  if (!g_prof.valid) return fail(B200BOOT_EINVAL, "no timed K1 launch recorded");
+  B2_CUDA(cudaEventSynchronize(g_prof.stop));
+  B2_CUDA(cudaEventElapsedTime(k0_ms, g_prof.begin, g_prof.start));
+  B2_CUDA(cudaEventElapsedTime(k1_ms, g_prof.start, g_prof.stop));
   return 0;
 }
 

@@ -14,6 +14,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "philox.cuh"
 
@@ -168,11 +169,15 @@ B2_HD int64_t binomial_ratio(int64_t n, int64_t num, int64_t den, const Stream& 
 
 // ---- Bin(n, 1/2): the node sampler of the bank-class split tree ---------------------------
 // Every split of the class tree (draw.cuh, class_count_tree) is an even split, so one
-// sampler with p = 1/2 serves all of them and its BTRS constants depend on n alone:
-// kernels read them from a table built once per call by the same function (half_setup), so
-// table and direct evaluation agree bit for bit.
+// sampler with p = 1/2 serves all of them:
 //   n <  kHalfBtrsMin: the number of set bits among n random bits (exact, no rejection);
-//   n >= kHalfBtrsMin: BTRS with p = 1/2, r = 1 — the same arithmetic as binomial_btrs.
+//   n >= kHalfBtrsMin: BTRS specialised to p = 1/2.  Its constants depend on n alone (kernels
+//        read them from a table built by half_setup itself, so table and direct evaluation
+//        agree bit for bit); the uniforms are built from the mantissa bits directly; and the
+//        full acceptance test compares with the exact ratio of the two probabilities,
+//        f(k) / f(m) = m! (n-m)! / (k! (n-k)!), through log-factorials (a table of
+//        lgamma(j + 1) in the kernels, lgamma itself elsewhere: the same values).
+// Explicit fma() where a product feeds a sum, so every caller rounds the same way.
 constexpr int64_t kHalfBtrsMin = 20;      // n * p >= 10
 
 struct HalfConsts {
@@ -189,19 +194,6 @@ B2_HD HalfConsts half_setup(int64_t n) {
   return h;
 }
 
-B2_HD BtrsConsts half_consts(int64_t n, const HalfConsts& h) {
-  BtrsConsts q;
-  q.nd = (double)n;
-  q.b = h.b;
-  q.a = h.a;
-  q.c = q.nd * 0.5 + 0.5;
-  q.v_r = h.v_r;
-  q.alpha = h.alpha;
-  q.r = 1.0;
-  q.m = floor((q.nd + 1.0) * 0.5);
-  return q;
-}
-
 B2_HD int popcount32(uint32_t x) {
 #if defined(__CUDA_ARCH__)
   return __popc(x);
@@ -210,33 +202,69 @@ B2_HD int popcount32(uint32_t x) {
 #endif
 }
 
+// [1, 2) from 52 random bits: the top 20 of `hi` and all of `lo` as the mantissa
+B2_HD double unit12(uint32_t hi, uint32_t lo) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double((int)(0x3FF00000u | (hi >> 12)), (int)lo);
+#else
+  const uint64_t bits = ((uint64_t)(0x3FF00000u | (hi >> 12)) << 32) | (uint64_t)lo;
+  double d;
+  memcpy(&d, &bits, sizeof d);
+  return d;
+#endif
+}
+
+// log(j!) for an integer-valued j >= 0
+B2_HD double log_factorial(double j) { return lgamma(j + 1.0); }
+
 // n < kHalfBtrsMin
 B2_HD int64_t binomial_half_small(int64_t n, const Words4& w) {
   return n <= 0 ? 0 : (int64_t)popcount32(w.w[0] & ((1u << (int)n) - 1u));
 }
 
-// First attempt only: the value if block 0 settles it (small n, or a proposal accepted by
-// the squeeze), -1 if the node needs the full sampler (binomial_half).
-B2_HD int64_t binomial_half_first(int64_t n, const BtrsConsts& q, const Words4& w) {
-  if (n < kHalfBtrsMin) return binomial_half_small(n, w);
-  double k, inv_us, v;
-  return btrs_propose(q, w, &k, &inv_us, &v) > 0 ? (int64_t)k : -1;
+// One proposal of Bin(n, 1/2), n >= kHalfBtrsMin, from the words of an attempt block:
+// +1 accepted by the squeeze, 0 needs half_accept (out: k, inv_us, v), -1 rejected.
+B2_HD int half_propose(double nd, const HalfConsts& h, const Words4& w, double* k_out, double* inv_us_out,
+                       double* v_out) {
+  const double u = unit12(w.w[0], w.w[1]) - 1.5;                          // [-1/2, 1/2)
+  const double v = unit12(w.w[2], w.w[3]) - (1.0 - 1.1102230246251565e-16);   // (0, 1): - 1 + 2^-53, exact
+  const double us = 0.5 - fabs(u);
+  *v_out = v;
+  if (us <= 0.0) return -1;                                               // u == -1/2 (probability 2^-52)
+  const double inv_us = 1.0 / us;
+  const double k = floor(fma(fma(2.0 * h.a, inv_us, h.b), u, fma(nd, 0.5, 0.5)));
+  *k_out = k;
+  *inv_us_out = inv_us;
+  if (us >= 0.07 && v <= h.v_r) return 1;
+  if (k < 0.0 || k > nd) return -1;
+  return 0;
 }
 
-// Bin(n, 1/2); `q` must be half_consts(n, half_setup(n) or its table entry)
-B2_HD int64_t binomial_half(int64_t n, const BtrsConsts& q, const Stream& s) {
-  if (n < kHalfBtrsMin) return binomial_half_small(n, stream_block(s, 0u));
-  for (uint32_t attempt = 0;; ++attempt) {
+// Full acceptance test of proposal k; lf(j) = log(j!)
+template <typename LF>
+B2_HD bool half_accept(double nd, const HalfConsts& h, double k, double inv_us, double v, LF&& lf) {
+  const double m = floor((nd + 1.0) * 0.5);
+  const double lhs = log(v * h.alpha / fma(h.a * inv_us, inv_us, h.b));
+  const double rhs = (lf(m) - lf(k)) + (lf(nd - m) - lf(nd - k));
+  return lhs <= rhs;
+}
+
+// Bin(n, 1/2), n >= kHalfBtrsMin, from attempt `first_attempt` on
+template <typename LF>
+B2_HD int64_t binomial_half_from(int64_t n, const HalfConsts& h, const Stream& s, uint32_t first_attempt, LF&& lf) {
+  const double nd = (double)n;
+  for (uint32_t attempt = first_attempt;; ++attempt) {
     const Words4 w = stream_block(s, attempt);
     double k, inv_us, v;
-    const int verdict = btrs_propose(q, w, &k, &inv_us, &v);
+    const int verdict = half_propose(nd, h, w, &k, &inv_us, &v);
     if (verdict > 0) return (int64_t)k;
-    if (verdict == 0 && btrs_accept(q, k, inv_us, v)) return (int64_t)k;
+    if (verdict == 0 && half_accept(nd, h, k, inv_us, v, lf)) return (int64_t)k;
   }
 }
 
 B2_HD int64_t binomial_half(int64_t n, const Stream& s) {
-  return binomial_half(n, half_consts(n, n >= kHalfBtrsMin ? half_setup(n) : HalfConsts{}), s);
+  if (n < kHalfBtrsMin) return binomial_half_small(n, stream_block(s, 0u));
+  return binomial_half_from(n, half_setup(n), s, 0u, [](double j) { return log_factorial(j); });
 }
 
 }  // namespace b200boot

@@ -1,6 +1,8 @@
 // Error plumbing, workspace carving and small device helpers shared by all kernels.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
+#include <mutex>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -32,15 +34,32 @@ inline int fail(int code, const char* fmt, ...) {
   } while (0)
 
 // every kernel launch of the library goes through this macro, which also counts it
-inline long long& launch_counter() {
-  static long long n = 0;
+inline std::atomic<long long>& launch_counter() {
+  static std::atomic<long long> n{0};
   return n;
 }
-#define B2_LAUNCH_CHECK()            \
-  do {                               \
-    ++b200boot::launch_counter();    \
-    B2_CUDA(cudaGetLastError());     \
+#define B2_LAUNCH_CHECK()                                                  \
+  do {                                                                     \
+    b200boot::launch_counter().fetch_add(1, std::memory_order_relaxed);   \
+    B2_CUDA(cudaGetLastError());                                           \
   } while (0)
+
+// One-time work per device (cudaFuncSetAttribute and the like) under std::call_once: exports
+// are called from several host threads (ctypes drops the GIL).  run() returns f's status on the
+// call that executes it and cudaSuccess afterwards.
+constexpr int kMaxDevices = 64;
+struct PerDeviceOnce {
+  std::once_flag flags[kMaxDevices];
+  template <typename F>
+  cudaError_t run(F&& f) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices) return f();
+    std::call_once(flags[dev], [&] { e = f(); });
+    return e;
+  }
+};
 
 // ---- workspace carving ---------------------------------------------------------
 struct Carver {
@@ -62,16 +81,16 @@ struct Carver {
 inline size_t pad256(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
 
 inline int sm_count() {
-  static int cached[64] = {0};
+  static std::atomic<int> cached[kMaxDevices];
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-  if (cached[dev] == 0) {
-    int n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+  int n = cached[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
       n = 148;
-    cached[dev] = n;
+    cached[dev].store(n, std::memory_order_relaxed);
   }
-  return cached[dev];
+  return n;
 }
 
 #if defined(__CUDACC__)

@@ -93,51 +93,72 @@ __global__ void __launch_bounds__(128) k0_class_counts_kernel(uint64_t seed, int
   }
 }
 
-// BTRS constants of Bin(n, 1/2) for every n below kHalfTableSize (entries below kHalfBtrsMin
-// are never read).  32 B per entry, 1 MB: L2-resident for the tree kernel.
+// Tables of the even-split sampler for every n below kHalfTableSize: the BTRS constants of
+// Bin(n, 1/2) (entries below kHalfBtrsMin are never read) and log(n!).  32 + 8 bytes per
+// entry, 1.25 MB: L2-resident for the tree kernel.  Built by the sampler's own functions, so
+// a table read and a direct evaluation give the same bits.
 constexpr int kHalfTableSize = 32768;
-__global__ void __launch_bounds__(256) k0_half_table_kernel(HalfConsts* __restrict__ table) {
+struct HalfTables {
+  HalfConsts* consts;
+  double* log_fact;
+};
+__global__ void __launch_bounds__(256) k0_half_table_kernel(HalfTables tab) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < kHalfTableSize) table[n] = half_setup(n < kHalfBtrsMin ? kHalfBtrsMin : n);
+  if (n >= kHalfTableSize) return;
+  tab.consts[n] = half_setup(n < kHalfBtrsMin ? kHalfBtrsMin : n);
+  tab.log_fact[n] = log_factorial((double)n);
 }
 
 // Resample-path form of the class split: a CTA takes a batch of (tile, resample) pairs, keeps
 // their 16-slot records in shared memory and walks the four levels of the split tree.  At a
-// level every node of the batch is independent: all threads first make the FIRST proposal of
-// their nodes (table lookup + one BTRS proposal + squeeze; dense, no divergence); the ~14 %
-// of nodes that need the full acceptance test go to a shared-memory queue and are then
-// resolved with every lane on the expensive path (binomial_half replays attempt 0).  One
-// launch, no global scratch; values are those of class_count_tree.  Output records are uint16
-// (a count beyond 65535 — never for 2^14-row tiles — saturates and raises *overflow, which the
-// finisher turns into NaN statistics).
+// level every node of the batch is independent and the work is kept dense in three passes:
+//   pass 0, all nodes: the first proposal (table lookup + one BTRS proposal + squeeze), which
+//           settles ~80 % of them; the others go to a shared-memory queue;
+//   pass 1, the queue: the full acceptance test of that first proposal and, if it fails, the
+//           second proposal with its squeeze; what is still open (~2 %) goes to a second queue;
+//   pass 2, the second queue: the sampler's loop from the second attempt on.
+// Each pass evaluates exactly what binomial_half evaluates for that attempt, so the values are
+// those of class_count_tree.  One launch, no global scratch.  Records are uint16: a count beyond
+// 65535 (never for 2^14-row tiles) saturates and raises *overflow, which the finisher turns into
+// NaN statistics.
 constexpr int kTreeThreads = 256;
 #ifndef B2_TREE_BATCH
 #define B2_TREE_BATCH 512
 #endif
-constexpr int kTreeBatch = B2_TREE_BATCH;  // pairs per CTA pass (node numbers of a level fit 16 bits)
+constexpr int kTreeBatch = B2_TREE_BATCH;      // pairs per CTA pass (node numbers of a level fit 16 bits)
 constexpr int kTreeRecStride = kClasses + 1;   // odd stride: slot reads of consecutive pairs spread over banks
+constexpr int kTreeQueue2 = 2 * kTreeBatch;    // capacity of the second queue (expected use: 2 % of the nodes)
 
-__device__ __forceinline__ BtrsConsts half_consts_lookup(int64_t n, const HalfConsts* __restrict__ table) {
-  if (n < kHalfBtrsMin) return half_consts(n, HalfConsts{});
-  if (n < kHalfTableSize) {
-    const double2 lo = __ldg(reinterpret_cast<const double2*>(table + n));
-    const double2 hi = __ldg(reinterpret_cast<const double2*>(table + n) + 1);
-    return half_consts(n, HalfConsts{lo.x, lo.y, hi.x, hi.y});
+struct TreeLookup {
+  const HalfConsts* __restrict__ consts;
+  const double* __restrict__ log_fact;
+  __device__ __forceinline__ HalfConsts operator()(int64_t n) const {
+    if (n < kHalfTableSize) {
+      const double2 lo = __ldg(reinterpret_cast<const double2*>(consts + n));
+      const double2 hi = __ldg(reinterpret_cast<const double2*>(consts + n) + 1);
+      return HalfConsts{lo.x, lo.y, hi.x, hi.y};
+    }
+    return half_setup(n);
   }
-  return half_consts(n, half_setup(n));
-}
+  __device__ __forceinline__ double lf(double j) const {
+    return j < (double)kHalfTableSize ? __ldg(log_fact + (int)j) : log_factorial(j);
+  }
+};
 
 __global__ void __launch_bounds__(kTreeThreads, 3) k0_class_tree_kernel(
     uint64_t seed, int64_t resample_lo, int64_t n_local, int64_t n_full,
-    const int32_t* __restrict__ counts, const HalfConsts* __restrict__ table,
-    uint16_t* __restrict__ cls, int32_t* __restrict__ overflow) {
-  __shared__ uint32_t s_rec[kTreeBatch * kTreeRecStride];
+    const int32_t* __restrict__ counts, HalfTables tab, uint16_t* __restrict__ cls,
+    int32_t* __restrict__ overflow) {
+  __shared__ uint16_t s_rec[kTreeBatch * kTreeRecStride];
   __shared__ uint32_t s_tile[kTreeBatch], s_res[kTreeBatch];
-  __shared__ uint16_t s_queue[kTreeBatch * 8];
-  __shared__ int s_qn[2];                  // queue length, one counter per level parity
+  __shared__ uint16_t s_q1[kTreeBatch * 8], s_q2[kTreeQueue2];
+  __shared__ int s_qn[2];
+  const TreeLookup look{tab.consts, tab.log_fact};
+  const auto lf = [&look](double j) { return look.lf(j); };
   const int tid = threadIdx.x;
   const int64_t total = n_full * n_local;
   const int64_t n_batches = (total + kTreeBatch - 1) / kTreeBatch;
+  bool sat = false;
   for (int64_t batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
     const int64_t e0 = batch * kTreeBatch;
     const int np = (int)min((int64_t)kTreeBatch, total - e0);
@@ -146,61 +167,91 @@ __global__ void __launch_bounds__(kTreeThreads, 3) k0_class_tree_kernel(
       const int64_t t = e / n_local;
       s_tile[p] = (uint32_t)t;
       s_res[p] = (uint32_t)(e - t * n_local);
-      s_rec[p * kTreeRecStride] = (uint32_t)__ldg(counts + e);
+      const int32_t n_t = __ldg(counts + e);
+      sat = sat || n_t > 65535;
+      s_rec[p * kTreeRecStride] = (uint16_t)min(n_t, 65535);
     }
-    if (tid == 0) s_qn[0] = 0;
+    if (tid < 2) s_qn[tid] = 0;
     __syncthreads();
 #pragma unroll 1
     for (int level = 0; level < 4; ++level) {
-      int* qn_ptr = &s_qn[level & 1];
       const int span = kClasses >> level;
       const int n_nodes = np << level;
+      auto node_slot = [&](int i) { return s_rec + (i >> level) * kTreeRecStride + (i & ((1 << level) - 1)) * span; };
+      auto node_stream = [&](int i) {
+        const int p = i >> level;
+        return make_stream(seed, resample_lo + (int64_t)s_res[p],
+                           class_node_cell_id((int64_t)s_tile[p], (1 << level) + (i & ((1 << level) - 1))),
+                           kPurposeBinomial);
+      };
+      auto settle = [&](uint16_t* slot, int64_t n, int64_t k) {
+        slot[0] = (uint16_t)k;
+        slot[span / 2] = (uint16_t)(n - k);
+      };
+      // pass 0: first proposal of every node
       for (int i = tid; i < n_nodes; i += kTreeThreads) {
-        const int p = i >> level, j = i & ((1 << level) - 1);
-        uint32_t* slot = s_rec + p * kTreeRecStride + j * span;
+        uint16_t* slot = node_slot(i);
         const int64_t n = (int64_t)*slot;
-        const Stream st = make_stream(seed, resample_lo + (int64_t)s_res[p],
-                                      class_node_cell_id((int64_t)s_tile[p], (1 << level) + j), kPurposeBinomial);
-        const int64_t k = binomial_half_first(n, half_consts_lookup(n, table), stream_block(st, 0u));
-        if (k >= 0) {
-          slot[0] = (uint32_t)k;
-          slot[span / 2] = (uint32_t)(n - k);
+        const Words4 w = stream_block(node_stream(i), 0u);
+        if (n < kHalfBtrsMin) {
+          settle(slot, n, binomial_half_small(n, w));
         } else {
-          s_queue[atomicAdd(qn_ptr, 1)] = (uint16_t)i;
+          double k, inv_us, v;
+          if (half_propose((double)n, look(n), w, &k, &inv_us, &v) > 0)
+            settle(slot, n, (int64_t)k);
+          else
+            s_q1[atomicAdd(&s_qn[0], 1)] = (uint16_t)i;
         }
       }
       __syncthreads();
-      const int qn = *qn_ptr;
-      if (tid == 0) s_qn[(level + 1) & 1] = 0;   // nobody touches the other counter during this level
-      for (int q = tid; q < qn; q += kTreeThreads) {
-        const int i = s_queue[q];
-        const int p = i >> level, j = i & ((1 << level) - 1);
-        uint32_t* slot = s_rec + p * kTreeRecStride + j * span;
+      // pass 1: full test of the first proposal, else second proposal
+      const int q1n = s_qn[0];
+      for (int q = tid; q < q1n; q += kTreeThreads) {
+        const int i = s_q1[q];
+        uint16_t* slot = node_slot(i);
         const int64_t n = (int64_t)*slot;
-        const Stream st = make_stream(seed, resample_lo + (int64_t)s_res[p],
-                                      class_node_cell_id((int64_t)s_tile[p], (1 << level) + j), kPurposeBinomial);
-        const int64_t k = binomial_half(n, half_consts_lookup(n, table), st);
-        slot[0] = (uint32_t)k;
-        slot[span / 2] = (uint32_t)(n - k);
+        const double nd = (double)n;
+        const HalfConsts h = look(n);
+        const Stream st = node_stream(i);
+        double k, inv_us, v;
+        int verdict = half_propose(nd, h, stream_block(st, 0u), &k, &inv_us, &v);
+        bool done = verdict == 0 && half_accept(nd, h, k, inv_us, v, lf);
+        if (!done) {
+          verdict = half_propose(nd, h, stream_block(st, 1u), &k, &inv_us, &v);
+          done = verdict > 0;
+        }
+        if (done) {
+          settle(slot, n, (int64_t)k);
+        } else {
+          const int pos = atomicAdd(&s_qn[1], 1);
+          if (pos < kTreeQueue2)
+            s_q2[pos] = (uint16_t)i;
+          else                                    // queue full (never in practice): finish here
+            settle(slot, n, binomial_half_from(n, h, st, 1u, lf));
+        }
       }
+      __syncthreads();
+      // pass 2: whatever is still open, from the second attempt on
+      const int q2n = min(s_qn[1], kTreeQueue2);
+      for (int q = tid; q < q2n; q += kTreeThreads) {
+        const int i = s_q2[q];
+        uint16_t* slot = node_slot(i);
+        const int64_t n = (int64_t)*slot;
+        settle(slot, n, binomial_half_from(n, look(n), node_stream(i), 1u, lf));
+      }
+      __syncthreads();
+      if (tid < 2) s_qn[tid] = 0;
       __syncthreads();
     }
     // packed store: two classes per 32-bit word, coalesced over the batch
     uint32_t* out = reinterpret_cast<uint32_t*>(cls + e0 * kClasses);
-    bool sat = false;
     for (int i = tid; i < np * (kClasses / 2); i += kTreeThreads) {
       const int p = i >> 3, c = (i & 7) * 2;
-      uint32_t lo = s_rec[p * kTreeRecStride + c], hi = s_rec[p * kTreeRecStride + c + 1];
-      if (lo > 65535u || hi > 65535u) {
-        sat = true;
-        lo = min(lo, 65535u);
-        hi = min(hi, 65535u);
-      }
-      out[i] = lo | (hi << 16);
+      out[i] = (uint32_t)s_rec[p * kTreeRecStride + c] | ((uint32_t)s_rec[p * kTreeRecStride + c + 1] << 16);
     }
-    if (sat) atomicExch(overflow, 1);
     __syncthreads();   // records are reloaded by the next batch
   }
+  if (sat) atomicExch(overflow, 1);
 }
 
 // ------------------------------------------------------------------ K1 --------

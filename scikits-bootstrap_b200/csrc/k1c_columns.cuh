@@ -285,14 +285,11 @@ int launch_k1c(const K1cParams& P0, cudaStream_t s) {
   P.n_rchunks = (int32_t)((P.n_local + P.rchunk - 1) / P.rchunk);
   P.n_items = (int64_t)P.n_colblocks * P.n_rchunks;
   if (P.n_items >= ((int64_t)1 << 31)) return fail(B200BOOT_EINVAL, "too many work items");
-  static bool configured[64] = {false};
-  int dev = 0;
-  B2_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
-    B2_CUDA(cudaFuncSetAttribute(k1c_columns_kernel<MS, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(kSmemHeader + kSmemDataBytes)));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
-  }
+  static PerDeviceOnce configured;     // one per <MS, W> instantiation
+  B2_CUDA(configured.run([] {
+    return cudaFuncSetAttribute(k1c_columns_kernel<MS, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(kSmemHeader + kSmemDataBytes));
+  }));
   const size_t smem = kSmemHeader + (size_t)P.n_rows * W * 8;
   const int grid = (int)std::min<int64_t>(sms, P.n_items);
   k1c_columns_kernel<MS, W><<<grid, kColThreads, smem, s>>>(P);

@@ -983,20 +983,15 @@ inline int median_resample(const double* data, int64_t n_rows, int64_t n_cols, i
   P.indices = indices;
   P.rule = rule;
   B2_CUDA(cudaMemsetAsync(w.work_counter, 0, 256, s));
-  static bool configured[64] = {false};
-  int dev = 0;
-  B2_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
-    B2_CUDA(cudaFuncSetAttribute(k1m_median_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(kSmemHeader + kSmemDataBytes)));
-    B2_CUDA(cudaFuncSetAttribute(k1m_median_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(kSmemHeader + kSmemDataBytes)));
-    B2_CUDA(cudaFuncSetAttribute(k1m_median_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(kSmemHeader + kSmemDataBytes)));
-    B2_CUDA(cudaFuncSetAttribute(k1m_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(kSmemHeader + kSmemDataBytes)));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
-  }
+  static PerDeviceOnce configured;
+  B2_CUDA(configured.run([] {
+    const int bytes = (int)(kSmemHeader + kSmemDataBytes);
+    cudaError_t e = cudaFuncSetAttribute(k1m_median_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k1m_median_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k1m_median_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k1m_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return e;
+  }));
 
   // short columns: tables for many resamples stay resident, columns stream through
   const int64_t slice_bytes = (int64_t)w.seg * 64 * kMedWarps;            // one lin slice per warp
@@ -1074,13 +1069,10 @@ inline int median_resample_sorted(const double* sorted_vals, int64_t n_rows, uin
   P.out = stat_out;
   P.rule = rule;
   const size_t smem = (size_t)(plan.tile() + 2) * 2 + 16;
-  static bool configured[64] = {false};
-  int dev = 0;
-  B2_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
-    B2_CUDA(cudaFuncSetAttribute(k1mt_median_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
-  }
+  static PerDeviceOnce configured;
+  B2_CUDA(configured.run([] {
+    return cudaFuncSetAttribute(k1mt_median_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  }));
   const int grid = (int)std::min<int64_t>((int64_t)sm_count() * 6, n_local);
   k1mt_median_tiled_kernel<<<grid, kMtThreads, smem, s>>>(P);
   B2_LAUNCH_CHECK();
