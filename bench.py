@@ -7,18 +7,28 @@ Workload (BASELINE.json configs[4], "cfg5"): 1-D float64, N = 1e7 rows,
 `ci(x, np.mean, method='bca', n_samples=1e5)`; a step is one whole ci() call =
 n_samples x N resampled points.  With N > 1 GPUs (torchrun, one rank per GPU,
 NCCL) the 1e5 resample ids are sharded over the ranks (strong scaling: the
-total work is the config's, fixed); the only collectives are the integer
-all-reduces of the z0 count and the radix-select histograms.
+total work is the config's, fixed); the only collective on the path is one
+all-gather of the 0.8 MB statistic vector.
 
 One JSON line is printed by rank 0.  Keys beyond the base contract:
-  roofline     K1 (fused draw+gather+reduce): algorithmic bytes = 8 B per resampled
-               point, duration from CUDA events recorded by the library around the
-               K1 launch on the launching stream; peak = MEASURED_PEAKS.json hbm_gbs.
-  cpu_baseline oracle port of the reference's compiled CPU path (numba prange over
-               resample ids, bootstrap.py:639-664) on a bounded sample, rank 0, N=1.
-  e2e          the same ci() call fed a pinned HOST tensor: H2D of the data and D2H
-               of the results are inside the timed region.
-`--impl reference` times the CPU port alone (all host threads) on the same config.
+  roofline     K1 (fused draw+gather+reduce) against the resource that binds it: rows are
+               served from shared memory, one 128-byte wavefront per half-warp LDS.64, i.e.
+               a floor of 16 resampled points per clock per SM.  `achieved` is computed in
+               this run from the library's CUDA events around the K1 launch, the SM count
+               and the SM clock sampled by nvidia-smi during the timed region; `frac_step`
+               is the same fraction for the whole step (occupancy kernels, finisher, BCa tail
+               included).  `hbm_yardstick` keeps SURVEY §8(d)'s 8 B/point figure against the
+               measured HBM peak, labelled non-binding.  `traffic` / `ncu` come from the
+               committed ncu capture (tools/ncu_k1.sh -> profiles/r02_k1_traffic.json).
+  configs      the other four BASELINE configs, timed here (1 GPU) with an in-run check of
+               each against the CPU oracle on the device's own materialised indices at a
+               reduced number of resamples.
+  shard_parity (N > 1) small sharded calls compared with their unsharded results before timing.
+  cpu_baseline the reference's own compiled CPU path (`ref.ci(..., use_numba=True)` from
+               baseline/_ref, all host threads) on a bounded number of resamples, rank 0, N=1.
+  e2e          the same ci() call fed a pinned HOST tensor: H2D of the data and D2H of the
+               results are inside the timed region.
+`--impl reference` times the reference alone on the same config (bounded samples).
 """
 import argparse
 import ctypes
@@ -38,6 +48,7 @@ N_ROWS = 10**7
 N_SAMPLES = 10**5
 DATA_SEED = 5
 BYTES_PER_POINT = 8            # one float64 operand per resampled point
+SMEM_FLOOR_PTS_PER_CLK_SM = 16.0   # 128 B/clk/SM of shared-memory bandwidth / 8 B per gathered row
 METRIC = "resampled points/sec (n_samples x N), BCa ci(np.mean)"
 UNIT = "points/s"
 
@@ -46,15 +57,13 @@ def make_data():
     return np.random.default_rng(DATA_SEED).standard_normal(N_ROWS) + 1.0
 
 
-def workload_config(extra=None):
-    cfg = {
+def workload_config():
+    """Identical for both arms (the driver compares the dicts)."""
+    return {
         "workload": "cfg5: ci(x[1e7] f64, np.mean, method='bca', n_samples=1e5), resamples sharded over ranks",
         "n_rows": N_ROWS, "n_samples": N_SAMPLES, "alpha": 0.05,
         "l2": "L2 flushed between timed steps (256 MiB write)",
     }
-    if extra:
-        cfg.update(extra)
-    return cfg
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -111,82 +120,120 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ----------------------------------------------------------------------------- CPU port
+# ----------------------------------------------------------------------------- CPU reference
 
-def cpu_port_rate(x, budget_s=12.0, min_resamples=None):
-    """Times the oracle port of the reference's CPU path for this config on a bounded
-    sample.  numba available: the prange kernels (reference use_numba=True path,
-    bootstrap.py:639-664), all threads.  Otherwise the numpy loop (bootstrap.py:429-432),
-    one thread, method='pi' (the numpy BCa jackknife is O(N^2): infeasible at N=1e7)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import bootstrap_oracle as orc
-    kernels = orc.numba_kernels()
-    n = len(x)
-    if kernels is not None:
-        import numba
-        boot_mean, jack_mean = kernels
-        threads = numba.get_num_threads()
-        boot_mean(x[:1000], 2 * threads, 1)       # JIT warm-up
-        jack_mean(x[:1000])
-        batch = max(threads, min_resamples or 0)
-        done, t0 = 0, time.perf_counter()
-        stats = []
-        while True:
-            stats.append(boot_mean(x, batch, 1000 + done))
-            done += batch
-            if time.perf_counter() - t0 > budget_s:
-                break
-        js = jack_mean(x)
-        stat = np.sort(np.concatenate(stats))
-        acc = orc.acceleration(js)
-        av = orc.bca_avals(stat, x.mean(), acc, np.array([0.025, 0.975]), len(stat))
-        orc.order_indices(av, len(stat))
-        dt = time.perf_counter() - t0
-        return {"value": done * n / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                "sample": f"{done} of {N_SAMPLES} resamples at N={n}, numba prange port of "
-                          f"bootstrap.py:639-664 incl. O(N) jackknife; {dt:.1f} s"}, dt, done
-    done, t0 = 0, time.perf_counter()
-    rng = np.random.default_rng(0)
-    vals = []
-    while True:
-        idx = rng.integers(0, n, n)
-        vals.append(x[idx].mean())
-        done += 1
-        if time.perf_counter() - t0 > budget_s:
-            break
-    dt = time.perf_counter() - t0
-    return {"value": done * n / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{done} of {N_SAMPLES} resamples at N={n}, numpy loop port of "
-                      f"bootstrap.py:429-432 (method='pi'; numpy BCa jackknife is O(N^2)); {dt:.1f} s"}, dt, done
+def load_reference():
+    """The unmodified reference package from baseline/_ref (baseline/install_ref.py), or None."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "scikits", "bootstrap")):
+        return None
+    os.environ.setdefault("NUMBA_CACHE_DIR", os.path.join("/tmp", "b200boot_numba_cache"))
+    sys.path.insert(0, ref_dir)
+    try:
+        import scikits.bootstrap as ref
+        return ref
+    except Exception:
+        return None
+    finally:
+        sys.path.remove(ref_dir)
+
+
+class CpuArm:
+    """Times the reference's CPU implementation of the config on a bounded number of resamples.
+
+    kind "reference": `ref.ci(x, np.mean, alpha=0.05, n_samples=k, method='bca', use_numba=True)`
+    from baseline/_ref — the reference's own public API and its compiled path
+    (bootstrap.py:415-425, 587-593, 639-664), every numba thread; per-resample cost does not
+    depend on k, so points/s at k resamples is the rate of the full config.
+    kind "port" (only if the reference or numba is absent on the box): the oracle's
+    restatement of the same path."""
+
+    def __init__(self, x):
+        self.x = x
+        self.ref = load_reference()
+        self.kind, self.threads = "port", 1
+        if self.ref is not None and getattr(self.ref.bootstrap, "NUMBA_AVAILABLE", False):
+            import numba
+            self.kind, self.threads = "reference", int(numba.get_num_threads())
+        else:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import bootstrap_oracle as orc
+            self.orc = orc
+            self.kernels = orc.numba_kernels()
+            if self.kernels is not None:
+                import numba
+                self.threads = int(numba.get_num_threads())
+        self.per_resample_s = None
+
+    def run(self, k, seed):
+        """One bounded call with k resamples; returns seconds."""
+        t0 = time.perf_counter()
+        if self.kind == "reference":
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                self.ref.ci(self.x, np.mean, alpha=0.05, n_samples=int(k), method="bca", seed=seed, use_numba=True)
+        elif self.kernels is not None:
+            boot_mean, jack_mean = self.kernels
+            stat = np.sort(boot_mean(self.x, int(k), 1000 + seed))
+            acc = self.orc.acceleration(jack_mean(self.x))
+            av = self.orc.bca_avals(stat, self.x.mean(), acc, np.array([0.025, 0.975]), len(stat))
+            self.orc.order_indices(av, len(stat))
+        else:
+            rng = np.random.default_rng(seed)
+            n = len(self.x)
+            for _ in range(int(k)):
+                self.x[rng.integers(0, n, n)].mean()
+        return time.perf_counter() - t0
+
+    def warm(self):
+        """JIT compile on a tiny input, then calibrate the cost of one resample."""
+        big, self.x = self.x, self.x[:1000]
+        self.run(2 * self.threads, 0)
+        self.x = big
+        k = max(2 * self.threads, 8)
+        dt = self.run(k, 1)
+        self.per_resample_s = dt / k
+
+    def timed(self, budget_s, seed):
+        k = int(max(self.threads, min(N_SAMPLES, budget_s / max(self.per_resample_s, 1e-9))))
+        k = max(self.threads, (k // self.threads) * self.threads)
+        dt = self.run(k, seed)
+        self.per_resample_s = dt / k           # the first calibration call pays page faults; follow the steady rate
+        return k, dt
+
+    def describe(self, k, dt):
+        what = ("reference ci(x, np.mean, method='bca', use_numba=True) from baseline/_ref"
+                if self.kind == "reference" else "oracle port of bootstrap.py:639-664 (reference or numba absent)")
+        return (f"{k} of {N_SAMPLES} resamples at N={len(self.x)} per call ({what}, jackknife included); "
+                f"{dt:.1f} s; the full config would take {N_SAMPLES * dt / k / 60:.0f} min at this rate")
 
 
 def run_reference_arm(args):
     """--impl reference: the CPU implementation alone, rank 0 only."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    x = make_data()
-    step_budget = 8.0
-    for _ in range(args.warmup):
-        cpu_port_rate(x, budget_s=0.5)
-    rates, times = [], []
-    info = None
-    for _ in range(args.steps):
-        info, dt, _ = cpu_port_rate(x, budget_s=step_budget)
-        rates.append(info["value"])
+    arm = CpuArm(make_data())
+    arm.warm()
+    for _ in range(max(args.warmup - 1, 0)):
+        arm.timed(0.5, 7)
+    rates, times, last = [], [], (0, 0.0)
+    for i in range(args.steps):
+        k, dt = arm.timed(8.0, 100 + i)
+        rates.append(k * N_ROWS / dt)
         times.append(dt)
+        last = (k, dt)
     value = float(np.mean(rates))
-    info["value"] = value
-    line = {
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config({"cpu_step": "bounded sample, see cpu_baseline.sample"}),
-        "cpu_baseline": info,
+        "data": "synthetic", "config": workload_config(),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.threads, "kind": arm.kind,
+                         "sample": arm.describe(*last)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }
-    emit(line)
+    })
 
 
 # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its
@@ -208,6 +255,130 @@ def emit(line):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
+# ----------------------------------------------------------------------------- other configs
+
+def _oracle():
+    p = os.path.join(ROOT, "oracle")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+    import bootstrap_oracle as orc
+    from scikits_bootstrap_b200 import _abi
+    orc.PHILOX_ROUNDS = int(_abi.lib().b200boot_philox_rounds())
+    return orc
+
+
+def _median_ms(fn, reps):
+    import torch
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        ts.append(1e3 * (time.perf_counter() - t0))
+    return float(np.median(ts))
+
+
+def _parity(boot, orc, tdata, dev_stat, host_stat, jstat, n_check, seed, method, multi=None, rtol=1e-12):
+    """The device's ci against the oracle fed the device's own materialised indices (K2)."""
+    import warnings
+    data = tdata if multi else tdata[0]
+    alphas = np.array([0.025, 0.975])
+    idx = np.array(list(boot.bootstrap_indices(tdata[0], n_check, seed=seed, n_arrays=len(tdata))))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = boot.ci(data, dev_stat, alpha=0.05, n_samples=n_check, method=method, multi=multi, seed=seed)
+        want = orc.ci_from_indices(tdata, host_stat, idx, alphas, n_check, method, jstat=jstat)
+    return bool(np.allclose(got, want, rtol=rtol, atol=1e-15)), n_check
+
+
+def other_configs(boot):
+    """cfg1-cfg4 of BASELINE.json on one GPU: wall time of the whole call (median, inputs as the
+    config states them: numpy arrays unless noted) and the oracle check.  Costs a few seconds."""
+    import torch
+    orc = _oracle()
+    out = {}
+    rng = np.random.default_rng
+    # cfg1
+    x = rng(0).standard_normal(1000)
+    xd = torch.from_numpy(x).cuda()
+    call = lambda d: boot.ci(d, np.mean, method="bca", n_samples=10_000, seed=0)   # noqa: E731
+    ms, ms_dev = _median_ms(lambda: call(x), 30), _median_ms(lambda: call(xd), 30)
+    ok, n_chk = _parity(boot, orc, (x,), np.mean, np.mean, orc.jack_mean(x), 10_000, 0, "bca")
+    out["cfg1"] = {"what": "ci(x[1e3], np.mean, 'bca', n_samples=1e4, seed=0)", "ms": ms, "ms_device_input": ms_dev,
+                   "points_per_s": 1e7 / (ms * 1e-3), "result": [float(v) for v in call(x)],
+                   "parity": ok, "parity_n_samples": n_chk}
+    # cfg2
+    x = rng(1).standard_normal(100_000)
+    call = lambda: boot.ci(x, np.average, method="pi", n_samples=100_000, seed=0)   # noqa: E731
+    ms = _median_ms(call, 5)
+    ok, n_chk = _parity(boot, orc, (x,), np.average, np.average, None, 200, 3, "pi")
+    out["cfg2"] = {"what": "ci(x[1e5], np.average, 'pi', n_samples=1e5)", "ms": ms,
+                   "points_per_s": 1e10 / (ms * 1e-3), "parity": ok, "parity_n_samples": n_chk}
+    # cfg3
+    a, b = rng(2).gamma(2, 1, 10**6), rng(3).gamma(3, 1, 10**6)
+    call = lambda: boot.ci((a, b), boot.ratio_of_means, method="bca", n_samples=100_000, multi="paired", seed=0)  # noqa: E731
+    ms = _median_ms(call, 3)
+    ok, n_chk = _parity(boot, orc, (a, b), boot.ratio_of_means, lambda u, v: np.mean(u) / np.mean(v),
+                        orc.jack_ratio_of_means(a, b), 40, 4, "bca", multi="paired")
+    out["cfg3"] = {"what": "ci((a, b)[1e6], ratio_of_means, 'bca', n_samples=1e5, multi='paired')", "ms": ms,
+                   "points_per_s": 1e11 / (ms * 1e-3), "parity": ok, "parity_n_samples": n_chk}
+    # cfg4
+    table = rng(4).standard_normal((1000, 10_000))
+    td = torch.from_numpy(table).cuda()
+    call = lambda: boot.ci(td, boot.median_axis0, method="bca", n_samples=10_000, seed=0)   # noqa: E731
+    callp = lambda: boot.pval(td, boot.median_axis0, n_samples=10_000, seed=0)              # noqa: E731
+    ms, ms_p = _median_ms(call, 3), _median_ms(callp, 3)
+    # columns share the index set, so a column subset under the same seed is the same run
+    import warnings
+    sub = np.ascontiguousarray(table[:, :8])
+    n_chk = 200
+    idx = np.array(list(boot.bootstrap_indices(sub, n_chk, seed=5)))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = boot.ci(sub, boot.median_axis0, alpha=0.05, n_samples=n_chk, method="bca", seed=5)
+        gotp = boot.pval(sub, boot.median_axis0, n_samples=n_chk, seed=5)
+        ok = True
+        for c in range(sub.shape[1]):
+            col = sub[:, c]
+            want = orc.ci_from_indices((col,), np.median, idx, np.array([0.025, 0.975]), n_chk, "bca",
+                                       jstat=orc.jack_median(col))
+            ok = ok and bool(np.allclose(got[:, c], want, rtol=1e-12, atol=1e-15))
+            ok = ok and bool(gotp[c] == np.mean(np.median(col[idx], axis=1) > 0))
+    out["cfg4"] = {"what": "ci(table[1000 x 10000] on device, median_axis0, 'bca', n_samples=1e4) + pval",
+                   "ms": ms, "ms_pval": ms_p, "points_per_s": 1e11 / (ms * 1e-3), "parity": ok,
+                   "parity_n_samples": n_chk, "parity_columns": int(sub.shape[1])}
+    return out
+
+
+def shard_parity(boot):
+    """Small calls sharded over the ranks against the same calls unsharded on this rank
+    (moments, median, pval, a returned distribution): identical arrays expected."""
+    import warnings
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal(50_001) + 1.0
+    a, b = rng.gamma(2, 1, 20_000), rng.gamma(3, 1, 20_000)
+    table = rng.standard_normal((400, 24))
+    cases = [
+        lambda: boot.ci(x, np.mean, n_samples=2003, seed=3),
+        lambda: boot.ci(x, np.std, n_samples=1001, seed=4, method="pi", alpha=(0.05, 0.5, 0.95)),
+        lambda: boot.ci((a, b), boot.ratio_of_means, n_samples=999, seed=5, multi="paired"),
+        lambda: boot.ci(x, np.median, n_samples=501, seed=6),
+        lambda: boot.ci(table, boot.median_axis0, n_samples=401, seed=7),
+        lambda: boot.pval(table, boot.mean_axis0, boot.greater_than(0.01), n_samples=501, seed=8),
+        lambda: boot.ci(x[:3000], np.mean, n_samples=601, seed=9, return_dist=True)[1],
+    ]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sharded = [np.asarray(c()) for c in cases]
+        boot.distributed.disable()
+        alone = [np.asarray(c()) for c in cases]
+        boot.distributed.enable()
+    return all(s.shape == u.shape and np.array_equal(s, u) for s, u in zip(sharded, alone)), len(cases)
+
+
 # ----------------------------------------------------------------------------- GPU arm
 
 def main():
@@ -221,6 +392,7 @@ def main():
     ap.add_argument("--n-samples", type=int, default=N_SAMPLES, help=argparse.SUPPRESS)
     ap.add_argument("--n-rows", type=int, default=N_ROWS, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-configs", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     N_ROWS, N_SAMPLES = args.n_rows, args.n_samples
     args.warmup = max(args.warmup, 3)      # timing rule: at least 3 warm-up steps (reported as run)
@@ -257,6 +429,15 @@ def main():
     def step(data, seed):
         return boot.ci(data, np.mean, alpha=0.05, n_samples=N_SAMPLES, method="bca", seed=seed)
 
+    sharded_ok = None
+    if world > 1:
+        ok, n_cases = shard_parity(boot)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        sharded_ok = {"ok": bool(int(flag.item())), "cases": n_cases,
+                      "what": "sharded vs unsharded on every rank: moments, paired ratio, median (1-D, columns), "
+                              "pval, returned distribution; identical arrays"}
+
     for w in range(args.warmup):
         step(x_dev, 1000 + w)
     barrier()
@@ -268,7 +449,7 @@ def main():
     _abi.check(L.b200boot_profile_enable(1))
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
-    k1_ms = []
+    k0_ms, k1_ms = [], []
     launches0 = L.b200boot_launch_count()
     barrier()
     t_wall0 = time.perf_counter()
@@ -278,9 +459,10 @@ def main():
         ev[i][0].record()
         result = step(x_dev, i)
         ev[i][1].record()
-        cms = ctypes.c_float()
-        _abi.check(L.b200boot_profile_last_k1_ms(ctypes.byref(cms)))
-        k1_ms.append(cms.value)
+        a, b = ctypes.c_float(), ctypes.c_float()
+        _abi.check(L.b200boot_profile_last_ms(ctypes.byref(a), ctypes.byref(b)))
+        k0_ms.append(a.value)
+        k1_ms.append(b.value)
     barrier()
     wall_s = time.perf_counter() - t_wall0
     launches = L.b200boot_launch_count() - launches0
@@ -302,48 +484,70 @@ def main():
     d2h = _device.TRAFFIC["d2h"] // max(args.steps, 1)
 
     # max over ranks
-    t = torch.tensor([dev_ms, e2e_s * 1e3, float(np.mean(k1_ms))], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s * 1e3, float(np.mean(k1_ms)), float(np.mean(k0_ms))],
+                     dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, k1_mean_ms = (float(v) for v in t.tolist())
+    dev_ms, e2e_ms, k1_mean_ms, k0_mean_ms = (float(v) for v in t.tolist())
 
     if rank == 0:
         value = points * args.steps / (dev_ms * 1e-3)
         e2e_value = points * args.steps / (e2e_ms * 1e-3)
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback (B200_PROFILING.md)"
+        n_sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        clk_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
         local_points = points / world
-        achieved = local_points * BYTES_PER_POINT / (k1_mean_ms * 1e-3) / 1e9
+        per_clk = lambda ms: local_points / (ms * 1e-3) / (n_sms * clk_mhz * 1e6)     # noqa: E731
+        achieved = per_clk(k1_mean_ms)
+        step_ms = dev_ms / args.steps
         traffic, ncu = None, None
-        tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02_k1_traffic.json")
         if os.path.exists(tpath):
             prof = json.load(open(tpath))
             traffic = prof.get("dram_bytes_per_launch")
-            # the kernel serves rows from shared memory: what binds it, from the committed
-            # ncu capture (profiles/), not re-measured here
-            ncu = {k: prof[k] for k in ("issue_slots_active_pct", "smem_wavefront_pipe_pct", "alu_pipe_pct",
-                                        "fp64_pipe_pct", "points_per_clk_per_sm", "source") if k in prof}
+            ncu = {k: v for k, v in prof.items() if k != "dram_bytes_per_launch"}
+        hbm_gbs = local_points * BYTES_PER_POINT / (k1_mean_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config({"parallelism": f"resample-shard x{world}", "result": [float(v) for v in result]}),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "kernel": "k1_resample_kernel<kMomSum>",
-                         "kernel_ms": k1_mean_ms, "peak_source": peak_src, "ncu_shared_memory_regime": ncu,
-                         "note": "algorithmic 8 B per resampled point; rows are staged in shared memory, so "
-                                 "DRAM traffic is far below the algorithmic bytes and frac may exceed 1"},
+            "config": workload_config(),
+            "parallelism": f"resample-shard x{world}", "result": [float(v) for v in result],
+            "philox_rounds": int(L.b200boot_philox_rounds()),
+            "roofline": {
+                "bound": "smem_wavefront", "achieved": achieved, "peak": SMEM_FLOOR_PTS_PER_CLK_SM,
+                "unit": "points/clk/SM", "frac": achieved / SMEM_FLOOR_PTS_PER_CLK_SM,
+                "frac_step": per_clk(step_ms) / SMEM_FLOOR_PTS_PER_CLK_SM,
+                "traffic": traffic, "kernel": "k1_resample_kernel<kMomSum, FAST>",
+                "kernel_ms": k1_mean_ms, "k0_ms": k0_mean_ms, "step_ms": step_ms,
+                "n_sms": n_sms, "sm_clock_mhz": clk_mhz,
+                "peak_source": "one 128-byte shared-memory wavefront per clock per SM serves 16 gathered float64 rows "
+                               "(every half-warp LDS.64 of K1 is one conflict-free wavefront)",
+                "hbm_yardstick": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
+                                  "peak_source": hbm_src,
+                                  "note": "SURVEY 8(d) yardstick, 8 B per resampled point; NOT the binding resource: rows "
+                                          "are staged in shared memory, DRAM traffic is `traffic` bytes per launch"},
+                "ncu": ncu,
+            },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "wall_s_timed_region": wall_s,
         }
+        if sharded_ok is not None:
+            line["shard_parity"] = sharded_ok
+        if world == 1 and not args.no_configs:
+            line["configs"] = other_configs(boot)
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_port_rate(make_data(), budget_s=12.0)[0]
+            arm = CpuArm(make_data())
+            arm.warm()
+            k, dt = arm.timed(12.0, 1)
+            line["cpu_baseline"] = {"value": k * N_ROWS / dt, "unit": UNIT, "cores": arm.threads, "kind": arm.kind,
+                                    "sample": arm.describe(k, dt)}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

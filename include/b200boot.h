@@ -219,6 +219,24 @@ int b200boot_fill_moving_block(uint64_t seed, int64_t n_rows, int64_t block_leng
 int b200boot_fill_subsample(uint64_t seed, int64_t n_rows, int64_t size, int64_t sample_lo,
                             int64_t sample_hi, int64_t* out, void* ws, size_t ws_bytes, void* stream);
 
+/* Small calls (one resident cell, a scalar moment statistic, n_samples <= 32768, <= 8 levels):
+ * the whole ci() of bootstrap.py:222-504 enqueued by ONE call — K1 (finishing the statistic
+ * itself), the single-CTA jackknife, and a single-CTA tail that counts stat < ostat
+ * (bootstrap.py:583), forms the BCa levels and ranks (bootstrap.py:609-629, :456) and selects
+ * the order statistics (bootstrap.py:485-490) — followed by one device-to-host copy of the
+ * 32-double result block into `result_host` (pinned; may be NULL):
+ *   [0..7] order statistics   [8..15] the ranks used   [16] #{stat < ostat}   [17..24] jackknife
+ *   summary as b200boot_jackknife writes it.
+ * The ranks are speculative (device evaluation of the reference's nppf / ncdf): the caller
+ * recomputes them on the host from [16] and [17..24] and selects again if they differ.
+ * stat_out: float64[n_samples] device; result_dev: 40 doubles device; ws as for
+ * b200boot_resample_stat with n_local = n_samples. */
+int b200boot_ci_small_supported(int stat_id, int n_arrays, int64_t n_rows, int64_t n_samples, int n_alphas);
+int b200boot_ci_small(const double* const* data, int n_arrays, int64_t n_rows, int stat_id, uint64_t seed,
+                      int64_t n_samples, const double* alphas, int n_alphas, int bca, int need_jack,
+                      double* stat_out, double* result_dev, double* result_host, void* ws, size_t ws_bytes,
+                      void* stream);
+
 /* Occupancies of the multinomial chain (K0), for inspection and tests:
  * counts int32[n_tiles][n_local]; class_counts (may be NULL) int32[n_full][n_local][16],
  * the split of every full tile's draws over its 16 shared-memory bank classes.

@@ -122,17 +122,28 @@ class Workspace:
 
 
 class _PerThreadWorkspace:
-    """One grow-only workspace per Python thread (calls from different threads may run
-    on different streams and must not share scratch)."""
+    """One grow-only workspace per (Python thread, device, CUDA stream): calls that may run
+    concurrently — other threads, or the same thread under another `torch.cuda.stream(...)` —
+    never share scratch; work on one stream is ordered, so reuse there is safe."""
+
+    _MAX_STREAMS = 8          # per thread; beyond that the least recently used scratch is dropped
 
     def __init__(self):
         import threading
         self._local = threading.local()
 
     def get(self, nbytes: int):
-        ws = getattr(self._local, "ws", None)
+        torch = _torch()
+        table = getattr(self._local, "table", None)
+        if table is None:
+            table = self._local.table = {}
+        key = (torch.cuda.current_device(), stream_ptr())
+        ws = table.pop(key, None)
         if ws is None:
-            ws = self._local.ws = Workspace()
+            ws = Workspace()
+            while len(table) >= self._MAX_STREAMS:
+                table.pop(next(iter(table)))
+        table[key] = ws                       # most recently used last
         return ws.get(nbytes)
 
 
@@ -198,6 +209,59 @@ def resample_stat(arrays: Sequence, stat_id: int, seed: int, lo: int, hi: int, o
         if not whole:
             out[:, a - lo:b - lo] = dst
     return out
+
+
+class _SmallCallBuffers:
+    """Per (thread, device, stream): the statistic vector, the device result block and its
+    pinned host mirror of b200boot_ci_small."""
+
+    def __init__(self):
+        import threading
+        self._local = threading.local()
+
+    def get(self, n_samples: int):
+        torch = _torch()
+        table = getattr(self._local, "table", None)
+        if table is None:
+            table = self._local.table = {}
+        key = (torch.cuda.current_device(), stream_ptr())
+        ent = table.get(key)
+        if ent is None or ent[0].numel() < n_samples:
+            if len(table) >= 8:
+                table.clear()
+            ent = (torch.empty(max(n_samples, 4096), dtype=torch.float64, device="cuda"),
+                   torch.empty(40, dtype=torch.float64, device="cuda"),
+                   torch.empty(32, dtype=torch.float64).pin_memory())
+            table[key] = ent
+        return ent
+
+
+_small = _SmallCallBuffers()
+
+
+def ci_small_supported(stat_id: int, n_arrays: int, n_rows: int, n_samples: int, n_alphas: int) -> bool:
+    return bool(_abi.lib().b200boot_ci_small_supported(stat_id, n_arrays, n_rows, n_samples, n_alphas))
+
+
+def ci_small(arrays: Sequence, stat_id: int, seed: int, n_samples: int, alphas: np.ndarray, bca: bool,
+             need_jack: bool):
+    """One library call for a whole short ci(): returns (stat float64[n_samples] CUDA view,
+    endpoints[A], ranks[A] int64, less, jack[8]) — ranks are the device's speculative ones."""
+    torch = _torch()
+    L = _abi.lib()
+    n_rows = arrays[0].numel()
+    a = np.ascontiguousarray(alphas, dtype=np.float64).reshape(-1)
+    stat, res_dev, res_host = _small.get(n_samples)
+    ws, wsz = workspace_for(stat_id, n_rows, len(arrays), 1, n_samples, len(a))
+    s = stream_ptr()
+    _abi.check(L.b200boot_ci_small(_ptr_array(arrays), len(arrays), n_rows, stat_id, seed, n_samples,
+                                   a.ctypes.data, len(a), int(bca), int(need_jack), stat.data_ptr(),
+                                   res_dev.data_ptr(), res_host.data_ptr(), ws, wsz, s))
+    torch.cuda.current_stream().synchronize()
+    TRAFFIC["d2h"] += 32 * 8
+    r = res_host.numpy()
+    na = len(a)
+    return (stat[:n_samples], r[:na].copy(), r[8:8 + na].astype(np.int64), int(r[16]), r[17:25].copy())
 
 
 def resample_stat_indexed(arrays: Sequence, stat_id: int, indices):

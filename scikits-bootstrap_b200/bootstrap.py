@@ -152,6 +152,8 @@ class _Run:
         self._parts = None
         self._jack_dev = None
         self._local = False          # sharded run whose statistic vector was gathered: finish without collectives
+        self._less = None            # small-call path: #{stat < ostat} and the speculative select
+        self._spec = None
         # rank statistics: which order statistics (None: np.median's)
         self.rule = _device.rank_rule(self.dev[0].shape[0], spec.q) if spec.stat_id == _abi.STAT_MEDIAN else None
 
@@ -238,6 +240,32 @@ class _Run:
         flat = [a.reshape(-1) for a in self.dev]
         return _device.resample_stat(flat, spec.stat_id, self.key, lo, hi, ready=ready).reshape(1, -1)
 
+    # -- short calls: everything in one library call ------------------------------------
+    def small_call(self, alphas: np.ndarray, bca: bool, need_jack: bool):
+        """cfg1-sized jobs (one resident cell, scalar moment statistic, short statistic vector,
+        not sharded, Philox draws): K1, the jackknife and a single-CTA tail (z0 count, levels,
+        ranks, select) are enqueued by one call and one 256-byte copy comes back.  Returns the
+        statistic vector float64[1][n] or None when the job does not qualify.  The ranks the
+        device used are speculative; `select` compares them with the host's."""
+        spec = self.spec
+        if (self.indices is not None or spec.independent or self.vector or spec.n_out != 1
+                or _dist.active() or spec.stat_id == _abi.STAT_MEDIAN or self.dev[0].dim() != 1):
+            return None
+        n_alphas = int(np.prod(alphas.shape)) if alphas.ndim else 1
+        if not _device.ci_small_supported(spec.stat_id, len(self.dev), self.dev[0].shape[0], self.n_samples, n_alphas):
+            return None
+        torch = _device._torch()
+        ready, self._ready = self._ready, None
+        if ready is not None:
+            torch.cuda.current_stream().wait_event(ready)
+        stat, vals, ranks, less, jack = _device.ci_small([a.reshape(-1) for a in self.dev], spec.stat_id, self.key,
+                                                         self.n_samples, alphas, bca, need_jack)
+        if need_jack:
+            self._jack = jack.reshape(1, 8)
+            self._less = np.array([less], dtype=np.int64)
+        self._spec = (ranks.reshape(-1, 1), vals.reshape(-1, 1))
+        return stat.reshape(1, -1)
+
     # -- K1i ---------------------------------------------------------------------
     def _resample_indexed(self):
         """Parity mode: gathers with the caller's index sets (e.g. the reference's own
@@ -274,6 +302,8 @@ class _Run:
         column (bootstrap.py:583).  For a scalar statistic the count kernel reads ostat
         straight from the jackknife output on the device, so the two results come back
         with one wait instead of a host round trip in between."""
+        if self._less is not None:                                 # small-call path: already on the host
+            return self._jack, self._less
         if self.n_cols == 1 and not self.spec.independent and self._jack is None:
             jd = self._jackknife_tensor()
             c = _device.count(stat, _abi.CMP_LT, jd)              # &jd[0][0] is ostat
@@ -362,6 +392,11 @@ class _Run:
     def select(self, stat, ranks: np.ndarray) -> np.ndarray:
         """ranks int[A][D] (global, 0-based) -> float64[A][D] order statistics."""
         torch = _device._torch()
+        if self._spec is not None:
+            spec_ranks, spec_vals = self._spec
+            self._spec = None
+            if spec_ranks.shape == np.shape(ranks) and np.array_equal(spec_ranks, ranks):
+                return spec_vals                                  # the device's ranks were the host's
         r = _device.host_to_device(np.asarray(ranks, dtype=np.int64), stat.device)
         sel = _device.Select(stat, r)
         out = sel.run(sharded=_dist.active() and not self._local)
@@ -511,7 +546,11 @@ def _ci_impl(data, statfunction, alpha, n_samples, method, output, epsilon, mult
 def _ci_on_device(spec, arrays, multi, n_samples, key, indices, alphas, method, output, return_dist):
     """Device part of ci (warnings use stacklevel=4: the user's frame)."""
     run = _Run(spec, arrays, multi, n_samples, key, indices)
-    stat = run.gather_small(run.resample())                       # float64[D][n_local]
+    stat = None
+    if not return_dist:
+        stat = run.small_call(alphas, method == "bca", method == "bca" or output == "errorbar")
+    if stat is None:
+        stat = run.gather_small(run.resample())                   # float64[D][n_local]
 
     ostat = None
     if method == "pi":

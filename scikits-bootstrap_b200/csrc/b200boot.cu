@@ -12,6 +12,7 @@
 #include "k6_gemm.cuh"
 #include "k3_jackknife.cuh"
 #include "k45_interval.cuh"
+#include "small_call.cuh"
 #include "stats.cuh"
 
 using namespace b200boot;
@@ -92,6 +93,13 @@ int prepare_rows(const double* const* data, int n_arrays, int64_t n_rows, int st
   rows[1] = n_arrays > 1 ? data[1] : nullptr;
   B2_CUDA(cudaMemsetAsync(w.jack, 0, sizeof(JackState), s));
   if (!stat_needs_centering(stat)) return 0;
+  if (n_rows <= kSmallMaxRows) {         // short arrays: means and centred rows in one single-CTA launch
+    center_small_kernel<<<1, kSmallThreads, 0, s>>>(rows[0], rows[1], n_rows, w.jack, w.centered[0],
+                                                    n_arrays > 1 ? w.centered[1] : nullptr);
+    B2_LAUNCH_CHECK();
+    for (int a = 0; a < n_arrays; ++a) rows[a] = w.centered[a];
+    return 0;
+  }
   int rc = run_reduction<2>(n_rows, RawSumsF{rows[0], rows[1]}, StoreCentersG{w.jack, (double)n_rows},
                             w.red, s);
   if (rc) return rc;
@@ -251,6 +259,11 @@ template <int MS>
 int jack_passes(const double** rows, int64_t n_rows, int stat, ResampleWs& w, double* out,
                 cudaStream_t s) {
   const double n = (double)n_rows;
+  if (n_rows <= kSmallMaxRows) {         // short arrays: the three passes in one single-CTA launch
+    k3_small_kernel<MS><<<1, kSmallThreads, 0, s>>>(rows[0], rows[1], n_rows, stat, w.jack, out);
+    B2_LAUNCH_CHECK();
+    return 0;
+  }
   int rc = run_reduction<MomTraits<MS>::kMoments>(n_rows, ContributionF<MS>{rows[0], rows[1]},
                                                   StoreTotalsG<MS>{w.jack, stat, n, rows[0], rows[1]}, w.red, s);
   if (rc) return rc;
@@ -376,6 +389,9 @@ int b200boot_resample_stat_after(const double* const* data, int n_arrays, int64_
   P.n_items = plan.n_tiles * n_chunks;
   if (P.n_items >= ((int64_t)1 << 31)) return fail(B200BOOT_EINVAL, "too many work items");
   P.smem_stride = plan.n_full > 0 ? plan.tile() : ((plan.rem + 1) & ~(int64_t)1);
+  P.stat = stat_id;
+  P.center = w.jack->center;
+  P.direct_out = plan.n_tiles == 1 ? stat_out : nullptr;     // one cell: K1 finishes the statistic itself
   const size_t smem = kSmemHeader + (size_t)P.smem_stride * 8 * n_arrays;
   const int grid = (int)std::min<int64_t>(sms, P.n_items);
   if (g_prof.enabled) B2_CUDA(cudaEventRecord(g_prof.start, s));
@@ -385,6 +401,7 @@ int b200boot_resample_stat_after(const double* const* data, int n_arrays, int64_
     B2_CUDA(cudaEventRecord(g_prof.stop, s));
     g_prof.valid = true;
   }
+  if (P.direct_out) return 0;
 
   k1_finish_kernel<<<blocks_for(n_local, 256, 1 << 30), 256, 0, s>>>(w.partial, plan.n_tiles, nm, n_local,
                                                                      stat_id, (double)n_rows, w.jack->center,
@@ -425,6 +442,48 @@ int b200boot_resample_stat_indexed(const double* const* data, int n_arrays, int6
   k1_finish_kernel<<<blocks_for(n_sets, 256, 1 << 30), 256, 0, s>>>(w.partial, 1, nm, n_sets, stat_id,
                                                                     (double)n_rows, w.jack->center, stat_out, nullptr);
   B2_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200boot_ci_small_supported(int stat_id, int n_arrays, int64_t n_rows, int64_t n_samples, int n_alphas) {
+  if (moment_set_of(stat_id) < 0 || stat_outputs(stat_id) != 1 || n_arrays != stat_arrays(stat_id)) return 0;
+  if (n_rows < 1 || n_rows > kSmallMaxRows || make_plan(n_rows, n_arrays).n_tiles != 1) return 0;
+  if (n_samples < 1 || n_samples > kSelSmallMaxRows || n_alphas < 1 || n_alphas > kSelMaxAlphas) return 0;
+  return 1;
+}
+
+int b200boot_ci_small(const double* const* data, int n_arrays, int64_t n_rows, int stat_id, uint64_t seed,
+                      int64_t n_samples, const double* alphas, int n_alphas, int bca, int need_jack,
+                      double* stat_out, double* result_dev, double* result_host, void* ws, size_t ws_bytes,
+                      void* stream) {
+  int rc = check_moment_stat(stat_id, n_arrays, n_rows);
+  if (rc) return rc;
+  if (!b200boot_ci_small_supported(stat_id, n_arrays, n_rows, n_samples, n_alphas))
+    return fail(B200BOOT_EUNSUPPORTED, "ci_small: shape outside the single-CTA small-call path");
+  if (!data || !alphas || !stat_out || !result_dev) return fail(B200BOOT_EINVAL, "null pointer");
+  if (bca) need_jack = 1;
+  cudaStream_t s = as_stream(stream);
+  // K1 over the single cell, finishing the statistic itself
+  rc = b200boot_resample_stat_after(data, n_arrays, n_rows, stat_id, seed, 0, n_samples, stat_out, ws, ws_bytes,
+                                    stream, nullptr);
+  if (rc) return rc;
+  double* jack_out = result_dev + kSmallResultDoubles;      // 8 more doubles behind the result block
+  if (need_jack) {
+    rc = b200boot_jackknife(data, n_arrays, n_rows, stat_id, jack_out, ws, ws_bytes, stream);
+    if (rc) return rc;
+  }
+  SmallTailParams P{};
+  P.stat = stat_out;
+  P.n_samples = n_samples;
+  P.jack = need_jack ? jack_out : nullptr;
+  for (int a = 0; a < n_alphas; ++a) P.alphas[a] = alphas[a];
+  P.n_alphas = n_alphas;
+  P.bca = bca ? 1 : 0;
+  P.res = result_dev;
+  ci_tail_small_kernel<<<1, kSmallThreads, 0, s>>>(P);
+  B2_LAUNCH_CHECK();
+  if (result_host)
+    B2_CUDA(cudaMemcpyAsync(result_host, result_dev, kSmallResultDoubles * sizeof(double), cudaMemcpyDeviceToHost, s));
   return 0;
 }
 

@@ -270,6 +270,11 @@ struct K1Params {
   int32_t n_chunks;
   int64_t n_items;
   int64_t smem_stride;    // elements between arrays in shared memory
+  // single-cell plans: the per-resample sums are the totals, so the warp finishes the
+  // statistic itself (no partial table, no finisher launch): direct_out[o * n_local + r]
+  double* direct_out;
+  const double* center;   // per-array means of pre-centred rows (finish_stat), may be null
+  int32_t stat;
 };
 
 // Accumulator bank of one lane: W independent FP64 chains per moment, combined in a
@@ -531,8 +536,18 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_resample_kernel(const K1Para
         lemire_accumulate<MS>(s_bytes, stride_bytes, P.rk, st, n, (uint32_t)sz, lane, tot);
       }
       if (lane == 0) {
+        if (P.direct_out != nullptr) {
+          double m[kMaxMoments];
 #pragma unroll
-        for (int m = 0; m < NM; ++m) P.partial[(t * NM + m) * P.n_local + rl] = tot[m];
+          for (int k = 0; k < NM; ++k) m[k] = 0.0 + tot[k];      // as the finisher's sum over one cell
+          const int n_out = stat_outputs(P.stat);
+          for (int o = 0; o < n_out; ++o)
+            P.direct_out[(int64_t)o * P.n_local + rl] =
+                finish_stat(stat_component(P.stat, o), m, (double)P.plan.n_rows, P.center);
+        } else {
+#pragma unroll
+          for (int m = 0; m < NM; ++m) P.partial[(t * NM + m) * P.n_local + rl] = tot[m];
+        }
       }
     }
   }

@@ -159,20 +159,14 @@ constexpr int kSelSmallThreads = 1024;
 constexpr int64_t kSelSmallMaxRows = 32768;
 constexpr int64_t kSelSmallMaxCols = (int64_t)1 << 30;
 
-__global__ void __launch_bounds__(kSelSmallThreads) k5_select_small_kernel(
-    const double* __restrict__ stat, int64_t n, int64_t n_cols, const int64_t* __restrict__ ranks,
-    int a_lo, int a_cnt, double* __restrict__ out) {
-  __shared__ unsigned int s_hist[kSelMaxAlphas][256];
-  __shared__ uint64_t s_prefix[kSelMaxAlphas];
-  __shared__ long long s_krem[kSelMaxAlphas];
+// The eight passes over one column for up to kSelMaxAlphas selects; s_prefix = 0 and s_krem = the
+// ranks on entry (set before a barrier or by the calling threads tid < a_cnt), s_prefix = the
+// keys of the order statistics on exit (after the final barrier).  All threads of the CTA call it.
+__device__ __forceinline__ void select_small_descend(const double* __restrict__ col, int64_t n, int a_cnt,
+                                                     unsigned int (*s_hist)[256], uint64_t* s_prefix,
+                                                     long long* s_krem) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthreads = blockDim.x;                 // 256 .. 1024 by column length, >= 32 * a_cnt
-  const int64_t d = blockIdx.x;
-  const double* col = stat + d * n;
-  if (tid < a_cnt) {
-    s_prefix[tid] = 0;
-    s_krem[tid] = ranks[(int64_t)(a_lo + tid) * n_cols + d];
-  }
   for (int pass = 0; pass < 8; ++pass) {
     for (int i = tid; i < a_cnt * 256; i += nthreads) (&s_hist[0][0])[i] = 0;
     __syncthreads();
@@ -218,6 +212,21 @@ __global__ void __launch_bounds__(kSelSmallThreads) k5_select_small_kernel(
     }
     __syncthreads();
   }
+}
+
+__global__ void __launch_bounds__(kSelSmallThreads) k5_select_small_kernel(
+    const double* __restrict__ stat, int64_t n, int64_t n_cols, const int64_t* __restrict__ ranks,
+    int a_lo, int a_cnt, double* __restrict__ out) {
+  __shared__ unsigned int s_hist[kSelMaxAlphas][256];
+  __shared__ uint64_t s_prefix[kSelMaxAlphas];
+  __shared__ long long s_krem[kSelMaxAlphas];
+  const int tid = threadIdx.x;
+  const int64_t d = blockIdx.x;
+  if (tid < a_cnt) {
+    s_prefix[tid] = 0;
+    s_krem[tid] = ranks[(int64_t)(a_lo + tid) * n_cols + d];
+  }
+  select_small_descend(stat + d * n, n, a_cnt, s_hist, s_prefix, s_krem);
   if (tid < a_cnt) out[(int64_t)(a_lo + tid) * n_cols + d] = value_of(s_prefix[tid]);
 }
 

@@ -549,6 +549,64 @@ def test_cfg1_matches_oracle_end_to_end():
     assert_allclose(out, [-0.10978462, 0.01280137], atol=0.15 * se)
 
 
+@pytest.mark.parametrize("stat_name,n,n_arrays", [("mean", 1000, 1), ("sum", 7, 1), ("var", 1000, 1), ("std", 28672, 1),
+                                                  ("ratio_of_means", 3000, 2), ("weighted_average", 50, 2),
+                                                  ("pearson_r", 14336, 2)])
+def test_small_call_path_equals_general_path(stat_name, n, n_arrays, monkeypatch):
+    """Short jobs run as one library call (K1 + single-CTA jackknife + single-CTA tail whose ranks
+    the host verifies); they must return exactly what the general path returns."""
+    rng = np.random.default_rng(n)
+    arrays = tuple(rng.gamma(2, 1, n) + 0.25 * k for k in range(n_arrays))
+    data = arrays if n_arrays > 1 else arrays[0]
+    f = DEVICE_STATS[stat_name]
+    calls = []
+    real = _device.ci_small
+    monkeypatch.setattr(_device, "ci_small", lambda *a, **k: calls.append(1) or real(*a, **k))
+    kw = [dict(method="bca"), dict(method="pi"), dict(method="bca", output="errorbar"),
+          dict(method="pi", output="errorbar", alpha=(0.1, 0.5, 0.9)), dict(method="bca", alpha=0.5, n_samples=32768)]
+    small = [boot.ci(data, f, seed=7, **{"n_samples": 4000, **k}) for k in kw]
+    assert len(calls) == len(kw)
+    monkeypatch.setattr(_device, "ci_small_supported", lambda *a: False)
+    general = [boot.ci(data, f, seed=7, **{"n_samples": 4000, **k}) for k in kw]
+    assert len(calls) == len(kw)
+    for s, g in zip(small, general):
+        assert_array_equal(s, g)
+
+
+def test_small_call_wrong_speculative_ranks_are_caught(monkeypatch):
+    """The device's ranks are only a guess: when the host's own levels give other ranks the
+    order statistics are selected again with the host's."""
+    x = np.random.default_rng(3).standard_normal(500)
+    want = boot.ci(x, np.mean, n_samples=2000, seed=1)
+    real = _device.ci_small
+
+    def skewed(*a, **k):
+        stat, vals, ranks, less, jack = real(*a, **k)
+        return stat, vals + 1.0, ranks + 1, less, jack
+    monkeypatch.setattr(_device, "ci_small", skewed)
+    assert_array_equal(boot.ci(x, np.mean, n_samples=2000, seed=1), want)
+    # degenerate data: every level is NaN, ranks fall back to 0 (bootstrap.py:480)
+    monkeypatch.setattr(_device, "ci_small", real)
+    with pytest.warns(boot.InstabilityWarning):
+        out = boot.ci(np.ones(50), np.mean, n_samples=300, seed=2)
+    assert_array_equal(out, [1.0, 1.0])
+
+
+def test_small_call_does_not_apply_where_it_must_not(monkeypatch):
+    calls = []
+    real = _device.ci_small
+    monkeypatch.setattr(_device, "ci_small", lambda *a, **k: calls.append(1) or real(*a, **k))
+    x = np.random.default_rng(4).standard_normal(40000)             # tiled plan
+    boot.ci(x, np.mean, n_samples=500, seed=1)
+    boot.ci(x[:1000], np.mean, n_samples=40000, seed=1)              # statistic vector too long
+    boot.ci(x[:1000], np.median, n_samples=500, seed=1)              # rank statistic
+    boot.ci(x[:1000], np.mean, n_samples=500, seed=1, return_dist=True)
+    boot.ci(x[:1000].reshape(-1, 2), boot.mean_axis0, n_samples=500, seed=1)
+    assert not calls
+    boot.ci(x[:1000], np.mean, n_samples=500, seed=1)
+    assert len(calls) == 1
+
+
 # ------------------------------------------------------------------ K3 -----------
 
 @pytest.mark.parametrize("stat_name", ["mean", "var", "std", "ratio_of_means", "weighted_average",
