@@ -237,6 +237,26 @@ int b200boot_ci_small(const double* const* data, int n_arrays, int64_t n_rows, i
                       double* stat_out, double* result_dev, double* result_host, void* ws, size_t ws_bytes,
                       void* stream);
 
+/* multi='independent' with a two-sample statistic f(s_a(a), s_b(b)) (bootstrap.py:438-444,
+ * 601-607, 708-714).  f is one of b200boot_op. */
+enum b200boot_op { B200BOOT_OP_SUB = 0, B200BOOT_OP_ADD = 1, B200BOOT_OP_DIV = 2, B200BOOT_OP_MUL = 3,
+                   B200BOOT_OP_LOG_RATIO = 4 };
+/* out[i] = f(a[i], b[i]): the two arrays' resample statistics combined */
+int b200boot_combine(int op, const double* a, const double* b, double* out, int64_t n, void* stream);
+/* K3 as vectors: values[i] = statistic of the data without row i (moment statistics; closed
+ * forms), summary[8] as b200boot_jackknife.  ws as for b200boot_jackknife. */
+int b200boot_jackknife_values(const double* const* data, int n_arrays, int64_t n_rows, int stat_id,
+                              double* values, double* summary, void* ws, size_t ws_bytes, void* stream);
+/* the same for rank statistics of an ascending array: values[r] = statistic without sorted row r */
+int b200boot_jackknife_values_sorted(const double* sorted_vals, int64_t n_rows, double* values,
+                                     double* summary, void* stream, const b200boot_rank_rule* rule);
+/* pooled jackknife of f(s_a, s_b): the n_a + n_b values f(loo_a[j], s_b), f(s_a, loo_b[j]);
+ * out[8] = {f(s_a, s_b), their mean, sum d^2, sum d^3, acceleration, 0, 0, 0}.
+ * s_a, s_b: device scalars.  ws: 64 KB. */
+int b200boot_jackknife_pooled(int op, const double* loo_a, int64_t n_a, const double* s_a,
+                              const double* loo_b, int64_t n_b, const double* s_b, double* out,
+                              void* ws, size_t ws_bytes, void* stream);
+
 /* Occupancies of the multinomial chain (K0), for inspection and tests:
  * counts int32[n_tiles][n_local]; class_counts (may be NULL) int32[n_full][n_local][16],
  * the split of every full tile's draws over its 16 shared-memory bank classes.

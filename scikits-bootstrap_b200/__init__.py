@@ -8,6 +8,7 @@ Import as `scikits_bootstrap_b200` (repo-root shim) and use like the reference:
 from . import _dist as distributed
 from ._abi import B200BootError
 from ._registry import (REGISTRY_NAMES, DeviceCompare, DeviceStat, between, diff_of, diff_of_means,
+                        independent, ratio_of,
                         fit_intercept, fit_slope, greater_equal, greater_than, less_equal,
                         less_than, linear_fit, mean_axis0,
                         median_axis0, pearson_r, percentile, percentile_axis0, positive, quantile,
@@ -22,6 +23,6 @@ __all__ = (
     "jackknife_indices", "bootstrap_indices_moving_block", "InstabilityWarning",
     "ratio_of_means", "weighted_average", "pearson_r", "linear_fit", "fit_slope", "fit_intercept",
     "mean_axis0", "var_axis0", "std_axis0",
-    "median_axis0", "quantile", "percentile", "quantile_axis0", "percentile_axis0", "diff_of_means", "diff_of", "less_than", "less_equal", "greater_than", "greater_equal",
+    "median_axis0", "quantile", "percentile", "quantile_axis0", "percentile_axis0", "diff_of_means", "diff_of", "ratio_of", "independent", "less_than", "less_equal", "greater_than", "greater_equal",
     "between", "positive", "ci_indexed", "pval_indexed", "distributed", "REGISTRY_NAMES", "B200BootError",
 )

@@ -18,6 +18,7 @@ STAT_MEAN, STAT_VAR, STAT_STD, STAT_RATIO_OF_MEANS, STAT_WEIGHTED_AVERAGE, STAT_
     STAT_MEDIAN, STAT_SUM, STAT_SLOPE, STAT_INTERCEPT, STAT_LINEAR_FIT = range(11)
 STAT_OUTPUTS = {STAT_LINEAR_FIT: 2}      # outputs per resample where not 1
 CMP_LT, CMP_LE, CMP_GT, CMP_GE, CMP_BETWEEN = range(5)
+OP_SUB, OP_ADD, OP_DIV, OP_MUL, OP_LOG_RATIO = range(5)
 
 
 class Plan(C.Structure):
@@ -70,6 +71,10 @@ SIGNATURES = {
     "b200boot_gather": (_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "b200boot_jackknife": (_int, [_vp, _int, _i64, _int, _vp, _vp, _sz, _vp]),
     "b200boot_jackknife_median_columns": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp, _vp]),
+    "b200boot_combine": (_int, [_int, _vp, _vp, _vp, _i64, _vp]),
+    "b200boot_jackknife_values": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
+    "b200boot_jackknife_values_sorted": (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "b200boot_jackknife_pooled": (_int, [_int, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "b200boot_count": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _vp]),
     "b200boot_select": (_int, [_vp, _i64, _i64, _vp, _int, _vp, _vp, _sz, _vp]),
     "b200boot_select_begin": (_int, [_vp, _int, _i64, _vp, _sz, _vp]),

@@ -537,6 +537,48 @@ def jackknife_median_columns(data2d, rule=None):
     return out
 
 
+def combine(op: int, a, b):
+    """f(a[i], b[i]) of two statistic vectors (multi='independent')."""
+    torch = _torch()
+    out = torch.empty_like(a)
+    _abi.check(_abi.lib().b200boot_combine(op, a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), stream_ptr()))
+    return out
+
+
+def jackknife_values(arrays: Sequence, stat_id: int):
+    """Leave-one-out statistic of every row (moment statistics): (values float64[N], summary float64[8])."""
+    torch = _torch()
+    n_rows = arrays[0].numel()
+    values = torch.empty(n_rows, dtype=torch.float64, device=arrays[0].device)
+    summary = torch.empty(8, dtype=torch.float64, device=arrays[0].device)
+    ws, wsz = workspace_for(stat_id, n_rows, len(arrays), 1, 0, 1)
+    _abi.check(_abi.lib().b200boot_jackknife_values(_ptr_array(arrays), len(arrays), n_rows, stat_id,
+                                                    values.data_ptr(), summary.data_ptr(), ws, wsz, stream_ptr()))
+    return values, summary
+
+
+def jackknife_values_sorted(sorted_vals, rule=None):
+    """The same for a rank statistic of an ascending array (values listed by sorted position)."""
+    torch = _torch()
+    n_rows = sorted_vals.numel()
+    values = torch.empty(n_rows, dtype=torch.float64, device=sorted_vals.device)
+    summary = torch.empty(8, dtype=torch.float64, device=sorted_vals.device)
+    _abi.check(_abi.lib().b200boot_jackknife_values_sorted(sorted_vals.data_ptr(), n_rows, values.data_ptr(),
+                                                           summary.data_ptr(), stream_ptr(), _rule_ptr(rule)))
+    return values, summary
+
+
+def jackknife_pooled(op: int, loo_a, s_a, loo_b, s_b):
+    """Pooled jackknife summary float64[1][8] of f(s_a, s_b) from the two leave-one-out vectors."""
+    torch = _torch()
+    out = torch.empty((1, 8), dtype=torch.float64, device=loo_a.device)
+    ws, wsz = _ws.get(64 << 10)
+    _abi.check(_abi.lib().b200boot_jackknife_pooled(op, loo_a.data_ptr(), loo_a.numel(), s_a.data_ptr(),
+                                                    loo_b.data_ptr(), loo_b.numel(), s_b.data_ptr(),
+                                                    out.data_ptr(), ws, wsz, stream_ptr()))
+    return out
+
+
 def count(stat, op: int, t0, t1=None):
     """K4 on stat float64[D][n] -> int64[D] CUDA tensor."""
     torch = _torch()

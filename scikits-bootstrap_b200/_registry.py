@@ -29,6 +29,8 @@ class StatSpec:
     independent: bool = False    # defined for multi='independent'
     n_out: int = 1               # length of the statistic's value (1: scalar)
     q: Optional[float] = None    # rank statistics: None = np.median, else np.quantile(x, q)
+    op: Optional[int] = None     # independent: the binary operation f of f(s_a(a), s_b(b))
+    inner: tuple = ()            # independent: the specs of s_a and s_b
 
 
 class DeviceStat:
@@ -83,9 +85,7 @@ std_axis0 = DeviceStat(StatSpec("std_axis0", _abi.STAT_STD, 1, axis0=True),
                        lambda a: np.std(a, axis=0), "np.std(a, axis=0) over (N, D) data")
 median_axis0 = DeviceStat(StatSpec("median_axis0", _abi.STAT_MEDIAN, 1, axis0=True),
                           lambda a: np.median(a, axis=0), "np.median(a, axis=0) over (N, D) data")
-diff_of_means = DeviceStat(StatSpec("diff_of_means", _abi.STAT_MEAN, 2, independent=True),
-                           lambda a, b: np.mean(a) - np.mean(b),
-                           "mean(a) - mean(b); for multi='independent'")
+
 
 def _quantile_spec(q, axis0: bool) -> StatSpec:
     q = float(q)
@@ -136,16 +136,45 @@ def _partial_quantile(part: functools.partial) -> Optional[StatSpec]:
     return _quantile_spec(q, axis0)
 
 
+# ---- multi='independent': f(s_a(a), s_b(b)) of two independent samples ---------------------
+_OPS = {
+    "sub": (_abi.OP_SUB, lambda u, v: u - v, "{a}(a) - {b}(b)"),
+    "add": (_abi.OP_ADD, lambda u, v: u + v, "{a}(a) + {b}(b)"),
+    "div": (_abi.OP_DIV, lambda u, v: u / v, "{a}(a) / {b}(b)"),
+    "mul": (_abi.OP_MUL, lambda u, v: u * v, "{a}(a) * {b}(b)"),
+    "log_ratio": (_abi.OP_LOG_RATIO, lambda u, v: np.log(u / v), "log({a}(a) / {b}(b))"),
+}
+
+
+def independent(op: str, stat_a, stat_b=None) -> DeviceStat:
+    """f(s_a(a), s_b(b)) for two INDEPENDENT samples (multi='independent'; the arrays may differ
+    in length, each is resampled on its own: bootstrap.py:438-444).  s_a, s_b: any scalar
+    single-array statistics of the registry (np.mean, np.var, np.std, np.sum, np.median,
+    quantile(q), percentile(p)); s_b defaults to s_a.  f: 'sub', 'add', 'div', 'mul' or
+    'log_ratio'.  The BCa jackknife pools the N_a + N_b leave-one-out values as the reference
+    does (bootstrap.py:601-607, 708-714)."""
+    if op not in _OPS:
+        raise ValueError(f"unknown operation {op!r}; one of {sorted(_OPS)}")
+    host_a, host_b = stat_a, (stat_a if stat_b is None else stat_b)
+    inner = tuple(require(f) for f in (host_a, host_b))
+    for sp in inner:
+        if sp.n_arrays != 1 or sp.axis0 or sp.n_out != 1 or sp.independent:
+            raise NotImplementedError(f"independent() needs scalar statistics of one 1-D array, got {sp.name}")
+    op_id, host_op, text = _OPS[op]
+    name = text.format(a=inner[0].name, b=inner[1].name)
+    spec = StatSpec(f"independent[{name}]", inner[0].stat_id, 2, independent=True, q=inner[0].q,
+                    op=op_id, inner=inner)
+    return DeviceStat(spec, lambda a, b: host_op(host_a(a), host_b(b)), name + " of independent samples")
+
+
 def diff_of(statfunction) -> DeviceStat:
-    """s(a) - s(b) for two INDEPENDENT samples (multi='independent'; the arrays may differ in
-    length), s any scalar single-array statistic of the registry: np.mean, np.var, np.std,
-    np.sum, np.median, quantile(q), percentile(p).  diff_of(np.mean) is diff_of_means."""
-    inner = require(statfunction)
-    if inner.n_arrays != 1 or inner.axis0 or inner.n_out != 1 or inner.independent:
-        raise NotImplementedError(f"diff_of needs a scalar statistic of one 1-D array, got {inner.name}")
-    host = statfunction
-    return DeviceStat(StatSpec(f"diff_of({inner.name})", inner.stat_id, 2, independent=True, q=inner.q),
-                      lambda a, b: host(a) - host(b), f"{inner.name}(a) - {inner.name}(b) of independent samples")
+    """s(a) - s(b) of independent samples: independent('sub', s)."""
+    return independent("sub", statfunction)
+
+
+def ratio_of(statfunction) -> DeviceStat:
+    """s(a) / s(b) of independent samples: independent('div', s)."""
+    return independent("div", statfunction)
 
 
 _BY_IDENTITY = {
@@ -166,7 +195,8 @@ REGISTRY_NAMES = ("np.mean, np.average, np.var, np.std, np.median, np.sum, "
                   "quantile(q), percentile(p), quantile_axis0(q), percentile_axis0(p), "
                   "functools.partial(np.<quantile|percentile>, q=...[, axis=0]), "
                   "ratio_of_means, weighted_average, pearson_r, linear_fit, fit_slope, fit_intercept, mean_axis0, var_axis0, std_axis0, "
-                  "median_axis0, diff_of_means, diff_of(<scalar statistic>)")
+                  "median_axis0, diff_of_means, diff_of(s), ratio_of(s), "
+                  "independent(<'sub'|'add'|'div'|'mul'|'log_ratio'>, s_a[, s_b])")
 
 
 def lookup(statfunction: Callable) -> Optional[StatSpec]:
@@ -189,6 +219,9 @@ def require(statfunction: Callable) -> StatSpec:
             "statfunction {!r} is not in the device statistic registry and there is no host "
             "fallback; registered: {}".format(statfunction, REGISTRY_NAMES))
     return spec
+
+
+diff_of_means = diff_of(np.mean)     # mean(a) - mean(b): the reference's own independent-mode test statistic
 
 
 # ---- comparison functions for pval ------------------------------------------------

@@ -206,7 +206,7 @@ class _Run:
             return self._resample_indexed()
         if spec.independent:
             a, b = (p.resample() for p in self.parts())
-            return a - b
+            return _device.combine(spec.op, a, b)
         if spec.stat_id == _abi.STAT_MEDIAN:
             if self._long_median():
                 cols = self._sorted()
@@ -336,33 +336,25 @@ class _Run:
         """multi='independent': one single-array job per data array, each with its own Philox
         key (its index stream is independent of the others: bootstrap.py:683-691)."""
         if self._parts is None:
-            inner = StatSpec(self.spec.name, self.spec.stat_id, 1, q=self.spec.q)
-            self._parts = [_Run(inner, [a], False, self.n_samples, (self.key + k * _ARRAY_KEY_STRIDE) & _MASK64)
+            self._parts = [_Run(self.spec.inner[k], [a], False, self.n_samples,
+                                (self.key + k * _ARRAY_KEY_STRIDE) & _MASK64)
                            for k, a in enumerate(self.dev)]
         return self._parts
 
+    def loo_values(self):
+        """Single-array job: the leave-one-out statistic of every row and the K3 summary,
+        both on the device (order of the values is irrelevant to their pooled moments)."""
+        if self.spec.stat_id == _abi.STAT_MEDIAN:
+            return _device.jackknife_values_sorted(self._sorted()[0], rule=self.rule)
+        return _device.jackknife_values([self.dev[0].reshape(-1)], self.spec.stat_id)
+
     def _jackknife_independent(self):
-        """s(a) - s(b) under multi='independent': sum_k N_k leave-one-out values, array-major
-        (bootstrap.py:601-607, 708-714).  Deleting row j of array k moves only s_k, so with each
-        array's own K3 summary (statistic s_k, jackknife mean m_k, and the sums d2_k, d3_k of
-        squared / cubed deviations m_k - loo_k[j]) the pooled moments are closed forms: the
-        pooled mean is J = (N_a (m_a - s_b) + N_b (s_a - m_b)) / (N_a + N_b); the deviations are
-        c_a + (m_a - loo_a[j]) and c_b - (m_b - loo_b[j]) with c_a = J - (m_a - s_b),
-        c_b = J - (s_a - m_b), and sum_j (m_k - loo_k[j]) = 0."""
-        torch = _device._torch()
-        (sa, ma, d2a, d3a), (sb, mb, d2b, d3b) = (p.jackknife()[0, :4] for p in self.parts())
-        na, nb = (float(a.shape[0]) for a in self.dev)
-        ostat = sa - sb
-        jmean = (na * (ma - sb) + nb * (sa - mb)) / (na + nb)
-        ca = jmean - (ma - sb)
-        cb = jmean - (sa - mb)
-        d2 = (na * ca * ca + d2a) + (nb * cb * cb + d2b)
-        d3 = (na * ca ** 3 + 3.0 * ca * d2a + d3a) + (nb * cb ** 3 + 3.0 * cb * d2b - d3b)
-        out = np.zeros(8)
-        out[0], out[1], out[2], out[3] = ostat, jmean, d2, d3
-        with np.errstate(invalid="ignore", divide="ignore"):
-            out[4] = d3 / (6.0 * d2 ** 1.5)
-        return torch.from_numpy(out.reshape(1, 8))
+        """f(s_a, s_b) under multi='independent': sum_k N_k leave-one-out values, array-major
+        (bootstrap.py:601-607, 708-714).  Deleting row j of array k moves only s_k, so the values
+        are f(loo_a[j], s_b) and f(s_a, loo_b[j]) with the per-array leave-one-out vectors of K3 /
+        K3m; their mean and the sums of squared and cubed deviations are reduced on the device."""
+        (va, ja), (vb, jb) = (p.loo_values() for p in self.parts())
+        return _device.jackknife_pooled(self.spec.op, va, ja[0:1], vb, jb[0:1])
 
     # -- sharded runs with a small statistic vector ---------------------------------
     def gather_small(self, stat):

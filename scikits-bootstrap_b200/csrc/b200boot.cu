@@ -13,6 +13,7 @@
 #include "k3_jackknife.cuh"
 #include "k45_interval.cuh"
 #include "small_call.cuh"
+#include "k3v_independent.cuh"
 #include "stats.cuh"
 
 using namespace b200boot;
@@ -272,6 +273,19 @@ int jack_passes(const double** rows, int64_t n_rows, int stat, ResampleWs& w, do
   if (rc) return rc;
   return run_reduction<2>(n_rows, JackDevF<MS>{w.jack, stat, n, rows[0], rows[1]},
                           StoreAccelG{w.jack, out}, w.red, s);
+}
+
+// leave-one-out statistic of every row (multi='independent'): totals by the jackknife passes,
+// then one elementwise kernel
+template <int MS>
+int loo_values(const double** rows, int64_t n_rows, int stat, ResampleWs& w, double* values, double* summary,
+               cudaStream_t s) {
+  int rc = jack_passes<MS>(rows, n_rows, stat, w, summary, s);       // leaves the totals in w.jack
+  if (rc) return rc;
+  loo_values_kernel<MS><<<blocks_for(n_rows, 256, 148 * 16), 256, 0, s>>>(w.jack, stat, n_rows, rows[0], rows[1],
+                                                                         values);
+  B2_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace
@@ -870,6 +884,72 @@ int b200boot_jackknife_median_sorted(const double* sorted_vals, int64_t n_rows, 
   RankRule full, loo;
   if (int rc = rank_rules(rule, n_rows, &full, &loo)) return rc;
   return median_jackknife_sorted(sorted_vals, n_rows, out, as_stream(stream), full, loo);
+}
+
+// ---- multi='independent': combine, leave-one-out vectors, pooled moments ------------------
+int b200boot_combine(int op, const double* a, const double* b, double* out, int64_t n, void* stream) {
+  if (!a || !b || !out || n < 0 || op < 0 || op > B200BOOT_OP_LOG_RATIO) return fail(B200BOOT_EINVAL, "bad arguments");
+  if (n == 0) return 0;
+  combine_kernel<<<blocks_for(n, 256, 148 * 16), 256, 0, as_stream(stream)>>>(op, a, b, out, n);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+
+int b200boot_jackknife_values(const double* const* data, int n_arrays, int64_t n_rows, int stat_id,
+                              double* values, double* summary, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_moment_stat(stat_id, n_arrays, n_rows);
+  if (rc) return rc;
+  if (!data || !values || !summary) return fail(B200BOOT_EINVAL, "null pointer");
+  if (stat_outputs(stat_id) != 1) return fail(B200BOOT_EUNSUPPORTED, "leave-one-out vectors need a scalar statistic");
+  cudaStream_t s = as_stream(stream);
+  const Plan plan = make_plan(n_rows, n_arrays);
+  if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
+    return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
+  Carver cv(ws, ws_bytes);
+  ResampleWs w = carve_resample(cv, plan, stat_id, 0);
+  if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+  const double* rows[2];
+  rc = prepare_rows(data, n_arrays, n_rows, stat_id, w, rows, s);
+  if (rc) return rc;
+  switch (moment_set_of(stat_id)) {
+    case kMomSum: return loo_values<kMomSum>(rows, n_rows, stat_id, w, values, summary, s);
+    case kMomSum2: return loo_values<kMomSum2>(rows, n_rows, stat_id, w, values, summary, s);
+    case kMomAB: return loo_values<kMomAB>(rows, n_rows, stat_id, w, values, summary, s);
+    case kMomXW: return loo_values<kMomXW>(rows, n_rows, stat_id, w, values, summary, s);
+    default: return loo_values<kMomPair5>(rows, n_rows, stat_id, w, values, summary, s);
+  }
+}
+
+int b200boot_jackknife_values_sorted(const double* sorted_vals, int64_t n_rows, double* values,
+                                     double* summary, void* stream, const b200boot_rank_rule* rule) {
+  if (!sorted_vals || !values || !summary || n_rows < 1) return fail(B200BOOT_EINVAL, "bad arguments");
+  RankRule full, loo;
+  if (int rc = rank_rules(rule, n_rows, &full, &loo)) return rc;
+  cudaStream_t s = as_stream(stream);
+  int rc = median_jackknife_sorted(sorted_vals, n_rows, summary, s, full, loo);
+  if (rc) return rc;
+  loo_values_sorted_kernel<<<blocks_for(n_rows, 256, 148 * 16), 256, 0, s>>>(sorted_vals, n_rows, loo, values);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200boot_jackknife_pooled(int op, const double* loo_a, int64_t n_a, const double* s_a,
+                              const double* loo_b, int64_t n_b, const double* s_b, double* out,
+                              void* ws, size_t ws_bytes, void* stream) {
+  if (!loo_a || !loo_b || !s_a || !s_b || !out || n_a < 1 || n_b < 1 || op < 0 || op > B200BOOT_OP_LOG_RATIO)
+    return fail(B200BOOT_EINVAL, "bad arguments");
+  if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
+    return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
+  Carver cv(ws, ws_bytes);
+  JackState* st = cv.take<JackState>(1);
+  double* red = cv.take<double>((size_t)kRedBlocks * kMaxMoments);
+  if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+  cudaStream_t s = as_stream(stream);
+  const PooledLoo p{op, loo_a, n_a, s_a, loo_b, n_b, s_b};
+  int rc = run_reduction<1>(n_a + n_b, PooledSumF{p}, StorePooledMeanG{p, st}, red, s);
+  if (rc) return rc;
+  return run_reduction<2>(n_a + n_b, PooledDevF{p, st}, StorePooledG{p, st, out}, red, s);
 }
 
 // ---- K6: count matrix and finisher around a library DGEMM ------------------------------

@@ -933,6 +933,67 @@ def test_independent_difference_of_statistics(name, stat, na, nb):
     assert p == np.mean(dist < 0.0)
 
 
+OPS = {"sub": lambda u, v: u - v, "add": lambda u, v: u + v, "div": lambda u, v: u / v,
+       "mul": lambda u, v: u * v, "log_ratio": lambda u, v: np.log(u / v)}
+
+
+@pytest.mark.parametrize("op", ["div", "log_ratio", "mul", "add", "sub"])
+@pytest.mark.parametrize("sa,sb,na,nb", [(np.mean, np.mean, 60, 45), (np.mean, np.std, 301, 120),
+                                         (np.median, np.mean, 200, 77), (np.var, np.median, 64, 1000)])
+def test_independent_general_two_sample_statistic(op, sa, sb, na, nb):
+    """f(s_a(a), s_b(b)) for independent samples, any registered f: the bootstrap distribution
+    against the oracle on the device's own per-array index streams, and the pooled jackknife
+    (N_a + N_b values, bootstrap.py:601-607, 708-714) against the reference's own loop
+    (oracle.jackknife_stats_independent_loop) to 1e-12."""
+    a = np.random.default_rng(na).gamma(2, 1, na) + 1.0
+    b = np.random.default_rng(nb + 7).gamma(3, 1, nb) + 1.0
+    f = lambda u, v: OPS[op](sa(u), sb(v))
+    dstat = boot.independent(op, sa, sb)
+    assert_allclose(dstat(a, b), f(a, b), rtol=1e-15)
+    n = 500
+    idx = list(boot.bootstrap_indices_independent((a, b), n, seed=17))
+    for method in ("pi", "bca"):
+        want = orc.ci_from_indices((a, b), f, idx, (0.05, 0.95), n, method, multi="independent")
+        got = boot.ci((a, b), dstat, alpha=(0.05, 0.95), n_samples=n, multi="independent", seed=17, method=method)
+        assert_allclose(got, want, rtol=RTOL, atol=1e-14)
+    # the pooled jackknife itself, through the C ABI
+    jstat = orc.jackknife_stats_independent_loop((a, b), f)
+    parts = []
+    for x, s in ((a, sa), (b, sb)):
+        spec = boot._registry.require(s)
+        xd = dev(x)
+        if spec.stat_id == _abi.STAT_MEDIAN:
+            parts.append(_device.jackknife_values_sorted(xd.sort().values))
+        else:
+            parts.append(_device.jackknife_values([xd], spec.stat_id))
+    (va, ja), (vb, jb) = parts
+    assert_allclose(np.sort(va.cpu().numpy()), np.sort([sa(np.delete(a, i)) for i in range(na)]), rtol=RTOL)
+    pooled = _device.jackknife_pooled(dstat.spec.op, va, ja[0:1], vb, jb[0:1]).cpu().numpy()[0]
+    assert_allclose(pooled[0], f(a, b), rtol=RTOL)
+    assert_allclose(pooled[1], jstat.mean(), rtol=RTOL)
+    assert_allclose(pooled[4], orc.acceleration(jstat), rtol=1e-9, atol=1e-15)
+
+
+def test_independent_ratio_of_means_matches_reference_style_run():
+    """ratio of the means of two independent samples of different lengths: endpoints bracket the
+    plain ratio, pval counts on the device, sharding-free determinism under the seed."""
+    rng = np.random.default_rng(3)
+    a, b = rng.gamma(4, 1, 5000), rng.gamma(2, 1, 40000)           # b spans several cells
+    st = boot.ratio_of(np.mean)
+    lo, hi = boot.ci((a, b), st, n_samples=4000, multi="independent", seed=5)
+    assert lo < a.mean() / b.mean() < hi
+    assert_array_equal([lo, hi], boot.ci((a, b), st, n_samples=4000, multi="independent", seed=5))
+    p = boot.pval((a, b), st, boot.greater_than(2.0), n_samples=4000, multi="independent", seed=5)
+    _, dist = boot.ci((a, b), st, n_samples=4000, multi="independent", seed=5, method="pi", return_dist=True)
+    assert p == np.mean(dist > 2.0)
+    with pytest.raises(NotImplementedError):
+        boot.ci((a, b), st, n_samples=10)                            # independent statistic without the mode
+    with pytest.raises(NotImplementedError):
+        boot.independent("div", boot.ratio_of_means)                 # inner statistics take one array
+    with pytest.raises(ValueError):
+        boot.independent("pow", np.mean)
+
+
 # ------------------------------------------------------------------ other plans --
 
 @pytest.mark.parametrize("n,L,wrap", [(5, 3, False), (4, 3, True), (1000, 7, False), (1000, 7, True), (40001, 50, True)])
@@ -1097,6 +1158,63 @@ def test_coverage_of_the_tiled_path():
 
 
 # ------------------------------------------------------------------ full size ----
+
+def test_cfg2_shape_parity():
+    """BASELINE cfg2: N = 1e5, np.average, percentile interval — the statistic over the device's
+    own materialised indices (oracle) at a reduced resample count, and the full call's shape."""
+    x = np.random.default_rng(1).standard_normal(100_000)
+    fused_vs_oracle((x,), "average", 200, seed=3)
+    out = boot.ci(x, np.average, method="pi", n_samples=100_000, seed=0)
+    se = x.std() / np.sqrt(x.size)
+    assert_allclose(out, x.mean() + np.array([-1.96, 1.96]) * se, atol=0.05 * se)
+
+
+def test_cfg3_shape_parity():
+    """BASELINE cfg3: two paired arrays of N = 1e6, ratio of means, BCa: the oracle on the
+    device's K2 indices (50 resamples), the O(N) jackknife against the closed form, and the
+    size-independent scale identity ratio(c a, b) = c ratio(a, b) under one seed."""
+    rng = np.random.default_rng
+    a, b = rng(2).gamma(2, 1, 10**6), rng(3).gamma(3, 1, 10**6)
+    fused_vs_oracle((a, b), "ratio_of_means", 50, seed=4, multi="paired")
+    m = 2000
+    _, d1 = boot.ci((a, b), boot.ratio_of_means, n_samples=m, seed=9, multi="paired", method="pi", return_dist=True)
+    _, d2 = boot.ci((4.0 * a, b), boot.ratio_of_means, n_samples=m, seed=9, multi="paired", method="pi",
+                    return_dist=True)
+    assert_allclose(d2, 4.0 * d1, rtol=1e-13)
+    j = _device.jackknife([dev(a), dev(b)], _abi.STAT_RATIO_OF_MEANS).cpu().numpy()
+    js = orc.jack_ratio_of_means(a, b)
+    assert_allclose(j[0], a.mean() / b.mean(), rtol=RTOL)
+    assert_allclose(j[1], js.mean(), rtol=RTOL)
+    assert_allclose(j[4], orc.acceleration(js), rtol=1e-9)
+    lo, hi = boot.ci((a, b), boot.ratio_of_means, n_samples=100_000, seed=0, multi="paired")
+    assert lo < a.mean() / b.mean() < hi and (hi - lo) < 0.01
+
+
+def test_cfg4_shape_parity():
+    """BASELINE cfg4: 1000 x 10 000 table, median of every column, BCa, plus pval.  All columns
+    share the index set, so a column of the full-width run equals the 1-D run under the same
+    seed; a column subset is checked against the oracle on the device's own indices."""
+    table = np.random.default_rng(4).standard_normal((1000, 10_000))
+    td = dev(table)
+    n = 400
+    full = boot.ci(td, boot.median_axis0, n_samples=n, seed=5)
+    pfull = boot.pval(td, boot.median_axis0, n_samples=n, seed=5)
+    assert full.shape == (2, 10_000) and pfull.shape == (10_000,)
+    idx = np.array(list(boot.bootstrap_indices(table, n, seed=5)))
+    for c in (0, 1, 4999, 9999):
+        col = table[:, c]
+        want = orc.ci_from_indices((col,), np.median, idx, np.array([0.025, 0.975]), n, "bca",
+                                   jstat=orc.jack_median(col))
+        assert_allclose(full[:, c], want, rtol=RTOL, atol=1e-15)
+        assert_array_equal(full[:, c], boot.ci(col, np.median, n_samples=n, seed=5))
+        assert pfull[c] == np.mean(np.median(col[idx], axis=1) > 0)
+    # the config's resample count: shapes, ordering, and the known sampling error of a median
+    out = boot.ci(td, boot.median_axis0, n_samples=10_000, seed=0)
+    assert (out[0] < out[1]).all()
+    width = out[1] - out[0]
+    assert abs(np.median(width) / (2 * 1.96 * 1.2533 / np.sqrt(1000)) - 1) < 0.1
+
+
 
 def test_full_size_properties_cfg5():
     """BASELINE cfg5 shape (N=1e7) at a reduced resample count: size-independent
