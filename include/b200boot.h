@@ -322,6 +322,25 @@ int b200boot_select_hist_buffer(int n_alphas, int64_t n_cols, void* ws, size_t w
 int b200boot_sort_columns(double* stat, int64_t n, int64_t n_cols, void* ws, size_t ws_bytes,
                           void* stream);
 
+/* K6i — (N, D) moment statistics as count matrix x data on the tensor cores, exactly
+ * (tcgen05.mma kind::i8: uint8 counts x eight int8 base-128 digits of every column in fixed
+ * point, int32 accumulators in TMEM, int64 recombination; csrc/k6i_mma.cuh).  mean / sum / var /
+ * std of every column for resamples [lo, hi): stat_out float64[D][hi - lo]; `second` (same shape)
+ * is scratch for var / std.  The counts are those of the single-cell Lemire stream
+ * (indices = NULL, n_rows within one cell) or of the materialised index sets `indices`
+ * int64[hi - lo][n_rows] (any n_rows < 131 000).  Columns holding non-finite values are
+ * recomputed the gather way inside the call (a resample that never draws the row stays finite).
+ * ws: b200boot_count_gemm_ws_bytes(n_rows, n_cols, hi - lo). */
+size_t b200boot_count_gemm_ws_bytes(int64_t n_rows, int64_t n_cols, int64_t n_local);
+int b200boot_resample_stat_columns_gemm(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld,
+                                        int stat_id, uint64_t seed, int64_t resample_lo, int64_t resample_hi,
+                                        const int64_t* indices, double* stat_out, double* second, void* ws,
+                                        size_t ws_bytes, void* stream);
+/* test hook of the same kernel: c[m][n] (int32) = a[m][k] (uint8) . b[n][k]^T (int8), k a multiple
+ * of 128, n a multiple of 256 */
+int b200boot_debug_i8_gemm(const uint8_t* a, const int8_t* b, int32_t* c, int64_t m, int64_t n_digit_rows,
+                           int64_t k_pad, void* stream);
+
 /* Instrumentation for bench.py: cumulative number of kernels this library has
  * launched (host counter), and optional CUDA-event timing of the K1 launch on the
  * caller's stream.  b200boot_profile_last_k1_ms synchronises on the stop event. */

@@ -83,6 +83,9 @@ SIGNATURES = {
     "b200boot_select_end": (_int, [_int, _i64, _vp, _vp, _sz, _vp]),
     "b200boot_select_hist_buffer": (_int, [_int, _i64, _vp, _sz, C.POINTER(_vp), C.POINTER(_i64)]),
     "b200boot_sort_columns": (_int, [_vp, _i64, _i64, _vp, _sz, _vp]),
+    "b200boot_count_gemm_ws_bytes": (_sz, [_i64, _i64, _i64]),
+    "b200boot_resample_stat_columns_gemm": (_int, [_vp, _i64, _i64, _i64, _int, _u64, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200boot_debug_i8_gemm": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "b200boot_launch_count": (_i64, []),
     "b200boot_profile_enable": (_int, [_int]),
     "b200boot_profile_last_k1_ms": (_int, [C.POINTER(C.c_float)]),

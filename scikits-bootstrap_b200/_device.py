@@ -310,49 +310,44 @@ _GEMM_COUNT_BYTES = 1 << 30  # count-matrix chunk
 
 
 def gemm_supported(stat_id: int, n_rows: int) -> bool:
-    """K6 covers mean / sum / var / std for any N: one-cell data build the count matrix
-    directly, longer data through the materialised indices of the tiled plan (K2)."""
-    return stat_id in (_abi.STAT_MEAN, _abi.STAT_SUM, _abi.STAT_VAR, _abi.STAT_STD) and 1 <= n_rows < 2**31
+    """K6i covers mean / sum / var / std for N < 131 000 (int32 digit sums stay exact): one-cell
+    data build the count matrix directly, longer data through the materialised indices of the
+    tiled plan (K2)."""
+    return stat_id in (_abi.STAT_MEAN, _abi.STAT_SUM, _abi.STAT_VAR, _abi.STAT_STD) and 1 <= n_rows < 131000
 
 
 def resample_stat_gemm(data2d, stat_id: int, seed: int, lo: int, hi: int):
-    """K6: data float64[N][D] -> float64[D][hi-lo].  Column sums of every resample as one FP64
-    GEMM (library DGEMM through torch.mm) of the data with the resamples' count matrix; var / std
-    use the column-centred data and its squares, as K1c does."""
+    """K6i: data float64[N][D] -> float64[D][hi-lo].  Column moment sums of every resample as the
+    resamples' count matrix times the data on the tensor cores, in exact integer arithmetic
+    (tcgen05 kind::i8, csrc/k6i_mma.cuh); var / std use the column-centred data and its squares, as
+    K1c does.  Data beyond one cell take their counts from the materialised indices of the tiled
+    plan (K2), in chunks of resamples."""
     torch = _torch()
     L = _abi.lib()
     n_rows, n_cols = data2d.shape
     n_local = hi - lo
     out = torch.empty((n_cols, n_local), dtype=torch.float64, device=data2d.device)
     two = stat_id in (_abi.STAT_VAR, _abi.STAT_STD)
-    x = data2d - data2d.mean(dim=0, keepdim=True) if two else data2d
-    xt = x.t()                                                    # [D][N] view: cuBLAS takes the transpose flag
-    x2t = (x * x).t() if two else None
-    second = torch.empty_like(out) if two else None
+    one_cell = bool(L.b200boot_gemm_supported(stat_id, n_rows))
     import os
     budget = int(os.environ.get("B200BOOT_GEMM_COUNT_BYTES", _GEMM_COUNT_BYTES))
-    step = max(1, min(n_local, budget // (8 * n_rows)))
-    counts = torch.empty((step, n_rows), dtype=torch.float64, device=data2d.device)
-    one_cell = bool(L.b200boot_gemm_supported(stat_id, n_rows))
+    per_resample = n_rows + (0 if one_cell else 8 * n_rows) + (8 * n_cols if two else 0)
+    step = max(1, min(n_local, budget // per_resample))
     for a in range(lo, hi, step):
         b = min(hi, a + step)
-        c = counts[:b - a]
-        if one_cell:
-            _abi.check(L.b200boot_count_matrix(seed, n_rows, a, b, c.data_ptr(), stream_ptr()))
-        else:
-            idx = fill_indices(seed, n_rows, 1, a, b)
-            _abi.check(L.b200boot_counts_from_indices(idx.data_ptr(), b - a, n_rows, c.data_ptr(), stream_ptr()))
-            del idx
-        if step == n_local:                                       # one chunk: write in place
-            torch.mm(xt, c.t(), out=out)
-            if two:
-                torch.mm(x2t, c.t(), out=second)
-        else:
-            out[:, a - lo:b - lo] = xt @ c.t()
-            if two:
-                second[:, a - lo:b - lo] = x2t @ c.t()
-    _abi.check(L.b200boot_finish_columns(stat_id, n_rows, n_cols, n_local, out.data_ptr(),
-                                         second.data_ptr() if two else None, stream_ptr()))
+        whole = a == lo and b == hi
+        dst = out if whole else torch.empty((n_cols, b - a), dtype=torch.float64, device=data2d.device)
+        second = torch.empty_like(dst) if two else None
+        idx = None if one_cell else fill_indices(seed, n_rows, 1, a, b)
+        need = L.b200boot_count_gemm_ws_bytes(n_rows, n_cols, b - a)
+        ws, wsz = _ws.get(need)
+        _abi.check(L.b200boot_resample_stat_columns_gemm(
+            data2d.data_ptr(), n_rows, n_cols, data2d.stride(0), stat_id, seed, a, b,
+            idx.data_ptr() if idx is not None else None, dst.data_ptr(),
+            second.data_ptr() if two else None, ws, wsz, stream_ptr()))
+        if not whole:
+            out[:, a - lo:b - lo] = dst
+        del idx, second
     return out
 
 

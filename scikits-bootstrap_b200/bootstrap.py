@@ -224,10 +224,9 @@ class _Run:
         if spec.n_out > 1:
             return _device.resample_stat([a.reshape(-1) for a in self.dev], spec.stat_id, self.key, lo, hi)
         if (self.vector and _device.gemm_pays(self.dev[0].shape[0], self.n_cols) and hi > lo
-                and _device.gemm_supported(spec.stat_id, self.dev[0].shape[0])
-                and bool(torch.isfinite(self.dev[0]).all())):
-            # K6.  Only for finite data: in a product 0 * nan is nan, so a row that a resample
-            # does not draw would still poison it, unlike the gather x[indices] (bootstrap.py:431)
+                and _device.gemm_supported(spec.stat_id, self.dev[0].shape[0])):
+            # K6i: count matrix x data on the tensor cores (exact integer split); columns with
+            # non-finite entries are redone the gather way inside the call, so no host check
             return _device.resample_stat_gemm(self.dev[0], spec.stat_id, self.key, lo, hi)
         if self.vector and _device.columns_block_width(spec.stat_id, self.dev[0].shape[0]) > 0:
             return _device.resample_stat_columns(self.dev[0], spec.stat_id, self.key, lo, hi)   # K1c

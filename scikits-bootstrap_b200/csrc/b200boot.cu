@@ -10,6 +10,7 @@
 #include "k1c_columns.cuh"
 #include "k1m_median.cuh"
 #include "k6_gemm.cuh"
+#include "k6i_mma.cuh"
 #include "k3_jackknife.cuh"
 #include "k45_interval.cuh"
 #include "small_call.cuh"
@@ -1000,6 +1001,150 @@ int b200boot_finish_columns(int stat_id, int64_t n_rows, int64_t n_cols, int64_t
                                                                                   s1, s2);
   B2_LAUNCH_CHECK();
   return 0;
+}
+
+// ---- K6i: the count x data contraction on tcgen05 (exact integer split) -----------------
+namespace {
+int64_t k6i_k_pad(int64_t n_rows) { return ((n_rows + kI8KChunk - 1) / kI8KChunk) * kI8KChunk; }
+int64_t k6i_cols_pad(int64_t n_cols) { return ((n_cols + kI8ColsPerTile - 1) / kI8ColsPerTile) * kI8ColsPerTile; }
+
+int launch_k6i(const K6iParams& P, cudaStream_t s) {
+  const bool resident = P.k_pad / kI8KChunk <= kI8MaxResidentChunks;
+  const size_t smem = k6i_smem_bytes(P.k_pad, resident);
+  static PerDeviceOnce configured;
+  B2_CUDA(configured.run([] {
+    cudaError_t e = cudaFuncSetAttribute(k6i_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)k6i_smem_bytes(kI8MaxResidentChunks * kI8KChunk, true));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(k6i_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)k6i_smem_bytes(kI8KChunk, false));
+    return e;
+  }));
+  const int64_t m_tiles = (P.m_total + kI8M - 1) / kI8M;
+  // column splits: fill the SMs when there are few resample tiles
+  int64_t splits = std::max<int64_t>(1, std::min<int64_t>(P.n_col_tiles, (2 * (int64_t)sm_count()) / std::max<int64_t>(m_tiles, 1)));
+  splits = std::min<int64_t>(splits, 65535);
+  const dim3 grid((unsigned)m_tiles, (unsigned)splits);
+  if (resident)
+    k6i_mma_kernel<true><<<grid, kI8Threads, smem, s>>>(P);
+  else
+    k6i_mma_kernel<false><<<grid, kI8Threads, smem, s>>>(P);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace
+
+size_t b200boot_count_gemm_ws_bytes(int64_t n_rows, int64_t n_cols, int64_t n_local) {
+  if (n_rows < 1 || n_cols < 1 || n_local < 0) return 0;
+  const int64_t k_pad = k6i_k_pad(n_rows), cp = k6i_cols_pad(n_cols);
+  return 4096 + pad256((size_t)cp * kI8Digits * k_pad) + 3 * pad256((size_t)cp * 8) +
+         pad256((size_t)std::max<int64_t>(n_local, 1) * k_pad);
+}
+
+int b200boot_resample_stat_columns_gemm(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld,
+                                        int stat_id, uint64_t seed, int64_t resample_lo, int64_t resample_hi,
+                                        const int64_t* indices, double* stat_out, double* second, void* ws,
+                                        size_t ws_bytes, void* stream) {
+  const int64_t n_local = resample_hi - resample_lo;
+  const int ms = moment_set_of(stat_id);
+  if (ms != kMomSum && ms != kMomSum2)
+    return fail(B200BOOT_EUNSUPPORTED, "statistic %d is not a single-array moment statistic", stat_id);
+  if (!data || !stat_out || n_rows < 1 || n_rows >= 131000 || n_cols < 1 || ld < n_cols || n_local < 0)
+    return fail(B200BOOT_EINVAL, "columns_gemm: bad arguments (n_rows must stay below 131 000)");
+  const bool two = ms == kMomSum2;
+  if (two && !second) return fail(B200BOOT_EINVAL, "var / std need the second-moment buffer");
+  if (n_local == 0) return 0;
+  if (!indices && n_rows > kSmemDataBytes / 8)
+    return fail(B200BOOT_EUNSUPPORTED, "columns_gemm: n_rows=%lld beyond one cell needs materialised indices",
+                (long long)n_rows);
+  if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
+    return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
+  cudaStream_t s = as_stream(stream);
+  const int64_t k_pad = k6i_k_pad(n_rows), cp = k6i_cols_pad(n_cols);
+  Carver cv(ws, ws_bytes);
+  int32_t* flags = cv.take<int32_t>(64);           // [0] count overflow, [1] some column is non-finite
+  int8_t* digits = cv.take<int8_t>((size_t)cp * kI8Digits * k_pad);
+  double* scale = cv.take<double>((size_t)cp);
+  double* centre = cv.take<double>((size_t)cp);
+  int32_t* bad_col = cv.take<int32_t>((size_t)cp * 2);
+  uint8_t* counts = cv.take<uint8_t>((size_t)n_local * k_pad);
+  if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+  B2_CUDA(cudaMemsetAsync(flags, 0, 256, s));
+  B2_CUDA(cudaMemsetAsync(bad_col, 0, (size_t)cp * 4, s));
+  // the resamples' count matrix, once
+  if (indices) {
+    B2_CUDA(cudaMemsetAsync(counts, 0, (size_t)n_local * k_pad, s));
+    k6i_count_bytes_from_indices_kernel<<<blocks_for(n_local * n_rows, 256, 148 * 16), 256, 0, s>>>(
+        indices, n_local, n_rows, k_pad, counts, flags);
+    B2_LAUNCH_CHECK();
+  } else {
+    static PerDeviceOnce configured;
+    B2_CUDA(configured.run([] {
+      return cudaFuncSetAttribute(k6i_count_bytes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    }));
+    const int grid = (int)std::min<int64_t>((int64_t)sm_count() * 4, n_local);
+    k6i_count_bytes_kernel<<<grid, 256, (size_t)k_pad, s>>>(seed, n_rows, k_pad, resample_lo, n_local, counts, flags);
+    B2_LAUNCH_CHECK();
+  }
+  const double* c = nullptr;
+  if (two) {                                       // var / std: columns centred on their means, as K1c does
+    const dim3 block(32, 8);
+    k1c_column_means_kernel<<<(unsigned)((n_cols + 31) / 32), block, 0, s>>>(data, n_rows, n_cols, ld, centre);
+    B2_LAUNCH_CHECK();
+    c = centre;
+  }
+  for (int pass = 0; pass < (two ? 2 : 1); ++pass) {
+    double* dst = pass == 0 ? stat_out : second;
+    B2_CUDA(cudaMemsetAsync(scale, 0, (size_t)cp * 8, s));
+    k6i_column_scale_kernel<<<(unsigned)((n_cols + 31) / 32), 256, 0, s>>>(data, n_rows, n_cols, ld, c, pass, scale,
+                                                                          bad_col, flags + 1);
+    B2_LAUNCH_CHECK();
+    k6i_digits_kernel<<<blocks_for(cp * (k_pad / 16), 256, 148 * 32), 256, 0, s>>>(data, n_rows, n_cols, cp, ld, k_pad,
+                                                                                  c, pass, scale, digits);
+    B2_LAUNCH_CHECK();
+    K6iParams P{};
+    P.counts = counts;
+    P.digits = digits;
+    P.scale = scale;
+    P.m_total = n_local;
+    P.k_pad = k_pad;
+    P.n_cols = n_cols;
+    P.n_col_tiles = cp / kI8ColsPerTile;
+    P.out = dst;
+    P.out_ld = n_local;
+    P.out_i32 = nullptr;
+    P.overflow = flags;
+    int rc = launch_k6i(P, s);
+    if (rc) return rc;
+    k6i_fixup_kernel<<<(unsigned)std::min<int64_t>((n_local * 32 + 255) / 256, (int64_t)sm_count() * 8), 256, 0, s>>>(
+        data, n_rows, n_cols, ld, c, pass, bad_col, flags + 1, seed, resample_lo, n_local, indices, dst);
+    B2_LAUNCH_CHECK();
+  }
+  const int64_t total = n_cols * n_local;
+  k6_finish_kernel<<<blocks_for(total, 256, 148 * 16), 256, 0, s>>>(stat_id, (double)n_rows, total, stat_out,
+                                                                   two ? second : nullptr);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200boot_debug_i8_gemm(const uint8_t* a, const int8_t* b, int32_t* c, int64_t m, int64_t n_digit_rows,
+                           int64_t k_pad, void* stream) {
+  if (!a || !b || !c || m < 1 || n_digit_rows < kI8N || n_digit_rows % kI8N != 0 || k_pad < kI8KChunk ||
+      k_pad % kI8KChunk != 0)
+    return fail(B200BOOT_EINVAL, "debug_i8_gemm: n must be a multiple of 256 and k of 128");
+  K6iParams P{};
+  P.counts = a;
+  P.digits = b;
+  P.scale = nullptr;
+  P.m_total = m;
+  P.k_pad = k_pad;
+  P.n_cols = 0;
+  P.n_col_tiles = n_digit_rows / kI8N;
+  P.out = nullptr;
+  P.out_ld = 0;
+  P.out_i32 = c;
+  P.overflow = nullptr;
+  return launch_k6i(P, as_stream(stream));
 }
 
 // ---- instrumentation ---------------------------------------------------------------
