@@ -257,6 +257,17 @@ int b200boot_jackknife_pooled(int op, const double* loo_a, int64_t n_a, const do
                               const double* loo_b, int64_t n_b, const double* s_b, double* out,
                               void* ws, size_t ws_bytes, void* stream);
 
+/* method='abc' (bootstrap.py:507-567) for np.average: the reference's weighted means with numpy's
+ * own arithmetic (single IEEE operations, pairwise summation order), so that its finite
+ * differences — rounding noise included — are reproduced:
+ *   tp[i] = average(x, p0 + ep (e_i - p0)), tm[i] = average(x, p0 - ep (e_i - p0)), p0 = 1/N;
+ *   out[v] = average(x, weights[v][:]) for explicit weight vectors float64[n_vectors][N];
+ *   weights = NULL, n_vectors = 1: out[0] = np.mean(x), numpy's pairwise sum over N. */
+int b200boot_abc_identity_averages(const double* x, int64_t n_rows, double ep, double* tp, double* tm,
+                                   void* stream);
+int b200boot_weighted_averages(const double* x, int64_t n_rows, const double* weights, int64_t n_vectors,
+                               double* out, void* stream);
+
 /* Occupancies of the multinomial chain (K0), for inspection and tests:
  * counts int32[n_tiles][n_local]; class_counts (may be NULL) int32[n_full][n_local][16],
  * the split of every full tile's draws over its 16 shared-memory bank classes.

@@ -75,6 +75,8 @@ SIGNATURES = {
     "b200boot_jackknife_values": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
     "b200boot_jackknife_values_sorted": (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "b200boot_jackknife_pooled": (_int, [_int, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "b200boot_abc_identity_averages": (_int, [_vp, _i64, C.c_double, _vp, _vp, _vp]),
+    "b200boot_weighted_averages": (_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "b200boot_count": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _vp]),
     "b200boot_select": (_int, [_vp, _i64, _i64, _vp, _int, _vp, _vp, _sz, _vp]),
     "b200boot_select_begin": (_int, [_vp, _int, _i64, _vp, _sz, _vp]),

@@ -532,6 +532,29 @@ def jackknife_median_columns(data2d, rule=None):
     return out
 
 
+def abc_identity_averages(x, ep: float):
+    """method='abc': the 2N perturbed weighted means (numpy arithmetic) -> (tp, tm) numpy arrays."""
+    torch = _torch()
+    n = x.numel()
+    out = torch.empty((2, n), dtype=torch.float64, device=x.device)
+    _abi.check(_abi.lib().b200boot_abc_identity_averages(x.data_ptr(), n, float(ep), out[0].data_ptr(),
+                                                         out[1].data_ptr(), stream_ptr()))
+    h = to_host(out)
+    return h[0], h[1]
+
+
+def weighted_averages(x, weights) -> np.ndarray:
+    """np.average(x, weights=w) for every row w of `weights` (numpy arithmetic, on the device);
+    weights=None: np.average(x) itself, as a one-element array."""
+    torch = _torch()
+    w = None if weights is None else host_to_device(np.ascontiguousarray(weights, dtype=np.float64), x.device)
+    n_vec = 1 if w is None else w.shape[0]
+    out = torch.empty(n_vec, dtype=torch.float64, device=x.device)
+    _abi.check(_abi.lib().b200boot_weighted_averages(x.data_ptr(), x.numel(), None if w is None else w.data_ptr(),
+                                                     n_vec, out.data_ptr(), stream_ptr()))
+    return to_host(out)
+
+
 def combine(op: int, a, b):
     """f(a[i], b[i]) of two statistic vectors (multi='independent')."""
     torch = _torch()

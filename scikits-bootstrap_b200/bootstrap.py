@@ -427,18 +427,18 @@ def ci(
                     return_dist, seed, use_numba, None)
 
 
-def _ci_abc(arrays, statfunction, alphas, output):
-    """ABC interval (bootstrap.py:507-567) for the statistic the reference's ABC supports
-    among the registry: the weighted mean, np.average (the reference calls
+def _ci_abc(arrays, statfunction, alphas, output, epsilon):
+    """ABC interval (bootstrap.py:507-567) for the statistic the reference's ABC supports among
+    the registry: the weighted mean, np.average (the reference calls
     `statfunction(x, weights=...)`; np.mean & co. fail its weights probe with the TypeError
     reproduced below).
 
-    For the weighted mean the finite-difference quantities of the reference have closed
-    forms — t1_i = x_i - mean, t2 = 0, cq = 0 — so the interval follows from the first
-    three central sums, which come from the device (K3).  This is the epsilon -> well-
-    conditioned limit of the reference's formulas: the reference's own result carries the
-    rounding noise of its second differences (2e-7 relative at N = 20, 5e-4 at N = 1000 with
-    the default epsilon; 1e-9 agreement at epsilon = 0.01), see DESIGN.md."""
+    The reference takes finite differences, with step epsilon / N, of 2N + 3 + A weighted means;
+    at the default epsilon its second differences are dominated by the rounding of those means,
+    so the answer is defined by numpy's arithmetic.  The device evaluates every weighted mean
+    with that arithmetic (single IEEE operations, numpy's pairwise summation order:
+    csrc/abc_method.cuh); what follows are the reference's own O(N) numpy expressions, so the
+    interval agrees with the reference to rounding of `pow` (about 1e-15) for any epsilon."""
     if statfunction is not np.average:
         if lookup(statfunction) is not None or statfunction is np.mean:
             raise TypeError("statfunction does not accept correct arguments for ABC")
@@ -449,21 +449,31 @@ def _ci_abc(arrays, statfunction, alphas, output):
         raise NotImplementedError("method='abc' needs a single 1-D array")
     with _device.device_context(arrays):
         x = _device.to_device_f64(arrays[0]).reshape(-1)
-        j = _device.to_host(_device.jackknife([x], _abi.STAT_MEAN))
-    n = float(x.numel())
-    t0 = j[0]
-    s2 = j[2] * (n - 1.0) ** 2           # sum (x - mean)^2   (K3: d_i = (x_i - mean)/(N-1))
-    s3 = j[3] * (n - 1.0) ** 3           # sum (x - mean)^3
-    sighat = np.sqrt(s2) / n
-    with np.errstate(invalid="ignore", divide="ignore"):
-        a = s3 / (6 * n ** 3 * sighat ** 3)
-        z0 = _interval.nppf(2 * _interval.ncdf(a) * _interval.ncdf(-0.0))
-        big_z = z0 + _interval.nppf(alphas)
-        za = big_z / (1 - a * big_z) ** 2
-        abc = t0 + za * s2 / (n ** 2 * sighat)
-    if output == "lowhigh":
-        return abc
-    return np.abs(abc - t0)[np.newaxis].T
+        nn = int(x.numel())
+        n = nn * 1.0
+        ep = epsilon / n * 1.0
+        p0 = np.repeat(1.0 / n, nn)
+        tp, tm = _device.abc_identity_averages(x, ep)
+        t0 = _device.weighted_averages(x, p0[np.newaxis])[0]
+        t1 = (tp - tm) / (2 * ep)
+        t2 = (tp - 2 * t0 + tm) / ep**2
+        sighat = np.sqrt(np.sum(t1**2)) / n
+        with np.errstate(invalid="ignore", divide="ignore"):
+            a = (np.sum(t1**3)) / (6 * n**3 * sighat**3)
+            delta = t1 / (n**2 * sighat)
+            cqp, cqm = _device.weighted_averages(x, np.stack([p0 + ep * delta, p0 - ep * delta]))
+            cq = (cqp - 2 * t0 + cqm) / (2 * sighat * ep**2)
+            bhat = np.sum(t2) / (2 * n**2)
+            curv = bhat / sighat - cq
+            z0 = _interval.nppf(2 * _interval.ncdf(a) * _interval.ncdf(-curv))
+            big_z = z0 + _interval.nppf(alphas)
+            za = big_z / (1 - a * big_z) ** 2
+            flat = np.atleast_1d(za).reshape(-1)
+            abc = _device.weighted_averages(x, np.stack([p0 + z * delta for z in flat])).reshape(np.shape(za))
+        if output == "lowhigh":
+            return abc
+        full = _device.weighted_averages(x, None)[0]                           # statfunction(*tdata)
+        return np.abs(abc - full)[np.newaxis].T
 
 
 def ci_indexed(data, statfunction=None, indices=None, alpha=0.05, method="bca", output="lowhigh",
@@ -509,7 +519,7 @@ def _ci_impl(data, statfunction, alpha, n_samples, method, output, epsilon, mult
             raise NotImplementedError("multi='independent' is not currently supported for ABC.")
         if output not in ("lowhigh", "errorbar"):
             raise ValueError("Output option {0} is not supported.".format(output))
-        return _ci_abc(arrays, statfunction, alphas, output)
+        return _ci_abc(arrays, statfunction, alphas, output, epsilon)
     if use_numba:                                                 # bootstrap.py:415-437
         if multi == "independent":
             raise NotImplementedError(

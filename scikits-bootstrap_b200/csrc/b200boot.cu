@@ -15,6 +15,7 @@
 #include "k45_interval.cuh"
 #include "small_call.cuh"
 #include "k3v_independent.cuh"
+#include "abc_method.cuh"
 #include "stats.cuh"
 
 using namespace b200boot;
@@ -951,6 +952,26 @@ int b200boot_jackknife_pooled(int op, const double* loo_a, int64_t n_a, const do
   int rc = run_reduction<1>(n_a + n_b, PooledSumF{p}, StorePooledMeanG{p, st}, red, s);
   if (rc) return rc;
   return run_reduction<2>(n_a + n_b, PooledDevF{p, st}, StorePooledG{p, st, out}, red, s);
+}
+
+// ---- method='abc': numpy-faithful weighted means --------------------------------------------
+int b200boot_abc_identity_averages(const double* x, int64_t n_rows, double ep, double* tp, double* tm,
+                                   void* stream) {
+  if (!x || !tp || !tm || n_rows < 1) return fail(B200BOOT_EINVAL, "bad arguments");
+  abc_identity_averages_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, as_stream(stream)>>>(x, n_rows, ep, tp, tm);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200boot_weighted_averages(const double* x, int64_t n_rows, const double* weights, int64_t n_vectors,
+                               double* out, void* stream) {
+  if (!x || !out || n_rows < 1 || n_vectors < 0 || (!weights && n_vectors != 1))
+    return fail(B200BOOT_EINVAL, "bad arguments");
+  if (n_vectors == 0) return 0;
+  abc_weighted_averages_kernel<<<(unsigned)((n_vectors + 31) / 32), 32, 0, as_stream(stream)>>>(x, n_rows, weights,
+                                                                                               n_vectors, out);
+  B2_LAUNCH_CHECK();
+  return 0;
 }
 
 // ---- K6: count matrix and finisher around a library DGEMM ------------------------------

@@ -724,23 +724,36 @@ def test_reference_property_tests():
 
 def test_abc_for_the_weighted_mean():
     """method='abc' (bootstrap.py:507-567; tests/bootstrap_test.py:140-150, 190-195, 372-376).
-    Device moments + closed forms = the well-conditioned limit of the reference's finite
-    differences: 1e-8 agreement with the oracle's faithful restatement at epsilon=0.01, and
-    within the reference's own rounding noise (2e-7) of its goldens at the default epsilon."""
+    The device evaluates the reference's 2N + 3 + A weighted means with numpy's own arithmetic
+    (pairwise summation order, single IEEE operations), so the finite differences — rounding
+    noise included — and with them the interval agree with the oracle's faithful restatement
+    for any epsilon, the default one included."""
     import pandas as pd
     got = boot.ci(DATA20, method="abc", seed=SEED)
-    assert_allclose(got, orc.ci_abc(DATA20, epsilon=0.01), rtol=1e-8)
-    assert_allclose(got, [0.20982275, 1.20374686], rtol=5e-7)
+    assert_allclose(got, orc.ci_abc(DATA20), rtol=RTOL)
+    assert_allclose(got, [0.20982275, 1.20374686], rtol=1e-7)                     # the reference's golden
     got = boot.ci(DATA20, alpha=(0.1, 0.2, 0.8, 0.9), method="abc")
-    assert_allclose(got, [0.39472915, 0.51161304, 0.93789723, 1.04407254], rtol=5e-7)
+    assert_allclose(got, orc.ci_abc(DATA20, alpha=(0.1, 0.2, 0.8, 0.9)), rtol=RTOL)
+    assert_allclose(got, [0.39472915, 0.51161304, 0.93789723, 1.04407254], rtol=1e-7)
     eb = boot.ci(DATA20, output="errorbar", method="abc")
     assert eb.shape == (2, 1)
+    assert_allclose(eb, orc.ci_abc(DATA20, output="errorbar"), rtol=1e-11)
     assert_allclose(eb.T, abs(np.average(DATA20) - boot.ci(DATA20, method="abc"))[np.newaxis])
     assert_allclose(boot.ci(pd.Series(DATA20, index=np.arange(50, 70)), method="abc"), boot.ci(DATA20, method="abc"))
-    x = np.random.default_rng(0).gamma(2, 1, 500)
-    assert_allclose(boot.ci(x, method="abc"), orc.ci_abc(x, epsilon=0.1), rtol=1e-7)      # noise ~ 1/epsilon^2
+    rng = np.random.default_rng(0)
+    for n, eps in ((7, 0.001), (128, 0.001), (129, 0.01), (500, 0.001), (500, 0.1), (1000, 0.001), (3001, 1e-4)):
+        x = rng.gamma(2, 1, n)
+        assert_allclose(boot.ci(x, method="abc", epsilon=eps), orc.ci_abc(x, epsilon=eps), rtol=RTOL), (n, eps)
+    # the weighted means themselves: numpy's bits
+    x = rng.standard_normal(777)
+    w = rng.random((5, 777))
+    got = _device.weighted_averages(dev(x), w)
+    assert_array_equal(got, [np.average(x, weights=wi) for wi in w])
+    assert _device.weighted_averages(dev(x), None)[0] == np.average(x)
     with pytest.raises(ValueError):
         boot.ci(DATA20, method="abc", return_dist=True)
+    with pytest.raises(TypeError):
+        boot.ci(DATA20, np.mean, method="abc")
 
 
 def test_warnings_match_reference():
@@ -987,7 +1000,7 @@ def test_independent_ratio_of_means_matches_reference_style_run():
     _, dist = boot.ci((a, b), st, n_samples=4000, multi="independent", seed=5, method="pi", return_dist=True)
     assert p == np.mean(dist > 2.0)
     with pytest.raises(NotImplementedError):
-        boot.ci((a, b), st, n_samples=10)                            # independent statistic without the mode
+        boot.ci((a, a), st, n_samples=10)                            # independent statistic without the mode
     with pytest.raises(NotImplementedError):
         boot.independent("div", boot.ratio_of_means)                 # inner statistics take one array
     with pytest.raises(ValueError):
