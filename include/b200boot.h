@@ -339,7 +339,7 @@ int b200boot_sort_columns(double* stat, int64_t n, int64_t n_cols, void* ws, siz
  * std of every column for resamples [lo, hi): stat_out float64[D][hi - lo]; `second` (same shape)
  * is scratch for var / std.  The counts are those of the single-cell Lemire stream
  * (indices = NULL, n_rows within one cell) or of the materialised index sets `indices`
- * int64[hi - lo][n_rows] (any n_rows < 131 000).  Columns holding non-finite values are
+ * int64[hi - lo][n_rows] (any n_rows < 2^25: the int32 digit sums stay exact).  Columns holding non-finite values are
  * recomputed the gather way inside the call (a resample that never draws the row stays finite).
  * ws: b200boot_count_gemm_ws_bytes(n_rows, n_cols, hi - lo). */
 size_t b200boot_count_gemm_ws_bytes(int64_t n_rows, int64_t n_cols, int64_t n_local);

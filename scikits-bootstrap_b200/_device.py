@@ -310,10 +310,10 @@ _GEMM_COUNT_BYTES = 1 << 30  # count-matrix chunk
 
 
 def gemm_supported(stat_id: int, n_rows: int) -> bool:
-    """K6i covers mean / sum / var / std for N < 131 000 (int32 digit sums stay exact): one-cell
+    """K6i covers mean / sum / var / std for N < 2^25 (int32 digit sums stay exact): one-cell
     data build the count matrix directly, longer data through the materialised indices of the
     tiled plan (K2)."""
-    return stat_id in (_abi.STAT_MEAN, _abi.STAT_SUM, _abi.STAT_VAR, _abi.STAT_STD) and 1 <= n_rows < 131000
+    return stat_id in (_abi.STAT_MEAN, _abi.STAT_SUM, _abi.STAT_VAR, _abi.STAT_STD) and 1 <= n_rows < 2**25
 
 
 def resample_stat_gemm(data2d, stat_id: int, seed: int, lo: int, hi: int):

@@ -1070,8 +1070,8 @@ int b200boot_resample_stat_columns_gemm(const double* data, int64_t n_rows, int6
   const int ms = moment_set_of(stat_id);
   if (ms != kMomSum && ms != kMomSum2)
     return fail(B200BOOT_EUNSUPPORTED, "statistic %d is not a single-array moment statistic", stat_id);
-  if (!data || !stat_out || n_rows < 1 || n_rows >= 131000 || n_cols < 1 || ld < n_cols || n_local < 0)
-    return fail(B200BOOT_EINVAL, "columns_gemm: bad arguments (n_rows must stay below 131 000)");
+  if (!data || !stat_out || n_rows < 1 || n_rows >= ((int64_t)1 << 25) || n_cols < 1 || ld < n_cols || n_local < 0)
+    return fail(B200BOOT_EINVAL, "columns_gemm: bad arguments (n_rows must stay below 2^25)");
   const bool two = ms == kMomSum2;
   if (two && !second) return fail(B200BOOT_EINVAL, "var / std need the second-moment buffer");
   if (n_local == 0) return 0;

@@ -11,9 +11,10 @@
 //     x[i][d] = q[i][d] * 2^(e_d - 52), |q| < 2^52 (rounding: half an ulp of the column's largest
 //     value — a plain FP64 sum rounds every addend to the running sum's ulp, which is no better),
 //     and q as eight balanced base-128 digits, q = sum_s dig_s * 128^s, dig_s in [-64, 63]: int8;
-//   * sum_i c[r][i] * dig_s[i][d] is an int32 dot product (|.| <= N * 255 * 64: exact for
-//     N < 131 000), one tcgen05.mma.kind::i8 column per (d, s); the eight digit sums are
-//     recombined in int64 (exact, < 2^63) and scaled once: one rounding per output.
+//   * sum_i c[r][i] * dig_s[i][d] is an int32 dot product (the counts of a resample add up to N,
+//     so |.| <= 64 N: exact for N < 2^25), one tcgen05.mma.kind::i8 column per (d, s); the digit
+//     sums are recombined exactly in two int64 halves, joined and scaled in FP64: two roundings
+//     per output.
 // Tile: 128 resamples (UMMA M) x 256 digit columns = 32 data columns (UMMA N), K = rows in
 // chunks of 128 bytes (one SWIZZLE_128B atom row), four K = 32 instructions per chunk.
 // Operands are staged in shared memory in the canonical K-major SWIZZLE_128B layout by the
@@ -325,11 +326,17 @@ __global__ void __launch_bounds__(kI8Threads, 1) k6i_mma_kernel(const K6iParams 
 #pragma unroll
         for (int c = 0; c < 32 / kI8Digits; ++c) {
           const int64_t d = tile * kI8ColsPerTile + cb * (32 / kI8Digits) + c;
-          long long acc = 0;
+          // digits 0..3 and 4..7 recombined exactly in int64 (each half below 2^52 for N < 2^25),
+          // then hi * 128^4 + lo in FP64: both conversions exact, one rounding
+          long long lo = 0, hi = 0;
 #pragma unroll
-          for (int s = kI8Digits - 1; s >= 0; --s) acc = acc * 128 + (long long)(int32_t)v[c * kI8Digits + s];
+          for (int s = 3; s >= 0; --s) {
+            lo = lo * 128 + (long long)(int32_t)v[c * kI8Digits + s];
+            hi = hi * 128 + (long long)(int32_t)v[c * kI8Digits + 4 + s];
+          }
           if (r < P.m_total && d < P.n_cols && P.out != nullptr)
-            P.out[d * P.out_ld + r] = poisoned ? nan("") : (double)acc * P.scale[d];
+            P.out[d * P.out_ld + r] =
+                poisoned ? nan("") : fma((double)hi, 268435456.0, (double)lo) * P.scale[d];
         }
       }
     }
