@@ -5,6 +5,7 @@ torch.distributed only; every computation is a libb200boot kernel."""
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from typing import Optional, Sequence, Tuple
 
 import numpy as np
@@ -17,12 +18,18 @@ def _torch():
     return torch
 
 
+_cuda_seen = False
+
+
 def require_cuda():
+    global _cuda_seen
     torch = _torch()
-    if not torch.cuda.is_available():
-        raise _abi.B200BootError(
-            "no CUDA device: scikits-bootstrap_b200 runs its resampling path on a B200 only "
-            "(there is no CPU fallback)")
+    if not _cuda_seen:                      # asked once: a device that was there stays there
+        if not torch.cuda.is_available():
+            raise _abi.B200BootError(
+                "no CUDA device: scikits-bootstrap_b200 runs its resampling path on a B200 only "
+                "(there is no CPU fallback)")
+        _cuda_seen = True
     return torch
 
 
@@ -167,9 +174,13 @@ def _ptr_array(tensors: Sequence) -> C.Array:
     return arr
 
 
+@functools.lru_cache(maxsize=256)
+def _workspace_bytes(stat_id: int, n_rows: int, n_arrays: int, n_cols: int, n_local: int, n_alphas: int) -> int:
+    return _abi.lib().b200boot_workspace_bytes(stat_id, n_rows, n_arrays, n_cols, n_local, n_alphas)
+
+
 def workspace_for(stat_id: int, n_rows: int, n_arrays: int, n_cols: int, n_local: int, n_alphas: int):
-    need = _abi.lib().b200boot_workspace_bytes(stat_id, n_rows, n_arrays, n_cols, n_local, n_alphas)
-    return _ws.get(need)
+    return _ws.get(_workspace_bytes(stat_id, n_rows, n_arrays, n_cols, n_local, n_alphas))
 
 
 def _ws_budget() -> int:
@@ -239,8 +250,13 @@ class _SmallCallBuffers:
 _small = _SmallCallBuffers()
 
 
-def ci_small_supported(stat_id: int, n_arrays: int, n_rows: int, n_samples: int, n_alphas: int) -> bool:
+@functools.lru_cache(maxsize=256)
+def _ci_small_supported(stat_id: int, n_arrays: int, n_rows: int, n_samples: int, n_alphas: int) -> bool:
     return bool(_abi.lib().b200boot_ci_small_supported(stat_id, n_arrays, n_rows, n_samples, n_alphas))
+
+
+def ci_small_supported(stat_id: int, n_arrays: int, n_rows: int, n_samples: int, n_alphas: int) -> bool:
+    return _ci_small_supported(stat_id, n_arrays, n_rows, n_samples, n_alphas)
 
 
 def ci_small(arrays: Sequence, stat_id: int, seed: int, n_samples: int, alphas: np.ndarray, bca: bool,

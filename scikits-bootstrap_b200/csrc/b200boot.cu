@@ -167,7 +167,7 @@ int launch_occupancies_fast(uint64_t seed, int64_t resample_lo, int64_t n_local,
     const int64_t n_batches = (total + kTreeBatch - 1) / kTreeBatch;
     const int grid = (int)std::min<int64_t>(n_batches, (int64_t)sm_count() * 32);
     k0_class_tree_kernel<<<grid, kTreeThreads, 0, s>>>(seed, resample_lo, n_local, plan.n_full, counts, half_tables,
-                                                       cls, overflow);
+                                                       cls, overflow, make_round_keys(seed));
     B2_LAUNCH_CHECK();
   }
   return 0;
@@ -479,13 +479,57 @@ int b200boot_ci_small(const double* const* data, int n_arrays, int64_t n_rows, i
   if (!data || !alphas || !stat_out || !result_dev) return fail(B200BOOT_EINVAL, "null pointer");
   if (bca) need_jack = 1;
   cudaStream_t s = as_stream(stream);
+  const Plan plan = make_plan(n_rows, n_arrays);
+  if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
+    return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
+  Carver cv(ws, ws_bytes);
+  ResampleWs w = carve_resample(cv, plan, stat_id, n_samples);
+  if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+  // one memset clears the work counter, the overflow flag and the jackknife state behind them
+  static_assert(sizeof(JackState) <= 256, "JackState must fit the slot behind the two counters");
+  B2_CUDA(cudaMemsetAsync(w.work_counter, 0, 512 + sizeof(JackState), s));
+  const double* rows[2] = {data[0], n_arrays > 1 ? data[1] : nullptr};
+  if (stat_needs_centering(stat_id)) {
+    center_small_kernel<<<1, kSmallThreads, 0, s>>>(rows[0], rows[1], n_rows, w.jack, w.centered[0],
+                                                    n_arrays > 1 ? w.centered[1] : nullptr);
+    B2_LAUNCH_CHECK();
+    for (int a = 0; a < n_arrays; ++a) rows[a] = w.centered[a];
+  }
   // K1 over the single cell, finishing the statistic itself
-  rc = b200boot_resample_stat_after(data, n_arrays, n_rows, stat_id, seed, 0, n_samples, stat_out, ws, ws_bytes,
-                                    stream, nullptr);
-  if (rc) return rc;
+  {
+    const int ms = moment_set_of(stat_id);
+    int64_t chunk = kK1Warps;                       // one pass of the CTA's warps per work item
+    const int64_t n_chunks = (n_samples + chunk - 1) / chunk;
+    K1Params P{};
+    P.data[0] = rows[0];
+    P.data[1] = rows[1];
+    P.plan = plan;
+    P.seed = seed;
+    P.resample_lo = 0;
+    P.n_local = n_samples;
+    P.rk = make_round_keys(seed);
+    P.partial = w.partial;
+    P.work_counter = w.work_counter;
+    P.chunk = (int32_t)chunk;
+    P.n_chunks = (int32_t)n_chunks;
+    P.n_items = n_chunks;
+    P.smem_stride = (plan.rem + 1) & ~(int64_t)1;
+    P.stat = stat_id;
+    P.center = w.jack->center;
+    P.direct_out = stat_out;
+    const size_t smem = kSmemHeader + (size_t)P.smem_stride * 8 * n_arrays;
+    rc = dispatch_k1(ms, P, smem, (int)std::min<int64_t>(sm_count(), P.n_items), s);
+    if (rc) return rc;
+  }
   double* jack_out = result_dev + kSmallResultDoubles;      // 8 more doubles behind the result block
   if (need_jack) {
-    rc = b200boot_jackknife(data, n_arrays, n_rows, stat_id, jack_out, ws, ws_bytes, stream);
+    switch (moment_set_of(stat_id)) {
+      case kMomSum: rc = jack_passes<kMomSum>(rows, n_rows, stat_id, w, jack_out, s); break;
+      case kMomSum2: rc = jack_passes<kMomSum2>(rows, n_rows, stat_id, w, jack_out, s); break;
+      case kMomAB: rc = jack_passes<kMomAB>(rows, n_rows, stat_id, w, jack_out, s); break;
+      case kMomXW: rc = jack_passes<kMomXW>(rows, n_rows, stat_id, w, jack_out, s); break;
+      default: rc = jack_passes<kMomPair5>(rows, n_rows, stat_id, w, jack_out, s); break;
+    }
     if (rc) return rc;
   }
   SmallTailParams P{};
@@ -496,7 +540,17 @@ int b200boot_ci_small(const double* const* data, int n_arrays, int64_t n_rows, i
   P.n_alphas = n_alphas;
   P.bca = bca ? 1 : 0;
   P.res = result_dev;
-  ci_tail_small_kernel<<<1, kSmallThreads, 0, s>>>(P);
+  P.n_pad = 0;
+  if (n_samples <= kSmallSortMax) {
+    P.n_pad = 2;
+    while (P.n_pad < n_samples) P.n_pad <<= 1;
+  }
+  static PerDeviceOnce tail_configured;
+  B2_CUDA(tail_configured.run([] {
+    return cudaFuncSetAttribute(ci_tail_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(kSmallSortMax * 8));
+  }));
+  ci_tail_small_kernel<<<1, kSmallThreads, (size_t)P.n_pad * 8, s>>>(P);
   B2_LAUNCH_CHECK();
   if (result_host)
     B2_CUDA(cudaMemcpyAsync(result_host, result_dev, kSmallResultDoubles * sizeof(double), cudaMemcpyDeviceToHost, s));

@@ -171,11 +171,27 @@ __device__ __forceinline__ void select_small_descend(const double* __restrict__ 
     for (int i = tid; i < a_cnt * 256; i += nthreads) (&s_hist[0][0])[i] = 0;
     __syncthreads();
     const int shift = 56 - 8 * pass;
-    for (int64_t r = tid; r < n; r += nthreads) {
-      const uint64_t k = key_of(col[r]);
+    // Statistic values crowd into a few bins (pass 0 sees little more than sign and exponent), and
+    // increments on one shared-memory address serialise.  Per warp and value: the lanes whose bin
+    // equals that of the first counted lane are added by that lane in one atomic (two ballots and
+    // a shuffle); only lanes with another bin issue their own.
+    const int64_t n_round = ((n + nthreads - 1) / nthreads) * nthreads;      // uniform trip count for the ballots
+    for (int64_t r = tid; r < n_round; r += nthreads) {
+      const bool live = r < n;
+      const uint64_t k = live ? key_of(col[r]) : 0ull;
       const unsigned int digit = (unsigned int)(k >> shift) & 0xFFu;
-      for (int a = 0; a < a_cnt; ++a)
-        if (pass == 0 || ((k ^ s_prefix[a]) >> (shift + 8)) == 0) atomicAdd(&s_hist[a][digit], 1u);
+      for (int a = 0; a < a_cnt; ++a) {
+        const bool hit = live && (pass == 0 || ((k ^ s_prefix[a]) >> (shift + 8)) == 0);
+        const unsigned int any_hit = __ballot_sync(0xffffffffu, hit);
+        if (any_hit == 0u) continue;                                           // warp-uniform
+        const int src = __ffs(any_hit) - 1;
+        const unsigned int d0 = __shfl_sync(0xffffffffu, digit, src);
+        const unsigned int same = __ballot_sync(0xffffffffu, hit && digit == d0);
+        if (lane == src)
+          atomicAdd(&s_hist[a][d0], (unsigned int)__popc(same));
+        else if (hit && digit != d0)
+          atomicAdd(&s_hist[a][digit], 1u);
+      }
     }
     __syncthreads();
     if (warp < a_cnt) {

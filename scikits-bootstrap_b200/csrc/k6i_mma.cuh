@@ -241,18 +241,33 @@ struct K6iParams {
   const int32_t* overflow;   // poisons the output when set
 };
 
-// copy rows [row0, row0 + n_rows_tile) x K bytes [k0, k0 + 128) of a row-major byte matrix into a
-// SWIZZLE_128B tile; rows at or beyond row_limit are zero-filled
-__device__ __forceinline__ void stage_chunk(unsigned char* dst, const unsigned char* __restrict__ src, int64_t row0,
-                                            int64_t row_limit, int n_rows_tile, int64_t k_pad, int64_t k0) {
-  for (int item = threadIdx.x; item < n_rows_tile * 8; item += kI8Threads) {
-    const int row = item >> 3, c16 = item & 7;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (row0 + row < row_limit)
-      v = __ldg(reinterpret_cast<const uint4*>(src + (row0 + row) * k_pad + k0 + c16 * 16));
-    *reinterpret_cast<uint4*>(dst + sw128_offset((uint32_t)row, (uint32_t)c16 * 16u)) = v;
+// One staged chunk in flight: rows [row0, row0 + ROWS) x K bytes [k0, k0 + 128) of a row-major byte
+// matrix, first loaded into registers (ROWS * 8 / 256 sixteen-byte pieces per thread), later
+// stored into a SWIZZLE_128B tile.  Splitting the two lets the loads of chunk j + 1 fly while
+// chunk j is stored, fenced and multiplied.  Rows at or beyond row_limit read as zero.
+template <int ROWS>
+struct ChunkRegs {
+  static constexpr int kPieces = ROWS * 8 / kI8Threads;
+  uint4 v[kPieces];
+  __device__ __forceinline__ void load(const unsigned char* __restrict__ src, int64_t row0, int64_t row_limit,
+                                       int64_t k_pad, int64_t k0) {
+#pragma unroll
+    for (int i = 0; i < kPieces; ++i) {
+      const int item = threadIdx.x + i * kI8Threads;
+      const int row = item >> 3, c16 = item & 7;
+      v[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (row0 + row < row_limit)
+        v[i] = __ldg(reinterpret_cast<const uint4*>(src + (row0 + row) * k_pad + k0 + c16 * 16));
+    }
   }
-}
+  __device__ __forceinline__ void store(unsigned char* dst) const {
+#pragma unroll
+    for (int i = 0; i < kPieces; ++i) {
+      const int item = threadIdx.x + i * kI8Threads;
+      *reinterpret_cast<uint4*>(dst + sw128_offset((uint32_t)(item >> 3), (uint32_t)(item & 7) * 16u)) = v[i];
+    }
+  }
+};
 
 template <bool A_RESIDENT>
 __global__ void __launch_bounds__(kI8Threads, 1) k6i_mma_kernel(const K6iParams P) {
@@ -268,6 +283,8 @@ __global__ void __launch_bounds__(kI8Threads, 1) k6i_mma_kernel(const K6iParams 
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t m0 = (int64_t)blockIdx.x * kI8M;
+  const unsigned char* digits = reinterpret_cast<const unsigned char*>(P.digits);
+  const int64_t b_limit = P.n_col_tiles * kI8N;
 
   if (tid == 0) {
     mbar_init(&bars[0], 1);
@@ -280,35 +297,51 @@ __global__ void __launch_bounds__(kI8Threads, 1) k6i_mma_kernel(const K6iParams 
   const uint32_t tmem_d = *s_tmem;
 
   if (A_RESIDENT) {
-    for (int j = 0; j < n_kchunks; ++j)
-      stage_chunk(s_a + (size_t)j * kI8AChunkBytes, P.counts, m0, P.m_total, kI8M, P.k_pad, (int64_t)j * kI8KChunk);
+    for (int j = 0; j < n_kchunks; ++j) {
+      ChunkRegs<kI8M> a;
+      a.load(P.counts, m0, P.m_total, P.k_pad, (int64_t)j * kI8KChunk);
+      a.store(s_a + (size_t)j * kI8AChunkBytes);
+    }
   }
 
-  uint32_t it = 0;               // staged chunks so far: buffer it & 1, use number it >> 1
-  for (int64_t tile = blockIdx.y; tile < P.n_col_tiles; tile += gridDim.y) {
-    const int64_t brow0 = tile * kI8N;
-    for (int j = 0; j < n_kchunks; ++j, ++it) {
-      const uint32_t buf = it & 1u;
-      if (it >= 2) mbar_wait(&bars[buf], ((it >> 1) - 1u) & 1u);     // the MMAs that read this buffer are done
-      if (!A_RESIDENT)
-        stage_chunk(s_a + (size_t)buf * kI8AChunkBytes, P.counts, m0, P.m_total, kI8M, P.k_pad, (int64_t)j * kI8KChunk);
-      stage_chunk(s_b + (size_t)buf * kI8BChunkBytes, reinterpret_cast<const unsigned char*>(P.digits), brow0,
-                  P.n_col_tiles * kI8N, kI8N, P.k_pad, (int64_t)j * kI8KChunk);
-      fence_proxy_async();           // generic-proxy stores -> visible to the tensor core (async proxy)
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(s_a + (size_t)(A_RESIDENT ? j : (int)buf) * kI8AChunkBytes);
-        const uint32_t b_addr = smem_u32(s_b + (size_t)buf * kI8BChunkBytes);
-#pragma unroll
-        for (int kk = 0; kk < kI8KChunk / 32; ++kk)
-          umma_i8(tmem_d, umma_desc_sw128(a_addr + kk * 32), umma_desc_sw128(b_addr + kk * 32), kI8InstrDesc,
-                  (j | kk) != 0 ? 1u : 0u);
-        umma_commit(&bars[buf]);     // arrives when every MMA issued so far has completed
-      }
+  // the CTA's sequence of (column tile, K chunk) steps; step `it` uses buffer it & 1
+  const int64_t n_my_tiles = blockIdx.y < P.n_col_tiles ? (P.n_col_tiles - blockIdx.y + gridDim.y - 1) / gridDim.y : 0;
+  const int64_t n_steps = n_my_tiles * n_kchunks;
+  auto step_tile = [&](int64_t st) { return (int64_t)blockIdx.y + (st / n_kchunks) * gridDim.y; };
+  ChunkRegs<kI8N> b_next;
+  ChunkRegs<kI8M> a_next;
+  if (n_steps > 0) {
+    b_next.load(digits, step_tile(0) * kI8N, b_limit, P.k_pad, 0);
+    if (!A_RESIDENT) a_next.load(P.counts, m0, P.m_total, P.k_pad, 0);
+  }
+  for (int64_t st = 0; st < n_steps; ++st) {
+    const uint32_t it = (uint32_t)st;
+    const uint32_t buf = it & 1u;
+    const int j = (int)(st % n_kchunks);
+    const int64_t tile = step_tile(st);
+    if (it >= 2) mbar_wait(&bars[buf], ((it >> 1) - 1u) & 1u);       // the MMAs that read this buffer are done
+    b_next.store(s_b + (size_t)buf * kI8BChunkBytes);
+    if (!A_RESIDENT) a_next.store(s_a + (size_t)buf * kI8AChunkBytes);
+    if (st + 1 < n_steps) {                                          // loads of the next step fly from here on
+      const int jn = (int)((st + 1) % n_kchunks);
+      b_next.load(digits, step_tile(st + 1) * kI8N, b_limit, P.k_pad, (int64_t)jn * kI8KChunk);
+      if (!A_RESIDENT) a_next.load(P.counts, m0, P.m_total, P.k_pad, (int64_t)jn * kI8KChunk);
     }
+    fence_proxy_async();           // generic-proxy stores -> visible to the tensor core (async proxy)
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(s_a + (size_t)(A_RESIDENT ? j : (int)buf) * kI8AChunkBytes);
+      const uint32_t b_addr = smem_u32(s_b + (size_t)buf * kI8BChunkBytes);
+#pragma unroll
+      for (int kk = 0; kk < kI8KChunk / 32; ++kk)
+        umma_i8(tmem_d, umma_desc_sw128(a_addr + kk * 32), umma_desc_sw128(b_addr + kk * 32), kI8InstrDesc,
+                (j | kk) != 0 ? 1u : 0u);
+      umma_commit(&bars[buf]);     // arrives when every MMA issued so far has completed
+    }
+    if (j + 1 < n_kchunks) continue;
     // accumulator complete: the last commit covers all MMAs of the tile
-    mbar_wait(&bars[(it - 1u) & 1u], ((it - 1u) >> 1) & 1u);
+    mbar_wait(&bars[buf], (it >> 1) & 1u);
     tc_fence_after();
     if (warp >= 4) {
       const int w4 = warp - 4;                          // TMEM lanes 32 w4 .. 32 w4 + 31
