@@ -231,6 +231,8 @@ int b200boot_fill_subsample(uint64_t seed, int64_t n_rows, int64_t size, int64_t
  * recomputes them on the host from [16] and [17..24] and selects again if they differ.
  * stat_out: float64[n_samples] device; result_dev: 40 doubles device; ws as for
  * b200boot_resample_stat with n_local = n_samples. */
+/* cudaStreamSynchronize on the caller's stream (the host wait that follows b200boot_ci_small) */
+int b200boot_stream_synchronize(void* stream);
 int b200boot_ci_small_supported(int stat_id, int n_arrays, int64_t n_rows, int64_t n_samples, int n_alphas);
 int b200boot_ci_small(const double* const* data, int n_arrays, int64_t n_rows, int stat_id, uint64_t seed,
                       int64_t n_samples, const double* alphas, int n_alphas, int bca, int need_jack,

@@ -157,14 +157,29 @@ class _PerThreadWorkspace:
 _ws = _PerThreadWorkspace()
 
 
+class _NoSwitch:
+    """The job already runs on the right device: nothing to enter or leave."""
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_SWITCH = _NoSwitch()
+
+
 def device_context(arrays):
     """Context manager selecting the CUDA device the job runs on: the device of the first
     CUDA tensor among the inputs, else the current device."""
     torch = require_cuda()
     for a in arrays:
         if isinstance(a, torch.Tensor) and a.device.type == "cuda":
+            if a.device.index == torch.cuda.current_device():
+                return _NO_SWITCH
             return torch.cuda.device(a.device)
-    return torch.cuda.device(torch.cuda.current_device())
+    return _NO_SWITCH
 
 
 def _ptr_array(tensors: Sequence) -> C.Array:
@@ -267,17 +282,25 @@ def ci_small(arrays: Sequence, stat_id: int, seed: int, n_samples: int, alphas: 
     L = _abi.lib()
     n_rows = arrays[0].numel()
     a = np.ascontiguousarray(alphas, dtype=np.float64).reshape(-1)
+    na = len(a)
     stat, res_dev, res_host = _small.get(n_samples)
-    ws, wsz = workspace_for(stat_id, n_rows, len(arrays), 1, n_samples, len(a))
+    ws, wsz = workspace_for(stat_id, n_rows, len(arrays), 1, n_samples, na)
     s = stream_ptr()
-    _abi.check(L.b200boot_ci_small(_ptr_array(arrays), len(arrays), n_rows, stat_id, seed, n_samples,
-                                   a.ctypes.data, len(a), int(bca), int(need_jack), stat.data_ptr(),
-                                   res_dev.data_ptr(), res_host.data_ptr(), ws, wsz, s))
-    torch.cuda.current_stream().synchronize()
+    rc = L.b200boot_ci_small(_ptr_array(arrays), len(arrays), n_rows, stat_id, seed, n_samples,
+                             a.ctypes.data, na, int(bca), int(need_jack), stat.data_ptr(),
+                             res_dev.data_ptr(), res_host.data_ptr(), ws, wsz, s)
+    if rc:
+        _abi.check(rc)
+    _sync_stream(s)
     TRAFFIC["d2h"] += 32 * 8
     r = res_host.numpy()
-    na = len(a)
     return (stat[:n_samples], r[:na].copy(), r[8:8 + na].astype(np.int64), int(r[16]), r[17:25].copy())
+
+
+def _sync_stream(stream: int) -> None:
+    """The one host wait of a small call: cudaStreamSynchronize through the library (a few
+    microseconds cheaper than building torch's stream object)."""
+    _abi.check(_abi.lib().b200boot_stream_synchronize(stream))
 
 
 def resample_stat_indexed(arrays: Sequence, stat_id: int, indices):

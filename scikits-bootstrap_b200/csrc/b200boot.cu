@@ -461,6 +461,11 @@ int b200boot_resample_stat_indexed(const double* const* data, int n_arrays, int6
   return 0;
 }
 
+int b200boot_stream_synchronize(void* stream) {
+  B2_CUDA(cudaStreamSynchronize(as_stream(stream)));
+  return 0;
+}
+
 int b200boot_ci_small_supported(int stat_id, int n_arrays, int64_t n_rows, int64_t n_samples, int n_alphas) {
   if (moment_set_of(stat_id) < 0 || stat_outputs(stat_id) != 1 || n_arrays != stat_arrays(stat_id)) return 0;
   if (n_rows < 1 || n_rows > kSmallMaxRows || make_plan(n_rows, n_arrays).n_tiles != 1) return 0;
@@ -540,17 +545,13 @@ int b200boot_ci_small(const double* const* data, int n_arrays, int64_t n_rows, i
   P.n_alphas = n_alphas;
   P.bca = bca ? 1 : 0;
   P.res = result_dev;
-  P.n_pad = 0;
-  if (n_samples <= kSmallSortMax) {
-    P.n_pad = 2;
-    while (P.n_pad < n_samples) P.n_pad <<= 1;
-  }
+  P.staged = n_samples <= kSmallStageMax ? 1 : 0;
   static PerDeviceOnce tail_configured;
   B2_CUDA(tail_configured.run([] {
     return cudaFuncSetAttribute(ci_tail_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(kSmallSortMax * 8));
+                                (int)(kSmallStageMax * 8));
   }));
-  ci_tail_small_kernel<<<1, kSmallThreads, (size_t)P.n_pad * 8, s>>>(P);
+  ci_tail_small_kernel<<<1, kSmallThreads, P.staged ? (size_t)n_samples * 8 : 0, s>>>(P);
   B2_LAUNCH_CHECK();
   if (result_host)
     B2_CUDA(cudaMemcpyAsync(result_host, result_dev, kSmallResultDoubles * sizeof(double), cudaMemcpyDeviceToHost, s));

@@ -155,35 +155,39 @@ struct SmallTailParams {
   double alphas[kSelMaxAlphas];
   int n_alphas;
   int bca;                // 1: BCa levels, 0: the alphas themselves
-  int n_pad;              // > 0: sort the keys in shared memory (power of two >= n_samples); 0: radix descent
+  int staged;             // the statistic vector is copied to shared memory first
   double* res;
 };
 
-// Dynamic shared memory holds the statistic vector as order-preserving keys, padded to a power
-// of two (P.n_pad > 0): the CTA sorts them with a bitonic network — about 7 us for 16 384 keys,
-// where the radix descent of longer vectors would spend its time on same-address histogram
-// atomics — and the order statistics are plain reads.  Longer vectors (P.n_pad == 0) keep the
-// descent over global memory.
-constexpr int64_t kSmallSortMax = 16384;      // 128 KB of keys
+// The tail runs in ONE CTA, i.e. on one SM: whatever it does to 1e4 values costs about a
+// microsecond per 1e5 thread-instructions.  Measured alternatives for the select of cfg1
+// (n = 1e4, two ranks; whole tail kernel, B200): byte-wise radix descent with ballot-aggregated
+// histogram atomics over the vector staged in shared memory — this version — 48 us; the same
+// with __match_any_sync aggregation 176 us; a bitonic sort of the keys in shared memory 165 us
+// (105 stages x 128 KB through a 128 B/clk pipe); a 64-step bit descent with register-resident
+// keys 36-48 us; quickselect with register-resident keys 100 us.  The select is a third of the
+// device time of a cfg1 call and a tenth of its wall time (the rest is host Python).
+constexpr int64_t kSmallStageMax = 24576;     // 192 KB of float64
 
 __global__ void __launch_bounds__(kSmallThreads) ci_tail_small_kernel(const SmallTailParams P) {
-  extern __shared__ uint64_t s_keys[];
+  extern __shared__ double s_stat[];
   __shared__ unsigned int s_hist[kSelMaxAlphas][256];
   __shared__ uint64_t s_prefix[kSelMaxAlphas];
   __shared__ long long s_krem[kSelMaxAlphas];
   __shared__ unsigned int s_less;
   const int tid = threadIdx.x;
   const int64_t n = P.n_samples;
-  const int n_pad = P.n_pad;
+  const double* stat = P.stat;
+  if (P.staged) {
+    for (int64_t r = tid; r < n; r += kSmallThreads) s_stat[r] = P.stat[r];
+    stat = s_stat;
+  }
   if (tid == 0) s_less = 0;
-  if (n_pad > 0)
-    for (int i = tid; i < n_pad; i += kSmallThreads) s_keys[i] = i < n ? key_of(P.stat[i]) : ~0ull;
   __syncthreads();
   if (P.bca) {
     const double ostat = P.jack[0];
     unsigned int local = 0;
-    for (int64_t r = tid; r < n; r += kSmallThreads)
-      local += (n_pad > 0 ? value_of(s_keys[r]) : P.stat[r]) < ostat ? 1u : 0u;   // strict '<', IEEE compare
+    for (int64_t r = tid; r < n; r += kSmallThreads) local += stat[r] < ostat ? 1u : 0u;   // strict '<'
     local = __reduce_add_sync(0xffffffffu, local);
     if ((tid & 31) == 0 && local) atomicAdd(&s_less, local);
   }
@@ -204,28 +208,8 @@ __global__ void __launch_bounds__(kSmallThreads) ci_tail_small_kernel(const Smal
   }
   if (tid == 0) P.res[16] = (double)s_less;
   if (tid < 8 && P.jack) P.res[17 + tid] = P.jack[tid];
-  if (n_pad > 0) {
-    // bitonic sort of the keys, ascending (NaN keys sort last, as numpy's sort does)
-    for (int k = 2; k <= n_pad; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        __syncthreads();
-        for (int t = tid; t < (n_pad >> 1); t += kSmallThreads) {
-          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));      // lower index of pair t
-          const int p = i | j;
-          const uint64_t x = s_keys[i], y = s_keys[p];
-          if ((x > y) == ((i & k) == 0)) {
-            s_keys[i] = y;
-            s_keys[p] = x;
-          }
-        }
-      }
-    }
-    __syncthreads();
-    if (tid < P.n_alphas) P.res[tid] = value_of(s_keys[s_krem[tid]]);
-    return;
-  }
   __syncthreads();
-  select_small_descend(P.stat, n, P.n_alphas, s_hist, s_prefix, s_krem);
+  select_small_descend(stat, n, P.n_alphas, s_hist, s_prefix, s_krem);
   if (tid < P.n_alphas) P.res[tid] = value_of(s_prefix[tid]);
 }
 
