@@ -213,6 +213,15 @@ int b200boot_fill_indices(uint64_t seed, int64_t n_rows, int n_arrays, int64_t r
 int b200boot_fill_moving_block(uint64_t seed, int64_t n_rows, int64_t block_length, int wrap,
                                int64_t resample_lo, int64_t resample_hi, int64_t* out, void* stream);
 
+/* K1b — the moving-block bootstrap as a fused resampling plan: the block starts that
+ * b200boot_fill_moving_block materialises, the L-contiguous gathers and the moment statistic in
+ * one kernel (no index array).  Arguments as b200boot_resample_stat plus block_length / wrap;
+ * ws as for b200boot_jackknife. */
+int b200boot_resample_stat_moving_block(const double* const* data, int n_arrays, int64_t n_rows, int stat_id,
+                                        uint64_t seed, int64_t block_length, int wrap, int64_t resample_lo,
+                                        int64_t resample_hi, double* stat_out, void* ws, size_t ws_bytes,
+                                        void* stream);
+
 /* K2c — subsamples without replacement (bootstrap.py:717-744): per sample the first
  * `size` entries of a uniform random permutation of 0..N-1 (argsort of 63-bit Philox
  * keys).  out: int64[sample_hi - sample_lo][size]; ws: 12 bytes per padded row entry. */

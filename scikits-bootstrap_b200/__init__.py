@@ -16,7 +16,7 @@ from ._registry import (REGISTRY_NAMES, DeviceCompare, DeviceStat, between, diff
                         weighted_average)
 from .bootstrap import (InstabilityWarning, __version__, bootstrap_indices,
                         bootstrap_indices_independent, bootstrap_indices_moving_block, ci,
-                        ci_indexed, jackknife_indices, pval, pval_indexed, subsample_indices)
+                        ci_indexed, ci_moving_block, jackknife_indices, pval, pval_indexed, subsample_indices)
 
 __all__ = (
     "ci", "pval", "bootstrap_indices", "bootstrap_indices_independent", "subsample_indices",
@@ -24,5 +24,5 @@ __all__ = (
     "ratio_of_means", "weighted_average", "pearson_r", "linear_fit", "fit_slope", "fit_intercept",
     "mean_axis0", "var_axis0", "std_axis0",
     "median_axis0", "quantile", "percentile", "quantile_axis0", "percentile_axis0", "diff_of_means", "diff_of", "ratio_of", "independent", "less_than", "less_equal", "greater_than", "greater_equal",
-    "between", "positive", "ci_indexed", "pval_indexed", "distributed", "REGISTRY_NAMES", "B200BootError",
+    "between", "positive", "ci_indexed", "ci_moving_block", "pval_indexed", "distributed", "REGISTRY_NAMES", "B200BootError",
 )

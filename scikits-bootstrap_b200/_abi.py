@@ -62,6 +62,7 @@ SIGNATURES = {
     "b200boot_jackknife_median_sorted": (_int, [_vp, _i64, _vp, _vp, _vp]),
     "b200boot_fill_indices": (_int, [_u64, _i64, _int, _i64, _i64, _vp, _vp, _sz, _vp]),
     "b200boot_fill_moving_block": (_int, [_u64, _i64, _i64, _int, _i64, _i64, _vp, _vp]),
+    "b200boot_resample_stat_moving_block": (_int, [_vp, _int, _i64, _int, _u64, _i64, _int, _i64, _i64, _vp, _vp, _sz, _vp]),
     "b200boot_fill_subsample": (_int, [_u64, _i64, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
     "b200boot_stream_synchronize": (_int, [_vp]),
     "b200boot_ci_small_supported": (_int, [_int, _int, _i64, _i64, _int]),

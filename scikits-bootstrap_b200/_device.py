@@ -237,6 +237,20 @@ def resample_stat(arrays: Sequence, stat_id: int, seed: int, lo: int, hi: int, o
     return out
 
 
+def resample_stat_moving_block(arrays: Sequence, stat_id: int, seed: int, block_length: int, wrap: bool,
+                               lo: int, hi: int):
+    """K1b: moment statistic of moving-block resamples -> float64[hi-lo] ([n_out][hi-lo])."""
+    torch = _torch()
+    n_rows = arrays[0].numel()
+    n_out = _abi.STAT_OUTPUTS.get(stat_id, 1)
+    out = torch.empty(hi - lo if n_out == 1 else (n_out, hi - lo), dtype=torch.float64, device=arrays[0].device)
+    ws, wsz = workspace_for(stat_id, n_rows, len(arrays), 1, 0, 1)
+    _abi.check(_abi.lib().b200boot_resample_stat_moving_block(_ptr_array(arrays), len(arrays), n_rows, stat_id, seed,
+                                                              int(block_length), int(bool(wrap)), lo, hi,
+                                                              out.data_ptr(), ws, wsz, stream_ptr()))
+    return out
+
+
 class _SmallCallBuffers:
     """Per (thread, device, stream): the statistic vector, the device result block and its
     pinned host mirror of b200boot_ci_small."""

@@ -106,9 +106,30 @@ def ncdf(x) -> np.ndarray:
     return out
 
 
+def _bca_levels_scalar(less: float, n_samples: int, accel: float, alphas: np.ndarray) -> np.ndarray:
+    """bca_levels for a scalar statistic and a handful of levels in Python floats: the same IEEE
+    operations in the same order as the array form (tests/test_host_probes.py compares them bit
+    for bit).  Raises ZeroDivisionError / OverflowError where numpy would produce inf or nan;
+    the caller then takes the array form."""
+    z0 = _nppf_scalar((1.0 * less) / n_samples)
+    out = np.empty(alphas.shape)
+    flat = out.reshape(-1)
+    for i, al in enumerate(alphas.reshape(-1).tolist()):
+        zs = z0 + _nppf_scalar(al)
+        flat[i] = 0.5 * (1 + math.erf((z0 + zs / (1 - accel * zs)) / _INV_SQRT2_DIV))
+    return out
+
+
 def bca_levels(less_counts: np.ndarray, n_samples: int, accel: np.ndarray,
                alphas: np.ndarray) -> np.ndarray:
     """Adjusted quantile levels: shape alphas.shape + stat shape."""
+    if np.ndim(less_counts) == 0 and np.ndim(accel) == 0 and alphas.size <= _SCALAR_LIMIT:
+        a, c = float(accel), float(less_counts)
+        if math.isfinite(a) and 0.0 < c < n_samples:          # finite z0 and acceleration: no inf / nan arithmetic
+            try:
+                return _bca_levels_scalar(c, n_samples, a, alphas)
+            except (ZeroDivisionError, OverflowError, ValueError):
+                pass
     z0 = nppf((1.0 * np.asarray(less_counts)) / n_samples)
     with np.errstate(invalid="ignore", divide="ignore"):
         zs = z0 + nppf(alphas).reshape(alphas.shape + (1,) * z0.ndim)

@@ -31,6 +31,7 @@ from ._registry import (DeviceCompare, DeviceStat, StatSpec, lookup, positive, r
 
 __all__ = (
     "ci",
+    "ci_moving_block",
     "pval",
     "bootstrap_indices",
     "bootstrap_indices_independent",
@@ -133,9 +134,10 @@ class _Run:
     column-major, float64[D][n_local]."""
 
     def __init__(self, spec: StatSpec, arrays: Sequence, multi, n_samples: int, key: int,
-                 indices=None):
+                 indices=None, blocks=None):
         self.spec, self.multi, self.n_samples, self.key = spec, multi, int(n_samples), key
         self.indices = indices       # parity mode: caller-supplied index sets (K1i)
+        self.blocks = blocks         # moving-block plan: (block_length, wrap), else None
         # pinned host tensors are copied on a side stream; `_ready` is recorded after the copies
         pairs = [_device.to_device_f64_async(a) for a in arrays]
         self.dev = [t for t, _ in pairs]
@@ -204,6 +206,12 @@ class _Run:
             ready = None
         if self.indices is not None:
             return self._resample_indexed()
+        if self.blocks is not None:
+            if spec.independent or spec.stat_id == _abi.STAT_MEDIAN or self.vector and spec.n_out == 1:
+                raise NotImplementedError("the moving-block plan covers moment statistics of 1-D (paired) arrays")
+            flat = [a.reshape(-1) for a in self.dev]
+            out = _device.resample_stat_moving_block(flat, spec.stat_id, self.key, self.blocks[0], self.blocks[1], lo, hi)
+            return out.reshape(self.n_cols, -1)
         if spec.independent:
             a, b = (p.resample() for p in self.parts())
             return _device.combine(spec.op, a, b)
@@ -247,7 +255,7 @@ class _Run:
         statistic vector float64[1][n] or None when the job does not qualify.  The ranks the
         device used are speculative; `select` compares them with the host's."""
         spec = self.spec
-        if (self.indices is not None or spec.independent or self.vector or spec.n_out != 1
+        if (self.indices is not None or self.blocks is not None or spec.independent or self.vector or spec.n_out != 1
                 or _dist.active() or spec.stat_id == _abi.STAT_MEDIAN or self.dev[0].dim() != 1):
             return None
         n_alphas = int(np.prod(alphas.shape)) if alphas.ndim else 1
@@ -476,6 +484,23 @@ def _ci_abc(arrays, statfunction, alphas, output, epsilon):
         return np.abs(abc - full)[np.newaxis].T
 
 
+def ci_moving_block(data, statfunction=None, alpha=0.05, n_samples=10000, block_length=3, wrap=False,
+                    method="pi", output="lowhigh", multi=None, return_dist=False, seed=None):
+    """`ci` with moving-block resamples (for dependent data): every resample is what
+    `bootstrap_indices_moving_block(data, n_samples, block_length, wrap, seed)` yields
+    (bootstrap.py:747-787), drawn, gathered and reduced in one fused kernel (K1b) without
+    materialising the indices.  The reference offers the index generator only; looping
+    `statfunction(data[idx])` over it gives the same statistics.  Moment statistics of 1-D data
+    or paired 1-D arrays; method 'pi' (default) or 'bca' (the jackknife acceleration treats the
+    rows as exchangeable, as the reference's `ci` would)."""
+    n_rows = _n_rows(data[0] if isinstance(data, tuple) else data)
+    block_length = int(block_length)
+    if block_length < 1 or (n_rows if wrap else n_rows - block_length) < 1:
+        raise ValueError("low >= high")          # numpy's error for an empty start range (:783)
+    return _ci_impl(data, statfunction, alpha, n_samples, method, output, 0.001, multi, return_dist,
+                    seed, False, None, (block_length, bool(wrap)))
+
+
 def ci_indexed(data, statfunction=None, indices=None, alpha=0.05, method="bca", output="lowhigh",
                multi=None, return_dist=False):
     """Parity mode of `ci`: identical pipeline, but the resamples are the caller's
@@ -487,7 +512,7 @@ def ci_indexed(data, statfunction=None, indices=None, alpha=0.05, method="bca", 
 
 
 def _ci_impl(data, statfunction, alpha, n_samples, method, output, epsilon, multi, return_dist,
-             seed, use_numba, indices):
+             seed, use_numba, indices, blocks=None):
     """Body shared by ci and ci_indexed (warnings use stacklevel=3: the user's frame)."""
     # alphas exactly as given, or (alpha/2, 1-alpha/2)             bootstrap.py:353-356
     if isinstance(alpha, Iterable):
@@ -540,13 +565,35 @@ def _ci_impl(data, statfunction, alpha, n_samples, method, output, epsilon, mult
     key = _seed_key(seed)
 
     with _device.device_context(arrays):
-        return _ci_on_device(spec, arrays, multi, n_samples, key, indices, alphas, method, output,
-                             return_dist)
+        res = _ci_on_device(spec, arrays, multi, n_samples, key, indices, alphas, method, output,
+                            return_dist, blocks)
+    # the reference's results carry the floating dtype of the data (np.mean of float32 is float32);
+    # the device computes in float64 and the result is rounded to that dtype once, at the end
+    low = _low_precision_dtype(arrays)
+    if low is None:
+        return res
+    if return_dist:
+        return res[0].astype(low), res[1].astype(low)
+    return res.astype(low)
 
 
-def _ci_on_device(spec, arrays, multi, n_samples, key, indices, alphas, method, output, return_dist):
+def _low_precision_dtype(arrays):
+    """np.float32 / np.float16 when every data array has that floating dtype, else None."""
+    kinds = set()
+    for a in arrays:
+        name = str(a.dtype).replace("torch.", "")
+        kinds.add(name)
+    if len(kinds) == 1:
+        name = kinds.pop()
+        if name in ("float32", "float16"):
+            return np.dtype(name)
+    return None
+
+
+def _ci_on_device(spec, arrays, multi, n_samples, key, indices, alphas, method, output, return_dist,
+                  blocks=None):
     """Device part of ci (warnings use stacklevel=4: the user's frame)."""
-    run = _Run(spec, arrays, multi, n_samples, key, indices)
+    run = _Run(spec, arrays, multi, n_samples, key, indices, blocks)
     stat = None
     if not return_dist:
         stat = run.small_call(alphas, method == "bca", method == "bca" or output == "errorbar")
@@ -658,6 +705,8 @@ def _pval_impl(data, statfunction, compfunction, n_samples, multi, seed, indices
     spec = require(statfunction)
     _check_spec(spec, arrays, multi)
     n_samples = int(n_samples)
+    if n_samples < 1:
+        raise ValueError("n_samples must be positive")
     key = _seed_key(seed)
     with _device.device_context(arrays):
         return _pval_on_device(spec, arrays, multi, n_samples, key, indices, compfunction)
@@ -683,6 +732,8 @@ def _n_rows(data) -> int:
 
 
 def _index_batches(key: int, n_rows: int, n_arrays: int, n_samples: int):
+    if n_rows < 1:
+        raise ValueError("low >= high")              # numpy's message for rng.integers(0, 0, ...)
     budget = 64 << 20
     step = max(1, min(n_samples, budget // (8 * n_rows)))
     for lo in range(0, n_samples, step):

@@ -635,6 +635,44 @@ int b200boot_fill_moving_block(uint64_t seed, int64_t n_rows, int64_t block_leng
   return 0;
 }
 
+int b200boot_resample_stat_moving_block(const double* const* data, int n_arrays, int64_t n_rows, int stat_id,
+                                        uint64_t seed, int64_t block_length, int wrap, int64_t resample_lo,
+                                        int64_t resample_hi, double* stat_out, void* ws, size_t ws_bytes,
+                                        void* stream) {
+  int rc = check_moment_stat(stat_id, n_arrays, n_rows);
+  if (rc) return rc;
+  const int64_t n_local = resample_hi - resample_lo;
+  if (n_local < 0 || resample_lo < 0 || block_length < 1) return fail(B200BOOT_EINVAL, "bad arguments");
+  const int64_t start_bound = wrap ? n_rows : n_rows - block_length;
+  if (start_bound < 1) return fail(B200BOOT_EINVAL, "low >= high: no admissible block start");
+  if (n_local == 0) return 0;
+  if (!data || !stat_out) return fail(B200BOOT_EINVAL, "null pointer");
+  cudaStream_t s = as_stream(stream);
+  const Plan plan = make_plan(n_rows, n_arrays);
+  if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
+    return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
+  Carver cv(ws, ws_bytes);
+  ResampleWs w = carve_resample(cv, plan, stat_id, 0);
+  if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+  const double* rows[2];
+  rc = prepare_rows(data, n_arrays, n_rows, stat_id, w, rows, s);
+  if (rc) return rc;
+  const int grid = blocks_for(n_local * 32, 256, (int64_t)sm_count() * 8);
+#define B2_K1B(MS)                                                                                              \
+  k1b_moving_block_kernel<MS><<<grid, 256, 0, s>>>(rows[0], rows[1], n_rows, block_length, start_bound, wrap ? 1 : 0, \
+                                                   seed, resample_lo, n_local, stat_id, w.jack->center, stat_out)
+  switch (moment_set_of(stat_id)) {
+    case kMomSum: B2_K1B(kMomSum); break;
+    case kMomSum2: B2_K1B(kMomSum2); break;
+    case kMomAB: B2_K1B(kMomAB); break;
+    case kMomXW: B2_K1B(kMomXW); break;
+    default: B2_K1B(kMomPair5); break;
+  }
+#undef B2_K1B
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
 int b200boot_fill_subsample(uint64_t seed, int64_t n_rows, int64_t size, int64_t sample_lo,
                             int64_t sample_hi, int64_t* out, void* ws, size_t ws_bytes, void* stream) {
   const int64_t n_local = sample_hi - sample_lo;

@@ -731,3 +731,75 @@ __global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ 
 }
 
 }  // namespace b200boot
+
+namespace b200boot {
+
+// ------------------------------------------------------------------ K1b -------
+// Moving-block bootstrap as a resampling plan (bootstrap.py:747-787 fused with the gather and
+// the statistic of bootstrap.py:429-432): per resample ceil(N / L) block starts — the very
+// draws k2_moving_block_kernel materialises (kPurposeBlock stream, Lemire) — and the rows
+// start .. start + L - 1 of every block, cut to N positions, modulo N when wrapping.  The
+// gathers are L-contiguous, so the rows come coalesced from L2 / HBM; no index array exists.
+// One warp per resample: blocks of at least 32 rows are walked by the lanes together, shorter
+// blocks one per lane.  Per-resample sums never cross warps, so the bits do not depend on grid
+// or shard.
+template <int MS>
+__global__ void __launch_bounds__(256) k1b_moving_block_kernel(const double* __restrict__ d0,
+                                                               const double* __restrict__ d1, int64_t n_rows,
+                                                               int64_t block_length, int64_t start_bound, int wrap,
+                                                               uint64_t seed, int64_t resample_lo, int64_t n_local,
+                                                               int stat, const double* __restrict__ center,
+                                                               double* __restrict__ out) {
+  constexpr int NA = MomTraits<MS>::kArrays;
+  constexpr int NM = MomTraits<MS>::kMoments;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_blocks = (n_rows + block_length - 1) / block_length;
+  const uint32_t n_q = (uint32_t)((n_blocks + 3) / 4);
+  const uint32_t thresh = lemire_threshold((uint32_t)start_bound);
+  for (int64_t rl = warp_global; rl < n_local; rl += n_warps) {
+    const Stream st = make_stream(seed, resample_lo + rl, 0u, kPurposeBlock);
+    double acc[NM];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) acc[m] = 0.0;
+    auto add_row = [&](int64_t idx) {
+      double v[NA], c[NM];
+      v[0] = d0[idx];
+      if (NA == 2) v[NA - 1] = d1[idx];
+      contribution<MS>(v, c);
+#pragma unroll
+      for (int m = 0; m < NM; ++m) acc[m] += c[m];
+    };
+    if (block_length >= 32) {
+      // every lane derives the same four starts of a Philox block; the lanes share each block's rows
+      for (uint32_t q = 0; q < n_q; ++q)
+        lemire_block<true>(st, q, (uint32_t)start_bound, thresh, n_blocks, [&](int, int64_t b, uint32_t start) {
+          const int64_t len = min(block_length, n_rows - b * block_length);
+          for (int64_t k = lane; k < len; k += 32) {
+            const int64_t v = (int64_t)start + k;
+            add_row(wrap ? v % n_rows : v);
+          }
+        });
+    } else {
+      for (uint32_t q = lane; q < n_q; q += 32)
+        lemire_block<true>(st, q, (uint32_t)start_bound, thresh, n_blocks, [&](int, int64_t b, uint32_t start) {
+          const int64_t len = min(block_length, n_rows - b * block_length);
+          for (int64_t k = 0; k < len; ++k) {
+            const int64_t v = (int64_t)start + k;
+            add_row(wrap ? v % n_rows : v);
+          }
+        });
+    }
+    double m[kMaxMoments];
+#pragma unroll
+    for (int k = 0; k < NM; ++k) m[k] = warp_sum(acc[k]);
+    if (lane == 0) {
+      const int n_out = stat_outputs(stat);
+      for (int o = 0; o < n_out; ++o)
+        out[(int64_t)o * n_local + rl] = finish_stat(stat_component(stat, o), m, (double)n_rows, center);
+    }
+  }
+}
+
+}  // namespace b200boot

@@ -449,7 +449,7 @@ def test_fuzz_shapes_against_oracle():
             if name == "median":
                 assert_array_equal(dist, want, err_msg=f"{name} n={n} m={m}")
             else:
-                assert_allclose(dist, want, rtol=1e-11, atol=1e-13, err_msg=f"{name} n={n} m={m}")
+                assert_allclose(dist, want, rtol=RTOL, atol=1e-13, err_msg=f"{name} n={n} m={m}")
 
 
 def test_fuzz_newer_statistics_against_numpy():
@@ -523,7 +523,7 @@ def test_fuzz_column_kernels_against_oracle():
             if name == "median_axis0":
                 assert_array_equal(dist, want, err_msg=msg)
             else:
-                assert_allclose(dist, want, rtol=1e-11, atol=1e-13, err_msg=msg)
+                assert_allclose(dist, want, rtol=RTOL, atol=1e-13, err_msg=msg)
             # jackknife pieces per column (K3c / K3m) against the closed forms
             jk = {"mean_axis0": orc.jack_mean, "median_axis0": orc.jack_median,
                   "std_axis0": lambda x: orc.jack_var(x, True)}[name]
@@ -533,7 +533,7 @@ def test_fuzz_column_kernels_against_oracle():
             for d in range(0, dcols, max(1, dcols // 3)):
                 j = jk(data[:, d])
                 assert_allclose(jd[d, 0], g(data)[d], rtol=1e-12, atol=1e-14, err_msg=msg)
-                assert_allclose(jd[d, 1], j.mean(), rtol=1e-11, atol=1e-13, err_msg=msg)
+                assert_allclose(jd[d, 1], j.mean(), rtol=RTOL, atol=1e-13, err_msg=msg)
                 d2 = np.sum((j.mean() - j) ** 2)
                 if d2 > 1e-18:
                     assert_allclose(jd[d, 2], d2, rtol=1e-6, err_msg=msg)
@@ -799,6 +799,31 @@ def test_edge_shapes():
         boot.ci(np.zeros(0), np.mean)
 
 
+def test_float32_data_give_float32_results_like_the_reference():
+    """np.mean / np.std of float32 resamples are float32 in the reference: results
+    carry the data's floating dtype and agree with the float64 run to float32 rounding."""
+    rng = np.random.default_rng(8)
+    x64 = rng.gamma(2, 1, 3000)
+    x32 = x64.astype(np.float32)
+    for f in (np.mean, np.std, np.median):
+        lo32 = boot.ci(x32, f, n_samples=2000, seed=3)
+        lo64 = boot.ci(x32.astype(np.float64), f, n_samples=2000, seed=3)
+        assert lo32.dtype == np.float32 and lo64.dtype == np.float64
+        assert_array_equal(lo32, lo64.astype(np.float32))
+        out, dist = boot.ci(x32, f, n_samples=500, seed=3, method="pi", return_dist=True)
+        assert out.dtype == np.float32 and dist.dtype == np.float32
+    # the oracle (the reference's arithmetic) on the same float32 data and the device's own indices
+    idx = np.array(list(boot.bootstrap_indices(x32, 300, seed=4)))
+    want = orc.ci_from_indices((x32,), np.mean, idx, (0.025, 0.975), 300, "pi")
+    got = boot.ci(x32, np.mean, n_samples=300, seed=4, method="pi")
+    assert want.dtype == np.float32
+    assert_allclose(got, want, rtol=2e-6)
+    assert boot.ci(np.arange(50), np.mean, n_samples=200, seed=1).dtype == np.float64       # ints -> float64
+    import torch
+    assert boot.ci(torch.from_numpy(x32).cuda(), np.mean, n_samples=200, seed=1).dtype == np.float32
+    assert boot.ci((x32, x64), boot.ratio_of_means, n_samples=200, seed=1).dtype == np.float64
+
+
 def test_input_forms_agree():
     import pandas as pd
     x = DATA20
@@ -932,7 +957,7 @@ def test_independent_difference_of_statistics(name, stat, na, nb):
         a = np.sort(a)
     want_dist = np.sort([f(a[i], b[j]) for i, j in idx])
     out, dist = boot.ci((a, b), dstat, n_samples=n, multi="independent", seed=13, method="pi", return_dist=True)
-    assert_allclose(dist, want_dist, rtol=1e-11, atol=1e-13)
+    assert_allclose(dist, want_dist, rtol=RTOL, atol=1e-13)
     # closed-form per-array leave-one-out values, pooled array-major as the reference does
     jack1 = {"mean": orc.jack_mean, "median": orc.jack_median, "std": lambda x: orc.jack_var(x, True),
              "var": orc.jack_var, "sum": lambda x: np.sum(x) - x, "q80": lambda x: orc.jack_quantile(x, 0.8)}[name]
@@ -941,7 +966,7 @@ def test_independent_difference_of_statistics(name, stat, na, nb):
         assert_allclose(jstat, orc.jackknife_stats_independent_loop((a, b), f), rtol=1e-9, atol=1e-12)
     want = orc.ci_from_indices((a, b), f, idx, (0.025, 0.975), n, "bca", multi="independent", jstat=jstat)
     got = boot.ci((a, b), dstat, n_samples=n, multi="independent", seed=13, method="bca")
-    assert_allclose(got, want, rtol=1e-11, atol=1e-13)
+    assert_allclose(got, want, rtol=RTOL, atol=1e-13)
     p = boot.pval((a, b), dstat, boot.less_than(0.0), n_samples=n, multi="independent", seed=13)
     assert p == np.mean(dist < 0.0)
 
@@ -1025,6 +1050,40 @@ def test_moving_block_indices(n, L, wrap):
         assert body[:, :, 0].max() < n - L                # numpy's half-open start range
     with pytest.raises(ValueError):
         list(boot.bootstrap_indices_moving_block(np.zeros(3), 2, block_length=3))
+
+
+@pytest.mark.parametrize("n,L,wrap", [(1000, 7, False), (1000, 7, True), (5000, 64, False), (40001, 50, True),
+                                      (300, 1, False), (64, 100, True)])
+def test_moving_block_plan_fused_with_the_statistic(n, L, wrap):
+    """K1b: block starts, L-contiguous gathers and the moment statistic in one kernel; the
+    resamples are exactly those of bootstrap_indices_moving_block (bootstrap.py:747-787), so the
+    statistics equal the oracle's over those indices."""
+    rng = np.random.default_rng(n + L)
+    x = np.cumsum(rng.standard_normal(n)) * 0.1 + 2.0                 # dependent data
+    y = 0.5 * x + rng.standard_normal(n)
+    m = 200
+    idx = np.array(list(boot.bootstrap_indices_moving_block(x, m, block_length=L, wrap=wrap, seed=5)))
+    for stat_name, tdata in (("mean", (x,)), ("std", (x,)), ("pearson_r", (x, y)), ("ratio_of_means", (x, y))):
+        data = tdata if len(tdata) > 1 else tdata[0]
+        want = np.sort(orc.stat_over_indices(tdata, STATS[stat_name], idx))
+        out, dist = boot.ci_moving_block(data, DEVICE_STATS[stat_name], n_samples=m, block_length=L, wrap=wrap,
+                                         seed=5, return_dist=True, multi="paired" if len(tdata) > 1 else None)
+        assert_allclose(dist, want, rtol=RTOL, atol=1e-14)
+        ref = orc.ci_from_indices(tdata, STATS[stat_name], idx, (0.025, 0.975), m, "pi")
+        assert_allclose(out, ref, rtol=RTOL, atol=1e-14)
+    # shards reproduce the whole: resample r depends on (seed, r) only
+    flat = [dev(x)]
+    whole = _device.resample_stat_moving_block(flat, _abi.STAT_MEAN, 5, L, wrap, 0, m).cpu().numpy()
+    parts = np.concatenate([_device.resample_stat_moving_block(flat, _abi.STAT_MEAN, 5, L, wrap, a, b).cpu().numpy()
+                            for a, b in ((0, 33), (33, 34), (34, m))])
+    assert_array_equal(whole, parts)
+    with pytest.raises(NotImplementedError):
+        boot.ci_moving_block(x, np.median, n_samples=10, block_length=L, wrap=wrap)
+
+
+def test_moving_block_plan_rejects_empty_start_range():
+    with pytest.raises(ValueError, match="low >= high"):
+        boot.ci_moving_block(np.arange(5.0), np.mean, block_length=5, wrap=False)
 
 
 def test_moving_block_starts_are_uniform():
@@ -1315,10 +1374,10 @@ def test_count_matrix_gemm_columns(n, d):
     for stat_id, f in ((_abi.STAT_MEAN, np.mean), (_abi.STAT_SUM, np.sum), (_abi.STAT_VAR, np.var), (_abi.STAT_STD, np.std)):
         got = _device.resample_stat_gemm(xd, stat_id, 21, 0, m).cpu().numpy()          # [D][m]
         want = np.stack([f(data[i], axis=0) for i in idx], axis=1)
-        assert_allclose(got, want, rtol=1e-11, atol=1e-13)
+        assert_allclose(got, want, rtol=RTOL, atol=1e-13)
         if _device.columns_block_width(stat_id, n) > 0:
             gather = _device.resample_stat_columns(xd, stat_id, 21, 0, m).cpu().numpy()
-            assert_allclose(got, gather, rtol=1e-11, atol=1e-13)
+            assert_allclose(got, gather, rtol=RTOL, atol=1e-13)
     L = _abi.lib()
     assert L.b200boot_gemm_supported(_abi.STAT_MEAN, 28672) == 1 and L.b200boot_gemm_supported(_abi.STAT_MEAN, 28673) == 0
     assert _device.gemm_supported(_abi.STAT_MEAN, 10**6) and not _device.gemm_supported(_abi.STAT_MEDIAN, 100)
@@ -1338,14 +1397,14 @@ def test_count_matrix_gemm_long_columns():
     for stat_id, f in ((_abi.STAT_MEAN, np.mean), (_abi.STAT_STD, np.std)):
         got = _device.resample_stat_gemm(xd, stat_id, 8, 0, m).cpu().numpy()
         want = np.stack([f(data[i], axis=0) for i in idx], axis=1)
-        assert_allclose(got, want, rtol=1e-11, atol=1e-13)
+        assert_allclose(got, want, rtol=RTOL, atol=1e-13)
     import os
     os.environ["B200BOOT_GEMM_COUNT_BYTES"] = str(8 * n * 7)          # chunks of 7 resamples
     try:
         chunked = _device.resample_stat_gemm(xd, _abi.STAT_MEAN, 8, 0, m).cpu().numpy()
     finally:
         del os.environ["B200BOOT_GEMM_COUNT_BYTES"]
-    assert_allclose(chunked, np.stack([data[i].mean(axis=0) for i in idx], axis=1), rtol=1e-11, atol=1e-13)
+    assert_allclose(chunked, np.stack([data[i].mean(axis=0) for i in idx], axis=1), rtol=RTOL, atol=1e-13)
     out = boot.ci(data, boot.mean_axis0, n_samples=100, seed=5, method="pi")
     one = boot.ci(data[:, 7], np.mean, n_samples=100, seed=5, method="pi")
     assert_allclose(out[:, 7], one, rtol=1e-12, atol=1e-15)

@@ -505,3 +505,25 @@ def _device_mod():
 def _registry_mod():
     from scikits_bootstrap_b200 import _registry
     return _registry
+
+
+def test_bca_levels_scalar_path_is_bit_equal_to_the_array_path():
+    """The per-call fast path of the BCa levels (Python floats) against the array form."""
+    from scikits_bootstrap_b200 import _interval
+    rng = np.random.default_rng(7)
+    for _ in range(400):
+        n = int(rng.integers(50, 200000))
+        less = np.int64(rng.integers(1, n))
+        accel = np.float64(rng.normal(0, 0.05))
+        alphas = np.sort(rng.random(int(rng.integers(1, 6))))
+        fast = _interval.bca_levels(less, n, accel, alphas)
+        z0 = _interval.nppf((1.0 * np.asarray(less)) / n)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            zs = z0 + _interval.nppf(alphas).reshape(alphas.shape + (1,) * z0.ndim)
+            slow = _interval.ncdf(z0 + zs / (1 - accel * zs))
+        assert fast.shape == slow.shape
+        assert (fast.view(np.uint64) == slow.view(np.uint64)).all()
+    # degenerate inputs take the array form (inf / nan arithmetic as numpy does it)
+    out = _interval.bca_levels(np.int64(0), 100, np.float64(0.01), np.array([0.025, 0.975]))
+    assert np.isnan(out).all() or ((out == 0) | (out == 1) | np.isnan(out)).all()
+    assert np.isnan(_interval.bca_levels(np.int64(10), 100, np.float64("nan"), np.array([0.5]))).all()
