@@ -1228,12 +1228,17 @@ int b200boot_resample_stat_columns_gemm(const double* data, int64_t n_rows, int6
     P.out_ld = n_local;
     P.out_i32 = nullptr;
     P.overflow = flags;
+    // the mean's division by N happens in the epilogue (the finisher's m[0] / cnt on the same
+    // rounded sum: same bits), so mean and sum need no finisher pass over the output
+    P.out_divisor = stat_id == kStatMean ? (double)n_rows : 1.0;
     int rc = launch_k6i(P, s);
     if (rc) return rc;
     k6i_fixup_kernel<<<(unsigned)std::min<int64_t>((n_local * 32 + 255) / 256, (int64_t)sm_count() * 8), 256, 0, s>>>(
-        data, n_rows, n_cols, ld, c, pass, bad_col, flags + 1, seed, resample_lo, n_local, indices, dst);
+        data, n_rows, n_cols, ld, c, pass, bad_col, flags + 1, seed, resample_lo, n_local, indices, P.out_divisor,
+        dst);
     B2_LAUNCH_CHECK();
   }
+  if (stat_id == kStatSum || stat_id == kStatMean) return 0;      // finished in the contraction's epilogue
   const int64_t total = n_cols * n_local;
   k6_finish_kernel<<<blocks_for(total, 256, 148 * 16), 256, 0, s>>>(stat_id, (double)n_rows, total, stat_out,
                                                                    two ? second : nullptr);
@@ -1258,6 +1263,7 @@ int b200boot_debug_i8_gemm(const uint8_t* a, const int8_t* b, int32_t* c, int64_
   P.out_ld = 0;
   P.out_i32 = c;
   P.overflow = nullptr;
+  P.out_divisor = 1.0;
   return launch_k6i(P, as_stream(stream));
 }
 

@@ -239,6 +239,7 @@ struct K6iParams {
   int64_t out_ld;
   int32_t* out_i32;          // test hook: raw accumulators [m_total][n_col_tiles * 256], or null
   const int32_t* overflow;   // poisons the output when set
+  double out_divisor;        // N for the mean (the finisher's division, same bits), else 1
 };
 
 // One staged chunk in flight: rows [row0, row0 + ROWS) x K bytes [k0, k0 + 128) of a row-major byte
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) k6i_mma_kernel(const K6iParams 
           }
           if (r < P.m_total && d < P.n_cols && P.out != nullptr)
             P.out[d * P.out_ld + r] =
-                poisoned ? nan("") : fma((double)hi, 268435456.0, (double)lo) * P.scale[d];
+                poisoned ? nan("") : (fma((double)hi, 268435456.0, (double)lo) * P.scale[d]) / P.out_divisor;
         }
       }
     }
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(256) k6i_fixup_kernel(const double* __restrict
                                                         const int32_t* __restrict__ any_bad, uint64_t seed,
                                                         int64_t resample_lo, int64_t n_local,
                                                         const int64_t* __restrict__ indices,
-                                                        double* __restrict__ out) {
+                                                        double out_divisor, double* __restrict__ out) {
   if (*any_bad == 0) return;
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(256) k6i_fixup_kernel(const double* __restrict
           lemire_block<true>(st, q, (uint32_t)n_rows, thresh, n_rows, [&](int, int64_t, uint32_t idx) { add((int64_t)idx); });
       }
       acc = warp_sum(acc);
-      if (lane == 0) out[d * n_local + rl] = acc;
+      if (lane == 0) out[d * n_local + rl] = acc / out_divisor;
     }
   }
 }
