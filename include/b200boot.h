@@ -228,18 +228,22 @@ int b200boot_resample_stat_moving_block(const double* const* data, int n_arrays,
 int b200boot_fill_subsample(uint64_t seed, int64_t n_rows, int64_t size, int64_t sample_lo,
                             int64_t sample_hi, int64_t* out, void* ws, size_t ws_bytes, void* stream);
 
-/* Small calls (one resident cell, a scalar moment statistic, n_samples <= 32768, <= 8 levels):
- * the whole ci() of bootstrap.py:222-504 enqueued by ONE call — K1 (finishing the statistic
- * itself), the single-CTA jackknife, and a single-CTA tail that counts stat < ostat
- * (bootstrap.py:583), forms the BCa levels and ranks (bootstrap.py:609-629, :456) and selects
- * the order statistics (bootstrap.py:485-490) — followed by one device-to-host copy of the
- * 32-double result block into `result_host` (pinned; may be NULL):
+/* Small calls (rows x arrays <= 28672 in one resident cell, a scalar moment statistic,
+ * n_samples <= 32768, <= 8 levels): the whole ci() of bootstrap.py:222-504 as ONE kernel launch.
+ * Every CTA keeps the rows in shared memory; the last CTA of the grid runs the closed-form
+ * jackknife (bootstrap.py:595-615) while the others resample (the single-cell Lemire stream of
+ * b200boot_resample_stat, bit-equal statistics); the CTA that finishes last counts stat < ostat
+ * (bootstrap.py:583), forms the BCa levels and ranks (bootstrap.py:609-629, :456) and selects the
+ * order statistics exactly (bootstrap.py:485-490; a monotone bucket map + exact ranking inside the
+ * bucket, radix descent for degenerate vectors).  The 32-double result block
  *   [0..7] order statistics   [8..15] the ranks used   [16] #{stat < ostat}   [17..24] jackknife
- *   summary as b200boot_jackknife writes it.
+ *   summary as b200boot_jackknife writes it
+ * is stored to result_dev and, when `result_host` is pinned memory the device can address, straight
+ * into it by the kernel (otherwise by one device-to-host copy; NULL: not at all).
  * The ranks are speculative (device evaluation of the reference's nppf / ncdf): the caller
  * recomputes them on the host from [16] and [17..24] and selects again if they differ.
- * stat_out: float64[n_samples] device; result_dev: 40 doubles device; ws as for
- * b200boot_resample_stat with n_local = n_samples. */
+ * stat_out: float64[n_samples] device; result_dev: 48 doubles device, ZERO before the first call
+ * (a ticket counter lives behind the results and is left at zero by every call); ws: 4096 bytes. */
 /* cudaStreamSynchronize on the caller's stream (the host wait that follows b200boot_ci_small) */
 int b200boot_stream_synchronize(void* stream);
 int b200boot_ci_small_supported(int stat_id, int n_arrays, int64_t n_rows, int64_t n_samples, int n_alphas);
@@ -247,6 +251,14 @@ int b200boot_ci_small(const double* const* data, int n_arrays, int64_t n_rows, i
                       int64_t n_samples, const double* alphas, int n_alphas, int bca, int need_jack,
                       double* stat_out, double* result_dev, double* result_host, void* ws, size_t ws_bytes,
                       void* stream);
+/* The same from HOST rows (float64, contiguous): each array is copied into the caller's pinned
+ * `staging[a]`, from there to the caller's device rows `data_dev[a]` (both >= n_rows doubles) on
+ * `stream`, the kernel follows, and the call returns after cudaStreamSynchronize: result_host
+ * (required) holds the result block. */
+int b200boot_ci_small_host(const double* const* host_data, double* const* staging, double* const* data_dev,
+                           int n_arrays, int64_t n_rows, int stat_id, uint64_t seed, int64_t n_samples,
+                           const double* alphas, int n_alphas, int bca, int need_jack, double* stat_out,
+                           double* result_dev, double* result_host, void* ws, size_t ws_bytes, void* stream);
 
 /* multi='independent' with a two-sample statistic f(s_a(a), s_b(b)) (bootstrap.py:438-444,
  * 601-607, 708-714).  f is one of b200boot_op. */

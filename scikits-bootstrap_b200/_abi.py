@@ -67,6 +67,8 @@ SIGNATURES = {
     "b200boot_stream_synchronize": (_int, [_vp]),
     "b200boot_ci_small_supported": (_int, [_int, _int, _i64, _i64, _int]),
     "b200boot_ci_small": (_int, [_vp, _int, _i64, _int, _u64, _i64, _vp, _int, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200boot_ci_small_host": (_int, [_vp, _vp, _vp, _int, _i64, _int, _u64, _i64, _vp, _int, _int, _int, _vp, _vp, _vp,
+                                      _vp, _sz, _vp]),
     "b200boot_tile_counts": (_int, [_u64, _i64, _int, _i64, _i64, _vp, _vp, _vp]),
     "b200boot_tile_counts_packed_ws_bytes": (_sz, [_i64, _int, _i64]),
     "b200boot_tile_counts_packed": (_int, [_u64, _i64, _int, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),

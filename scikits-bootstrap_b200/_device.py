@@ -252,8 +252,9 @@ def resample_stat_moving_block(arrays: Sequence, stat_id: int, seed: int, block_
 
 
 class _SmallCallBuffers:
-    """Per (thread, device, stream): the statistic vector, the device result block and its
-    pinned host mirror of b200boot_ci_small."""
+    """Per (thread, device, stream): the statistic vector, the device result block (whose ticket
+    counter behind the results starts at zero), its pinned host mirror, and — for host inputs —
+    a pinned staging block and the device rows of b200boot_ci_small_host."""
 
     def __init__(self):
         import threading
@@ -266,16 +267,35 @@ class _SmallCallBuffers:
             table = self._local.table = {}
         key = (torch.cuda.current_device(), stream_ptr())
         ent = table.get(key)
-        if ent is None or ent[0].numel() < n_samples:
+        if ent is None or ent.stat.numel() < n_samples:
             if len(table) >= 8:
                 table.clear()
-            ent = (torch.empty(max(n_samples, 4096), dtype=torch.float64, device="cuda"),
-                   torch.empty(40, dtype=torch.float64, device="cuda"),
-                   torch.empty(32, dtype=torch.float64).pin_memory())
-            table[key] = ent
+            ent = table[key] = _SmallEntry(torch, max(n_samples, 4096))
         return ent
 
 
+class _SmallEntry:
+    __slots__ = ("stat", "res_dev", "res_host", "res_np", "staging", "rows", "stat_ptr", "res_dev_ptr",
+                 "res_host_ptr", "staging_ptrs", "rows_ptrs", "alphas", "alphas_ptr", "host_ptrs")
+
+    def __init__(self, torch, n_stat: int):
+        self.stat = torch.empty(n_stat, dtype=torch.float64, device="cuda")
+        self.res_dev = torch.zeros(48, dtype=torch.float64, device="cuda")
+        self.res_host = torch.zeros(32, dtype=torch.float64).pin_memory()
+        self.res_np = self.res_host.numpy()
+        self.staging = torch.empty((2, SMALL_MAX_CELL), dtype=torch.float64).pin_memory()
+        self.rows = torch.empty((2, SMALL_MAX_CELL), dtype=torch.float64, device="cuda")
+        self.stat_ptr = self.stat.data_ptr()
+        self.res_dev_ptr = self.res_dev.data_ptr()
+        self.res_host_ptr = self.res_host.data_ptr()
+        self.staging_ptrs = (C.c_void_p * 2)(self.staging[0].data_ptr(), self.staging[1].data_ptr())
+        self.rows_ptrs = (C.c_void_p * 2)(self.rows[0].data_ptr(), self.rows[1].data_ptr())
+        self.host_ptrs = (C.c_void_p * 2)()
+        self.alphas = (C.c_double * 8)()
+        self.alphas_ptr = C.addressof(self.alphas)
+
+
+SMALL_MAX_CELL = 28672          # rows x arrays of the fused small call (kFusedMaxCellDoubles)
 _small = _SmallCallBuffers()
 
 
@@ -290,25 +310,41 @@ def ci_small_supported(stat_id: int, n_arrays: int, n_rows: int, n_samples: int,
 
 def ci_small(arrays: Sequence, stat_id: int, seed: int, n_samples: int, alphas: np.ndarray, bca: bool,
              need_jack: bool):
-    """One library call for a whole short ci(): returns (stat float64[n_samples] CUDA view,
-    endpoints[A], ranks[A] int64, less, jack[8]) — ranks are the device's speculative ones."""
-    torch = _torch()
+    """One library call (one kernel) for a whole short ci(): returns (stat float64[n_samples] CUDA
+    view, endpoints[A], ranks[A] int64, less, jack[8]) — ranks are the device's speculative ones.
+    `arrays`: float64 CUDA tensors, or contiguous float64 numpy arrays (staged through pinned
+    memory inside the call)."""
     L = _abi.lib()
-    n_rows = arrays[0].numel()
+    n_arrays = len(arrays)
     a = np.ascontiguousarray(alphas, dtype=np.float64).reshape(-1)
     na = len(a)
-    stat, res_dev, res_host = _small.get(n_samples)
-    ws, wsz = workspace_for(stat_id, n_rows, len(arrays), 1, n_samples, na)
+    ent = _small.get(n_samples)
+    for i in range(na):
+        ent.alphas[i] = a[i]
     s = stream_ptr()
-    rc = L.b200boot_ci_small(_ptr_array(arrays), len(arrays), n_rows, stat_id, seed, n_samples,
-                             a.ctypes.data, na, int(bca), int(need_jack), stat.data_ptr(),
-                             res_dev.data_ptr(), res_host.data_ptr(), ws, wsz, s)
-    if rc:
-        _abi.check(rc)
-    _sync_stream(s)
+    if isinstance(arrays[0], np.ndarray):
+        n_rows = arrays[0].shape[0]
+        ws, wsz = _ws.get(4096)
+        for i, x in enumerate(arrays):
+            ent.host_ptrs[i] = x.ctypes.data
+        TRAFFIC["h2d"] += 8 * n_rows * n_arrays
+        rc = L.b200boot_ci_small_host(ent.host_ptrs, ent.staging_ptrs, ent.rows_ptrs, n_arrays, n_rows, stat_id, seed,
+                                      n_samples, ent.alphas_ptr, na, int(bca), int(need_jack), ent.stat_ptr,
+                                      ent.res_dev_ptr, ent.res_host_ptr, ws, wsz, s)
+        if rc:
+            _abi.check(rc)
+    else:
+        n_rows = arrays[0].numel()
+        ws, wsz = _ws.get(4096)
+        rc = L.b200boot_ci_small(_ptr_array(arrays), n_arrays, n_rows, stat_id, seed, n_samples,
+                                 ent.alphas_ptr, na, int(bca), int(need_jack), ent.stat_ptr,
+                                 ent.res_dev_ptr, ent.res_host_ptr, ws, wsz, s)
+        if rc:
+            _abi.check(rc)
+        _sync_stream(s)
     TRAFFIC["d2h"] += 32 * 8
-    r = res_host.numpy()
-    return (stat[:n_samples], r[:na].copy(), r[8:8 + na].astype(np.int64), int(r[16]), r[17:25].copy())
+    r = ent.res_np
+    return (ent.stat[:n_samples], r[:na].copy(), r[8:8 + na].astype(np.int64), int(r[16]), r[17:25].copy())
 
 
 def _sync_stream(stream: int) -> None:

@@ -20,6 +20,7 @@ What differs, by design:
 """
 from __future__ import annotations
 
+import math
 import warnings
 from collections.abc import Iterable
 from typing import Any, Callable, Iterator, Optional, Sequence, Tuple, Union
@@ -431,8 +432,115 @@ def ci(
         `scikits_bootstrap_b200.REGISTRY_NAMES`); default np.average.
     Returns the interval endpoints, and the sorted bootstrap distribution as well
     when return_dist=True."""
+    if multi is None and not return_dist and not use_numba and (type(data) is np.ndarray or _is_tensor(data)):
+        res = _ci_small_direct(data, statfunction, alpha, n_samples, method, output, seed)
+        if res is not None:
+            return res
     return _ci_impl(data, statfunction, alpha, n_samples, method, output, epsilon, multi,
                     return_dist, seed, use_numba, None)
+
+
+class _SmallRun:
+    """What _ci_tail needs from a job whose device work is already done (the fused small call)."""
+    vector = False
+    n_cols = 1
+
+    def __init__(self, vals, ranks, less, jack):
+        self._spec = (ranks.reshape(-1, 1), vals.reshape(-1, 1))
+        self._jack = jack.reshape(1, 8)
+        self._less = np.array([less], dtype=np.int64)
+
+    def jackknife_and_less(self, stat):
+        return self._jack, self._less
+
+    def jackknife(self):
+        return self._jack
+
+    def select(self, stat, ranks):
+        spec_ranks, spec_vals = self._spec
+        if spec_ranks.shape == np.shape(ranks) and np.array_equal(spec_ranks, ranks):
+            return spec_vals                                      # the device's ranks were the host's
+        stat = stat.reshape(1, -1)
+        r = _device.host_to_device(np.asarray(ranks, dtype=np.int64), stat.device)
+        return _device.to_host(_device.Select(stat, r).run(sharded=False))
+
+
+def _ci_small_direct(data, statfunction, alpha, n_samples, method, output, seed):
+    """Short calls (cfg1: N = 1e3, n_samples = 1e4) are bound by per-call overheads, so the
+    common form — one contiguous 1-D float64 numpy array or CUDA tensor, a scalar moment
+    statistic, a float alpha — skips the general job set-up: host rows go to the device inside
+    the one library call that also runs the fused kernel (b200boot_ci_small_host), and the
+    interval follows from the returned block in Python floats (_small_tail; the general tail
+    whenever anything is out of the ordinary).  Returns None when the call is not of that
+    form; the result is what the general path returns, bit for bit."""
+    if (type(alpha) is not float or type(n_samples) is not int or method not in ("pi", "bca")
+            or output not in ("lowhigh", "errorbar") or _dist.active()):
+        return None
+    if type(data) is np.ndarray:
+        if data.ndim != 1 or data.dtype != np.float64 or not data.flags.c_contiguous:
+            return None
+        n_rows = data.shape[0]
+    else:
+        torch = _device.require_cuda()
+        if (not data.is_cuda or data.dtype != torch.float64 or data.dim() != 1 or not data.is_contiguous()
+                or data.device.index != torch.cuda.current_device()):
+            return None
+        n_rows = data.shape[0]
+    spec = lookup(np.average if statfunction is None else statfunction)
+    if (spec is None or spec.n_arrays != 1 or spec.independent or spec.n_out != 1
+            or spec.stat_id == _abi.STAT_MEDIAN or n_rows < 1):
+        return None
+    _device.require_cuda()
+    if not _device.ci_small_supported(spec.stat_id, 1, n_rows, n_samples, 2):
+        return None
+    key = _seed_key(seed)
+    alphas = np.array([alpha / 2, 1 - alpha / 2])
+    bca = method == "bca"
+    stat, vals, ranks, less, jack = _device.ci_small((data,), spec.stat_id, key, n_samples, alphas, bca,
+                                                     bca or output == "errorbar")
+    out = _small_tail(vals, ranks, less, jack, alphas, n_samples, bca, output)
+    if out is not None:
+        return out
+    return _ci_tail(_SmallRun(vals, ranks, less, jack), stat, alphas, n_samples, method, output, False, 4)
+
+
+def _small_tail(vals, ranks, less, jack, alphas, n_samples, bca, output):
+    """_ci_tail for a scalar statistic and two levels when nothing is out of the ordinary: finite
+    acceleration, 0 < less < n_samples, finite levels, and the device's speculative ranks equal
+    to the host's.  Python floats, the same IEEE operations in the same order as the array forms
+    (_interval._bca_levels_scalar and order_indices' per-element path, which are the ones
+    _ci_tail takes for such input).  Anything else returns None and the general tail decides."""
+    levels = alphas.tolist()
+    if bca:
+        accel, c = float(jack[4]), float(less)
+        if not (math.isfinite(accel) and 0.0 < c < n_samples):
+            return None
+        try:
+            levels = _interval._bca_levels_scalar(c, n_samples, accel, alphas).tolist()
+        except (ZeroDivisionError, OverflowError, ValueError):
+            return None
+    top = n_samples - 1
+    extremal = top10 = False
+    for a, r in zip(levels, ranks.tolist()):
+        v = top * a
+        if v != v or abs(v) >= 4.0e18:
+            return None
+        k = round(v)
+        if k == 0 or k == top:
+            extremal = True
+        elif k < 10 or k >= n_samples - 10:
+            top10 = True
+        if min(max(k, 0), top) != r:
+            return None
+    if extremal:
+        warnings.warn("Some values used extremal samples; " + "results are probably unstable.",
+                      InstabilityWarning, stacklevel=4)
+    elif top10:
+        warnings.warn("Some values used top 10 low/high samples; " + "results may be unstable.",
+                      InstabilityWarning, stacklevel=4)
+    if output == "lowhigh":
+        return vals
+    return np.abs(jack[0] - vals)[np.newaxis].T                   # bootstrap.py:491-497
 
 
 def _ci_abc(arrays, statfunction, alphas, output, epsilon):
@@ -592,14 +700,19 @@ def _low_precision_dtype(arrays):
 
 def _ci_on_device(spec, arrays, multi, n_samples, key, indices, alphas, method, output, return_dist,
                   blocks=None):
-    """Device part of ci (warnings use stacklevel=4: the user's frame)."""
+    """Device part of ci (warnings use stacklevel=5: the user's frame)."""
     run = _Run(spec, arrays, multi, n_samples, key, indices, blocks)
     stat = None
     if not return_dist:
         stat = run.small_call(alphas, method == "bca", method == "bca" or output == "errorbar")
     if stat is None:
         stat = run.gather_small(run.resample())                   # float64[D][n_local]
+    return _ci_tail(run, stat, alphas, n_samples, method, output, return_dist, 5)
 
+
+def _ci_tail(run, stat, alphas, n_samples, method, output, return_dist, stacklevel):
+    """From the statistic vector to the interval: bootstrap.py:445-504.  `stacklevel` reaches
+    the user's frame from here."""
     ostat = None
     if method == "pi":
         avals = alphas
@@ -618,7 +731,7 @@ def _ci_on_device(spec, arrays, multi, n_samples, key, indices, alphas, method, 
 Statistic values were likely all equal. Affected CI will \
 be inaccurate.".format(nanind),
                 InstabilityWarning,
-                stacklevel=4,
+                stacklevel=stacklevel,
             )
         avals = _interval.bca_levels(less, n_samples, accel_s, alphas)
 
@@ -628,19 +741,19 @@ be inaccurate.".format(nanind),
             "Some values were NaN; results are probably unstable "
             + "(all values were probably equal)",
             InstabilityWarning,
-            stacklevel=4,
+            stacklevel=stacklevel,
         )
     if "extremal" in flags:
         warnings.warn(
             "Some values used extremal samples; " + "results are probably unstable.",
             InstabilityWarning,
-            stacklevel=4,
+            stacklevel=stacklevel,
         )
     elif "top10" in flags:
         warnings.warn(
             "Some values used top 10 low/high samples; " + "results may be unstable.",
             InstabilityWarning,
-            stacklevel=4,
+            stacklevel=stacklevel,
         )
 
     # order statistics without sorting: ranks int[A][D]            bootstrap.py:482-490

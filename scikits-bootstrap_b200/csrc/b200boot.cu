@@ -2,6 +2,7 @@
 // Host side only enqueues work on the caller's stream; all scratch comes from
 // the caller's workspace.
 #include <algorithm>
+#include <string.h>
 #include <vector>
 
 #include "common.cuh"
@@ -468,93 +469,132 @@ int b200boot_stream_synchronize(void* stream) {
 
 int b200boot_ci_small_supported(int stat_id, int n_arrays, int64_t n_rows, int64_t n_samples, int n_alphas) {
   if (moment_set_of(stat_id) < 0 || stat_outputs(stat_id) != 1 || n_arrays != stat_arrays(stat_id)) return 0;
-  if (n_rows < 1 || n_rows > kSmallMaxRows || make_plan(n_rows, n_arrays).n_tiles != 1) return 0;
+  if (n_rows < 1 || n_rows * n_arrays > kFusedMaxCellDoubles || make_plan(n_rows, n_arrays).n_tiles != 1) return 0;
   if (n_samples < 1 || n_samples > kSelSmallMaxRows || n_alphas < 1 || n_alphas > kSelMaxAlphas) return 0;
   return 1;
 }
+
+}  // extern "C"
+
+namespace {
+
+template <int MS>
+int launch_small_fused(const SmallFusedParams& P, int grid, size_t smem, cudaStream_t s) {
+  static PerDeviceOnce configured;
+  B2_CUDA(configured.run([] {
+    return cudaFuncSetAttribute(ci_small_fused_kernel<MS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(kFusedMaxCellDoubles * 8));
+  }));
+  ci_small_fused_kernel<MS><<<grid, kSmallThreads, smem, s>>>(P);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+// the device address of a pinned host block the kernel may store to, or null (then the result
+// block comes back by a copy operation); the last answer is remembered per host thread
+double* device_view_of_pinned(double* host) {
+  static thread_local double* last_host = nullptr;
+  static thread_local double* last_dev = nullptr;
+  if (host == nullptr) return nullptr;
+  if (host == last_host) return last_dev;
+  cudaPointerAttributes attr{};
+  double* dev = nullptr;
+  if (cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+      attr.devicePointer != nullptr)
+    dev = static_cast<double*>(attr.devicePointer);
+  else
+    (void)cudaGetLastError();
+  last_host = host;
+  last_dev = dev;
+  return dev;
+}
+
+int enqueue_ci_small(const double* const* data, int n_arrays, int64_t n_rows, int stat_id, uint64_t seed,
+                     int64_t n_samples, const double* alphas, int n_alphas, int bca, int need_jack,
+                     double* stat_out, double* result_dev, double* result_host, void* ws, size_t ws_bytes,
+                     cudaStream_t s) {
+  int rc = check_moment_stat(stat_id, n_arrays, n_rows);
+  if (rc) return rc;
+  if (!b200boot_ci_small_supported(stat_id, n_arrays, n_rows, n_samples, n_alphas))
+    return fail(B200BOOT_EUNSUPPORTED, "ci_small: shape outside the small-call path");
+  if (!data || !alphas || !stat_out || !result_dev) return fail(B200BOOT_EINVAL, "null pointer");
+  if (bca) need_jack = 1;
+  if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
+    return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
+  Carver cv(ws, ws_bytes);
+  JackState* jack_state = cv.take<JackState>(1);
+  if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+  SmallFusedParams P{};
+  P.data[0] = data[0];
+  P.data[1] = n_arrays > 1 ? data[1] : nullptr;
+  P.n_rows = n_rows;
+  P.smem_stride = (n_rows + 1) & ~(int64_t)1;
+  P.stat = stat_id;
+  P.centre = stat_needs_centering(stat_id) ? 1 : 0;
+  P.seed = seed;
+  P.rk = make_round_keys(seed);
+  P.stat_out = stat_out;
+  P.jack_state = jack_state;
+  P.jack_out = need_jack ? result_dev + kSmallResultDoubles : nullptr;     // 8 doubles behind the result block
+  P.done = reinterpret_cast<int32_t*>(result_dev + kSmallResultDoubles + 8);
+  P.res_host = device_view_of_pinned(result_host);
+  P.tail.stat = stat_out;
+  P.tail.n_samples = n_samples;
+  P.tail.jack = P.jack_out;
+  for (int a = 0; a < n_alphas; ++a) P.tail.alphas[a] = alphas[a];
+  P.tail.n_alphas = n_alphas;
+  P.tail.bca = bca ? 1 : 0;
+  P.tail.res = result_dev;
+  P.tail.staged = n_samples <= kFusedStageMax ? 1 : 0;
+  const size_t cell = (size_t)P.smem_stride * 8 * n_arrays;
+  const size_t tail = (P.tail.staged ? tail_stage_bytes(n_samples) : 0) + tail_scratch_bytes();
+  const size_t smem = std::max(cell, tail);
+  // one warp per resample; the last CTA is the jackknife's when there is more than one
+  const int64_t res_ctas = (n_samples + kSmallThreads / 32 - 1) / (kSmallThreads / 32);
+  const int grid = (int)std::min<int64_t>(sm_count(), res_ctas + (need_jack ? 1 : 0));
+  switch (moment_set_of(stat_id)) {
+    case kMomSum: rc = launch_small_fused<kMomSum>(P, grid, smem, s); break;
+    case kMomSum2: rc = launch_small_fused<kMomSum2>(P, grid, smem, s); break;
+    case kMomAB: rc = launch_small_fused<kMomAB>(P, grid, smem, s); break;
+    case kMomXW: rc = launch_small_fused<kMomXW>(P, grid, smem, s); break;
+    default: rc = launch_small_fused<kMomPair5>(P, grid, smem, s); break;
+  }
+  if (rc) return rc;
+  if (result_host && P.res_host == nullptr)
+    B2_CUDA(cudaMemcpyAsync(result_host, result_dev, kSmallResultDoubles * sizeof(double), cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
 
 int b200boot_ci_small(const double* const* data, int n_arrays, int64_t n_rows, int stat_id, uint64_t seed,
                       int64_t n_samples, const double* alphas, int n_alphas, int bca, int need_jack,
                       double* stat_out, double* result_dev, double* result_host, void* ws, size_t ws_bytes,
                       void* stream) {
-  int rc = check_moment_stat(stat_id, n_arrays, n_rows);
-  if (rc) return rc;
-  if (!b200boot_ci_small_supported(stat_id, n_arrays, n_rows, n_samples, n_alphas))
-    return fail(B200BOOT_EUNSUPPORTED, "ci_small: shape outside the single-CTA small-call path");
-  if (!data || !alphas || !stat_out || !result_dev) return fail(B200BOOT_EINVAL, "null pointer");
-  if (bca) need_jack = 1;
+  return enqueue_ci_small(data, n_arrays, n_rows, stat_id, seed, n_samples, alphas, n_alphas, bca, need_jack,
+                          stat_out, result_dev, result_host, ws, ws_bytes, as_stream(stream));
+}
+
+int b200boot_ci_small_host(const double* const* host_data, double* const* staging, double* const* data_dev,
+                           int n_arrays, int64_t n_rows, int stat_id, uint64_t seed, int64_t n_samples,
+                           const double* alphas, int n_alphas, int bca, int need_jack, double* stat_out,
+                           double* result_dev, double* result_host, void* ws, size_t ws_bytes, void* stream) {
+  if (!host_data || !staging || !data_dev || n_arrays < 1 || n_arrays > 2 || n_rows < 1)
+    return fail(B200BOOT_EINVAL, "ci_small_host: bad arguments");
+  if (!result_host) return fail(B200BOOT_EINVAL, "ci_small_host: result_host is required");
   cudaStream_t s = as_stream(stream);
-  const Plan plan = make_plan(n_rows, n_arrays);
-  if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
-    return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
-  Carver cv(ws, ws_bytes);
-  ResampleWs w = carve_resample(cv, plan, stat_id, n_samples);
-  if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
-  // one memset clears the work counter, the overflow flag and the jackknife state behind them
-  static_assert(sizeof(JackState) <= 256, "JackState must fit the slot behind the two counters");
-  B2_CUDA(cudaMemsetAsync(w.work_counter, 0, 512 + sizeof(JackState), s));
-  const double* rows[2] = {data[0], n_arrays > 1 ? data[1] : nullptr};
-  if (stat_needs_centering(stat_id)) {
-    center_small_kernel<<<1, kSmallThreads, 0, s>>>(rows[0], rows[1], n_rows, w.jack, w.centered[0],
-                                                    n_arrays > 1 ? w.centered[1] : nullptr);
-    B2_LAUNCH_CHECK();
-    for (int a = 0; a < n_arrays; ++a) rows[a] = w.centered[a];
+  const size_t bytes = (size_t)n_rows * sizeof(double);
+  for (int a = 0; a < n_arrays; ++a) {
+    if (!host_data[a] || !staging[a] || !data_dev[a]) return fail(B200BOOT_EINVAL, "ci_small_host: null pointer");
+    memcpy(staging[a], host_data[a], bytes);           // pageable -> pinned: the copy below is a plain DMA
+    B2_CUDA(cudaMemcpyAsync(data_dev[a], staging[a], bytes, cudaMemcpyHostToDevice, s));
   }
-  // K1 over the single cell, finishing the statistic itself
-  {
-    const int ms = moment_set_of(stat_id);
-    int64_t chunk = kK1Warps;                       // one pass of the CTA's warps per work item
-    const int64_t n_chunks = (n_samples + chunk - 1) / chunk;
-    K1Params P{};
-    P.data[0] = rows[0];
-    P.data[1] = rows[1];
-    P.plan = plan;
-    P.seed = seed;
-    P.resample_lo = 0;
-    P.n_local = n_samples;
-    P.rk = make_round_keys(seed);
-    P.partial = w.partial;
-    P.work_counter = w.work_counter;
-    P.chunk = (int32_t)chunk;
-    P.n_chunks = (int32_t)n_chunks;
-    P.n_items = n_chunks;
-    P.smem_stride = (plan.rem + 1) & ~(int64_t)1;
-    P.stat = stat_id;
-    P.center = w.jack->center;
-    P.direct_out = stat_out;
-    const size_t smem = kSmemHeader + (size_t)P.smem_stride * 8 * n_arrays;
-    rc = dispatch_k1(ms, P, smem, (int)std::min<int64_t>(sm_count(), P.n_items), s);
-    if (rc) return rc;
-  }
-  double* jack_out = result_dev + kSmallResultDoubles;      // 8 more doubles behind the result block
-  if (need_jack) {
-    switch (moment_set_of(stat_id)) {
-      case kMomSum: rc = jack_passes<kMomSum>(rows, n_rows, stat_id, w, jack_out, s); break;
-      case kMomSum2: rc = jack_passes<kMomSum2>(rows, n_rows, stat_id, w, jack_out, s); break;
-      case kMomAB: rc = jack_passes<kMomAB>(rows, n_rows, stat_id, w, jack_out, s); break;
-      case kMomXW: rc = jack_passes<kMomXW>(rows, n_rows, stat_id, w, jack_out, s); break;
-      default: rc = jack_passes<kMomPair5>(rows, n_rows, stat_id, w, jack_out, s); break;
-    }
-    if (rc) return rc;
-  }
-  SmallTailParams P{};
-  P.stat = stat_out;
-  P.n_samples = n_samples;
-  P.jack = need_jack ? jack_out : nullptr;
-  for (int a = 0; a < n_alphas; ++a) P.alphas[a] = alphas[a];
-  P.n_alphas = n_alphas;
-  P.bca = bca ? 1 : 0;
-  P.res = result_dev;
-  P.staged = n_samples <= kSmallStageMax ? 1 : 0;
-  static PerDeviceOnce tail_configured;
-  B2_CUDA(tail_configured.run([] {
-    return cudaFuncSetAttribute(ci_tail_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(kSmallStageMax * 8));
-  }));
-  ci_tail_small_kernel<<<1, kSmallThreads, P.staged ? (size_t)n_samples * 8 : 0, s>>>(P);
-  B2_LAUNCH_CHECK();
-  if (result_host)
-    B2_CUDA(cudaMemcpyAsync(result_host, result_dev, kSmallResultDoubles * sizeof(double), cudaMemcpyDeviceToHost, s));
+  const int rc = enqueue_ci_small(data_dev, n_arrays, n_rows, stat_id, seed, n_samples, alphas, n_alphas, bca,
+                                  need_jack, stat_out, result_dev, result_host, ws, ws_bytes, s);
+  if (rc) return rc;
+  B2_CUDA(cudaStreamSynchronize(s));
   return 0;
 }
 

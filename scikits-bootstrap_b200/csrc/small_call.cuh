@@ -213,4 +213,358 @@ __global__ void __launch_bounds__(kSmallThreads) ci_tail_small_kernel(const Smal
   if (tid < P.n_alphas) P.res[tid] = value_of(s_prefix[tid]);
 }
 
+
+// ---- the fused small call: ONE launch for K1 + jackknife + tail -----------------------------
+// A cfg1-sized ci() is bound by launch latencies and by whatever runs on a single SM.  The fused
+// kernel removes the launch boundaries and shortens the single-SM part:
+//   * every CTA loads the (short) rows into shared memory and, for centred statistics, centres
+//     them itself — the same thread-strided sums in the same order in every CTA, so all CTAs hold
+//     the bits center_small_kernel would have written;
+//   * the last CTA of the grid runs the closed-form jackknife (k3_small's passes) while the others
+//     resample (one warp per resample over the single-cell Lemire stream, exactly K1's
+//     lemire_accumulate + finish_stat: bit-equal to the general path);
+//   * the CTA that finishes last (ticket counter) runs the tail: z0 count, speculative BCa levels
+//     and ranks as before, and a BUCKET select instead of the 8-pass radix descent: min / max of
+//     the statistic vector, a monotone linear map into 4096 buckets, one histogram pass, one scan,
+//     then the few values sharing the bucket of each rank are ranked exactly by their keys.  The
+//     map is monotone non-decreasing in the value, so the k-th smallest value lies in the bucket
+//     whose cumulative count first exceeds k: the result is sort(stat)[k] bit for bit.  Degenerate
+//     vectors (all equal, non-finite range, NaN ranks, a crowded bucket) take the radix descent.
+//   * the 32-double result block is also stored straight into the caller's pinned host mirror
+//     when that memory is device-accessible (no copy operation behind the kernel).
+constexpr int kBktBins = 4096;
+constexpr int kBktCand = 256;                   // candidates kept per rank; more -> radix descent
+constexpr int64_t kFusedStageMax = 16384;       // statistic vectors up to here are staged (128 KB)
+constexpr int64_t kFusedMaxCellDoubles = 28672; // rows x arrays resident (224 KB), K1's single-cell limit
+
+struct SmallFusedParams {
+  const double* data[2];
+  int64_t n_rows;
+  int64_t smem_stride;      // doubles between the two arrays in shared memory
+  int stat;
+  int centre;               // rows are centred on their means first
+  uint64_t seed;
+  RoundKeys rk;
+  double* stat_out;         // [n_samples]
+  JackState* jack_state;
+  double* jack_out;         // [8] device, or null: no jackknife
+  int32_t* done;            // ticket counter: zero on entry, reset on exit
+  double* res_host;         // device-accessible pinned mirror of tail.res, or null
+  SmallTailParams tail;
+};
+
+// dynamic shared memory of the tail, behind the staged vector
+struct TailScratch {
+  unsigned int* hist;                       // [kBktBins]
+  uint64_t* cand;                           // [kSelMaxAlphas][kBktCand]
+  unsigned int (*hist2)[256];               // [kSelMaxAlphas][256]: radix descent
+};
+inline __host__ __device__ size_t tail_stage_bytes(int64_t n) { return ((size_t)n * 8 + 15) & ~(size_t)15; }
+inline __host__ __device__ size_t tail_scratch_bytes() {
+  return (size_t)kBktBins * 4 + (size_t)kSelMaxAlphas * kBktCand * 8 + (size_t)kSelMaxAlphas * 256 * 4;
+}
+
+__device__ __forceinline__ int bucket_of(double v, double lo, double scale) {
+  const int b = (int)((v - lo) * scale);    // v >= lo: non-negative, monotone in v
+  return b < kBktBins - 1 ? b : kBktBins - 1;
+}
+
+// All 1024 threads of one CTA.  `smem`: (staged ? n doubles : 0) + tail_scratch_bytes().
+__device__ __noinline__ void small_tail_bucket(const SmallTailParams& P, unsigned char* smem, double* res_host) {
+  __shared__ double s_red[kSmallThreads / 32][2];
+  __shared__ unsigned int s_cnt_red[kSmallThreads / 32][2];
+  __shared__ unsigned int s_scan[kSmallThreads / 32];
+  __shared__ uint64_t s_prefix[kSelMaxAlphas];
+  __shared__ long long s_krem[kSelMaxAlphas], s_rank[kSelMaxAlphas];
+  __shared__ int s_bucket[kSelMaxAlphas];
+  __shared__ unsigned int s_ccnt[kSelMaxAlphas];
+  __shared__ double s_val[kSelMaxAlphas];
+  __shared__ int s_slow;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n = P.n_samples;
+  const int A = P.n_alphas;
+  double* s_stat = reinterpret_cast<double*>(smem);
+  unsigned char* scratch = smem + (P.staged ? tail_stage_bytes(n) : 0);
+  TailScratch T;
+  T.hist = reinterpret_cast<unsigned int*>(scratch);
+  T.cand = reinterpret_cast<uint64_t*>(scratch + (size_t)kBktBins * 4);
+  T.hist2 = reinterpret_cast<unsigned int(*)[256]>(scratch + (size_t)kBktBins * 4 + (size_t)kSelMaxAlphas * kBktCand * 8);
+
+  // pass A: stage, min / max of the non-NaN values, NaN count, #{stat < ostat}
+  const double ostat = P.bca ? __ldcg(P.jack) : 0.0;
+  double lo = INFINITY, hi = -INFINITY;
+  unsigned int less = 0, nans = 0;
+  for (int64_t r = tid; r < n; r += kSmallThreads) {
+    const double v = __ldcg(P.stat + r);
+    if (P.staged) s_stat[r] = v;
+    if (v != v) {
+      ++nans;
+    } else {
+      lo = fmin(lo, v);
+      hi = fmax(hi, v);
+    }
+    less += (P.bca && v < ostat) ? 1u : 0u;                          // strict '<'  bootstrap.py:583
+  }
+  for (int i = tid; i < kBktBins; i += kSmallThreads) T.hist[i] = 0u;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+  }
+  less = __reduce_add_sync(0xffffffffu, less);
+  nans = __reduce_add_sync(0xffffffffu, nans);
+  if (lane == 0) {
+    s_red[warp][0] = lo;
+    s_red[warp][1] = hi;
+    s_cnt_red[warp][0] = less;
+    s_cnt_red[warp][1] = nans;
+  }
+  if (tid == 0) s_slow = 0;
+  if (tid < kSelMaxAlphas) s_ccnt[tid] = 0u;
+  __syncthreads();
+  lo = INFINITY, hi = -INFINITY, less = 0, nans = 0;
+  for (int w = 0; w < kSmallThreads / 32; ++w) {
+    lo = fmin(lo, s_red[w][0]);
+    hi = fmax(hi, s_red[w][1]);
+    less += s_cnt_red[w][0];
+    nans += s_cnt_red[w][1];
+  }
+  const double* stat = P.staged ? s_stat : P.stat;
+  const double* jack = P.jack;
+
+  // speculative levels and ranks (the host verifies them)
+  if (tid < A) {
+    double aval = P.alphas[tid];
+    if (P.bca) {
+      const double z0 = dev_nppf((1.0 * (double)less) / (double)n);
+      const double zs = z0 + dev_nppf(P.alphas[tid]);
+      aval = dev_ncdf(z0 + zs / (1.0 - __ldcg(jack + 4) * zs));
+    }
+    double v = rint((double)(n - 1) * aval);          // half to even, as np.round
+    if (v != v) v = 0.0;                               // nan_to_num
+    v = fmin(fmax(v, 0.0), (double)(n - 1));           // clip, as the host does before selecting
+    s_rank[tid] = (long long)v;
+    P.res[8 + tid] = v;
+    if (res_host) res_host[8 + tid] = v;
+  }
+  if (tid == 0) {
+    P.res[16] = (double)less;
+    if (res_host) res_host[16] = (double)less;
+  }
+  if (tid < 8 && jack) {
+    const double j = __ldcg(jack + tid);
+    P.res[17 + tid] = j;
+    if (res_host) res_host[17 + tid] = j;
+  }
+
+  // bucket select
+  const double range = hi - lo;
+  const double scale = (double)kBktBins / range;
+  const bool fast = hi > lo && isfinite(range) && isfinite(scale) && isfinite(lo);
+  if (fast) {
+    for (int64_t r = tid; r < n; r += kSmallThreads) {
+      const double v = P.staged ? stat[r] : __ldcg(stat + r);
+      if (v == v) atomicAdd(&T.hist[bucket_of(v, lo, scale)], 1u);
+    }
+    __syncthreads();
+    // exclusive scan over the buckets: thread t owns buckets 4t .. 4t + 3
+    const uint4 h4 = reinterpret_cast<const uint4*>(T.hist)[tid];
+    const unsigned int mine = h4.x + h4.y + h4.z + h4.w;
+    unsigned int inc = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned int o = __shfl_up_sync(0xffffffffu, inc, off);
+      if (lane >= off) inc += o;
+    }
+    if (lane == 31) s_scan[warp] = inc;
+    __syncthreads();
+    unsigned int base = 0;
+    for (int w = 0; w < warp; ++w) base += s_scan[w];
+    const long long below0 = (long long)base + (long long)(inc - mine);
+    const unsigned int hs[4] = {h4.x, h4.y, h4.z, h4.w};
+    for (int a = 0; a < A; ++a) {
+      const long long k = s_rank[a];
+      if (k >= n - (long long)nans) {                  // a NaN is asked for: radix descent
+        if (tid == 0) s_slow = 1;
+      } else if (k >= below0 && k < below0 + (long long)mine) {
+        long long below = below0;
+        for (int b = 0; b < 4; ++b) {
+          if (k < below + (long long)hs[b]) {
+            s_bucket[a] = tid * 4 + b;
+            s_krem[a] = k - below;
+            break;
+          }
+          below += hs[b];
+        }
+      }
+    }
+    __syncthreads();
+    if (!s_slow) {
+      // the values of each rank's bucket, as keys
+      for (int64_t r = tid; r < n; r += kSmallThreads) {
+        const double v = P.staged ? stat[r] : __ldcg(stat + r);
+        if (v != v) continue;
+        const int b = bucket_of(v, lo, scale);
+        for (int a = 0; a < A; ++a)
+          if (b == s_bucket[a]) {
+            const unsigned int pos = atomicAdd(&s_ccnt[a], 1u);
+            if (pos < (unsigned int)kBktCand) T.cand[a * kBktCand + pos] = key_of(v);
+          }
+      }
+      __syncthreads();
+      for (int a = 0; a < A; ++a)
+        if (s_ccnt[a] > (unsigned int)kBktCand && tid == 0) s_slow = 1;
+      __syncthreads();
+      if (!s_slow) {
+        // exact rank inside the bucket: four ranks at a time, 256 threads each
+        for (int a0 = 0; a0 < A; a0 += kSmallThreads / kBktCand) {
+          const int a = a0 + tid / kBktCand, t = tid % kBktCand;
+          if (a < A && t < (int)s_ccnt[a]) {
+            const uint64_t* c = T.cand + a * kBktCand;
+            const uint64_t key = c[t];
+            const int cnt = (int)s_ccnt[a];
+            int before = 0;
+            for (int j = 0; j < cnt; ++j) before += (c[j] < key || (c[j] == key && j < t)) ? 1 : 0;
+            if (before == (int)s_krem[a]) s_val[a] = value_of(key);
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+  if (!fast || s_slow) {
+    __syncthreads();
+    if (tid < A) {
+      s_prefix[tid] = 0;
+      s_krem[tid] = s_rank[tid];
+    }
+    __syncthreads();
+    select_small_descend(stat, n, A, T.hist2, s_prefix, s_krem);
+    if (tid < A) s_val[tid] = value_of(s_prefix[tid]);
+    __syncthreads();
+  }
+  if (tid < A) {
+    P.res[tid] = s_val[tid];
+    if (res_host) res_host[tid] = s_val[tid];
+  }
+  if (res_host) __threadfence_system();
+}
+
+// Closed-form jackknife of the resident rows by the whole CTA (the passes of k3_small_kernel).
+template <int MS>
+__device__ __noinline__ void k3_small_body(const double* d0, const double* d1, int64_t n_rows, int stat, JackState* st,
+                              double* out, double (*s_part)[kMaxMoments]) {
+  constexpr int NM = MomTraits<MS>::kMoments;
+  const double n = (double)n_rows;
+  double acc[kMaxMoments];
+#pragma unroll
+  for (int k = 0; k < kMaxMoments; ++k) acc[k] = 0.0;
+  const ContributionF<MS> contrib{d0, d1};
+  for (int64_t i = threadIdx.x; i < n_rows; i += kSmallThreads) {
+    double c[kMaxMoments];
+    contrib(i, c);
+#pragma unroll
+    for (int k = 0; k < NM; ++k) acc[k] += c[k];
+  }
+  block_sum_small<kMaxMoments>(acc, s_part);
+  if (threadIdx.x == 0) StoreTotalsG<MS>{st, stat, n, d0, d1}(acc);
+  __syncthreads();
+  __threadfence_block();
+  double s1[kMaxMoments] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int64_t i = threadIdx.x; i < n_rows; i += kSmallThreads)
+    s1[0] += leave_one_out<MS>(st, stat, n, d0, d1, i) - st->j0;
+  block_sum_small<kMaxMoments>(s1, s_part);
+  if (threadIdx.x == 0) StoreJmeanG{st, n}(s1);
+  __syncthreads();
+  __threadfence_block();
+  double s2[kMaxMoments] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int64_t i = threadIdx.x; i < n_rows; i += kSmallThreads) {
+    const double d = st->jmean - leave_one_out<MS>(st, stat, n, d0, d1, i);
+    s2[0] += d * d;
+    s2[1] += d * d * d;
+  }
+  block_sum_small<kMaxMoments>(s2, s_part);
+  if (threadIdx.x == 0) StoreAccelG{st, out}(s2);
+}
+
+template <int MS>
+__global__ void __launch_bounds__(kSmallThreads, 1) ci_small_fused_kernel(const SmallFusedParams P) {
+  constexpr int NA = MomTraits<MS>::kArrays;
+  constexpr int NM = MomTraits<MS>::kMoments;
+  extern __shared__ __align__(128) unsigned char sf_smem[];
+  __shared__ double s_part[kSmallThreads / 32][kMaxMoments];
+  __shared__ double s_centre[2];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n_rows = P.n_rows;
+  double* s_data = reinterpret_cast<double*>(sf_smem);
+  double* s_d1 = s_data + P.smem_stride;
+
+  // rows -> shared memory (centred on their means where the statistic asks for it, with the
+  // arithmetic of center_small_kernel)
+  if (P.centre) {
+    double acc[kMaxMoments] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int64_t i = tid; i < n_rows; i += kSmallThreads) {
+      acc[0] += P.data[0][i];
+      if (NA == 2) acc[1] += P.data[1][i];
+    }
+    block_sum_small<kMaxMoments>(acc, s_part);
+    const double m0 = acc[0] / (double)n_rows, m1 = acc[1] / (double)n_rows;
+    if (tid == 0) {
+      s_centre[0] = m0;
+      s_centre[1] = m1;
+    }
+    for (int64_t i = tid; i < n_rows; i += kSmallThreads) {
+      s_data[i] = P.data[0][i] - m0;
+      if (NA == 2) s_d1[i] = P.data[1][i] - m1;
+    }
+  } else {
+    if (tid == 0) s_centre[0] = s_centre[1] = 0.0;
+    for (int64_t i = tid; i < n_rows; i += kSmallThreads) {
+      s_data[i] = P.data[0][i];
+      if (NA == 2) s_d1[i] = P.data[1][i];
+    }
+  }
+  __syncthreads();
+
+  const bool with_jack = P.jack_out != nullptr;
+  const bool jack_cta = with_jack && gridDim.x > 1 && blockIdx.x == gridDim.x - 1;
+  const int n_res_ctas = (with_jack && gridDim.x > 1) ? gridDim.x - 1 : gridDim.x;
+  if (!jack_cta) {
+    const unsigned char* s_bytes = sf_smem;
+    const uint32_t stride_bytes = (uint32_t)(P.smem_stride * 8);
+    const int64_t step = (int64_t)n_res_ctas * (kSmallThreads / 32);
+    for (int64_t rl = (int64_t)blockIdx.x * (kSmallThreads / 32) + warp; rl < P.tail.n_samples; rl += step) {
+      double tot[NM];
+      const Stream st = make_stream(P.seed, rl, 0u, kPurposeIndex);
+      lemire_accumulate<MS>(s_bytes, stride_bytes, P.rk, st, n_rows, (uint32_t)n_rows, lane, tot);
+      if (lane == 0) {
+        double m[kMaxMoments];
+#pragma unroll
+        for (int k = 0; k < NM; ++k) m[k] = 0.0 + tot[k];      // as the finisher's sum over one cell
+        P.stat_out[rl] = finish_stat(P.stat, m, (double)n_rows, s_centre);
+      }
+    }
+  }
+  if (with_jack && (jack_cta || gridDim.x == 1)) {
+    if (tid == 0) {
+      P.jack_state->center[0] = s_centre[0];
+      P.jack_state->center[1] = s_centre[1];
+    }
+    __syncthreads();
+    __threadfence_block();
+    k3_small_body<MS>(s_data, NA == 2 ? s_d1 : nullptr, n_rows, P.stat, P.jack_state, P.jack_out, s_part);
+  }
+
+  // the CTA that finishes last runs the tail
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(P.done, 1) == (int)gridDim.x - 1 ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  small_tail_bucket(P.tail, sf_smem, P.res_host);
+  if (tid == 0) *P.done = 0;          // the ticket counter is left ready for the next call
+}
+
 }  // namespace b200boot

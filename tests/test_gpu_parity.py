@@ -573,6 +573,68 @@ def test_small_call_path_equals_general_path(stat_name, n, n_arrays, monkeypatch
         assert_array_equal(s, g)
 
 
+def _edge_data(kind):
+    rng = np.random.default_rng(11)
+    if kind == "nan":
+        x = rng.standard_normal(300)
+        x[5] = np.nan                     # most resamples draw it: the statistic vector is mostly NaN
+        return x
+    if kind == "rare_nan":
+        x = rng.standard_normal(3000)
+        x[7] = np.nan
+        return x
+    if kind == "inf":
+        x = rng.standard_normal(2000)
+        x[3] = np.inf
+        return x
+    if kind == "ties":
+        return rng.integers(0, 2, 20).astype(float)      # ~21 distinct means: crowded buckets
+    if kind == "huge":
+        return rng.standard_normal(500) * 1e300
+    if kind == "tiny":
+        return rng.standard_normal(500) * 1e-310          # subnormal range
+    if kind == "signed_zero":
+        return np.array([0.0, -0.0] * 8)
+    if kind == "two_values":
+        return np.array([1.0] * 30 + [1.0 + 2.0 ** -52])
+    return rng.standard_normal(1000)
+
+
+@pytest.mark.parametrize("kind", ["plain", "nan", "rare_nan", "inf", "ties", "huge", "tiny", "signed_zero", "two_values"])
+def test_small_call_select_edge_cases(kind, monkeypatch):
+    """The fused small call selects by a monotone bucket map with an exact ranking inside the
+    bucket and falls back to the radix descent for degenerate vectors: in every case the
+    interval is the general path's (sort(stat)[k] bit for bit), from numpy and from CUDA input."""
+    import warnings
+    x = _edge_data(kind)
+    kws = [dict(method="bca", n_samples=4000), dict(method="pi", n_samples=1), dict(method="pi", n_samples=2),
+           dict(method="bca", n_samples=3), dict(method="pi", n_samples=20000, alpha=(0.001, 0.01, 0.1, 0.3, 0.5, 0.7, 0.9, 0.999)),
+           dict(method="bca", n_samples=32768), dict(method="pi", n_samples=16384, output="errorbar"),
+           dict(method="bca", n_samples=16385)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for f in (np.mean, np.std):
+            small = [boot.ci(x, f, seed=3, **k) for k in kws]
+            small_dev = [boot.ci(dev(x), f, seed=3, **k) for k in kws]
+            monkeypatch.setattr(_device, "ci_small_supported", lambda *a: False)
+            general = [boot.ci(x, f, seed=3, **k) for k in kws]
+            monkeypatch.undo()
+            for a, b, c in zip(small, small_dev, general):
+                assert_array_equal(a, c)
+                assert_array_equal(b, c)
+
+
+def test_small_call_is_reentrant_on_its_buffers():
+    """The fused kernel's ticket counter is left at zero by every call: many calls in a row, of
+    different shapes, from one thread."""
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(777)
+    want = {n: boot.ci(x, np.mean, n_samples=n, seed=9) for n in (10, 500, 9000)}
+    for _ in range(20):
+        for n in (9000, 10, 500):
+            assert_array_equal(boot.ci(x, np.mean, n_samples=n, seed=9), want[n])
+
+
 def test_small_call_wrong_speculative_ranks_are_caught(monkeypatch):
     """The device's ranks are only a guess: when the host's own levels give other ranks the
     order statistics are selected again with the host's."""

@@ -10,8 +10,9 @@ L = _abi.lib()
 x = torch.from_numpy(np.random.default_rng(0).standard_normal(1000)).cuda()
 n = 10000
 a = np.array([0.025, 0.975])
-stat, res_dev, res_host = _device._small.get(n)
-ws, wsz = _device.workspace_for(_abi.STAT_MEAN, 1000, 1, 1, n, 2)
+ent = _device._small.get(n)
+stat, res_dev, res_host = ent.stat, ent.res_dev, ent.res_host
+ws, wsz = _device._ws.get(4096)
 ptrs = _device._ptr_array([x])
 s = _device.stream_ptr()
 def call(seed):
