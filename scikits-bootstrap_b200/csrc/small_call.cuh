@@ -1,12 +1,12 @@
 // Small calls: when the data are one resident cell and the statistic vector is short, a whole
-// ci() is launch- and round-trip-bound (cfg1: N = 1e3, n_samples = 1e4).  This file holds the
-// single-CTA kernels that shorten such a call to three launches and one device-to-host copy:
-//   center_small_kernel   means + centred rows of short arrays (var / std / Pearson / fit);
-//   k3_small_kernel       the closed-form jackknife (bootstrap.py:595-615) in one CTA — also
-//                         what b200boot_jackknife runs for short arrays, so the short and the
-//                         general call agree bit for bit;
-//   ci_tail_small_kernel  z0 count (bootstrap.py:583), BCa levels (:609-629), order-statistic
-//                         ranks (:456, :480) and their exact radix select (:485-490) in one CTA.
+// ci() is launch- and round-trip-bound (cfg1: N = 1e3, n_samples = 1e4).  This file holds
+//   center_small_kernel    means + centred rows of short arrays (var / std / Pearson / fit);
+//   k3_small_kernel        the closed-form jackknife (bootstrap.py:595-615) in one CTA — what
+//                          b200boot_jackknife runs for short arrays;
+//   ci_small_fused_kernel  a whole short ci() in ONE launch: resampling (K1's single-cell path),
+//                          the jackknife, the z0 count (bootstrap.py:583), the BCa levels
+//                          (:609-629), the order-statistic ranks (:456, :480) and their exact
+//                          select (:485-490).
 // The tail's levels are SPECULATIVE: nppf / ncdf are evaluated on the device with the
 // reference's formulas, but the host recomputes the ranks with its own (verbatim) math from
 // the returned count and jackknife summary and only accepts the device's order statistics
@@ -66,47 +66,6 @@ __global__ void __launch_bounds__(kSmallThreads) center_small_kernel(const doubl
   }
 }
 
-// Closed-form jackknife of a short array (pair): the three passes of jack_passes in one CTA.
-// out[8] as StoreAccelG writes it.
-template <int MS>
-__global__ void __launch_bounds__(kSmallThreads) k3_small_kernel(const double* __restrict__ d0,
-                                                                 const double* __restrict__ d1, int64_t n_rows,
-                                                                 int stat, JackState* st, double* __restrict__ out) {
-  constexpr int NM = MomTraits<MS>::kMoments;
-  __shared__ double s_part[kSmallThreads / 32][kMaxMoments];
-  const double n = (double)n_rows;
-  double acc[kMaxMoments];
-#pragma unroll
-  for (int k = 0; k < kMaxMoments; ++k) acc[k] = 0.0;
-  const ContributionF<MS> contrib{d0, d1};
-  for (int64_t i = threadIdx.x; i < n_rows; i += kSmallThreads) {
-    double c[kMaxMoments];
-    contrib(i, c);
-#pragma unroll
-    for (int k = 0; k < NM; ++k) acc[k] += c[k];
-  }
-  block_sum_small<kMaxMoments>(acc, s_part);
-  if (threadIdx.x == 0) StoreTotalsG<MS>{st, stat, n, d0, d1}(acc);
-  __syncthreads();
-  __threadfence_block();
-  // jackknife mean, relative to the leave-one-out value of row 0
-  double s1[kMaxMoments] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  for (int64_t i = threadIdx.x; i < n_rows; i += kSmallThreads)
-    s1[0] += leave_one_out<MS>(st, stat, n, d0, d1, i) - st->j0;
-  block_sum_small<kMaxMoments>(s1, s_part);
-  if (threadIdx.x == 0) StoreJmeanG{st, n}(s1);
-  __syncthreads();
-  __threadfence_block();
-  double s2[kMaxMoments] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  for (int64_t i = threadIdx.x; i < n_rows; i += kSmallThreads) {
-    const double d = st->jmean - leave_one_out<MS>(st, stat, n, d0, d1, i);
-    s2[0] += d * d;
-    s2[1] += d * d * d;
-  }
-  block_sum_small<kMaxMoments>(s2, s_part);
-  if (threadIdx.x == 0) StoreAccelG{st, out}(s2);
-}
-
 // ---- the reference's normal cdf / inverse cdf on the device (speculative ranks only) ---------
 // Same operations in the same order as _interval.py (bootstrap.py:75-119).
 __device__ __forceinline__ double horner6(const double* c, double t) {
@@ -159,61 +118,6 @@ struct SmallTailParams {
   double* res;
 };
 
-// The tail runs in ONE CTA, i.e. on one SM: whatever it does to 1e4 values costs about a
-// microsecond per 1e5 thread-instructions.  Measured alternatives for the select of cfg1
-// (n = 1e4, two ranks; whole tail kernel, B200): byte-wise radix descent with ballot-aggregated
-// histogram atomics over the vector staged in shared memory — this version — 48 us; the same
-// with __match_any_sync aggregation 176 us; a bitonic sort of the keys in shared memory 165 us
-// (105 stages x 128 KB through a 128 B/clk pipe); a 64-step bit descent with register-resident
-// keys 36-48 us; quickselect with register-resident keys 100 us.  The select is a third of the
-// device time of a cfg1 call and a tenth of its wall time (the rest is host Python).
-constexpr int64_t kSmallStageMax = 24576;     // 192 KB of float64
-
-__global__ void __launch_bounds__(kSmallThreads) ci_tail_small_kernel(const SmallTailParams P) {
-  extern __shared__ double s_stat[];
-  __shared__ unsigned int s_hist[kSelMaxAlphas][256];
-  __shared__ uint64_t s_prefix[kSelMaxAlphas];
-  __shared__ long long s_krem[kSelMaxAlphas];
-  __shared__ unsigned int s_less;
-  const int tid = threadIdx.x;
-  const int64_t n = P.n_samples;
-  const double* stat = P.stat;
-  if (P.staged) {
-    for (int64_t r = tid; r < n; r += kSmallThreads) s_stat[r] = P.stat[r];
-    stat = s_stat;
-  }
-  if (tid == 0) s_less = 0;
-  __syncthreads();
-  if (P.bca) {
-    const double ostat = P.jack[0];
-    unsigned int local = 0;
-    for (int64_t r = tid; r < n; r += kSmallThreads) local += stat[r] < ostat ? 1u : 0u;   // strict '<'
-    local = __reduce_add_sync(0xffffffffu, local);
-    if ((tid & 31) == 0 && local) atomicAdd(&s_less, local);
-  }
-  __syncthreads();
-  if (tid < P.n_alphas) {
-    double aval = P.alphas[tid];
-    if (P.bca) {
-      const double z0 = dev_nppf((1.0 * (double)s_less) / (double)n);
-      const double zs = z0 + dev_nppf(P.alphas[tid]);
-      aval = dev_ncdf(z0 + zs / (1.0 - P.jack[4] * zs));
-    }
-    double v = rint((double)(n - 1) * aval);          // half to even, as np.round
-    if (v != v) v = 0.0;                               // nan_to_num
-    v = fmin(fmax(v, 0.0), (double)(n - 1));           // clip, as the host does before selecting
-    s_krem[tid] = (long long)v;
-    s_prefix[tid] = 0;
-    P.res[8 + tid] = v;
-  }
-  if (tid == 0) P.res[16] = (double)s_less;
-  if (tid < 8 && P.jack) P.res[17 + tid] = P.jack[tid];
-  __syncthreads();
-  select_small_descend(stat, n, P.n_alphas, s_hist, s_prefix, s_krem);
-  if (tid < P.n_alphas) P.res[tid] = value_of(s_prefix[tid]);
-}
-
-
 // ---- the fused small call: ONE launch for K1 + jackknife + tail -----------------------------
 // A cfg1-sized ci() is bound by launch latencies and by whatever runs on a single SM.  The fused
 // kernel removes the launch boundaries and shortens the single-SM part:
@@ -232,6 +136,12 @@ __global__ void __launch_bounds__(kSmallThreads) ci_tail_small_kernel(const Smal
 //     vectors (all equal, non-finite range, NaN ranks, a crowded bucket) take the radix descent.
 //   * the 32-double result block is also stored straight into the caller's pinned host mirror
 //     when that memory is device-accessible (no copy operation behind the kernel).
+// Measured on B200 (cfg1, BCa): three launches + copy (K1 23 us, jackknife 10.5 us, single-CTA
+// tail 54 us, of which the ballot-aggregated 8-pass radix descent was ~45 us — itself the best
+// of five selects tried: __match_any aggregation 176 us, shared-memory bitonic sort 165 us,
+// 64-step bit descent 36-48 us, quickselect 100 us) = 98 us of device time per call; this
+// kernel: 42 us (launch + row load ~24 us with an empty statistic vector, ~5 us per round of
+// 4704 resamples, the rest the tail).
 constexpr int kBktBins = 4096;
 constexpr int kBktCand = 256;                   // candidates kept per rank; more -> radix descent
 constexpr int64_t kFusedStageMax = 16384;       // statistic vectors up to here are staged (128 KB)
@@ -485,6 +395,15 @@ __device__ __noinline__ void k3_small_body(const double* d0, const double* d1, i
   }
   block_sum_small<kMaxMoments>(s2, s_part);
   if (threadIdx.x == 0) StoreAccelG{st, out}(s2);
+}
+
+// Closed-form jackknife of a short array (pair) as its own launch; out[8] as StoreAccelG writes it.
+template <int MS>
+__global__ void __launch_bounds__(kSmallThreads) k3_small_kernel(const double* __restrict__ d0,
+                                                                 const double* __restrict__ d1, int64_t n_rows,
+                                                                 int stat, JackState* st, double* __restrict__ out) {
+  __shared__ double s_part[kSmallThreads / 32][kMaxMoments];
+  k3_small_body<MS>(d0, d1, n_rows, stat, st, out, s_part);
 }
 
 template <int MS>
