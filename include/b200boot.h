@@ -194,6 +194,21 @@ int b200boot_resample_median_columns_indexed(const double* data, int64_t n_rows,
 int b200boot_resample_median_sorted(const double* sorted_vals, int64_t n_rows, uint64_t seed,
                                     int64_t resample_lo, int64_t resample_hi, double* stat_out, void* ws,
                                     size_t ws_bytes, void* stream, const b200boot_rank_rule* rule);
+/* K1mr — rank statistics of LONG (N, D) data in row space (bootstrap.py:431 gathers whole rows:
+ * all columns of a resample share the index set).  b200boot_rank_columns sorts every column once:
+ * sorted_out float64[D][N] ascending, rank_out int32[N][D] = position of row i in column d's
+ * order; ws: b200boot_rank_columns_ws_bytes (more workspace = more columns per sorting pass).
+ * b200boot_median_rows_indexed then takes index sets int64[n_sets][N] — what
+ * b200boot_fill_indices yields, or the caller's own (out-of-range entries are ignored) — and
+ * finds each column's order statistics exactly by a two-level counting select over the drawn
+ * rows' ranks: stat_out[d * out_ld + set].  1 <= N <= 2^24. */
+size_t b200boot_rank_columns_ws_bytes(int64_t n_rows, int64_t n_cols);
+int b200boot_rank_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, double* sorted_out,
+                          int32_t* rank_out, void* ws, size_t ws_bytes, void* stream);
+int b200boot_median_rows_supported(int64_t n_rows);
+int b200boot_median_rows_indexed(const double* sorted_vals, const int32_t* rank, int64_t n_rows, int64_t n_cols,
+                                 const int64_t* indices, int64_t n_sets, double* stat_out, int64_t out_ld,
+                                 void* stream, const b200boot_rank_rule* rule);
 /* K3m on a sorted 1-D array of any length: out float64[8] as b200boot_jackknife. */
 int b200boot_jackknife_median_sorted(const double* sorted_vals, int64_t n_rows, double* out, void* stream,
                                      const b200boot_rank_rule* rule);

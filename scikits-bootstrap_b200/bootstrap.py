@@ -59,6 +59,8 @@ _MASK64 = (1 << 64) - 1
 _GATHER_LIMIT_BYTES = 32 << 20
 # key offset between the arrays of multi='independent' (odd 64-bit constant)
 _ARRAY_KEY_STRIDE = 0x9E3779B97F4A7C15
+# K1mr: materialised index sets per batch
+_ROWS_INDEX_BYTES = 256 << 20
 
 
 def _seed_key(seed: SeedType) -> int:
@@ -154,6 +156,7 @@ class _Run:
         self._sorted_vals = None
         self._parts = None
         self._jack_dev = None
+        self._rows = None            # K1mr tables: (sorted [D][N], rank [N][D])
         self._local = False          # sharded run whose statistic vector was gathered: finish without collectives
         self._less = None            # small-call path: #{stat < ostat} and the speculative select
         self._spec = None
@@ -167,20 +170,44 @@ class _Run:
             self._columns = self.dev[0].t().contiguous()
         return self._columns
 
-    # -- long 1-D median: rank-space path over the sorted data --------------------
+    # -- long medians --------------------------------------------------------------------
     def _long_median(self) -> bool:
-        """np.median over more rows than fit in shared memory: the resample is taken in
-        rank space, i.e. it is sorted(x)[bootstrap_indices(...)] (same distribution as
-        x[bootstrap_indices(...)] for this permutation-invariant statistic).  With D > 1
-        columns each column is resampled in its own rank space with the same index sets:
-        every column's bootstrap distribution (all that ci and pval read) is exact, but
-        the rows of the returned distribution are not row-aligned across columns."""
-        if self.spec.stat_id != _abi.STAT_MEDIAN or self.dev[0].shape[0] <= _device.MEDIAN_RESIDENT_ROWS:
+        """np.median / quantiles over more rows than K1m keeps resident."""
+        return (self.spec.stat_id == _abi.STAT_MEDIAN
+                and self.dev[0].shape[0] > _device.MEDIAN_RESIDENT_ROWS)
+
+    def _row_space(self) -> bool:
+        """Long rank statistics that must stay in ROW space (K1mr): (N, D) data with D > 1 —
+        x[indices] gathers whole rows (bootstrap.py:431), so the columns of a resample share
+        their rows — and index-supplied runs.  A single long column without supplied indices
+        takes the rank-space path K1mt instead: its resample is sorted(x)[bootstrap_indices(...)],
+        the same distribution for a permutation-invariant statistic at O(tiles) work per resample."""
+        if not self._long_median():
             return False
-        if self.indices is not None:
-            raise NotImplementedError("index-supplied median needs N <= {} rows".format(
-                _device.MEDIAN_RESIDENT_ROWS))
-        return True
+        want = self.indices is not None or (self.vector and self.n_cols > 1)
+        if want and self.dev[0].shape[0] > _device.MEDIAN_ROWS_MAX:
+            if self.indices is not None:
+                raise NotImplementedError("index-supplied median needs N <= {} rows".format(_device.MEDIAN_ROWS_MAX))
+            return False          # beyond 2^24 rows: per-column rank space (marginals exact, rows not joint)
+        return want
+
+    def _rows_tables(self):
+        """K1mr preparation, once per job: every column sorted, and each row's rank per column."""
+        if self._rows is None:
+            data2d = self.dev[0] if self.dev[0].dim() == 2 else self.dev[0].reshape(-1, 1)
+            self._rows = _device.rank_columns(data2d.contiguous())
+            self._sorted_vals = self._rows[0]
+        return self._rows
+
+    def _median_rows(self, index_batches, n_sets):
+        torch = _device._torch()
+        sorted_vals, rank = self._rows_tables()
+        out = torch.empty((self.n_cols, n_sets), dtype=torch.float64, device=sorted_vals.device)
+        at = 0
+        for idx in index_batches:
+            _device.median_rows_indexed(sorted_vals, rank, idx, out, at, rule=self.rule)
+            at += idx.shape[0]
+        return out
 
     def _sorted(self):
         """float64[D][N]: every column ascending."""
@@ -217,6 +244,12 @@ class _Run:
             a, b = (p.resample() for p in self.parts())
             return _device.combine(spec.op, a, b)
         if spec.stat_id == _abi.STAT_MEDIAN:
+            if self._row_space():
+                n_rows = self.dev[0].shape[0]
+                step = max(1, min(hi - lo, _ROWS_INDEX_BYTES // (8 * n_rows)))
+                batches = (_device.fill_indices(self.key, n_rows, 1, a, min(hi, a + step))
+                           for a in range(lo, hi, step))
+                return self._median_rows(batches, hi - lo)
             if self._long_median():
                 cols = self._sorted()
                 out = torch.empty((self.n_cols, hi - lo), dtype=torch.float64, device=cols.device)
@@ -289,6 +322,8 @@ class _Run:
         if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= n_rows):
             raise IndexError("index out of range")
         if spec.stat_id == _abi.STAT_MEDIAN:
+            if self._row_space():
+                return self._median_rows([idx], idx.shape[0])
             data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
             return _device.resample_median_columns_indexed(data2d, idx, rule=self.rule)
         if self.vector and spec.n_out == 1:

@@ -10,6 +10,7 @@
 #include "k1_resample.cuh"
 #include "k1c_columns.cuh"
 #include "k1m_median.cuh"
+#include "k1mr_rows.cuh"
 #include "k6_gemm.cuh"
 #include "k6i_mma.cuh"
 #include "k3_jackknife.cuh"
@@ -955,6 +956,91 @@ int rank_rules(const b200boot_rank_rule* rule, int64_t n_rows, RankRule* full, R
   return ok ? 0 : fail(B200BOOT_EINVAL, "rank rule: ranks outside the sample or weight outside [0, 1]");
 }
 }  // namespace
+
+size_t b200boot_rank_columns_ws_bytes(int64_t n_rows, int64_t n_cols) {
+  if (n_rows < 1 || n_cols < 1) return 0;
+  int64_t n_pad = 1;
+  while (n_pad < n_rows) n_pad <<= 1;
+  const int64_t nd = std::min<int64_t>(n_cols, 8);             // columns sorted per pass
+  return 4096 + pad256((size_t)n_pad * nd * 8) + pad256((size_t)n_pad * nd * 4);
+}
+
+int b200boot_rank_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, double* sorted_out,
+                          int32_t* rank_out, void* ws, size_t ws_bytes, void* stream) {
+  if (!data || !sorted_out || !rank_out || n_rows < 1 || n_cols < 1 || ld < n_cols || n_rows >= ((int64_t)1 << 31))
+    return fail(B200BOOT_EINVAL, "rank_columns: bad arguments");
+  if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
+    return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
+  cudaStream_t s = as_stream(stream);
+  int64_t n_pad = 1;
+  while (n_pad < n_rows) n_pad <<= 1;
+  // as many columns per pass as the workspace holds (12 bytes per padded entry)
+  const size_t per_col = pad256((size_t)n_pad * 8) + pad256((size_t)n_pad * 4);
+  const int64_t fit = ws_bytes > 4096 ? (int64_t)((ws_bytes - 4096) / per_col) : 0;
+  const int64_t step = std::min<int64_t>(std::min<int64_t>(fit, n_cols), 65535);
+  if (step < 1) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", (size_t)4096 + per_col);
+  for (int64_t d0 = 0; d0 < n_cols; d0 += step) {
+    const int64_t nd = std::min<int64_t>(step, n_cols - d0);
+    Carver cv(ws, ws_bytes);
+    uint64_t* keys = cv.take<uint64_t>((size_t)n_pad * nd);
+    uint32_t* idx = cv.take<uint32_t>((size_t)n_pad * nd);
+    if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+    psort_load_kernel<<<blocks_for(n_pad * nd, 256, 148 * 32), 256, 0, s>>>(data + d0, n_rows, nd, ld, n_pad, keys, idx);
+    B2_LAUNCH_CHECK();
+    int rc = psort_pairs(keys, idx, n_pad, (unsigned)nd, s);
+    if (rc) return rc;
+    rows_rank_kernel<<<blocks_for(n_rows * nd, 256, 148 * 32), 256, 0, s>>>(keys, idx, n_rows, n_pad, n_cols, d0, nd,
+                                                                            rank_out, sorted_out);
+    B2_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int b200boot_median_rows_supported(int64_t n_rows) { return n_rows >= 1 && n_rows <= kRowsMaxRows ? 1 : 0; }
+
+int b200boot_median_rows_indexed(const double* sorted_vals, const int32_t* rank, int64_t n_rows, int64_t n_cols,
+                                 const int64_t* indices, int64_t n_sets, double* stat_out, int64_t out_ld,
+                                 void* stream, const b200boot_rank_rule* rule) {
+  if (!sorted_vals || !rank || !indices || !stat_out || n_cols < 1 || n_sets < 0 || out_ld < n_sets)
+    return fail(B200BOOT_EINVAL, "median_rows_indexed: bad arguments");
+  if (!b200boot_median_rows_supported(n_rows))
+    return fail(B200BOOT_EUNSUPPORTED, "median_rows_indexed: 1 <= n_rows <= 2^24");
+  if (n_sets == 0) return 0;
+  RowsParams P{};
+  RankRule loo;
+  int rc = rank_rules(rule, n_rows, &P.rule, &loo);
+  if (rc) return rc;
+  int bits = 0;
+  while (((int64_t)1 << bits) < n_rows) ++bits;
+  P.shift = (bits + 1) / 2;
+  P.hi_bins = (int32_t)((n_rows + ((int64_t)1 << P.shift) - 1) >> P.shift);
+  P.rank = rank;
+  P.sorted = sorted_vals;
+  P.indices = indices;
+  P.n_rows = n_rows;
+  P.n_cols = n_cols;
+  P.n_sets = n_sets;
+  P.out = stat_out;
+  P.out_ld = out_ld;
+  static PerDeviceOnce configured;
+  B2_CUDA(configured.run([] {
+    return cudaFuncSetAttribute(k1mr_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)rows_smem_bytes());
+  }));
+  cudaStream_t s = as_stream(stream);
+  const int64_t groups = (n_cols + kRowsGroup - 1) / kRowsGroup;
+  for (int64_t g0 = 0; g0 < groups; g0 += 65535) {
+    RowsParams Q = P;
+    const int64_t ng = std::min<int64_t>(65535, groups - g0);
+    Q.rank = P.rank + g0 * kRowsGroup;
+    Q.sorted = P.sorted + g0 * kRowsGroup * n_rows;
+    Q.out = P.out + g0 * kRowsGroup * out_ld;
+    Q.n_cols = n_cols;                  // row stride of the rank table
+    k1mr_select_kernel<<<dim3((unsigned)n_sets, (unsigned)ng), kRowsThreads, rows_smem_bytes(), s>>>(Q, n_cols - g0 * kRowsGroup);
+    B2_LAUNCH_CHECK();
+  }
+  return 0;
+}
 
 int b200boot_resample_median_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld,
                                      uint64_t seed, int64_t resample_lo, int64_t resample_hi,

@@ -1,0 +1,161 @@
+// K1mr — rank statistics (median, quantiles) of LONG (N, D) data in ROW space.
+//
+// The reference gathers whole rows, x[indices] (bootstrap.py:431), so every column of a
+// resample sees the same rows.  For columns longer than K1m's resident limit (28 672 rows) the
+// 1-D path K1mt works in the rank space of its single column; with D > 1 columns that would
+// give every column its own rows.  Here the resample stays in row space:
+//   * once per job, every column is sorted as (key, row) pairs; rank[i][d] = position of row i
+//     in column d's ascending order (ties in any fixed order: equal values give equal results);
+//   * a resample's k-th order statistic of column d is sorted[d][p_k], p_k = the k-th smallest
+//     of the drawn rows' ranks rank[idx_j][d], j = 0..N-1 — found exactly by a two-level
+//     counting select over the rank bits (shared-memory histograms of the high, then the low
+//     half of the bits), without sorting the resample;
+//   * the index sets are the materialised draws of the tiled plan (K2: exactly what
+//     `bootstrap_indices` yields and what K1 consumes) or the caller's own (parity mode).
+// One CTA per (resample, group of four columns): the index row is read once per group, the
+// rank table (int32 [N][D], L2-resident) is gathered per drawn row.
+#pragma once
+#include "common.cuh"
+#include "k1m_median.cuh"
+#include "k45_interval.cuh"
+
+namespace b200boot {
+
+constexpr int kRowsThreads = 512;
+constexpr int kRowsGroup = 4;                   // columns per CTA
+constexpr int kRowsMaxBins = 4096;              // per level: N <= 2^24 rows
+constexpr int64_t kRowsMaxRows = (int64_t)1 << 24;
+
+// rank[idx[d][p] * n_cols + d] = p and sorted[d][p] = value of the key, p < n_rows
+__global__ void __launch_bounds__(256) rows_rank_kernel(const uint64_t* __restrict__ keys,
+                                                        const uint32_t* __restrict__ idx, int64_t n_rows,
+                                                        int64_t n_pad, int64_t n_cols, int64_t d0, int64_t nd,
+                                                        int32_t* __restrict__ rank, double* __restrict__ sorted) {
+  const int64_t total = nd * n_rows;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t dl = e / n_rows, p = e - dl * n_rows;
+    const int64_t d = d0 + dl;
+    rank[(int64_t)idx[dl * n_pad + p] * n_cols + d] = (int32_t)p;
+    sorted[d * n_rows + p] = value_of(keys[dl * n_pad + p]);
+  }
+}
+
+struct RowsParams {
+  const int32_t* rank;       // [N][D]
+  const double* sorted;      // [D][N]
+  const int64_t* indices;    // [n_sets][N]
+  int64_t n_rows, n_cols, n_sets;   // n_cols: row stride of the rank table
+  int32_t shift;             // low bits per rank: bins of level 2 = 1 << shift
+  int32_t hi_bins;           // bins of level 1 = ceil(N / 2^shift)
+  RankRule rule;
+  double* out;               // [D][out_ld]
+  int64_t out_ld;
+};
+
+// first bin whose cumulative count exceeds k (k below the total): warp-cooperative over n_bins
+// (a multiple of 32 is not required); returns the bin and writes the count below it
+__device__ __forceinline__ int rows_find_bin(const unsigned int* hist, int n_bins, long long k, long long* below_out) {
+  const int lane = threadIdx.x & 31;
+  const int per = (n_bins + 31) / 32;
+  const int b0 = lane * per, b1 = min(n_bins, b0 + per);
+  unsigned int mine = 0;
+  for (int b = b0; b < b1; ++b) mine += hist[b];
+  unsigned int inc = mine;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned int o = __shfl_up_sync(0xffffffffu, inc, off);
+    if (lane >= off) inc += o;
+  }
+  const unsigned int hit = __ballot_sync(0xffffffffu, (long long)inc > k);
+  const int owner = hit ? __ffs(hit) - 1 : 31;
+  int bin = n_bins - 1;
+  long long below = 0;
+  if (lane == owner) {
+    below = (long long)(inc - mine);
+    for (int b = b0; b < b1; ++b) {
+      const long long c = hist[b];
+      if (k < below + c) {
+        bin = b;
+        break;
+      }
+      below += c;
+    }
+  }
+  bin = __shfl_sync(0xffffffffu, bin, owner);
+  below = __shfl_sync(0xffffffffu, below, owner);
+  *below_out = below;
+  return bin;
+}
+
+__global__ void __launch_bounds__(kRowsThreads) k1mr_select_kernel(const RowsParams P, const int64_t cols_left) {
+  // level 1: one histogram per column; level 2: one per (column, target rank)
+  extern __shared__ unsigned int rows_hist[];            // [kRowsGroup][2][kRowsMaxBins]
+  __shared__ int s_bin[kRowsGroup][2];
+  __shared__ long long s_krem[kRowsGroup][2];
+  __shared__ int s_pos[kRowsGroup][2];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int64_t set = blockIdx.x;
+  const int64_t d0 = (int64_t)blockIdx.y * kRowsGroup;
+  const int nc = (int)min((int64_t)kRowsGroup, cols_left - d0);
+  const int64_t* idx = P.indices + set * P.n_rows;
+  const int lo_bins = 1 << P.shift;
+  const unsigned int lo_mask = (unsigned int)lo_bins - 1u;
+  const int two = P.rule.k_hi != P.rule.k_lo ? 1 : 0;
+  auto h1 = [&](int c) { return rows_hist + (size_t)c * 2 * kRowsMaxBins; };
+  auto h2 = [&](int c, int t) { return rows_hist + ((size_t)c * 2 + t) * kRowsMaxBins; };
+
+  for (int i = tid; i < nc * 2 * kRowsMaxBins; i += kRowsThreads) rows_hist[i] = 0u;
+  __syncthreads();
+  for (int64_t j = tid; j < P.n_rows; j += kRowsThreads) {
+    const int64_t i = idx[j];
+    if ((uint64_t)i >= (uint64_t)P.n_rows) continue;           // out-of-range entries are ignored
+    const int32_t* r = P.rank + i * P.n_cols + d0;
+    for (int c = 0; c < nc; ++c) atomicAdd(h1(c) + ((unsigned int)__ldg(r + c) >> P.shift), 1u);
+  }
+  __syncthreads();
+  if (warp < nc * 2) {
+    const int c = warp >> 1, t = warp & 1;
+    long long below;
+    const long long k = t ? P.rule.k_hi : P.rule.k_lo;
+    const int bin = rows_find_bin(h1(c), P.hi_bins, k, &below);
+    if ((tid & 31) == 0) {
+      s_bin[c][t] = bin;
+      s_krem[c][t] = k - below;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < nc * 2 * kRowsMaxBins; i += kRowsThreads) rows_hist[i] = 0u;
+  __syncthreads();
+  for (int64_t j = tid; j < P.n_rows; j += kRowsThreads) {
+    const int64_t i = idx[j];
+    if ((uint64_t)i >= (uint64_t)P.n_rows) continue;
+    const int32_t* r = P.rank + i * P.n_cols + d0;
+    for (int c = 0; c < nc; ++c) {
+      const unsigned int p = (unsigned int)__ldg(r + c);
+      const int hb = (int)(p >> P.shift);
+      if (hb == s_bin[c][0]) atomicAdd(h2(c, 0) + (p & lo_mask), 1u);
+      if (two && hb == s_bin[c][1]) atomicAdd(h2(c, 1) + (p & lo_mask), 1u);
+    }
+  }
+  __syncthreads();
+  if (warp < nc * 2) {
+    const int c = warp >> 1, t = warp & 1;
+    if (t == 0 || two) {
+      long long below;
+      const int bin = rows_find_bin(h2(c, t), lo_bins, s_krem[c][t], &below);
+      if ((tid & 31) == 0) s_pos[c][t] = (s_bin[c][t] << P.shift) | bin;
+    }
+  }
+  __syncthreads();
+  if (tid < nc) {
+    const double* col = P.sorted + (d0 + tid) * P.n_rows;
+    const double a = col[s_pos[tid][0]];
+    const double b = two ? col[s_pos[tid][1]] : a;
+    P.out[(d0 + tid) * P.out_ld + set] = rank_combine(P.rule, a, b);
+  }
+}
+
+inline size_t rows_smem_bytes() { return (size_t)kRowsGroup * 2 * kRowsMaxBins * sizeof(unsigned int); }
+
+}  // namespace b200boot

@@ -345,26 +345,57 @@ def test_long_quantile_runs_in_rank_space(n):
         assert_array_equal(got, ref)
 
 
-def test_long_median_over_columns():
-    """(N, D) data with more rows than the resident limit: every column is resampled in its
-    own rank space with the same index sets, so column d equals the 1-D run on data[:, d]."""
+@pytest.mark.parametrize("n,d,q", [(30001, 3, None), (28673, 5, None), (40000, 2, 0.9), (65536, 9, 0.25)])
+def test_long_median_over_columns_is_row_aligned(n, d, q):
+    """(N, D) data with more rows than K1m's resident limit stay in row space (K1mr): every
+    resample gathers whole rows, x[indices] (bootstrap.py:431), so the returned distribution
+    holds the oracle's joint rows on the materialised indices, for medians and quantiles."""
     import warnings
-    rng = np.random.default_rng(12)
-    data = rng.standard_normal((30001, 3))
-    data[:, 1] = np.round(data[:, 1], 2)
-    m = 300
+    rng = np.random.default_rng(n + d)
+    data = rng.standard_normal((n, d))
+    data[:, 1] = np.round(data[:, 1], 2 if q is None else 5)   # ties in one column (heavy for the median)
+    f = boot.median_axis0 if q is None else boot.quantile_axis0(q)
+    host = (lambda x: np.median(x, axis=0)) if q is None else (lambda x: np.quantile(x, q, axis=0))
+    jack1 = orc.jack_median if q is None else (lambda c: orc.jack_quantile(c, q))
+    m = 120
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        out, dist = boot.ci(data, boot.median_axis0, n_samples=m, seed=5, return_dist=True)
-        eb = boot.ci(dev(data), functools.partial(np.median, axis=0), n_samples=m, seed=5, output="errorbar")
-        p = boot.pval(data, boot.median_axis0, boot.greater_than(0.005), n_samples=m, seed=5)
-        assert out.shape == (2, 3) and dist.shape == (m, 3) and eb.shape == (3, 2)
-        for d in range(3):
-            o1, d1 = boot.ci(data[:, d], np.median, n_samples=m, seed=5, return_dist=True)
-            assert_array_equal(out[:, d], o1)
-            assert_array_equal(dist[:, d], d1)
-            assert_array_equal(eb[d], np.abs(np.median(data[:, d]) - o1))
-            assert p[d] == (d1 > 0.005).mean()
+        out, dist = boot.ci(data, f, n_samples=m, seed=5, return_dist=True)
+        idx = np.array(list(boot.bootstrap_indices(data, m, seed=5)))
+        want = np.stack([host(data[i]) for i in idx])
+        assert_array_equal(dist, np.sort(want, axis=0))
+        jst = np.stack([jack1(data[:, c]) for c in range(d)], axis=1)
+        ref = orc.ci_from_indices((data,), host, idx, (0.025, 0.975), m, "bca", jstat=jst)
+        # a column whose leave-one-out values are all equal (heavy ties) has no acceleration: the
+        # device says NaN exactly, the reference is at the mercy of np.mean's rounding (DESIGN 5)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            defined = [c for c in range(d) if np.isfinite(orc.acceleration(jst[:, c]))]
+        assert 0 in defined
+        assert_array_equal(out[:, defined], ref[:, defined])
+        eb = boot.ci(dev(data), f, n_samples=m, seed=5, output="errorbar")
+        assert_array_equal(eb, np.abs(host(data) - out).T)
+        p = boot.pval(data, f, boot.greater_than(0.005), n_samples=m, seed=5)
+        assert_array_equal(p, (want > 0.005).mean(axis=0))
+        # the joint rows are rows of ONE resample: the unsorted statistic vectors line up
+        # (column c's vector equals the row-space statistic of that column alone)
+        run_idx = boot.ci_indexed(data[:, 0], np.median if q is None else boot.quantile(q), indices=idx,
+                                  method="pi", return_dist=True)[1]
+        assert_array_equal(run_idx, np.sort(want[:, 0]))
+
+
+def test_long_median_index_supplied():
+    """Index-supplied (parity) mode beyond the resident limit: the reference's own PCG64 index
+    sets, 1-D and (N, D) data."""
+    n, m = 30011, 60
+    rng = np.random.default_rng(8)
+    x = rng.gamma(2.0, 1.0, n)
+    idx = np.array(list(orc.bootstrap_indices_pcg64(n, m, 21)))
+    want = np.sort(np.array([np.median(x[i]) for i in idx]))
+    out, dist = boot.ci_indexed(x, np.median, indices=idx, method="pi", return_dist=True)
+    assert_array_equal(dist, want)
+    data = np.stack([x, -x, np.round(x, 1)], axis=1)
+    out, dist = boot.ci_indexed(data, boot.median_axis0, indices=idx, method="pi", return_dist=True)
+    assert_array_equal(dist, np.sort(np.stack([np.median(data[i], axis=0) for i in idx]), axis=0))
 
 
 def test_fused_median_columns_share_the_index_set():
