@@ -266,6 +266,14 @@ int b200boot_ci_small(const double* const* data, int n_arrays, int64_t n_rows, i
                       int64_t n_samples, const double* alphas, int n_alphas, int bca, int need_jack,
                       double* stat_out, double* result_dev, double* result_host, void* ws, size_t ws_bytes,
                       void* stream);
+/* The tail of b200boot_ci_small as its own launch, for a statistic vector of any origin (K1 of
+ * the general path, a gathered sharded vector), n_samples <= 2^21: #{stat < jack[0]}
+ * (bootstrap.py:583), speculative BCa levels and ranks, exact order statistics — one CTA, the
+ * 32-double result block of b200boot_ci_small (jack: the 8 doubles b200boot_jackknife wrote, on
+ * the device; may be NULL when bca == 0).  result_dev: 32 doubles; result_host as above. */
+int b200boot_ci_tail_supported(int64_t n_samples, int n_alphas);
+int b200boot_ci_tail(const double* stat, int64_t n_samples, const double* jack, const double* alphas, int n_alphas,
+                     int bca, double* result_dev, double* result_host, void* stream);
 /* The same from HOST rows (float64, contiguous): each array is copied into the caller's pinned
  * `staging[a]`, from there to the caller's device rows `data_dev[a]` (both >= n_rows doubles) on
  * `stream`, the kernel follows, and the call returns after cudaStreamSynchronize: result_host

@@ -347,6 +347,32 @@ def ci_small(arrays: Sequence, stat_id: int, seed: int, n_samples: int, alphas: 
     return (ent.stat[:n_samples], r[:na].copy(), r[8:8 + na].astype(np.int64), int(r[16]), r[17:25].copy())
 
 
+def ci_tail_supported(n_samples: int, n_alphas: int) -> bool:
+    return 1 <= n_samples <= (1 << 21) and 1 <= n_alphas <= 8
+
+
+def ci_tail(stat, jack_dev, alphas: np.ndarray, bca: bool):
+    """The single-CTA tail over a statistic vector already on the device (float64[n] CUDA,
+    contiguous): returns (endpoints[A], ranks[A] int64, less, jack[8]) after one host wait;
+    ranks are the device's speculative ones.  jack_dev: float64[8] CUDA (K3 output) or None."""
+    L = _abi.lib()
+    a = np.ascontiguousarray(alphas, dtype=np.float64).reshape(-1)
+    na = len(a)
+    n = stat.numel()
+    ent = _small.get(1)
+    for i in range(na):
+        ent.alphas[i] = a[i]
+    s = stream_ptr()
+    rc = L.b200boot_ci_tail(stat.data_ptr(), n, jack_dev.data_ptr() if jack_dev is not None else None,
+                            ent.alphas_ptr, na, int(bca), ent.res_dev_ptr, ent.res_host_ptr, s)
+    if rc:
+        _abi.check(rc)
+    _sync_stream(s)
+    TRAFFIC["d2h"] += 32 * 8
+    r = ent.res_np
+    return r[:na].copy(), r[8:8 + na].astype(np.int64), int(r[16]), r[17:25].copy()
+
+
 def _sync_stream(stream: int) -> None:
     """The one host wait of a small call: cudaStreamSynchronize through the library (a few
     microseconds cheaper than building torch's stream object)."""

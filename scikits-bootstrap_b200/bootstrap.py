@@ -307,6 +307,29 @@ class _Run:
         self._spec = (ranks.reshape(-1, 1), vals.reshape(-1, 1))
         return stat.reshape(1, -1)
 
+    def tail_call(self, stat, alphas: np.ndarray, bca: bool, need_jack: bool) -> None:
+        """Scalar statistics with a moderately long vector (cfg5: 1e5 values; a sharded run's
+        gathered vector): the jackknife summary stays on the device and ONE single-CTA launch
+        counts stat < ostat, forms speculative levels and ranks and selects the order
+        statistics; one 256-byte block comes back (instead of count -> host -> 8 radix passes ->
+        host).  `select` verifies the ranks against the host's, as for the small call."""
+        if (self.n_cols != 1 or self.vector or (_dist.active() and not self._local) or self._spec is not None
+                or stat.shape[0] != 1):
+            return
+        n_alphas = int(np.prod(alphas.shape)) if alphas.ndim else 1
+        if not _device.ci_tail_supported(stat.shape[1], n_alphas):
+            return
+        jd = None
+        if need_jack:
+            if self._jack is not None:
+                return                                   # already on the host: the general tail is as short
+            jd = self._jackknife_tensor().reshape(-1)
+        vals, ranks, less, jack = _device.ci_tail(stat.reshape(-1), jd, alphas, bca)
+        if need_jack:
+            self._jack = jack.reshape(1, 8)
+            self._less = np.array([less], dtype=np.int64)
+        self._spec = (ranks.reshape(-1, 1), vals.reshape(-1, 1))
+
     # -- K1i ---------------------------------------------------------------------
     def _resample_indexed(self):
         """Parity mode: gathers with the caller's index sets (e.g. the reference's own
@@ -742,6 +765,8 @@ def _ci_on_device(spec, arrays, multi, n_samples, key, indices, alphas, method, 
         stat = run.small_call(alphas, method == "bca", method == "bca" or output == "errorbar")
     if stat is None:
         stat = run.gather_small(run.resample())                   # float64[D][n_local]
+        if not return_dist:
+            run.tail_call(stat, alphas, method == "bca", method == "bca" or output == "errorbar")
     return _ci_tail(run, stat, alphas, n_samples, method, output, return_dist, 5)
 
 

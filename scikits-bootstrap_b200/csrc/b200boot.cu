@@ -547,6 +547,7 @@ int enqueue_ci_small(const double* const* data, int n_arrays, int64_t n_rows, in
   P.tail.bca = bca ? 1 : 0;
   P.tail.res = result_dev;
   P.tail.staged = n_samples <= kFusedStageMax ? 1 : 0;
+  P.tail.n_bins = kBktBins;
   const size_t cell = (size_t)P.smem_stride * 8 * n_arrays;
   const size_t tail = (P.tail.staged ? tail_stage_bytes(n_samples) : 0) + tail_scratch_bytes();
   const size_t smem = std::max(cell, tail);
@@ -576,6 +577,41 @@ int b200boot_ci_small(const double* const* data, int n_arrays, int64_t n_rows, i
                       void* stream) {
   return enqueue_ci_small(data, n_arrays, n_rows, stat_id, seed, n_samples, alphas, n_alphas, bca, need_jack,
                           stat_out, result_dev, result_host, ws, ws_bytes, as_stream(stream));
+}
+
+int b200boot_ci_tail_supported(int64_t n_samples, int n_alphas) {
+  return n_samples >= 1 && n_samples <= kTailMaxValues && n_alphas >= 1 && n_alphas <= kSelMaxAlphas ? 1 : 0;
+}
+
+int b200boot_ci_tail(const double* stat, int64_t n_samples, const double* jack, const double* alphas, int n_alphas,
+                     int bca, double* result_dev, double* result_host, void* stream) {
+  if (!stat || !alphas || !result_dev || (bca && !jack)) return fail(B200BOOT_EINVAL, "ci_tail: null pointer");
+  if (!b200boot_ci_tail_supported(n_samples, n_alphas))
+    return fail(B200BOOT_EUNSUPPORTED, "ci_tail: 1 <= n_samples <= 2^21, 1 <= n_alphas <= 8");
+  cudaStream_t s = as_stream(stream);
+  SmallTailParams P{};
+  P.stat = stat;
+  P.n_samples = n_samples;
+  P.jack = jack;
+  for (int a = 0; a < n_alphas; ++a) P.alphas[a] = alphas[a];
+  P.n_alphas = n_alphas;
+  P.bca = bca ? 1 : 0;
+  P.res = result_dev;
+  P.staged = n_samples <= kFusedStageMax ? 1 : 0;
+  P.n_bins = P.staged ? kBktBins : kBktBinsWide;
+  const size_t smem = (P.staged ? tail_stage_bytes(n_samples) : 0) + tail_scratch_bytes(P.n_bins);
+  static PerDeviceOnce configured;
+  B2_CUDA(configured.run([] {
+    return cudaFuncSetAttribute(ci_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)std::max(tail_stage_bytes(kFusedStageMax) + tail_scratch_bytes(kBktBins),
+                                              tail_scratch_bytes(kBktBinsWide)));
+  }));
+  double* host_view = device_view_of_pinned(result_host);
+  ci_tail_kernel<<<1, kSmallThreads, smem, s>>>(P, host_view);
+  B2_LAUNCH_CHECK();
+  if (result_host && host_view == nullptr)
+    B2_CUDA(cudaMemcpyAsync(result_host, result_dev, kSmallResultDoubles * sizeof(double), cudaMemcpyDeviceToHost, s));
+  return 0;
 }
 
 int b200boot_ci_small_host(const double* const* host_data, double* const* staging, double* const* data_dev,

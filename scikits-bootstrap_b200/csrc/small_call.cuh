@@ -115,6 +115,7 @@ struct SmallTailParams {
   int n_alphas;
   int bca;                // 1: BCa levels, 0: the alphas themselves
   int staged;             // the statistic vector is copied to shared memory first
+  int n_bins;             // buckets of the select: kBktBins (staged) or kBktBinsWide
   double* res;
 };
 
@@ -142,7 +143,9 @@ struct SmallTailParams {
 // 64-step bit descent 36-48 us, quickselect 100 us) = 98 us of device time per call; this
 // kernel: 42 us (launch + row load ~24 us with an empty statistic vector, ~5 us per round of
 // 4704 resamples, the rest the tail).
-constexpr int kBktBins = 4096;
+constexpr int kBktBins = 4096;                  // buckets when the vector is staged next to them
+constexpr int kBktBinsWide = 32768;             // long (unstaged) vectors: 128 KB of buckets
+constexpr int64_t kTailMaxValues = (int64_t)1 << 21;   // single-CTA tail up to here
 constexpr int kBktCand = 256;                   // candidates kept per rank; more -> radix descent
 constexpr int64_t kFusedStageMax = 16384;       // statistic vectors up to here are staged (128 KB)
 constexpr int64_t kFusedMaxCellDoubles = 28672; // rows x arrays resident (224 KB), K1's single-cell limit
@@ -170,13 +173,13 @@ struct TailScratch {
   unsigned int (*hist2)[256];               // [kSelMaxAlphas][256]: radix descent
 };
 inline __host__ __device__ size_t tail_stage_bytes(int64_t n) { return ((size_t)n * 8 + 15) & ~(size_t)15; }
-inline __host__ __device__ size_t tail_scratch_bytes() {
-  return (size_t)kBktBins * 4 + (size_t)kSelMaxAlphas * kBktCand * 8 + (size_t)kSelMaxAlphas * 256 * 4;
+inline __host__ __device__ size_t tail_scratch_bytes(int n_bins = kBktBins) {
+  return (size_t)n_bins * 4 + (size_t)kSelMaxAlphas * kBktCand * 8 + (size_t)kSelMaxAlphas * 256 * 4;
 }
 
-__device__ __forceinline__ int bucket_of(double v, double lo, double scale) {
+__device__ __forceinline__ int bucket_of(double v, double lo, double scale, int n_bins) {
   const int b = (int)((v - lo) * scale);    // v >= lo: non-negative, monotone in v
-  return b < kBktBins - 1 ? b : kBktBins - 1;
+  return b < n_bins - 1 ? b : n_bins - 1;
 }
 
 // All 1024 threads of one CTA.  `smem`: (staged ? n doubles : 0) + tail_scratch_bytes().
@@ -197,8 +200,9 @@ __device__ __noinline__ void small_tail_bucket(const SmallTailParams& P, unsigne
   unsigned char* scratch = smem + (P.staged ? tail_stage_bytes(n) : 0);
   TailScratch T;
   T.hist = reinterpret_cast<unsigned int*>(scratch);
-  T.cand = reinterpret_cast<uint64_t*>(scratch + (size_t)kBktBins * 4);
-  T.hist2 = reinterpret_cast<unsigned int(*)[256]>(scratch + (size_t)kBktBins * 4 + (size_t)kSelMaxAlphas * kBktCand * 8);
+  const int n_bins = P.n_bins;                 // a multiple of 4 * kSmallThreads
+  T.cand = reinterpret_cast<uint64_t*>(scratch + (size_t)n_bins * 4);
+  T.hist2 = reinterpret_cast<unsigned int(*)[256]>(scratch + (size_t)n_bins * 4 + (size_t)kSelMaxAlphas * kBktCand * 8);
 
   // pass A: stage, min / max of the non-NaN values, NaN count, #{stat < ostat}
   const double ostat = P.bca ? __ldcg(P.jack) : 0.0;
@@ -215,7 +219,7 @@ __device__ __noinline__ void small_tail_bucket(const SmallTailParams& P, unsigne
     }
     less += (P.bca && v < ostat) ? 1u : 0u;                          // strict '<'  bootstrap.py:583
   }
-  for (int i = tid; i < kBktBins; i += kSmallThreads) T.hist[i] = 0u;
+  for (int i = tid; i < n_bins; i += kSmallThreads) T.hist[i] = 0u;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, off));
@@ -269,17 +273,22 @@ __device__ __noinline__ void small_tail_bucket(const SmallTailParams& P, unsigne
 
   // bucket select
   const double range = hi - lo;
-  const double scale = (double)kBktBins / range;
+  const double scale = (double)n_bins / range;
   const bool fast = hi > lo && isfinite(range) && isfinite(scale) && isfinite(lo);
   if (fast) {
     for (int64_t r = tid; r < n; r += kSmallThreads) {
       const double v = P.staged ? stat[r] : __ldcg(stat + r);
-      if (v == v) atomicAdd(&T.hist[bucket_of(v, lo, scale)], 1u);
+      if (v == v) atomicAdd(&T.hist[bucket_of(v, lo, scale, n_bins)], 1u);
     }
     __syncthreads();
-    // exclusive scan over the buckets: thread t owns buckets 4t .. 4t + 3
-    const uint4 h4 = reinterpret_cast<const uint4*>(T.hist)[tid];
-    const unsigned int mine = h4.x + h4.y + h4.z + h4.w;
+    // exclusive scan over the buckets: thread t owns the `per` consecutive buckets from t * per
+    const int per = n_bins / kSmallThreads;
+    const uint4* mine4 = reinterpret_cast<const uint4*>(T.hist + (size_t)tid * per);
+    unsigned int mine = 0;
+    for (int g = 0; g < per / 4; ++g) {
+      const uint4 h4 = mine4[g];
+      mine += h4.x + h4.y + h4.z + h4.w;
+    }
     unsigned int inc = mine;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -291,20 +300,20 @@ __device__ __noinline__ void small_tail_bucket(const SmallTailParams& P, unsigne
     unsigned int base = 0;
     for (int w = 0; w < warp; ++w) base += s_scan[w];
     const long long below0 = (long long)base + (long long)(inc - mine);
-    const unsigned int hs[4] = {h4.x, h4.y, h4.z, h4.w};
     for (int a = 0; a < A; ++a) {
       const long long k = s_rank[a];
       if (k >= n - (long long)nans) {                  // a NaN is asked for: radix descent
         if (tid == 0) s_slow = 1;
       } else if (k >= below0 && k < below0 + (long long)mine) {
         long long below = below0;
-        for (int b = 0; b < 4; ++b) {
-          if (k < below + (long long)hs[b]) {
-            s_bucket[a] = tid * 4 + b;
+        for (int b = 0; b < per; ++b) {
+          const long long c = T.hist[(size_t)tid * per + b];
+          if (k < below + c) {
+            s_bucket[a] = tid * per + b;
             s_krem[a] = k - below;
             break;
           }
-          below += hs[b];
+          below += c;
         }
       }
     }
@@ -314,7 +323,7 @@ __device__ __noinline__ void small_tail_bucket(const SmallTailParams& P, unsigne
       for (int64_t r = tid; r < n; r += kSmallThreads) {
         const double v = P.staged ? stat[r] : __ldcg(stat + r);
         if (v != v) continue;
-        const int b = bucket_of(v, lo, scale);
+        const int b = bucket_of(v, lo, scale, n_bins);
         for (int a = 0; a < A; ++a)
           if (b == s_bucket[a]) {
             const unsigned int pos = atomicAdd(&s_ccnt[a], 1u);
@@ -358,6 +367,14 @@ __device__ __noinline__ void small_tail_bucket(const SmallTailParams& P, unsigne
     if (res_host) res_host[tid] = s_val[tid];
   }
   if (res_host) __threadfence_system();
+}
+
+// The tail as its own launch, for statistic vectors of any origin (the general path's K1, a
+// gathered sharded vector) up to kTailMaxValues values: one CTA, one result block, one host wait
+// instead of count -> host -> 8 x (hist + pick) -> host.
+__global__ void __launch_bounds__(kSmallThreads, 1) ci_tail_kernel(const SmallTailParams P, double* res_host) {
+  extern __shared__ __align__(128) unsigned char tail_smem[];
+  small_tail_bucket(P, tail_smem, res_host);
 }
 
 // Closed-form jackknife of the resident rows by the whole CTA (the passes of k3_small_kernel).

@@ -666,6 +666,50 @@ def test_small_call_is_reentrant_on_its_buffers():
             assert_array_equal(boot.ci(x, np.mean, n_samples=n, seed=9), want[n])
 
 
+@pytest.mark.parametrize("stat_name,n,n_arrays", [("mean", 40000, 1), ("std", 30000, 1), ("median", 3000, 1),
+                                                  ("median", 40000, 1), ("ratio_of_means", 20000, 2),
+                                                  ("mean", 500, 1)])
+def test_single_launch_tail_equals_general_tail(stat_name, n, n_arrays, monkeypatch):
+    """Scalar statistics outside the small-call shape finish with ONE single-CTA launch (count,
+    speculative levels and ranks, bucket select over up to 2^21 values) whose ranks the host
+    verifies; the interval must be what the count / radix-select launches give."""
+    import warnings
+    rng = np.random.default_rng(n)
+    arrays = tuple(rng.gamma(2, 1, n) + 0.25 * k for k in range(n_arrays))
+    data = arrays if n_arrays > 1 else arrays[0]
+    f = DEVICE_STATS[stat_name]
+    kws = [dict(method="bca", n_samples=50000), dict(method="pi", n_samples=40000, output="errorbar"),
+           dict(method="bca", n_samples=33000, alpha=(0.001, 0.01, 0.1, 0.3, 0.5, 0.7, 0.9, 0.999)),
+           dict(method="bca", n_samples=70001, output="errorbar")]
+    calls = []
+    real = _device.ci_tail
+    monkeypatch.setattr(_device, "ci_tail", lambda *a, **k: calls.append(1) or real(*a, **k))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        one = [boot.ci(data, f, seed=4, **k) for k in kws]
+        assert len(calls) == len(kws)
+        monkeypatch.setattr(_device, "ci_tail_supported", lambda *a: False)
+        general = [boot.ci(data, f, seed=4, **k) for k in kws]
+        assert len(calls) == len(kws)
+    for a, b in zip(one, general):
+        assert_array_equal(a, b)
+
+
+def test_single_launch_tail_degenerate_vectors(monkeypatch):
+    import warnings
+    rng = np.random.default_rng(2)
+    cases = [np.ones(40000), np.r_[rng.standard_normal(39999), np.nan], rng.integers(0, 2, 40000).astype(float),
+             np.r_[rng.standard_normal(39999), np.inf]]
+    for x in cases:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            a = boot.ci(x, np.mean, n_samples=40000, seed=1)
+            monkeypatch.setattr(_device, "ci_tail_supported", lambda *a: False)
+            b = boot.ci(x, np.mean, n_samples=40000, seed=1)
+            monkeypatch.undo()
+        assert_array_equal(a, b)
+
+
 def test_small_call_wrong_speculative_ranks_are_caught(monkeypatch):
     """The device's ranks are only a guess: when the host's own levels give other ranks the
     order statistics are selected again with the host's."""
