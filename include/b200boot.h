@@ -407,6 +407,12 @@ int b200boot_profile_last_k1_ms(float* ms);
 /* the occupancy kernels (K0) and the K1 launch of the calling thread's last resample call */
 int b200boot_profile_last_ms(float* k0_ms, float* k1_ms);
 
+/* The reference's normal cdf (bootstrap.py:72-76: np.vectorize of 0.5 * (1 + math.erf(x / sqrt(2))))
+ * over an array on the HOST, with the C library's erf — the function math.erf calls — so the
+ * values equal the reference's bit for bit without a Python-level loop (a BCa tail over 10^4
+ * columns evaluates 2 x 10^4 levels).  x, out: host float64[n]; may alias. */
+void b200boot_host_ncdf(const double* x, double* out, int64_t n);
+
 /* Host-side probes built from the same __host__ __device__ sources as the
  * kernels (no GPU needed); used by the CPU test-suite only. */
 void b200boot_host_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);   /* 10 rounds */

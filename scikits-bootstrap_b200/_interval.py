@@ -97,9 +97,17 @@ def _nppf_array(p: np.ndarray) -> np.ndarray:
 
 
 def ncdf(x) -> np.ndarray:
-    """Standard-normal cdf through math.erf, element by element."""
+    """Standard-normal cdf as the reference evaluates it (np.vectorize over math.erf,
+    bootstrap.py:72-76): a handful of values go through math.erf, arrays through the library's
+    host loop over the C library's erf — the very function math.erf calls, so the bits are the
+    same (tests/test_host_probes.py compares the two paths)."""
     x = np.asarray(x, dtype=float)
     out = np.empty(x.shape)
+    if x.size > _SCALAR_LIMIT:
+        from . import _abi
+        xc = np.ascontiguousarray(x)
+        _abi.lib().b200boot_host_ncdf(xc.ctypes.data, out.ctypes.data, xc.size)
+        return out
     oi = out.reshape(-1)
     for i, v in enumerate(x.reshape(-1)):
         oi[i] = 0.5 * (1 + math.erf(v / _INV_SQRT2_DIV))

@@ -116,6 +116,9 @@ struct SmallTailParams {
   int bca;                // 1: BCa levels, 0: the alphas themselves
   int staged;             // the statistic vector is copied to shared memory first
   int n_bins;             // buckets of the select: kBktBins (staged) or kBktBinsWide
+  const int64_t* ranks;   // select-only mode: the ranks are given (stride rank_stride), no count / levels
+  int64_t rank_stride;
+  int64_t res_stride;     // res[a * res_stride] (select-only mode; the tail writes its block densely)
   double* res;
 };
 
@@ -246,8 +249,13 @@ __device__ __noinline__ void small_tail_bucket(const SmallTailParams& P, unsigne
   const double* stat = P.staged ? s_stat : P.stat;
   const double* jack = P.jack;
 
-  // speculative levels and ranks (the host verifies them)
-  if (tid < A) {
+  if (P.ranks != nullptr) {
+    if (tid < A) {
+      const long long r = (long long)__ldg(P.ranks + tid * P.rank_stride);
+      s_rank[tid] = r < 0 ? 0 : (r > (long long)(n - 1) ? (long long)(n - 1) : r);
+    }
+  } else if (tid < A) {
+    // speculative levels and ranks (the host verifies them)
     double aval = P.alphas[tid];
     if (P.bca) {
       const double z0 = dev_nppf((1.0 * (double)less) / (double)n);
@@ -261,11 +269,11 @@ __device__ __noinline__ void small_tail_bucket(const SmallTailParams& P, unsigne
     P.res[8 + tid] = v;
     if (res_host) res_host[8 + tid] = v;
   }
-  if (tid == 0) {
+  if (tid == 0 && P.ranks == nullptr) {
     P.res[16] = (double)less;
     if (res_host) res_host[16] = (double)less;
   }
-  if (tid < 8 && jack) {
+  if (tid < 8 && jack && P.ranks == nullptr) {
     const double j = __ldcg(jack + tid);
     P.res[17 + tid] = j;
     if (res_host) res_host[17 + tid] = j;
@@ -363,7 +371,7 @@ __device__ __noinline__ void small_tail_bucket(const SmallTailParams& P, unsigne
     __syncthreads();
   }
   if (tid < A) {
-    P.res[tid] = s_val[tid];
+    P.res[P.ranks != nullptr ? tid * P.res_stride : (int64_t)tid] = s_val[tid];
     if (res_host) res_host[tid] = s_val[tid];
   }
   if (res_host) __threadfence_system();
@@ -375,6 +383,33 @@ __device__ __noinline__ void small_tail_bucket(const SmallTailParams& P, unsigne
 __global__ void __launch_bounds__(kSmallThreads, 1) ci_tail_kernel(const SmallTailParams P, double* res_host) {
   extern __shared__ __align__(128) unsigned char tail_smem[];
   small_tail_bucket(P, tail_smem, res_host);
+}
+
+// K5 for tables of short columns (cfg4: 10^4 columns of 10^4 values): one CTA per column runs
+// the bucket select with the caller's ranks — three passes over the column instead of the eight
+// of the radix descent.  out[(a_lo + a) * n_cols + d].
+__global__ void __launch_bounds__(kSmallThreads, 1) k5_select_bucket_kernel(const double* __restrict__ stat, int64_t n,
+                                                                          int64_t n_cols,
+                                                                          const int64_t* __restrict__ ranks, int a_lo,
+                                                                          int a_cnt, int staged,
+                                                                          double* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char sel_smem[];
+  for (int64_t d = blockIdx.x; d < n_cols; d += gridDim.x) {
+    SmallTailParams P;
+    P.stat = stat + d * n;
+    P.n_samples = n;
+    P.jack = nullptr;
+    P.n_alphas = a_cnt;
+    P.bca = 0;
+    P.staged = staged;
+    P.n_bins = kBktBins;
+    P.ranks = ranks + (int64_t)a_lo * n_cols + d;
+    P.rank_stride = n_cols;
+    P.res = out + (int64_t)a_lo * n_cols + d;
+    P.res_stride = n_cols;
+    small_tail_bucket(P, sel_smem, nullptr);
+    __syncthreads();
+  }
 }
 
 // Closed-form jackknife of the resident rows by the whole CTA (the passes of k3_small_kernel).

@@ -527,3 +527,25 @@ def test_bca_levels_scalar_path_is_bit_equal_to_the_array_path():
     out = _interval.bca_levels(np.int64(0), 100, np.float64(0.01), np.array([0.025, 0.975]))
     assert np.isnan(out).all() or ((out == 0) | (out == 1) | np.isnan(out)).all()
     assert np.isnan(_interval.bca_levels(np.int64(10), 100, np.float64("nan"), np.array([0.5]))).all()
+
+
+def test_ncdf_array_path_equals_math_erf_bitwise():
+    """Arrays of levels go through the library's host loop over the C library's erf; a handful
+    of values through math.erf (the reference's np.vectorize(math.erf) path): same bits."""
+    import math
+    from scikits_bootstrap_b200 import _interval
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.standard_normal(50000) * 3, rng.standard_normal(20000) * 1e-3,
+                        rng.standard_normal(5000) * 40, [0.0, -0.0, np.inf, -np.inf, np.nan, 1e-320, -1e-320, 5.0, -5.0]])
+    got = _interval.ncdf(x)
+    want = np.array([0.5 * (1 + math.erf(v / math.sqrt(2))) for v in x.tolist()])
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    assert _interval.ncdf(x.reshape(-1, 3)[:200]).shape == (200, 3)
+    # and the BCa levels of many columns equal the per-column scalar path
+    less = rng.integers(1, 999, 500)
+    accel = rng.standard_normal(500) * 0.02
+    alphas = np.array([0.025, 0.975])
+    many = _interval.bca_levels(less, 1000, accel, alphas)
+    for d in (0, 17, 499):
+        one = _interval.bca_levels(less[d], 1000, accel[d], alphas)
+        assert np.array_equal(many[:, d].view(np.uint64), one.view(np.uint64))
