@@ -2,6 +2,7 @@
 // Host side only enqueues work on the caller's stream; all scratch comes from
 // the caller's workspace.
 #include <algorithm>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -13,6 +14,7 @@
 #include "k1mr_rows.cuh"
 #include "k6_gemm.cuh"
 #include "k6i_mma.cuh"
+#include "k6i_pipe.cuh"
 #include "k3_jackknife.cuh"
 #include "k45_interval.cuh"
 #include "small_call.cuh"
@@ -1328,11 +1330,69 @@ int launch_k6i(const K6iParams& P, cudaStream_t s) {
 }
 }  // namespace
 
+// image sizes of the pipelined contraction (k6i_pipe.cuh)
+inline int64_t k6i_a_image_tiles(int64_t m_total) { return (m_total + kI8M - 1) / kI8M; }
+inline size_t k6i_a_image_bytes(int64_t m_total, int64_t k_pad) {
+  return (size_t)k6i_a_image_tiles(m_total) * (size_t)(k_pad / kI8KChunk) * kI8AChunkBytes;
+}
+inline size_t k6i_b_image_bytes(int64_t n_col_tiles, int64_t k_pad) {
+  return (size_t)n_col_tiles * (size_t)(k_pad / kI8KChunk) * kI8BChunkBytes;
+}
+
+// The contraction through the warp-specialised pipeline: operands re-laid as tile images first.
+int launch_k6i_pipe(const K6iParams& P, unsigned char* a_img, unsigned char* b_img, cudaStream_t s) {
+  const int64_t m_tiles = (P.m_total + kI8M - 1) / kI8M;
+  const int n_kchunks = (int)(P.k_pad / kI8KChunk);
+  const int64_t a_tiles = k6i_a_image_tiles(P.m_total);
+  k6i_image_kernel<kI8M><<<blocks_for(a_tiles * kI8M * (P.k_pad / 16), 256, 148 * 16), 256, 0, s>>>(
+      P.counts, P.m_total, P.k_pad, a_tiles, a_img);
+  B2_LAUNCH_CHECK();
+  k6i_image_kernel<kI8N><<<blocks_for(P.n_col_tiles * kI8N * (P.k_pad / 16), 256, 148 * 16), 256, 0, s>>>(
+      reinterpret_cast<const unsigned char*>(P.digits), P.n_col_tiles * kI8N, P.k_pad, P.n_col_tiles, b_img);
+  B2_LAUNCH_CHECK();
+  const bool resident = n_kchunks <= kPipeMaxResidentChunks;
+  const size_t limit = 227 * 1024;
+  int n_stages = kPipeMaxStages;
+  while (n_stages > 2 && k6i_pipe_smem_bytes(n_kchunks, resident, n_stages) > limit) --n_stages;
+  const size_t smem = k6i_pipe_smem_bytes(n_kchunks, resident, n_stages);
+  if (smem > limit) return fail(B200BOOT_EUNSUPPORTED, "k6i pipeline: shared memory");
+  static PerDeviceOnce configured;
+  B2_CUDA(configured.run([] {
+    cudaError_t e = cudaFuncSetAttribute(k6i_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(k6i_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return e;
+  }));
+  K6iPipeParams Q{};
+  Q.a_img = a_img;
+  Q.b_img = b_img;
+  Q.scale = P.scale;
+  Q.m_total = P.m_total;
+  Q.m_tiles = m_tiles;
+  Q.n_kchunks = n_kchunks;
+  Q.n_stages = n_stages;
+  Q.n_cols = P.n_cols;
+  Q.n_col_tiles = P.n_col_tiles;
+  Q.out = P.out;
+  Q.out_ld = P.out_ld;
+  Q.out_i32 = P.out_i32;
+  Q.overflow = P.overflow;
+  Q.out_divisor = P.out_divisor;
+  const int grid = (int)std::min<int64_t>(sm_count(), m_tiles * P.n_col_tiles);
+  if (resident)
+    k6i_pipe_kernel<true><<<grid, kPipeThreads, smem, s>>>(Q);
+  else
+    k6i_pipe_kernel<false><<<grid, kPipeThreads, smem, s>>>(Q);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
 size_t b200boot_count_gemm_ws_bytes(int64_t n_rows, int64_t n_cols, int64_t n_local) {
   if (n_rows < 1 || n_cols < 1 || n_local < 0) return 0;
   const int64_t k_pad = k6i_k_pad(n_rows), cp = k6i_cols_pad(n_cols);
   return 4096 + pad256((size_t)cp * kI8Digits * k_pad) + 3 * pad256((size_t)cp * 8) +
-         pad256((size_t)std::max<int64_t>(n_local, 1) * k_pad);
+         pad256((size_t)std::max<int64_t>(n_local, 1) * k_pad) + pad256(k6i_a_image_bytes(std::max<int64_t>(n_local, 1), k_pad)) +
+         pad256(k6i_b_image_bytes(cp / kI8ColsPerTile, k_pad));
 }
 
 int b200boot_resample_stat_columns_gemm(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld,
@@ -1362,7 +1422,10 @@ int b200boot_resample_stat_columns_gemm(const double* data, int64_t n_rows, int6
   double* centre = cv.take<double>((size_t)cp);
   int32_t* bad_col = cv.take<int32_t>((size_t)cp * 2);
   uint8_t* counts = cv.take<uint8_t>((size_t)n_local * k_pad);
+  unsigned char* a_img = cv.take<unsigned char>(k6i_a_image_bytes(n_local, k_pad));
+  unsigned char* b_img = cv.take<unsigned char>(k6i_b_image_bytes(cp / kI8ColsPerTile, k_pad));
   if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+  static const bool use_pipe = getenv("B200BOOT_K6I_PIPE") == nullptr || atoi(getenv("B200BOOT_K6I_PIPE")) != 0;
   B2_CUDA(cudaMemsetAsync(flags, 0, 256, s));
   B2_CUDA(cudaMemsetAsync(bad_col, 0, (size_t)cp * 4, s));
   // the resamples' count matrix, once
@@ -1411,7 +1474,7 @@ int b200boot_resample_stat_columns_gemm(const double* data, int64_t n_rows, int6
     // the mean's division by N happens in the epilogue (the finisher's m[0] / cnt on the same
     // rounded sum: same bits), so mean and sum need no finisher pass over the output
     P.out_divisor = stat_id == kStatMean ? (double)n_rows : 1.0;
-    int rc = launch_k6i(P, s);
+    int rc = use_pipe ? launch_k6i_pipe(P, a_img, b_img, s) : launch_k6i(P, s);
     if (rc) return rc;
     k6i_fixup_kernel<<<(unsigned)std::min<int64_t>((n_local * 32 + 255) / 256, (int64_t)sm_count() * 8), 256, 0, s>>>(
         data, n_rows, n_cols, ld, c, pass, bad_col, flags + 1, seed, resample_lo, n_local, indices, P.out_divisor,
@@ -1444,7 +1507,20 @@ int b200boot_debug_i8_gemm(const uint8_t* a, const int8_t* b, int32_t* c, int64_
   P.out_i32 = c;
   P.overflow = nullptr;
   P.out_divisor = 1.0;
-  return launch_k6i(P, as_stream(stream));
+  if (getenv("B200BOOT_K6I_PIPE") != nullptr && atoi(getenv("B200BOOT_K6I_PIPE")) == 0)
+    return launch_k6i(P, as_stream(stream));                 // the first (unpipelined) form
+  // test hook only: the images live in memory of their own for the duration of the call
+  cudaStream_t s = as_stream(stream);
+  unsigned char *a_img = nullptr, *b_img = nullptr;
+  B2_CUDA(cudaMalloc(&a_img, k6i_a_image_bytes(m, k_pad)));
+  B2_CUDA(cudaMalloc(&b_img, k6i_b_image_bytes(P.n_col_tiles, k_pad)));
+  int rc = launch_k6i_pipe(P, a_img, b_img, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  cudaFree(a_img);
+  cudaFree(b_img);
+  if (rc) return rc;
+  B2_CUDA(e);
+  return 0;
 }
 
 // ---- instrumentation ---------------------------------------------------------------
