@@ -409,18 +409,25 @@ def resample_stat_columns(data2d, stat_id: int, seed: int, lo: int, hi: int):
     return out
 
 
-GEMM_MIN_COLS = 32           # below this the gather kernels win (K1c serves 32 columns per draw)
+GEMM_MIN_COLS = 64           # long data up to 2^18 rows: below this one K1 pass per column wins
+GEMM_MIN_COLS_HUGE = 1024    # longer data: the byte count matrix no longer fits L2
 
 
 def gemm_pays(n_rows: int, n_cols: int) -> bool:
-    """Measured crossover of the GEMM form against the gather kernels (mean, n = 2e4 resamples):
-    K6 is nearly flat in the number of columns, K1c grows in steps of 8 columns and with N.
-    One-cell data: from 8 columns on once N * D >= 20 000 (N = 7000: D = 8 -> 0.73 vs 1.19 ms;
-    N = 1000: D = 24 -> 0.20 vs 0.26 ms, D = 16 -> 0.19 vs 0.17 ms); longer data, where the
-    alternative is one K1 pass per column and the count matrix goes through K2: 32 columns."""
+    """Measured crossover of the GEMM form against the gather kernels (mean; B200).
+    One-cell data (K6i builds the count matrix itself; K1c is the alternative): from 8 columns on
+    once N * D >= 20 000 (N = 7000: D = 8 -> 0.73 vs 1.19 ms; N = 1000: D = 24 -> 0.20 vs
+    0.26 ms, D = 16 -> 0.19 vs 0.17 ms).  Longer data, where the alternative is one K1 pass per
+    column and the count matrix is built from the materialised indices of the tiled plan (an
+    atomic per draw on an n x N byte matrix, plus the index arrays through HBM):
+    tools/long_cols_crossover.py, n = 2000: N = 1e5: 0.2 ms per column against 10.1 ms + 0.02 ms
+    per column (crossover ~50 columns); N = 1e6: 0.83 ms per column against 640 ms (~770 columns:
+    the 2 GB count matrix is out of L2 and every draw is a DRAM read-modify-write)."""
     if n_rows <= MEDIAN_RESIDENT_ROWS:
         return n_cols >= 8 and n_rows * n_cols >= 20000
-    return n_cols >= GEMM_MIN_COLS
+    return n_cols >= (GEMM_MIN_COLS if n_rows <= (1 << 18) else GEMM_MIN_COLS_HUGE)
+
+
 _GEMM_COUNT_BYTES = 1 << 30  # count-matrix chunk
 
 

@@ -493,8 +493,9 @@ def test_registry_recognises_quantiles_fits_and_differences():
         reg.require(lambda v: v.mean())
     # which form serves (N, D) moment statistics: the measured crossover
     dev = _device_mod()
-    assert dev.gemm_pays(1000, 10000) and dev.gemm_pays(7000, 8) and dev.gemm_pays(100000, 32)
-    assert not dev.gemm_pays(1000, 16) and not dev.gemm_pays(7000, 4) and not dev.gemm_pays(100000, 31)
+    assert dev.gemm_pays(1000, 10000) and dev.gemm_pays(7000, 8) and dev.gemm_pays(100000, 64)
+    assert dev.gemm_pays(1000000, 1024) and not dev.gemm_pays(1000000, 1023)
+    assert not dev.gemm_pays(1000, 16) and not dev.gemm_pays(7000, 4) and not dev.gemm_pays(100000, 63)
 
 
 def _device_mod():
