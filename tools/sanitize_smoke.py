@@ -23,3 +23,18 @@ print(len(list(boot.bootstrap_indices(x, 3, seed=1))), boot.subsample_indices(x[
 idx = np.array(list(boot.bootstrap_indices(x[:500], 40, seed=2)))
 print(boot.ci_indexed(x[:500], np.var, idx), boot.ci_indexed(x[:500], np.median, idx))
 print(boot.ci(x[:20], method="abc"))
+# round-2 paths: fused small call (numpy and CUDA input), single-launch tail, row-space long
+# medians, K6i pipeline (resident and streamed count tile), moving-block plan, generic independent
+import torch
+print(boot.ci(x[:1000], np.mean, n_samples=2000, seed=3), boot.ci(torch.from_numpy(x[:1000]).cuda(), np.std, n_samples=300, seed=3))
+print(boot.ci((a[:3000], b[:3000]), boot.pearson_r, n_samples=500, seed=3))
+print(boot.ci(x, np.mean, n_samples=40000, seed=3, alpha=(0.01, 0.5, 0.99)))
+big = rng.standard_normal((29000, 5))
+print(boot.ci(big, boot.median_axis0, n_samples=40, seed=1, method="pi")[:, :2])
+print(boot.ci(big, boot.quantile_axis0(0.3), n_samples=40, seed=1, method="pi")[:, :2])
+wide = rng.standard_normal((1000, 300))
+print(boot.ci(wide, boot.mean_axis0, n_samples=300, seed=1, method="pi")[:, :2])
+tall = rng.standard_normal((1500, 40))
+print(boot.ci(tall, boot.std_axis0, n_samples=200, seed=1, method="pi")[:, :2])
+print(boot.ci_moving_block(x[:5000], np.mean, n_samples=100, block_length=7, seed=1))
+print(boot.ci((a[:600], b[:450]), boot.independent("div", np.mean, np.median), n_samples=200, seed=1, multi="independent"))
