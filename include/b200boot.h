@@ -209,6 +209,17 @@ int b200boot_median_rows_supported(int64_t n_rows);
 int b200boot_median_rows_indexed(const double* sorted_vals, const int32_t* rank, int64_t n_rows, int64_t n_cols,
                                  const int64_t* indices, int64_t n_sets, double* stat_out, int64_t out_ld,
                                  void* stream, const b200boot_rank_rule* rule);
+/* NaN propagation for rank statistics: np.median / np.quantile of a sample holding a NaN is NaN
+ * (so the reference's statistic is NaN for every resample that draws a NaN row), while the rank
+ * kernels order NaNs last.  Columns with NaNs are flagged (flags int32[n_cols + 1], the last entry
+ * = any) and patched afterwards: out[set] = NaN for every index set int64[n_sets][N] that holds a
+ * row i with src[i * stride] NaN; rows of a [n_cols][width] table (the jackknife summaries) of
+ * flagged columns become NaN. */
+int b200boot_nan_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, int32_t* flags,
+                         void* stream);
+int b200boot_nan_fixup(const double* src, int64_t stride, int64_t n_rows, const int64_t* indices, int64_t n_sets,
+                       double* out, void* stream);
+int b200boot_nan_poison_rows(double* table, int64_t n_cols, int width, const int32_t* flags, void* stream);
 /* K3m on a sorted 1-D array of any length: out float64[8] as b200boot_jackknife. */
 int b200boot_jackknife_median_sorted(const double* sorted_vals, int64_t n_rows, double* out, void* stream,
                                      const b200boot_rank_rule* rule);

@@ -74,6 +74,9 @@ SIGNATURES = {
     "b200boot_ci_tail_supported": (_int, [_i64, _int]),
     "b200boot_ci_tail": (_int, [_vp, _i64, _vp, _vp, _int, _int, _vp, _vp, _vp]),
     "b200boot_host_ncdf": (None, [_vp, _vp, _i64]),
+    "b200boot_nan_columns": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
+    "b200boot_nan_fixup": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "b200boot_nan_poison_rows": (_int, [_vp, _i64, _int, _vp, _vp]),
     "b200boot_ci_small_host": (_int, [_vp, _vp, _vp, _int, _i64, _int, _u64, _i64, _vp, _int, _int, _int, _vp, _vp, _vp,
                                       _vp, _sz, _vp]),
     "b200boot_tile_counts": (_int, [_u64, _i64, _int, _i64, _i64, _vp, _vp, _vp]),

@@ -565,6 +565,27 @@ def jackknife_median_sorted(sorted_vals, rule=None):
     return out
 
 
+def nan_columns(data2d):
+    """(flags int32[D + 1] CUDA tensor, host bool[D]): which columns of an (N, D) tensor hold NaNs."""
+    torch = _torch()
+    n_rows, n_cols = data2d.shape
+    flags = torch.empty(n_cols + 1, dtype=torch.int32, device=data2d.device)
+    _abi.check(_abi.lib().b200boot_nan_columns(data2d.data_ptr(), n_rows, n_cols, data2d.stride(0), flags.data_ptr(),
+                                               stream_ptr()))
+    return flags, to_host(flags)[:n_cols].astype(bool)
+
+
+def nan_fixup(src, stride: int, n_rows: int, indices, out_row):
+    """out_row[set] = NaN wherever indices[set] draws a NaN of src[:: stride]."""
+    _abi.check(_abi.lib().b200boot_nan_fixup(src.data_ptr(), stride, n_rows, indices.data_ptr(), indices.shape[0],
+                                             out_row.data_ptr(), stream_ptr()))
+
+
+def nan_poison_rows(table, flags):
+    n_cols, width = table.shape
+    _abi.check(_abi.lib().b200boot_nan_poison_rows(table.data_ptr(), n_cols, width, flags.data_ptr(), stream_ptr()))
+
+
 MEDIAN_ROWS_MAX = 1 << 24        # csrc/k1mr_rows.cuh: kRowsMaxRows
 
 

@@ -157,6 +157,7 @@ class _Run:
         self._parts = None
         self._jack_dev = None
         self._rows = None            # K1mr tables: (sorted [D][N], rank [N][D])
+        self._nan = None             # rank statistics: which columns hold NaNs
         self._local = False          # sharded run whose statistic vector was gathered: finish without collectives
         self._less = None            # small-call path: #{stat < ostat} and the speculative select
         self._spec = None
@@ -244,25 +245,7 @@ class _Run:
             a, b = (p.resample() for p in self.parts())
             return _device.combine(spec.op, a, b)
         if spec.stat_id == _abi.STAT_MEDIAN:
-            if self._row_space():
-                n_rows = self.dev[0].shape[0]
-                step = max(1, min(hi - lo, _ROWS_INDEX_BYTES // (8 * n_rows)))
-                batches = (_device.fill_indices(self.key, n_rows, 1, a, min(hi, a + step))
-                           for a in range(lo, hi, step))
-                return self._median_rows(batches, hi - lo)
-            if self._long_median():
-                cols = self._sorted()
-                out = torch.empty((self.n_cols, hi - lo), dtype=torch.float64, device=cols.device)
-                for d in range(self.n_cols):
-                    _device.resample_median_sorted(cols[d], self.key, lo, hi, out=out[d:d + 1], rule=self.rule)
-                return out
-            data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
-            if hi > lo:
-                # the columns are sorted for the resampling anyway: take the jackknife summary along
-                out, self._jack_dev = _device.resample_median_columns(data2d, self.key, lo, hi, rule=self.rule,
-                                                                      with_jackknife=True)
-                return out
-            return _device.resample_median_columns(data2d, self.key, lo, hi, rule=self.rule)
+            return self._propagate_nan(self._resample_rank_statistic(lo, hi), lo, hi)
         if spec.n_out > 1:
             return _device.resample_stat([a.reshape(-1) for a in self.dev], spec.stat_id, self.key, lo, hi)
         if (self.vector and _device.gemm_pays(self.dev[0].shape[0], self.n_cols) and hi > lo
@@ -280,6 +263,59 @@ class _Run:
             return out
         flat = [a.reshape(-1) for a in self.dev]
         return _device.resample_stat(flat, spec.stat_id, self.key, lo, hi, ready=ready).reshape(1, -1)
+
+    def _resample_rank_statistic(self, lo, hi):
+        """Median / quantile kernels (NaNs ordered last; _propagate_nan restores numpy's rule)."""
+        torch = _device._torch()
+        if self._row_space():
+            return self._median_rows(self._index_batches(lo, hi), hi - lo)
+        if self._long_median():
+            cols = self._sorted()
+            out = torch.empty((self.n_cols, hi - lo), dtype=torch.float64, device=cols.device)
+            for d in range(self.n_cols):
+                _device.resample_median_sorted(cols[d], self.key, lo, hi, out=out[d:d + 1], rule=self.rule)
+            return out
+        data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
+        if hi > lo:
+            # the columns are sorted for the resampling anyway: take the jackknife summary along
+            out, self._jack_dev = _device.resample_median_columns(data2d, self.key, lo, hi, rule=self.rule,
+                                                                  with_jackknife=True)
+            return out
+        return _device.resample_median_columns(data2d, self.key, lo, hi, rule=self.rule)
+
+    def _index_batches(self, lo, hi):
+        """The materialised draws of resamples [lo, hi) (K2), in batches of bounded size."""
+        n_rows = self.dev[0].shape[0]
+        step = max(1, min(hi - lo, _ROWS_INDEX_BYTES // (8 * n_rows)))
+        return (_device.fill_indices(self.key, n_rows, 1, a, min(hi, a + step)) for a in range(lo, hi, step))
+
+    def _nan_flags(self):
+        """(device flags, host bool[D]) of the columns holding NaNs — rank statistics only: np.median
+        and np.quantile of a sample with a NaN are NaN, the rank kernels order NaNs last."""
+        if self._nan is None:
+            data2d = self.dev[0] if self.dev[0].dim() == 2 else self.dev[0].reshape(-1, 1)
+            self._nan = _device.nan_columns(data2d)
+        return self._nan
+
+    def _propagate_nan(self, out, lo, hi, index_batches=None):
+        """numpy's NaN rule for rank statistics: a resample that draws a NaN row of column d has a
+        NaN statistic there (statfunction(x[indices]), bootstrap.py:431).  Only columns with NaNs
+        pay: their resamples' draws are replayed (K2) and looked up."""
+        flags, host = self._nan_flags()
+        if not host.any() or hi <= lo:
+            return out
+        data2d = self.dev[0] if self.dev[0].dim() == 2 else self.dev[0].reshape(-1, 1)
+        n_rows = data2d.shape[0]
+        rank_space = index_batches is None and self._long_median() and not self._row_space()
+        at = 0
+        for idx in (index_batches if index_batches is not None else self._index_batches(lo, hi)):
+            for d in np.nonzero(host)[0].tolist():
+                if rank_space:      # K1mt resamples sorted(x): the same draws address the sorted column
+                    _device.nan_fixup(self._sorted()[d], 1, n_rows, idx, out[d, at:])
+                else:
+                    _device.nan_fixup(data2d[:, d], data2d.stride(0), n_rows, idx, out[d, at:])
+            at += idx.shape[0]
+        return out
 
     # -- short calls: everything in one library call ------------------------------------
     def small_call(self, alphas: np.ndarray, bca: bool, need_jack: bool):
@@ -346,9 +382,11 @@ class _Run:
             raise IndexError("index out of range")
         if spec.stat_id == _abi.STAT_MEDIAN:
             if self._row_space():
-                return self._median_rows([idx], idx.shape[0])
-            data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
-            return _device.resample_median_columns_indexed(data2d, idx, rule=self.rule)
+                out = self._median_rows([idx], idx.shape[0])
+            else:
+                data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
+                out = _device.resample_median_columns_indexed(data2d, idx, rule=self.rule)
+            return self._propagate_nan(out, 0, idx.shape[0], index_batches=[idx])
         if self.vector and spec.n_out == 1:
             cols = self.columns()
             return torch.stack([_device.resample_stat_indexed([cols[d]], spec.stat_id, idx)
@@ -384,6 +422,9 @@ class _Run:
         spec = self.spec
         if spec.independent:
             j = self._jackknife_independent()
+            for p in self.parts():        # a rank statistic of an array with a NaN: every pooled value is NaN
+                if p.spec.stat_id == _abi.STAT_MEDIAN and p._nan_flags()[1].any():
+                    _device.nan_poison_rows(j, p._nan_flags()[0])
         elif spec.stat_id == _abi.STAT_MEDIAN:
             if self._long_median():
                 j = torch.cat([_device.jackknife_median_sorted(c, rule=self.rule) for c in self._sorted()])
@@ -392,6 +433,9 @@ class _Run:
             else:
                 data2d = self.dev[0] if self.vector else self.dev[0].reshape(-1, 1)
                 j = _device.jackknife_median_columns(data2d, rule=self.rule)
+            flags, host = self._nan_flags()
+            if host.any():                # statfunction(data) and the leave-one-out values are NaN (numpy's rule)
+                _device.nan_poison_rows(j, flags)
         elif self.vector and spec.n_out == 1:
             j = _device.jackknife_columns(self.dev[0], spec.stat_id)                               # K3c
         else:

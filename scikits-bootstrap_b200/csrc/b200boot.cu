@@ -1053,6 +1053,35 @@ int b200boot_rank_columns(const double* data, int64_t n_rows, int64_t n_cols, in
   return 0;
 }
 
+int b200boot_nan_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, int32_t* flags,
+                         void* stream) {
+  if (!data || !flags || n_rows < 1 || n_cols < 1 || ld < n_cols) return fail(B200BOOT_EINVAL, "nan_columns: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  B2_CUDA(cudaMemsetAsync(flags, 0, (size_t)(n_cols + 1) * sizeof(int32_t), s));
+  nan_columns_kernel<<<(unsigned)((n_cols + 31) / 32), 256, 0, s>>>(data, n_rows, n_cols, ld, flags);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200boot_nan_fixup(const double* src, int64_t stride, int64_t n_rows, const int64_t* indices, int64_t n_sets,
+                       double* out, void* stream) {
+  if (!src || !indices || !out || stride < 1 || n_rows < 1 || n_sets < 0)
+    return fail(B200BOOT_EINVAL, "nan_fixup: bad arguments");
+  if (n_sets == 0) return 0;
+  nan_fixup_kernel<<<blocks_for(n_sets * 32, 256, 148 * 8), 256, 0, as_stream(stream)>>>(src, stride, n_rows, indices,
+                                                                                        n_sets, out);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200boot_nan_poison_rows(double* table, int64_t n_cols, int width, const int32_t* flags, void* stream) {
+  if (!table || !flags || n_cols < 1 || width < 1) return fail(B200BOOT_EINVAL, "nan_poison_rows: bad arguments");
+  nan_poison_rows_kernel<<<blocks_for(n_cols * width, 256, 1 << 20), 256, 0, as_stream(stream)>>>(table, n_cols, width,
+                                                                                                 flags);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
 int b200boot_median_rows_supported(int64_t n_rows) { return n_rows >= 1 && n_rows <= kRowsMaxRows ? 1 : 0; }
 
 int b200boot_median_rows_indexed(const double* sorted_vals, const int32_t* rank, int64_t n_rows, int64_t n_cols,

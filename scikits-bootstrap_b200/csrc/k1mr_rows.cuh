@@ -156,6 +156,59 @@ __global__ void __launch_bounds__(kRowsThreads) k1mr_select_kernel(const RowsPar
   }
 }
 
+// ---- NaN propagation for rank statistics ----------------------------------------------------
+// np.median / np.quantile return NaN as soon as the sample holds one (the reference's
+// statfunction(x[indices]) therefore gives NaN for every resample that draws a NaN row), whereas
+// the rank kernels order NaNs last and would pick a finite order statistic.  Data with NaNs are
+// rare, so the rank kernels stay as they are and the affected columns are patched afterwards:
+// nan_columns_kernel flags them, nan_fixup_kernel sets the statistic of every index set that
+// contains a NaN row of a flagged column to NaN, nan_poison_rows_kernel does the same for the
+// jackknife summary (leave-one-out samples of a column with a NaN are NaN, bar at most one).
+__global__ void __launch_bounds__(256) nan_columns_kernel(const double* __restrict__ data, int64_t n_rows,
+                                                          int64_t n_cols, int64_t ld, int32_t* __restrict__ flags) {
+  // 32 columns per CTA (coalesced rows), 8 row groups; flags[n_cols] = any column flagged
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int64_t d = (int64_t)blockIdx.x * 32 + cx;
+  bool bad = false;
+  if (d < n_cols)
+    for (int64_t i = ry; i < n_rows; i += 8) {
+      const double v = data[i * ld + d];
+      bad = bad || v != v;
+    }
+  if (bad) {
+    atomicExch(flags + d, 1);
+    atomicExch(flags + n_cols, 1);
+  }
+}
+
+// out[set] = NaN when any of src[idx[set][j] * stride] is NaN; one warp per index set
+__global__ void __launch_bounds__(256) nan_fixup_kernel(const double* __restrict__ src, int64_t stride, int64_t n_rows,
+                                                        const int64_t* __restrict__ idx, int64_t n_sets,
+                                                        double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t set = warp_global; set < n_sets; set += n_warps) {
+    bool bad = false;
+    for (int64_t j = lane; j < n_rows; j += 32) {
+      const int64_t i = idx[set * n_rows + j];
+      if ((uint64_t)i < (uint64_t)n_rows) {
+        const double v = src[i * stride];
+        bad = bad || v != v;
+      }
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) out[set] = nan("");
+  }
+}
+
+// rows of a [n_cols][width] table whose column is flagged become NaN
+__global__ void __launch_bounds__(256) nan_poison_rows_kernel(double* __restrict__ table, int64_t n_cols, int width,
+                                                              const int32_t* __restrict__ flags) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_cols * width) return;
+  if (flags[e / width]) table[e] = nan("");
+}
+
 inline size_t rows_smem_bytes() { return (size_t)kRowsGroup * 2 * kRowsMaxBins * sizeof(unsigned int); }
 
 }  // namespace b200boot

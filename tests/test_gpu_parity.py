@@ -383,6 +383,39 @@ def test_long_median_over_columns_is_row_aligned(n, d, q):
         assert_array_equal(run_idx, np.sort(want[:, 0]))
 
 
+@pytest.mark.parametrize("n,d", [(400, 1), (3000, 4), (30001, 1), (29000, 3)])
+def test_rank_statistics_propagate_nan_like_numpy(n, d):
+    """np.median / np.quantile of a sample holding a NaN are NaN, so the reference's statistic is NaN
+    for every resample that draws a NaN row; all rank paths (resident K1m, rank-space K1mt,
+    row-space K1mr, index-supplied) must say the same."""
+    import warnings
+    rng = np.random.default_rng(n)
+    data = rng.standard_normal((n, d))
+    data[3, 0] = np.nan                               # one NaN row in column 0 ...
+    if d > 2:
+        data[[5, 7, 11], 2] = np.nan                  # ... three in column 2, none in the others
+    x = data[:, 0] if d == 1 else data
+    m = 60
+    for f, host in ((np.median if d == 1 else boot.median_axis0, lambda u: np.median(u, axis=0)),
+                    (boot.quantile(0.3) if d == 1 else boot.quantile_axis0(0.3), lambda u: np.quantile(u, 0.3, axis=0))):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out, dist = boot.ci(x, f, n_samples=m, seed=2, method="pi", return_dist=True)
+            idx = np.array(list(boot.bootstrap_indices(x, m, seed=2)))
+            src = np.sort(x) if (d == 1 and n > 28672) else x          # K1mt resamples sorted(x)
+            want = np.stack([host(src[i]) for i in idx]).reshape(m, -1)
+            assert np.isnan(want[:, 0]).any() and (d == 1 or not np.isnan(want[:, 1]).any())
+            assert_array_equal(dist.reshape(m, -1), np.sort(want, axis=0))
+            bca = boot.ci(x, f, n_samples=m, seed=2, method="bca")
+            # column 0 holds a NaN: its leave-one-out values are NaN (bar one), the acceleration is NaN
+            jst = np.full((n,) if d == 1 else (n, d), np.nan)
+            ref = orc.ci_from_indices((src,), host, idx, (0.025, 0.975), m, "bca", jstat=jst)
+            assert_array_equal(np.asarray(bca).reshape(2, -1)[:, 0], np.asarray(ref).reshape(2, -1)[:, 0])
+            pcg = np.array(list(orc.bootstrap_indices_pcg64(n, 20, 4)))
+            got = boot.ci_indexed(x, f, indices=pcg, method="pi", return_dist=True)[1]
+            assert_array_equal(got.reshape(20, -1), np.sort(np.stack([host(x[i]) for i in pcg]).reshape(20, -1), axis=0))
+
+
 def test_long_median_index_supplied():
     """Index-supplied (parity) mode beyond the resident limit: the reference's own PCG64 index
     sets, 1-D and (N, D) data."""
