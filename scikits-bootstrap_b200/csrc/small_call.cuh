@@ -185,6 +185,28 @@ __device__ __forceinline__ int bucket_of(double v, double lo, double scale, int 
   return b < n_bins - 1 ? b : n_bins - 1;
 }
 
+// f(r, v) for every element of the vector, thread-strided, four loads in flight per thread: the
+// unstaged vector comes from L2 and a dependent load per iteration would make each pass cost
+// ~100 L2 latencies for 1e5 values (measured: tail 97 us -> see DESIGN 4a).
+template <typename F>
+__device__ __forceinline__ void for_each_value(const double* __restrict__ src, bool from_global, int64_t n, F&& f) {
+  constexpr int kBatch = 4;
+  const int64_t step = (int64_t)kSmallThreads * kBatch;
+  for (int64_t r0 = threadIdx.x; r0 < n; r0 += step) {
+    double v[kBatch];
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+      const int64_t r = r0 + (int64_t)k * kSmallThreads;
+      v[k] = r < n ? (from_global ? __ldcg(src + r) : src[r]) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+      const int64_t r = r0 + (int64_t)k * kSmallThreads;
+      if (r < n) f(r, v[k]);
+    }
+  }
+}
+
 // All 1024 threads of one CTA.  `smem`: (staged ? n doubles : 0) + tail_scratch_bytes().
 __device__ __noinline__ void small_tail_bucket(const SmallTailParams& P, unsigned char* smem, double* res_host) {
   __shared__ double s_red[kSmallThreads / 32][2];
@@ -197,10 +219,14 @@ __device__ __noinline__ void small_tail_bucket(const SmallTailParams& P, unsigne
   __shared__ double s_val[kSelMaxAlphas];
   __shared__ int s_slow;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // the parameter block lives in local memory (the function is not inlined): what the per-value
+  // loops need is copied to registers once, or every value would reload it
   const int64_t n = P.n_samples;
   const int A = P.n_alphas;
+  const bool staged = P.staged != 0, bca = P.bca != 0;
+  const double* const gstat = P.stat;
   double* s_stat = reinterpret_cast<double*>(smem);
-  unsigned char* scratch = smem + (P.staged ? tail_stage_bytes(n) : 0);
+  unsigned char* scratch = smem + (staged ? tail_stage_bytes(n) : 0);
   TailScratch T;
   T.hist = reinterpret_cast<unsigned int*>(scratch);
   const int n_bins = P.n_bins;                 // a multiple of 4 * kSmallThreads
@@ -208,20 +234,19 @@ __device__ __noinline__ void small_tail_bucket(const SmallTailParams& P, unsigne
   T.hist2 = reinterpret_cast<unsigned int(*)[256]>(scratch + (size_t)n_bins * 4 + (size_t)kSelMaxAlphas * kBktCand * 8);
 
   // pass A: stage, min / max of the non-NaN values, NaN count, #{stat < ostat}
-  const double ostat = P.bca ? __ldcg(P.jack) : 0.0;
+  const double ostat = bca ? __ldcg(P.jack) : 0.0;
   double lo = INFINITY, hi = -INFINITY;
   unsigned int less = 0, nans = 0;
-  for (int64_t r = tid; r < n; r += kSmallThreads) {
-    const double v = __ldcg(P.stat + r);
-    if (P.staged) s_stat[r] = v;
+  for_each_value(gstat, true, n, [&](int64_t r, double v) {
+    if (staged) s_stat[r] = v;
     if (v != v) {
       ++nans;
     } else {
       lo = fmin(lo, v);
       hi = fmax(hi, v);
     }
-    less += (P.bca && v < ostat) ? 1u : 0u;                          // strict '<'  bootstrap.py:583
-  }
+    less += (bca && v < ostat) ? 1u : 0u;                          // strict '<'  bootstrap.py:583
+  });
   for (int i = tid; i < n_bins; i += kSmallThreads) T.hist[i] = 0u;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
@@ -246,7 +271,7 @@ __device__ __noinline__ void small_tail_bucket(const SmallTailParams& P, unsigne
     less += s_cnt_red[w][0];
     nans += s_cnt_red[w][1];
   }
-  const double* stat = P.staged ? s_stat : P.stat;
+  const double* stat = staged ? s_stat : gstat;
   const double* jack = P.jack;
 
   if (P.ranks != nullptr) {
@@ -284,10 +309,9 @@ __device__ __noinline__ void small_tail_bucket(const SmallTailParams& P, unsigne
   const double scale = (double)n_bins / range;
   const bool fast = hi > lo && isfinite(range) && isfinite(scale) && isfinite(lo);
   if (fast) {
-    for (int64_t r = tid; r < n; r += kSmallThreads) {
-      const double v = P.staged ? stat[r] : __ldcg(stat + r);
+    for_each_value(stat, !staged, n, [&](int64_t, double v) {
       if (v == v) atomicAdd(&T.hist[bucket_of(v, lo, scale, n_bins)], 1u);
-    }
+    });
     __syncthreads();
     // exclusive scan over the buckets: thread t owns the `per` consecutive buckets from t * per
     const int per = n_bins / kSmallThreads;
@@ -328,16 +352,19 @@ __device__ __noinline__ void small_tail_bucket(const SmallTailParams& P, unsigne
     __syncthreads();
     if (!s_slow) {
       // the values of each rank's bucket, as keys
-      for (int64_t r = tid; r < n; r += kSmallThreads) {
-        const double v = P.staged ? stat[r] : __ldcg(stat + r);
-        if (v != v) continue;
+      int my_bucket[kSelMaxAlphas];
+#pragma unroll
+      for (int a = 0; a < kSelMaxAlphas; ++a) my_bucket[a] = a < A ? s_bucket[a] : -1;
+      for_each_value(stat, !staged, n, [&](int64_t, double v) {
+        if (v != v) return;
         const int b = bucket_of(v, lo, scale, n_bins);
-        for (int a = 0; a < A; ++a)
-          if (b == s_bucket[a]) {
+#pragma unroll
+        for (int a = 0; a < kSelMaxAlphas; ++a)
+          if (b == my_bucket[a]) {
             const unsigned int pos = atomicAdd(&s_ccnt[a], 1u);
             if (pos < (unsigned int)kBktCand) T.cand[a * kBktCand + pos] = key_of(v);
           }
-      }
+      });
       __syncthreads();
       for (int a = 0; a < A; ++a)
         if (s_ccnt[a] > (unsigned int)kBktCand && tid == 0) s_slow = 1;
