@@ -110,6 +110,16 @@ int b200boot_resample_stat_after(const double* const* data, int n_arrays, int64_
                                  double* stat_out, void* ws, size_t ws_bytes, void* stream,
                                  void* data_ready_event);
 
+/* b200boot_resample_stat with the rows still in HOST memory (float64, contiguous; pageable or
+ * pinned): the occupancy chains are enqueued first, then each array is copied to the caller's
+ * device rows `data_dev[a]` (n_rows doubles) on `copy_stream` (a stream other than `stream`), and
+ * only what reads the data waits for the copy — staging a pageable array and the transfer run
+ * under K0.  The range must not be empty. */
+int b200boot_resample_stat_host(const double* const* host_data, double* const* data_dev, int n_arrays,
+                                int64_t n_rows, int stat_id, uint64_t seed, int64_t resample_lo,
+                                int64_t resample_hi, double* stat_out, void* ws, size_t ws_bytes, void* stream,
+                                void* copy_stream);
+
 /* K1i — parity mode: the caller supplies the index arrays (e.g. the reference's
  * own PCG64 draws).  Replaces bootstrap.py:431 only.  indices: int64[n_sets][N]
  * row-major, values in [0, N).  stat_out: float64[n_sets] ([n_out][n_sets]). */

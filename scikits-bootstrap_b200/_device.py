@@ -206,9 +206,21 @@ def _ws_budget() -> int:
     return int(os.environ.get("B200BOOT_WS_BYTES", 12 << 30))
 
 
-def resample_stat(arrays: Sequence, stat_id: int, seed: int, lo: int, hi: int, out=None, ready=None):
+def copy_stream(device_index: int):
+    """The side stream host-to-device copies run on (one per device)."""
+    torch = _torch()
+    side = _copy_streams.get(device_index)
+    if side is None:
+        side = _copy_streams[device_index] = torch.cuda.Stream(device=torch.device("cuda", device_index))
+    return side
+
+
+def resample_stat(arrays: Sequence, stat_id: int, seed: int, lo: int, hi: int, out=None, ready=None,
+                  host_rows=None):
     """K1 on contiguous float64[N] CUDA tensors -> float64[hi-lo] CUDA tensor
-    (float64[n_out][hi-lo] for a statistic with several outputs)."""
+    (float64[n_out][hi-lo] for a statistic with several outputs).  host_rows: the numpy arrays
+    whose rows `arrays` are still to receive (copied under the occupancy chains of the first
+    sub-range, b200boot_resample_stat_host)."""
     torch = _torch()
     L = _abi.lib()
     n_rows = arrays[0].numel()
@@ -227,11 +239,20 @@ def resample_stat(arrays: Sequence, stat_id: int, seed: int, lo: int, hi: int, o
         ws, wsz = workspace_for(stat_id, n_rows, len(arrays), 1, b - a, 1)
         whole = n_out == 1 or (a == lo and b == hi)
         dst = out[a - lo:] if n_out == 1 else (out if whole else out.new_empty((n_out, b - a)))
-        # `ready`: event recorded after the arrays' host-to-device copy on another stream; the
-        # first sub-range waits for it (after its occupancy chains), later ones follow in order
-        ev = ready.cuda_event if (ready is not None and a == lo) else None
-        _abi.check(L.b200boot_resample_stat_after(ptrs, len(arrays), n_rows, stat_id, seed, a, b,
-                                                  dst.data_ptr(), ws, wsz, stream_ptr(), ev))
+        if host_rows is not None and a == lo:
+            side = copy_stream(arrays[0].device.index)
+            hp = (C.c_void_p * len(host_rows))(*[h.ctypes.data for h in host_rows])
+            for t in arrays:
+                t.record_stream(side)
+            TRAFFIC["h2d"] += 8 * n_rows * len(host_rows)
+            _abi.check(L.b200boot_resample_stat_host(hp, ptrs, len(arrays), n_rows, stat_id, seed, a, b,
+                                                     dst.data_ptr(), ws, wsz, stream_ptr(), side.cuda_stream))
+        else:
+            # `ready`: event recorded after the arrays' host-to-device copy on another stream; the
+            # first sub-range waits for it (after its occupancy chains), later ones follow in order
+            ev = ready.cuda_event if (ready is not None and a == lo) else None
+            _abi.check(L.b200boot_resample_stat_after(ptrs, len(arrays), n_rows, stat_id, seed, a, b,
+                                                      dst.data_ptr(), ws, wsz, stream_ptr(), ev))
         if not whole:
             out[:, a - lo:b - lo] = dst
     return out

@@ -61,6 +61,8 @@ _GATHER_LIMIT_BYTES = 32 << 20
 _ARRAY_KEY_STRIDE = 0x9E3779B97F4A7C15
 # K1mr: materialised index sets per batch
 _ROWS_INDEX_BYTES = 256 << 20
+# numpy rows from this size on are copied by the resampling call, under its occupancy chains
+_DEFER_COPY_BYTES = 4 << 20
 
 
 def _seed_key(seed: SeedType) -> int:
@@ -141,16 +143,25 @@ class _Run:
         self.spec, self.multi, self.n_samples, self.key = spec, multi, int(n_samples), key
         self.indices = indices       # parity mode: caller-supplied index sets (K1i)
         self.blocks = blocks         # moving-block plan: (block_length, wrap), else None
-        # pinned host tensors are copied on a side stream; `_ready` is recorded after the copies
-        pairs = [_device.to_device_f64_async(a) for a in arrays]
-        self.dev = [t for t, _ in pairs]
-        events = [e for _, e in pairs if e is not None]
-        self._ready = events[-1] if events else None      # one side stream: the last event covers all
+        self.rank, self.world = _dist.world()
+        self.lo, self.hi = _dist.shard_range(self.n_samples, self.rank, self.world)
+        self._host_rows = None
+        if self._defer_copy(arrays):
+            # long numpy rows of a plain K1 job: the copy (8 ms of host staging per 80 MB of pageable
+            # memory) is issued by the resampling call itself, behind its occupancy chains
+            torch = _device.require_cuda()
+            self.dev = [torch.empty(a.shape, dtype=torch.float64, device="cuda") for a in arrays]
+            self._host_rows = list(arrays)
+            self._ready = None
+        else:
+            # pinned host tensors are copied on a side stream; `_ready` is recorded after the copies
+            pairs = [_device.to_device_f64_async(a) for a in arrays]
+            self.dev = [t for t, _ in pairs]
+            events = [e for _, e in pairs if e is not None]
+            self._ready = events[-1] if events else None      # one side stream: the last event covers all
         # the statistic has shape (D,): one value per data column, or a multi-output statistic
         self.vector = (spec.axis0 and self.dev[0].dim() == 2) or spec.n_out > 1
         self.n_cols = spec.n_out if spec.n_out > 1 else (self.dev[0].shape[1] if self.vector else 1)
-        self.rank, self.world = _dist.world()
-        self.lo, self.hi = _dist.shard_range(self.n_samples, self.rank, self.world)
         self._columns = None
         self._jack = None
         self._sorted_vals = None
@@ -163,6 +174,17 @@ class _Run:
         self._spec = None
         # rank statistics: which order statistics (None: np.median's)
         self.rule = _device.rank_rule(self.dev[0].shape[0], spec.q) if spec.stat_id == _abi.STAT_MEDIAN else None
+
+    def _defer_copy(self, arrays) -> bool:
+        """Host rows that can travel under K0: contiguous 1-D float64 numpy arrays of at least
+        4 MB feeding the plain K1 path (scalar moment statistic, Philox draws, a non-empty shard) —
+        the one path whose first device work does not read the data."""
+        spec = self.spec
+        return (self.indices is None and self.blocks is None and not spec.independent
+                and spec.stat_id != _abi.STAT_MEDIAN and spec.n_out == 1 and self.hi > self.lo
+                and all(type(a) is np.ndarray and a.ndim == 1 and a.dtype == np.float64
+                        and a.flags.c_contiguous for a in arrays)
+                and arrays[0].nbytes >= _DEFER_COPY_BYTES)
 
     # -- data views ------------------------------------------------------------
     def columns(self):
@@ -262,7 +284,9 @@ class _Run:
                 _device.resample_stat([cols[d]], spec.stat_id, self.key, lo, hi, out=out[d])
             return out
         flat = [a.reshape(-1) for a in self.dev]
-        return _device.resample_stat(flat, spec.stat_id, self.key, lo, hi, ready=ready).reshape(1, -1)
+        host_rows, self._host_rows = self._host_rows, None
+        return _device.resample_stat(flat, spec.stat_id, self.key, lo, hi, ready=ready,
+                                     host_rows=host_rows).reshape(1, -1)
 
     def _resample_rank_statistic(self, lo, hi):
         """Median / quantile kernels (NaNs ordered last; _propagate_nan restores numpy's rule)."""

@@ -344,10 +344,19 @@ int b200boot_resample_stat(const double* const* data, int n_arrays, int64_t n_ro
                                       ws, ws_bytes, stream, nullptr);
 }
 
-int b200boot_resample_stat_after(const double* const* data, int n_arrays, int64_t n_rows, int stat_id,
-                                 uint64_t seed, int64_t resample_lo, int64_t resample_hi,
-                                 double* stat_out, void* ws, size_t ws_bytes, void* stream,
-                                 void* data_ready_event) {
+}  // extern "C"
+
+namespace {
+
+// K0 + K1 + finish.  The occupancy chains (K0) do not read the data, so the data may still be on
+// their way while K0 runs: either the caller copies them on another stream and hands over the
+// event recorded behind the copy (`data_ready_event`), or the rows are still in HOST memory
+// (`host_data`, pageable or pinned) and are copied here, on `copy_stream`, after K0 has been
+// enqueued — the host-side staging of a pageable array (8 ms for 80 MB) and the transfer then run
+// under K0 instead of in front of it.
+int resample_stat_impl(const double* const* data, int n_arrays, int64_t n_rows, int stat_id, uint64_t seed,
+                       int64_t resample_lo, int64_t resample_hi, double* stat_out, void* ws, size_t ws_bytes,
+                       void* stream, void* data_ready_event, const double* const* host_data, void* copy_stream) {
   int rc = check_moment_stat(stat_id, n_arrays, n_rows);
   if (rc) return rc;
   const int64_t n_local = resample_hi - resample_lo;
@@ -365,20 +374,36 @@ int b200boot_resample_stat_after(const double* const* data, int n_arrays, int64_
   // The occupancy chains do not read the data: when the caller is still copying it in on
   // another stream, only what follows them waits for the copy.
   cudaEvent_t ready = reinterpret_cast<cudaEvent_t>(data_ready_event);
-  if (ready && stat_needs_centering(stat_id)) {   // the centring pass reads the data first
-    B2_CUDA(cudaStreamWaitEvent(s, ready, 0));
-    ready = nullptr;
+  cudaEvent_t ev_entry = nullptr, ev_copied = nullptr;
+  if (host_data) {
+    // the device rows may have earlier users on `s` (a recycled allocation): the copy stream
+    // starts behind everything enqueued on `s` so far, but not behind K0
+    B2_CUDA(cudaEventCreateWithFlags(&ev_entry, cudaEventDisableTiming));
+    B2_CUDA(cudaEventCreateWithFlags(&ev_copied, cudaEventDisableTiming));
+    B2_CUDA(cudaEventRecord(ev_entry, s));
   }
-  const double* rows[2];
-  rc = prepare_rows(data, n_arrays, n_rows, stat_id, w, rows, s);
-  if (rc) return rc;
-
   B2_CUDA(cudaMemsetAsync(w.work_counter, 0, 512, s));   // work counter and (next 256 B) the overflow flag
   if (g_prof.enabled) B2_CUDA(cudaEventRecord(g_prof.begin, s));
   rc = launch_occupancies_fast(seed, resample_lo, n_local, plan, w.counts, w.gcounts, w.cls, w.half_tables,
                                w.overflow, s);
   if (rc) return rc;
-  if (ready) B2_CUDA(cudaStreamWaitEvent(s, ready, 0));
+  if (host_data) {
+    cudaStream_t cs = as_stream(copy_stream);
+    B2_CUDA(cudaStreamWaitEvent(cs, ev_entry, 0));
+    for (int a = 0; a < n_arrays; ++a)
+      B2_CUDA(cudaMemcpyAsync(const_cast<double*>(data[a]), host_data[a], (size_t)n_rows * sizeof(double),
+                              cudaMemcpyHostToDevice, cs));
+    B2_CUDA(cudaEventRecord(ev_copied, cs));
+    B2_CUDA(cudaStreamWaitEvent(s, ev_copied, 0));
+    B2_CUDA(cudaEventDestroy(ev_entry));          // released once the work that uses them has run
+    B2_CUDA(cudaEventDestroy(ev_copied));
+  } else if (ready) {
+    B2_CUDA(cudaStreamWaitEvent(s, ready, 0));
+  }
+  // centring (var / std / Pearson / fit) reads the data: behind the copy, and behind K0
+  const double* rows[2];
+  rc = prepare_rows(data, n_arrays, n_rows, stat_id, w, rows, s);
+  if (rc) return rc;
 
   const int ms = moment_set_of(stat_id);
   const int nm = ms == kMomSum ? 1 : (ms == kMomPair5 ? 5 : 2);
@@ -429,6 +454,32 @@ int b200boot_resample_stat_after(const double* const* data, int n_arrays, int64_
                                                                      stat_out, w.overflow);
   B2_LAUNCH_CHECK();
   return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200boot_resample_stat_after(const double* const* data, int n_arrays, int64_t n_rows, int stat_id,
+                                 uint64_t seed, int64_t resample_lo, int64_t resample_hi,
+                                 double* stat_out, void* ws, size_t ws_bytes, void* stream,
+                                 void* data_ready_event) {
+  return resample_stat_impl(data, n_arrays, n_rows, stat_id, seed, resample_lo, resample_hi, stat_out, ws, ws_bytes,
+                            stream, data_ready_event, nullptr, nullptr);
+}
+
+int b200boot_resample_stat_host(const double* const* host_data, double* const* data_dev, int n_arrays,
+                                int64_t n_rows, int stat_id, uint64_t seed, int64_t resample_lo,
+                                int64_t resample_hi, double* stat_out, void* ws, size_t ws_bytes, void* stream,
+                                void* copy_stream) {
+  if (!host_data || !data_dev || !copy_stream || copy_stream == stream)
+    return fail(B200BOOT_EINVAL, "resample_stat_host: host rows, device rows and a separate copy stream are required");
+  for (int a = 0; a < n_arrays && a < 2; ++a)
+    if (!host_data[a] || !data_dev[a]) return fail(B200BOOT_EINVAL, "resample_stat_host: null pointer");
+  if (resample_hi <= resample_lo)
+    return fail(B200BOOT_EINVAL, "resample_stat_host: empty resample range (the rows would not be copied)");
+  return resample_stat_impl(data_dev, n_arrays, n_rows, stat_id, seed, resample_lo, resample_hi, stat_out, ws,
+                            ws_bytes, stream, nullptr, host_data, copy_stream);
 }
 
 int b200boot_resample_stat_indexed(const double* const* data, int n_arrays, int64_t n_rows,

@@ -743,6 +743,39 @@ def test_single_launch_tail_degenerate_vectors(monkeypatch):
         assert_array_equal(a, b)
 
 
+def test_long_numpy_rows_travel_under_the_occupancy_chains(monkeypatch):
+    """Long numpy inputs of the plain K1 path are copied by the resampling call itself, behind its
+    occupancy chains (b200boot_resample_stat_host); same results as from a CUDA tensor."""
+    rng = np.random.default_rng(6)
+    a, b = rng.gamma(2.0, 1.0, 600_000), rng.gamma(3.0, 1.0, 600_000)
+    calls = []
+    real = _device.resample_stat
+
+    def spy(*args, **kw):
+        calls.append(kw.get("host_rows") is not None)
+        return real(*args, **kw)
+    monkeypatch.setattr(_device, "resample_stat", spy)
+    for data, f, kw in [(a, np.mean, {}), (a, np.std, dict(method="pi")), ((a, b), boot.ratio_of_means, {}),
+                        ((a, b), boot.pearson_r, dict(output="errorbar"))]:
+        dev_data = tuple(dev(t) for t in data) if isinstance(data, tuple) else dev(data)
+        before = _device.TRAFFIC["h2d"]
+        got = boot.ci(data, f, n_samples=300, seed=12, **kw)
+        assert calls[-1] is True
+        n_arrays = len(data) if isinstance(data, tuple) else 1
+        assert _device.TRAFFIC["h2d"] - before >= 8 * 600_000 * n_arrays
+        want = boot.ci(dev_data, f, n_samples=300, seed=12, **kw)
+        assert calls[-1] is False
+        assert_array_equal(got, want)
+    p = boot.pval(a, np.mean, boot.greater_than(2.0), n_samples=300, seed=3)
+    assert calls[-1] is True and p == boot.pval(dev(a), np.mean, boot.greater_than(2.0), n_samples=300, seed=3)
+    # short rows, read-only or strided arrays take the ordinary copy
+    ro = a[:700_000].copy()
+    ro.setflags(write=False)
+    for data in (a[:1000], a[::2], ro):
+        boot.ci(data, np.mean, n_samples=64, seed=1, method="pi")
+    assert calls[-3:] == [False, False, True] or calls[-2:] == [False, True]
+
+
 def test_small_call_wrong_speculative_ranks_are_caught(monkeypatch):
     """The device's ranks are only a guess: when the host's own levels give other ranks the
     order statistics are selected again with the host's."""
