@@ -23,6 +23,10 @@ def main():
     x = rng.standard_normal(50001) + 1.0
     a, b = rng.gamma(2, 1, 20000), rng.gamma(3, 1, 20000)
     table = rng.standard_normal((500, 37))
+    tall = rng.standard_normal((29001, 3))                  # beyond the resident rows: row-space medians (K1mr)
+    long_rows = rng.gamma(2.0, 1.0, 600_000)                # numpy rows copied under the occupancy chains
+    holes = x[:3000].copy()
+    holes[17] = np.nan                                      # numpy's NaN rule for rank statistics
     cases = [
         lambda: boot.ci(x, np.mean, n_samples=1003, seed=3),
         lambda: boot.ci(x, np.std, n_samples=1003, seed=3, alpha=(0.05, 0.5, 0.95), method="pi"),
@@ -38,6 +42,12 @@ def main():
         lambda: boot.ci(x, boot.percentile(90), n_samples=333, seed=11),
         lambda: boot.ci(table, boot.quantile_axis0(0.25), n_samples=301, seed=12),
         lambda: boot.ci((a[:6000], x), boot.diff_of(np.median), n_samples=401, seed=13, multi="independent"),
+        lambda: boot.ci(tall, boot.median_axis0, n_samples=90, seed=14, method="pi"),
+        lambda: boot.ci(tall, boot.quantile_axis0(0.7), n_samples=64, seed=15, return_dist=True, method="pi")[1],
+        lambda: boot.ci(long_rows, np.mean, n_samples=40000, seed=16),       # single-launch tail over 4e4 values
+        lambda: boot.ci(long_rows, np.std, n_samples=301, seed=17, method="pi"),
+        lambda: boot.ci(holes, np.median, n_samples=201, seed=18, method="pi", return_dist=True)[1],
+        lambda: boot.ci(x[:1000], np.mean, n_samples=2000, seed=19),         # small-call shape (unsharded: one kernel)
         lambda: boot.ci(x, np.mean, n_samples=64, seed=None),          # seed agreed through a broadcast
     ]
     boot.distributed.enable()
