@@ -185,9 +185,10 @@ __device__ __forceinline__ int bucket_of(double v, double lo, double scale, int 
   return b < n_bins - 1 ? b : n_bins - 1;
 }
 
-// f(r, v) for every element of the vector, thread-strided, four loads in flight per thread: the
-// unstaged vector comes from L2 and a dependent load per iteration would make each pass cost
-// ~100 L2 latencies for 1e5 values (measured: tail 97 us -> see DESIGN 4a).
+// f(r, v) for every element of the vector, thread-strided, four loads in flight per thread (an
+// unstaged vector comes from L2).  The single-CTA tail is instruction-bound, not latency-bound:
+// 1e5 values cost ~97 us with or without the batching (~47 thread-instructions per value visit,
+// three visits; ncu source view).
 template <typename F>
 __device__ __forceinline__ void for_each_value(const double* __restrict__ src, bool from_global, int64_t n, F&& f) {
   constexpr int kBatch = 4;
