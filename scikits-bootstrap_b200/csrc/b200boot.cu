@@ -1063,6 +1063,65 @@ int rank_rules(const b200boot_rank_rule* rule, int64_t n_rows, RankRule* full, R
                   full->gamma >= 0.0 && full->gamma <= 1.0 && loo->gamma >= 0.0 && loo->gamma <= 1.0;
   return ok ? 0 : fail(B200BOOT_EINVAL, "rank rule: ranks outside the sample or weight outside [0, 1]");
 }
+
+// K1m1: one resident column (csrc/k1mr_rows.cuh).  Sorts the column once ((key, row) pairs ->
+// sorted values + rank table), then a warp (N <= 2048) or a CTA per resample.
+int median_single_column(const double* data, int64_t n_rows, int64_t ld, uint64_t seed, int64_t resample_lo,
+                         int64_t n_sets, const int64_t* indices, double* stat_out, void* ws, size_t ws_bytes,
+                         cudaStream_t s, const RankRule& full, const RankRule& loo, double* jack_out) {
+  if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
+    return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
+  int64_t n_pad = 1;
+  while (n_pad < n_rows) n_pad <<= 1;
+  Carver cv(ws, ws_bytes);
+  uint64_t* keys = cv.take<uint64_t>((size_t)n_pad);
+  uint32_t* idx = cv.take<uint32_t>((size_t)n_pad);
+  double* sorted = cv.take<double>((size_t)n_rows);
+  int32_t* rank = cv.take<int32_t>((size_t)n_rows);
+  if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+  psort_load_kernel<<<blocks_for(n_pad, 256, 148 * 32), 256, 0, s>>>(data, n_rows, 1, ld, n_pad, keys, idx);
+  B2_LAUNCH_CHECK();
+  int rc = psort_pairs(keys, idx, n_pad, 1u, s);
+  if (rc) return rc;
+  rows_rank_kernel<<<blocks_for(n_rows, 256, 148 * 32), 256, 0, s>>>(keys, idx, n_rows, n_pad, 1, 0, 1, rank, sorted);
+  B2_LAUNCH_CHECK();
+  if (jack_out) {
+    k3m_jackknife_median_kernel<<<1, 256, 0, s>>>(sorted, n_rows, full, loo, jack_out);
+    B2_LAUNCH_CHECK();
+  }
+  M1Params P{};
+  P.rank = rank;
+  P.sorted = sorted;
+  P.indices = indices;
+  P.n_rows = n_rows;
+  P.n_sets = n_sets;
+  P.seed = seed;
+  P.resample_lo = resample_lo;
+  P.rule = full;
+  P.out = stat_out;
+  P.rk = make_round_keys(seed);
+  static PerDeviceOnce configured;
+  B2_CUDA(configured.run([] {
+    cudaError_t e = cudaFuncSetAttribute(k1m1_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)m1_smem_bytes(2048, 32));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(k1m1_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)m1_smem_bytes(kMedMaxRows, 256));
+    return e;
+  }));
+  if (n_rows <= 2048) {
+    const size_t smem = m1_smem_bytes(n_rows, 32);
+    const int grid = (int)std::min<int64_t>((n_sets + 7) / 8, (int64_t)sm_count() * 8);
+    k1m1_kernel<32><<<grid, 256, smem, s>>>(P);
+  } else {
+    const size_t smem = m1_smem_bytes(n_rows, 256);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
+    const int grid = (int)std::min<int64_t>(n_sets, (int64_t)sm_count() * per_sm);
+    k1m1_kernel<256><<<grid, 256, smem, s>>>(P);
+  }
+  B2_LAUNCH_CHECK();
+  return 0;
+}
 }  // namespace
 
 size_t b200boot_rank_columns_ws_bytes(int64_t n_rows, int64_t n_cols) {
@@ -1109,7 +1168,11 @@ int b200boot_nan_columns(const double* data, int64_t n_rows, int64_t n_cols, int
   if (!data || !flags || n_rows < 1 || n_cols < 1 || ld < n_cols) return fail(B200BOOT_EINVAL, "nan_columns: bad arguments");
   cudaStream_t s = as_stream(stream);
   B2_CUDA(cudaMemsetAsync(flags, 0, (size_t)(n_cols + 1) * sizeof(int32_t), s));
-  nan_columns_kernel<<<(unsigned)((n_cols + 31) / 32), 256, 0, s>>>(data, n_rows, n_cols, ld, flags);
+  // enough CTAs over the rows to fill the device when there are few columns
+  const int64_t col_ctas = (n_cols + 31) / 32;
+  const int64_t row_ctas = std::max<int64_t>(1, std::min<int64_t>((n_rows + 255) / 256, (4 * (int64_t)sm_count()) / col_ctas));
+  nan_columns_kernel<<<dim3((unsigned)col_ctas, (unsigned)std::min<int64_t>(row_ctas, 65535)), 256, 0, s>>>(
+      data, n_rows, n_cols, ld, flags);
   B2_LAUNCH_CHECK();
   return 0;
 }
@@ -1185,6 +1248,9 @@ int b200boot_resample_median_columns(const double* data, int64_t n_rows, int64_t
                                      const b200boot_rank_rule* rule, double* jack_out) {
   RankRule full, loo;
   if (int rc = rank_rules(rule, n_rows, &full, &loo)) return rc;
+  if (n_cols == 1 && data && stat_out && n_rows >= 1 && n_rows <= kMedMaxRows && resample_hi > resample_lo)
+    return median_single_column(data, n_rows, ld, seed, resample_lo, resample_hi - resample_lo, nullptr, stat_out,
+                                ws, ws_bytes, as_stream(stream), full, loo, jack_out);
   return median_resample(data, n_rows, n_cols, ld, seed, resample_lo, resample_hi, stat_out, ws,
                          ws_bytes, as_stream(stream), full, nullptr, jack_out, &loo);
 }
@@ -1196,6 +1262,9 @@ int b200boot_resample_median_columns_indexed(const double* data, int64_t n_rows,
   if (!indices) return fail(B200BOOT_EINVAL, "null indices");
   RankRule full, loo;
   if (int rc = rank_rules(rule, n_rows, &full, &loo)) return rc;
+  if (n_cols == 1 && data && stat_out && n_rows >= 1 && n_rows <= kMedMaxRows && n_sets > 0)
+    return median_single_column(data, n_rows, ld, 0, 0, n_sets, indices, stat_out, ws, ws_bytes, as_stream(stream),
+                                full, loo, nullptr);
   return median_resample(data, n_rows, n_cols, ld, 0, 0, n_sets, stat_out, ws, ws_bytes,
                          as_stream(stream), full, indices);
 }
