@@ -1248,9 +1248,20 @@ int b200boot_resample_median_columns(const double* data, int64_t n_rows, int64_t
                                      const b200boot_rank_rule* rule, double* jack_out) {
   RankRule full, loo;
   if (int rc = rank_rules(rule, n_rows, &full, &loo)) return rc;
-  if (n_cols == 1 && data && stat_out && n_rows >= 1 && n_rows <= kMedMaxRows && resample_hi > resample_lo)
-    return median_single_column(data, n_rows, ld, seed, resample_lo, resample_hi - resample_lo, nullptr, stat_out,
-                                ws, ws_bytes, as_stream(stream), full, loo, jack_out);
+  // one column — or a few long ones, where K1m would leave all but a few warps idle — go column
+  // by column through K1m1 (same seed: same index sets, the rows stay aligned across columns)
+  // (measured, n = 1e4, K1m vs the loop: N = 3000: D = 2 0.76 vs 0.53 ms, D = 4 0.77 vs 0.80;
+  // N = 1e4: D = 8 5.45 vs 3.18, D = 16 6.51 vs 6.23; N = 28 000: D = 16 31.6 vs 23.0, D = 32 49.5 vs 45.8)
+  const int few = n_rows <= 2048 ? 1 : (n_rows <= 4096 ? 2 : (n_rows <= 8192 ? 4 : (n_rows <= 16384 ? 16 : 32)));
+  if (data && stat_out && n_rows >= 1 && n_rows <= kMedMaxRows && resample_hi > resample_lo && n_cols <= few) {
+    const int64_t n_local = resample_hi - resample_lo;
+    for (int64_t d = 0; d < n_cols; ++d) {
+      int rc = median_single_column(data + d, n_rows, ld, seed, resample_lo, n_local, nullptr, stat_out + d * n_local,
+                                    ws, ws_bytes, as_stream(stream), full, loo, jack_out ? jack_out + 8 * d : nullptr);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   return median_resample(data, n_rows, n_cols, ld, seed, resample_lo, resample_hi, stat_out, ws,
                          ws_bytes, as_stream(stream), full, nullptr, jack_out, &loo);
 }
