@@ -558,7 +558,8 @@ def ci(
         `scikits_bootstrap_b200.REGISTRY_NAMES`); default np.average.
     Returns the interval endpoints, and the sorted bootstrap distribution as well
     when return_dist=True."""
-    if multi is None and not return_dist and not use_numba and (type(data) is np.ndarray or _is_tensor(data)):
+    if (multi is None and not return_dist and not use_numba
+            and (type(data) is np.ndarray or type(data) is tuple or _is_tensor(data))):
         res = _ci_small_direct(data, statfunction, alpha, n_samples, method, output, seed)
         if res is not None:
             return res
@@ -602,27 +603,33 @@ def _ci_small_direct(data, statfunction, alpha, n_samples, method, output, seed)
     if (type(alpha) is not float or type(n_samples) is not int or method not in ("pi", "bca")
             or output not in ("lowhigh", "errorbar") or _dist.active()):
         return None
-    if type(data) is np.ndarray:
+    if type(data) is tuple:                      # paired arrays (multi=None on a tuple means paired)
+        if not (len(data) == 2 and all(type(a) is np.ndarray and a.ndim == 1 and a.dtype == np.float64
+                                       and a.flags.c_contiguous for a in data)
+                and data[0].shape[0] == data[1].shape[0]):
+            return None
+        arrays, n_rows = data, data[0].shape[0]
+    elif type(data) is np.ndarray:
         if data.ndim != 1 or data.dtype != np.float64 or not data.flags.c_contiguous:
             return None
-        n_rows = data.shape[0]
+        arrays, n_rows = (data,), data.shape[0]
     else:
         torch = _device.require_cuda()
         if (not data.is_cuda or data.dtype != torch.float64 or data.dim() != 1 or not data.is_contiguous()
                 or data.device.index != torch.cuda.current_device()):
             return None
-        n_rows = data.shape[0]
+        arrays, n_rows = (data,), data.shape[0]
     spec = lookup(np.average if statfunction is None else statfunction)
-    if (spec is None or spec.n_arrays != 1 or spec.independent or spec.n_out != 1
+    if (spec is None or spec.n_arrays != len(arrays) or spec.independent or spec.n_out != 1
             or spec.stat_id == _abi.STAT_MEDIAN or n_rows < 1):
         return None
     _device.require_cuda()
-    if not _device.ci_small_supported(spec.stat_id, 1, n_rows, n_samples, 2):
+    if not _device.ci_small_supported(spec.stat_id, len(arrays), n_rows, n_samples, 2):
         return None
     key = _seed_key(seed)
     alphas = np.array([alpha / 2, 1 - alpha / 2])
     bca = method == "bca"
-    stat, vals, ranks, less, jack = _device.ci_small((data,), spec.stat_id, key, n_samples, alphas, bca,
+    stat, vals, ranks, less, jack = _device.ci_small(arrays, spec.stat_id, key, n_samples, alphas, bca,
                                                      bca or output == "errorbar")
     out = _small_tail(vals, ranks, less, jack, alphas, n_samples, bca, output)
     if out is not None:
