@@ -287,6 +287,15 @@ int b200boot_ci_small(const double* const* data, int n_arrays, int64_t n_rows, i
                       int64_t n_samples, const double* alphas, int n_alphas, int bca, int need_jack,
                       double* stat_out, double* result_dev, double* result_host, void* ws, size_t ws_bytes,
                       void* stream);
+/* pval of a short job (bootstrap.py:790-866) through the same single kernel: the statistic vector
+ * and, instead of levels and order statistics, #{stat op t0 [, t1]} (op a b200boot_cmp) in
+ * result[16].  data: device rows; host_data (may be NULL): the rows are still on the host and are
+ * staged through `staging` into `data` first.  Returns after the stream has been synchronised. */
+int b200boot_pval_small(const double* const* data, const double* const* host_data, double* const* staging,
+                        int n_arrays, int64_t n_rows, int stat_id, uint64_t seed, int64_t n_samples, int cmp_op,
+                        double t0, double t1, double* stat_out, double* result_dev, double* result_host, void* ws,
+                        size_t ws_bytes, void* stream);
+
 /* The tail of b200boot_ci_small as its own launch, for a statistic vector of any origin (K1 of
  * the general path, a gathered sharded vector), n_samples <= 2^21: #{stat < jack[0]}
  * (bootstrap.py:583), speculative BCa levels and ranks, exact order statistics — one CTA, the

@@ -368,6 +368,31 @@ def ci_small(arrays: Sequence, stat_id: int, seed: int, n_samples: int, alphas: 
     return (ent.stat[:n_samples], r[:na].copy(), r[8:8 + na].astype(np.int64), int(r[16]), r[17:25].copy())
 
 
+def pval_small(arrays: Sequence, stat_id: int, seed: int, n_samples: int, op: int, t0: float, t1: float) -> int:
+    """One kernel for a short pval(): #{statistic op t0 [, t1]} over n_samples resamples.  `arrays`:
+    float64 CUDA tensors or contiguous float64 numpy arrays."""
+    L = _abi.lib()
+    n_arrays = len(arrays)
+    ent = _small.get(n_samples)
+    ws, wsz = _ws.get(4096)
+    if isinstance(arrays[0], np.ndarray):
+        n_rows = arrays[0].shape[0]
+        for i, x in enumerate(arrays):
+            ent.host_ptrs[i] = x.ctypes.data
+        TRAFFIC["h2d"] += 8 * n_rows * n_arrays
+        rc = L.b200boot_pval_small(ent.rows_ptrs, ent.host_ptrs, ent.staging_ptrs, n_arrays, n_rows, stat_id, seed,
+                                   n_samples, op, t0, t1, ent.stat_ptr, ent.res_dev_ptr, ent.res_host_ptr, ws, wsz,
+                                   stream_ptr())
+    else:
+        n_rows = arrays[0].numel()
+        rc = L.b200boot_pval_small(_ptr_array(arrays), None, None, n_arrays, n_rows, stat_id, seed, n_samples, op,
+                                   t0, t1, ent.stat_ptr, ent.res_dev_ptr, ent.res_host_ptr, ws, wsz, stream_ptr())
+    if rc:
+        _abi.check(rc)
+    TRAFFIC["d2h"] += 32 * 8
+    return int(ent.res_np[16])
+
+
 def ci_tail_supported(n_samples: int, n_alphas: int) -> bool:
     return 1 <= n_samples <= (1 << 21) and 1 <= n_alphas <= 8
 

@@ -935,7 +935,50 @@ def pval(
     by row, as the reference does (bootstrap.py:861).  Beyond the reference (whose
     pval treats any truthy `multi` as paired, bootstrap.py:841-850): multi='independent'
     resamples each array on its own, as `ci` does."""
+    if multi is None and isinstance(compfunction, DeviceCompare):
+        res = _pval_small_direct(data, statfunction, compfunction, n_samples, seed)
+        if res is not None:
+            return res
     return _pval_impl(data, statfunction, compfunction, n_samples, multi, seed, None)
+
+
+def _pval_small_direct(data, statfunction, compfunction, n_samples, seed):
+    """Short pval() calls on one contiguous 1-D float64 array (numpy or CUDA) or a pair of such
+    numpy arrays with a device criterion: one kernel (the fused small call counting the criterion
+    instead of selecting order statistics).  None when the call is not of that form; the value is
+    the general path's."""
+    if type(n_samples) is not int or _dist.active():
+        return None
+    if type(data) is tuple:
+        if not (len(data) == 2 and all(type(a) is np.ndarray and a.ndim == 1 and a.dtype == np.float64
+                                       and a.flags.c_contiguous for a in data)
+                and data[0].shape[0] == data[1].shape[0]):
+            return None
+        arrays, n_rows = data, data[0].shape[0]
+    elif type(data) is np.ndarray:
+        if data.ndim != 1 or data.dtype != np.float64 or not data.flags.c_contiguous:
+            return None
+        arrays, n_rows = (data,), data.shape[0]
+    elif _is_tensor(data):
+        torch = _device.require_cuda()
+        if (not data.is_cuda or data.dtype != torch.float64 or data.dim() != 1 or not data.is_contiguous()
+                or data.device.index != torch.cuda.current_device()):
+            return None
+        arrays, n_rows = (data,), data.shape[0]
+    else:
+        return None
+    if not callable(statfunction):
+        return None
+    spec = lookup(statfunction)
+    if (spec is None or spec.n_arrays != len(arrays) or spec.independent or spec.n_out != 1
+            or spec.stat_id == _abi.STAT_MEDIAN or n_rows < 1):
+        return None
+    _device.require_cuda()
+    if not _device.ci_small_supported(spec.stat_id, len(arrays), n_rows, n_samples, 1):
+        return None
+    key = _seed_key(seed)
+    hits = _device.pval_small(arrays, spec.stat_id, key, n_samples, compfunction.op, compfunction.t0, compfunction.t1)
+    return np.float64(hits / float(n_samples))
 
 
 def pval_indexed(data, statfunction=np.average, compfunction=positive, indices=None, multi=None):

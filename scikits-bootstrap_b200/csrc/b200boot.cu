@@ -567,12 +567,13 @@ double* device_view_of_pinned(double* host) {
 int enqueue_ci_small(const double* const* data, int n_arrays, int64_t n_rows, int stat_id, uint64_t seed,
                      int64_t n_samples, const double* alphas, int n_alphas, int bca, int need_jack,
                      double* stat_out, double* result_dev, double* result_host, void* ws, size_t ws_bytes,
-                     cudaStream_t s) {
+                     cudaStream_t s, int cmp_op = -1, double cmp_t0 = 0.0, double cmp_t1 = 0.0) {
   int rc = check_moment_stat(stat_id, n_arrays, n_rows);
   if (rc) return rc;
-  if (!b200boot_ci_small_supported(stat_id, n_arrays, n_rows, n_samples, n_alphas))
+  if (!b200boot_ci_small_supported(stat_id, n_arrays, n_rows, n_samples, cmp_op >= 0 ? 1 : n_alphas))
     return fail(B200BOOT_EUNSUPPORTED, "ci_small: shape outside the small-call path");
-  if (!data || !alphas || !stat_out || !result_dev) return fail(B200BOOT_EINVAL, "null pointer");
+  if (!data || (!alphas && n_alphas > 0) || !stat_out || !result_dev) return fail(B200BOOT_EINVAL, "null pointer");
+  if (cmp_op >= 0) n_alphas = 0, bca = 0, need_jack = 0;      // pval: the tail only counts
   if (bca) need_jack = 1;
   if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
     return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
@@ -603,6 +604,9 @@ int enqueue_ci_small(const double* const* data, int n_arrays, int64_t n_rows, in
   P.tail.staged = n_samples <= kFusedStageMax ? 1 : 0;
   P.tail.n_bins = kBktBins;
   P.tail.ranks = nullptr;
+  P.tail.cmp_op = cmp_op;
+  P.tail.cmp_t0 = cmp_t0;
+  P.tail.cmp_t1 = cmp_t1;
   const size_t cell = (size_t)P.smem_stride * 8 * n_arrays;
   const size_t tail = (P.tail.staged ? tail_stage_bytes(n_samples) : 0) + tail_scratch_bytes();
   const size_t smem = std::max(cell, tail);
@@ -655,6 +659,7 @@ int b200boot_ci_tail(const double* stat, int64_t n_samples, const double* jack, 
   P.staged = n_samples <= kFusedStageMax ? 1 : 0;
   P.n_bins = P.staged ? kBktBins : kBktBinsWide;
   P.ranks = nullptr;
+  P.cmp_op = -1;
   const size_t smem = (P.staged ? tail_stage_bytes(n_samples) : 0) + tail_scratch_bytes(P.n_bins);
   static PerDeviceOnce configured;
   B2_CUDA(configured.run([] {
@@ -686,6 +691,30 @@ int b200boot_ci_small_host(const double* const* host_data, double* const* stagin
   }
   const int rc = enqueue_ci_small(data_dev, n_arrays, n_rows, stat_id, seed, n_samples, alphas, n_alphas, bca,
                                   need_jack, stat_out, result_dev, result_host, ws, ws_bytes, s);
+  if (rc) return rc;
+  B2_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int b200boot_pval_small(const double* const* data, const double* const* host_data, double* const* staging,
+                        int n_arrays, int64_t n_rows, int stat_id, uint64_t seed, int64_t n_samples, int cmp_op,
+                        double t0, double t1, double* stat_out, double* result_dev, double* result_host, void* ws,
+                        size_t ws_bytes, void* stream) {
+  if (cmp_op < B200BOOT_CMP_LT || cmp_op > B200BOOT_CMP_BETWEEN) return fail(B200BOOT_EINVAL, "pval_small: bad criterion");
+  if (!data || !result_host || n_arrays < 1 || n_arrays > 2 || n_rows < 1)
+    return fail(B200BOOT_EINVAL, "pval_small: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  if (host_data) {                                  // rows still on the host: staged like b200boot_ci_small_host
+    if (!staging) return fail(B200BOOT_EINVAL, "pval_small: staging buffers are required for host rows");
+    const size_t bytes = (size_t)n_rows * sizeof(double);
+    for (int a = 0; a < n_arrays; ++a) {
+      if (!host_data[a] || !staging[a] || !data[a]) return fail(B200BOOT_EINVAL, "pval_small: null pointer");
+      memcpy(staging[a], host_data[a], bytes);
+      B2_CUDA(cudaMemcpyAsync(const_cast<double*>(data[a]), staging[a], bytes, cudaMemcpyHostToDevice, s));
+    }
+  }
+  const int rc = enqueue_ci_small(data, n_arrays, n_rows, stat_id, seed, n_samples, nullptr, 0, 0, 0, stat_out,
+                                  result_dev, result_host, ws, ws_bytes, s, cmp_op, t0, t1);
   if (rc) return rc;
   B2_CUDA(cudaStreamSynchronize(s));
   return 0;

@@ -119,6 +119,8 @@ struct SmallTailParams {
   const int64_t* ranks;   // select-only mode: the ranks are given (stride rank_stride), no count / levels
   int64_t rank_stride;
   int64_t res_stride;     // res[a * res_stride] (select-only mode; the tail writes its block densely)
+  int cmp_op;             // pval mode (n_alphas == 0): res[16] = #{stat op t0 [, t1]}, a b200boot_cmp; else -1
+  double cmp_t0, cmp_t1;
   double* res;
 };
 
@@ -225,6 +227,8 @@ __device__ __noinline__ void small_tail_bucket(const SmallTailParams& P, unsigne
   const int64_t n = P.n_samples;
   const int A = P.n_alphas;
   const bool staged = P.staged != 0, bca = P.bca != 0;
+  const int cmp_op = P.cmp_op;
+  const double cmp_t0 = P.cmp_t0, cmp_t1 = P.cmp_t1;
   const double* const gstat = P.stat;
   double* s_stat = reinterpret_cast<double*>(smem);
   unsigned char* scratch = smem + (staged ? tail_stage_bytes(n) : 0);
@@ -247,6 +251,17 @@ __device__ __noinline__ void small_tail_bucket(const SmallTailParams& P, unsigne
       hi = fmax(hi, v);
     }
     less += (bca && v < ostat) ? 1u : 0u;                          // strict '<'  bootstrap.py:583
+    if (cmp_op >= 0) {                                               // pval criterion  bootstrap.py:861-866
+      bool hit;
+      switch (cmp_op) {
+        case B200BOOT_CMP_LT: hit = v < cmp_t0; break;
+        case B200BOOT_CMP_LE: hit = v <= cmp_t0; break;
+        case B200BOOT_CMP_GT: hit = v > cmp_t0; break;
+        case B200BOOT_CMP_GE: hit = v >= cmp_t0; break;
+        default: hit = (cmp_t0 <= v) && (v <= cmp_t1); break;
+      }
+      less += hit ? 1u : 0u;
+    }
   });
   for (int i = tid; i < n_bins; i += kSmallThreads) T.hist[i] = 0u;
 #pragma unroll
@@ -274,6 +289,16 @@ __device__ __noinline__ void small_tail_bucket(const SmallTailParams& P, unsigne
   }
   const double* stat = staged ? s_stat : gstat;
   const double* jack = P.jack;
+  if (A == 0) {                                      // pval mode: the count is the result
+    if (tid == 0) {
+      P.res[16] = (double)less;
+      if (res_host) {
+        res_host[16] = (double)less;
+        __threadfence_system();
+      }
+    }
+    return;
+  }
 
   if (P.ranks != nullptr) {
     if (tid < A) {
@@ -435,6 +460,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k5_select_bucket_kernel(cons
     P.rank_stride = n_cols;
     P.res = out + (int64_t)a_lo * n_cols + d;
     P.res_stride = n_cols;
+    P.cmp_op = -1;
     small_tail_bucket(P, sel_smem, nullptr);
     __syncthreads();
   }

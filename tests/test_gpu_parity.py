@@ -776,6 +776,33 @@ def test_long_numpy_rows_travel_under_the_occupancy_chains(monkeypatch):
     assert calls[-3:] == [False, False, True] or calls[-2:] == [False, True]
 
 
+def test_small_pval_is_one_kernel_and_equals_general_path(monkeypatch):
+    """Short pval() calls with a device criterion run the fused small-call kernel, counting the
+    criterion instead of selecting order statistics; the value is the general path's."""
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal(800) + 0.05
+    a, b = rng.gamma(2, 1, 500), rng.gamma(2.2, 1, 500)
+    crits = [boot.positive, boot.less_than(0.04), boot.less_equal(0.05), boot.greater_equal(0.0),
+             boot.between(0.0, 0.08)]
+    calls = []
+    real = _device.pval_small
+    monkeypatch.setattr(_device, "pval_small", lambda *a_, **k: calls.append(1) or real(*a_, **k))
+    jobs = [(x, np.mean), (x, np.std), (dev(x), np.mean), ((a, b), boot.ratio_of_means), ((a, b), boot.pearson_r)]
+    small = [boot.pval(d, f, c, n_samples=3000, seed=5) for d, f in jobs for c in crits]
+    assert len(calls) == len(jobs) * len(crits)
+    assert all(isinstance(v, np.float64) for v in small)
+    monkeypatch.setattr(_device, "ci_small_supported", lambda *a_: False)
+    general = [boot.pval(d, f, c, n_samples=3000, seed=5) for d, f in jobs for c in crits]
+    assert len(calls) == len(jobs) * len(crits)
+    assert small == general
+    assert 0.0 < small[0] < 1.0
+    # what does not qualify takes the general path: host callables, medians, 2-D data
+    boot.pval(x, np.mean, lambda s: s > 0, n_samples=200, seed=1)
+    boot.pval(x, np.median, boot.positive, n_samples=200, seed=1)
+    boot.pval(x.reshape(-1, 2), boot.mean_axis0, boot.positive, n_samples=200, seed=1)
+    assert len(calls) == len(jobs) * len(crits)
+
+
 def test_small_call_wrong_speculative_ranks_are_caught(monkeypatch):
     """The device's ranks are only a guess: when the host's own levels give other ranks the
     order statistics are selected again with the host's."""
