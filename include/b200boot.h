@@ -230,6 +230,19 @@ int b200boot_nan_columns(const double* data, int64_t n_rows, int64_t n_cols, int
 int b200boot_nan_fixup(const double* src, int64_t stride, int64_t n_rows, const int64_t* indices, int64_t n_sets,
                        double* out, void* stream);
 int b200boot_nan_poison_rows(double* table, int64_t n_cols, int width, const int32_t* flags, void* stream);
+/* A whole ci() of a rank statistic (np.median, or a quantile through `rule`) of ONE resident
+ * column (N <= 28 672) in one library call: (host rows staged,) the column sorted, its jackknife
+ * summary, the resamples (K1m1) and the single-CTA tail of b200boot_ci_tail; returns after the
+ * stream has been synchronised with the 32-double result block in result_host
+ * ([25] = 1 when the column holds NaNs: numpy's NaN rule applies and the caller takes the general
+ * path).  data: device rows (n_rows doubles; the destination of the copy when host_data is given);
+ * result_dev: 48 doubles; ws: b200boot_workspace_bytes(B200BOOT_STAT_MEDIAN, n_rows, 1, 1, n_samples, 1). */
+int b200boot_ci_median_small_supported(int64_t n_rows, int64_t n_samples, int n_alphas);
+int b200boot_ci_median_small(const double* data, const double* host_data, double* staging, int64_t n_rows,
+                             uint64_t seed, int64_t n_samples, const double* alphas, int n_alphas, int bca,
+                             int need_jack, const b200boot_rank_rule* rule, double* stat_out, double* result_dev,
+                             double* result_host, void* ws, size_t ws_bytes, void* stream);
+
 /* K3m on a sorted 1-D array of any length: out float64[8] as b200boot_jackknife. */
 int b200boot_jackknife_median_sorted(const double* sorted_vals, int64_t n_rows, double* out, void* stream,
                                      const b200boot_rank_rule* rule);

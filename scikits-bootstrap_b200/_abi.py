@@ -80,6 +80,9 @@ SIGNATURES = {
     "b200boot_resample_stat_host": (_int, [_vp, _vp, _int, _i64, _int, _u64, _i64, _i64, _vp, _vp, _sz, _vp, _vp]),
     "b200boot_pval_small": (_int, [_vp, _vp, _vp, _int, _i64, _int, _u64, _i64, _int, C.c_double, C.c_double, _vp, _vp, _vp,
                                    _vp, _sz, _vp]),
+    "b200boot_ci_median_small_supported": (_int, [_i64, _i64, _int]),
+    "b200boot_ci_median_small": (_int, [_vp, _vp, _vp, _i64, _u64, _i64, _vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp,
+                                        _sz, _vp]),
     "b200boot_ci_small_host": (_int, [_vp, _vp, _vp, _int, _i64, _int, _u64, _i64, _vp, _int, _int, _int, _vp, _vp, _vp,
                                       _vp, _sz, _vp]),
     "b200boot_tile_counts": (_int, [_u64, _i64, _int, _i64, _i64, _vp, _vp, _vp]),

@@ -393,6 +393,40 @@ def pval_small(arrays: Sequence, stat_id: int, seed: int, n_samples: int, op: in
     return int(ent.res_np[16])
 
 
+def ci_median_small_supported(n_rows: int, n_samples: int, n_alphas: int) -> bool:
+    return 1 <= n_rows <= MEDIAN_RESIDENT_ROWS and ci_tail_supported(n_samples, n_alphas)
+
+
+def ci_median_small(x, seed: int, n_samples: int, alphas: np.ndarray, bca: bool, need_jack: bool, rule=None):
+    """One library call for ci() of np.median / a quantile of one resident column.  x: a contiguous
+    float64 numpy array or CUDA tensor.  Returns (stat CUDA view, endpoints[A], ranks[A] int64, less,
+    jack[8], has_nan)."""
+    torch = _torch()
+    L = _abi.lib()
+    a = np.ascontiguousarray(alphas, dtype=np.float64).reshape(-1)
+    na = len(a)
+    ent = _small.get(n_samples)
+    for i in range(na):
+        ent.alphas[i] = a[i]
+    if isinstance(x, np.ndarray):
+        n_rows = x.shape[0]
+        TRAFFIC["h2d"] += 8 * n_rows
+        data_ptr, host_ptr, staging_ptr = ent.rows_ptrs[0], x.ctypes.data, ent.staging_ptrs[0]
+    else:
+        n_rows = x.numel()
+        data_ptr, host_ptr, staging_ptr = x.data_ptr(), None, None
+    ws, wsz = workspace_for(_abi.STAT_MEDIAN, n_rows, 1, 1, n_samples, 1)
+    rc = L.b200boot_ci_median_small(data_ptr, host_ptr, staging_ptr, n_rows, seed, n_samples, ent.alphas_ptr, na,
+                                    int(bca), int(need_jack), _rule_ptr(rule), ent.stat_ptr, ent.res_dev_ptr,
+                                    ent.res_host_ptr, ws, wsz, stream_ptr())
+    if rc:
+        _abi.check(rc)
+    TRAFFIC["d2h"] += 32 * 8
+    r = ent.res_np
+    return (ent.stat[:n_samples], r[:na].copy(), r[8:8 + na].astype(np.int64), int(r[16]), r[17:25].copy(),
+            bool(r[25] != 0.0))
+
+
 def ci_tail_supported(n_samples: int, n_alphas: int) -> bool:
     return 1 <= n_samples <= (1 << 21) and 1 <= n_alphas <= 8
 

@@ -561,10 +561,20 @@ def ci(
     if (multi is None and not return_dist and not use_numba
             and (type(data) is np.ndarray or type(data) is tuple or _is_tensor(data))):
         res = _ci_small_direct(data, statfunction, alpha, n_samples, method, output, seed)
-        if res is not None:
+        if type(res) is _RetryWithKey:        # the general path, with the key the seed was already turned into
+            seed = res.key
+        elif res is not None:
             return res
     return _ci_impl(data, statfunction, alpha, n_samples, method, output, epsilon, multi,
                     return_dist, seed, use_numba, None)
+
+
+class _RetryWithKey:
+    """The direct path found something out of its ordinary (NaNs under a rank statistic) after
+    the seed had been consumed: the general path runs with that key."""
+
+    def __init__(self, key):
+        self.key = key
 
 
 class _SmallRun:
@@ -620,17 +630,28 @@ def _ci_small_direct(data, statfunction, alpha, n_samples, method, output, seed)
             return None
         arrays, n_rows = (data,), data.shape[0]
     spec = lookup(np.average if statfunction is None else statfunction)
-    if (spec is None or spec.n_arrays != len(arrays) or spec.independent or spec.n_out != 1
-            or spec.stat_id == _abi.STAT_MEDIAN or n_rows < 1):
+    if (spec is None or spec.n_arrays != len(arrays) or spec.independent or spec.n_out != 1 or n_rows < 1):
         return None
     _device.require_cuda()
-    if not _device.ci_small_supported(spec.stat_id, len(arrays), n_rows, n_samples, 2):
-        return None
-    key = _seed_key(seed)
-    alphas = np.array([alpha / 2, 1 - alpha / 2])
     bca = method == "bca"
-    stat, vals, ranks, less, jack = _device.ci_small(arrays, spec.stat_id, key, n_samples, alphas, bca,
-                                                     bca or output == "errorbar")
+    if spec.stat_id == _abi.STAT_MEDIAN:
+        # rank statistics of one resident column: sort, jackknife, resamples (K1m1) and tail in one
+        # library call; data holding NaNs go to the general path (numpy's NaN rule)
+        if not _device.ci_median_small_supported(n_rows, n_samples, 2):
+            return None
+        key = _seed_key(seed)
+        alphas = np.array([alpha / 2, 1 - alpha / 2])
+        stat, vals, ranks, less, jack, has_nan = _device.ci_median_small(
+            arrays[0], key, n_samples, alphas, bca, bca or output == "errorbar", rule=_device.rank_rule(n_rows, spec.q))
+        if has_nan:
+            return _RetryWithKey(key)
+    else:
+        if not _device.ci_small_supported(spec.stat_id, len(arrays), n_rows, n_samples, 2):
+            return None
+        key = _seed_key(seed)
+        alphas = np.array([alpha / 2, 1 - alpha / 2])
+        stat, vals, ranks, less, jack = _device.ci_small(arrays, spec.stat_id, key, n_samples, alphas, bca,
+                                                         bca or output == "errorbar")
     out = _small_tail(vals, ranks, less, jack, alphas, n_samples, bca, output)
     if out is not None:
         return out

@@ -642,12 +642,14 @@ int b200boot_ci_tail_supported(int64_t n_samples, int n_alphas) {
   return n_samples >= 1 && n_samples <= kTailMaxValues && n_alphas >= 1 && n_alphas <= kSelMaxAlphas ? 1 : 0;
 }
 
-int b200boot_ci_tail(const double* stat, int64_t n_samples, const double* jack, const double* alphas, int n_alphas,
-                     int bca, double* result_dev, double* result_host, void* stream) {
+}  // extern "C"
+
+namespace {
+int enqueue_ci_tail(const double* stat, int64_t n_samples, const double* jack, const double* alphas, int n_alphas,
+                    int bca, double* result_dev, double* result_host, cudaStream_t s, const double* nan_probe) {
   if (!stat || !alphas || !result_dev || (bca && !jack)) return fail(B200BOOT_EINVAL, "ci_tail: null pointer");
   if (!b200boot_ci_tail_supported(n_samples, n_alphas))
     return fail(B200BOOT_EUNSUPPORTED, "ci_tail: 1 <= n_samples <= 2^21, 1 <= n_alphas <= 8");
-  cudaStream_t s = as_stream(stream);
   SmallTailParams P{};
   P.stat = stat;
   P.n_samples = n_samples;
@@ -668,11 +670,20 @@ int b200boot_ci_tail(const double* stat, int64_t n_samples, const double* jack, 
                                               tail_scratch_bytes(kBktBinsWide)));
   }));
   double* host_view = device_view_of_pinned(result_host);
-  ci_tail_kernel<<<1, kSmallThreads, smem, s>>>(P, host_view);
+  ci_tail_kernel<<<1, kSmallThreads, smem, s>>>(P, host_view, nan_probe);
   B2_LAUNCH_CHECK();
   if (result_host && host_view == nullptr)
     B2_CUDA(cudaMemcpyAsync(result_host, result_dev, kSmallResultDoubles * sizeof(double), cudaMemcpyDeviceToHost, s));
   return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int b200boot_ci_tail(const double* stat, int64_t n_samples, const double* jack, const double* alphas, int n_alphas,
+                     int bca, double* result_dev, double* result_host, void* stream) {
+  return enqueue_ci_tail(stat, n_samples, jack, alphas, n_alphas, bca, result_dev, result_host, as_stream(stream),
+                         nullptr);
 }
 
 int b200boot_ci_small_host(const double* const* host_data, double* const* staging, double* const* data_dev,
@@ -1097,7 +1108,8 @@ int rank_rules(const b200boot_rank_rule* rule, int64_t n_rows, RankRule* full, R
 // sorted values + rank table), then a warp (N <= 2048) or a CTA per resample.
 int median_single_column(const double* data, int64_t n_rows, int64_t ld, uint64_t seed, int64_t resample_lo,
                          int64_t n_sets, const int64_t* indices, double* stat_out, void* ws, size_t ws_bytes,
-                         cudaStream_t s, const RankRule& full, const RankRule& loo, double* jack_out) {
+                         cudaStream_t s, const RankRule& full, const RankRule& loo, double* jack_out,
+                         const double** sorted_out = nullptr) {
   if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
     return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
   int64_t n_pad = 1;
@@ -1108,6 +1120,7 @@ int median_single_column(const double* data, int64_t n_rows, int64_t ld, uint64_
   double* sorted = cv.take<double>((size_t)n_rows);
   int32_t* rank = cv.take<int32_t>((size_t)n_rows);
   if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+  if (sorted_out) *sorted_out = sorted;
   psort_load_kernel<<<blocks_for(n_pad, 256, 148 * 32), 256, 0, s>>>(data, n_rows, 1, ld, n_pad, keys, idx);
   B2_LAUNCH_CHECK();
   int rc = psort_pairs(keys, idx, n_pad, 1u, s);
@@ -1307,6 +1320,40 @@ int b200boot_resample_median_columns_indexed(const double* data, int64_t n_rows,
                                 full, loo, nullptr);
   return median_resample(data, n_rows, n_cols, ld, 0, 0, n_sets, stat_out, ws, ws_bytes,
                          as_stream(stream), full, indices);
+}
+
+int b200boot_ci_median_small_supported(int64_t n_rows, int64_t n_samples, int n_alphas) {
+  return n_rows >= 1 && n_rows <= kMedMaxRows && b200boot_ci_tail_supported(n_samples, n_alphas) ? 1 : 0;
+}
+
+int b200boot_ci_median_small(const double* data, const double* host_data, double* staging, int64_t n_rows,
+                             uint64_t seed, int64_t n_samples, const double* alphas, int n_alphas, int bca,
+                             int need_jack, const b200boot_rank_rule* rule, double* stat_out, double* result_dev,
+                             double* result_host, void* ws, size_t ws_bytes, void* stream) {
+  if (!data || !alphas || !stat_out || !result_dev || !result_host)
+    return fail(B200BOOT_EINVAL, "ci_median_small: null pointer");
+  if (!b200boot_ci_median_small_supported(n_rows, n_samples, n_alphas))
+    return fail(B200BOOT_EUNSUPPORTED, "ci_median_small: one resident column, n_samples <= 2^21, <= 8 levels");
+  RankRule full, loo;
+  if (int rc = rank_rules(rule, n_rows, &full, &loo)) return rc;
+  cudaStream_t s = as_stream(stream);
+  if (host_data) {
+    if (!staging) return fail(B200BOOT_EINVAL, "ci_median_small: a staging buffer is required for host rows");
+    memcpy(staging, host_data, (size_t)n_rows * sizeof(double));
+    B2_CUDA(cudaMemcpyAsync(const_cast<double*>(data), staging, (size_t)n_rows * sizeof(double),
+                            cudaMemcpyHostToDevice, s));
+  }
+  if (bca) need_jack = 1;
+  double* jack = need_jack ? result_dev + kSmallResultDoubles : nullptr;
+  const double* sorted = nullptr;
+  int rc = median_single_column(data, n_rows, 1, seed, 0, n_samples, nullptr, stat_out, ws, ws_bytes, s, full, loo,
+                                jack, &sorted);
+  if (rc) return rc;
+  rc = enqueue_ci_tail(stat_out, n_samples, jack, alphas, n_alphas, bca, result_dev, result_host, s,
+                       sorted + (n_rows - 1));
+  if (rc) return rc;
+  B2_CUDA(cudaStreamSynchronize(s));
+  return 0;
 }
 
 int b200boot_jackknife_median_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld,

@@ -433,8 +433,16 @@ __device__ __noinline__ void small_tail_bucket(const SmallTailParams& P, unsigne
 // The tail as its own launch, for statistic vectors of any origin (the general path's K1, a
 // gathered sharded vector) up to kTailMaxValues values: one CTA, one result block, one host wait
 // instead of count -> host -> 8 x (hist + pick) -> host.
-__global__ void __launch_bounds__(kSmallThreads, 1) ci_tail_kernel(const SmallTailParams P, double* res_host) {
+// nan_probe (may be null): the largest value of a sorted column; res[25] = 1 when it is NaN, i.e. the
+// column holds NaNs and numpy's rule for rank statistics applies (the caller then takes the general path).
+__global__ void __launch_bounds__(kSmallThreads, 1) ci_tail_kernel(const SmallTailParams P, double* res_host,
+                                                                 const double* nan_probe) {
   extern __shared__ __align__(128) unsigned char tail_smem[];
+  if (threadIdx.x == 0) {
+    const double flag = (nan_probe != nullptr && __ldcg(nan_probe) != __ldcg(nan_probe)) ? 1.0 : 0.0;
+    P.res[25] = flag;
+    if (res_host) res_host[25] = flag;
+  }
   small_tail_bucket(P, tail_smem, res_host);
 }
 

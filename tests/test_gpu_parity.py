@@ -717,6 +717,7 @@ def test_single_launch_tail_equals_general_tail(stat_name, n, n_arrays, monkeypa
     calls = []
     real = _device.ci_tail
     monkeypatch.setattr(_device, "ci_tail", lambda *a, **k: calls.append(1) or real(*a, **k))
+    monkeypatch.setattr(_device, "ci_median_small_supported", lambda *a: False)   # the general job, not the one-call median
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         one = [boot.ci(data, f, seed=4, **k) for k in kws]
@@ -801,6 +802,39 @@ def test_small_pval_is_one_kernel_and_equals_general_path(monkeypatch):
     boot.pval(x, np.median, boot.positive, n_samples=200, seed=1)
     boot.pval(x.reshape(-1, 2), boot.mean_axis0, boot.positive, n_samples=200, seed=1)
     assert len(calls) == len(jobs) * len(crits)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 100, 1000, 2048, 2049, 10000, 28672])
+def test_one_call_median_equals_general_path(n, monkeypatch):
+    """ci() of np.median / a quantile of one resident column is one library call (sort, jackknife,
+    K1m1 resamples, single-CTA tail); same interval as the general path and as the oracle on the
+    materialised indices; NaN data fall back to the general path (numpy's rule)."""
+    import warnings
+    rng = np.random.default_rng(n)
+    x = np.round(rng.gamma(2.0, 1.0, n), 3)
+    calls = []
+    real = _device.ci_median_small
+    monkeypatch.setattr(_device, "ci_median_small", lambda *a, **k: calls.append(1) or real(*a, **k))
+    kws = [dict(method="bca"), dict(method="pi"), dict(method="bca", output="errorbar", alpha=0.2)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for f in (np.median, boot.quantile(0.8)):
+            one = [boot.ci(x, f, n_samples=700, seed=3, **k) for k in kws] + [boot.ci(dev(x), f, n_samples=700, seed=3)]
+            assert len(calls) == len(kws) + 1
+            monkeypatch.setattr(_device, "ci_median_small_supported", lambda *a: False)
+            general = [boot.ci(x, f, n_samples=700, seed=3, **k) for k in kws] + [boot.ci(dev(x), f, n_samples=700, seed=3)]
+            monkeypatch.undo()
+            monkeypatch.setattr(_device, "ci_median_small", lambda *a, **k: calls.append(1) or real(*a, **k))
+            for a, b in zip(one, general):
+                assert_array_equal(a, b)
+            calls.clear()
+        if n >= 7:
+            y = x.copy()
+            y[n // 2] = np.nan
+            got = boot.ci(y, np.median, n_samples=300, seed=4, method="pi")
+            idx = np.array(list(boot.bootstrap_indices(y, 300, seed=4)))
+            want = orc.ci_from_indices((y,), np.median, idx, (0.025, 0.975), 300, "pi")
+            assert_array_equal(got, want)
 
 
 def test_small_call_wrong_speculative_ranks_are_caught(monkeypatch):
