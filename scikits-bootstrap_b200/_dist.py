@@ -77,6 +77,13 @@ def all_gather_ragged(t, n_total: int, dim: int = -1):
     rank, ws = world()
     sizes = [shard_range(n_total, r, ws)[1] - shard_range(n_total, r, ws)[0] for r in range(ws)]
     width = max(sizes)
+    if (min(sizes) == width and t.numel() == width and t.is_contiguous()
+            and dist.get_backend(_group) == "nccl"):
+        # equal shards of one row (the usual case: a scalar statistic, n divisible by the ranks):
+        # the ranks' shards land side by side in the result, no padding, no list of parts, no cat
+        out = torch.empty(t.shape[:-1] + (n_total,), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out.view(-1), t.view(-1), group=_group)
+        return out
     pad = torch.zeros(t.shape[:-1] + (width,), dtype=t.dtype, device=t.device)
     pad[..., : t.shape[-1]] = t
     parts = [torch.empty_like(pad) for _ in range(ws)]
