@@ -1132,6 +1132,43 @@ def test_input_on_another_device_and_threads():
         assert_array_equal(a, b)
 
 
+def test_direct_paths_from_concurrent_threads():
+    """The one-call paths (fused small call, one-call median, small pval, host rows under K0) keep
+    their buffers per thread and stream: four threads at once give the single-thread results."""
+    import threading
+    rng = np.random.default_rng(1)
+    small, mid, long_rows = rng.standard_normal(900), rng.gamma(2.0, 1.0, 5000), rng.standard_normal(700_000)
+
+    def job(seed):
+        return [boot.ci(small, np.mean, n_samples=3000, seed=seed),
+                boot.ci(small, np.std, n_samples=500, seed=seed, method="pi"),
+                boot.ci(mid, np.median, n_samples=800, seed=seed),
+                boot.ci(small, boot.quantile(0.25), n_samples=800, seed=seed, method="pi"),
+                np.asarray(boot.pval(small, np.mean, boot.less_than(0.02), n_samples=2000, seed=seed)),
+                boot.ci((small, small[::-1].copy()), boot.pearson_r, n_samples=600, seed=seed),
+                boot.ci(long_rows, np.mean, n_samples=64, seed=seed, method="pi")]
+    ref = [job(s) for s in range(4)]
+    got = [None] * 4
+    errors = []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                got[i] = job(i)
+        except Exception as e:                      # noqa: BLE001 - surfaced below
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for a, b in zip(got, ref):
+        for u, v in zip(a, b):
+            assert_array_equal(u, v)
+
+
 def test_paired_tuple_equals_axis0_columns():
     """A (N, D) array under an axis-0 statistic shares one index set across columns
     (bootstrap.py:431): each column equals the 1-D run with the same seed."""
