@@ -15,6 +15,7 @@
 #include "k6_gemm.cuh"
 #include "k6i_mma.cuh"
 #include "k6i_pipe.cuh"
+#include "k1mg_gemm.cuh"
 #include "k3_jackknife.cuh"
 #include "k45_interval.cuh"
 #include "small_call.cuh"
@@ -296,6 +297,143 @@ int loo_values(const double** rows, int64_t n_rows, int stat, ResampleWs& w, dou
 
 }  // namespace
 
+namespace {
+
+// ---- K1mg: medians of many short columns through the tensor cores (csrc/k1mg_gemm.cuh) --------
+constexpr int64_t kMgMinCols = 64;
+constexpr int64_t kMgMaxRows = 1024;      // resident count tile (128 KB) + two digit stages + two permutation blocks
+
+inline int64_t mg_k_pad(int64_t n_rows) { return ((n_rows + kI8KChunk - 1) / kI8KChunk) * kI8KChunk; }
+inline int64_t mg_col_tiles(int64_t n_cols) { return (n_cols + kMgColsPerTile - 1) / kMgColsPerTile; }
+inline bool median_gemm_applies(int64_t n_rows, int64_t n_cols) {
+  return n_cols >= kMgMinCols && n_rows >= 32 && n_rows <= kMgMaxRows;
+}
+
+struct MgWs {
+  int32_t* flags;
+  uint64_t* keys;
+  uint32_t* idx;
+  double* sorted;
+  int32_t* rank;
+  uint8_t* counts;
+  unsigned char* a_img;
+  unsigned char* b_img;
+  uint16_t* perm_img;
+  int64_t n_pad, k_pad;
+};
+
+MgWs mg_carve(Carver& cv, int64_t n_rows, int64_t n_cols, int64_t n_local) {
+  MgWs w{};
+  w.n_pad = 1;
+  while (w.n_pad < n_rows) w.n_pad <<= 1;
+  w.k_pad = mg_k_pad(n_rows);
+  const int64_t m_tiles = (std::max<int64_t>(n_local, 1) + kI8M - 1) / kI8M;
+  w.flags = cv.take<int32_t>(64);
+  w.keys = cv.take<uint64_t>((size_t)w.n_pad * n_cols);
+  w.idx = cv.take<uint32_t>((size_t)w.n_pad * n_cols);
+  w.sorted = cv.take<double>((size_t)n_rows * n_cols);
+  w.rank = cv.take<int32_t>((size_t)n_rows * n_cols);
+  w.counts = cv.take<uint8_t>((size_t)std::max<int64_t>(n_local, 1) * w.k_pad);
+  w.a_img = cv.take<unsigned char>((size_t)m_tiles * (size_t)(w.k_pad / kI8KChunk) * kI8AChunkBytes);
+  w.b_img = cv.take<unsigned char>((size_t)mg_col_tiles(n_cols) * (size_t)(w.k_pad / kI8KChunk) * kI8BChunkBytes);
+  w.perm_img = cv.take<uint16_t>((size_t)mg_col_tiles(n_cols) * kMgColsPerTile * (size_t)w.k_pad);
+  return w;
+}
+
+size_t median_gemm_ws_bytes(int64_t n_rows, int64_t n_cols, int64_t n_local) {
+  if (!median_gemm_applies(n_rows, n_cols)) return 0;
+  Carver cv(reinterpret_cast<void*>(256), ~(size_t)0 >> 1);
+  mg_carve(cv, n_rows, n_cols, n_local);
+  return cv.used;
+}
+
+int median_gemm(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, uint64_t seed, int64_t resample_lo,
+                int64_t n_local, double* stat_out, void* ws, size_t ws_bytes, cudaStream_t s, const RankRule& full,
+                const RankRule& loo, double* jack_out) {
+  if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
+    return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
+  Carver cv(ws, ws_bytes);
+  MgWs w = mg_carve(cv, n_rows, n_cols, n_local);
+  if (!cv.ok) return fail(B200BOOT_EWORKSPACE, "workspace too small: need %zu bytes", cv.used);
+  // every column sorted as (key, row) pairs: sorted values, permutation (idx) and rank table
+  psort_load_kernel<<<blocks_for(w.n_pad * n_cols, 256, 148 * 32), 256, 0, s>>>(data, n_rows, n_cols, ld, w.n_pad,
+                                                                                w.keys, w.idx);
+  B2_LAUNCH_CHECK();
+  for (int64_t d0 = 0; d0 < n_cols; d0 += 65535) {
+    const unsigned nd = (unsigned)std::min<int64_t>(65535, n_cols - d0);
+    int rc = psort_pairs(w.keys + d0 * w.n_pad, w.idx + d0 * w.n_pad, w.n_pad, nd, s);
+    if (rc) return rc;
+  }
+  rows_rank_kernel<<<blocks_for(n_rows * n_cols, 256, 148 * 32), 256, 0, s>>>(w.keys, w.idx, n_rows, w.n_pad, n_cols, 0,
+                                                                              n_cols, w.rank, w.sorted);
+  B2_LAUNCH_CHECK();
+  if (jack_out) {
+    for (int64_t d0 = 0; d0 < n_cols; d0 += 1 << 30) {
+      const int64_t nd = std::min<int64_t>((int64_t)1 << 30, n_cols - d0);
+      k3m_jackknife_median_kernel<<<(unsigned)nd, 256, 0, s>>>(w.sorted + d0 * n_rows, n_rows, full, loo,
+                                                               jack_out + d0 * 8);
+      B2_LAUNCH_CHECK();
+    }
+  }
+  // the resamples' count matrix (the multiplicities of the single-cell Lemire stream) and both images
+  B2_CUDA(cudaMemsetAsync(w.flags, 0, 256, s));
+  {
+    static PerDeviceOnce configured;
+    B2_CUDA(configured.run([] {
+      return cudaFuncSetAttribute(k6i_count_bytes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    }));
+    const int grid = (int)std::min<int64_t>((int64_t)sm_count() * 4, n_local);
+    k6i_count_bytes_kernel<<<grid, 256, (size_t)w.k_pad, s>>>(seed, n_rows, w.k_pad, resample_lo, n_local, w.counts,
+                                                             w.flags);
+    B2_LAUNCH_CHECK();
+  }
+  const int64_t m_tiles = (n_local + kI8M - 1) / kI8M;
+  const int64_t n_col_tiles = mg_col_tiles(n_cols);
+  const int n_kchunks = (int)(w.k_pad / kI8KChunk);
+  k6i_image_kernel<kI8M><<<blocks_for(m_tiles * kI8M * (w.k_pad / 16), 256, 148 * 16), 256, 0, s>>>(
+      w.counts, n_local, w.k_pad, m_tiles, w.a_img);
+  B2_LAUNCH_CHECK();
+  const int seg = (int)((n_rows + kMgT - 1) / kMgT);
+  k1mg_indicator_image_kernel<<<blocks_for(n_col_tiles * kMgColsPerTile * (w.k_pad / 16), 256, 148 * 16), 256, 0, s>>>(
+      w.rank, n_rows, n_cols, w.k_pad, n_col_tiles, seg, w.b_img);
+  B2_LAUNCH_CHECK();
+  k1mg_perm_image_kernel<<<blocks_for(n_col_tiles * kMgColsPerTile * w.k_pad, 256, 148 * 16), 256, 0, s>>>(
+      w.idx, n_rows, w.n_pad, n_cols, w.k_pad, n_col_tiles, w.perm_img);
+  B2_LAUNCH_CHECK();
+  const size_t limit = 227 * 1024;
+  int n_stages = kPipeMaxStages;
+  while (n_stages > 2 && k1mg_smem_bytes(n_kchunks, n_stages) > limit) --n_stages;
+  const size_t smem = k1mg_smem_bytes(n_kchunks, n_stages);
+  if (smem > limit) return fail(B200BOOT_EUNSUPPORTED, "K1mg: shared memory");
+  static PerDeviceOnce configured;
+  B2_CUDA(configured.run([] {
+    return cudaFuncSetAttribute(k1mg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  }));
+  K1mgParams P{};
+  P.a_img = w.a_img;
+  P.b_img = w.b_img;
+  P.perm_img = w.perm_img;
+  P.sorted = w.sorted;
+  P.m_total = n_local;
+  P.m_tiles = m_tiles;
+  P.n_kchunks = n_kchunks;
+  P.n_stages = n_stages;
+  P.n_rows = n_rows;
+  P.n_cols = n_cols;
+  P.n_col_tiles = n_col_tiles;
+  P.seg = seg;
+  P.rule = full;
+  P.out = stat_out;
+  P.out_ld = n_local;
+  P.overflow = w.flags;
+  const int grid = (int)std::min<int64_t>(sm_count(), m_tiles * n_col_tiles);
+  k1mg_kernel<<<grid, kPipeThreads, smem, s>>>(P);
+  B2_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
 extern "C" {
 
 int b200boot_version(void) { return B200BOOT_ABI_VERSION; }
@@ -319,7 +457,7 @@ size_t b200boot_workspace_bytes(int stat_id, int64_t n_rows, int n_arrays, int64
   if (n_rows < 1 || n_arrays < 1 || n_local < 0 || n_cols < 1) return 0;
   size_t total = 4096;
   if (stat_id == kStatMedian) {
-    total += median_ws_bytes(n_rows, n_cols, n_local);
+    total += std::max(median_ws_bytes(n_rows, n_cols, n_local), median_gemm_ws_bytes(n_rows, n_cols, n_local));
   } else if (n_cols > 1) {
     total += columns_ws_bytes(n_cols);
   } else {
@@ -1304,6 +1442,11 @@ int b200boot_resample_median_columns(const double* data, int64_t n_rows, int64_t
     }
     return 0;
   }
+  // many short columns: prefix counts on the tensor cores + short walks (K1mg)
+  static const bool use_mg = getenv("B200BOOT_K1MG") == nullptr || atoi(getenv("B200BOOT_K1MG")) != 0;
+  if (use_mg && data && stat_out && resample_hi > resample_lo && median_gemm_applies(n_rows, n_cols))
+    return median_gemm(data, n_rows, n_cols, ld, seed, resample_lo, resample_hi - resample_lo, stat_out, ws, ws_bytes,
+                       as_stream(stream), full, loo, jack_out);
   return median_resample(data, n_rows, n_cols, ld, seed, resample_lo, resample_hi, stat_out, ws,
                          ws_bytes, as_stream(stream), full, nullptr, jack_out, &loo);
 }
