@@ -331,15 +331,17 @@ def other_configs(boot):
     call = lambda: boot.ci(td, boot.median_axis0, method="bca", n_samples=10_000, seed=0)   # noqa: E731
     callp = lambda: boot.pval(td, boot.median_axis0, n_samples=10_000, seed=0)              # noqa: E731
     ms, ms_p = _median_ms(call, 3), _median_ms(callp, 3)
-    # columns share the index set, so a column subset under the same seed is the same run
+    # parity on the WHOLE table (the kernels the timing above ran: all 10^4 columns share the index
+    # set), checked against the oracle on eight of its columns
     import warnings
-    sub = np.ascontiguousarray(table[:, :8])
+    cols = [0, 1, 17, 4999, 5000, 7777, 9998, 9999]
+    sub = np.ascontiguousarray(table[:, cols])
     n_chk = 200
-    idx = np.array(list(boot.bootstrap_indices(sub, n_chk, seed=5)))
+    idx = np.array(list(boot.bootstrap_indices(table[:, :1], n_chk, seed=5)))
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        got = boot.ci(sub, boot.median_axis0, alpha=0.05, n_samples=n_chk, method="bca", seed=5)
-        gotp = boot.pval(sub, boot.median_axis0, n_samples=n_chk, seed=5)
+        got = boot.ci(td, boot.median_axis0, alpha=0.05, n_samples=n_chk, method="bca", seed=5)[:, cols]
+        gotp = boot.pval(td, boot.median_axis0, n_samples=n_chk, seed=5)[cols]
         ok = True
         for c in range(sub.shape[1]):
             col = sub[:, c]

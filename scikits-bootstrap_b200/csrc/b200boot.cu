@@ -426,7 +426,12 @@ int median_gemm(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, 
   P.out = stat_out;
   P.out_ld = n_local;
   P.overflow = w.flags;
-  const int grid = (int)std::min<int64_t>(sm_count(), m_tiles * n_col_tiles);
+  // ~32 work items per CTA: fine enough to balance, coarse enough that reloading the count tile
+  // per item (128 KB against seg_tiles x 256 KB of indicator chunks) stays a few per cent
+  const int64_t want_segs = std::max<int64_t>(1, (32 * (int64_t)sm_count() + m_tiles - 1) / m_tiles);
+  P.seg_tiles = std::max<int64_t>(1, (n_col_tiles + want_segs - 1) / want_segs);
+  const int64_t n_items = ((n_col_tiles + P.seg_tiles - 1) / P.seg_tiles) * m_tiles;
+  const int grid = (int)std::min<int64_t>(sm_count(), n_items);
   k1mg_kernel<<<grid, kPipeThreads, smem, s>>>(P);
   B2_LAUNCH_CHECK();
   return 0;

@@ -79,7 +79,9 @@ __global__ void __launch_bounds__(256) k1mg_perm_image_kernel(const uint32_t* __
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
     const int64_t d = e / k_pad, p = e - d * k_pad;
-    perm_img[e] = (d < n_cols && p < n_rows) ? (uint16_t)__ldg(idx + d * n_pad + p) : (uint16_t)0;
+    // positions past the end point at row n_rows, whose count byte is zero (k_pad > n_rows), so the
+    // finishing walk needs no bound check; with n_rows == k_pad there are no such positions
+    perm_img[e] = (d < n_cols && p < n_rows) ? (uint16_t)__ldg(idx + d * n_pad + p) : (uint16_t)(n_rows < k_pad ? n_rows : 0);
   }
 }
 
@@ -91,6 +93,7 @@ struct K1mgParams {
   int64_t m_total, m_tiles;
   int32_t n_kchunks, n_stages;
   int64_t n_rows, n_cols, n_col_tiles;
+  int64_t seg_tiles;            // column tiles per work item (see the kernel's unit order)
   int32_t seg;
   RankRule rule;
   double* out;                  // out[d * out_ld + r]
@@ -143,39 +146,39 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k1mg_kernel(const K1mgParams 
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  const int64_t n_units = P.m_tiles * P.n_col_tiles;
-  const int64_t u_begin = n_units * blockIdx.x / gridDim.x;
-  const int64_t u_end = n_units * (blockIdx.x + 1) / gridDim.x;
+  // Unit order.  A work item is (column segment, resample tile): the seg_tiles column tiles of the
+  // segment against one count tile.  Items are numbered segment-major and dealt out round-robin
+  // (CTA b takes items b, b + G, ...), so at any time all CTAs work inside one or two column
+  // segments: their indicator blocks (a few MB) stay in L2 while every resample tile re-reads
+  // them.  With contiguous ranges per CTA the CTAs were spread over the whole 328 MB image, which
+  // then came from HBM once per resample tile (ncu: 27.9 GB of DRAM reads, 4.2 TB/s).
+  const int64_t n_segs = (P.n_col_tiles + P.seg_tiles - 1) / P.seg_tiles;
+  const int64_t n_items = n_segs * P.m_tiles;
 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- producer ----------------
-      uint32_t it = 0, a_loads = 0;
-      int64_t cur_mt = -1;
-      for (int64_t u = u_begin; u < u_end; ++u) {
-        const int64_t mt = u / P.n_col_tiles, ct = u - mt * P.n_col_tiles;
-        if (mt != cur_mt) {
-          if (a_loads > 0) {
-            mbar_wait(afree, (a_loads - 1u) & 1u);                       // the MMAs reading the old tile are done
-            // ... and so are the walks of the epilogue, which read it too
-            const uint32_t need = (uint32_t)(u - u_begin) * (uint32_t)(kPipeEpiGroups * 4);
-            while (s_epi_done[0] + s_epi_done[1] < need) __nanosleep(64);
-            fence_proxy_async();
-          }
-          mbar_expect_tx(afull, (uint32_t)n_kchunks * kI8AChunkBytes);
-          for (int kc = 0; kc < n_kchunks; ++kc)
-            bulk_copy_g2s(s_a + (size_t)kc * kI8AChunkBytes,
-                          P.a_img + (mt * n_kchunks + kc) * (int64_t)kI8AChunkBytes, kI8AChunkBytes, afull);
-          ++a_loads;
-          cur_mt = mt;
+      uint32_t it = 0, ti = 0, items_done = 0;
+      for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++items_done) {
+        const int64_t sg = item / P.m_tiles, mt = item - sg * P.m_tiles;
+        const int64_t ct0 = sg * P.seg_tiles, ct1 = min(ct0 + P.seg_tiles, P.n_col_tiles);
+        if (items_done > 0) {
+          mbar_wait(afree, (items_done - 1u) & 1u);                      // the MMAs reading the old count tile are done
+          // ... and so are the walks of the epilogue, which read it too
+          const uint32_t need = ti * (uint32_t)(kPipeEpiGroups * 4);
+          while (s_epi_done[0] + s_epi_done[1] < need) __nanosleep(64);
+          fence_proxy_async();
         }
-        {
+        mbar_expect_tx(afull, (uint32_t)n_kchunks * kI8AChunkBytes);
+        for (int kc = 0; kc < n_kchunks; ++kc)
+          bulk_copy_g2s(s_a + (size_t)kc * kI8AChunkBytes, P.a_img + (mt * n_kchunks + kc) * (int64_t)kI8AChunkBytes,
+                        kI8AChunkBytes, afull);
+        for (int64_t ct = ct0; ct < ct1; ++ct, ++ti) {
           // the unit's permutations, double-buffered like the accumulators: buffer (unit & 1) is
-          // free once every epilogue warp is past the unit before last
-          const uint32_t ti = (uint32_t)(u - u_begin);
+          // free once every epilogue warp is past the unit before last (counted per parity: a
+          // total over all units could be reached by fast warps that are already past the NEXT
+          // unit while a slow one is still walking this buffer's last unit)
           if (ti >= 2) {
-            // (counted per parity: a total over all units could be reached by fast warps that are
-            // already past the NEXT unit while a slow one is still walking this buffer's last unit)
             const uint32_t need = (ti >> 1) * (uint32_t)(kPipeEpiGroups * 4);
             while (s_epi_done[ti & 1u] < need) __nanosleep(32);
             fence_proxy_async();
@@ -184,47 +187,44 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k1mg_kernel(const K1mgParams 
           bulk_copy_g2s(s_perm + (size_t)(ti & 1u) * perm_bytes,
                         reinterpret_cast<const unsigned char*>(P.perm_img) + ct * (int64_t)perm_bytes, perm_bytes,
                         &pfull[ti & 1u]);
-        }
-        for (int kc = 0; kc < n_kchunks; ++kc, ++it) {
-          const uint32_t s = it % (uint32_t)n_stages;
-          mbar_wait(&empty[s], ((it / (uint32_t)n_stages) & 1u) ^ 1u);
-          mbar_expect_tx(&full[s], stage_bytes);
-          bulk_copy_g2s(s_ring + (size_t)s * stage_bytes, P.b_img + (ct * n_kchunks + kc) * (int64_t)kI8BChunkBytes,
-                        kI8BChunkBytes, &full[s]);
+          for (int kc = 0; kc < n_kchunks; ++kc, ++it) {
+            const uint32_t s = it % (uint32_t)n_stages;
+            mbar_wait(&empty[s], ((it / (uint32_t)n_stages) & 1u) ^ 1u);
+            mbar_expect_tx(&full[s], stage_bytes);
+            bulk_copy_g2s(s_ring + (size_t)s * stage_bytes, P.b_img + (ct * n_kchunks + kc) * (int64_t)kI8BChunkBytes,
+                          kI8BChunkBytes, &full[s]);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
-      uint32_t it = 0, tile_i = 0, a_loads = 0;
-      int64_t cur_mt = -1;
-      for (int64_t u = u_begin; u < u_end; ++u, ++tile_i) {
-        const int64_t mt = u / P.n_col_tiles;
-        if (mt != cur_mt) {
-          mbar_wait(afull, a_loads & 1u);
-          ++a_loads;
-          cur_mt = mt;
-        }
-        const uint32_t buf = tile_i & 1u;
-        mbar_wait(&tempty[buf], ((tile_i >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * (uint32_t)kI8N;
-        for (int kc = 0; kc < n_kchunks; ++kc, ++it) {
-          const uint32_t s = it % (uint32_t)n_stages;
-          mbar_wait(&full[s], (it / (uint32_t)n_stages) & 1u);
+      uint32_t it = 0, tile_i = 0, items_done = 0;
+      for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++items_done) {
+        const int64_t sg = item / P.m_tiles;
+        const int64_t ct0 = sg * P.seg_tiles, ct1 = min(ct0 + P.seg_tiles, P.n_col_tiles);
+        mbar_wait(afull, items_done & 1u);
+        for (int64_t ct = ct0; ct < ct1; ++ct, ++tile_i) {
+          const uint32_t buf = tile_i & 1u;
+          mbar_wait(&tempty[buf], ((tile_i >> 1) & 1u) ^ 1u);
           tc_fence_after();
-          const uint32_t b_addr = smem_u32(s_ring + (size_t)s * stage_bytes);
-          const uint32_t a_addr = smem_u32(s_a + (size_t)kc * kI8AChunkBytes);
+          const uint32_t tmem_d = tmem_base + buf * (uint32_t)kI8N;
+          for (int kc = 0; kc < n_kchunks; ++kc, ++it) {
+            const uint32_t s = it % (uint32_t)n_stages;
+            mbar_wait(&full[s], (it / (uint32_t)n_stages) & 1u);
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(s_ring + (size_t)s * stage_bytes);
+            const uint32_t a_addr = smem_u32(s_a + (size_t)kc * kI8AChunkBytes);
 #pragma unroll
-          for (int kk = 0; kk < kI8KChunk / 32; ++kk)
-            umma_i8(tmem_d, umma_desc_sw128(a_addr + kk * 32), umma_desc_sw128(b_addr + kk * 32), kI8InstrDesc,
-                    (kc | kk) != 0 ? 1u : 0u);
-          umma_commit(&empty[s]);
+            for (int kk = 0; kk < kI8KChunk / 32; ++kk)
+              umma_i8(tmem_d, umma_desc_sw128(a_addr + kk * 32), umma_desc_sw128(b_addr + kk * 32), kI8InstrDesc,
+                      (kc | kk) != 0 ? 1u : 0u);
+            umma_commit(&empty[s]);
+          }
+          umma_commit(&tfull[buf]);
         }
-        umma_commit(&tfull[buf]);
-        const bool last_of_mt = (u + 1 == u_end) || ((u + 1) / P.n_col_tiles != mt);
-        if (last_of_mt) umma_commit(afree);
+        umma_commit(afree);                                              // this item's count tile has been read
       }
     }
   } else if (warp >= 4) {
@@ -235,9 +235,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k1mg_kernel(const K1mgParams 
     const int two = P.rule.k_hi != P.rule.k_lo ? 1 : 0;
     const int seg = P.seg;
     const uint32_t r_local = (uint32_t)(w4 * 32 + lane);
+    const unsigned char* s_row = s_a + (r_local >> 3) * 1024u + (r_local & 7u) * 128u;   // this lane's row of a count chunk
+    const uint32_t rx4 = (r_local & 7u) << 4;
+    const int k_pad = n_kchunks * kI8KChunk;
     uint32_t tile_i = 0;
-    for (int64_t u = u_begin; u < u_end; ++u, ++tile_i) {
-      const int64_t mt = u / P.n_col_tiles, ct = u - mt * P.n_col_tiles;
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x)
+    for (int64_t sg = item / P.m_tiles, mt = item - sg * P.m_tiles, ct = sg * P.seg_tiles;
+         ct < min((sg + 1) * P.seg_tiles, P.n_col_tiles); ++ct, ++tile_i) {
       const uint32_t buf = tile_i & 1u;
       const int64_t r = mt * kI8M + r_local;
       mbar_wait(&tfull[buf], (tile_i >> 1) & 1u);
@@ -263,33 +267,36 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k1mg_kernel(const K1mgParams 
           if (r >= P.m_total || d >= P.n_cols) continue;
           const uint32_t* S = v + c * kMgT;                              // S[j] = #draws with rank < (j + 1) seg
           const long long k_lo = P.rule.k_lo, k_hi = P.rule.k_hi;
+          // first j with S[j] > k_lo, and the draws below segment j (S is non-decreasing)
           int j = 0;
-#pragma unroll
-          for (int t = 0; t < kMgT - 1; ++t) j += ((long long)S[t] <= k_lo) ? 1 : 0;   // first j with S[j] > k_lo
           long long acc = 0;
 #pragma unroll
-          for (int t = 0; t < kMgT - 1; ++t) acc = (t == j - 1) ? (long long)S[t] : acc;
-          const uint16_t* perm = perm_tile + (size_t)(cb * (32 / kMgT) + c) * (size_t)(n_kchunks * kI8KChunk);
+          for (int t = 0; t < kMgT - 1; ++t) {
+            const bool below = (long long)S[t] <= k_lo;
+            j += below ? 1 : 0;
+            acc = below ? (long long)S[t] : acc;
+          }
+          const uint16_t* perm = perm_tile + (size_t)(cb * (32 / kMgT) + c) * (size_t)k_pad;
           int pos_lo = -1, pos_hi = -1;
-          const int n = (int)P.n_rows;
           // the walk, kMgWalk positions at a time: the permutation entries and the count bytes of a
           // group are independent loads (a position-by-position walk is a chain of two dependent
-          // loads per step and made the kernel latency-bound: 85 k cycles per tile; the lanes of a
-          // warp walk segments of different lengths, so the warp pays for its longest walk)
-          for (int p0 = j * seg; p0 < n && pos_hi < 0; p0 += kMgWalk) {
-            uint32_t row[kMgWalk], cnt[kMgWalk];
+          // loads per step: 85 k cycles per tile; the lanes of a warp walk segments of different
+          // lengths, so the warp pays for its longest walk).  Positions past the column's end hold
+          // a row whose count byte is zero (k1mg_perm_image_kernel), so the loop needs no bound
+          // checks; the byte of row i in the swizzled count tile is at
+          // tile_row_base + (i >> 7) * 16 KB + ((i & 127) ^ ((row & 7) << 4)).
+          for (int p0 = j * seg; p0 < k_pad && pos_hi < 0; p0 += kMgWalk) {
+            uint32_t cnt[kMgWalk];
 #pragma unroll
-            for (int t = 0; t < kMgWalk; ++t) row[t] = p0 + t < n ? (uint32_t)perm[p0 + t] : 0u;
-#pragma unroll
-            for (int t = 0; t < kMgWalk; ++t)
-              cnt[t] = p0 + t < n
-                           ? (uint32_t)s_a[(size_t)(row[t] >> 7) * kI8AChunkBytes + sw128_offset(r_local, row[t] & 127u)]
-                           : 0u;
+            for (int t = 0; t < kMgWalk; ++t) {
+              const uint32_t i = perm[p0 + t];
+              cnt[t] = s_row[((i >> 7) << 14) + ((i & 127u) ^ rx4)];
+            }
 #pragma unroll
             for (int t = 0; t < kMgWalk; ++t) {
               acc += cnt[t];
-              if (pos_lo < 0 && acc > k_lo) pos_lo = p0 + t;
-              if (pos_hi < 0 && acc > k_hi) pos_hi = p0 + t;
+              pos_lo = (pos_lo < 0 && acc > k_lo) ? p0 + t : pos_lo;
+              pos_hi = (pos_hi < 0 && acc > k_hi) ? p0 + t : pos_hi;
             }
           }
           const double* col = P.sorted + d * P.n_rows;
