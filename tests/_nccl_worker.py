@@ -25,6 +25,7 @@ def main():
     table = rng.standard_normal((500, 37))
     tall = rng.standard_normal((29001, 3))                  # beyond the resident rows: row-space medians (K1mr)
     long_rows = rng.gamma(2.0, 1.0, 600_000)                # numpy rows copied under the occupancy chains
+    wide = rng.standard_normal((300, 80))                   # many short columns: prefix counts on the tensor cores (K1mg)
     holes = x[:3000].copy()
     holes[17] = np.nan                                      # numpy's NaN rule for rank statistics
     cases = [
@@ -48,6 +49,8 @@ def main():
         lambda: boot.ci(long_rows, np.std, n_samples=301, seed=17, method="pi"),
         lambda: boot.ci(holes, np.median, n_samples=201, seed=18, method="pi", return_dist=True)[1],
         lambda: boot.ci(x[:1000], np.mean, n_samples=2000, seed=19),         # small-call shape (unsharded: one kernel)
+        lambda: boot.ci(wide, boot.median_axis0, n_samples=403, seed=20),
+        lambda: boot.pval(wide, boot.quantile_axis0(0.4), boot.less_than(-0.2), n_samples=403, seed=21),
         lambda: boot.ci(x, np.mean, n_samples=64, seed=None),          # seed agreed through a broadcast
     ]
     boot.distributed.enable()
