@@ -416,6 +416,33 @@ def test_rank_statistics_propagate_nan_like_numpy(n, d):
             assert_array_equal(got.reshape(20, -1), np.sort(np.stack([host(x[i]) for i in pcg]).reshape(20, -1), axis=0))
 
 
+@pytest.mark.parametrize("n,d", [(32, 64), (100, 130), (513, 64), (1000, 72), (1023, 200), (1024, 65)])
+def test_many_short_columns_through_the_tensor_cores(n, d):
+    """K1mg (N <= 1024 rows, D >= 64 columns): 32 prefix counts per (resample, column) as a count
+    matrix x 0/1 indicator matrix product on tcgen05, finished by a short walk.  The returned
+    distribution must hold the oracle's rows on the materialised indices — medians (one and two
+    middle ranks), an interpolated quantile, heavy ties, resample counts off the tile size."""
+    import warnings
+    rng = np.random.default_rng(n * 1000 + d)
+    data = rng.standard_normal((n, d))
+    data[:, 1] = np.round(data[:, 1], 1)                 # heavy ties
+    data[:, 2] = 1.5                                     # a constant column
+    m = 130
+    idx = np.array(list(boot.bootstrap_indices(data, m, seed=8)))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for f, host in ((boot.median_axis0, lambda u: np.median(u, axis=0)),
+                        (boot.quantile_axis0(0.33), lambda u: np.quantile(u, 0.33, axis=0))):
+            out, dist = boot.ci(data, f, n_samples=m, seed=8, method="pi", return_dist=True)
+            want = np.stack([host(data[i]) for i in idx])
+            assert_array_equal(dist, np.sort(want, axis=0))
+            p = boot.pval(data, f, boot.greater_than(0.1), n_samples=m, seed=8)
+            assert_array_equal(p, (want > 0.1).mean(axis=0))
+        for c in (0, 1, d - 1):                         # column c == the 1-D run with the same seed
+            assert_array_equal(boot.ci(data[:, c], np.median, n_samples=m, seed=8, method="pi"),
+                               boot.ci(data, boot.median_axis0, n_samples=m, seed=8, method="pi")[:, c])
+
+
 def test_long_median_index_supplied():
     """Index-supplied (parity) mode beyond the resident limit: the reference's own PCG64 index
     sets, 1-D and (N, D) data."""
