@@ -300,7 +300,9 @@ int loo_values(const double** rows, int64_t n_rows, int stat, ResampleWs& w, dou
 namespace {
 
 // ---- K1mg: medians of many short columns through the tensor cores (csrc/k1mg_gemm.cuh) --------
-constexpr int64_t kMgMinCols = 64;
+// measured against K1m (tools/mg_crossover.py, n = 1e4): N = 1000: D = 2 0.12 vs 0.25 ms, D = 32 0.14 vs 0.33,
+// D = 64 0.18 vs 0.41, D = 1e4 (cfg4) 8.1 vs 24 ms; N = 200, D = 8: 0.09 vs 0.12; N = 64, D = 16: 0.09 vs 0.11
+constexpr int64_t kMgMinCols = 2;
 constexpr int64_t kMgMaxRows = 1024;      // resident count tile (128 KB) + two digit stages + two permutation blocks
 
 inline int64_t mg_k_pad(int64_t n_rows) { return ((n_rows + kI8KChunk - 1) / kI8KChunk) * kI8KChunk; }

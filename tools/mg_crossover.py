@@ -1,12 +1,14 @@
-"""K1m vs K1mg over table shapes (development aid; B200BOOT_K1MG=0 selects K1m)."""
+"""K1m vs K1mg over table shapes (development aid; B200BOOT_K1MG=0 selects K1m,
+B200BOOT_MG_MIN_COLS lowers K1mg's column threshold)."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from scikits_bootstrap_b200 import _device
 rng = np.random.default_rng(0)
-for (n, d, m) in [(1000, 64, 10000), (1000, 256, 10000), (1000, 1000, 1000), (500, 2000, 5000), (100, 10000, 10000),
-                  (1000, 10000, 1000), (200, 64, 500), (1000, 128, 300), (64, 4096, 2000)]:
+shapes = [(1000, 2, 10000), (1000, 4, 10000), (1000, 8, 10000), (1000, 16, 10000), (1000, 32, 10000), (200, 8, 10000),
+          (200, 32, 2000), (1000, 8, 1000), (64, 16, 10000)]
+for (n, d, m) in shapes:
     x = torch.from_numpy(rng.standard_normal((n, d))).cuda()
     ts = []
     for it in range(4):
