@@ -304,11 +304,16 @@ namespace {
 // D = 64 0.18 vs 0.41, D = 1e4 (cfg4) 8.1 vs 24 ms; N = 200, D = 8: 0.09 vs 0.12; N = 64, D = 16: 0.09 vs 0.11
 constexpr int64_t kMgMinCols = 2;
 constexpr int64_t kMgMaxRows = 1024;      // resident count tile (128 KB) + two digit stages + two permutation blocks
+constexpr size_t kMgStreamMaxWs = (size_t)3 << 30;   // longer columns: only while the images stay moderate
 
 inline int64_t mg_k_pad(int64_t n_rows) { return ((n_rows + kI8KChunk - 1) / kI8KChunk) * kI8KChunk; }
 inline int64_t mg_col_tiles(int64_t n_cols) { return (n_cols + kMgColsPerTile - 1) / kMgColsPerTile; }
-inline bool median_gemm_applies(int64_t n_rows, int64_t n_cols) {
-  return n_cols >= kMgMinCols && n_rows >= 32 && n_rows <= kMgMaxRows;
+size_t median_gemm_ws_bytes(int64_t n_rows, int64_t n_cols, int64_t n_local);
+inline bool median_gemm_applies(int64_t n_rows, int64_t n_cols, int64_t n_local) {
+  if (n_cols < kMgMinCols || n_rows < 32) return false;
+  if (n_rows <= kMgMaxRows) return true;
+  // streamed form (1024 < N <= 28 672): measured against K1m / the K1m1 loop in tools/mg_crossover.py
+  return n_rows <= kMedMaxRows && median_gemm_ws_bytes(n_rows, n_cols, n_local) <= kMgStreamMaxWs;
 }
 
 struct MgWs {
@@ -338,12 +343,13 @@ MgWs mg_carve(Carver& cv, int64_t n_rows, int64_t n_cols, int64_t n_local) {
   w.counts = cv.take<uint8_t>((size_t)std::max<int64_t>(n_local, 1) * w.k_pad);
   w.a_img = cv.take<unsigned char>((size_t)m_tiles * (size_t)(w.k_pad / kI8KChunk) * kI8AChunkBytes);
   w.b_img = cv.take<unsigned char>((size_t)mg_col_tiles(n_cols) * (size_t)(w.k_pad / kI8KChunk) * kI8BChunkBytes);
-  w.perm_img = cv.take<uint16_t>((size_t)mg_col_tiles(n_cols) * kMgColsPerTile * (size_t)w.k_pad);
+  w.perm_img = n_rows <= kMgMaxRows ? cv.take<uint16_t>((size_t)mg_col_tiles(n_cols) * kMgColsPerTile * (size_t)w.k_pad)
+                                    : nullptr;
   return w;
 }
 
 size_t median_gemm_ws_bytes(int64_t n_rows, int64_t n_cols, int64_t n_local) {
-  if (!median_gemm_applies(n_rows, n_cols)) return 0;
+  if (n_cols < kMgMinCols || n_rows < 32 || n_rows > kMedMaxRows) return 0;
   Carver cv(reinterpret_cast<void*>(256), ~(size_t)0 >> 1);
   mg_carve(cv, n_rows, n_cols, n_local);
   return cv.used;
@@ -399,10 +405,48 @@ int median_gemm(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, 
   k1mg_indicator_image_kernel<<<blocks_for(n_col_tiles * kMgColsPerTile * (w.k_pad / 16), 256, 148 * 16), 256, 0, s>>>(
       w.rank, n_rows, n_cols, w.k_pad, n_col_tiles, seg, w.b_img);
   B2_LAUNCH_CHECK();
+  // ~32 work items per CTA: fine enough to balance, coarse enough that reloading the count tile
+  // per item (128 KB against seg_tiles x 256 KB of indicator chunks) stays a few per cent
+  const int64_t want_segs = std::max<int64_t>(1, (32 * (int64_t)sm_count() + m_tiles - 1) / m_tiles);
+  const int64_t seg_tiles = std::max<int64_t>(1, (n_col_tiles + want_segs - 1) / want_segs);
+  const int64_t n_items = ((n_col_tiles + seg_tiles - 1) / seg_tiles) * m_tiles;
+  const int grid = (int)std::min<int64_t>(sm_count(), n_items);
+  const size_t limit = 227 * 1024;
+  if (n_rows > kMgMaxRows) {
+    // longer columns: count chunks streamed next to the indicator chunks, walks over L2
+    static PerDeviceOnce configured_stream;
+    B2_CUDA(configured_stream.run([] {
+      return cudaFuncSetAttribute(k1mg_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    }));
+    int n_stages = kPipeMaxStages;
+    while (n_stages > 2 && k1mg_stream_smem_bytes(n_stages) > limit) --n_stages;
+    K1mgStreamParams Q{};
+    Q.a_img = w.a_img;
+    Q.b_img = w.b_img;
+    Q.counts = w.counts;
+    Q.perm = w.idx;
+    Q.perm_ld = w.n_pad;
+    Q.sorted = w.sorted;
+    Q.m_total = n_local;
+    Q.m_tiles = m_tiles;
+    Q.n_kchunks = n_kchunks;
+    Q.n_stages = n_stages;
+    Q.n_rows = n_rows;
+    Q.n_cols = n_cols;
+    Q.n_col_tiles = n_col_tiles;
+    Q.seg_tiles = seg_tiles;
+    Q.seg = seg;
+    Q.rule = full;
+    Q.out = stat_out;
+    Q.out_ld = n_local;
+    Q.overflow = w.flags;
+    k1mg_stream_kernel<<<grid, kPipeThreads, k1mg_stream_smem_bytes(n_stages), s>>>(Q);
+    B2_LAUNCH_CHECK();
+    return 0;
+  }
   k1mg_perm_image_kernel<<<blocks_for(n_col_tiles * kMgColsPerTile * w.k_pad, 256, 148 * 16), 256, 0, s>>>(
       w.idx, n_rows, w.n_pad, n_cols, w.k_pad, n_col_tiles, w.perm_img);
   B2_LAUNCH_CHECK();
-  const size_t limit = 227 * 1024;
   int n_stages = kPipeMaxStages;
   while (n_stages > 2 && k1mg_smem_bytes(n_kchunks, n_stages) > limit) --n_stages;
   const size_t smem = k1mg_smem_bytes(n_kchunks, n_stages);
@@ -428,12 +472,7 @@ int median_gemm(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, 
   P.out = stat_out;
   P.out_ld = n_local;
   P.overflow = w.flags;
-  // ~32 work items per CTA: fine enough to balance, coarse enough that reloading the count tile
-  // per item (128 KB against seg_tiles x 256 KB of indicator chunks) stays a few per cent
-  const int64_t want_segs = std::max<int64_t>(1, (32 * (int64_t)sm_count() + m_tiles - 1) / m_tiles);
-  P.seg_tiles = std::max<int64_t>(1, (n_col_tiles + want_segs - 1) / want_segs);
-  const int64_t n_items = ((n_col_tiles + P.seg_tiles - 1) / P.seg_tiles) * m_tiles;
-  const int grid = (int)std::min<int64_t>(sm_count(), n_items);
+  P.seg_tiles = seg_tiles;
   k1mg_kernel<<<grid, kPipeThreads, smem, s>>>(P);
   B2_LAUNCH_CHECK();
   return 0;
@@ -464,7 +503,8 @@ size_t b200boot_workspace_bytes(int stat_id, int64_t n_rows, int n_arrays, int64
   if (n_rows < 1 || n_arrays < 1 || n_local < 0 || n_cols < 1) return 0;
   size_t total = 4096;
   if (stat_id == kStatMedian) {
-    total += std::max(median_ws_bytes(n_rows, n_cols, n_local), median_gemm_ws_bytes(n_rows, n_cols, n_local));
+    total += std::max(median_ws_bytes(n_rows, n_cols, n_local),
+                      median_gemm_applies(n_rows, n_cols, n_local) ? median_gemm_ws_bytes(n_rows, n_cols, n_local) : (size_t)0);
   } else if (n_cols > 1) {
     total += columns_ws_bytes(n_cols);
   } else {
@@ -1435,6 +1475,14 @@ int b200boot_resample_median_columns(const double* data, int64_t n_rows, int64_t
                                      const b200boot_rank_rule* rule, double* jack_out) {
   RankRule full, loo;
   if (int rc = rank_rules(rule, n_rows, &full, &loo)) return rc;
+  // two or more resident columns: prefix counts on the tensor cores + short walks (K1mg; the
+  // streamed form for 1024 < N <= 28 672 while its images fit 3 GB: tools/mg_crossover.py, n = 1e4:
+  // N = 1e4: D = 2 0.47 vs 0.77 ms, D = 32 1.06 vs 8.3, D = 256 5.4 vs 36.9; N = 28 000, D = 32: 3.4 vs 45.6)
+  static const bool use_mg = getenv("B200BOOT_K1MG") == nullptr || atoi(getenv("B200BOOT_K1MG")) != 0;
+  if (use_mg && data && stat_out && resample_hi > resample_lo &&
+      median_gemm_applies(n_rows, n_cols, resample_hi - resample_lo))
+    return median_gemm(data, n_rows, n_cols, ld, seed, resample_lo, resample_hi - resample_lo, stat_out, ws, ws_bytes,
+                       as_stream(stream), full, loo, jack_out);
   // one column — or a few long ones, where K1m would leave all but a few warps idle — go column
   // by column through K1m1 (same seed: same index sets, the rows stay aligned across columns)
   // (measured, n = 1e4, K1m vs the loop: N = 3000: D = 2 0.76 vs 0.53 ms, D = 4 0.77 vs 0.80;
@@ -1449,11 +1497,6 @@ int b200boot_resample_median_columns(const double* data, int64_t n_rows, int64_t
     }
     return 0;
   }
-  // many short columns: prefix counts on the tensor cores + short walks (K1mg)
-  static const bool use_mg = getenv("B200BOOT_K1MG") == nullptr || atoi(getenv("B200BOOT_K1MG")) != 0;
-  if (use_mg && data && stat_out && resample_hi > resample_lo && median_gemm_applies(n_rows, n_cols))
-    return median_gemm(data, n_rows, n_cols, ld, seed, resample_lo, resample_hi - resample_lo, stat_out, ws, ws_bytes,
-                       as_stream(stream), full, loo, jack_out);
   return median_resample(data, n_rows, n_cols, ld, seed, resample_lo, resample_hi, stat_out, ws,
                          ws_bytes, as_stream(stream), full, nullptr, jack_out, &loo);
 }

@@ -317,6 +317,174 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k1mg_kernel(const K1mgParams 
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// ---- the same for longer columns (1024 < N <= 28 672): the count tile no longer fits shared memory,
+// so count chunks are streamed through the ring next to the indicator chunks, and the finishing walk
+// reads the permutation (uint32 [D][perm_ld]) and the count bytes (the row-major count matrix,
+// [m_total][k_pad]) from L2.  Segments are longer (s = ceil(N / 32) positions), but such tables have
+// few (resample, column) pairs per drawn index, and K1m spends its time on the count tables.
+struct K1mgStreamParams {
+  const unsigned char* a_img;   // [m_tiles][n_kchunks][16 KB] counts (tile images, for the MMAs)
+  const unsigned char* b_img;   // [n_col_tiles][n_kchunks][32 KB] indicators
+  const uint8_t* counts;        // [m_total][k_pad] row-major (for the walks)
+  const uint32_t* perm;         // [D][perm_ld]
+  int64_t perm_ld;
+  const double* sorted;         // [D][N]
+  int64_t m_total, m_tiles;
+  int32_t n_kchunks, n_stages;
+  int64_t n_rows, n_cols, n_col_tiles, seg_tiles;
+  int32_t seg;
+  RankRule rule;
+  double* out;
+  int64_t out_ld;
+  const int32_t* overflow;
+};
+
+__global__ void __launch_bounds__(kPipeThreads, 1) k1mg_stream_kernel(const K1mgStreamParams P) {
+  extern __shared__ unsigned char mgs_smem_raw[];
+  unsigned char* smem = mgs_smem_raw + ((1024u - (smem_u32(mgs_smem_raw) & 1023u)) & 1023u);
+  const int n_kchunks = P.n_kchunks;
+  const int n_stages = P.n_stages;
+  const uint32_t stage_bytes = (uint32_t)(kI8AChunkBytes + kI8BChunkBytes);
+  unsigned char* s_ring = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + (size_t)n_stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kPipeMaxStages;
+  uint64_t* tfull = bars + 2 * kPipeMaxStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < n_stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], kPipeEpiGroups * 128);
+    }
+  }
+  if (warp == 0) tmem_alloc(s_tmem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const int64_t n_segs = (P.n_col_tiles + P.seg_tiles - 1) / P.seg_tiles;
+  const int64_t n_items = n_segs * P.m_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int64_t sg = item / P.m_tiles, mt = item - sg * P.m_tiles;
+        for (int64_t ct = sg * P.seg_tiles; ct < min((sg + 1) * P.seg_tiles, P.n_col_tiles); ++ct)
+          for (int kc = 0; kc < n_kchunks; ++kc, ++it) {
+            const uint32_t s = it % (uint32_t)n_stages;
+            mbar_wait(&empty[s], ((it / (uint32_t)n_stages) & 1u) ^ 1u);
+            unsigned char* dst = s_ring + (size_t)s * stage_bytes;
+            mbar_expect_tx(&full[s], stage_bytes);
+            bulk_copy_g2s(dst, P.b_img + (ct * n_kchunks + kc) * (int64_t)kI8BChunkBytes, kI8BChunkBytes, &full[s]);
+            bulk_copy_g2s(dst + kI8BChunkBytes, P.a_img + (mt * n_kchunks + kc) * (int64_t)kI8AChunkBytes,
+                          kI8AChunkBytes, &full[s]);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, tile_i = 0;
+      for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int64_t sg = item / P.m_tiles;
+        for (int64_t ct = sg * P.seg_tiles; ct < min((sg + 1) * P.seg_tiles, P.n_col_tiles); ++ct, ++tile_i) {
+          const uint32_t buf = tile_i & 1u;
+          mbar_wait(&tempty[buf], ((tile_i >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + buf * (uint32_t)kI8N;
+          for (int kc = 0; kc < n_kchunks; ++kc, ++it) {
+            const uint32_t s = it % (uint32_t)n_stages;
+            mbar_wait(&full[s], (it / (uint32_t)n_stages) & 1u);
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(s_ring + (size_t)s * stage_bytes);
+            const uint32_t a_addr = b_addr + (uint32_t)kI8BChunkBytes;
+#pragma unroll
+            for (int kk = 0; kk < kI8KChunk / 32; ++kk)
+              umma_i8(tmem_d, umma_desc_sw128(a_addr + kk * 32), umma_desc_sw128(b_addr + kk * 32), kI8InstrDesc,
+                      (kc | kk) != 0 ? 1u : 0u);
+            umma_commit(&empty[s]);
+          }
+          umma_commit(&tfull[buf]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int w4 = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    const bool poisoned = P.overflow != nullptr && *P.overflow != 0;
+    const int two = P.rule.k_hi != P.rule.k_lo ? 1 : 0;
+    const int seg = P.seg;
+    const int n = (int)P.n_rows;
+    const int64_t k_pad = (int64_t)n_kchunks * kI8KChunk;
+    const uint32_t r_local = (uint32_t)(w4 * 32 + lane);
+    uint32_t tile_i = 0;
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x)
+    for (int64_t sg = item / P.m_tiles, mt = item - sg * P.m_tiles, ct = sg * P.seg_tiles;
+         ct < min((sg + 1) * P.seg_tiles, P.n_col_tiles); ++ct, ++tile_i) {
+      const uint32_t buf = tile_i & 1u;
+      const int64_t r = mt * kI8M + r_local;
+      const uint8_t* cnt_row = P.counts + min(r, P.m_total - 1) * k_pad;
+      mbar_wait(&tfull[buf], (tile_i >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + buf * (uint32_t)kI8N;
+      for (int cb = grp; cb < kI8N / 32; cb += kPipeEpiGroups) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(tmem_d + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(cb * 32), v);
+        if (cb + kPipeEpiGroups >= kI8N / 32) {
+          tc_fence_before();
+          mbar_arrive(&tempty[buf]);
+        }
+#pragma unroll
+        for (int c = 0; c < 32 / kMgT; ++c) {
+          const int64_t d = ct * kMgColsPerTile + cb * (32 / kMgT) + c;
+          if (r >= P.m_total || d >= P.n_cols) continue;
+          const uint32_t* S = v + c * kMgT;
+          const long long k_lo = P.rule.k_lo, k_hi = P.rule.k_hi;
+          int j = 0;
+          long long acc = 0;
+#pragma unroll
+          for (int t = 0; t < kMgT - 1; ++t) {
+            const bool below = (long long)S[t] <= k_lo;
+            j += below ? 1 : 0;
+            acc = below ? (long long)S[t] : acc;
+          }
+          const uint32_t* perm = P.perm + d * P.perm_ld;
+          int pos_lo = -1, pos_hi = -1;
+          for (int p0 = j * seg; p0 < n && pos_hi < 0; p0 += kMgWalk) {
+            uint32_t cnt[kMgWalk];
+#pragma unroll
+            for (int t = 0; t < kMgWalk; ++t) cnt[t] = p0 + t < n ? (uint32_t)__ldg(cnt_row + __ldg(perm + p0 + t)) : 0u;
+#pragma unroll
+            for (int t = 0; t < kMgWalk; ++t) {
+              acc += cnt[t];
+              pos_lo = (pos_lo < 0 && acc > k_lo) ? p0 + t : pos_lo;
+              pos_hi = (pos_hi < 0 && acc > k_hi) ? p0 + t : pos_hi;
+            }
+          }
+          const double* col = P.sorted + d * P.n_rows;
+          const double a = pos_lo >= 0 ? col[pos_lo] : nan("");
+          const double b = two ? (pos_hi >= 0 ? col[pos_hi] : nan("")) : a;
+          __stcs(P.out + d * P.out_ld + r, poisoned ? nan("") : rank_combine(P.rule, a, b));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+inline size_t k1mg_stream_smem_bytes(int n_stages) {
+  return 1024 + (size_t)n_stages * (size_t)(kI8AChunkBytes + kI8BChunkBytes) + (2 * kPipeMaxStages + 8) * sizeof(uint64_t) + 64;
+}
+
 inline size_t k1mg_smem_bytes(int n_kchunks, int n_stages) {
   return 1024 + (size_t)n_kchunks * kI8AChunkBytes + (size_t)n_stages * kI8BChunkBytes +
          2 * (size_t)(kMgColsPerTile * n_kchunks * kI8KChunk * 2) + (2 * kPipeMaxStages + 10) * sizeof(uint64_t) + 64;
