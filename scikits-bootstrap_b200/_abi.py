@@ -9,7 +9,7 @@ import os
 import threading
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-# B200BOOT_LIB_PATH: development aid (tools/k1_variants.py times experimental builds)
+# B200BOOT_LIB_PATH: development aid (tools/try_variants.sh times experimental builds)
 LIB_PATH = os.environ.get("B200BOOT_LIB_PATH") or os.path.join(_PKG_DIR, "libb200boot.so")
 
 ABI_VERSION = 1

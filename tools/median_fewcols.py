@@ -1,4 +1,5 @@
-"""Resident medians of a few columns: K1m vs column-by-column K1m1 (development aid)."""
+"""Resident medians of a few columns (development aid; B200BOOT_K1MG=0 takes K1m / the
+column-by-column K1m1 loop instead of K1mg)."""
 import os, sys, time, warnings
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

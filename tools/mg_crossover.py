@@ -1,5 +1,5 @@
 """K1m / K1m1-loop vs K1mg over table shapes (development aid; B200BOOT_K1MG=0 selects the
-older kernels, B200BOOT_MG_STREAM_COLS sets the column threshold of the streamed form)."""
+older kernels)."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
