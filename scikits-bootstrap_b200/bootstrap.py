@@ -60,7 +60,7 @@ _GATHER_LIMIT_BYTES = 32 << 20
 # key offset between the arrays of multi='independent' (odd 64-bit constant)
 _ARRAY_KEY_STRIDE = 0x9E3779B97F4A7C15
 # K1mr: materialised index sets per batch
-_ROWS_INDEX_BYTES = 256 << 20
+_ROWS_INDEX_BYTES = 1 << 30
 # numpy rows from this size on are copied by the resampling call, under its occupancy chains
 _DEFER_COPY_BYTES = 4 << 20
 

@@ -972,7 +972,7 @@ int b200boot_fill_indices(uint64_t seed, int64_t n_rows, int n_arrays, int64_t r
     int rc = launch_occupancies(seed, resample_lo, n_local, plan, counts, cls, s);
     if (rc) return rc;
   }
-  k2_fill_indices_kernel<<<blocks_for(n_local * 32, 256, 148 * 8), 256, 0, s>>>(plan, seed, resample_lo,
+  k2_fill_indices_kernel<<<blocks_for(n_local * plan.n_tiles * 32, 256, 148 * 8), 256, 0, s>>>(plan, seed, resample_lo,
                                                                                n_local, counts, cls, out);
   B2_LAUNCH_CHECK();
   return 0;

@@ -624,30 +624,37 @@ __global__ void __launch_bounds__(256) k2_fill_indices_kernel(Plan plan, uint64_
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const uint32_t m7 = ((1u << (plan.log2_tile - 4)) - 1u) << 7;
-  for (int64_t rl = warp_global; rl < n_local; rl += n_warps) {
+  // a warp per (resample, cell): long arrays have few resamples per batch and many cells, and a
+  // warp per resample left the device empty (N = 1e6, 32 resamples: 58 GB/s of index writes).  The
+  // cell's first position in the resample is the sum of the earlier cells' occupancies.
+  const int64_t n_units = n_local * plan.n_tiles;
+  for (int64_t unit = warp_global; unit < n_units; unit += n_warps) {
+    const int64_t rl = unit / plan.n_tiles, t = unit - rl * plan.n_tiles;
     int64_t* row = out + rl * plan.n_rows;
     int64_t offset = 0;
-    for (int64_t t = 0; t < plan.n_tiles; ++t) {
-      const int64_t sz = plan.cell_size(t);
-      const int64_t row0 = t < plan.n_full ? (t << plan.log2_tile) : (plan.n_full << plan.log2_tile);
-      auto put = [&](int, int64_t pos, uint32_t idx) { row[offset + pos] = row0 + (int64_t)idx; };
-      if (t < plan.n_full) {
-        for (int c = 0; c < kClasses; ++c) {
-          const int64_t n_c = cls[(t * n_local + rl) * kClasses + c];
-          const Stream st = make_stream(seed, resample_lo + rl, class_cell_id(t, c), kPurposeIndex);
-          const uint32_t nblk = (uint32_t)((n_c + kClassDrawsPerBlock - 1) / kClassDrawsPerBlock);
-          for (uint32_t q = lane; q < nblk; q += 32) class_block<true>(st, q, m7, c, n_c, put);
-          offset += n_c;
-        }
-      } else {
-        const int64_t n = counts ? (int64_t)counts[t * n_local + rl] : plan.n_rows;
-        const Stream st = make_stream(seed, resample_lo + rl, (uint32_t)t, kPurposeIndex);
-        const uint32_t nblk = (uint32_t)((n + 3) / 4);
-        const uint32_t thresh = lemire_threshold((uint32_t)sz);
-        for (uint32_t q = lane; q < nblk; q += 32)
-          lemire_block<true>(st, q, (uint32_t)sz, thresh, n, put);
-        offset += n;
+    if (counts) {
+      for (int64_t u = lane; u < t; u += 32) offset += (int64_t)counts[u * n_local + rl];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) offset += __shfl_xor_sync(0xffffffffu, offset, o);
+    }
+    const int64_t sz = plan.cell_size(t);
+    const int64_t row0 = t < plan.n_full ? (t << plan.log2_tile) : (plan.n_full << plan.log2_tile);
+    auto put = [&](int, int64_t pos, uint32_t idx) { row[offset + pos] = row0 + (int64_t)idx; };
+    if (t < plan.n_full) {
+      for (int c = 0; c < kClasses; ++c) {
+        const int64_t n_c = cls[(t * n_local + rl) * kClasses + c];
+        const Stream st = make_stream(seed, resample_lo + rl, class_cell_id(t, c), kPurposeIndex);
+        const uint32_t nblk = (uint32_t)((n_c + kClassDrawsPerBlock - 1) / kClassDrawsPerBlock);
+        for (uint32_t q = lane; q < nblk; q += 32) class_block<true>(st, q, m7, c, n_c, put);
+        offset += n_c;
       }
+    } else {
+      const int64_t n = counts ? (int64_t)counts[t * n_local + rl] : plan.n_rows;
+      const Stream st = make_stream(seed, resample_lo + rl, (uint32_t)t, kPurposeIndex);
+      const uint32_t nblk = (uint32_t)((n + 3) / 4);
+      const uint32_t thresh = lemire_threshold((uint32_t)sz);
+      for (uint32_t q = lane; q < nblk; q += 32)
+        lemire_block<true>(st, q, (uint32_t)sz, thresh, n, put);
     }
   }
 }

@@ -107,11 +107,25 @@ __global__ void __launch_bounds__(kRowsThreads) k1mr_select_kernel(const RowsPar
 
   for (int i = tid; i < nc * 2 * kRowsMaxBins; i += kRowsThreads) rows_hist[i] = 0u;
   __syncthreads();
-  for (int64_t j = tid; j < P.n_rows; j += kRowsThreads) {
-    const int64_t i = idx[j];
-    if ((uint64_t)i >= (uint64_t)P.n_rows) continue;           // out-of-range entries are ignored
-    const int32_t* r = P.rank + i * P.n_cols + d0;
-    for (int c = 0; c < nc; ++c) atomicAdd(h1(c) + ((unsigned int)__ldg(r + c) >> P.shift), 1u);
+  // four index entries and their rank rows in flight per thread: the rank gathers are random L2
+  // reads and a CTA per SM cannot hide their latency one at a time (N = 1e6: 153 -> see DESIGN 5)
+  constexpr int kRowsBatch = 4;
+  for (int64_t j0 = tid; j0 < P.n_rows; j0 += (int64_t)kRowsThreads * kRowsBatch) {
+    unsigned int p[kRowsBatch][kRowsGroup];
+#pragma unroll
+    for (int b = 0; b < kRowsBatch; ++b) {
+      const int64_t j = j0 + (int64_t)b * kRowsThreads;
+      const int64_t i = j < P.n_rows ? idx[j] : -1;
+      const bool ok = (uint64_t)i < (uint64_t)P.n_rows;          // out-of-range entries are ignored
+      const int32_t* r = P.rank + (ok ? i : 0) * P.n_cols + d0;
+#pragma unroll
+      for (int c = 0; c < kRowsGroup; ++c) p[b][c] = (ok && c < nc) ? (unsigned int)__ldg(r + c) : 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int b = 0; b < kRowsBatch; ++b)
+#pragma unroll
+      for (int c = 0; c < kRowsGroup; ++c)
+        if (p[b][c] != 0xFFFFFFFFu) atomicAdd(h1(c) + (p[b][c] >> P.shift), 1u);
   }
   __syncthreads();
   if (warp < nc * 2) {
@@ -127,16 +141,26 @@ __global__ void __launch_bounds__(kRowsThreads) k1mr_select_kernel(const RowsPar
   __syncthreads();
   for (int i = tid; i < nc * 2 * kRowsMaxBins; i += kRowsThreads) rows_hist[i] = 0u;
   __syncthreads();
-  for (int64_t j = tid; j < P.n_rows; j += kRowsThreads) {
-    const int64_t i = idx[j];
-    if ((uint64_t)i >= (uint64_t)P.n_rows) continue;
-    const int32_t* r = P.rank + i * P.n_cols + d0;
-    for (int c = 0; c < nc; ++c) {
-      const unsigned int p = (unsigned int)__ldg(r + c);
-      const int hb = (int)(p >> P.shift);
-      if (hb == s_bin[c][0]) atomicAdd(h2(c, 0) + (p & lo_mask), 1u);
-      if (two && hb == s_bin[c][1]) atomicAdd(h2(c, 1) + (p & lo_mask), 1u);
+  for (int64_t j0 = tid; j0 < P.n_rows; j0 += (int64_t)kRowsThreads * kRowsBatch) {
+    unsigned int p[kRowsBatch][kRowsGroup];
+#pragma unroll
+    for (int b = 0; b < kRowsBatch; ++b) {
+      const int64_t j = j0 + (int64_t)b * kRowsThreads;
+      const int64_t i = j < P.n_rows ? idx[j] : -1;
+      const bool ok = (uint64_t)i < (uint64_t)P.n_rows;
+      const int32_t* r = P.rank + (ok ? i : 0) * P.n_cols + d0;
+#pragma unroll
+      for (int c = 0; c < kRowsGroup; ++c) p[b][c] = (ok && c < nc) ? (unsigned int)__ldg(r + c) : 0xFFFFFFFFu;
     }
+#pragma unroll
+    for (int b = 0; b < kRowsBatch; ++b)
+#pragma unroll
+      for (int c = 0; c < kRowsGroup; ++c) {
+        if (p[b][c] == 0xFFFFFFFFu) continue;
+        const int hb = (int)(p[b][c] >> P.shift);
+        if (hb == s_bin[c][0]) atomicAdd(h2(c, 0) + (p[b][c] & lo_mask), 1u);
+        if (two && hb == s_bin[c][1]) atomicAdd(h2(c, 1) + (p[b][c] & lo_mask), 1u);
+      }
   }
   __syncthreads();
   if (warp < nc * 2) {
