@@ -490,6 +490,13 @@ def main():
                      dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # bytes over all ranks: a sharded run copies 1/G of the pinned rows per rank and
+        # all-gathers them over NVLink (_device.to_device_f64_async)
+        io = torch.tensor([h2d, d2h], dtype=torch.int64, device="cuda")
+        dist.all_reduce(io, op=dist.ReduceOp.SUM)
+        h2d_all, d2h_all = (int(v) for v in io.tolist())
+    else:
+        h2d_all, d2h_all = int(h2d), int(d2h)
     dev_ms, e2e_ms, k1_mean_ms, k0_mean_ms = (float(v) for v in t.tolist())
 
     if rank == 0:
@@ -534,8 +541,10 @@ def main():
                                           "are staged in shared memory, DRAM traffic is `traffic` bytes per launch"},
                 "ncu": ncu,
             },
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms / args.steps},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
+                    "ms_per_step": e2e_ms / args.steps,
+                    "bytes": "summed over the ranks" + ("; each rank copies 1/G of the pinned rows, all-gathered over NVLink"
+                                                      if world > 1 else "")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "wall_s_timed_region": wall_s,

@@ -10,7 +10,7 @@ from typing import Optional, Sequence, Tuple
 
 import numpy as np
 
-from . import _abi
+from . import _abi, _dist
 
 
 def _torch():
@@ -52,6 +52,7 @@ def host_to_device(arr: np.ndarray, device):
 
 
 _copy_streams = {}
+SHARD_COPY_BYTES = 32 << 20      # sharded runs: pinned 1-D rows from this size on are copied 1/G per rank
 
 
 def to_device_f64_async(x, device=None):
@@ -66,8 +67,30 @@ def to_device_f64_async(x, device=None):
     side = _copy_streams.get(dev.index)
     if side is None:
         side = _copy_streams[dev.index] = torch.cuda.Stream(device=dev)
-    dst = torch.empty(x.shape, dtype=torch.float64, device=dev)
     side.wait_stream(torch.cuda.current_stream(dev))      # the block may have pending users there
+    rank, ranks = _dist.world()
+    if ranks > 1 and x.dim() == 1 and x.numel() * 8 >= SHARD_COPY_BYTES and _dist.backend() == "nccl":
+        # sharded run, replicated rows: every rank copies 1/G of them from its host copy and the
+        # ranks all-gather over NVLink (HGX boards pair GPUs on a PCIe switch uplink: eight ranks
+        # copying 80 MB each at once got ~25 GB/s apiece, 3.4 ms against K0's 2.1 ms at G = 8)
+        n = x.numel()
+        width = -(-n // ranks)
+        lo, hi = min(rank * width, n), min((rank + 1) * width, n)
+        whole = torch.empty(ranks * width, dtype=torch.float64, device=dev)
+        part = torch.empty(width, dtype=torch.float64, device=dev)
+        with torch.cuda.stream(side):
+            if hi > lo:
+                part[: hi - lo].copy_(x[lo:hi], non_blocking=True)
+            if hi - lo < width:
+                part[hi - lo:].zero_()
+            _dist.all_gather_equal(whole, part)
+        for t in (whole, part):
+            t.record_stream(side)
+        event = torch.cuda.Event()
+        event.record(side)
+        TRAFFIC["h2d"] += (hi - lo) * 8
+        return whole[:n], event
+    dst = torch.empty(x.shape, dtype=torch.float64, device=dev)
     with torch.cuda.stream(side):
         dst.copy_(x, non_blocking=True)
     dst.record_stream(side)

@@ -44,6 +44,20 @@ def world() -> Tuple[int, int]:
     return dist.get_rank(_group), dist.get_world_size(_group)
 
 
+def backend() -> str:
+    """Backend of the sharding group ('nccl', 'gloo'); '' when not sharded."""
+    if not _enabled:
+        return ""
+    import torch.distributed as dist
+    return dist.get_backend(_group)
+
+
+def all_gather_equal(out, part) -> None:
+    """out[r * len(part) : (r + 1) * len(part)] = rank r's `part`, on the current stream."""
+    import torch.distributed as dist
+    dist.all_gather_into_tensor(out, part, group=_group)
+
+
 def shard_range(n_samples: int, rank: int, world_size: int) -> Tuple[int, int]:
     """Contiguous resample-id range of `rank`: [rank*n/G, (rank+1)*n/G)."""
     return (rank * n_samples) // world_size, ((rank + 1) * n_samples) // world_size

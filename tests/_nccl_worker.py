@@ -26,6 +26,9 @@ def main():
     tall = rng.standard_normal((29001, 3))                  # beyond the resident rows: row-space medians (K1mr)
     long_rows = rng.gamma(2.0, 1.0, 600_000)                # numpy rows copied under the occupancy chains
     wide = rng.standard_normal((300, 80))                   # many short columns: prefix counts on the tensor cores (K1mg)
+    # pinned rows above _device.SHARD_COPY_BYTES: every rank copies 1/G of them, all-gather over NVLink
+    # (odd length: the last rank's part is padded)
+    pinned = torch.from_numpy(rng.standard_normal(4_500_001) + 2.0).pin_memory()
     holes = x[:3000].copy()
     holes[17] = np.nan                                      # numpy's NaN rule for rank statistics
     cases = [
@@ -51,6 +54,8 @@ def main():
         lambda: boot.ci(x[:1000], np.mean, n_samples=2000, seed=19),         # small-call shape (unsharded: one kernel)
         lambda: boot.ci(wide, boot.median_axis0, n_samples=403, seed=20),
         lambda: boot.pval(wide, boot.quantile_axis0(0.4), boot.less_than(-0.2), n_samples=403, seed=21),
+        lambda: boot.ci(pinned, np.mean, n_samples=302, seed=22),
+        lambda: boot.ci(pinned, np.median, n_samples=101, seed=23, method="pi"),
         lambda: boot.ci(x, np.mean, n_samples=64, seed=None),          # seed agreed through a broadcast
     ]
     boot.distributed.enable()
