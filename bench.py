@@ -491,7 +491,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         # bytes over all ranks: a sharded run copies 1/G of the pinned rows per rank and
-        # all-gathers them over NVLink (_device.to_device_f64_async)
+        # all-gathers them over NVLink (_device.shard_copy_async)
         io = torch.tensor([h2d, d2h], dtype=torch.int64, device="cuda")
         dist.all_reduce(io, op=dist.ReduceOp.SUM)
         h2d_all, d2h_all = (int(v) for v in io.tolist())

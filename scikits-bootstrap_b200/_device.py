@@ -55,41 +55,77 @@ _copy_streams = {}
 SHARD_COPY_BYTES = 32 << 20      # sharded runs: pinned 1-D rows from this size on are copied 1/G per rank
 
 
-def to_device_f64_async(x, device=None):
-    """Like to_device_f64, but a pinned host tensor is copied on a side stream: returns
-    (tensor, event) where `event` (or None) is recorded after the copy.  Work that does
-    not read the data can be enqueued before the consumer waits for the event."""
-    torch = require_cuda()
-    if not (isinstance(x, torch.Tensor) and x.device.type == "cpu" and x.is_pinned()
-            and x.dtype == torch.float64 and x.is_contiguous()):
-        return to_device_f64(x, device), None
-    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+def _copy_stream(dev):
+    torch = _torch()
     side = _copy_streams.get(dev.index)
     if side is None:
         side = _copy_streams[dev.index] = torch.cuda.Stream(device=dev)
     side.wait_stream(torch.cuda.current_stream(dev))      # the block may have pending users there
+    return side
+
+
+def shard_copy_async(x, device=None):
+    """Sharded run (NCCL), replicated host rows: a contiguous 1-D float64 numpy array or CPU
+    tensor of SHARD_COPY_BYTES or more is copied 1/G per rank on the copy stream and the ranks
+    all-gather over NVLink.  HGX boards pair GPUs on a PCIe switch uplink: eight ranks copying
+    80 MB each at once got ~25 GB/s apiece, 3.4 ms against K0's 2.1 ms at G = 8 (and a pageable
+    source is staged by the host at ~10 GB/s: 1 ms for a tenth instead of 8 ms for the whole).
+    Returns (tensor, event recorded after the gather), or None when the input is something else."""
+    torch = require_cuda()
     rank, ranks = _dist.world()
-    if ranks > 1 and x.dim() == 1 and x.numel() * 8 >= SHARD_COPY_BYTES and _dist.backend() == "nccl":
-        # sharded run, replicated rows: every rank copies 1/G of them from its host copy and the
-        # ranks all-gather over NVLink (HGX boards pair GPUs on a PCIe switch uplink: eight ranks
-        # copying 80 MB each at once got ~25 GB/s apiece, 3.4 ms against K0's 2.1 ms at G = 8)
+    if ranks < 2 or _dist.backend() != "nccl":
+        return None
+    if type(x) is np.ndarray:
+        if not (x.ndim == 1 and x.dtype == np.float64 and x.flags.c_contiguous):
+            return None
+        n = x.shape[0]
+    elif isinstance(x, torch.Tensor) and x.device.type == "cpu":
+        if not (x.dim() == 1 and x.dtype == torch.float64 and x.is_contiguous()):
+            return None
         n = x.numel()
-        width = -(-n // ranks)
-        lo, hi = min(rank * width, n), min((rank + 1) * width, n)
-        whole = torch.empty(ranks * width, dtype=torch.float64, device=dev)
-        part = torch.empty(width, dtype=torch.float64, device=dev)
-        with torch.cuda.stream(side):
-            if hi > lo:
-                part[: hi - lo].copy_(x[lo:hi], non_blocking=True)
-            if hi - lo < width:
-                part[hi - lo:].zero_()
-            _dist.all_gather_equal(whole, part)
-        for t in (whole, part):
-            t.record_stream(side)
-        event = torch.cuda.Event()
-        event.record(side)
-        TRAFFIC["h2d"] += (hi - lo) * 8
-        return whole[:n], event
+    else:
+        return None
+    if n * 8 < SHARD_COPY_BYTES:
+        return None
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    side = _copy_stream(dev)
+    width = -(-n // ranks)
+    lo, hi = min(rank * width, n), min((rank + 1) * width, n)
+    src = x[lo:hi]
+    if type(src) is np.ndarray:
+        if not src.flags.writeable:      # torch.from_numpy wants a writable buffer (it is only read)
+            src = src.copy()
+        src = torch.from_numpy(src)
+    whole = torch.empty(ranks * width, dtype=torch.float64, device=dev)
+    part = torch.empty(width, dtype=torch.float64, device=dev)
+    with torch.cuda.stream(side):
+        if hi > lo:
+            part[: hi - lo].copy_(src, non_blocking=True)
+        if hi - lo < width:
+            part[hi - lo:].zero_()
+        _dist.all_gather_equal(whole, part)
+    for t in (whole, part):
+        t.record_stream(side)
+    event = torch.cuda.Event()
+    event.record(side)
+    TRAFFIC["h2d"] += (hi - lo) * 8
+    return whole[:n], event
+
+
+def to_device_f64_async(x, device=None):
+    """Like to_device_f64, but a pinned host tensor is copied on a side stream: returns
+    (tensor, event) where `event` (or None) is recorded after the copy.  Work that does
+    not read the data can be enqueued before the consumer waits for the event.  Long host
+    rows of a sharded run take the split copy (shard_copy_async)."""
+    torch = require_cuda()
+    split = shard_copy_async(x, device)
+    if split is not None:
+        return split
+    if not (isinstance(x, torch.Tensor) and x.device.type == "cpu" and x.is_pinned()
+            and x.dtype == torch.float64 and x.is_contiguous()):
+        return to_device_f64(x, device), None
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    side = _copy_stream(dev)
     dst = torch.empty(x.shape, dtype=torch.float64, device=dev)
     with torch.cuda.stream(side):
         dst.copy_(x, non_blocking=True)

@@ -146,7 +146,9 @@ class _Run:
         self.rank, self.world = _dist.world()
         self.lo, self.hi = _dist.shard_range(self.n_samples, self.rank, self.world)
         self._host_rows = None
-        if self._defer_copy(arrays):
+        if self.world > 1 and arrays[0].nbytes >= _device.SHARD_COPY_BYTES and self._split_copy(arrays):
+            pass                     # long host rows of a sharded run: 1/G per rank + all-gather over NVLink
+        elif self._defer_copy(arrays):
             # long numpy rows of a plain K1 job: the copy (8 ms of host staging per 80 MB of pageable
             # memory) is issued by the resampling call itself, behind its occupancy chains
             torch = _device.require_cuda()
@@ -174,6 +176,19 @@ class _Run:
         self._spec = None
         # rank statistics: which order statistics (None: np.median's)
         self.rule = _device.rank_rule(self.dev[0].shape[0], spec.q) if spec.stat_id == _abi.STAT_MEDIAN else None
+
+    def _split_copy(self, arrays) -> bool:
+        """Every array a long contiguous 1-D float64 host array of a run sharded over NCCL:
+        copied in parts and all-gathered (_device.shard_copy_async); `_ready` covers the gather."""
+        if not all(type(a) is np.ndarray and a.ndim == 1 and a.dtype == np.float64 and a.flags.c_contiguous
+                   and a.nbytes >= _device.SHARD_COPY_BYTES for a in arrays):
+            return False
+        pairs = [_device.shard_copy_async(a) for a in arrays]
+        if any(p is None for p in pairs):          # (not an NCCL group: all of them are None)
+            return False
+        self.dev = [t for t, _ in pairs]
+        self._ready = pairs[-1][1]                 # one copy stream: the last event covers all
+        return True
 
     def _defer_copy(self, arrays) -> bool:
         """Host rows that can travel under K0: contiguous 1-D float64 numpy arrays of at least

@@ -56,6 +56,8 @@ def main():
         lambda: boot.pval(wide, boot.quantile_axis0(0.4), boot.less_than(-0.2), n_samples=403, seed=21),
         lambda: boot.ci(pinned, np.mean, n_samples=302, seed=22),
         lambda: boot.ci(pinned, np.median, n_samples=101, seed=23, method="pi"),
+        lambda: boot.ci(pinned.numpy(), np.std, n_samples=203, seed=24),                  # numpy rows, same split copy
+        lambda: boot.ci((pinned.numpy(), pinned.numpy()[::-1].copy()), boot.ratio_of_means, n_samples=99, seed=25),
         lambda: boot.ci(x, np.mean, n_samples=64, seed=None),          # seed agreed through a broadcast
     ]
     boot.distributed.enable()
