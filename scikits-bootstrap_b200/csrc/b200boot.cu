@@ -1441,6 +1441,7 @@ int b200boot_median_rows_indexed(const double* sorted_vals, const int32_t* rank,
   while (((int64_t)1 << bits) < n_rows) ++bits;
   P.shift = (bits + 1) / 2;
   P.hi_bins = (int32_t)((n_rows + ((int64_t)1 << P.shift) - 1) >> P.shift);
+  P.bins = (std::max<int32_t>(P.hi_bins, (int32_t)1 << P.shift) + 31) & ~31;
   P.rank = rank;
   P.sorted = sorted_vals;
   P.indices = indices;
@@ -1463,7 +1464,7 @@ int b200boot_median_rows_indexed(const double* sorted_vals, const int32_t* rank,
     Q.sorted = P.sorted + g0 * kRowsGroup * n_rows;
     Q.out = P.out + g0 * kRowsGroup * out_ld;
     Q.n_cols = n_cols;                  // row stride of the rank table
-    k1mr_select_kernel<<<dim3((unsigned)n_sets, (unsigned)ng), kRowsThreads, rows_smem_bytes(), s>>>(Q, n_cols - g0 * kRowsGroup);
+    k1mr_select_kernel<<<dim3((unsigned)n_sets, (unsigned)ng), kRowsThreads, rows_smem_bytes(P.bins), s>>>(Q, n_cols - g0 * kRowsGroup);
     B2_LAUNCH_CHECK();
   }
   return 0;

@@ -48,6 +48,7 @@ struct RowsParams {
   int64_t n_rows, n_cols, n_sets;   // n_cols: row stride of the rank table
   int32_t shift;             // low bits per rank: bins of level 2 = 1 << shift
   int32_t hi_bins;           // bins of level 1 = ceil(N / 2^shift)
+  int32_t bins;              // histogram stride in shared memory: max(hi_bins, 2^shift) rounded up to 32
   RankRule rule;
   double* out;               // [D][out_ld]
   int64_t out_ld;
@@ -88,9 +89,27 @@ __device__ __forceinline__ int rows_find_bin(const unsigned int* hist, int n_bin
   return bin;
 }
 
+// the group's ranks of one drawn row.  The rows are random: every lane of a load touches its own
+// sector, so a load costs the L1 32 tag cycles whatever its width — four 32-bit loads per row made
+// the kernel L1-tag-bound (6e10 rows/s at N = 1e6: 4 cycles per row and SM).  When the row stride
+// is a multiple of four columns the group's 16 bytes come with one 128-bit load.
+__device__ __forceinline__ void rows_load_ranks(const int32_t* r, bool ok, int nc, bool vec, unsigned int* p) {
+  static_assert(kRowsGroup == 4, "one uint4 per row group");
+  if (vec) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(r));
+    p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
+#pragma unroll
+    for (int c = 0; c < kRowsGroup; ++c)
+      if (!ok || c >= nc) p[c] = 0xFFFFFFFFu;
+  } else {
+#pragma unroll
+    for (int c = 0; c < kRowsGroup; ++c) p[c] = (ok && c < nc) ? (unsigned int)__ldg(r + c) : 0xFFFFFFFFu;
+  }
+}
+
 __global__ void __launch_bounds__(kRowsThreads) k1mr_select_kernel(const RowsParams P, const int64_t cols_left) {
   // level 1: one histogram per column; level 2: one per (column, target rank)
-  extern __shared__ unsigned int rows_hist[];            // [kRowsGroup][2][kRowsMaxBins]
+  extern __shared__ unsigned int rows_hist[];            // [kRowsGroup][2][P.bins]
   __shared__ int s_bin[kRowsGroup][2];
   __shared__ long long s_krem[kRowsGroup][2];
   __shared__ int s_pos[kRowsGroup][2];
@@ -102,13 +121,15 @@ __global__ void __launch_bounds__(kRowsThreads) k1mr_select_kernel(const RowsPar
   const int lo_bins = 1 << P.shift;
   const unsigned int lo_mask = (unsigned int)lo_bins - 1u;
   const int two = P.rule.k_hi != P.rule.k_lo ? 1 : 0;
-  auto h1 = [&](int c) { return rows_hist + (size_t)c * 2 * kRowsMaxBins; };
-  auto h2 = [&](int c, int t) { return rows_hist + ((size_t)c * 2 + t) * kRowsMaxBins; };
+  const bool vec = (P.n_cols & 3) == 0 && (reinterpret_cast<uintptr_t>(P.rank + d0) & 15) == 0;
+  const int bins = P.bins;
+  auto h1 = [&](int c) { return rows_hist + (size_t)c * 2 * bins; };
+  auto h2 = [&](int c, int t) { return rows_hist + ((size_t)c * 2 + t) * bins; };
 
-  for (int i = tid; i < nc * 2 * kRowsMaxBins; i += kRowsThreads) rows_hist[i] = 0u;
+  for (int i = tid; i < nc * 2 * bins; i += kRowsThreads) rows_hist[i] = 0u;
   __syncthreads();
   // four index entries and their rank rows in flight per thread: the rank gathers are random L2
-  // reads and a CTA per SM cannot hide their latency one at a time (N = 1e6: 153 -> see DESIGN 5)
+  // reads and their latency is hidden by loads in flight only (N = 1e6: 153 -> see DESIGN 5)
   constexpr int kRowsBatch = 4;
   for (int64_t j0 = tid; j0 < P.n_rows; j0 += (int64_t)kRowsThreads * kRowsBatch) {
     unsigned int p[kRowsBatch][kRowsGroup];
@@ -118,8 +139,7 @@ __global__ void __launch_bounds__(kRowsThreads) k1mr_select_kernel(const RowsPar
       const int64_t i = j < P.n_rows ? idx[j] : -1;
       const bool ok = (uint64_t)i < (uint64_t)P.n_rows;          // out-of-range entries are ignored
       const int32_t* r = P.rank + (ok ? i : 0) * P.n_cols + d0;
-#pragma unroll
-      for (int c = 0; c < kRowsGroup; ++c) p[b][c] = (ok && c < nc) ? (unsigned int)__ldg(r + c) : 0xFFFFFFFFu;
+      rows_load_ranks(r, ok, nc, vec, p[b]);
     }
 #pragma unroll
     for (int b = 0; b < kRowsBatch; ++b)
@@ -139,7 +159,7 @@ __global__ void __launch_bounds__(kRowsThreads) k1mr_select_kernel(const RowsPar
     }
   }
   __syncthreads();
-  for (int i = tid; i < nc * 2 * kRowsMaxBins; i += kRowsThreads) rows_hist[i] = 0u;
+  for (int i = tid; i < nc * 2 * bins; i += kRowsThreads) rows_hist[i] = 0u;
   __syncthreads();
   for (int64_t j0 = tid; j0 < P.n_rows; j0 += (int64_t)kRowsThreads * kRowsBatch) {
     unsigned int p[kRowsBatch][kRowsGroup];
@@ -149,8 +169,7 @@ __global__ void __launch_bounds__(kRowsThreads) k1mr_select_kernel(const RowsPar
       const int64_t i = j < P.n_rows ? idx[j] : -1;
       const bool ok = (uint64_t)i < (uint64_t)P.n_rows;
       const int32_t* r = P.rank + (ok ? i : 0) * P.n_cols + d0;
-#pragma unroll
-      for (int c = 0; c < kRowsGroup; ++c) p[b][c] = (ok && c < nc) ? (unsigned int)__ldg(r + c) : 0xFFFFFFFFu;
+      rows_load_ranks(r, ok, nc, vec, p[b]);
     }
 #pragma unroll
     for (int b = 0; b < kRowsBatch; ++b)
@@ -361,6 +380,9 @@ __global__ void __launch_bounds__(256) nan_poison_rows_kernel(double* __restrict
   if (flags[e / width]) table[e] = nan("");
 }
 
-inline size_t rows_smem_bytes() { return (size_t)kRowsGroup * 2 * kRowsMaxBins * sizeof(unsigned int); }
+// shared memory of one CTA: the histograms are as long as the job's rank bits need (N = 1e6: 32 KB,
+// four CTAs of 512 threads per SM; the 128 KB of N = 2^24 allow one:
+// 25 % occupancy against random L2 gathers)
+inline size_t rows_smem_bytes(int bins = kRowsMaxBins) { return (size_t)kRowsGroup * 2 * bins * sizeof(unsigned int); }
 
 }  // namespace b200boot
