@@ -21,7 +21,7 @@
 
 namespace b200boot {
 
-constexpr int kRowsThreads = 512;
+constexpr int kRowsThreads = 1024;
 constexpr int kRowsGroup = 4;                   // columns per CTA
 constexpr int kRowsMaxBins = 4096;              // per level: N <= 2^24 rows
 constexpr int64_t kRowsMaxRows = (int64_t)1 << 24;
