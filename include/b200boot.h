@@ -215,6 +215,14 @@ int b200boot_resample_median_sorted(const double* sorted_vals, int64_t n_rows, u
 size_t b200boot_rank_columns_ws_bytes(int64_t n_rows, int64_t n_cols);
 int b200boot_rank_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, double* sorted_out,
                           int32_t* rank_out, void* ws, size_t ws_bytes, void* stream);
+/* The same pair with an explicit row stride of the rank table, rank_out int32[N][rank_ld],
+ * rank_ld >= n_cols (entries beyond n_cols are never interpreted): with rank_ld a multiple of
+ * four the select reads a row's group of four ranks with one 128-bit load. */
+int b200boot_rank_columns_ld(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, double* sorted_out,
+                             int32_t* rank_out, int64_t rank_ld, void* ws, size_t ws_bytes, void* stream);
+int b200boot_median_rows_indexed_ld(const double* sorted_vals, const int32_t* rank, int64_t rank_ld, int64_t n_rows,
+                                    int64_t n_cols, const int64_t* indices, int64_t n_sets, double* stat_out,
+                                    int64_t out_ld, void* stream, const b200boot_rank_rule* rule);
 int b200boot_median_rows_supported(int64_t n_rows);
 int b200boot_median_rows_indexed(const double* sorted_vals, const int32_t* rank, int64_t n_rows, int64_t n_cols,
                                  const int64_t* indices, int64_t n_sets, double* stat_out, int64_t out_ld,

@@ -69,6 +69,8 @@ SIGNATURES = {
     "b200boot_ci_small": (_int, [_vp, _int, _i64, _int, _u64, _i64, _vp, _int, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200boot_rank_columns_ws_bytes": (_sz, [_i64, _i64]),
     "b200boot_rank_columns": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "b200boot_rank_columns_ld": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "b200boot_median_rows_indexed_ld": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _vp]),
     "b200boot_median_rows_supported": (_int, [_i64]),
     "b200boot_median_rows_indexed": (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _vp]),
     "b200boot_ci_tail_supported": (_int, [_i64, _int]),

@@ -729,16 +729,18 @@ MEDIAN_ROWS_MAX = 1 << 24        # csrc/k1mr_rows.cuh: kRowsMaxRows
 
 
 def rank_columns(data2d):
-    """K1mr preparation: (sorted float64[D][N], rank int32[N][D]) of an (N, D) CUDA tensor."""
+    """K1mr preparation: (sorted float64[D][N], rank int32[N][D4]) of an (N, D) CUDA tensor; the
+    rank rows are padded to a multiple of four columns (D4) so that the select reads a row's group
+    of four ranks with one 128-bit load (the pad entries are never interpreted)."""
     torch = _torch()
     n_rows, n_cols = data2d.shape
     sorted_vals = torch.empty((n_cols, n_rows), dtype=torch.float64, device=data2d.device)
-    rank = torch.empty((n_rows, n_cols), dtype=torch.int32, device=data2d.device)
+    rank = torch.empty((n_rows, (n_cols + 3) // 4 * 4), dtype=torch.int32, device=data2d.device)
     L = _abi.lib()
     need = L.b200boot_rank_columns_ws_bytes(n_rows, n_cols)
     ws, wsz = _ws.get(need)
-    _abi.check(L.b200boot_rank_columns(data2d.data_ptr(), n_rows, n_cols, data2d.stride(0), sorted_vals.data_ptr(),
-                                       rank.data_ptr(), ws, wsz, stream_ptr()))
+    _abi.check(L.b200boot_rank_columns_ld(data2d.data_ptr(), n_rows, n_cols, data2d.stride(0), sorted_vals.data_ptr(),
+                                          rank.data_ptr(), rank.stride(0), ws, wsz, stream_ptr()))
     return sorted_vals, rank
 
 
@@ -747,10 +749,10 @@ def median_rows_indexed(sorted_vals, rank, indices, out, col_offset: int, rule=N
     out[:, col_offset : col_offset + n_sets] (out float64[D][n_total])."""
     n_cols, n_rows = sorted_vals.shape
     n_sets = indices.shape[0]
-    _abi.check(_abi.lib().b200boot_median_rows_indexed(sorted_vals.data_ptr(), rank.data_ptr(), n_rows, n_cols,
-                                                       indices.data_ptr(), n_sets,
-                                                       out.data_ptr() + 8 * col_offset, out.stride(0),
-                                                       stream_ptr(), _rule_ptr(rule)))
+    _abi.check(_abi.lib().b200boot_median_rows_indexed_ld(sorted_vals.data_ptr(), rank.data_ptr(), rank.stride(0),
+                                                          n_rows, n_cols, indices.data_ptr(), n_sets,
+                                                          out.data_ptr() + 8 * col_offset, out.stride(0),
+                                                          stream_ptr(), _rule_ptr(rule)))
     return out
 
 

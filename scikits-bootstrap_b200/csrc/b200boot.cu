@@ -1361,7 +1361,13 @@ size_t b200boot_rank_columns_ws_bytes(int64_t n_rows, int64_t n_cols) {
 
 int b200boot_rank_columns(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, double* sorted_out,
                           int32_t* rank_out, void* ws, size_t ws_bytes, void* stream) {
-  if (!data || !sorted_out || !rank_out || n_rows < 1 || n_cols < 1 || ld < n_cols || n_rows >= ((int64_t)1 << 31))
+  return b200boot_rank_columns_ld(data, n_rows, n_cols, ld, sorted_out, rank_out, n_cols, ws, ws_bytes, stream);
+}
+
+int b200boot_rank_columns_ld(const double* data, int64_t n_rows, int64_t n_cols, int64_t ld, double* sorted_out,
+                             int32_t* rank_out, int64_t rank_ld, void* ws, size_t ws_bytes, void* stream) {
+  if (!data || !sorted_out || !rank_out || n_rows < 1 || n_cols < 1 || ld < n_cols || rank_ld < n_cols ||
+      n_rows >= ((int64_t)1 << 31))
     return fail(B200BOOT_EINVAL, "rank_columns: bad arguments");
   if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0)
     return fail(B200BOOT_EWORKSPACE, "workspace must be 256-byte aligned");
@@ -1383,7 +1389,7 @@ int b200boot_rank_columns(const double* data, int64_t n_rows, int64_t n_cols, in
     B2_LAUNCH_CHECK();
     int rc = psort_pairs(keys, idx, n_pad, (unsigned)nd, s);
     if (rc) return rc;
-    rows_rank_kernel<<<blocks_for(n_rows * nd, 256, 148 * 32), 256, 0, s>>>(keys, idx, n_rows, n_pad, n_cols, d0, nd,
+    rows_rank_kernel<<<blocks_for(n_rows * nd, 256, 148 * 32), 256, 0, s>>>(keys, idx, n_rows, n_pad, rank_ld, d0, nd,
                                                                             rank_out, sorted_out);
     B2_LAUNCH_CHECK();
   }
@@ -1428,7 +1434,14 @@ int b200boot_median_rows_supported(int64_t n_rows) { return n_rows >= 1 && n_row
 int b200boot_median_rows_indexed(const double* sorted_vals, const int32_t* rank, int64_t n_rows, int64_t n_cols,
                                  const int64_t* indices, int64_t n_sets, double* stat_out, int64_t out_ld,
                                  void* stream, const b200boot_rank_rule* rule) {
-  if (!sorted_vals || !rank || !indices || !stat_out || n_cols < 1 || n_sets < 0 || out_ld < n_sets)
+  return b200boot_median_rows_indexed_ld(sorted_vals, rank, n_cols, n_rows, n_cols, indices, n_sets, stat_out, out_ld,
+                                         stream, rule);
+}
+
+int b200boot_median_rows_indexed_ld(const double* sorted_vals, const int32_t* rank, int64_t rank_ld, int64_t n_rows,
+                                    int64_t n_cols, const int64_t* indices, int64_t n_sets, double* stat_out,
+                                    int64_t out_ld, void* stream, const b200boot_rank_rule* rule) {
+  if (!sorted_vals || !rank || !indices || !stat_out || n_cols < 1 || rank_ld < n_cols || n_sets < 0 || out_ld < n_sets)
     return fail(B200BOOT_EINVAL, "median_rows_indexed: bad arguments");
   if (!b200boot_median_rows_supported(n_rows))
     return fail(B200BOOT_EUNSUPPORTED, "median_rows_indexed: 1 <= n_rows <= 2^24");
@@ -1463,7 +1476,7 @@ int b200boot_median_rows_indexed(const double* sorted_vals, const int32_t* rank,
     Q.rank = P.rank + g0 * kRowsGroup;
     Q.sorted = P.sorted + g0 * kRowsGroup * n_rows;
     Q.out = P.out + g0 * kRowsGroup * out_ld;
-    Q.n_cols = n_cols;                  // row stride of the rank table
+    Q.n_cols = rank_ld;                 // row stride of the rank table
     k1mr_select_kernel<<<dim3((unsigned)n_sets, (unsigned)ng), kRowsThreads, rows_smem_bytes(P.bins), s>>>(Q, n_cols - g0 * kRowsGroup);
     B2_LAUNCH_CHECK();
   }
