@@ -615,11 +615,13 @@ __global__ void __launch_bounds__(256) k1_indexed_kernel(const double* __restric
 // ------------------------------------------------------------------ K2 --------
 // Writes the canonical index array of each resample: cells in order, inside a
 // cell the draws in stream-position order — exactly what K1 consumes.
+constexpr int kK2StagePitch = kClassDrawsPerBlock + 1;   // odd pitch: the lanes' rows start in distinct banks
 __global__ void __launch_bounds__(256) k2_fill_indices_kernel(Plan plan, uint64_t seed,
                                                               int64_t resample_lo, int64_t n_local,
                                                               const int32_t* __restrict__ counts,
                                                               const int32_t* __restrict__ cls,
                                                               int64_t* __restrict__ out) {
+  __shared__ uint32_t s_stage[256 / 32][32 * kK2StagePitch];
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -641,11 +643,29 @@ __global__ void __launch_bounds__(256) k2_fill_indices_kernel(Plan plan, uint64_
     const int64_t row0 = t < plan.n_full ? (t << plan.log2_tile) : (plan.n_full << plan.log2_tile);
     auto put = [&](int, int64_t pos, uint32_t idx) { row[offset + pos] = row0 + (int64_t)idx; };
     if (t < plan.n_full) {
+      // A lane draws a whole block: twelve consecutive positions.  Stored from the lanes' own
+      // registers that is a 96-byte stride between lanes (every store instruction touches 32
+      // sectors for 8 bytes each: 0.5 TB/s of index writes); the warp's 384 draws of a round go
+      // through a shared-memory transpose instead and leave as twelve 256-byte rows.
+      uint32_t* stage = s_stage[threadIdx.x >> 5];
       for (int c = 0; c < kClasses; ++c) {
         const int64_t n_c = cls[(t * n_local + rl) * kClasses + c];
         const Stream st = make_stream(seed, resample_lo + rl, class_cell_id(t, c), kPurposeIndex);
         const uint32_t nblk = (uint32_t)((n_c + kClassDrawsPerBlock - 1) / kClassDrawsPerBlock);
-        for (uint32_t q = lane; q < nblk; q += 32) class_block<true>(st, q, m7, c, n_c, put);
+        for (uint32_t q0 = 0; q0 < nblk; q0 += 32) {
+          if (q0 + lane < nblk)
+            class_block<false>(st, q0 + lane, m7, c, n_c,
+                               [&](int j, int64_t, uint32_t idx) { stage[lane * kK2StagePitch + j] = idx; });
+          __syncwarp();
+          const int64_t base = (int64_t)q0 * kClassDrawsPerBlock;
+#pragma unroll
+          for (int k = 0; k < kClassDrawsPerBlock; ++k) {
+            const int p = k * 32 + lane;
+            if (base + p < n_c)
+              row[offset + base + p] = row0 + (int64_t)stage[(p / kClassDrawsPerBlock) * kK2StagePitch + p % kClassDrawsPerBlock];
+          }
+          __syncwarp();
+        }
         offset += n_c;
       }
     } else {
