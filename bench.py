@@ -543,8 +543,10 @@ def main():
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
                     "ms_per_step": e2e_ms / args.steps,
-                    "bytes": "summed over the ranks" + ("; each rank copies 1/G of the pinned rows, all-gathered over NVLink"
-                                                      if world > 1 else "")},
+                    "bytes": "summed over the ranks" + (
+                        "" if world == 1 else
+                        "; each rank copies 1/G of the pinned rows, all-gathered over NVLink" if h2d_all < 2 * 8 * N_ROWS
+                        else "; each rank copies its own replica of the pinned rows")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "wall_s_timed_region": wall_s,

@@ -52,7 +52,9 @@ def host_to_device(arr: np.ndarray, device):
 
 
 _copy_streams = {}
-SHARD_COPY_BYTES = 32 << 20      # sharded runs: pinned 1-D rows from this size on are copied 1/G per rank
+SHARD_COPY_BYTES = 32 << 20      # sharded runs: host rows from this size on are copied 1/G per rank ...
+SHARD_COPY_MIN_RANKS = 8         # ... from this many ranks on (measured: the split costs ~0.4 ms of host
+                                 # time before K0 is enqueued; 80 MB whole per rank hides under K0 up to 4 ranks)
 
 
 def _copy_stream(dev):
@@ -73,7 +75,7 @@ def shard_copy_async(x, device=None):
     Returns (tensor, event recorded after the gather), or None when the input is something else."""
     torch = require_cuda()
     rank, ranks = _dist.world()
-    if ranks < 2 or _dist.backend() != "nccl":
+    if ranks < max(2, SHARD_COPY_MIN_RANKS) or _dist.backend() != "nccl":
         return None
     if type(x) is np.ndarray:
         if not (x.ndim == 1 and x.dtype == np.float64 and x.flags.c_contiguous):

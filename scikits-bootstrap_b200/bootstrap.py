@@ -146,7 +146,8 @@ class _Run:
         self.rank, self.world = _dist.world()
         self.lo, self.hi = _dist.shard_range(self.n_samples, self.rank, self.world)
         self._host_rows = None
-        if self.world > 1 and arrays[0].nbytes >= _device.SHARD_COPY_BYTES and self._split_copy(arrays):
+        if (self.world >= max(2, _device.SHARD_COPY_MIN_RANKS) and arrays[0].nbytes >= _device.SHARD_COPY_BYTES
+                and self._split_copy(arrays)):
             pass                     # long host rows of a sharded run: 1/G per rank + all-gather over NVLink
         elif self._defer_copy(arrays):
             # long numpy rows of a plain K1 job: the copy (8 ms of host staging per 80 MB of pageable

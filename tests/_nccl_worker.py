@@ -60,6 +60,7 @@ def main():
         lambda: boot.ci((pinned.numpy(), pinned.numpy()[::-1].copy()), boot.ratio_of_means, n_samples=99, seed=25),
         lambda: boot.ci(x, np.mean, n_samples=64, seed=None),          # seed agreed through a broadcast
     ]
+    boot._device.SHARD_COPY_MIN_RANKS = 2         # (8 by default: exercise the split copy on any box)
     boot.distributed.enable()
     sharded = [np.asarray(c()) for c in cases[:-1]]
     # small statistic vectors are gathered and finished locally; with the limit at zero the same
