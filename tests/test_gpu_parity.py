@@ -345,7 +345,8 @@ def test_long_quantile_runs_in_rank_space(n):
         assert_array_equal(got, ref)
 
 
-@pytest.mark.parametrize("n,d,q", [(30001, 3, None), (28673, 5, None), (40000, 2, 0.9), (65536, 9, 0.25)])
+@pytest.mark.parametrize("n,d,q", [(30001, 3, None), (28673, 5, None), (40000, 2, 0.9), (65536, 9, 0.25),
+                                   (29001, 4, None), (33000, 8, 0.4)])      # whole groups of four columns: 128-bit rank loads only
 def test_long_median_over_columns_is_row_aligned(n, d, q):
     """(N, D) data with more rows than K1m's resident limit stay in row space (K1mr): every
     resample gathers whole rows, x[indices] (bootstrap.py:431), so the returned distribution
