@@ -59,8 +59,8 @@ _MASK64 = (1 << 64) - 1
 _GATHER_LIMIT_BYTES = 32 << 20
 # key offset between the arrays of multi='independent' (odd 64-bit constant)
 _ARRAY_KEY_STRIDE = 0x9E3779B97F4A7C15
-# K1mr: materialised index sets per batch
-_ROWS_INDEX_BYTES = 1 << 30
+# K1mr: materialised index sets per batch (2 GB: at N = 1e6 that is 268 sets = two select CTAs per SM)
+_ROWS_INDEX_BYTES = 2 << 30
 # numpy rows from this size on are copied by the resampling call, under its occupancy chains
 _DEFER_COPY_BYTES = 4 << 20
 
